@@ -1,0 +1,266 @@
+// CUDA-core fp32 implicit-GEMM convolutions with a fixed reduction order ("exact-order" mode,
+// DRS_PREC_FP32) and the layers that do not belong on the tensor cores: conv1 (Ci = 3..5, K = 75..125,
+// HBM-bound) in every precision.  Reference op: _conv_layer, isprs:700-723.
+#pragma once
+#include "drs_common.cuh"
+
+constexpr int SIMT_BM = 64, SIMT_BN = 64, SIMT_BK = 16, SIMT_THREADS = 256;
+
+// out[m, co] = act( (sum_{tap,c} in[pix(m)+tap][c] * w[(tap*ci+c)*co_total + co]) * scale[co] + shift[co] )
+// w is HWIO flattened ([k*k*ci][co_total]) -- exactly the TF variable layout, no packing needed.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(SIMT_THREADS)
+conv_simt_kernel(const TIn* __restrict__ in, int in_cstride, int in_coff, int ci, const float* __restrict__ w,
+                 TOut* __restrict__ out, int out_cstride, int out_coff, int co, int M, int crop, int ksize, int rate,
+                 int pad_b, const float* __restrict__ scale, const float* __restrict__ shift, int act) {
+  __shared__ float As[SIMT_BK][SIMT_BM + 4];
+  __shared__ float Bs[SIMT_BK][SIMT_BN + 4];
+  const int t = threadIdx.x;
+  const int m0 = blockIdx.x * SIMT_BM;
+  const int n0 = blockIdx.y * SIMT_BN;
+  const int Ktot = ksize * ksize * ci;
+  const int cc = crop * crop;
+
+  // A-load slots: kk_local = t % 16, pixels (t / 16) + 16 * i
+  const int a_kk = t & 15;
+  int a_n[4], a_y[4], a_x[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + (t >> 4) + 16 * i;
+    if (m < M) {
+      a_n[i] = m / cc;
+      int r = m - a_n[i] * cc;
+      a_y[i] = r / crop;
+      a_x[i] = r - a_y[i] * crop;
+    } else {
+      a_n[i] = -1;
+      a_y[i] = a_x[i] = 0;
+    }
+  }
+  const int b_co = t & 63;
+  const int b_kk = t >> 6;
+
+  const int tx = t & 15, ty = t >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  for (int k0 = 0; k0 < Ktot; k0 += SIMT_BK) {
+    {
+      const int kk = k0 + a_kk;
+      int tap = 0, c = 0, dy = 0, dx = 0;
+      const bool kvalid = kk < Ktot;
+      if (kvalid) {
+        tap = kk / ci;
+        c = kk - tap * ci;
+        const int ky = tap / ksize, kx = tap - ky * ksize;
+        dy = ky * rate - pad_b;
+        dx = kx * rate - pad_b;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v = 0.0f;
+        if (kvalid && a_n[i] >= 0) {
+          const int iy = a_y[i] + dy, ix = a_x[i] + dx;
+          if (iy >= 0 && iy < crop && ix >= 0 && ix < crop)
+            v = to_f32(in[((int64_t)(a_n[i] * crop + iy) * crop + ix) * in_cstride + in_coff + c]);
+        }
+        As[a_kk][(t >> 4) + 16 * i] = v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = k0 + b_kk + 4 * i;
+      float v = 0.0f;
+      if (kk < Ktot && n0 + b_co < co) v = w[(int64_t)kk * co + n0 + b_co];
+      Bs[b_kk + 4 * i][b_co] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SIMT_BK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= co) continue;
+      const float v = apply_act(fmaf(acc[i][j], scale[n], shift[n]), act);
+      out[(int64_t)m * out_cstride + out_coff + n] = from_f32<TOut>(v);
+    }
+  }
+}
+
+template <typename TIn, typename TOut>
+static void launch_conv_simt(Handle* h, const TIn* in, int in_cstride, int in_coff, int ci, const float* w, TOut* out,
+                             int out_cstride, int out_coff, int co, int B, int crop, int k, int rate, int pad_b,
+                             const float* scale, const float* shift, int act) {
+  const int64_t M = (int64_t)B * crop * crop;
+  dim3 grid((unsigned)ceil_div(M, SIMT_BM), (unsigned)ceil_div(co, SIMT_BN));
+  conv_simt_kernel<TIn, TOut><<<grid, SIMT_THREADS, 0, h->stream>>>(in, in_cstride, in_coff, ci, w, out, out_cstride,
+                                                                    out_coff, co, (int)M, crop, k, rate, pad_b, scale,
+                                                                    shift, act);
+  LAUNCH_CHECK(h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad (fp32, fixed order): dW[kk][co] = sum_m A[m][kk] * dY[m][co], split over pixel ranges.
+// part[s][kk][co] for split s; reduced in split order by reduce_partials_kernel.
+// ------------------------------------------------------------------------------------------------
+template <typename TIn, typename TG>
+__global__ void __launch_bounds__(SIMT_THREADS)
+wgrad_simt_kernel(const TIn* __restrict__ in, int in_cstride, int in_coff, int ci, const TG* __restrict__ dy,
+                  int dy_cstride, int dy_coff, int co, float* __restrict__ part, int M, int crop, int ksize, int rate,
+                  int pad_b, int m_per_split) {
+  __shared__ float As[SIMT_BK][SIMT_BM + 4];   // [m][kk]
+  __shared__ float Bs[SIMT_BK][SIMT_BN + 4];   // [m][co]
+  const int t = threadIdx.x;
+  const int k0 = blockIdx.x * SIMT_BM;
+  const int n0 = blockIdx.y * SIMT_BN;
+  const int split = blockIdx.z;
+  const int Ktot = ksize * ksize * ci;
+  const int cc = crop * crop;
+  const int m_begin = split * m_per_split;
+  const int m_end = min(M, m_begin + m_per_split);
+
+  const int a_kk = k0 + (t & 63);
+  int c = 0, dyo = 0, dxo = 0;
+  const bool kvalid = a_kk < Ktot;
+  if (kvalid) {
+    const int tap = a_kk / ci;
+    c = a_kk - tap * ci;
+    const int ky = tap / ksize, kx = tap - ky * ksize;
+    dyo = ky * rate - pad_b;
+    dxo = kx * rate - pad_b;
+  }
+  const int tx = t & 15, ty = t >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  for (int mb = m_begin; mb < m_end; mb += SIMT_BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ml = (t >> 6) + 4 * i;
+      const int m = mb + ml;
+      float va = 0.0f, vb = 0.0f;
+      if (m < m_end) {
+        if (kvalid) {
+          const int n = m / cc;
+          const int r = m - n * cc;
+          const int y = r / crop, x = r - y * crop;
+          const int iy = y + dyo, ix = x + dxo;
+          if (iy >= 0 && iy < crop && ix >= 0 && ix < crop)
+            va = to_f32(in[((int64_t)(n * crop + iy) * crop + ix) * in_cstride + in_coff + c]);
+        }
+        if (n0 + (t & 63) < co) vb = to_f32(dy[(int64_t)m * dy_cstride + dy_coff + n0 + (t & 63)]);
+      }
+      As[ml][t & 63] = va;
+      Bs[ml][t & 63] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int mm = 0; mm < SIMT_BK; ++mm) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[mm][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[mm][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int kk = k0 + ty * 4 + i;
+    if (kk >= Ktot) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= co) continue;
+      part[((int64_t)split * Ktot + kk) * co + n] = acc[i][j];
+    }
+  }
+}
+
+// out[i] = sum_{s=0..S-1} part[s][i] (fixed order); optionally out += existing
+__global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int k = 0; k < S; ++k) s += part[(int64_t)k * n + i];
+  out[i] = s;
+}
+
+template <typename TIn, typename TG>
+static void launch_wgrad_simt(Handle* h, const TIn* in, int in_cstride, int in_coff, int ci, const TG* dy,
+                              int dy_cstride, int dy_coff, int co, float* dw, float* part, int max_splits, int B,
+                              int crop, int k, int rate, int pad_b) {
+  const int64_t M = (int64_t)B * crop * crop;
+  const int Ktot = k * k * ci;
+  int splits = (int)ceil_div(M, 2048);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int m_per = (int)round_up(ceil_div(M, splits), SIMT_BK);
+  splits = (int)ceil_div(M, m_per);
+  dim3 grid((unsigned)ceil_div(Ktot, SIMT_BM), (unsigned)ceil_div(co, SIMT_BN), (unsigned)splits);
+  wgrad_simt_kernel<TIn, TG><<<grid, SIMT_THREADS, 0, h->stream>>>(in, in_cstride, in_coff, ci, dy, dy_cstride, dy_coff,
+                                                                   co, part, (int)M, crop, k, rate, pad_b, m_per);
+  LAUNCH_CHECK(h);
+  const int64_t n = (int64_t)Ktot * co;
+  reduce_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, h->stream>>>(part, dw, n, splits);
+  LAUNCH_CHECK(h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: master fp32 HWIO -> operand matrices
+// ------------------------------------------------------------------------------------------------
+// fprop operand  Wf[co][tap*ci + c] = W[tap][c][co]
+template <typename T>
+__global__ void pack_fprop_kernel(const float* __restrict__ w, T* __restrict__ out, int taps, int ci, int co) {
+  const int64_t n = (int64_t)taps * ci * co;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int o = (int)(i / ((int64_t)taps * ci));
+  const int kk = (int)(i - (int64_t)o * taps * ci);
+  out[i] = from_f32<T>(w[(int64_t)kk * co + o]);
+}
+// dgrad operand  Wd[c][tap'*co + o] = W[taps-1-tap'][c][o]   (K-major for the tensor-core path)
+template <typename T>
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, T* __restrict__ out, int taps, int ci, int co) {
+  const int64_t n = (int64_t)taps * ci * co;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i / ((int64_t)taps * co));
+  const int r = (int)(i - (int64_t)c * taps * co);
+  const int tp = r / co, o = r - tp * co;
+  out[i] = from_f32<T>(w[((int64_t)(taps - 1 - tp) * ci + c) * co + o]);
+}
+// dgrad operand for the SIMT path: HWIO-like [tap'*co + o][c] fp32
+__global__ void pack_dgrad_simt_kernel(const float* __restrict__ w, float* __restrict__ out, int taps, int ci, int co) {
+  const int64_t n = (int64_t)taps * ci * co;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i % ci);
+  const int r = (int)(i / ci);
+  const int tp = r / co, o = r - tp * co;
+  out[i] = w[((int64_t)(taps - 1 - tp) * ci + c) * co + o];
+}

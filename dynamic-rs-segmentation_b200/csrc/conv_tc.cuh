@@ -1,0 +1,389 @@
+// Dilated SAME convolution (stride 1) as an implicit GEMM on the 5th-gen tensor cores.
+//
+// Reference op: tf.nn.atrous_conv2d(x, W[kh,kw,Ci,Co], rate, 'SAME') + bias -> BN -> act
+// (_conv_layer, /root/reference/isprs_dilated_random.py:700-723).  Also used for dgrad (a dilated
+// convolution of dY with the tap-flipped, Ci/Co-transposed filter and swapped padding).
+//
+//   GEMM:  D[M, N] = A[M, K] * B[N, K]^T      M = B*crop*crop output pixels (NHWC raster)
+//                                             N = Co,  K = kh*kw*Ci  (k index = tap*Ci + c)
+//   A tile  128 pixels x BLOCK_K channels of ONE filter tap, fetched by a TMA *im2col* load:
+//           128 consecutive output pixels (running across row and image boundaries), displaced by the
+//           tap offset (kx*rate, ky*rate); pixels outside the image are zero-filled by the TMA unit,
+//           which is exactly SAME padding (asymmetric before/after for even kernels included).
+//   B tile  N x BLOCK_K slice of the packed filter matrix [Co][K] (K-major), tiled TMA load.
+//   Both land in shared memory in the canonical K-major 128B-swizzled (64B when BLOCK_K=32) layout
+//   that tcgen05.mma reads through shared-memory descriptors; the fp32 accumulator lives in TMEM
+//   (two stages, so the epilogue of tile i overlaps the main loop of tile i+1).
+//   Epilogue: tcgen05.ld -> y = act(acc*scale[c] + shift[c]) (bias / folded BN) -> fp16|bf16 ->
+//   swizzled staging in shared memory -> TMA store into a channel slice of the NHWC output
+//   (dense nets write straight into the concat buffer: tf.concat, isprs:921-948, costs nothing).
+//
+// Warp roles (256 threads, persistent, one CTA per SM):
+//   warp 0 lane 0 : TMA producer          warp 1 lane 0 : tcgen05.mma issuer
+//   warp 2        : TMEM allocator        warps 4..7    : epilogue (TMEM lane quadrant = warp % 4)
+#pragma once
+#include "drs_common.cuh"
+#include "ptx_sm100.cuh"
+
+struct ConvTcParams {
+  int M_total;        // output pixels
+  int crop;           // H = W
+  int ksize, rate, pad_b;
+  int ci, in_coff;    // channels consumed, channel offset inside the input buffer
+  int co, out_coff;   // N, channel offset inside the output buffer
+  int num_tiles;      // ceil(M_total / 128)
+  int stages;         // smem pipeline depth
+  int acc_stride;     // TMEM columns between the two accumulator stages
+  int tmem_cols;      // allocated TMEM columns (power of two >= 32)
+  int act;
+  int smem_needed;    // bytes used from the 1024B-aligned base
+  int smem_provided;  // dynamic shared memory bytes of the launch
+  uint32_t idesc;
+  const float* scale; // [co]
+  const float* shift; // [co]
+  uint32_t* diag;     // host-mapped diagnostics
+};
+
+constexpr int CONV_TC_THREADS = 256;
+constexpr int CONV_TC_BM = 128;
+
+template <typename OutT>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// BLOCK_K: channels per K step (64 -> 128B swizzle, 32 -> 64B swizzle).  EPI_C: channels per epilogue
+// store box (64 -> 128B swizzle, 32 -> 64B swizzle).
+template <int BLOCK_K, int EPI_C, typename OutT>
+__global__ void __launch_bounds__(CONV_TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const ConvTcParams p) {
+  constexpr int A_BYTES = CONV_TC_BM * BLOCK_K * 2;
+  constexpr int SW_BYTES = BLOCK_K * 2;                        // swizzle span of the operand tiles
+  constexpr uint32_t OP_LAYOUT = (SW_BYTES == 128) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
+  constexpr uint32_t OP_SBO = 8 * SW_BYTES;                    // 8 rows of one swizzle atom
+  constexpr int STG_BYTES = CONV_TC_BM * EPI_C * 2;            // one epilogue staging buffer
+  constexpr int MAX_STAGES = 8;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // operand tiles need 1024B alignment (swizzle atom); the launch adds slack only when it fits
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  if (pad + static_cast<uint32_t>(p.smem_needed) > static_cast<uint32_t>(p.smem_provided)) {
+    if (threadIdx.x == 0 && p.diag) {
+      p.diag[0] = 0xBAD00001u;
+      p.diag[1] = raw_addr;
+      __threadfence_system();
+    }
+    __trap();
+  }
+  const int B_BYTES = p.co * BLOCK_K * 2;
+  const int stage_bytes = A_BYTES + B_BYTES;
+  uint8_t* stg = smem + p.stages * stage_bytes;                // 2 staging buffers (1024B aligned)
+  float* s_scale = reinterpret_cast<float*>(stg + 2 * STG_BYTES);
+  float* s_shift = s_scale + 256;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + 256);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int taps = p.ksize * p.ksize;
+  const int kb_per_tap = p.ci / BLOCK_K;
+  const int num_kb = taps * kb_per_tap;
+
+  for (int i = threadIdx.x; i < p.co; i += CONV_TC_THREADS) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    ptx::prefetch_tensormap(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], 4);   // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_holder, static_cast<uint32_t>(p.tmem_cols));
+    ptx::tmem_relinquish();
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int cc = p.crop * p.crop;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m0 = tile * CONV_TC_BM;
+        const int n_img = m0 / cc;
+        const int rem = m0 - n_img * cc;
+        const int py = rem / p.crop;
+        const int px = rem - py * p.crop;
+        for (int t = 0; t < taps; ++t) {
+          const int ky = t / p.ksize, kx = t - ky * p.ksize;
+          for (int kb = 0; kb < kb_per_tap; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.diag, 0x100 + stage);
+            uint8_t* sa = smem + stage * stage_bytes;
+            uint8_t* sb = sa + A_BYTES;
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+            ptx::tma_load_im2col_4d(sa, &tmA, &full_bar[stage], p.in_coff + kb * BLOCK_K, px - p.pad_b, py - p.pad_b,
+                                    n_img, static_cast<uint16_t>(kx * p.rate), static_cast<uint16_t>(ky * p.rate));
+            ptx::tma_load_2d(sb, &tmB, &full_bar[stage], (t * kb_per_tap + kb) * BLOCK_K, 0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty[as], aphase ^ 1, p.diag, 0x200 + as);
+        ptx::tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.acc_stride);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase, p.diag, 0x300 + stage);
+          ptx::tcgen05_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + A_BYTES;
+          const uint64_t adesc = ptx::make_smem_desc(sa, 16, OP_SBO, OP_LAYOUT);
+          const uint64_t bdesc = ptx::make_smem_desc(sb, 16, OP_SBO, OP_LAYOUT);
+#pragma unroll
+          for (int j = 0; j < BLOCK_K / 16; ++j) {
+            // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the >>4 address field
+            ptx::umma_f16(d_tmem, adesc + static_cast<uint64_t>(j * 2), bdesc + static_cast<uint64_t>(j * 2), p.idesc,
+                          static_cast<uint32_t>((kb | j) != 0));
+          }
+          ptx::umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[as]);        // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;            // accumulator row == pixel within the tile
+    const int epi_tid = threadIdx.x - 128;
+    constexpr int CHUNK16 = EPI_C / 8;           // 16-byte chunks per staged row
+    const int sw = (EPI_C == 64) ? (row & 7) : ((row >> 1) & 3);
+    const int n_chunks = p.co / EPI_C;
+    int as = 0;
+    uint32_t aphase = 0;
+    int sbuf = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&tmem_full[as], aphase, p.diag, 0x400 + as);
+      ptx::tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.acc_stride);
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        uint32_t v[EPI_C];
+        ptx::tmem_ld_32x32b_x32(t_row + ch * EPI_C, v);
+        if (EPI_C == 64) ptx::tmem_ld_32x32b_x32(t_row + ch * EPI_C + 32, v + (EPI_C == 64 ? 32 : 0));
+        ptx::tmem_wait_ld();
+        // the TMA store that last read staging buffer `sbuf` (two chunks ago) must have drained
+        if (epi_tid == 0) ptx::tma_store_wait_read<1>();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint8_t* srow = stg + sbuf * STG_BYTES + row * (EPI_C * 2);
+        const float* sc = s_scale + ch * EPI_C;
+        const float* sh = s_shift + ch * EPI_C;
+#pragma unroll
+        for (int j = 0; j < CHUNK16; ++j) {
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c0 = j * 8 + e * 2;
+            float a = apply_act(fmaf(__uint_as_float(v[c0]), sc[c0], sh[c0]), p.act);
+            float b = apply_act(fmaf(__uint_as_float(v[c0 + 1]), sc[c0 + 1], sh[c0 + 1]), p.act);
+            o[e] = pack2<OutT>(a, b);
+          }
+          *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (epi_tid == 0) {
+          ptx::tma_store_2d(&tmC, stg + sbuf * STG_BYTES, p.out_coff + ch * EPI_C, tile * CONV_TC_BM);
+          ptx::tma_store_commit();
+        }
+        sbuf ^= 1;
+      }
+      // all TMEM reads of this accumulator stage are complete (wait::ld above)
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (epi_tid == 0) ptx::tma_store_wait_all();
+  }
+
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct ConvTcArgs {
+  const void* in;      // NHWC [B,crop,crop,in_cstride] fp16/bf16
+  int in_cstride, in_coff, ci;
+  const void* w;       // packed [co][k*k*ci] fp16/bf16
+  void* out;           // NHWC [B*crop*crop, out_cstride]
+  int out_cstride, out_coff, co;
+  int B, crop, k, rate, pad_b;
+  const float* scale;
+  const float* shift;
+  int act;
+  int etype;           // ET_F16 / ET_BF16 (operands and output)
+};
+
+static inline CUtensorMapDataType tm_dtype(int etype) {
+  return etype == ET_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+}
+
+static void encode_tiled_2d(Handle* h, CUtensorMap* tm, int etype, const void* base, uint64_t inner, uint64_t outer,
+                            uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                        : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                        : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
+                                               : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = h->encodeTiled(tm, tm_dtype(etype), 2, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DRS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu stride=%llu box=%ux%u", (int)r,
+            (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner,
+            box_outer);
+}
+
+// NHWC activation tensor seen as (C, W, H, N); the bounding box of base pixels is the output raster.
+static void encode_im2col(Handle* h, CUtensorMap* tm, int etype, const void* base, int cstride, int crop, int B,
+                          int pad_b, int channels_per_pixel, int pixels_per_column, int swizzle_bytes) {
+  cuuint64_t dims[4] = {(cuuint64_t)cstride, (cuuint64_t)crop, (cuuint64_t)crop, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)cstride * 2, (cuuint64_t)cstride * 2 * crop, (cuuint64_t)cstride * 2 * crop * crop};
+  // SAME, stride 1: lower = -pad_before; upper = pad_after - (k-1)*rate = -pad_before  (W, H order)
+  int lower[2] = {-pad_b, -pad_b};
+  int upper[2] = {-pad_b, -pad_b};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = h->encodeIm2col(tm, tm_dtype(etype), 4, const_cast<void*>(base), dims, strides, lower, upper,
+                               (cuuint32_t)channels_per_pixel, (cuuint32_t)pixels_per_column, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DRS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (%d): C=%d crop=%d B=%d pad=%d cpp=%d", (int)r, cstride,
+            crop, B, pad_b, channels_per_pixel);
+  // Known driver issue (<= 13.1) for small tensors in im2col mode; same workaround the CUTLASS headers apply.
+  if (h->driver_version <= 13010) {
+    size_t bytes = (size_t)cstride * 2 * crop * crop * B;
+    if (bytes < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  }
+}
+
+template <int BLOCK_K, int EPI_C, typename OutT>
+static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
+  alignas(64) CUtensorMap tmA, tmB, tmC;
+  const int64_t M = (int64_t)a.B * a.crop * a.crop;
+  const int taps = a.k * a.k;
+  const int sw_op = BLOCK_K * 2;
+  encode_im2col(h, &tmA, a.etype, a.in, a.in_cstride, a.crop, a.B, a.pad_b, BLOCK_K, CONV_TC_BM, sw_op);
+  encode_tiled_2d(h, &tmB, a.etype, a.w, (uint64_t)taps * a.ci, (uint64_t)a.co, (uint64_t)taps * a.ci * 2, BLOCK_K,
+                  (uint32_t)a.co, sw_op);
+  encode_tiled_2d(h, &tmC, a.etype, a.out, (uint64_t)a.out_cstride, (uint64_t)M, (uint64_t)a.out_cstride * 2, EPI_C,
+                  CONV_TC_BM, EPI_C * 2);
+
+  ConvTcParams p;
+  p.M_total = (int)M;
+  p.crop = a.crop;
+  p.ksize = a.k;
+  p.rate = a.rate;
+  p.pad_b = a.pad_b;
+  p.ci = a.ci;
+  p.in_coff = a.in_coff;
+  p.co = a.co;
+  p.out_coff = a.out_coff;
+  p.num_tiles = (int)ceil_div(M, CONV_TC_BM);
+  p.acc_stride = a.co <= 32 ? 32 : a.co <= 64 ? 64 : a.co <= 128 ? 128 : 256;
+  p.tmem_cols = 2 * p.acc_stride;
+  p.act = a.act;
+  p.idesc = make_idesc_f16(128, a.co, a.etype == ET_BF16, a.etype == ET_BF16, 0, 0);
+  p.scale = a.scale;
+  p.shift = a.shift;
+  p.diag = h->diag_dev;
+
+  const int stage_bytes = CONV_TC_BM * BLOCK_K * 2 + a.co * BLOCK_K * 2;
+  const int fixed = 2 * CONV_TC_BM * EPI_C * 2 + 2 * 256 * 4 + (2 * 8 + 4) * 8 + 16;
+  const int budget = 227 * 1024;
+  int stages = (budget - fixed) / stage_bytes;
+  if (stages > 8) stages = 8;
+  DRS_CHECK(stages >= 2, "conv_tc: tile does not fit shared memory (co=%d)", a.co);
+  p.stages = stages;
+  p.smem_needed = fixed + stages * stage_bytes;
+  const int smem_bytes = p.smem_needed + 1024 <= budget ? p.smem_needed + 1024 : budget;
+  p.smem_provided = smem_bytes;
+
+  auto kern = conv_tc_kernel<BLOCK_K, EPI_C, OutT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+    attr_set = true;
+  }
+  int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
+  kern<<<grid, CONV_TC_THREADS, smem_bytes, h->stream>>>(tmA, tmB, tmC, p);
+  LAUNCH_CHECK(h);
+}
+
+// Dispatch on K-step width and epilogue box; requirements are checked loudly.
+static void launch_conv_tc(Handle* h, const ConvTcArgs& a) {
+  DRS_CHECK(a.ci % 32 == 0, "conv_tc: Ci=%d must be a multiple of 32", a.ci);
+  DRS_CHECK(a.co % 32 == 0 && a.co >= 32 && a.co <= 256, "conv_tc: Co=%d must be a multiple of 32 in [32,256]", a.co);
+  DRS_CHECK(a.in_cstride % 8 == 0 && a.out_cstride % 8 == 0, "conv_tc: channel strides must be multiples of 8");
+  DRS_CHECK(a.in_coff % 8 == 0 && a.out_coff % 8 == 0, "conv_tc: channel offsets must be multiples of 8");
+  const bool k64 = (a.ci % 64 == 0);
+  const bool e64 = (a.co % 64 == 0);
+  if (a.etype == ET_F16) {
+    if (k64 && e64) launch_conv_tc_t<64, 64, __half>(h, a);
+    else if (k64) launch_conv_tc_t<64, 32, __half>(h, a);
+    else if (e64) launch_conv_tc_t<32, 64, __half>(h, a);
+    else launch_conv_tc_t<32, 32, __half>(h, a);
+  } else {
+    if (k64 && e64) launch_conv_tc_t<64, 64, __nv_bfloat16>(h, a);
+    else if (k64) launch_conv_tc_t<64, 32, __nv_bfloat16>(h, a);
+    else if (e64) launch_conv_tc_t<32, 64, __nv_bfloat16>(h, a);
+    else launch_conv_tc_t<32, 32, __nv_bfloat16>(h, a);
+  }
+}

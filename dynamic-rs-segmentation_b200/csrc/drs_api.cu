@@ -1,0 +1,555 @@
+// libdrs.so -- C-ABI entry points (include/drs.h) and the orchestration of the four dilated nets.
+// Reference graph: dilated_icpr_original / dilated_grsl / dilated_icpr_rate6_densely / dilated_grsl_rate8
+// (/root/reference/isprs_dilated_random.py:761-788, 962-993, 914-959, 996-1033), loss_def (1089-1099),
+// MomentumOptimizer (1685-1687).  No CPU fallback: every compute entry point needs an sm_100 device.
+#include "conv_simt.cuh"
+#include "conv_tc.cuh"
+#include "drs_common.cuh"
+#include "ops.cuh"
+#include "scene.cuh"
+
+thread_local char g_drs_err[1024] = {0};
+
+#define API_BEGIN try {
+#define API_END                                                        \
+  }                                                                    \
+  catch (const DrsError& e) { return e.code; }                         \
+  catch (const std::exception& e) {                                    \
+    snprintf(g_drs_err, sizeof(g_drs_err), "exception: %s", e.what()); \
+    return 2;                                                          \
+  }                                                                    \
+  return 0;
+
+static inline unsigned nblk(int64_t n, int t) { return (unsigned)ceil_div(n, t); }
+static inline int act_type(const Handle* h) { return h->cfg.precision == DRS_PREC_FP32 ? ET_F32 : (h->cfg.precision == DRS_PREC_F16 ? ET_F16 : ET_BF16); }
+
+// ------------------------------------------------------------------------------------------------
+// network description
+// ------------------------------------------------------------------------------------------------
+struct ConvSpec { int k, rate, co; };
+static void build_net(NetDesc& n, const drs_config& cfg) {
+  static const ConvSpec d6[] = {{5, 1, 64}, {5, 1, 64}, {4, 2, 128}, {4, 2, 128}, {3, 4, 256}, {3, 4, 256}};
+  static const ConvSpec d6p[] = {{5, 1, 64}, {5, 2, 64}, {4, 3, 128}, {4, 4, 128}, {3, 5, 256}, {3, 6, 256}};
+  static const ConvSpec dd6[] = {{5, 1, 32}, {5, 2, 32}, {4, 3, 64}, {4, 4, 64}, {3, 5, 128}, {3, 6, 128}};
+  static const ConvSpec d8p[] = {{5, 1, 64}, {5, 2, 64}, {4, 3, 128}, {4, 4, 128}, {3, 5, 192}, {3, 6, 192}, {3, 7, 256}, {3, 8, 256}};
+  const ConvSpec* sp = nullptr;
+  int L = 0;
+  n.net_type = cfg.net_type;
+  n.channels = cfg.channels;
+  n.classes = cfg.num_classes;
+  n.pool = n.dense = false;
+  const char* prefix = "conv";
+  switch (cfg.net_type) {
+    case DRS_NET_DILATED6: sp = d6; L = 6; n.act = ACT_RELU; if (cfg.isprs_scopes) prefix = "main_conv"; break;
+    case DRS_NET_DILATED6_POOLING: sp = d6p; L = 6; n.act = ACT_LRELU; n.pool = true; break;
+    case DRS_NET_DENSE_DILATED6: sp = dd6; L = 6; n.act = ACT_RELU; n.dense = true; break;
+    case DRS_NET_DILATED8_POOLING: sp = d8p; L = 8; n.act = ACT_LRELU; n.pool = true; break;
+    default: DRS_FAIL("Error! Net type not identified: %d", cfg.net_type);
+  }
+  DRS_CHECK(cfg.channels >= 1 && cfg.channels <= 16, "channels=%d out of range", cfg.channels);
+  DRS_CHECK(cfg.num_classes >= 2 && cfg.num_classes <= MAX_CLASSES, "num_classes=%d out of range [2,%d]", cfg.num_classes, MAX_CLASSES);
+  int cin = cfg.channels;
+  int64_t off = 0, boff = 0;
+  int feat = 0;   // dense: running width of the concat buffer
+  n.convs.clear();
+  for (int i = 0; i < L; ++i) {
+    ConvLayer c;
+    c.scope = std::string(prefix) + std::to_string(i + 1);
+    c.k = sp[i].k; c.rate = sp[i].rate; c.ci = cin; c.co = sp[i].co;
+    const int total = (c.k - 1) * c.rate;
+    c.pad_b = total / 2; c.pad_a = total - c.pad_b;
+    c.in_coff = 0;
+    c.out_coff = n.dense ? feat : 0;
+    c.w_off = off; off += (int64_t)c.k * c.k * c.ci * c.co;
+    c.b_off = off; off += c.co;
+    c.mm_off = boff; boff += c.co;
+    c.mv_off = boff; boff += c.co;
+    n.convs.push_back(c);
+    if (n.dense) { feat += c.co; cin = feat; } else cin = c.co;
+  }
+  n.cls_in = cin;
+  n.cls_w_off = off; off += (int64_t)cin * cfg.num_classes;
+  n.cls_b_off = off; off += cfg.num_classes;
+  n.n_trainable = off;
+  n.n_bnstat = boff;
+  n.feat_stride = 0;
+  for (auto& c : n.convs) n.feat_stride = std::max(n.feat_stride, c.co);
+  if (n.dense) n.feat_stride = feat;
+}
+
+// ------------------------------------------------------------------------------------------------
+// life cycle
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* drs_last_error(void) { return g_drs_err; }
+extern "C" int drs_version(void) { return DRS_VERSION; }
+
+struct HandleExtra {
+  uint8_t* is_weight = nullptr;   // [n_trainable] 1 for `weights` variables
+  SceneTable table;               // host copy of the device scene table
+  // training scratch kept between calls
+  float* mean = nullptr;          // [sum co] batch mean of the last train step (per layer, same offsets as mm_off/2)
+  float* inv_std = nullptr;
+  float* sums = nullptr;          // [2*256]
+  float* loss_dev = nullptr;      // [4]: ce, l2, count, spare
+  unsigned int* cm_dev = nullptr; // [K*K+1]
+  unsigned int* count_dev = nullptr;
+  float* ones = nullptr;          // [512]
+  float* zeros = nullptr;         // [512]
+  float* cls_w_eval = nullptr;
+  // profiling
+  double conv_flops = 0;
+  int64_t conv_launches = 0;
+};
+static std::map<Handle*, HandleExtra*> g_extra;
+static HandleExtra* X(Handle* h) { return g_extra[h]; }
+
+static void free_packed(Handle* h) {
+  for (auto& c : h->net.convs) {
+    if (c.w_fprop) cudaFree(c.w_fprop);
+    if (c.w_dgrad) cudaFree(c.w_dgrad);
+    if (c.fold_scale) cudaFree(c.fold_scale);
+    if (c.fold_shift) cudaFree(c.fold_shift);
+    c.w_fprop = c.w_dgrad = nullptr;
+    c.fold_scale = c.fold_shift = nullptr;
+  }
+}
+
+extern "C" int drs_create(drs_handle_t* out, const drs_config* cfg) {
+  API_BEGIN
+  DRS_CHECK(out && cfg, "drs_create: null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  DRS_CHECK(e == cudaSuccess && ndev > 0, "drs_create: no CUDA device (%s); libdrs has no CPU fallback", cudaGetErrorString(e));
+  DRS_CHECK(cfg->device >= 0 && cfg->device < ndev, "drs_create: device %d out of range (%d devices)", cfg->device, ndev);
+  CUDA_CHECK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+  DRS_CHECK(prop.major == 10, "drs_create: device %s is sm_%d%d; libdrs is built for sm_100a only", prop.name, prop.major, prop.minor);
+  Handle* h = new Handle();
+  HandleExtra* x = new HandleExtra();
+  g_extra[h] = x;
+  h->cfg = *cfg;
+  h->sm_count = prop.multiProcessorCount;
+  CUDA_CHECK(cudaDriverGetVersion(&h->driver_version));
+  build_net(h->net, *cfg);
+  CUDA_CHECK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  const int64_t nt = h->net.n_trainable;
+  CUDA_CHECK(cudaMalloc(&h->params, nt * 4));
+  CUDA_CHECK(cudaMalloc(&h->grads, (nt + 1024) * 4));
+  CUDA_CHECK(cudaMalloc(&h->moms, nt * 4));
+  CUDA_CHECK(cudaMalloc(&h->bnstat, h->net.n_bnstat * 4));
+  CUDA_CHECK(cudaMemset(h->params, 0, nt * 4));
+  CUDA_CHECK(cudaMemset(h->grads, 0, (nt + 1024) * 4));
+  CUDA_CHECK(cudaMemset(h->moms, 0, nt * 4));
+  CUDA_CHECK(cudaMalloc(&x->is_weight, nt));
+  {
+    std::vector<uint8_t> isw(nt, 0);
+    for (auto& c : h->net.convs)
+      for (int64_t i = c.w_off; i < c.b_off; ++i) isw[i] = 1;
+    for (int64_t i = h->net.cls_w_off; i < h->net.cls_b_off; ++i) isw[i] = 1;
+    CUDA_CHECK(cudaMemcpy(x->is_weight, isw.data(), nt, cudaMemcpyHostToDevice));
+    // moving_mean = 0, moving_variance = 1 (Appendix B.3)
+    std::vector<float> bn(h->net.n_bnstat, 0.0f);
+    for (auto& c : h->net.convs)
+      for (int i = 0; i < c.co; ++i) bn[c.mv_off + i] = 1.0f;
+    CUDA_CHECK(cudaMemcpy(h->bnstat, bn.data(), bn.size() * 4, cudaMemcpyHostToDevice));
+  }
+  CUDA_CHECK(cudaMalloc(&x->mean, h->net.n_bnstat * 4));
+  CUDA_CHECK(cudaMalloc(&x->inv_std, h->net.n_bnstat * 4));
+  CUDA_CHECK(cudaMalloc(&x->sums, 2 * 512 * 4));
+  CUDA_CHECK(cudaMalloc(&x->loss_dev, 16 * 4));
+  CUDA_CHECK(cudaMalloc(&x->cm_dev, (MAX_CLASSES * MAX_CLASSES + 1) * 4));
+  CUDA_CHECK(cudaMalloc(&x->count_dev, 16));
+  CUDA_CHECK(cudaMalloc(&x->ones, 512 * 4));
+  CUDA_CHECK(cudaMalloc(&x->zeros, 512 * 4));
+  CUDA_CHECK(cudaMemset(x->zeros, 0, 512 * 4));
+  {
+    std::vector<float> o(512, 1.0f);
+    CUDA_CHECK(cudaMemcpy(x->ones, o.data(), 512 * 4, cudaMemcpyHostToDevice));
+  }
+  memset(&x->table, 0, sizeof(x->table));
+  CUDA_CHECK(cudaHostAlloc(&h->diag_host, 64, cudaHostAllocMapped));
+  memset(h->diag_host, 0, 64);
+  CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->diag_dev, h->diag_host, 0));
+  // driver entry points for tensor-map encoding (no link-time dependency on libcuda)
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    DRS_CHECK(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    h->encodeTiled = (PFN_encodeTiled)fn;
+    fn = nullptr;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
+    DRS_CHECK(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col not available");
+    h->encodeIm2col = (PFN_encodeIm2col)fn;
+  }
+  CUDA_CHECK(cudaEventCreate(&h->ev_a));
+  CUDA_CHECK(cudaEventCreate(&h->ev_b));
+  h->packed_dirty = true;
+  *out = h;
+  API_END
+}
+
+extern "C" int drs_destroy(drs_handle_t h) {
+  API_BEGIN
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  HandleExtra* x = X(h);
+  free_packed(h);
+  for (auto& kv : h->scenes) {
+    if (kv.second.data) cudaFree(kv.second.data);
+    if (kv.second.labels) cudaFree(kv.second.labels);
+  }
+  cudaFree(h->params); cudaFree(h->grads); cudaFree(h->moms); cudaFree(h->bnstat);
+  if (h->arena.base) cudaFree(h->arena.base);
+  if (h->dstage) cudaFree(h->dstage);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->diag_host) cudaFreeHost(h->diag_host);
+  if (x) {
+    cudaFree(x->is_weight); cudaFree(x->mean); cudaFree(x->inv_std); cudaFree(x->sums); cudaFree(x->loss_dev);
+    cudaFree(x->cm_dev); cudaFree(x->count_dev); cudaFree(x->ones); cudaFree(x->zeros);
+    delete x;
+    g_extra.erase(h);
+  }
+  for (auto& pr : h->conv_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  cudaEventDestroy(h->ev_a); cudaEventDestroy(h->ev_b);
+  cudaStreamDestroy(h->own_stream);
+  delete h;
+  API_END
+}
+
+extern "C" int drs_set_stream(drs_handle_t h, void* s) {
+  API_BEGIN
+  DRS_CHECK(h, "null handle");
+  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  API_END
+}
+extern "C" int drs_synchronize(drs_handle_t h) {
+  API_BEGIN
+  DRS_CHECK(h, "null handle");
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) {
+    DRS_FAIL("stream failed: %s (diag %08x blk %u thr %u par %u)", cudaGetErrorString(e), h->diag_host[0], h->diag_host[1],
+             h->diag_host[2], h->diag_host[3]);
+  }
+  API_END
+}
+extern "C" int64_t drs_launch_count(drs_handle_t h) { return h ? h->launches : -1; }
+
+// ------------------------------------------------------------------------------------------------
+// variables
+// ------------------------------------------------------------------------------------------------
+struct VarRef { float* ptr; int64_t count; int kind; };  // kind 0 device float, 1 global_step
+static bool find_var(Handle* h, const std::string& name, VarRef& r, bool grad = false) {
+  float* base = grad ? h->grads : h->params;
+  auto slot = [&](const std::string& nm, float* p, float* m, int64_t cnt) -> bool {
+    if (name == nm) { r = {p, cnt, 0}; return true; }
+    if (!grad && m && name == nm + "/Momentum") { r = {m, cnt, 0}; return true; }
+    return false;
+  };
+  for (auto& c : h->net.convs) {
+    const int64_t wc = (int64_t)c.k * c.k * c.ci * c.co;
+    if (slot(c.scope + "/weights", base + c.w_off, h->moms + c.w_off, wc)) return true;
+    if (slot(c.scope + "/biases", base + c.b_off, h->moms + c.b_off, c.co)) return true;
+    if (!grad) {
+      if (slot(c.scope + "/moving_mean", h->bnstat + c.mm_off, nullptr, c.co)) return true;
+      if (slot(c.scope + "/moving_variance", h->bnstat + c.mv_off, nullptr, c.co)) return true;
+    }
+  }
+  if (slot("conv_classifier/weights", base + h->net.cls_w_off, h->moms + h->net.cls_w_off, (int64_t)h->net.cls_in * h->net.classes)) return true;
+  if (slot("conv_classifier/biases", base + h->net.cls_b_off, h->moms + h->net.cls_b_off, h->net.classes)) return true;
+  if (!grad && (name == "global_step" || name == "main_global_step")) { r = {nullptr, 1, 1}; return true; }
+  return false;
+}
+static void list_vars(Handle* h, std::vector<std::pair<std::string, int64_t>>& v) {
+  for (auto& c : h->net.convs) {
+    const int64_t wc = (int64_t)c.k * c.k * c.ci * c.co;
+    v.push_back({c.scope + "/weights", wc});
+    v.push_back({c.scope + "/biases", c.co});
+    v.push_back({c.scope + "/moving_mean", c.co});
+    v.push_back({c.scope + "/moving_variance", c.co});
+    v.push_back({c.scope + "/weights/Momentum", wc});
+    v.push_back({c.scope + "/biases/Momentum", c.co});
+  }
+  v.push_back({"conv_classifier/weights", (int64_t)h->net.cls_in * h->net.classes});
+  v.push_back({"conv_classifier/biases", h->net.classes});
+  v.push_back({"conv_classifier/weights/Momentum", (int64_t)h->net.cls_in * h->net.classes});
+  v.push_back({"conv_classifier/biases/Momentum", h->net.classes});
+  v.push_back({"global_step", 1});
+}
+extern "C" int drs_num_variables(drs_handle_t h) {
+  if (!h) return -1;
+  std::vector<std::pair<std::string, int64_t>> v;
+  list_vars(h, v);
+  return (int)v.size();
+}
+extern "C" int drs_variable_name(drs_handle_t h, int index, char* name_out, int cap, int64_t* count_out) {
+  API_BEGIN
+  DRS_CHECK(h, "null handle");
+  std::vector<std::pair<std::string, int64_t>> v;
+  list_vars(h, v);
+  DRS_CHECK(index >= 0 && index < (int)v.size(), "variable index %d out of range", index);
+  if (name_out && cap > 0) snprintf(name_out, cap, "%s", v[index].first.c_str());
+  if (count_out) *count_out = v[index].second;
+  API_END
+}
+extern "C" int drs_set_variable(drs_handle_t h, const char* name, const float* data, int64_t count) {
+  API_BEGIN
+  DRS_CHECK(h && name && data, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  VarRef r;
+  DRS_CHECK(find_var(h, name, r), "unknown variable '%s'", name);
+  DRS_CHECK(r.count == count, "variable '%s' has %lld elements, got %lld", name, (long long)r.count, (long long)count);
+  if (r.kind == 1) { h->global_step = (int64_t)data[0]; return 0; }
+  CUDA_CHECK(cudaMemcpyAsync(r.ptr, data, count * 4, cudaMemcpyHostToDevice, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->packed_dirty = true;
+  API_END
+}
+extern "C" int drs_get_variable(drs_handle_t h, const char* name, float* data, int64_t count) {
+  API_BEGIN
+  DRS_CHECK(h && name && data, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  VarRef r;
+  DRS_CHECK(find_var(h, name, r), "unknown variable '%s'", name);
+  DRS_CHECK(r.count == count, "variable '%s' has %lld elements, got %lld", name, (long long)r.count, (long long)count);
+  if (r.kind == 1) { data[0] = (float)h->global_step; return 0; }
+  CUDA_CHECK(cudaMemcpyAsync(data, r.ptr, count * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+extern "C" int drs_get_gradient(drs_handle_t h, const char* name, float* data, int64_t count) {
+  API_BEGIN
+  DRS_CHECK(h && name && data, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  VarRef r;
+  DRS_CHECK(find_var(h, name, r, true), "unknown trainable variable '%s'", name);
+  DRS_CHECK(r.count == count, "variable '%s' has %lld elements, got %lld", name, (long long)r.count, (long long)count);
+  CUDA_CHECK(cudaMemcpyAsync(data, r.ptr, count * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+extern "C" int drs_set_allreduce(drs_handle_t h, drs_allreduce_fn fn, void* user, int32_t world, int32_t sync_bn) {
+  API_BEGIN
+  DRS_CHECK(h, "null handle");
+  h->allreduce = fn;
+  h->allreduce_user = user;
+  h->world = fn ? (world > 0 ? world : 1) : 1;
+  h->sync_bn = fn ? sync_bn : 0;
+  API_END
+}
+static void do_allreduce(Handle* h, float* buf, int64_t count) {
+  if (!h->allreduce || h->world <= 1) return;
+  int rc = h->allreduce(h->allreduce_user, buf, count, (void*)h->stream);
+  DRS_CHECK(rc == 0, "allreduce callback failed with %d", rc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed operands / folded BN refresh (after set_variable or an optimizer step)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static void pack_layer_t(Handle* h, ConvLayer& c, bool need_dgrad) {
+  const int taps = c.k * c.k;
+  const int64_t n = (int64_t)taps * c.ci * c.co;
+  if (!c.w_fprop) CUDA_CHECK(cudaMalloc(&c.w_fprop, n * sizeof(T)));
+  pack_fprop_kernel<T><<<nblk(n, 256), 256, 0, h->stream>>>(h->params + c.w_off, (T*)c.w_fprop, taps, c.ci, c.co);
+  LAUNCH_CHECK(h);
+  if (need_dgrad) {
+    if (!c.w_dgrad) CUDA_CHECK(cudaMalloc(&c.w_dgrad, n * sizeof(T)));
+    pack_dgrad_kernel<T><<<nblk(n, 256), 256, 0, h->stream>>>(h->params + c.w_off, (T*)c.w_dgrad, taps, c.ci, c.co);
+    LAUNCH_CHECK(h);
+  }
+}
+static void refresh_packed(Handle* h, bool training) {
+  if (!h->packed_dirty) return;
+  const int et = act_type(h);
+  for (size_t l = 0; l < h->net.convs.size(); ++l) {
+    ConvLayer& c = h->net.convs[l];
+    if (!c.fold_scale) {
+      CUDA_CHECK(cudaMalloc(&c.fold_scale, c.co * 4));
+      CUDA_CHECK(cudaMalloc(&c.fold_shift, c.co * 4));
+    }
+    fold_bn_kernel<<<nblk(c.co, 128), 128, 0, h->stream>>>(h->params + c.b_off, h->bnstat + c.mm_off, h->bnstat + c.mv_off,
+                                                            h->cfg.bn_eps, c.fold_scale, c.fold_shift, c.co);
+    LAUNCH_CHECK(h);
+    if (l == 0) continue;   // conv1 always runs on the CUDA-core kernel straight from the HWIO weights
+    if (et == ET_F32) {
+      const int taps = c.k * c.k;
+      const int64_t n = (int64_t)taps * c.ci * c.co;
+      if (!c.w_dgrad) CUDA_CHECK(cudaMalloc(&c.w_dgrad, n * 4));
+      pack_dgrad_simt_kernel<<<nblk(n, 256), 256, 0, h->stream>>>(h->params + c.w_off, (float*)c.w_dgrad, taps, c.ci, c.co);
+      LAUNCH_CHECK(h);
+    } else if (et == ET_F16) {
+      pack_layer_t<__half>(h, c, true);
+    } else {
+      pack_layer_t<__nv_bfloat16>(h, c, true);
+    }
+  }
+  (void)training;
+  h->packed_dirty = false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one convolution, any precision
+// ------------------------------------------------------------------------------------------------
+struct ActBuf { void* p; int cs; int co; };   // pointer, channel stride, channel offset
+
+static void prof_begin(Handle* h, cudaEvent_t* a, cudaEvent_t* b) {
+  if (!h->time_convs) return;
+  if (h->conv_events_used == h->conv_events.size()) {
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    h->conv_events.push_back({e0, e1});
+  }
+  *a = h->conv_events[h->conv_events_used].first;
+  *b = h->conv_events[h->conv_events_used].second;
+  h->conv_events_used++;
+  CUDA_CHECK(cudaEventRecord(*a, h->stream));
+}
+static void prof_end(Handle* h, cudaEvent_t b) {
+  if (!h->time_convs) return;
+  CUDA_CHECK(cudaEventRecord(b, h->stream));
+}
+
+// generic conv over activation type TA.  w_simt: HWIO fp32 [k*k*ci][co]; w_tc: packed [co][k*k*ci].
+template <typename TA>
+static void run_conv(Handle* h, const ActBuf& in, int ci, const float* w_simt, const void* w_tc, const ActBuf& out, int co,
+                     int B, int crop, int k, int rate, int pad_b, const float* scale, const float* shift, int act) {
+  if (ElemTag<TA>::v == ET_F32) {
+    launch_conv_simt<TA, TA>(h, (const TA*)in.p, in.cs, in.co, ci, w_simt, (TA*)out.p, out.cs, out.co, co, B, crop, k, rate,
+                             pad_b, scale, shift, act);
+    return;
+  }
+  cudaEvent_t ea = nullptr, eb = nullptr;
+  prof_begin(h, &ea, &eb);
+  // tensor-core path; N > 256 is split into equal column tiles
+  int nsplit = 1;
+  while (co / nsplit > 256 || (co % nsplit) != 0 || ((co / nsplit) % 32) != 0) {
+    ++nsplit;
+    DRS_CHECK(nsplit <= 8, "cannot tile N=%d", co);
+  }
+  const int nt = co / nsplit;
+  for (int s = 0; s < nsplit; ++s) {
+    ConvTcArgs a;
+    a.in = in.p; a.in_cstride = in.cs; a.in_coff = in.co; a.ci = ci;
+    a.w = (const char*)w_tc + (size_t)s * nt * k * k * ci * 2;
+    a.out = out.p; a.out_cstride = out.cs; a.out_coff = out.co + s * nt; a.co = nt;
+    a.B = B; a.crop = crop; a.k = k; a.rate = rate; a.pad_b = pad_b;
+    a.scale = scale + s * nt; a.shift = shift + s * nt; a.act = act;
+    a.etype = ElemTag<TA>::v;
+    launch_conv_tc(h, a);
+  }
+  prof_end(h, eb);
+  X(h)->conv_flops += 2.0 * (double)B * crop * crop * k * k * ci * co;
+  X(h)->conv_launches += nsplit;
+}
+
+// ------------------------------------------------------------------------------------------------
+// inference forward (eval-mode BN folded into the conv epilogue)
+// ------------------------------------------------------------------------------------------------
+template <typename TA>
+static void forward_eval_t(Handle* h, const float* x_dev, int B, int crop, float* logits_dev, uint8_t* pred_dev) {
+  NetDesc& n = h->net;
+  const int64_t M = (int64_t)B * crop * crop;
+  refresh_packed(h, false);
+  const int fs = n.feat_stride;
+  const size_t buf_bytes = (size_t)M * fs * sizeof(TA);
+  const int nbuf = n.dense ? 1 : 3;
+  ensure_arena(h, nbuf * (buf_bytes + 4096) + (size_t)M * n.classes * 4 + 65536);
+  h->arena.reset();
+  TA* bufs[3] = {nullptr, nullptr, nullptr};
+  for (int i = 0; i < nbuf; ++i) bufs[i] = (TA*)arena_take(h, buf_bytes);
+  float* logits = logits_dev ? logits_dev : (float*)arena_take(h, (size_t)M * n.classes * 4);
+  h->taps.clear();
+
+  ActBuf cur{nullptr, 0, 0};
+  int xi = 0;   // index of the buffer holding the current input (non-dense)
+  for (size_t l = 0; l < n.convs.size(); ++l) {
+    ConvLayer& c = n.convs[l];
+    ActBuf out;
+    if (n.dense) out = {bufs[0], fs, c.out_coff};
+    else out = {bufs[(xi + 1) % 3], fs, 0};
+    if (l == 0) {
+      launch_conv_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, h->params + c.w_off, (TA*)out.p, out.cs, out.co, c.co,
+                                  B, crop, c.k, c.rate, c.pad_b, c.fold_scale, c.fold_shift, n.act);
+    } else {
+      run_conv<TA>(h, cur, c.ci, h->params + c.w_off, c.w_fprop, out, c.co, B, crop, c.k, c.rate, c.pad_b, c.fold_scale,
+                   c.fold_shift, n.act);
+    }
+    if (n.pool) {
+      ActBuf pout{bufs[(xi + 2) % 3], fs, 0};
+      maxpool3_fwd_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>((const TA*)out.p, out.cs, out.co, (TA*)pout.p,
+                                                                                 pout.cs, pout.co, nullptr, c.co, M, crop);
+      LAUNCH_CHECK(h);
+      cur = pout;
+      xi = (xi + 2) % 3;
+    } else if (n.dense) {
+      cur = {bufs[0], fs, 0};
+    } else {
+      cur = out;
+      xi = (xi + 1) % 3;
+    }
+    h->taps[c.scope] = {n.dense ? out.p : cur.p, ElemTag<TA>::v, fs, n.dense ? c.out_coff : 0, c.co, M};
+  }
+  const int threads = 256;
+  int blocks = (int)std::min<int64_t>(ceil_div(M, threads / 32), (int64_t)h->sm_count * 8);
+  classifier_fwd_kernel<TA><<<blocks, threads, n.cls_in * n.classes * 4, h->stream>>>(
+      (const TA*)cur.p, cur.cs, cur.co, n.cls_in, h->params + n.cls_w_off, h->params + n.cls_b_off, n.classes, logits, pred_dev, M);
+  LAUNCH_CHECK(h);
+}
+
+static void forward_eval(Handle* h, const float* x_dev, int B, int crop, float* logits_dev, uint8_t* pred_dev) {
+  DRS_CHECK(B >= 1 && crop >= 3 && crop <= 256, "forward: bad B=%d crop=%d", B, crop);
+  DRS_CHECK((int64_t)B * crop * crop < (int64_t)1 << 30, "forward: too many pixels in one call");
+  switch (act_type(h)) {
+    case ET_F32: forward_eval_t<float>(h, x_dev, B, crop, logits_dev, pred_dev); break;
+    case ET_F16: forward_eval_t<__half>(h, x_dev, B, crop, logits_dev, pred_dev); break;
+    default: forward_eval_t<__nv_bfloat16>(h, x_dev, B, crop, logits_dev, pred_dev); break;
+  }
+}
+
+__global__ void widen_u8_i64_kernel(const uint8_t* __restrict__ in, long long* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+extern "C" int drs_forward_dev(drs_handle_t h, const float* x_dev, int32_t B, int32_t crop, float* logits_dev, uint8_t* pred_dev) {
+  API_BEGIN
+  DRS_CHECK(h && x_dev, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  forward_eval(h, x_dev, B, crop, logits_dev, pred_dev);
+  API_END
+}
+
+extern "C" int drs_forward_host(drs_handle_t h, const float* x_host, int32_t B, int32_t crop, float* logits_host, int64_t* pred_host) {
+  API_BEGIN
+  DRS_CHECK(h && x_host, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  const int64_t M = (int64_t)B * crop * crop;
+  const int C = h->net.channels, K = h->net.classes;
+  const size_t xb = (size_t)M * C * 4, lb = (size_t)M * K * 4;
+  ensure_dstage(h, xb + lb + (size_t)M * 9 + 4096);
+  char* d = (char*)h->dstage;
+  float* x_dev = (float*)d;
+  float* lg_dev = (float*)(d + round_up(xb, 256));
+  long long* p64 = (long long*)((char*)lg_dev + round_up(lb, 256));
+  uint8_t* p8 = (uint8_t*)(p64 + M);
+  CUDA_CHECK(cudaMemcpyAsync(x_dev, x_host, xb, cudaMemcpyHostToDevice, h->stream));
+  forward_eval(h, x_dev, B, crop, lg_dev, p8);
+  if (logits_host) CUDA_CHECK(cudaMemcpyAsync(logits_host, lg_dev, lb, cudaMemcpyDeviceToHost, h->stream));
+  if (pred_host) {
+    widen_u8_i64_kernel<<<nblk(M, 256), 256, 0, h->stream>>>(p8, p64, M);
+    LAUNCH_CHECK(h);
+    CUDA_CHECK(cudaMemcpyAsync(pred_host, p64, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  int rc = drs_synchronize(h);
+  if (rc) return rc;
+  API_END
+}
+
+#include "drs_train.cuh"
+#include "drs_scene_api.cuh"

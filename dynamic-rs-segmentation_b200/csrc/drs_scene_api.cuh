@@ -1,0 +1,420 @@
+// Scene-resident entry points (gather, ordered accumulate + argmax, whole-scene inference, confusion)
+// and the debug / profiling hooks.  Included by drs_api.cu.
+#pragma once
+
+extern "C" int drs_scene_upload(drs_handle_t h, int32_t scene_id, const void* scene_host, int32_t H, int32_t W, int32_t C,
+                                int32_t dtype, const uint8_t* labels_host) {
+  API_BEGIN
+  DRS_CHECK(h && scene_host, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  DRS_CHECK(scene_id >= 0 && scene_id < MAX_SCENES, "scene_id %d out of range [0,%d)", scene_id, MAX_SCENES);
+  DRS_CHECK(dtype == DRS_SCENE_F64 || dtype == DRS_SCENE_F32, "bad scene dtype %d", dtype);
+  DRS_CHECK(C == h->net.channels, "scene has %d channels, net expects %d", C, h->net.channels);
+  Scene& s = h->scenes[scene_id];
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (s.data) CUDA_CHECK(cudaFree(s.data));
+  if (s.labels) CUDA_CHECK(cudaFree(s.labels));
+  s = Scene();
+  const size_t bytes = (size_t)H * W * C * (dtype == DRS_SCENE_F64 ? 8 : 4);
+  CUDA_CHECK(cudaMalloc(&s.data, bytes));
+  CUDA_CHECK(cudaMemcpyAsync(s.data, scene_host, bytes, cudaMemcpyHostToDevice, h->stream));
+  if (labels_host) {
+    CUDA_CHECK(cudaMalloc(&s.labels, (size_t)H * W));
+    CUDA_CHECK(cudaMemcpyAsync(s.labels, labels_host, (size_t)H * W, cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  s.H = H; s.W = W; s.C = C; s.dtype = dtype;
+  X(h)->table.s[scene_id] = SceneDesc{s.data, s.labels, H, W, C, dtype};
+  API_END
+}
+
+extern "C" int drs_scene_free(drs_handle_t h, int32_t scene_id) {
+  API_BEGIN
+  DRS_CHECK(h, "null handle");
+  auto it = h->scenes.find(scene_id);
+  if (it == h->scenes.end()) return 0;
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (it->second.data) cudaFree(it->second.data);
+  if (it->second.labels) cudaFree(it->second.labels);
+  h->scenes.erase(it);
+  memset(&X(h)->table.s[scene_id], 0, sizeof(SceneDesc));
+  API_END
+}
+
+extern "C" int drs_set_normalization(drs_handle_t h, const double* mean3, const double* std3) {
+  API_BEGIN
+  DRS_CHECK(h && mean3 && std3, "null argument");
+  for (int i = 0; i < 3; ++i) { h->norm_mean[i] = mean3[i]; h->norm_std[i] = std3[i]; }
+  API_END
+}
+
+// all pointer members of gp are device pointers
+static void launch_gather(Handle* h, GatherParams gp) {
+  for (int i = 0; i < 3; ++i) { gp.mean[i] = h->norm_mean[i]; gp.stdv[i] = h->norm_std[i]; }
+  gp.C = h->net.channels;
+  const int64_t n = (int64_t)gp.B * gp.crop * gp.crop * gp.C;
+  gather_kernel<<<nblk(n, 256), 256, 0, h->stream>>>(X(h)->table, gp);
+  LAUNCH_CHECK(h);
+}
+
+extern "C" int drs_gather_dev(drs_handle_t h, const int32_t* inst_host, const uint8_t* flips_host, int32_t B, int32_t crop,
+                              const double* noise_host, const uint8_t* noise_on_host, const double* over_x_host,
+                              const uint8_t* over_y_host, const uint8_t* over_on_host, float* x_out_dev, float* y_out_dev) {
+  API_BEGIN
+  DRS_CHECK(h && inst_host && x_out_dev, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  const int C = h->net.channels;
+  const int64_t pp = (int64_t)B * crop * crop;
+  for (int b = 0; b < B; ++b) {
+    const int sid = inst_host[b * 3], r = inst_host[b * 3 + 1], c = inst_host[b * 3 + 2];
+    const bool over = over_on_host && over_on_host[b];
+    if (over) continue;
+    auto it = h->scenes.find(sid);
+    DRS_CHECK(it != h->scenes.end(), "gather: scene %d not uploaded", sid);
+    DRS_CHECK(r >= 0 && c >= 0 && r + crop <= it->second.H && c + crop <= it->second.W,
+              "Error: Current PATCH size is out of the scene (scene %d, row %d, col %d, crop %d)", sid, r, c, crop);
+  }
+  size_t need = round_up((size_t)B * 3 * 4, 256) + 3 * round_up((size_t)B, 256);
+  if (noise_host) need += round_up((size_t)pp * C * 8, 256);
+  if (over_x_host) need += round_up((size_t)pp * C * 8, 256) + round_up((size_t)pp, 256);
+  ensure_dstage(h, need + 1024);
+  char* d = (char*)h->dstage;
+  GatherParams gp;
+  memset(&gp, 0, sizeof(gp));
+  auto put = [&](const void* src, size_t bytes) -> void* {
+    void* dst = d;
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    d += round_up(bytes, 256);
+    return dst;
+  };
+  gp.inst = (const int32_t*)put(inst_host, (size_t)B * 12);
+  if (flips_host) gp.flips = (const uint8_t*)put(flips_host, B);
+  if (noise_host && noise_on_host) {
+    gp.noise_on = (const uint8_t*)put(noise_on_host, B);
+    gp.noise = (const double*)put(noise_host, (size_t)pp * C * 8);
+  }
+  if (over_x_host && over_on_host) {
+    gp.over_on = (const uint8_t*)put(over_on_host, B);
+    gp.over_x = (const double*)put(over_x_host, (size_t)pp * C * 8);
+    if (over_y_host) gp.over_y = (const uint8_t*)put(over_y_host, (size_t)pp);
+  }
+  gp.x_out = x_out_dev;
+  gp.y_out = y_out_dev;
+  gp.B = B;
+  gp.crop = crop;
+  launch_gather(h, gp);
+  // the staging buffer is reused by the next call: the copies above must have been consumed
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+// host-only: the visiting order of create_patches_per_map (no GPU needed)
+extern "C" int drs_grid_positions(int32_t H, int32_t W, int32_t crop, int32_t batch, int32_t variant, int32_t* pos_out,
+                                  int64_t cap_pairs, int64_t* n_out) {
+  API_BEGIN
+  std::vector<int32_t> pos;
+  grid_positions(H, W, crop, batch, variant, pos);
+  const int64_t n = (int64_t)pos.size() / 2;
+  if (n_out) *n_out = n;
+  if (pos_out) {
+    DRS_CHECK(cap_pairs >= n, "grid_positions: capacity %lld < %lld", (long long)cap_pairs, (long long)n);
+    memcpy(pos_out, pos.data(), pos.size() * 4);
+  }
+  API_END
+}
+
+// cell tables of an ordered position list (host)
+struct CellTables {
+  int nh, nw, stride;
+  std::vector<int32_t> off, seq;
+};
+static void build_cells(const std::vector<int32_t>& pos, int H, int W, int crop, CellTables& ct) {
+  const int stride = crop / 2;
+  ct.stride = stride;
+  ct.nh = grid_count(H, crop, stride);
+  ct.nw = grid_count(W, crop, stride);
+  const int ncell = ct.nh * ct.nw;
+  const int64_t P = (int64_t)pos.size() / 2;
+  std::vector<int32_t> cell_of(P);
+  ct.off.assign(ncell + 1, 0);
+  for (int64_t p = 0; p < P; ++p) {
+    const int y0 = pos[2 * p], x0 = pos[2 * p + 1];
+    int i = (y0 % stride == 0 && y0 / stride < ct.nh) ? y0 / stride : -1;
+    int j = (x0 % stride == 0 && x0 / stride < ct.nw) ? x0 / stride : -1;
+    if (y0 == H - crop) i = ct.nh - 1;
+    if (x0 == W - crop) j = ct.nw - 1;
+    DRS_CHECK(i >= 0 && j >= 0, "accumulate: position (%d,%d) is not on the sliding-window lattice", y0, x0);
+    cell_of[p] = i * ct.nw + j;
+    ct.off[cell_of[p] + 1]++;
+  }
+  for (int c = 0; c < ncell; ++c) ct.off[c + 1] += ct.off[c];
+  ct.seq.assign(P, 0);
+  std::vector<int32_t> fill(ct.off.begin(), ct.off.end() - 1);
+  for (int64_t p = 0; p < P; ++p) ct.seq[fill[cell_of[p]]++] = (int32_t)p;   // ascending visit order per cell
+}
+
+struct ScenePass {
+  float* prob = nullptr;
+  uint32_t* occur = nullptr;
+  int32_t* cell_off = nullptr;
+  int32_t* cell_seq = nullptr;
+  void release() {
+    if (prob) cudaFree(prob);
+    if (occur) cudaFree(occur);
+    if (cell_off) cudaFree(cell_off);
+    if (cell_seq) cudaFree(cell_seq);
+    prob = nullptr; occur = nullptr; cell_off = cell_seq = nullptr;
+  }
+};
+
+static void accumulate_chunk(Handle* h, const ScenePass& sp, const CellTables& ct, const float* logits, const std::vector<int32_t>& pos,
+                             int seq0, int seq1, int H, int W, int K, int crop, int row_begin, int row_end) {
+  int y_lo = H, y_hi = 0;
+  for (int s = seq0; s < seq1; ++s) {
+    y_lo = std::min(y_lo, pos[2 * s]);
+    y_hi = std::max(y_hi, pos[2 * s] + crop);
+  }
+  y_lo = std::max(y_lo, row_begin);
+  y_hi = std::min(y_hi, row_end);
+  if (y_hi <= y_lo) return;
+  AccumParams ap;
+  ap.logits = logits; ap.cell_off = sp.cell_off; ap.cell_seq = sp.cell_seq; ap.prob = sp.prob; ap.occur = sp.occur;
+  ap.H = H; ap.W = W; ap.K = K; ap.crop = crop; ap.stride = ct.stride; ap.nh = ct.nh; ap.nw = ct.nw;
+  ap.row_begin = row_begin; ap.row_end = row_end; ap.y_lo = y_lo; ap.y_hi = y_hi; ap.seq0 = seq0; ap.seq1 = seq1;
+  dim3 grid(nblk(W, 128), (unsigned)(y_hi - y_lo));
+  accumulate_kernel<<<grid, 128, 0, h->stream>>>(ap);
+  LAUNCH_CHECK(h);
+}
+
+static void scene_pass_begin(Handle* h, ScenePass& sp, const CellTables& ct, int rows, int W, int K) {
+  CUDA_CHECK(cudaMalloc(&sp.prob, (size_t)rows * W * K * 4));
+  CUDA_CHECK(cudaMalloc(&sp.occur, (size_t)rows * W * 4));
+  CUDA_CHECK(cudaMalloc(&sp.cell_off, ct.off.size() * 4));
+  CUDA_CHECK(cudaMalloc(&sp.cell_seq, std::max<size_t>(ct.seq.size(), 1) * 4));
+  CUDA_CHECK(cudaMemsetAsync(sp.prob, 0, (size_t)rows * W * K * 4, h->stream));
+  CUDA_CHECK(cudaMemsetAsync(sp.occur, 0, (size_t)rows * W * 4, h->stream));
+  CUDA_CHECK(cudaMemcpyAsync(sp.cell_off, ct.off.data(), ct.off.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  if (!ct.seq.empty()) CUDA_CHECK(cudaMemcpyAsync(sp.cell_seq, ct.seq.data(), ct.seq.size() * 4, cudaMemcpyHostToDevice, h->stream));
+}
+
+static void scene_pass_finish(Handle* h, ScenePass& sp, int rows, int W, int K, uint8_t* labels_host, double* mean_host) {
+  const int64_t npix = (int64_t)rows * W;
+  uint8_t* lab_dev = nullptr;
+  double* mean_dev = nullptr;
+  CUDA_CHECK(cudaMalloc(&lab_dev, npix));
+  if (mean_host) CUDA_CHECK(cudaMalloc(&mean_dev, npix * K * 8));
+  scene_argmax_kernel<<<nblk(npix, 256), 256, 0, h->stream>>>(sp.prob, sp.occur, npix, K, lab_dev, mean_dev);
+  LAUNCH_CHECK(h);
+  CUDA_CHECK(cudaMemcpyAsync(labels_host, lab_dev, npix, cudaMemcpyDeviceToHost, h->stream));
+  if (mean_host) CUDA_CHECK(cudaMemcpyAsync(mean_host, mean_dev, npix * K * 8, cudaMemcpyDeviceToHost, h->stream));
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(lab_dev);
+  if (mean_dev) cudaFree(mean_dev);
+  CUDA_CHECK(e);
+}
+
+extern "C" int drs_accumulate_argmax(drs_handle_t h, const float* logits_dev, const int32_t* pos_host, int32_t P, int32_t crop,
+                                     int32_t K, int32_t H, int32_t W, uint8_t* labels_out_host, double* mean_out_host) {
+  API_BEGIN
+  DRS_CHECK(h && logits_dev && pos_host && labels_out_host, "null argument");
+  DRS_CHECK(K >= 1 && K <= MAX_CLASSES, "K=%d out of range", K);
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  std::vector<int32_t> pos(pos_host, pos_host + (size_t)P * 2);
+  CellTables ct;
+  build_cells(pos, H, W, crop, ct);
+  ScenePass sp;
+  try {
+    scene_pass_begin(h, sp, ct, H, W, K);
+    accumulate_chunk(h, sp, ct, logits_dev, pos, 0, P, H, W, K, crop, 0, H);
+    scene_pass_finish(h, sp, H, W, K, labels_out_host, mean_out_host);
+  } catch (...) { sp.release(); throw; }
+  sp.release();
+  API_END
+}
+
+extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, int32_t batch, int32_t variant, int32_t row_begin,
+                               int32_t row_end, uint8_t* labels_out_host, double* mean_out_host) {
+  API_BEGIN
+  DRS_CHECK(h && labels_out_host, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  auto it = h->scenes.find(scene_id);
+  DRS_CHECK(it != h->scenes.end(), "scene_infer: scene %d not uploaded", scene_id);
+  const Scene& sc = it->second;
+  const int H = sc.H, W = sc.W, K = h->net.classes, C = h->net.channels;
+  if (row_end <= 0 || row_end > H) row_end = H;
+  if (row_begin < 0) row_begin = 0;
+  DRS_CHECK(row_begin < row_end, "scene_infer: empty stripe");
+  // visiting order of the script, restricted to patches that touch the stripe (order preserved)
+  std::vector<int32_t> all, pos;
+  grid_positions(H, W, crop, batch, variant, all);
+  for (size_t p = 0; p < all.size() / 2; ++p)
+    if (all[2 * p] < row_end && all[2 * p] + crop > row_begin) { pos.push_back(all[2 * p]); pos.push_back(all[2 * p + 1]); }
+  const int P = (int)(pos.size() / 2);
+  CellTables ct;
+  build_cells(pos, H, W, crop, ct);
+  const int rows = row_end - row_begin;
+  const int64_t max_pix = (int64_t)3 << 19;   // ~1.5 M patch pixels per forward chunk
+  int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(P, max_pix / ((int64_t)crop * crop)));
+  ScenePass sp;
+  int32_t* inst_dev = nullptr;
+  float* x_dev = nullptr;
+  float* lg_dev = nullptr;
+  auto cleanup = [&]() {
+    sp.release();
+    if (inst_dev) cudaFree(inst_dev);
+    if (x_dev) cudaFree(x_dev);
+    if (lg_dev) cudaFree(lg_dev);
+  };
+  try {
+    scene_pass_begin(h, sp, ct, rows, W, K);
+    std::vector<int32_t> inst((size_t)P * 3);
+    for (int p = 0; p < P; ++p) { inst[3 * p] = scene_id; inst[3 * p + 1] = pos[2 * p]; inst[3 * p + 2] = pos[2 * p + 1]; }
+    CUDA_CHECK(cudaMalloc(&inst_dev, std::max<size_t>(inst.size(), 1) * 4));
+    CUDA_CHECK(cudaMemcpyAsync(inst_dev, inst.data(), inst.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMalloc(&x_dev, (size_t)chunk * crop * crop * C * 4));
+    CUDA_CHECK(cudaMalloc(&lg_dev, (size_t)chunk * crop * crop * K * 4));
+    for (int s0 = 0; s0 < P; s0 += chunk) {
+      const int nb = std::min(chunk, P - s0);
+      GatherParams gp;
+      memset(&gp, 0, sizeof(gp));
+      gp.inst = inst_dev + (size_t)s0 * 3;
+      gp.x_out = x_dev;
+      gp.B = nb;
+      gp.crop = crop;
+      launch_gather(h, gp);
+      forward_eval(h, x_dev, nb, crop, lg_dev, nullptr);
+      accumulate_chunk(h, sp, ct, lg_dev, pos, s0, s0 + nb, H, W, K, crop, row_begin, row_end);
+    }
+    scene_pass_finish(h, sp, rows, W, K, labels_out_host, mean_out_host);
+  } catch (...) { cleanup(); throw; }
+  cleanup();
+  API_END
+}
+
+extern "C" int drs_confusion_dev(drs_handle_t h, const uint8_t* truth_dev, const uint8_t* pred_dev, const uint8_t* mask_dev,
+                                 int64_t n, int32_t K, int32_t ignore_label, uint32_t* cm_out_host) {
+  API_BEGIN
+  DRS_CHECK(h && truth_dev && pred_dev && cm_out_host, "null argument");
+  DRS_CHECK(K >= 1 && K <= MAX_CLASSES, "K=%d out of range", K);
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  HandleExtra* x = X(h);
+  CUDA_CHECK(cudaMemsetAsync(x->cm_dev, 0, (K * K + 1) * 4, h->stream));
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(std::max<int64_t>(n, 1), 256), (int64_t)h->sm_count * 8);
+  confusion_kernel<<<blocks, 256, 0, h->stream>>>(truth_dev, pred_dev, mask_dev, n, K, ignore_label, x->cm_dev);
+  LAUNCH_CHECK(h);
+  CUDA_CHECK(cudaMemcpyAsync(cm_out_host, x->cm_dev, (K * K + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// profiling + debug hooks
+// ------------------------------------------------------------------------------------------------
+extern "C" int drs_set_profiling(drs_handle_t h, int32_t on) {
+  API_BEGIN
+  DRS_CHECK(h, "null handle");
+  h->time_convs = on != 0;
+  h->conv_events_used = 0;
+  X(h)->conv_flops = 0;
+  X(h)->conv_launches = 0;
+  API_END
+}
+// Sum of the device time of the tensor-core convolution launches recorded since drs_set_profiling(1)
+// (CUDA events on the handle's stream), their count and their algorithmic FLOPs; resets the record.
+extern "C" int drs_profile_read(drs_handle_t h, float* conv_ms, int64_t* conv_launches, double* conv_flops) {
+  API_BEGIN
+  DRS_CHECK(h, "null handle");
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  float total = 0.0f;
+  for (size_t i = 0; i < h->conv_events_used; ++i) {
+    float ms = 0.0f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, h->conv_events[i].first, h->conv_events[i].second));
+    total += ms;
+  }
+  if (conv_ms) *conv_ms = total;
+  if (conv_launches) *conv_launches = X(h)->conv_launches;
+  if (conv_flops) *conv_flops = X(h)->conv_flops;
+  h->conv_events_used = 0;
+  X(h)->conv_flops = 0;
+  X(h)->conv_launches = 0;
+  API_END
+}
+extern "C" int drs_last_conv_ms(drs_handle_t h, float* ms_out) { return drs_profile_read(h, ms_out, nullptr, nullptr); }
+
+extern "C" int drs_debug_activation(drs_handle_t h, const char* name, float* out_host, int64_t count) {
+  API_BEGIN
+  DRS_CHECK(h && name && out_host, "null argument");
+  auto it = h->taps.find(name);
+  DRS_CHECK(it != h->taps.end(), "no activation recorded for scope '%s'", name);
+  const Handle::Tap& t = it->second;
+  DRS_CHECK(count == t.pixels * t.co, "activation '%s' has %lld elements, got %lld", name, (long long)(t.pixels * t.co), (long long)count);
+  float* tmp = nullptr;
+  CUDA_CHECK(cudaMalloc(&tmp, count * 4));
+  if (t.type == ET_F32) slice_to_f32_kernel<float><<<nblk(count, 256), 256, 0, h->stream>>>((const float*)t.ptr, t.cstride, t.coff, t.co, t.pixels, tmp);
+  else if (t.type == ET_F16) slice_to_f32_kernel<__half><<<nblk(count, 256), 256, 0, h->stream>>>((const __half*)t.ptr, t.cstride, t.coff, t.co, t.pixels, tmp);
+  else slice_to_f32_kernel<__nv_bfloat16><<<nblk(count, 256), 256, 0, h->stream>>>((const __nv_bfloat16*)t.ptr, t.cstride, t.coff, t.co, t.pixels, tmp);
+  h->launches++;
+  cudaError_t e = cudaMemcpyAsync(out_host, tmp, count * 4, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(tmp);
+  CUDA_CHECK(e);
+  API_END
+}
+
+// One convolution through the production kernels (unit tests): y = act(conv(x, w) * scale + shift)
+extern "C" int drs_debug_conv(drs_handle_t h, const float* x_host, const float* w_host, const float* scale_host, const float* shift_host,
+                              int32_t B, int32_t crop, int32_t k, int32_t rate, int32_t Ci, int32_t Co, int32_t act, int32_t precision,
+                              float* y_host) {
+  API_BEGIN
+  DRS_CHECK(h && x_host && w_host && scale_host && shift_host && y_host, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  const int64_t M = (int64_t)B * crop * crop;
+  const int taps = k * k;
+  const int64_t nw = (int64_t)taps * Ci * Co;
+  const int pad_b = ((k - 1) * rate) / 2;
+  float *x32 = nullptr, *w32 = nullptr, *sc = nullptr, *sh = nullptr, *y32 = nullptr;
+  void *xa = nullptr, *wp = nullptr, *ya = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(x32); cudaFree(w32); cudaFree(sc); cudaFree(sh); cudaFree(y32); cudaFree(xa); cudaFree(wp); cudaFree(ya);
+  };
+  try {
+    CUDA_CHECK(cudaMalloc(&x32, M * Ci * 4));
+    CUDA_CHECK(cudaMalloc(&w32, nw * 4));
+    CUDA_CHECK(cudaMalloc(&sc, Co * 4));
+    CUDA_CHECK(cudaMalloc(&sh, Co * 4));
+    CUDA_CHECK(cudaMalloc(&y32, M * Co * 4));
+    CUDA_CHECK(cudaMemcpyAsync(x32, x_host, M * Ci * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(w32, w_host, nw * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(sc, scale_host, Co * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(sh, shift_host, Co * 4, cudaMemcpyHostToDevice, h->stream));
+    if (precision == DRS_PREC_FP32) {
+      launch_conv_simt<float, float>(h, x32, Ci, 0, Ci, w32, y32, Co, 0, Co, B, crop, k, rate, pad_b, sc, sh, act);
+    } else {
+      CUDA_CHECK(cudaMalloc(&xa, M * Ci * 2));
+      CUDA_CHECK(cudaMalloc(&wp, nw * 2));
+      CUDA_CHECK(cudaMalloc(&ya, M * Co * 2));
+      ConvTcArgs a;
+      a.in = xa; a.in_cstride = Ci; a.in_coff = 0; a.ci = Ci; a.w = wp; a.out = ya; a.out_cstride = Co; a.out_coff = 0; a.co = Co;
+      a.B = B; a.crop = crop; a.k = k; a.rate = rate; a.pad_b = pad_b; a.scale = sc; a.shift = sh; a.act = act;
+      if (precision == DRS_PREC_F16) {
+        cast_kernel<float, __half><<<nblk(M * Ci, 256), 256, 0, h->stream>>>(x32, (__half*)xa, M * Ci);
+        pack_fprop_kernel<__half><<<nblk(nw, 256), 256, 0, h->stream>>>(w32, (__half*)wp, taps, Ci, Co);
+        a.etype = ET_F16;
+        launch_conv_tc(h, a);
+        cast_kernel<__half, float><<<nblk(M * Co, 256), 256, 0, h->stream>>>((const __half*)ya, y32, M * Co);
+      } else {
+        cast_kernel<float, __nv_bfloat16><<<nblk(M * Ci, 256), 256, 0, h->stream>>>(x32, (__nv_bfloat16*)xa, M * Ci);
+        pack_fprop_kernel<__nv_bfloat16><<<nblk(nw, 256), 256, 0, h->stream>>>(w32, (__nv_bfloat16*)wp, taps, Ci, Co);
+        a.etype = ET_BF16;
+        launch_conv_tc(h, a);
+        cast_kernel<__nv_bfloat16, float><<<nblk(M * Co, 256), 256, 0, h->stream>>>((const __nv_bfloat16*)ya, y32, M * Co);
+      }
+      h->launches += 3;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(y_host, y32, M * Co * 4, cudaMemcpyDeviceToHost, h->stream));
+    int rc = drs_synchronize(h);
+    if (rc) throw DrsError{rc};
+  } catch (...) { cleanup(); throw; }
+  cleanup();
+  API_END
+}

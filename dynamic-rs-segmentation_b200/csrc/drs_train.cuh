@@ -1,0 +1,307 @@
+// One training step == sess.run([optimizer, loss, pred_up], is_training=True)
+// (/root/reference/isprs_dilated_random.py:1750-1752; graph 1683-1690).  Included by drs_api.cu.
+#pragma once
+
+__global__ void pack_extras_kernel(float* __restrict__ dst, const float* __restrict__ loss, const unsigned int* __restrict__ cm, int ncm) {
+  const int i = threadIdx.x;
+  if (i == 0) dst[0] = loss[0];
+  if (i < ncm) dst[1 + i] = (float)cm[i];
+}
+__global__ void unpack_extras_kernel(const float* __restrict__ src, float* __restrict__ loss, unsigned int* __restrict__ cm, int ncm) {
+  const int i = threadIdx.x;
+  if (i == 0) loss[0] = src[0];
+  if (i < ncm) cm[i] = (unsigned int)(src[1 + i] + 0.5f);
+}
+__global__ void add2_kernel(const float* __restrict__ a, float* __restrict__ out) { out[2] = a[0] + a[1]; }
+
+template <typename TA>
+static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev, int B, int crop,
+                         float* loss_host, uint8_t* pred_out_dev, uint32_t* cm_out_dev) {
+  NetDesc& n = h->net;
+  HandleExtra* x = X(h);
+  const int L = (int)n.convs.size();
+  const int K = n.classes;
+  const int64_t M = (int64_t)B * crop * crop;
+  const size_t es = sizeof(TA);
+  refresh_packed(h, true);
+
+  // ---------------------------------------------------------------- workspace plan
+  int maxc = n.cls_in;
+  for (auto& c : n.convs) maxc = std::max(maxc, std::max(c.co, c.ci));
+  size_t need = 1 << 20;
+  auto add = [&](size_t b) { need += round_up(b, 1024) + 1024; };
+  for (auto& c : n.convs) {
+    add(M * c.co * es);                       // Z
+    if (n.pool) add(M * c.co);                // idx
+    if (!n.dense) add(M * c.co * es);         // X_{l+1}
+  }
+  if (n.dense) add(M * n.feat_stride * es * 2);   // F and GF
+  add(M * maxc * es);                         // T
+  add(M * maxc * es);                         // DZ
+  add(M * maxc * es * 2);                     // G ping-pong / dense dgrad temp
+  add(M * K * 4 * 2);                         // logits, dlogits
+  add(M * 2);                                 // labels u8, pred
+  const int nb_bn = (int)ceil_div(M, BN_ROWS_PER_BLOCK);
+  add((size_t)nb_bn * 2 * 256 * 4);
+  const int nb_ce = (int)ceil_div(M, CE_THREADS);
+  add((size_t)nb_ce * 4);
+  const int nb_cls = (int)ceil_div(M, CLS_ROWS_PER_BLOCK);
+  add((size_t)nb_cls * (n.cls_in + 1) * K * 4);
+  const int max_splits = 48;
+  size_t max_w = 0;
+  for (auto& c : n.convs) max_w = std::max(max_w, (size_t)c.k * c.k * c.ci * c.co);
+  add(max_w * 4 * max_splits);
+  const int nb_opt = (int)ceil_div(n.n_trainable, 256);
+  add((size_t)nb_opt * 4);
+  ensure_arena(h, need);
+  h->arena.reset();
+
+  std::vector<TA*> Z(L), Xn(L);
+  std::vector<uint8_t*> idx(L, nullptr);
+  TA* F = nullptr;
+  TA* GF = nullptr;
+  for (int l = 0; l < L; ++l) {
+    ConvLayer& c = n.convs[l];
+    Z[l] = (TA*)arena_take(h, M * c.co * es);
+    if (n.pool) idx[l] = (uint8_t*)arena_take(h, M * c.co);
+    if (!n.dense) Xn[l] = (TA*)arena_take(h, M * c.co * es);
+  }
+  if (n.dense) {
+    F = (TA*)arena_take(h, M * n.feat_stride * es);
+    GF = (TA*)arena_take(h, M * n.feat_stride * es);
+  }
+  TA* T = (TA*)arena_take(h, M * maxc * es);
+  TA* DZ = (TA*)arena_take(h, M * maxc * es);
+  TA* G0 = (TA*)arena_take(h, M * maxc * es);
+  TA* G1 = (TA*)arena_take(h, M * maxc * es);
+  float* logits = (float*)arena_take(h, M * K * 4);
+  float* dlogits = (float*)arena_take(h, M * K * 4);
+  uint8_t* labels_u8 = (uint8_t*)arena_take(h, M);
+  uint8_t* pred = pred_out_dev ? pred_out_dev : (uint8_t*)arena_take(h, M);
+  float* part_bn = (float*)arena_take(h, (size_t)nb_bn * 2 * 256 * 4);
+  float* part_ce = (float*)arena_take(h, (size_t)nb_ce * 4);
+  float* part_cls = (float*)arena_take(h, (size_t)nb_cls * n.cls_in * K * 4);
+  float* part_clsb = (float*)arena_take(h, (size_t)nb_cls * K * 4);
+  float* part_w = (float*)arena_take(h, max_w * 4 * max_splits);
+  float* part_l2 = (float*)arena_take(h, (size_t)nb_opt * 4);
+  h->taps.clear();
+
+  CUDA_CHECK(cudaMemsetAsync(h->grads, 0, (n.n_trainable + 1024) * 4, h->stream));
+  const double bn_count = (double)M * (h->sync_bn ? h->world : 1);
+
+  // ---------------------------------------------------------------- forward (train-mode BN)
+  auto input_of = [&](int l) -> ActBuf {
+    if (l == 0) return ActBuf{(void*)x_dev, n.channels, 0};
+    if (n.dense) return ActBuf{F, n.feat_stride, 0};
+    return ActBuf{Xn[l - 1], n.convs[l - 1].co, 0};
+  };
+  for (int l = 0; l < L; ++l) {
+    ConvLayer& c = n.convs[l];
+    ActBuf zb{Z[l], c.co, 0};
+    // conv + bias (raw): scale = 1, shift = bias, no activation   (isprs:710-713)
+    if (l == 0) {
+      launch_conv_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, h->params + c.w_off, Z[l], c.co, 0, c.co, B, crop, c.k,
+                                  c.rate, c.pad_b, x->ones, h->params + c.b_off, ACT_NONE);
+    } else {
+      run_conv<TA>(h, input_of(l), c.ci, h->params + c.w_off, c.w_fprop, zb, c.co, B, crop, c.k, c.rate, c.pad_b, x->ones,
+                   h->params + c.b_off, ACT_NONE);
+    }
+    // batch statistics (biased variance), moving-average update          (isprs:658-660)
+    float* mean = x->mean + c.mm_off;
+    float* istd = x->inv_std + c.mm_off;
+    bn_partial_kernel<TA, TA, 0><<<nb_bn, c.co, 0, h->stream>>>(Z[l], c.co, 0, nullptr, 0, 0, nullptr, nullptr, 0, part_bn, c.co, M);
+    LAUNCH_CHECK(h);
+    bn_reduce_kernel<<<nblk(c.co, 128), 128, 0, h->stream>>>(part_bn, x->sums, c.co, nb_bn);
+    LAUNCH_CHECK(h);
+    if (h->sync_bn) do_allreduce(h, x->sums, 2 * c.co);
+    bn_finalize_kernel<<<nblk(c.co, 128), 128, 0, h->stream>>>(x->sums, mean, istd, h->bnstat + c.mm_off, h->bnstat + c.mv_off, c.co,
+                                                                bn_count, h->cfg.bn_eps, h->cfg.bn_decay, h->cfg.bn_unbiased_ema);
+    LAUNCH_CHECK(h);
+    // normalise + activation (+ pool)
+    ActBuf ab = n.pool ? ActBuf{T, c.co, 0} : (n.dense ? ActBuf{F, n.feat_stride, c.out_coff} : ActBuf{Xn[l], c.co, 0});
+    bn_apply_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>(Z[l], c.co, 0, mean, istd, n.act, (TA*)ab.p, ab.cs, ab.co, c.co, M);
+    LAUNCH_CHECK(h);
+    if (n.pool) {
+      maxpool3_fwd_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>(T, c.co, 0, Xn[l], c.co, 0, idx[l], c.co, M, crop);
+      LAUNCH_CHECK(h);
+    }
+    h->taps[c.scope] = {n.dense ? (void*)F : (void*)Xn[l], ElemTag<TA>::v, n.dense ? n.feat_stride : c.co, n.dense ? c.out_coff : 0, c.co, M};
+  }
+  ActBuf feat = n.dense ? ActBuf{F, n.feat_stride, 0} : ActBuf{Xn[L - 1], n.convs[L - 1].co, 0};
+  {
+    int blocks = (int)std::min<int64_t>(ceil_div(M, 8), (int64_t)h->sm_count * 8);
+    classifier_fwd_kernel<TA><<<blocks, 256, n.cls_in * K * 4, h->stream>>>((const TA*)feat.p, feat.cs, feat.co, n.cls_in,
+                                                                            h->params + n.cls_w_off, h->params + n.cls_b_off, K, logits, pred, M);
+    LAUNCH_CHECK(h);
+  }
+
+  // ---------------------------------------------------------------- loss (isprs:1089-1099, contest:881-901)
+  double count = (double)M;
+  if (mask_dev) {
+    CUDA_CHECK(cudaMemsetAsync(x->count_dev, 0, 4, h->stream));
+    mask_count_kernel<<<std::min<int64_t>(ceil_div(M, 256), 1024), 256, 0, h->stream>>>(mask_dev, M, x->count_dev);
+    LAUNCH_CHECK(h);
+    unsigned int cnt = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&cnt, x->count_dev, 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    count = (double)cnt;
+    if (h->world > 1) {
+      float fc = (float)cnt;
+      CUDA_CHECK(cudaMemcpyAsync(x->loss_dev + 3, &fc, 4, cudaMemcpyHostToDevice, h->stream));
+      do_allreduce(h, x->loss_dev + 3, 1);
+      CUDA_CHECK(cudaMemcpyAsync(&fc, x->loss_dev + 3, 4, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      count = (double)fc;
+    }
+  } else {
+    count = (double)M * h->world;
+  }
+  const float inv_count = count > 0 ? (float)(1.0 / count) : 0.0f;
+  ce_fwd_bwd_kernel<<<nb_ce, CE_THREADS, 0, h->stream>>>(logits, y_dev, mask_dev, K, M, inv_count, dlogits, part_ce, labels_u8);
+  LAUNCH_CHECK(h);
+  sum_fixed_kernel<<<1, 256, 0, h->stream>>>(part_ce, nb_ce, x->loss_dev, inv_count);
+  LAUNCH_CHECK(h);
+  // fused calc_accuracy_by_crop (isprs:510-531)
+  CUDA_CHECK(cudaMemsetAsync(x->cm_dev, 0, (K * K + 1) * 4, h->stream));
+  confusion_kernel<<<std::min<int64_t>(ceil_div(M, 256), (int64_t)h->sm_count * 4), 256, 0, h->stream>>>(labels_u8, pred, mask_dev, M, K, -1, x->cm_dev);
+  LAUNCH_CHECK(h);
+
+  // ---------------------------------------------------------------- backward
+  // classifier: dW, db, dX
+  classifier_bwd_weight_kernel<TA><<<nb_cls, (unsigned)round_up(std::max(n.cls_in, K), 32), 0, h->stream>>>(
+      (const TA*)feat.p, feat.cs, feat.co, n.cls_in, dlogits, K, part_cls, part_clsb, M);
+  LAUNCH_CHECK(h);
+  reduce_partials_kernel<<<nblk((int64_t)n.cls_in * K, 256), 256, 0, h->stream>>>(part_cls, h->grads + n.cls_w_off, (int64_t)n.cls_in * K, nb_cls);
+  LAUNCH_CHECK(h);
+  reduce_partials_kernel<<<1, 256, 0, h->stream>>>(part_clsb, h->grads + n.cls_b_off, K, nb_cls);
+  LAUNCH_CHECK(h);
+  TA* Gcur = n.dense ? GF : G0;
+  TA* Gnext = G1;
+  const int gcs0 = n.dense ? n.feat_stride : n.cls_in;
+  {
+    int blocks = (int)std::min<int64_t>(ceil_div(M * (n.cls_in / 8), 256), (int64_t)h->sm_count * 16);
+    classifier_bwd_data_kernel<TA><<<blocks, 256, n.cls_in * K * 4, h->stream>>>(dlogits, h->params + n.cls_w_off, K, Gcur, gcs0, 0, n.cls_in, M);
+    LAUNCH_CHECK(h);
+  }
+  int gcs = gcs0;   // channel stride of Gcur (non-dense)
+  for (int l = L - 1; l >= 0; --l) {
+    ConvLayer& c = n.convs[l];
+    ActBuf dOut = n.dense ? ActBuf{GF, n.feat_stride, c.out_coff} : ActBuf{Gcur, gcs, 0};
+    ActBuf dA = dOut;
+    if (n.pool) {
+      maxpool3_bwd_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>((const TA*)dOut.p, dOut.cs, dOut.co, idx[l], T, c.co, 0, c.co, M, crop);
+      LAUNCH_CHECK(h);
+      dA = ActBuf{T, c.co, 0};
+    }
+    float* mean = x->mean + c.mm_off;
+    float* istd = x->inv_std + c.mm_off;
+    bn_partial_kernel<TA, TA, 1><<<nb_bn, c.co, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, n.act, part_bn, c.co, M);
+    LAUNCH_CHECK(h);
+    bn_reduce_kernel<<<nblk(c.co, 128), 128, 0, h->stream>>>(part_bn, x->sums, c.co, nb_bn);
+    LAUNCH_CHECK(h);
+    if (h->sync_bn) do_allreduce(h, x->sums, 2 * c.co);
+    bn_bwd_apply_kernel<TA, TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, x->sums,
+                                                                                   1.0 / bn_count, n.act, DZ, c.co, 0, c.co, M);
+    LAUNCH_CHECK(h);
+    // wgrad (bias gradient is identically zero behind a BN without beta: sum_m dZ = 0)
+    ActBuf xin = input_of(l);
+    if (l == 0) {
+      launch_wgrad_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, DZ, c.co, 0, c.co, h->grads + c.w_off, part_w, max_splits, B, crop, c.k, c.rate, c.pad_b);
+    } else {
+      launch_wgrad_simt<TA, TA>(h, (const TA*)xin.p, xin.cs, xin.co, c.ci, DZ, c.co, 0, c.co, h->grads + c.w_off, part_w, max_splits, B, crop, c.k, c.rate, c.pad_b);
+    }
+    // dgrad: dilated conv of dZ with flipped taps, padding swapped
+    if (l > 0) {
+      ActBuf dzb{DZ, c.co, 0};
+      if (n.dense) {
+        ActBuf tmp{G0, c.ci, 0};
+        run_conv<TA>(h, dzb, c.co, (const float*)c.w_dgrad, c.w_dgrad, tmp, c.ci, B, crop, c.k, c.rate, c.pad_a, x->ones, x->zeros, ACT_NONE);
+        add_slice_kernel<TA><<<nblk(M * (c.ci / 8), 256), 256, 0, h->stream>>>(GF, n.feat_stride, 0, G0, c.ci, 0, c.ci, M);
+        LAUNCH_CHECK(h);
+      } else {
+        ActBuf gn{Gnext, c.ci, 0};
+        run_conv<TA>(h, dzb, c.co, (const float*)c.w_dgrad, c.w_dgrad, gn, c.ci, B, crop, c.k, c.rate, c.pad_a, x->ones, x->zeros, ACT_NONE);
+        std::swap(Gcur, Gnext);
+        gcs = c.ci;
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- exchange + update
+  if (h->world > 1) {
+    pack_extras_kernel<<<1, 128, 0, h->stream>>>(h->grads + n.n_trainable, x->loss_dev, x->cm_dev, K * K + 1);
+    LAUNCH_CHECK(h);
+    do_allreduce(h, h->grads, n.n_trainable + 2 + K * K);
+    unpack_extras_kernel<<<1, 128, 0, h->stream>>>(h->grads + n.n_trainable, x->loss_dev, x->cm_dev, K * K + 1);
+    LAUNCH_CHECK(h);
+  }
+  const float lr = h->cfg.lr_initial * powf(h->cfg.decay_rate, (float)(h->global_step / (h->cfg.decay_steps > 0 ? h->cfg.decay_steps : 1)));
+  momentum_update_kernel<<<nb_opt, 256, 0, h->stream>>>(h->params, h->grads, h->moms, n.n_trainable, x->is_weight, h->cfg.weight_decay, lr,
+                                                        h->cfg.momentum, 1.0f, part_l2);
+  LAUNCH_CHECK(h);
+  sum_fixed_kernel<<<1, 256, 0, h->stream>>>(part_l2, nb_opt, x->loss_dev + 1, 0.5f * h->cfg.weight_decay);
+  LAUNCH_CHECK(h);
+  add2_kernel<<<1, 1, 0, h->stream>>>(x->loss_dev, x->loss_dev);
+  LAUNCH_CHECK(h);
+  h->global_step++;
+  h->packed_dirty = true;
+  if (cm_out_dev) CUDA_CHECK(cudaMemcpyAsync(cm_out_dev, x->cm_dev, (K * K + 1) * 4, cudaMemcpyDeviceToDevice, h->stream));
+  if (loss_host) {
+    CUDA_CHECK(cudaMemcpyAsync(loss_host, x->loss_dev + 2, 4, cudaMemcpyDeviceToHost, h->stream));
+    int rc = drs_synchronize(h);
+    if (rc) throw DrsError{rc};
+  }
+}
+
+static void train_step(Handle* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev, int B, int crop,
+                       float* loss_host, uint8_t* pred_dev, uint32_t* cm_dev) {
+  DRS_CHECK(B >= 1 && crop >= 3 && crop <= 256, "train_step: bad B=%d crop=%d", B, crop);
+  switch (act_type(h)) {
+    case ET_F32: train_step_t<float>(h, x_dev, y_dev, mask_dev, B, crop, loss_host, pred_dev, cm_dev); break;
+    case ET_BF16: train_step_t<__nv_bfloat16>(h, x_dev, y_dev, mask_dev, B, crop, loss_host, pred_dev, cm_dev); break;
+    default:
+      DRS_FAIL("train_step: precision F16 is inference-only (gradients underflow in fp16); create the handle with DRS_PREC_BF16 or DRS_PREC_FP32");
+  }
+}
+
+extern "C" int drs_train_step_dev(drs_handle_t h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev, int32_t B,
+                                  int32_t crop, float* loss_out_host, uint8_t* pred_dev, uint32_t* cm_dev) {
+  API_BEGIN
+  DRS_CHECK(h && x_dev && y_dev, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  train_step(h, x_dev, y_dev, mask_dev, B, crop, loss_out_host, pred_dev, cm_dev);
+  API_END
+}
+
+extern "C" int drs_train_step_host(drs_handle_t h, const float* x_host, const float* y_host, const uint8_t* mask_host, int32_t B,
+                                   int32_t crop, float* loss_out, int64_t* pred_host, uint32_t* cm_host) {
+  API_BEGIN
+  DRS_CHECK(h && x_host && y_host, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  const int64_t M = (int64_t)B * crop * crop;
+  const int C = h->net.channels, K = h->net.classes;
+  const size_t xb = round_up((size_t)M * C * 4, 256), yb = round_up((size_t)M * 4, 256), mb = round_up((size_t)M, 256);
+  ensure_dstage(h, xb + yb + mb + (size_t)M * 9 + 4096 + 1024);
+  char* d = (char*)h->dstage;
+  float* x_dev = (float*)d;
+  float* y_dev = (float*)(d + xb);
+  uint8_t* m_dev = (uint8_t*)(d + xb + yb);
+  long long* p64 = (long long*)(d + xb + yb + mb);
+  uint8_t* p8 = (uint8_t*)(p64 + M);
+  uint32_t* cm_dev = (uint32_t*)(d + xb + yb + mb + round_up((size_t)M * 9, 256));
+  CUDA_CHECK(cudaMemcpyAsync(x_dev, x_host, (size_t)M * C * 4, cudaMemcpyHostToDevice, h->stream));
+  CUDA_CHECK(cudaMemcpyAsync(y_dev, y_host, (size_t)M * 4, cudaMemcpyHostToDevice, h->stream));
+  if (mask_host) CUDA_CHECK(cudaMemcpyAsync(m_dev, mask_host, (size_t)M, cudaMemcpyHostToDevice, h->stream));
+  float loss = 0.0f;
+  train_step(h, x_dev, y_dev, mask_host ? m_dev : nullptr, B, crop, &loss, p8, cm_dev);
+  if (pred_host) {
+    widen_u8_i64_kernel<<<nblk(M, 256), 256, 0, h->stream>>>(p8, p64, M);
+    LAUNCH_CHECK(h);
+    CUDA_CHECK(cudaMemcpyAsync(pred_host, p64, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (cm_host) CUDA_CHECK(cudaMemcpyAsync(cm_host, cm_dev, (K * K + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+  int rc = drs_synchronize(h);
+  if (rc) return rc;
+  if (loss_out) *loss_out = loss;
+  API_END
+}

@@ -1,0 +1,110 @@
+"""ctypes binding of libdrs.so (include/drs.h).
+
+The library is the product: there is no Python or CPU fallback.  ``load()`` raises if the shared
+object has not been built (``python dynamic-rs-segmentation_b200/csrc/build.py`` or
+``__graft_entry__.build()``), and every compute call raises ``DrsError`` with the library's message
+when it fails (e.g. no sm_100 device).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdrs.so")
+
+NET_TYPES = {
+    "dilated_icpr_original": 0,        # isprs:761
+    "dilated_grsl": 1,                 # isprs:962
+    "dilated_icpr_rate6_densely": 2,   # isprs:914
+    "dilated_grsl_rate8": 3,           # isprs:996 (contest / coffee key)
+    "dilated8_grsl": 3,                # isprs CLI key (isprs:1672-1673)
+}
+PREC = {"fp32": 0, "f16": 1, "bf16": 2}
+SCENE_F64, SCENE_F32 = 0, 1
+GRID = {"isprs": 0, "contest": 1, "coffee": 2}
+
+
+class DrsError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("net_type", C.c_int32), ("channels", C.c_int32), ("num_classes", C.c_int32),
+                ("precision", C.c_int32), ("weight_decay", C.c_float), ("lr_initial", C.c_float),
+                ("decay_steps", C.c_int32), ("decay_rate", C.c_float), ("momentum", C.c_float),
+                ("bn_decay", C.c_float), ("bn_eps", C.c_float), ("bn_unbiased_ema", C.c_int32),
+                ("device", C.c_int32), ("isprs_scopes", C.c_int32)]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "drs_create": (C.c_int, [C.POINTER(_P), C.POINTER(Config)]),
+    "drs_destroy": (C.c_int, [_P]),
+    "drs_last_error": (C.c_char_p, []),
+    "drs_version": (C.c_int, []),
+    "drs_set_stream": (C.c_int, [_P, _P]),
+    "drs_synchronize": (C.c_int, [_P]),
+    "drs_num_variables": (C.c_int, [_P]),
+    "drs_variable_name": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64)]),
+    "drs_set_variable": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
+    "drs_get_variable": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
+    "drs_get_gradient": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
+    "drs_forward_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "drs_forward_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "drs_train_step_host": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P, _P]),
+    "drs_train_step_dev": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P, _P]),
+    "drs_set_allreduce": (C.c_int, [_P, ALLREDUCE_FN, _P, C.c_int32, C.c_int32]),
+    "drs_scene_upload": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "drs_scene_free": (C.c_int, [_P, C.c_int32]),
+    "drs_set_normalization": (C.c_int, [_P, _P, _P]),
+    "drs_gather_dev": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    "drs_grid_positions": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64,
+                                     C.POINTER(C.c_int64)]),
+    "drs_accumulate_argmax": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "drs_scene_infer": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "drs_confusion_dev": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "drs_launch_count": (C.c_int64, [_P]),
+    "drs_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "drs_profile_read": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "drs_last_conv_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "drs_debug_activation": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
+    "drs_debug_conv": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_int32, _P]),
+}
+EXPORTS = sorted(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """dlopen libdrs.so and declare the prototypes.  Raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DrsError("libdrs.so not built (%s missing): run `python dynamic-rs-segmentation_b200/csrc/build.py`; "
+                       "there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise DrsError(load().drs_last_error().decode("utf-8", "replace"))
+
+
+def ptr(a):
+    """Raw address of a NumPy array / torch tensor / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return a.ctypes.data

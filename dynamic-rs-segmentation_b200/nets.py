@@ -1,0 +1,93 @@
+"""Network specifications of the four dilated FCNs and their variable initialisation.
+
+Mirrors the reference's net builders (isprs_dilated_random.py:761-788, 914-959, 962-993, 996-1033)
+and ``_conv_layer`` defaults (isprs:700-723): xavier-uniform conv weights, conv biases 0.1, classifier
+bias 0.0, BN moving_mean 0 / moving_variance 1.  The compute itself lives in libdrs.so; this module only
+describes shapes and names (TF variable scopes) so that checkpoints and parity tests line up.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+
+# (kernel, rate, Co) per conv layer
+SPECS = {
+    "dilated_icpr_original": dict(act="relu", pool=False, dense=False,
+                                  convs=[(5, 1, 64), (5, 1, 64), (4, 2, 128), (4, 2, 128), (3, 4, 256), (3, 4, 256)]),
+    "dilated_grsl": dict(act="lrelu", pool=True, dense=False,
+                         convs=[(5, 1, 64), (5, 2, 64), (4, 3, 128), (4, 4, 128), (3, 5, 256), (3, 6, 256)]),
+    "dilated_icpr_rate6_densely": dict(act="relu", pool=False, dense=True,
+                                       convs=[(5, 1, 32), (5, 2, 32), (4, 3, 64), (4, 4, 64), (3, 5, 128), (3, 6, 128)]),
+    "dilated_grsl_rate8": dict(act="lrelu", pool=True, dense=False,
+                               convs=[(5, 1, 64), (5, 2, 64), (4, 3, 128), (4, 4, 128), (3, 5, 192), (3, 6, 192),
+                                      (3, 7, 256), (3, 8, 256)]),
+}
+SPECS["dilated8_grsl"] = SPECS["dilated_grsl_rate8"]
+NET_TYPES = tuple(SPECS)
+
+
+def scope_prefix(net_type, isprs_scopes):
+    # isprs names Dilated6's layers main_conv1..6 (isprs:766-777); coffee uses conv1..6 (coffee:635-662)
+    return "main_conv" if (net_type == "dilated_icpr_original" and isprs_scopes) else "conv"
+
+
+def layer_plan(net_type, channels, isprs_scopes=True):
+    """[(scope, k, rate, Ci, Co)], classifier input width."""
+    spec = SPECS[net_type]
+    prefix = scope_prefix(net_type, isprs_scopes)
+    plan, cin = [], channels
+    for i, (k, r, co) in enumerate(spec["convs"]):
+        plan.append(("%s%d" % (prefix, i + 1), k, r, cin, co))
+        if spec["dense"]:
+            cin = co if i == 0 else cin + co
+        else:
+            cin = co
+    return plan, cin
+
+
+def variable_shapes(net_type, channels, num_classes, isprs_scopes=True):
+    plan, cls_in = layer_plan(net_type, channels, isprs_scopes)
+    shapes = OrderedDict()
+    for scope, k, r, ci, co in plan:
+        shapes[scope + "/weights"] = (k, k, ci, co)
+        shapes[scope + "/biases"] = (co,)
+        shapes[scope + "/moving_mean"] = (co,)
+        shapes[scope + "/moving_variance"] = (co,)
+    shapes["conv_classifier/weights"] = (1, 1, cls_in, num_classes)
+    shapes["conv_classifier/biases"] = (num_classes,)
+    return shapes
+
+
+def initial_variables(net_type, channels, num_classes, seed, isprs_scopes=True):
+    """``sess.run(tf.initialize_all_variables())`` (isprs:1698, 1717) with a seeded generator.
+
+    tf.contrib.layers.xavier_initializer_conv2d default: uniform(-l, l), l = sqrt(6 / (fan_in + fan_out)),
+    fan_in = kh*kw*Ci, fan_out = kh*kw*Co (isprs:702)."""
+    rs = np.random.RandomState(seed)
+    out = OrderedDict()
+    for name, shape in variable_shapes(net_type, channels, num_classes, isprs_scopes).items():
+        if name.endswith("/weights"):
+            kh, kw, ci, co = shape
+            lim = math.sqrt(6.0 / (kh * kw * ci + kh * kw * co))
+            out[name] = rs.uniform(-lim, lim, size=shape).astype(np.float32)
+        elif name == "conv_classifier/biases":
+            out[name] = np.zeros(shape, dtype=np.float32)
+        elif name.endswith("/biases"):
+            out[name] = np.full(shape, 0.1, dtype=np.float32)
+        elif name.endswith("/moving_mean"):
+            out[name] = np.zeros(shape, dtype=np.float32)
+        else:
+            out[name] = np.ones(shape, dtype=np.float32)
+    return out
+
+
+def macs_per_pixel(net_type, channels, num_classes):
+    """Forward multiply-accumulates per output pixel."""
+    plan, cls_in = layer_plan(net_type, channels)
+    return sum(k * k * ci * co for _, k, r, ci, co in plan) + cls_in * num_classes
+
+
+def tensor_core_macs_per_pixel(net_type, channels):
+    """MACs per pixel of the layers that run on the tcgen05 kernel (all but conv1 and the classifier)."""
+    plan, _ = layer_plan(net_type, channels)
+    return sum(k * k * ci * co for _, k, r, ci, co in plan[1:])

@@ -1,0 +1,285 @@
+"""``Session`` -- the drop-in for the reference's ``tf.Session`` on the hot path.
+
+The reference's only compute seam is ``sess.run(fetches, feed_dict)``:
+
+    train : sess.run([optimizer, loss, pred_up], {x, y, crop, keep_prob, is_training=True[, mask]})
+            isprs:1750-1752, contest:1083-1086, coffee:1295-1297
+    infer : sess.run([pred_up, logits], {x, y, crop, keep_prob=1, is_training=False})
+            isprs:1274-1275, contest:929-931, coffee:1058-1059
+
+``Session.train_step`` / ``Session.infer`` take the same NumPy feeds (flattened NHWC ``x``, float class ids
+``y``) and return the same fetches (fp32 scalar loss incl. the L2 terms, int64 ``pred_up`` [B,crop,crop],
+fp32 ``logits`` [B,crop,crop,K]).  Everything is computed by libdrs.so on the GPU; nothing here falls back
+to NumPy or PyTorch.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as L
+from . import nets
+
+
+class Session:
+    def __init__(self, net_type, channels, num_classes, weight_decay=0.005, lr_initial=0.01, decay_steps=50000,
+                 decay_rate=0.5, momentum=0.9, precision="bf16", device=0, isprs_scopes=True, bn_unbiased_ema=True,
+                 seed=None):
+        if net_type not in L.NET_TYPES:
+            # same message the reference prints before returning (isprs:1679)
+            raise ValueError("Error! Net type not identified: " + str(net_type))
+        self._lib = L.load()
+        self.net_type, self.channels, self.num_classes = net_type, int(channels), int(num_classes)
+        self.precision = precision
+        self.isprs_scopes = bool(isprs_scopes)
+        cfg = L.Config(L.NET_TYPES[net_type], channels, num_classes, L.PREC[precision], weight_decay, lr_initial,
+                       decay_steps, decay_rate, momentum, 0.999, 0.001, int(bool(bn_unbiased_ema)), device,
+                       int(self.isprs_scopes))
+        self._h = C.c_void_p()
+        L.check(self._lib.drs_create(C.byref(self._h), C.byref(cfg)))
+        self._cb = None
+        self._keep = []
+        if seed is not None:
+            self.init_variables(seed)
+
+    # ---------------------------------------------------------------- life cycle
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.drs_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream):
+        L.check(self._lib.drs_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+
+    def synchronize(self):
+        L.check(self._lib.drs_synchronize(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.drs_launch_count(self._h))
+
+    # ---------------------------------------------------------------- variables (tf.train.Saver / init)
+    def variable_names(self):
+        n = self._lib.drs_num_variables(self._h)
+        out = []
+        buf = C.create_string_buffer(256)
+        cnt = C.c_int64()
+        for i in range(n):
+            L.check(self._lib.drs_variable_name(self._h, i, buf, 256, C.byref(cnt)))
+            out.append((buf.value.decode(), int(cnt.value)))
+        return out
+
+    def set_variable(self, name, value):
+        a = np.ascontiguousarray(np.asarray(value, dtype=np.float32))
+        L.check(self._lib.drs_set_variable(self._h, name.encode(), L.ptr(a), a.size))
+
+    def get_variable(self, name, shape=None):
+        cnt = dict(self.variable_names())[name]
+        a = np.empty(cnt, dtype=np.float32)
+        L.check(self._lib.drs_get_variable(self._h, name.encode(), L.ptr(a), cnt))
+        return a.reshape(shape) if shape is not None else a
+
+    def get_gradient(self, name, shape=None):
+        cnt = dict(self.variable_names())[name]
+        a = np.empty(cnt, dtype=np.float32)
+        L.check(self._lib.drs_get_gradient(self._h, name.encode(), L.ptr(a), cnt))
+        return a.reshape(shape) if shape is not None else a
+
+    def init_variables(self, seed):
+        """sess.run(init) (isprs:1717) with a seeded xavier-uniform draw."""
+        self.load_variables(nets.initial_variables(self.net_type, self.channels, self.num_classes, seed,
+                                                   self.isprs_scopes))
+
+    def load_variables(self, variables):
+        for k, v in variables.items():
+            self.set_variable(k, v)
+
+    def variables(self):
+        shapes = nets.variable_shapes(self.net_type, self.channels, self.num_classes, self.isprs_scopes)
+        out = {}
+        for name, cnt in self.variable_names():
+            base = name[:-len("/Momentum")] if name.endswith("/Momentum") else name
+            out[name] = self.get_variable(name, shapes.get(base))
+        return out
+
+    def save(self, path):
+        """saver.save(sess, output_path + 'model', global_step=step) (isprs:1798): one .npz keyed by TF names."""
+        np.savez(path, **{k.replace("/", "__"): v for k, v in self.variables().items()})
+
+    def restore(self, path):
+        with np.load(path if str(path).endswith(".npz") else str(path) + ".npz") as z:
+            for k in z.files:
+                self.set_variable(k.replace("__", "/"), z[k])
+
+    @property
+    def global_step(self):
+        return int(self.get_variable("global_step")[0])
+
+    # ---------------------------------------------------------------- sess.run
+    def infer(self, x, crop, want_logits=True):
+        """(pred_up int64 [B,crop,crop], logits fp32 [B,crop,crop,K])  -- isprs:1274-1275."""
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+        B = x.shape[0]
+        if x.size != B * crop * crop * self.channels:
+            raise ValueError("x has %d elements, expected B*crop*crop*C = %d" % (x.size, B * crop * crop * self.channels))
+        pred = np.empty((B, crop, crop), dtype=np.int64)
+        logits = np.empty((B, crop, crop, self.num_classes), dtype=np.float32) if want_logits else None
+        L.check(self._lib.drs_forward_host(self._h, L.ptr(x), B, crop, L.ptr(logits), L.ptr(pred)))
+        return pred, logits
+
+    def train_step(self, x, y, crop, mask=None, want_cm=False):
+        """(loss fp32, pred_up int64 [B,crop,crop][, cm uint32 [K,K], n_correct])  -- isprs:1750-1752."""
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float32))
+        B = x.shape[0]
+        if x.size != B * crop * crop * self.channels or y.size != B * crop * crop:
+            raise ValueError("feed shapes do not match B=%d crop=%d C=%d" % (B, crop, self.channels))
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(np.asarray(mask).astype(np.uint8))
+        pred = np.empty((B, crop, crop), dtype=np.int64)
+        K = self.num_classes
+        cm = np.zeros(K * K + 1, dtype=np.uint32)
+        loss = C.c_float()
+        L.check(self._lib.drs_train_step_host(self._h, L.ptr(x), L.ptr(y), L.ptr(m), B, crop, C.byref(loss),
+                                              L.ptr(pred), L.ptr(cm)))
+        if want_cm:
+            return np.float32(loss.value), pred, cm[:K * K].reshape(K, K).copy(), int(cm[K * K])
+        return np.float32(loss.value), pred
+
+    # device-pointer variants (inputs already resident in HBM; torch tensors or raw addresses)
+    def infer_dev(self, x_dev, B, crop, logits_dev=None, pred_dev=None):
+        L.check(self._lib.drs_forward_dev(self._h, L.ptr(x_dev), B, crop, L.ptr(logits_dev), L.ptr(pred_dev)))
+
+    def train_step_dev(self, x_dev, y_dev, B, crop, mask_dev=None, pred_dev=None, cm_dev=None, want_loss=True):
+        loss = C.c_float()
+        L.check(self._lib.drs_train_step_dev(self._h, L.ptr(x_dev), L.ptr(y_dev), L.ptr(mask_dev), B, crop,
+                                             C.byref(loss) if want_loss else None, L.ptr(pred_dev), L.ptr(cm_dev)))
+        return np.float32(loss.value) if want_loss else None
+
+    # ---------------------------------------------------------------- data-parallel hook
+    def set_allreduce(self, fn, world_size, sync_bn=False):
+        """fn(buf_ptr:int, count:int, stream:int) must sum ``count`` floats at ``buf_ptr`` over ranks in place."""
+        if fn is None:
+            L.check(self._lib.drs_set_allreduce(self._h, L.ALLREDUCE_FN(0), None, 1, 0))
+            self._cb = None
+            return
+
+        def _cb(user, buf, count, stream):
+            try:
+                fn(int(buf), int(count), int(stream or 0))
+                return 0
+            except Exception as e:  # surfaced as a DrsError by the library
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        self._cb = L.ALLREDUCE_FN(_cb)
+        L.check(self._lib.drs_set_allreduce(self._h, self._cb, None, int(world_size), int(bool(sync_bn))))
+
+    # ---------------------------------------------------------------- scene path
+    def upload_scene(self, scene_id, scene, labels=None):
+        scene = np.ascontiguousarray(scene)
+        if scene.dtype == np.float64:
+            dt = L.SCENE_F64
+        elif scene.dtype == np.float32:
+            dt = L.SCENE_F32
+        else:
+            raise ValueError("scene dtype must be float64 (isprs) or float32 (contest/coffee), got %s" % scene.dtype)
+        H, W, Cc = scene.shape
+        lab = None if labels is None else np.ascontiguousarray(np.asarray(labels, dtype=np.uint8).reshape(H, W))
+        L.check(self._lib.drs_scene_upload(self._h, scene_id, L.ptr(scene), H, W, Cc, dt, L.ptr(lab)))
+
+    def free_scene(self, scene_id):
+        L.check(self._lib.drs_scene_free(self._h, scene_id))
+
+    def set_normalization(self, mean_full, std_full):
+        m = np.ascontiguousarray(np.asarray(mean_full, dtype=np.float64)[:3])
+        s = np.ascontiguousarray(np.asarray(std_full, dtype=np.float64)[:3])
+        L.check(self._lib.drs_set_normalization(self._h, L.ptr(m), L.ptr(s)))
+
+    def gather_dev(self, inst, flips, crop, x_out_dev, y_out_dev=None, noise=None, noise_on=None, over_x=None,
+                   over_y=None, over_on=None):
+        inst = np.ascontiguousarray(np.asarray(inst, dtype=np.int32).reshape(-1, 3))
+        B = inst.shape[0]
+        f = None if flips is None else np.ascontiguousarray(np.asarray(flips, dtype=np.uint8))
+        nz = None if noise is None else np.ascontiguousarray(np.asarray(noise, dtype=np.float64))
+        nzo = None if noise_on is None else np.ascontiguousarray(np.asarray(noise_on, dtype=np.uint8))
+        ox = None if over_x is None else np.ascontiguousarray(np.asarray(over_x, dtype=np.float64))
+        oy = None if over_y is None else np.ascontiguousarray(np.asarray(over_y, dtype=np.uint8))
+        oo = None if over_on is None else np.ascontiguousarray(np.asarray(over_on, dtype=np.uint8))
+        L.check(self._lib.drs_gather_dev(self._h, L.ptr(inst), L.ptr(f), B, crop, L.ptr(nz), L.ptr(nzo), L.ptr(ox),
+                                         L.ptr(oy), L.ptr(oo), L.ptr(x_out_dev), L.ptr(y_out_dev)))
+
+    def accumulate_argmax(self, logits_dev, positions, crop, H, W, want_mean=False):
+        pos = np.ascontiguousarray(np.asarray(positions, dtype=np.int32).reshape(-1, 2))
+        K = self.num_classes
+        labels = np.empty((H, W), dtype=np.uint8)
+        mean = np.empty((H, W, K), dtype=np.float64) if want_mean else None
+        L.check(self._lib.drs_accumulate_argmax(self._h, L.ptr(logits_dev), L.ptr(pos), pos.shape[0], crop, K, H, W,
+                                                L.ptr(labels), L.ptr(mean)))
+        return (labels, mean) if want_mean else labels
+
+    def scene_infer(self, scene_id, crop, batch, H, W, variant="isprs", row_begin=0, row_end=None, want_mean=False):
+        """The inner loop of validate_test / test / generate_final_maps (isprs:1249-1284) for one scene (stripe)."""
+        row_end = H if row_end is None else row_end
+        rows = row_end - row_begin
+        labels = np.empty((rows, W), dtype=np.uint8)
+        mean = np.empty((rows, W, self.num_classes), dtype=np.float64) if want_mean else None
+        L.check(self._lib.drs_scene_infer(self._h, scene_id, crop, batch, L.GRID[variant], row_begin, row_end,
+                                          L.ptr(labels), L.ptr(mean)))
+        return (labels, mean) if want_mean else labels
+
+    def confusion_dev(self, truth_dev, pred_dev, n, mask_dev=None, ignore_label=-1):
+        K = self.num_classes
+        cm = np.zeros(K * K + 1, dtype=np.uint32)
+        L.check(self._lib.drs_confusion_dev(self._h, L.ptr(truth_dev), L.ptr(pred_dev), L.ptr(mask_dev), n, K,
+                                            ignore_label, L.ptr(cm)))
+        return cm[:K * K].reshape(K, K).copy(), int(cm[K * K])
+
+    # ---------------------------------------------------------------- profiling / debug
+    def set_profiling(self, on=True):
+        L.check(self._lib.drs_set_profiling(self._h, int(bool(on))))
+
+    def profile_read(self):
+        ms, n, fl = C.c_float(), C.c_int64(), C.c_double()
+        L.check(self._lib.drs_profile_read(self._h, C.byref(ms), C.byref(n), C.byref(fl)))
+        return float(ms.value), int(n.value), float(fl.value)
+
+    def debug_activation(self, scope, B, crop, co):
+        a = np.empty((B, crop, crop, co), dtype=np.float32)
+        L.check(self._lib.drs_debug_activation(self._h, scope.encode(), L.ptr(a), a.size))
+        return a
+
+    def debug_conv(self, x, w, scale, shift, rate, act=0, precision="f16"):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        B, crop, _, ci = x.shape
+        k, _, _, co = w.shape
+        sc = np.ascontiguousarray(scale, dtype=np.float32)
+        sh = np.ascontiguousarray(shift, dtype=np.float32)
+        y = np.empty((B, crop, crop, co), dtype=np.float32)
+        L.check(self._lib.drs_debug_conv(self._h, L.ptr(x), L.ptr(w), L.ptr(sc), L.ptr(sh), B, crop, k, rate, ci, co, act,
+                                         L.PREC[precision], L.ptr(y)))
+        return y
+
+
+def grid_positions(H, W, crop, batch, variant="isprs"):
+    """Visiting order of create_patches_per_map over a whole scene (host code inside libdrs, no GPU)."""
+    lib = L.load()
+    n = C.c_int64()
+    L.check(lib.drs_grid_positions(H, W, crop, batch, L.GRID[variant], None, 0, C.byref(n)))
+    pos = np.empty((n.value, 2), dtype=np.int32)
+    L.check(lib.drs_grid_positions(H, W, crop, batch, L.GRID[variant], L.ptr(pos), n.value, C.byref(n)))
+    return pos

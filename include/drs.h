@@ -1,0 +1,185 @@
+/*
+ * drs.h -- C-ABI of libdrs.so, the B200-native (sm_100a) hot path of
+ * keillernogueira/dynamic-rs-segmentation.
+ *
+ * The reference has no FFI: its compute seam is `tf.Session.run(fetches, feed_dict)`
+ * called from the three Python scripts, plus the NumPy host loops either side of it
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface it
+ * replaces (file:line under /root/reference).  Conventions:
+ *   - one handle per process / GPU, not thread-safe;
+ *   - every function returns 0 on success, non-zero on error; the message is
+ *     available from drs_last_error();
+ *   - pointers ending in _host are host memory owned by the caller (the NumPy buffers
+ *     of feed_dict / the fetched arrays); pointers ending in _dev are device memory
+ *     owned by the caller; the library owns weights, optimizer slots and workspace;
+ *   - work is enqueued on the handle's stream (drs_set_stream); *_host entry points
+ *     synchronise that stream before returning, *_dev entry points do not;
+ *   - tensors are NHWC, weights HWIO [kh,kw,Ci,Co], labels/pred are class ids.
+ * There is no CPU fallback: every compute entry point fails if no sm_100 device is present.
+ */
+#ifndef DRS_H_
+#define DRS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct drs_handle_s* drs_handle_t;
+
+/* net_type keys of the scripts' CLI (isprs:1660-1680, contest:996-1013, coffee:1197-1220) */
+enum drs_net_type {
+  DRS_NET_DILATED6 = 0,          /* dilated_icpr_original      isprs:761-788  */
+  DRS_NET_DILATED6_POOLING = 1,  /* dilated_grsl               isprs:962-993  */
+  DRS_NET_DENSE_DILATED6 = 2,    /* dilated_icpr_rate6_densely isprs:914-959  */
+  DRS_NET_DILATED8_POOLING = 3   /* dilated_grsl_rate8 / dilated8_grsl isprs:996-1033 */
+};
+
+/* arithmetic of the convolution stack */
+enum drs_precision {
+  DRS_PREC_FP32 = 0,  /* CUDA-core fp32, fixed reduction order (exact-order mode)          */
+  DRS_PREC_F16 = 1,   /* tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM           */
+  DRS_PREC_BF16 = 2   /* tcgen05 kind::f16, bf16 operands, fp32 accumulate (training default) */
+};
+
+enum drs_scene_dtype { DRS_SCENE_F64 = 0, DRS_SCENE_F32 = 1 };
+
+/* sliding-window variants: which script's create_patches_per_map */
+enum drs_grid_variant { DRS_GRID_ISPRS = 0, DRS_GRID_CONTEST = 1, DRS_GRID_COFFEE = 2 };
+
+typedef struct drs_config {
+  int32_t net_type;        /* enum drs_net_type */
+  int32_t channels;        /* input channels C (Vaihingen 4, Potsdam 5, contest/coffee 3) */
+  int32_t num_classes;     /* K (6 / 7 / 2) */
+  int32_t precision;       /* enum drs_precision */
+  float weight_decay;      /* isprs:640-652: wd * l2_loss(W) for every `weights` variable */
+  float lr_initial;        /* isprs:1686 exponential_decay(lr_initial, step, decay_steps, decay_rate, staircase) */
+  int32_t decay_steps;     /* 50000 */
+  float decay_rate;        /* 0.5 isprs / 0.1 contest, coffee */
+  float momentum;          /* 0.9, isprs:1687 MomentumOptimizer */
+  float bn_decay;          /* 0.999, tf.contrib.layers.batch_norm default (isprs:658) */
+  float bn_eps;            /* 0.001 */
+  int32_t bn_unbiased_ema; /* 1: moving_variance EMA fed with the Bessel-corrected batch variance (fused TF path) */
+  int32_t device;          /* CUDA device ordinal */
+  int32_t isprs_scopes;    /* 1: Dilated6 variables are named main_conv1..6 (isprs:766-777) instead of conv1..6 */
+} drs_config;
+
+/* ---- life cycle ------------------------------------------------------------------- */
+int drs_create(drs_handle_t* out, const drs_config* cfg);
+int drs_destroy(drs_handle_t h);
+const char* drs_last_error(void);
+int drs_version(void);
+/* cudaStream_t to enqueue on (NULL = the handle's own stream). */
+int drs_set_stream(drs_handle_t h, void* cuda_stream);
+int drs_synchronize(drs_handle_t h);
+
+/* ---- variables: tf.train.Saver / sess.run(init) (isprs:1693-1717) ------------------- */
+/* Variables are addressed by TF scope name: "<scope>/weights", "<scope>/biases",
+ * "<scope>/moving_mean", "<scope>/moving_variance", "<scope>/weights/Momentum",
+ * "<scope>/biases/Momentum", and the scalar "global_step". */
+int drs_num_variables(drs_handle_t h);
+int drs_variable_name(drs_handle_t h, int index, char* name_out, int name_cap, int64_t* count_out);
+int drs_set_variable(drs_handle_t h, const char* name, const float* data_host, int64_t count);
+int drs_get_variable(drs_handle_t h, const char* name, float* data_host, int64_t count);
+/* gradient of the last train step w.r.t. a trainable variable (parity tests) */
+int drs_get_gradient(drs_handle_t h, const char* name, float* data_host, int64_t count);
+
+/* ---- compute seam: sess.run ---------------------------------------------------------- */
+/* infer:  sess.run([pred_up, logits], is_training=False)   isprs:1274-1275, contest:929-931, coffee:1058-1059
+ *   x       [B, crop*crop*C] fp32 (row-major NHWC, isprs:763)
+ *   logits  [B, crop, crop, K] fp32 (may be NULL)
+ *   pred    [B, crop, crop] int64 on the host path (tf.argmax, isprs:1690), uint8 on the device path (may be NULL) */
+int drs_forward_host(drs_handle_t h, const float* x_host, int32_t B, int32_t crop,
+                     float* logits_host, int64_t* pred_host);
+int drs_forward_dev(drs_handle_t h, const float* x_dev, int32_t B, int32_t crop,
+                    float* logits_dev, uint8_t* pred_dev);
+
+/* train:  sess.run([optimizer, loss, pred_up], is_training=True)  isprs:1750-1752, contest:1083-1086, coffee:1295-1297
+ *   y     [B, crop*crop] class ids fed as float32 (isprs:1654, cast isprs:1091)
+ *   mask  [B, crop*crop] 0/1 bytes or NULL (contest boolean_mask, contest:886-888)
+ *   loss  CE mean (+mask) + sum wd*l2_loss(W), with pre-update weights (isprs:1089-1099)
+ *   pred  argmax of the same train-mode forward
+ *   cm    K*K uint32 confusion counts + [K*K] = #correct, of (y, pred) over masked pixels
+ *         (calc_accuracy_by_crop, isprs:510-531) -- fused so that the host loop disappears; may be NULL */
+int drs_train_step_host(drs_handle_t h, const float* x_host, const float* y_host, const uint8_t* mask_host,
+                        int32_t B, int32_t crop, float* loss_out, int64_t* pred_host, uint32_t* cm_host);
+int drs_train_step_dev(drs_handle_t h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
+                       int32_t B, int32_t crop, float* loss_out_host, uint8_t* pred_dev, uint32_t* cm_dev);
+
+/* Data-parallel exchange hook: called on the handle's stream order with a device buffer that must be
+ * summed over ranks in place (flat gradients ++ loss numerator ++ confusion counts; and, when
+ * sync_bn != 0, the per-layer BN statistics).  NULL = single process.  The reference has no
+ * multi-device code; this is the one exchange step of the sharded path. */
+typedef int (*drs_allreduce_fn)(void* user, float* buf_dev, int64_t count, void* cuda_stream);
+int drs_set_allreduce(drs_handle_t h, drs_allreduce_fn fn, void* user, int32_t world_size, int32_t sync_bn);
+
+/* ---- scene path: NumPy loops around sess.run ----------------------------------------- */
+/* Keep a scene resident in HBM (replaces the per-batch NumPy slicing of isprs:259, 364).
+ * scene [H,W,C] float64 (isprs img_as_float) or float32 (contest/coffee); labels [H,W] uint8 or NULL. */
+int drs_scene_upload(drs_handle_t h, int32_t scene_id, const void* scene_host, int32_t H, int32_t W, int32_t C,
+                     int32_t dtype, const uint8_t* labels_host);
+int drs_scene_free(drs_handle_t h, int32_t scene_id);
+/* normalize_images (isprs:74-81): (x - mean)/std on channels 0..2 only, in the scene's dtype. */
+int drs_set_normalization(drs_handle_t h, const double* mean3, const double* std3);
+
+/* dynamically_create_patches + normalize_images (isprs:245-334, 74-81; contest:192-254; coffee:241-293)
+ *   inst   [B,3] int32 (scene_id, row, col) AFTER the caller's shift-back (host keeps RNG + border rule)
+ *   flips  [B] uint8: 0 none, 1 flipud, 2 fliplr (isprs:304-318)
+ *   noise  [B,crop,crop,C] float64 added before normalisation where noise_on[b]!=0 (isprs:298-301), or NULL
+ *   x_out  [B,crop,crop,C] fp32 device; y_out [B,crop,crop] fp32 device (labels as fed), may be NULL
+ *   over_x [B,crop,crop,C] float64 / over_y [B,crop,crop] uint8: patches that replace the scene crop where
+ *          over_on[b]!=0 (the host-rotated patches of isprs:292-296; GPU rotation is a "next" row), or NULL */
+int drs_gather_dev(drs_handle_t h, const int32_t* inst_host, const uint8_t* flips_host, int32_t B, int32_t crop,
+                   const double* noise_host, const uint8_t* noise_on_host, const double* over_x_host,
+                   const uint8_t* over_y_host, const uint8_t* over_on_host, float* x_out_dev, float* y_out_dev);
+
+/* create_patches_per_map index arithmetic (isprs:344-375, contest:267-301 incl. the offset_h bug, coffee:302-322):
+ * (row, col) of every patch in visiting order, batch after batch.  Pure host code (no device needed).
+ *   pos_out [cap_pairs,2] int32 or NULL (query the count through n_out). */
+int drs_grid_positions(int32_t H, int32_t W, int32_t crop, int32_t batch, int32_t variant, int32_t* pos_out,
+                       int64_t cap_pairs, int64_t* n_out);
+
+/* accumulate + argmax (isprs:1261-1284, contest:916-941, coffee:1045-1068), standalone:
+ *   logits [P,crop,crop,K] fp32 device, pos [P,2] int32 host (row, col) in visiting order.
+ *   labels_out [H,W] uint8 host; mean_out [H,W,K] float64 host or NULL (prob_im / occur_im).
+ * Adds per pixel in visiting order (bit-identical to NumPy's sequential fp32 `+=`), no atomics. */
+int drs_accumulate_argmax(drs_handle_t h, const float* logits_dev, const int32_t* pos_host, int32_t P, int32_t crop,
+                          int32_t K, int32_t H, int32_t W, uint8_t* labels_out_host, double* mean_out_host);
+
+/* Whole validate_test / test / generate_final_maps inner loop (isprs:1249-1284) for rows [row_begin,row_end)
+ * of an uploaded scene: grid -> gather+normalise -> forward -> ordered accumulate -> argmax.
+ *   batch     the script's batch_size (fixes the contest/coffee visiting order; results do not depend on
+ *             the internal chunking because eval-mode BN is batch-independent)
+ *   labels_out [row_end-row_begin, W] uint8 host.
+ * A rank that owns an output stripe evaluates every patch intersecting it, so stripes need no exchange. */
+int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, int32_t batch, int32_t variant,
+                    int32_t row_begin, int32_t row_end, uint8_t* labels_out_host, double* mean_out_host);
+
+/* calc_accuracy_by_crop (isprs:510-531) / per-pixel scene confusion (isprs:1289-1296, contest:944-948):
+ *   truth, pred [n] uint8 device; mask [n] or NULL; ignore_label <0 = none.
+ *   cm_out [K*K+1] uint32 host: counts[true][pred] then #correct. */
+int drs_confusion_dev(drs_handle_t h, const uint8_t* truth_dev, const uint8_t* pred_dev, const uint8_t* mask_dev,
+                      int64_t n, int32_t K, int32_t ignore_label, uint32_t* cm_out_host);
+
+/* ---- introspection for bench / tests ---------------------------------------------------- */
+/* number of kernels this library has launched since creation (bench.py "gpu_launches") */
+int64_t drs_launch_count(drs_handle_t h);
+/* Per-launch timing of the tensor-core convolution kernels with CUDA events on the handle's stream:
+ * drs_set_profiling(h,1) starts a record; drs_profile_read returns the summed device time (ms), the number of
+ * launches and their algorithmic FLOPs since then, and resets the record. */
+int drs_set_profiling(drs_handle_t h, int32_t on);
+int drs_profile_read(drs_handle_t h, float* conv_ms, int64_t* conv_launches, double* conv_flops);
+int drs_last_conv_ms(drs_handle_t h, float* ms_out);
+/* debug: copy the activation of conv scope `name` from the last forward (post act/pool) as fp32 NHWC */
+int drs_debug_activation(drs_handle_t h, const char* name, float* out_host, int64_t count);
+/* unit-test entry: one dilated SAME convolution through the tcgen05 path (or SIMT when precision=FP32).
+ *   x [B,crop,crop,Ci] fp32 host, w HWIO fp32 host, scale/shift [Co] (y = act(conv*scale+shift)), act 0/1/2 */
+int drs_debug_conv(drs_handle_t h, const float* x_host, const float* w_host, const float* scale_host,
+                   const float* shift_host, int32_t B, int32_t crop, int32_t k, int32_t rate, int32_t Ci, int32_t Co,
+                   int32_t act, int32_t precision, float* y_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRS_H_ */

@@ -1,0 +1,335 @@
+"""Generate tests/golden/host_golden.npz by running the REAL reference functions.
+
+Run in the build container only (needs /root/reference):
+    python -m oracle.make_golden
+
+The reference has no tests or fixtures, so the golden vectors
+are produced by importing its three scripts with stubbed tensorflow/gdal/skimage
+(``oracle/ref_import.py``) and calling its own host functions -- including the
+full ``validate_test`` / ``test`` / ``train`` loops driven through a fake
+``sess.run`` whose "logits" are a closed-form function of the fed patches
+(``fake_logits`` below, IEEE-exact operations only).  That pins, against the
+reference's own code: the sliding-window grid of all three scripts (incl. the
+contest offset bug F10), overlap accumulation + argmax, train-patch gathering with
+augmentation, normalisation, per-crop confusion, batch selection, patch-size
+draws and the score update / best-size selection.
+"""
+import io
+import os
+import random
+import sys
+import tempfile
+from contextlib import redirect_stdout
+
+import numpy as np
+
+from oracle import ref_import
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "host_golden.npz")
+
+
+def fake_logits(bx, crop, channels, num_classes):
+    """Closed-form stand-in for the network: IEEE-exact ops only (add, mul, fmod)."""
+    x = np.asarray(bx, dtype=np.float64).reshape(-1, crop, crop, channels)
+    s = np.zeros(x.shape[:3], dtype=np.float64)
+    for c in range(channels):
+        s = s + x[..., c] * float(c + 1)
+    out = np.empty(x.shape[:3] + (num_classes,), dtype=np.float32)
+    for k in range(num_classes):
+        out[..., k] = np.fmod(np.abs(s) * (3.0 + 2.0 * k) + 0.61 * k, 5.0).astype(np.float32)
+    return out
+
+
+class FakeSession:
+    """Stands in for tf.Session: ``run(fetches, feed_dict)`` -> closed-form results."""
+
+    def __init__(self, channels, num_classes):
+        self.channels = channels
+        self.num_classes = num_classes
+        self.log = []          # per call: (is_training, crop, B, sum_x, sum_y)
+
+    def run(self, fetches, feed_dict=None):
+        if feed_dict is None:
+            return None
+        crop = bx = by = is_training = None
+        arrays = []
+        for v in feed_dict.values():
+            if isinstance(v, (bool, np.bool_)):
+                is_training = bool(v)
+            elif isinstance(v, (int, np.integer)):
+                crop = int(v)
+            elif isinstance(v, float):
+                pass
+            else:
+                arrays.append(np.asarray(v))
+        for a in arrays:
+            if a.shape[1] == crop * crop * self.channels and a.dtype != np.bool_:
+                bx = a
+        for a in arrays:
+            if a is not bx and a.shape[1] == crop * crop and a.dtype != np.bool_:
+                by = a
+        logits = fake_logits(bx, crop, self.channels, self.num_classes)
+        pred = np.argmax(logits, axis=3).astype(np.int64)
+        self.log.append((int(is_training), crop, bx.shape[0], float(np.sum(bx.astype(np.float64))),
+                         float(np.sum(by.astype(np.float64)))))
+        if is_training:
+            loss = np.float32(np.mean(logits.astype(np.float64)))
+            return None, loss, pred
+        if isinstance(fetches, (list, tuple)):
+            return pred, logits
+        return pred
+
+
+def synth_scene(rs, h, w, c, k, block=10, dtype=np.float64, cycle=False):
+    img = (rs.randint(0, 256, size=(h, w, c)).astype(np.uint8) / 255.0).astype(dtype)
+    nb_h, nb_w = (h + block - 1) // block, (w + block - 1) // block
+    if cycle:   # every class is the majority of some window (needed by select_super_batch_instances)
+        cls = (np.arange(nb_h * nb_w).reshape(nb_h, nb_w) + rs.randint(0, k)) % k
+    else:
+        cls = rs.randint(0, k, size=(nb_h, nb_w))
+    lab = np.repeat(np.repeat(cls, block, axis=0), block, axis=1)[:h, :w]
+    return img, lab.astype(np.uint8)
+
+
+def main():
+    isprs, contest, coffee = ref_import.load()
+    tf = isprs.tf
+    G = {}
+
+    # ---- 1. sliding-window grids ----------------------------------------------------
+    grid_cases = [("isprs", 200, 260, 25, 16), ("isprs", 260, 200, 25, 16), ("isprs", 131, 97, 33, 7),
+                  ("isprs", 100, 100, 50, 4), ("isprs", 73, 73, 25, 8), ("isprs", 61, 90, 30, 5),
+                  ("contest", 260, 200, 25, 16), ("contest", 200, 260, 25, 16), ("contest", 131, 97, 33, 7),
+                  ("contest", 90, 90, 25, 6),
+                  ("coffee", 100, 100, 25, 16), ("coffee", 120, 120, 33, 5)]
+    mods = {"isprs": isprs, "contest": contest, "coffee": coffee}
+    G["grid_cases"] = np.array([[VARIANT_ID[v], h, w, c, b] for v, h, w, c, b in grid_cases], dtype=np.int64)
+    for n, (v, h, w, crop, batch) in enumerate(grid_cases):
+        stride = int(np.floor(crop / 2.0))
+        data = np.zeros((h, w, 1), dtype=np.uint8)
+        mask = np.zeros((h, w), dtype=np.uint8)
+        th = int((h - crop) / stride) + (1 if (h - crop) % stride == 0 else 2)
+        tw = int((w - crop) / stride) + (1 if (w - crop) % stride == 0 else 2)
+        total = th * tw
+        nb = int(total / batch) + 1 if total % batch != 0 else int(total / batch)
+        pos_all, lens = [], []
+        for i in range(nb):
+            out = mods[v].create_patches_per_map(data, mask, crop, stride, i, batch)
+            pos = out[-1]
+            lens.append(len(pos))
+            pos_all.extend([(int(p[0]), int(p[1])) for p in pos])
+        G["grid_%d_pos" % n] = np.array(pos_all, dtype=np.int32).reshape(-1, 2)
+        G["grid_%d_lens" % n] = np.array(lens, dtype=np.int32)
+
+    # ---- 2. select_batch ------------------------------------------------------------
+    random.seed(7)
+    total, bs = 50, 8
+    shuffle = np.asarray(random.sample(range(total), total))
+    it = 0
+    batches, its = [], []
+    for _ in range(20):
+        shuffle, batch, it = isprs.select_batch(shuffle, bs, it, total)
+        batches.append(batch)
+        its.append(it)
+    G["select_batch_batches"] = np.array(batches, dtype=np.int64)
+    G["select_batch_its"] = np.array(its, dtype=np.int64)
+
+    # ---- 3. multinomial probabilities ----------------------------------------------
+    G["probs_25_49"] = isprs.define_multinomial_probs([25, 29, 33, 37, 41, 45, 49])
+    G["probs_7_15"] = isprs.define_multinomial_probs([7, 9, 15])
+
+    # ---- 4. select_best_patch_size -------------------------------------------------
+    rs = np.random.RandomState(5)
+    best = []
+    for case in range(8):
+        dist = ["multi_fixed", "uniform"][case % 2]
+        upd = ["acc", "loss"][(case // 2) % 2]
+        values = [25, 33, 41, 49] if dist == "multi_fixed" else [25, 32]
+        n = len(values) if dist == "multi_fixed" else values[-1] - values[0] + 1
+        pal = rs.rand(n).astype(np.float32) * 10
+        occ = rs.randint(0, 4, size=n).astype(np.int32)
+        chosen = np.zeros(n, dtype=np.int32)
+        G["best_%d_in" % case] = np.stack([pal.astype(np.float64), occ.astype(np.float64)])
+        with redirect_stdout(io.StringIO()):
+            val = isprs.select_best_patch_size(dist, values, pal, occ, upd, chosen)
+        best.append(int(val))
+        G["best_%d_occ_out" % case] = occ
+        G["best_%d_chosen_out" % case] = chosen
+    G["best_vals"] = np.array(best, dtype=np.int64)
+
+    # ---- 5. isprs train-patch gather with augmentation -------------------------------
+    rs = np.random.RandomState(21)
+    scenes, labs = [], []
+    for _ in range(2):
+        img, lab = synth_scene(rs, 60, 70, 4, 6)
+        scenes.append(img)
+        labs.append(lab)
+    scenes_a, labs_a = np.asarray(scenes), np.asarray(labs)
+    inst = np.array([(0, 3, 5, 30), (1, 55, 10, 77), (0, 10, 65, 181), (1, 57, 66, 299), (0, 0, 0, 45),
+                     (1, 20, 20, 90)], dtype=np.int64)
+    G["gather_scenes"] = scenes_a
+    G["gather_labels"] = labs_a
+    G["gather_inst"] = inst
+    for crop in (9, 12):
+        np.random.seed(100 + crop)
+        p, l, m = isprs.dynamically_create_patches(scenes_a, labs_a, inst, crop, is_train=True)
+        G["gather_train_%d_p" % crop], G["gather_train_%d_l" % crop], G["gather_train_%d_m" % crop] = p, l, m
+        p, l, m = isprs.dynamically_create_patches(scenes_a, labs_a, inst, crop, is_train=False)
+        G["gather_eval_%d_p" % crop], G["gather_eval_%d_l" % crop] = p, l
+    mean = np.array([0.48, 0.51, 0.47, 0.5])
+    std = np.array([0.29, 0.28, 0.3, 0.27])
+    pn = G["gather_eval_9_p"].copy()
+    isprs.normalize_images(pn, mean, std)
+    G["norm_mean"], G["norm_std"], G["norm_out"] = mean, std, pn
+
+    # contest / coffee gathers (flip by shuffle-index range)
+    img, lab = synth_scene(rs, 50, 64, 3, 8, dtype=np.float32)       # labels 0..7, 7 = unlabelled
+    distr = [(0, 0), (10, 20), (41, 55), (45, 60), (30, 3)]
+    shuf = np.array([0, 6, 12, 3, 8, 14, 4, 9])
+    p, l, m = contest.dynamically_create_patches(img, lab, 11, distr, shuf, is_train=True)
+    G["contest_scene"], G["contest_labels"] = img, lab
+    G["contest_distr"], G["contest_shuf"] = np.array(distr), shuf
+    G["contest_gather_p"], G["contest_gather_l"], G["contest_gather_m"] = p, l, m
+    imgs = np.stack([synth_scene(rs, 40, 40, 3, 2, dtype=np.float32)[0] for _ in range(2)])
+    labsc = np.stack([synth_scene(rs, 40, 40, 3, 2)[1] for _ in range(2)])
+    cdistr = [(0, (0, 0)), (1, (33, 35)), (1, (5, 38)), (0, (20, 20))]
+    cshuf = np.array([0, 5, 10, 3, 7])
+    p, l = coffee.dynamically_create_patches(imgs, labsc, 9, cdistr, cshuf)
+    G["coffee_scenes"], G["coffee_labels"] = imgs, labsc
+    G["coffee_distr"] = np.array([(m_, xy[0], xy[1]) for m_, xy in cdistr])
+    G["coffee_shuf"] = cshuf
+    G["coffee_gather_p"], G["coffee_gather_l"] = p, l
+
+    # ---- 6. per-crop confusion --------------------------------------------------------
+    rs = np.random.RandomState(9)
+    true = rs.randint(0, 6, size=(3, 7, 7)).astype(np.int64)
+    pred = rs.randint(0, 5, size=(3, 7, 7)).astype(np.int64)
+    msk = rs.rand(3, 7, 7) > 0.3
+    track = np.zeros((6, 6), dtype=np.uint32)
+    acc, acc_norm, cm = isprs.calc_accuracy_by_crop(true, pred, track, msk)
+    G["cm_true"], G["cm_pred"], G["cm_mask"] = true, pred, msk
+    G["cm_out"], G["cm_acc"] = cm, np.array([acc, acc_norm], dtype=np.float64)
+    acc2, acc_norm2, cm2 = isprs.calc_accuracy_by_crop(true, pred, track, None)
+    G["cm_nomask_out"], G["cm_nomask_acc"] = cm2, np.array([acc2, acc_norm2], dtype=np.float64)
+    trackc = np.zeros((7, 7), dtype=np.uint32)
+    acc3, acc_norm3, cm3 = contest.calc_cccuracy_by_crop(true, pred, msk, trackc)
+    G["cm_contest_out"], G["cm_contest_acc"] = cm3, np.array([acc3, acc_norm3], dtype=np.float64)
+
+    # ---- 7. full-scene loops through a fake session ------------------------------------
+    captured = {}
+
+    def grab(a, b, **kw):
+        captured["pred"] = np.asarray(b).copy()
+        return 0.0
+
+    def grab_f1(a, b, average=None, **kw):
+        return np.zeros(6) if average is None else 0.0
+
+    # isprs.validate_test (isprs:1241-1344)
+    rs = np.random.RandomState(33)
+    img, lab = synth_scene(rs, 120, 150, 4, 6)
+    isprs.cohen_kappa_score, isprs.f1_score = grab, grab_f1
+    for crop, batch in ((25, 16), (30, 7)):
+        sess = FakeSession(4, 6)
+        with redirect_stdout(io.StringIO()):
+            isprs.validate_test(sess, np.asarray([img]), np.asarray([lab]), ["1"], batch, mean, std,
+                                "x", "y", "crop", "keep", "is_training", "pred_up", "logits", crop, 0, "")
+        G["vt_isprs_%d_labels" % crop] = captured["pred"].reshape(120, 150).astype(np.uint8)
+        G["vt_isprs_%d_log" % crop] = np.array(sess.log, dtype=np.float64)
+    G["vt_isprs_scene"], G["vt_isprs_gt"] = img, lab
+
+    # contest.test (contest:904-967) on a non-square scene -> exercises bug F10.
+    # The reference computes the batch count with py2 ``/`` (contest:919-920), a float under py3;
+    # shadow ``range`` in the module namespace so the loop runs with the intended integer.
+    img3, lab3 = synth_scene(rs, 130, 100, 3, 7, dtype=np.float32)
+    contest.cohen_kappa_score = lambda a, b, **kw: captured.__setitem__("pred", np.asarray(b).copy()) or 0.0
+    contest.f1_score = lambda a, b, **kw: 0.0
+    contest.range = lambda *a: range(*[int(v) for v in a])
+    sess = FakeSession(3, 7)
+    with redirect_stdout(io.StringIO()):
+        contest.test(sess, img3, lab3, mean[:3], std[:3], 16, "x", "y", "mask", "crop", "keep", "is_training",
+                     "pred_up", "logits", 0, 25, "")
+    G["vt_contest_scene"], G["vt_contest_gt"] = img3, lab3
+    G["vt_contest_labels"] = captured["pred"].reshape(130, 100).astype(np.uint8)
+    G["vt_contest_log"] = np.array(sess.log, dtype=np.float64)
+
+    # coffee.test (coffee:1032-1096), square tiles
+    imgs2 = np.stack([synth_scene(rs, 64, 64, 3, 2, dtype=np.float32)[0] for _ in range(2)])
+    labs2 = np.stack([synth_scene(rs, 64, 64, 3, 2)[1] for _ in range(2)])[..., None]
+    maps = []
+    coffee.save_map = lambda path, step, m: maps.append(np.asarray(m).copy())
+    coffee.range = lambda *a: range(*[int(v) for v in a])
+    coffee.cohen_kappa_score = lambda a, b, **kw: 0.0
+    coffee.f1_score = lambda a, b, **kw: 0.0
+    sess = FakeSession(3, 2)
+    try:
+        with redirect_stdout(io.StringIO()):
+            coffee.test(sess, imgs2, labs2, mean[:3], std[:3], 16, "x", "y", "crop", "keep", "is_training",
+                        "pred_up", "logits", 0, 25, "")
+    except Exception as e:  # metrics tail of coffee.test is py2-era; maps are captured before it
+        print("coffee.test tail raised (ignored):", type(e).__name__, e)
+    G["vt_coffee_scenes"], G["vt_coffee_gt"] = imgs2, labs2
+    G["vt_coffee_labels"] = np.stack(maps).astype(np.uint8)
+
+    # ---- 8. isprs.train loop through a fake session (policy + data path end to end) ----
+    rs = np.random.RandomState(44)
+    tr = [synth_scene(rs, 75, 100, 4, 6, block=25, cycle=True) for _ in range(2)]
+    te = [synth_scene(rs, 75, 100, 4, 6, block=25, cycle=True) for _ in range(1)]
+    tr_d, tr_l = np.asarray([a for a, _ in tr]), np.asarray([b for _, b in tr])
+    te_d, te_l = np.asarray([a for a, _ in te]), np.asarray([b for _, b in te])
+    G["train_scenes"], G["train_labels"] = tr_d, tr_l
+    G["test_scenes"], G["test_labels"] = te_d, te_l
+    cases = [("multi_fixed", [9, 13, 17], "loss"), ("uniform", [9, 14], "acc"),
+             ("multinomial", [9, 11, 17], "acc"), ("single_fixed", [11], "loss")]
+    cwd = os.getcwd()
+    for ci, (dist, values, upd) in enumerate(cases):
+        tmp = tempfile.mkdtemp()
+        os.chdir(tmp)
+        try:
+            np.random.seed(1000 + ci)
+            random.seed(2000 + ci)
+            with redirect_stdout(io.StringIO()):
+                tr_distr = isprs.create_distributions_over_classes(tr_l, crop_size=25, stride_crop=5)
+                te_distr = isprs.create_distributions_over_classes(te_l, crop_size=25, stride_crop=5)
+                rot = isprs.create_rotation_distribution(tr_distr)
+                mean_f, std_f = isprs.dynamically_calculate_mean_and_std(tr_d, tr_distr, crop_size=25)
+            n = len(values) if dist == "multi_fixed" else values[-1] - values[0] + 1
+            pal = np.zeros(n, dtype=np.float32)
+            occ = np.zeros(n, dtype=np.int32)
+            chosen = np.zeros(n, dtype=np.int32)
+            probs = isprs.define_multinomial_probs(values) if dist == "multinomial" else None
+            sess = FakeSession(4, 6)
+            tf.placeholder.side_effect = lambda *a, **k: object()
+            tf.Session.return_value.__enter__.return_value = sess
+            buf = io.StringIO()
+            try:
+                with redirect_stdout(buf):
+                    isprs.train(tr_d, tr_l, tr_distr, rot, te_d, te_l, te_distr, ["1"], 0.01, 4, 14, 0.005,
+                                mean_f, std_f, upd, dist, values,
+                                None if dist == "single_fixed" else pal,
+                                None if dist == "single_fixed" else occ,
+                                None if dist == "single_fixed" else chosen,
+                                probs, 20, tmp + "/", 50, "dilated_icpr_original", "vaihingen", "")
+            except TypeError as e:   # final validation() uses py2 ``/`` in range (isprs:1577-1578)
+                print("isprs.train tail raised (expected, py2 range):", e)
+            G["train_%d_log" % ci] = np.array(sess.log, dtype=np.float64)
+            G["train_%d_mean" % ci], G["train_%d_std" % ci] = mean_f, std_f
+            if dist != "single_fixed":
+                G["train_%d_pal" % ci] = np.load(tmp + "/patch_acc_loss_step_14.npy")
+                G["train_%d_occ" % ci] = np.load(tmp + "/patch_occur_step_14.npy")
+                G["train_%d_chosen" % ci] = np.load(tmp + "/patch_chosen_values_step_14.npy")
+        finally:
+            os.chdir(cwd)
+    G["train_cases"] = np.array([[DIST_ID[d], UPD_ID[u]] + v + [0] * (4 - len(v)) for d, v, u in cases], dtype=np.int64)
+
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    np.savez_compressed(OUT, **G)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes,", len(G), "arrays")
+
+
+VARIANT_ID = {"isprs": 0, "contest": 1, "coffee": 2}
+DIST_ID = {"single_fixed": 0, "multi_fixed": 1, "uniform": 2, "multinomial": 3}
+UPD_ID = {"acc": 0, "loss": 1}
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,215 @@
+"""GPU bring-up diagnostics: runs groups of checks in subprocesses (a trapped kernel must not take the
+other groups down) and prints per-case errors.  Usage on a GPU box:
+
+    python tools/gpu_diag.py [group ...]        groups: conv_simt conv_tc nets train scene
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def torch_conv(x, w, rate):
+    import torch
+    import torch.nn.functional as F
+    k = w.shape[0]
+    total = (k - 1) * rate
+    pb, pa = total // 2, total - total // 2
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2).double()
+    wt = torch.from_numpy(w).permute(3, 2, 0, 1).contiguous().double()
+    y = F.conv2d(F.pad(xt, (pb, pa, pb, pa)), wt, dilation=rate)
+    return y.permute(0, 2, 3, 1).contiguous().numpy()
+
+
+def act_np(v, act):
+    import numpy as np
+    if act == 1:
+        return np.maximum(v, 0)
+    if act == 2:
+        return np.maximum(0.1 * v, v)
+    return v
+
+
+def group_conv(prec):
+    import numpy as np
+    import drs_b200
+    s = drs_b200.Session("dilated_grsl", 4, 6, precision="fp32" if prec == "fp32" else prec)
+    rs = np.random.RandomState(0)
+    if prec == "fp32":
+        cases = [(2, 9, 3, 1, 4, 64), (1, 25, 5, 1, 4, 64), (3, 13, 4, 3, 64, 128), (2, 11, 4, 2, 32, 32),
+                 (1, 25, 3, 6, 128, 96), (2, 7, 5, 2, 5, 32)]
+    else:
+        cases = [(2, 9, 3, 1, 64, 64), (1, 25, 5, 2, 64, 64), (3, 13, 4, 3, 64, 128), (2, 11, 4, 4, 128, 128),
+                 (2, 25, 3, 5, 128, 256), (1, 25, 3, 6, 256, 256), (5, 7, 3, 8, 256, 256), (2, 25, 5, 2, 32, 32),
+                 (2, 17, 4, 3, 64, 64), (1, 33, 3, 5, 128, 192), (1, 30, 3, 7, 192, 256), (4, 25, 3, 6, 320, 128),
+                 (2, 12, 3, 1, 128, 160), (16, 25, 3, 4, 256, 256)]
+    ok = True
+    for (B, crop, k, rate, ci, co) in cases:
+        x = rs.randn(B, crop, crop, ci).astype(np.float32)
+        w = (rs.randn(k, k, ci, co) / np.sqrt(k * k * ci)).astype(np.float32)
+        scale = (0.5 + rs.rand(co)).astype(np.float32)
+        shift = rs.randn(co).astype(np.float32) * 0.1
+        act = int(rs.randint(0, 3))
+        if prec == "f16":
+            xr, wr = x.astype(np.float16).astype(np.float32), w.astype(np.float16).astype(np.float32)
+        elif prec == "bf16":
+            import torch
+            xr = torch.from_numpy(x).bfloat16().float().numpy()
+            wr = torch.from_numpy(w).bfloat16().float().numpy()
+        else:
+            xr, wr = x, w
+        ref = act_np(torch_conv(xr, wr, rate) * scale + shift, act)
+        t0 = time.time()
+        y = s.debug_conv(x, w, scale, shift, rate, act, prec)
+        err = float(np.abs(y - ref).max())
+        tol = 1e-4 if prec == "fp32" else (4e-3 if prec == "f16" else 3e-2)
+        good = err < tol
+        ok &= good
+        print("conv[%s] B%d c%d k%d r%d %d->%d act%d: max|err|=%.3e %s (%.1f ms)" %
+              (prec, B, crop, k, rate, ci, co, act, err, "ok" if good else "FAIL", 1e3 * (time.time() - t0)), flush=True)
+        if not good:
+            bad = np.argwhere(np.abs(y - ref) > tol)
+            print("   first bad idx", bad[:5].tolist(), "count", len(bad), "of", y.size)
+            print("   y", y[tuple(bad[0])], "ref", ref[tuple(bad[0])])
+    return ok
+
+
+def group_nets():
+    import numpy as np
+    import torch
+    import drs_b200
+    from oracle import nets_torch
+    ok = True
+    for net, C, K in (("dilated_icpr_original", 4, 6), ("dilated_grsl", 4, 6), ("dilated_icpr_rate6_densely", 5, 6),
+                      ("dilated_grsl_rate8", 5, 6), ("dilated_grsl", 3, 7), ("dilated_icpr_original", 3, 2)):
+        params = nets_torch.init_params(net, C, K, seed=3)
+        # non-trivial BN statistics
+        rs = np.random.RandomState(4)
+        for k in params:
+            if k.endswith("moving_mean"):
+                params[k] = (rs.randn(*params[k].shape) * 0.2).astype(np.float32)
+            if k.endswith("moving_variance"):
+                params[k] = (0.5 + rs.rand(*params[k].shape)).astype(np.float32)
+        scoped = {k.replace("main_conv", "conv") if net != "dilated_icpr_original" else k: v for k, v in params.items()}
+        orc = nets_torch.OracleNet(net, C, K, params)
+        for B, crop in ((3, 25), (2, 33), (5, 7)):
+            x = rs.randn(B, crop * crop * C).astype(np.float32)
+            pred_o, logits_o = orc.infer(torch.from_numpy(x), crop)
+            logits_o = logits_o.numpy()
+            for prec, tol in (("fp32", 2e-3), ("f16", 3e-2), ("bf16", 2e-1)):
+                s = drs_b200.Session(net, C, K, precision=prec)
+                s.load_variables(scoped)
+                pred, logits = s.infer(x, crop)
+                err = float(np.abs(logits - logits_o).max())
+                agree = float((pred == pred_o.numpy()).mean())
+                p_o = torch.softmax(torch.from_numpy(logits_o), -1).numpy()
+                p_g = torch.softmax(torch.from_numpy(logits), -1).numpy()
+                perr = float(np.abs(p_o - p_g).max())
+                good = err < tol
+                ok &= good
+                print("net %s C%d K%d B%d c%d [%s]: max|dlogit|=%.3e max|dprob|=%.3e argmax agree=%.5f %s" %
+                      (net, C, K, B, crop, prec, err, perr, agree, "ok" if good else "FAIL"), flush=True)
+                if not good and prec == "fp32":
+                    for scope, k_, r_, ci_, co_ in orc.plan:
+                        taps = {}
+                        orc.forward(torch.from_numpy(x), crop, False, taps=taps)
+                        a = s.debug_activation(scope, B, crop, co_)
+                        print("    %s: max|err|=%.3e" % (scope, float(np.abs(a - taps[scope].numpy()).max())))
+                s.close()
+    return ok
+
+
+def group_train():
+    import numpy as np
+    import torch
+    import drs_b200
+    from oracle import nets_torch
+    ok = True
+    for net, C, K, use_mask in (("dilated_icpr_original", 4, 6, False), ("dilated_grsl", 4, 6, False),
+                                ("dilated_icpr_rate6_densely", 5, 6, False), ("dilated_grsl_rate8", 3, 7, True)):
+        for prec, tol in (("fp32", 2e-3), ("bf16", 6e-2)):
+            params = nets_torch.init_params(net, C, K, seed=5)
+            orc = nets_torch.OracleNet(net, C, K, params)
+            s = drs_b200.Session(net, C, K, precision=prec, weight_decay=0.005, lr_initial=0.01)
+            s.load_variables(params)
+            rs = np.random.RandomState(6)
+            for step, (B, crop) in enumerate(((4, 13), (3, 17), (2, 25))):
+                x = rs.randn(B, crop * crop * C).astype(np.float32)
+                y = rs.randint(0, K, size=(B, crop * crop)).astype(np.float32)
+                mask = (rs.rand(B, crop * crop) > 0.3) if use_mask else None
+                lo, po, _ = orc.train_step(torch.from_numpy(x), torch.from_numpy(y), crop, 0.01, 0.005,
+                                           mask=None if mask is None else torch.from_numpy(mask))
+                lg, pg, cm, nc = s.train_step(x, y, crop, mask=mask, want_cm=True)
+                agree = float((pg == po.numpy()).mean())
+                # gradient check on a few variables
+                gerr = 0.0
+                for name in orc.trainable():
+                    if name.endswith("/weights"):
+                        g_o = orc.last_grads[name].numpy()
+                        if name != "conv_classifier/weights":
+                            pass
+                        g_g = s.get_gradient(name, g_o.shape)
+                        # oracle grads exclude nothing: autograd of (CE + L2) -> includes wd*W, as ours
+                        den = np.abs(g_o).max() + 1e-12
+                        gerr = max(gerr, float(np.abs(g_g - g_o).max() / den))
+                werr = 0.0
+                for name in ("conv_classifier/weights", orc.plan[0][0] + "/weights", orc.plan[-1][0] + "/weights",
+                             orc.plan[-1][0] + "/moving_mean", orc.plan[-1][0] + "/moving_variance"):
+                    w_o = orc.p[name].detach().numpy()
+                    w_g = s.get_variable(name, w_o.shape)
+                    werr = max(werr, float(np.abs(w_g - w_o).max()))
+                good = abs(lg - lo) < tol * max(1.0, abs(lo)) and gerr < (5e-3 if prec == "fp32" else 1.5e-1)
+                ok &= good
+                print("train %s [%s] step%d B%d c%d: loss %.6f vs %.6f  rel-grad-err %.3e  var-err %.3e  pred agree %.4f "
+                      "cm-sum %d correct %d %s" % (net, prec, step, B, crop, lg, lo, gerr, werr, agree, int(cm.sum()), nc,
+                                                   "ok" if good else "FAIL"), flush=True)
+            s.close()
+    return ok
+
+
+def group_scene():
+    import numpy as np
+    import torch
+    import drs_b200
+    from oracle import host_np
+    ok = True
+    rs = np.random.RandomState(8)
+    # accumulate + argmax against the NumPy loop, all variants incl. the contest offset bug
+    for variant, H, W, crop, batch, K in (("isprs", 120, 150, 25, 16, 6), ("isprs", 97, 131, 33, 7, 6),
+                                          ("contest", 130, 100, 25, 16, 7), ("contest", 100, 130, 25, 16, 7),
+                                          ("coffee", 64, 64, 25, 16, 2), ("isprs", 100, 100, 50, 4, 6)):
+        pos = drs_b200.grid_positions(H, W, crop, batch, variant)
+        ref_pos = np.array(host_np.all_patch_positions(H, W, crop, batch, variant), dtype=np.int32)
+        same = pos.shape == ref_pos.shape and bool((pos == ref_pos).all())
+        logits = rs.randn(len(pos), crop, crop, K).astype(np.float32)
+        s = drs_b200.Session("dilated_grsl", 3, K, precision="fp32")
+        lg = torch.from_numpy(logits).cuda()
+        labels, mean = s.accumulate_argmax(lg, pos, crop, H, W, want_mean=True)
+        ref_l, ref_m = host_np.accumulate_argmax(logits, ref_pos, H, W, crop, return_mean=True)
+        exact = bool((labels == ref_l).all()) and bool((mean == ref_m).all())
+        ok &= same and exact
+        print("accumulate %s %dx%d c%d b%d: positions %s, labels+mean bit-exact %s (P=%d)" %
+              (variant, H, W, crop, batch, same, exact, len(pos)), flush=True)
+        s.close()
+    return ok
+
+
+GROUPS = {"conv_simt": lambda: group_conv("fp32"), "conv_tc": lambda: group_conv("f16") & group_conv("bf16"),
+          "nets": group_nets, "train": group_train, "scene": group_scene}
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--run":
+        good = GROUPS[sys.argv[2]]()
+        print("GROUP %s: %s" % (sys.argv[2], "PASS" if good else "FAIL"))
+        sys.exit(0 if good else 1)
+    groups = sys.argv[1:] or list(GROUPS)
+    summary = {}
+    for g in groups:
+        t0 = time.time()
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--run", g], cwd=ROOT, timeout=900)
+        summary[g] = {"rc": r.returncode, "s": round(time.time() - t0, 1)}
+    print(json.dumps(summary))
