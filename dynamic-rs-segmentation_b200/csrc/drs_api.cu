@@ -99,6 +99,9 @@ struct HandleExtra {
   // profiling
   double conv_flops = 0;
   int64_t conv_launches = 0;
+  // DRS_DEBUG_KEEP=1: fp32 copies of backward intermediates ("dz:<scope>", "da:<scope>")
+  std::vector<float*> keep;
+  bool debug_keep = false;
 };
 static std::map<Handle*, HandleExtra*> g_extra;
 static HandleExtra* X(Handle* h) { return g_extra[h]; }
@@ -549,6 +552,26 @@ extern "C" int drs_forward_host(drs_handle_t h, const float* x_host, int32_t B, 
   int rc = drs_synchronize(h);
   if (rc) return rc;
   API_END
+}
+
+template <typename T>
+static void debug_keep(Handle* h, const std::string& name, const T* ptr, int cs, int co, int C, int64_t M) {
+  HandleExtra* x = X(h);
+  if (!x->debug_keep) return;
+  float* buf = nullptr;
+  CUDA_CHECK(cudaMalloc(&buf, M * C * 4));
+  x->keep.push_back(buf);
+  slice_to_f32_kernel<T><<<nblk(M * C, 256), 256, 0, h->stream>>>(ptr, cs, co, C, M, buf);
+  LAUNCH_CHECK(h);
+  h->taps[name] = {buf, ET_F32, C, 0, C, M};
+}
+static void debug_keep_reset(Handle* h) {
+  HandleExtra* x = X(h);
+  x->debug_keep = getenv("DRS_DEBUG_KEEP") != nullptr;
+  if (x->keep.empty()) return;
+  cudaStreamSynchronize(h->stream);
+  for (float* p : x->keep) cudaFree(p);
+  x->keep.clear();
 }
 
 #include "drs_train.cuh"

@@ -15,8 +15,9 @@ __global__ void unpack_extras_kernel(const float* __restrict__ src, float* __res
 __global__ void add2_kernel(const float* __restrict__ a, float* __restrict__ out) { out[2] = a[0] + a[1]; }
 
 template <typename TA>
-static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev, int B, int crop,
-                         float* loss_host, uint8_t* pred_out_dev, uint32_t* cm_out_dev) {
+static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
+                         const uint8_t* acc_mask_dev, int B, int crop, float* loss_host, uint8_t* pred_out_dev,
+                         uint32_t* cm_out_dev) {
   NetDesc& n = h->net;
   HandleExtra* x = X(h);
   const int L = (int)n.convs.size();
@@ -85,6 +86,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   float* part_w = (float*)arena_take(h, max_w * 4 * max_splits);
   float* part_l2 = (float*)arena_take(h, (size_t)nb_opt * 4);
   h->taps.clear();
+  debug_keep_reset(h);
 
   CUDA_CHECK(cudaMemsetAsync(h->grads, 0, (n.n_trainable + 1024) * 4, h->stream));
   const double bn_count = (double)M * (h->sync_bn ? h->world : 1);
@@ -139,7 +141,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   double count = (double)M;
   if (mask_dev) {
     CUDA_CHECK(cudaMemsetAsync(x->count_dev, 0, 4, h->stream));
-    mask_count_kernel<<<std::min<int64_t>(ceil_div(M, 256), 1024), 256, 0, h->stream>>>(mask_dev, M, x->count_dev);
+    mask_count_kernel<<<(unsigned)std::min<int64_t>(ceil_div(M, 256), 1024), 256, 0, h->stream>>>(mask_dev, M, x->count_dev);
     LAUNCH_CHECK(h);
     unsigned int cnt = 0;
     CUDA_CHECK(cudaMemcpyAsync(&cnt, x->count_dev, 4, cudaMemcpyDeviceToHost, h->stream));
@@ -163,7 +165,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   LAUNCH_CHECK(h);
   // fused calc_accuracy_by_crop (isprs:510-531)
   CUDA_CHECK(cudaMemsetAsync(x->cm_dev, 0, (K * K + 1) * 4, h->stream));
-  confusion_kernel<<<std::min<int64_t>(ceil_div(M, 256), (int64_t)h->sm_count * 4), 256, 0, h->stream>>>(labels_u8, pred, mask_dev, M, K, -1, x->cm_dev);
+  confusion_kernel<<<(unsigned)std::min<int64_t>(ceil_div(M, 256), (int64_t)h->sm_count * 4), 256, 0, h->stream>>>(labels_u8, pred, acc_mask_dev ? acc_mask_dev : mask_dev, M, K, -1, x->cm_dev);
   LAUNCH_CHECK(h);
 
   // ---------------------------------------------------------------- backward
@@ -203,6 +205,8 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     bn_bwd_apply_kernel<TA, TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, x->sums,
                                                                                    1.0 / bn_count, n.act, DZ, c.co, 0, c.co, M);
     LAUNCH_CHECK(h);
+    debug_keep<TA>(h, "da:" + c.scope, (const TA*)dA.p, dA.cs, dA.co, c.co, M);
+    debug_keep<TA>(h, "dz:" + c.scope, DZ, c.co, 0, c.co, M);
     // wgrad (bias gradient is identically zero behind a BN without beta: sum_m dZ = 0)
     ActBuf xin = input_of(l);
     if (l == 0) {
@@ -253,47 +257,51 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   }
 }
 
-static void train_step(Handle* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev, int B, int crop,
-                       float* loss_host, uint8_t* pred_dev, uint32_t* cm_dev) {
+static void train_step(Handle* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
+                       const uint8_t* acc_mask_dev, int B, int crop, float* loss_host, uint8_t* pred_dev, uint32_t* cm_dev) {
   DRS_CHECK(B >= 1 && crop >= 3 && crop <= 256, "train_step: bad B=%d crop=%d", B, crop);
   switch (act_type(h)) {
-    case ET_F32: train_step_t<float>(h, x_dev, y_dev, mask_dev, B, crop, loss_host, pred_dev, cm_dev); break;
-    case ET_BF16: train_step_t<__nv_bfloat16>(h, x_dev, y_dev, mask_dev, B, crop, loss_host, pred_dev, cm_dev); break;
+    case ET_F32: train_step_t<float>(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, loss_host, pred_dev, cm_dev); break;
+    case ET_BF16: train_step_t<__nv_bfloat16>(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, loss_host, pred_dev, cm_dev); break;
     default:
       DRS_FAIL("train_step: precision F16 is inference-only (gradients underflow in fp16); create the handle with DRS_PREC_BF16 or DRS_PREC_FP32");
   }
 }
 
-extern "C" int drs_train_step_dev(drs_handle_t h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev, int32_t B,
-                                  int32_t crop, float* loss_out_host, uint8_t* pred_dev, uint32_t* cm_dev) {
+extern "C" int drs_train_step_dev(drs_handle_t h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
+                                  const uint8_t* acc_mask_dev, int32_t B, int32_t crop, float* loss_out_host, uint8_t* pred_dev,
+                                  uint32_t* cm_dev) {
   API_BEGIN
   DRS_CHECK(h && x_dev && y_dev, "null argument");
   CUDA_CHECK(cudaSetDevice(h->cfg.device));
-  train_step(h, x_dev, y_dev, mask_dev, B, crop, loss_out_host, pred_dev, cm_dev);
+  train_step(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, loss_out_host, pred_dev, cm_dev);
   API_END
 }
 
-extern "C" int drs_train_step_host(drs_handle_t h, const float* x_host, const float* y_host, const uint8_t* mask_host, int32_t B,
-                                   int32_t crop, float* loss_out, int64_t* pred_host, uint32_t* cm_host) {
+extern "C" int drs_train_step_host(drs_handle_t h, const float* x_host, const float* y_host, const uint8_t* mask_host,
+                                   const uint8_t* acc_mask_host, int32_t B, int32_t crop, float* loss_out, int64_t* pred_host,
+                                   uint32_t* cm_host) {
   API_BEGIN
   DRS_CHECK(h && x_host && y_host, "null argument");
   CUDA_CHECK(cudaSetDevice(h->cfg.device));
   const int64_t M = (int64_t)B * crop * crop;
   const int C = h->net.channels, K = h->net.classes;
   const size_t xb = round_up((size_t)M * C * 4, 256), yb = round_up((size_t)M * 4, 256), mb = round_up((size_t)M, 256);
-  ensure_dstage(h, xb + yb + mb + (size_t)M * 9 + 4096 + 1024);
+  ensure_dstage(h, xb + yb + 2 * mb + (size_t)M * 9 + 4096 + 1024);
   char* d = (char*)h->dstage;
   float* x_dev = (float*)d;
   float* y_dev = (float*)(d + xb);
   uint8_t* m_dev = (uint8_t*)(d + xb + yb);
-  long long* p64 = (long long*)(d + xb + yb + mb);
+  uint8_t* am_dev = (uint8_t*)(d + xb + yb + mb);
+  long long* p64 = (long long*)(d + xb + yb + 2 * mb);
   uint8_t* p8 = (uint8_t*)(p64 + M);
-  uint32_t* cm_dev = (uint32_t*)(d + xb + yb + mb + round_up((size_t)M * 9, 256));
+  uint32_t* cm_dev = (uint32_t*)(d + xb + yb + 2 * mb + round_up((size_t)M * 9, 256));
   CUDA_CHECK(cudaMemcpyAsync(x_dev, x_host, (size_t)M * C * 4, cudaMemcpyHostToDevice, h->stream));
   CUDA_CHECK(cudaMemcpyAsync(y_dev, y_host, (size_t)M * 4, cudaMemcpyHostToDevice, h->stream));
   if (mask_host) CUDA_CHECK(cudaMemcpyAsync(m_dev, mask_host, (size_t)M, cudaMemcpyHostToDevice, h->stream));
+  if (acc_mask_host) CUDA_CHECK(cudaMemcpyAsync(am_dev, acc_mask_host, (size_t)M, cudaMemcpyHostToDevice, h->stream));
   float loss = 0.0f;
-  train_step(h, x_dev, y_dev, mask_host ? m_dev : nullptr, B, crop, &loss, p8, cm_dev);
+  train_step(h, x_dev, y_dev, mask_host ? m_dev : nullptr, acc_mask_host ? am_dev : nullptr, B, crop, &loss, p8, cm_dev);
   if (pred_host) {
     widen_u8_i64_kernel<<<nblk(M, 256), 256, 0, h->stream>>>(p8, p64, M);
     LAUNCH_CHECK(h);

@@ -1,0 +1,352 @@
+"""Host-side mirror of the reference's L2/L3 logic: batch selection, patch-size
+policy, augmentation decisions, instance sampling.  Same function names, argument meaning and RNG
+consumption as the reference scripts, so that a run seeded like the reference draws the same patch sizes,
+batches and augmentations (bit-exact; pinned by tests/golden/host_golden.npz).
+
+What is NOT here: anything that touches pixels every step.  Patch gathering, normalisation, the network,
+the loss, the per-crop confusion matrix, overlap accumulation and argmax run in libdrs.so on the GPU
+(``Session``).  The only per-pixel host work left is the nearest-neighbour rotation of the ~50 % of isprs
+training patches that the reference rotates with ``scipy.ndimage.rotate`` (row N1 of SURVEY.md section 8f).
+"""
+import math
+import random
+
+import numpy as np
+
+FLIP_NONE, FLIP_UD, FLIP_LR = 0, 1, 2
+
+
+class BatchColors:      # isprs:20-28
+    HEADER = '\033[95m'
+    OKBLUE = '\033[94m'
+    OKGREEN = '\033[92m'
+    WARNING = '\033[93m'
+    FAIL = '\033[91m'
+    ENDC = '\033[0m'
+    BOLD = '\033[1m'
+    UNDERLINE = '\033[4m'
+
+
+# ------------------------------------------------------------------------------------------------
+# policy (L3) -- isprs:46-71, 549-608, 1727-1737, 1757-1763
+# ------------------------------------------------------------------------------------------------
+def select_batch(shuffle, batch_size, it, total_size):
+    """isprs:46-58: epoch shuffle with wrap-around refill (python ``random`` stream)."""
+    batch = shuffle[it:min(it + batch_size, total_size)]
+    if min(it + batch_size, total_size) == total_size or total_size == it + batch_size:
+        shuffle = np.asarray(random.sample(range(total_size), total_size))
+        it = 0
+        if len(batch) < batch_size:
+            diff = batch_size - len(batch)
+            batch = np.concatenate((batch, shuffle[it:it + diff]))
+            it = diff
+    else:
+        it += batch_size
+    return shuffle, batch, it
+
+
+def define_multinomial_probs(values, dif_prob=2):
+    """isprs:61-71: listed sizes get dif_prob/interval each, the rest share the remainder."""
+    interval_size = values[-1] - values[0] + 1
+    general_prob = 1.0 / float(interval_size)
+    max_prob = general_prob * dif_prob
+    probs = np.full(interval_size, (1.0 - max_prob * len(values)) / float(interval_size - len(values)))
+    for i in range(len(values)):
+        probs[values[i] - values[0]] = max_prob
+    return probs
+
+
+def init_score_arrays(distribution_type, values, occur_init=0):
+    """isprs:2054-2064 (zeros); contest starts patch_occur at ones (contest:1275-1279)."""
+    if distribution_type == 'multi_fixed':
+        n = len(values)
+    elif distribution_type in ('uniform', 'multinomial'):
+        n = values[-1] - values[0] + 1
+    else:
+        return None, None, None
+    patch_acc_loss = np.zeros(n, dtype=np.float32)
+    patch_occur = np.full(n, occur_init, dtype=np.int32)
+    patch_chosen_values = np.zeros(n, dtype=np.int32)
+    return patch_acc_loss, patch_occur, patch_chosen_values
+
+
+def draw_patch_size(distribution_type, values, probs=None):
+    """isprs:1727-1737: one draw from the legacy global ``np.random`` stream.  -> (size, index|None)"""
+    if distribution_type == 'multi_fixed':
+        cur_size_int = np.random.randint(len(values))
+        return int(values[cur_size_int]), cur_size_int
+    if distribution_type == 'uniform':
+        cur_patch_size = int(np.random.uniform(values[0], values[-1] + 1, 1)[0])
+        return cur_patch_size, cur_patch_size - values[0]
+    if distribution_type == 'multinomial':
+        cur_size_int = np.random.multinomial(1, probs).argmax()
+        return values[0] + cur_size_int, cur_size_int
+    if distribution_type == 'single_fixed':
+        return int(values[0]), None
+    raise ValueError('distribution_type ' + str(distribution_type))
+
+
+def update_scores(patch_acc_loss, patch_occur, cur_size_int, update_type, batch_loss, acc_norm, loss_scale=1.0):
+    """isprs:1757-1763 (loss_scale = epoch_counter/10.0) / contest:1091-1094, coffee:1302-1307 (loss_scale = 1)."""
+    patch_acc_loss[cur_size_int] += (batch_loss * loss_scale if update_type == 'loss' else acc_norm)
+    patch_occur[cur_size_int] += 1
+
+
+def select_best_patch_size(distribution_type, values, patch_acc_loss, patch_occur, is_loss_or_acc='acc',
+                           patch_chosen_values=None, debug=False):
+    """isprs:549-608.  Mutates patch_occur (0 -> 1) and patch_chosen_values in place like the reference."""
+    patch_occur[np.where(patch_occur == 0)] = 1
+    patch_mean = patch_acc_loss / patch_occur
+    cur_patch_val = None
+    if is_loss_or_acc == 'acc':
+        argmax_acc = np.argmax(patch_mean)
+        if distribution_type == 'multi_fixed':
+            cur_patch_val = int(values[argmax_acc])
+        elif distribution_type in ('uniform', 'multinomial'):
+            cur_patch_val = values[0] + argmax_acc
+        if patch_chosen_values is not None:
+            patch_chosen_values[int(argmax_acc)] += 1
+        if debug:
+            print('patch_acc_loss', patch_acc_loss)
+            print('patch_occur', patch_occur)
+            print('patch_mean', patch_mean)
+            print('argmax_acc', argmax_acc)
+            print('specific', argmax_acc, patch_acc_loss[argmax_acc], patch_occur[argmax_acc], patch_mean[argmax_acc])
+    elif is_loss_or_acc == 'loss':
+        arg_sort_out = np.argsort(patch_mean)
+        if debug:
+            print('patch_acc_loss', patch_acc_loss)
+            print('patch_occur', patch_occur)
+            print('patch_mean', patch_mean)
+            print('arg_sort_out', arg_sort_out)
+        n = len(values) if distribution_type == 'multi_fixed' else values[-1] - values[0] + 1
+        for i in range(n):
+            if patch_occur[arg_sort_out[i]] > 0:
+                if distribution_type == 'multi_fixed':
+                    cur_patch_val = int(values[arg_sort_out[i]])
+                else:
+                    cur_patch_val = values[0] + arg_sort_out[i]
+                if patch_chosen_values is not None:
+                    patch_chosen_values[arg_sort_out[i]] += 1
+                if debug:
+                    print('specific', arg_sort_out[i], patch_acc_loss[arg_sort_out[i]], patch_occur[arg_sort_out[i]],
+                          patch_mean[arg_sort_out[i]])
+                break
+    if debug:
+        print('Current patch size ', cur_patch_val)
+        if patch_chosen_values is not None:
+            print('Distr of chosen sizes ', patch_chosen_values)
+    return cur_patch_val
+
+
+def acc_norm_from_cm(cm, num_classes):
+    """Tail of calc_accuracy_by_crop (isprs:526-529): mean per-class recall, divisor always K."""
+    _sum = 0.0
+    for i in range(num_classes):
+        s = np.sum(cm[i])
+        _sum += (cm[i][i] / float(s) if s != 0 else 0)
+    return _sum / float(num_classes)
+
+
+# ------------------------------------------------------------------------------------------------
+# one-off set-up (C13/C14 of SURVEY.md section 2): kept on the host, reference semantics
+# ------------------------------------------------------------------------------------------------
+def shift_back(cur_x, cur_y, crop_size, h, w):
+    """Border rule of every gather in the reference (isprs:259-269): a window that sticks out is moved back."""
+    len_x = max(0, min(cur_x + crop_size, h) - cur_x)
+    len_y = max(0, min(cur_y + crop_size, w) - cur_y)
+    if len_x != crop_size:
+        cur_x = cur_x - (crop_size - len_x)
+    if len_y != crop_size:
+        cur_y = cur_y - (crop_size - len_y)
+    return cur_x, cur_y
+
+
+def create_distributions_over_classes(labels, crop_size, stride_crop, num_classes, verbose=True):
+    """isprs:448-483: (map, x, y) of every reference-size window, bucketed by its majority class."""
+    classes = [[] for _ in range(num_classes)]
+    for k in range(len(labels)):
+        w, h = labels[k].shape
+        for i in range(0, w, stride_crop):
+            for j in range(0, h, stride_crop):
+                cur_x, cur_y = shift_back(i, j, crop_size, w, h)
+                patch_class = labels[k][cur_x:cur_x + crop_size, cur_y:cur_y + crop_size]
+                if patch_class.shape != (crop_size, crop_size):
+                    raise ValueError("Error create_distributions_over_classes: Current patch size is " +
+                                     str(len(patch_class)) + "x" + str(len(patch_class[0])))
+                count = np.bincount(patch_class.astype(int).flatten())
+                classes[int(np.argmax(count))].append((k, cur_x, cur_y))
+    if verbose:
+        for i in range(len(classes)):
+            print(BatchColors.OKBLUE + 'Class ' + str(i + 1) + ' has length ' + str(len(classes[i])) + BatchColors.ENDC)
+    return classes
+
+
+def create_rotation_distribution(training_class_distribution, verbose=True):
+    """isprs:486-496: one angle in [0,360) per instance (np.random stream)."""
+    rotation = [None] * len(training_class_distribution)
+    for i in range(len(training_class_distribution)):
+        rotation[i] = np.random.randint(0, 360, size=len(training_class_distribution[i]))
+    if verbose:
+        for i in range(len(training_class_distribution)):
+            print(BatchColors.OKBLUE + 'Class ' + str(i + 1) + ' has length ' + str(len(training_class_distribution[i])) +
+                  ' and rotation length ' + str(len(rotation[i])) + BatchColors.ENDC)
+    return rotation
+
+
+def select_super_batch_instances(class_distribution, rotation_distribution=None, batch_size=100, super_batch=500):
+    """isprs:403-445: class-balanced draw of batch_size*super_batch (map, x, y, rot) instances."""
+    instances = []
+    overall_count = 0
+    samples_per_class = int((batch_size * super_batch) / len(class_distribution))
+    for i in range(len(class_distribution)):
+        n = len(class_distribution[i])
+        shuffle = np.asarray(random.sample(range(n), (samples_per_class if n >= samples_per_class else n)))
+        for j in shuffle:
+            cur_map, cur_x, cur_y = class_distribution[i][j][0], class_distribution[i][j][1], class_distribution[i][j][2]
+            cur_rot = (rotation_distribution[i][j] if (rotation_distribution is not None) else 0)
+            instances.append((cur_map, cur_x, cur_y, cur_rot))
+            overall_count += 1
+    if overall_count != (batch_size * super_batch):
+        lack = (batch_size * super_batch) - overall_count
+        for i in range(lack):
+            rand_class = np.random.randint(len(class_distribution))
+            rand_map = np.random.randint(len(class_distribution[rand_class]))
+            cur_map = class_distribution[rand_class][rand_map][0]
+            cur_x = class_distribution[rand_class][rand_map][1]
+            cur_y = class_distribution[rand_class][rand_map][2]
+            cur_rot = (rotation_distribution[rand_class][rand_map] if (rotation_distribution is not None) else 0)
+            instances.append((cur_map, cur_x, cur_y, cur_rot))
+            overall_count += 1
+    assert overall_count == (batch_size * super_batch), "Could not select ALL instances"
+    return np.asarray(instances)
+
+
+def compute_image_mean(data):
+    """isprs:84-88: mean over everything per channel; std across patches at pixel (0,0) only."""
+    mean_full = np.mean(np.mean(np.mean(data, axis=0), axis=0), axis=0)
+    std_full = np.std(data, axis=0, ddof=1)[0, 0, :]
+    return mean_full, std_full
+
+
+def dynamically_calculate_mean_and_std(data, indexes, crop_size):
+    """isprs:151-184: chunked (5000 patches) mean/std over all reference-crop windows."""
+    total = []
+    for cls in indexes:
+        total = total + list(cls)
+    mean_full, std_full, all_patches = [], [], []
+    for i in range(len(total)):
+        cur_map, cur_x, cur_y = total[i][0], total[i][1], total[i][2]
+        all_patches.append(data[cur_map][cur_x:cur_x + crop_size, cur_y:cur_y + crop_size, :])
+        if i > 0 and i % 5000 == 0:
+            mean, std = compute_image_mean(np.asarray(all_patches))
+            mean_full.append(mean)
+            std_full.append(std)
+            all_patches = []
+    mean, std = compute_image_mean(np.asarray(all_patches))
+    mean_full.append(mean)
+    std_full.append(std)
+    return np.mean(mean_full, axis=0), np.mean(std_full, axis=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-step augmentation plan (decisions on the host, pixels on the GPU)
+# ------------------------------------------------------------------------------------------------
+class BatchPlan:
+    """What ``dynamically_create_patches`` decided for one batch; consumed by Session.gather_dev."""
+    __slots__ = ("inst", "flips", "noise", "noise_on", "over_x", "over_y", "over_on", "acc_mask", "crop")
+
+
+def plan_isprs_batch(data, mask_data, training_instances_batch, crop_size, is_train=True):
+    """isprs:245-334.  Consumes np.random exactly like the reference, per patch:
+    randint(0,2) rotate?  randint(0,2) noise? (+ normal(0,0.01,shape) if yes)  randint(0,3) flip.
+    Rotated patches (scipy nearest-neighbour, isprs:294-296) are produced here and handed to the gather as
+    overrides; every other patch is cut from the HBM-resident scene by the gather kernel."""
+    import scipy.ndimage
+    B = len(training_instances_batch)
+    C = data[0].shape[-1]
+    p = BatchPlan()
+    p.crop = crop_size
+    p.inst = np.zeros((B, 3), dtype=np.int32)
+    p.flips = np.zeros(B, dtype=np.uint8)
+    p.noise_on = np.zeros(B, dtype=np.uint8)
+    p.over_on = np.zeros(B, dtype=np.uint8)
+    p.noise = None
+    p.over_x = None
+    p.over_y = None
+    p.acc_mask = None
+    for i in range(B):
+        cur_map = int(training_instances_batch[i][0])
+        h, w = data[cur_map].shape[0], data[cur_map].shape[1]
+        cur_x, cur_y = shift_back(int(training_instances_batch[i][1]), int(training_instances_batch[i][2]), crop_size, h, w)
+        if cur_x < 0 or cur_y < 0 or cur_x + crop_size > h or cur_y + crop_size > w:
+            raise ValueError(BatchColors.FAIL + "Error: Current PATCH size is " + str(min(h, crop_size)) + "x" +
+                             str(min(w, crop_size)) + BatchColors.ENDC)
+        p.inst[i] = (cur_map, cur_x, cur_y)
+        if not is_train:
+            continue
+        cur_rot = training_instances_batch[i][3]
+        possible_rotation = np.random.randint(0, 2)
+        if possible_rotation == 1:
+            if p.over_x is None:
+                p.over_x = np.zeros((B, crop_size, crop_size, C), dtype=np.float64)
+                p.over_y = np.zeros((B, crop_size, crop_size), dtype=np.uint8)
+                p.acc_mask = np.ones((B, crop_size, crop_size), dtype=np.uint8)
+            cur_patch = data[cur_map][cur_x:cur_x + crop_size, cur_y:cur_y + crop_size, :]
+            cur_mask_patch = mask_data[cur_map][cur_x:cur_x + crop_size, cur_y:cur_y + crop_size]
+            p.over_x[i] = scipy.ndimage.rotate(cur_patch, cur_rot, order=0, reshape=False)
+            p.over_y[i] = scipy.ndimage.rotate(cur_mask_patch, cur_rot, order=0, reshape=False)
+            p.acc_mask[i] = scipy.ndimage.rotate(np.ones((crop_size, crop_size), dtype=bool), cur_rot, order=0,
+                                                 reshape=False)
+            p.over_on[i] = 1
+        possible_noise = np.random.randint(0, 2)
+        if possible_noise == 1:
+            if p.noise is None:
+                p.noise = np.zeros((B, crop_size, crop_size, C), dtype=np.float64)
+            p.noise[i] = np.random.normal(0, 0.01, (crop_size, crop_size, C))
+            p.noise_on[i] = 1
+        possible_flip = np.random.randint(0, 3)
+        p.flips[i] = (FLIP_NONE, FLIP_UD, FLIP_LR)[possible_flip]     # isprs:304-318
+    # the accuracy mask is flipped together with the patch (isprs:308-317)
+    if p.acc_mask is not None:
+        for i in range(B):
+            if p.flips[i] == FLIP_UD:
+                p.acc_mask[i] = np.flipud(p.acc_mask[i])
+            elif p.flips[i] == FLIP_LR:
+                p.acc_mask[i] = np.fliplr(p.acc_mask[i])
+    return p
+
+
+def plan_index_flip_batch(class_distribution, shuffle_batch, crop_size, shapes, with_map=False):
+    """contest:192-254 / coffee:241-293: flip encoded by the shuffle index range
+    [0,N) none, [N,2N) fliplr, [2N,3N) flipud; window start shifted back at the border (negative-offset slices)."""
+    n = len(class_distribution)
+    B = len(shuffle_batch)
+    p = BatchPlan()
+    p.crop = crop_size
+    p.inst = np.zeros((B, 3), dtype=np.int32)
+    p.flips = np.zeros(B, dtype=np.uint8)
+    p.noise = p.noise_on = p.over_x = p.over_y = p.over_on = p.acc_mask = None
+    for b, i in enumerate(shuffle_batch):
+        i = int(i)
+        if i >= 2 * n:
+            cur_pos, flip = i - 2 * n, FLIP_UD
+        elif i >= n:
+            cur_pos, flip = i - n, FLIP_LR
+        else:
+            cur_pos, flip = i, FLIP_NONE
+        if with_map:      # coffee: (map, (x, y))
+            cur_map = int(class_distribution[cur_pos][0])
+            cur_x, cur_y = int(class_distribution[cur_pos][1][0]), int(class_distribution[cur_pos][1][1])
+        else:             # contest: (x, y), single scene
+            cur_map = 0
+            cur_x, cur_y = int(class_distribution[cur_pos][0]), int(class_distribution[cur_pos][1])
+        h, w = shapes[cur_map]
+        cur_x, cur_y = shift_back(cur_x, cur_y, crop_size, h, w)
+        p.inst[b] = (cur_map, cur_x, cur_y)
+        p.flips[b] = flip
+    return p
+
+
+def sliding_stride(crop_size):
+    return int(math.floor(crop_size / 2.0))       # isprs:1243

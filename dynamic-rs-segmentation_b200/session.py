@@ -138,7 +138,7 @@ class Session:
         L.check(self._lib.drs_forward_host(self._h, L.ptr(x), B, crop, L.ptr(logits), L.ptr(pred)))
         return pred, logits
 
-    def train_step(self, x, y, crop, mask=None, want_cm=False):
+    def train_step(self, x, y, crop, mask=None, want_cm=False, acc_mask=None):
         """(loss fp32, pred_up int64 [B,crop,crop][, cm uint32 [K,K], n_correct])  -- isprs:1750-1752."""
         x = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
         y = np.ascontiguousarray(np.asarray(y, dtype=np.float32))
@@ -148,11 +148,14 @@ class Session:
         m = None
         if mask is not None:
             m = np.ascontiguousarray(np.asarray(mask).astype(np.uint8))
+        am = None
+        if acc_mask is not None:
+            am = np.ascontiguousarray(np.asarray(acc_mask).astype(np.uint8))
         pred = np.empty((B, crop, crop), dtype=np.int64)
         K = self.num_classes
         cm = np.zeros(K * K + 1, dtype=np.uint32)
         loss = C.c_float()
-        L.check(self._lib.drs_train_step_host(self._h, L.ptr(x), L.ptr(y), L.ptr(m), B, crop, C.byref(loss),
+        L.check(self._lib.drs_train_step_host(self._h, L.ptr(x), L.ptr(y), L.ptr(m), L.ptr(am), B, crop, C.byref(loss),
                                               L.ptr(pred), L.ptr(cm)))
         if want_cm:
             return np.float32(loss.value), pred, cm[:K * K].reshape(K, K).copy(), int(cm[K * K])
@@ -162,9 +165,10 @@ class Session:
     def infer_dev(self, x_dev, B, crop, logits_dev=None, pred_dev=None):
         L.check(self._lib.drs_forward_dev(self._h, L.ptr(x_dev), B, crop, L.ptr(logits_dev), L.ptr(pred_dev)))
 
-    def train_step_dev(self, x_dev, y_dev, B, crop, mask_dev=None, pred_dev=None, cm_dev=None, want_loss=True):
+    def train_step_dev(self, x_dev, y_dev, B, crop, mask_dev=None, pred_dev=None, cm_dev=None, want_loss=True,
+                       acc_mask_dev=None):
         loss = C.c_float()
-        L.check(self._lib.drs_train_step_dev(self._h, L.ptr(x_dev), L.ptr(y_dev), L.ptr(mask_dev), B, crop,
+        L.check(self._lib.drs_train_step_dev(self._h, L.ptr(x_dev), L.ptr(y_dev), L.ptr(mask_dev), L.ptr(acc_mask_dev), B, crop,
                                              C.byref(loss) if want_loss else None, L.ptr(pred_dev), L.ptr(cm_dev)))
         return np.float32(loss.value) if want_loss else None
 

@@ -100,12 +100,16 @@ int drs_forward_dev(drs_handle_t h, const float* x_dev, int32_t B, int32_t crop,
  *   mask  [B, crop*crop] 0/1 bytes or NULL (contest boolean_mask, contest:886-888)
  *   loss  CE mean (+mask) + sum wd*l2_loss(W), with pre-update weights (isprs:1089-1099)
  *   pred  argmax of the same train-mode forward
- *   cm    K*K uint32 confusion counts + [K*K] = #correct, of (y, pred) over masked pixels
- *         (calc_accuracy_by_crop, isprs:510-531) -- fused so that the host loop disappears; may be NULL */
+ *   cm    K*K uint32 confusion counts + [K*K] = #correct, of (y, pred)
+ *         (calc_accuracy_by_crop, isprs:510-531) -- fused so that the host loop disappears; may be NULL.
+ *         Counted over acc_mask when given (isprs b_mask: False in the corners of rotated patches,
+ *         isprs:285-296, 1754), else over mask, else over every pixel. */
 int drs_train_step_host(drs_handle_t h, const float* x_host, const float* y_host, const uint8_t* mask_host,
-                        int32_t B, int32_t crop, float* loss_out, int64_t* pred_host, uint32_t* cm_host);
+                        const uint8_t* acc_mask_host, int32_t B, int32_t crop, float* loss_out, int64_t* pred_host,
+                        uint32_t* cm_host);
 int drs_train_step_dev(drs_handle_t h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
-                       int32_t B, int32_t crop, float* loss_out_host, uint8_t* pred_dev, uint32_t* cm_dev);
+                       const uint8_t* acc_mask_dev, int32_t B, int32_t crop, float* loss_out_host, uint8_t* pred_dev,
+                       uint32_t* cm_dev);
 
 /* Data-parallel exchange hook: called on the handle's stream order with a device buffer that must be
  * summed over ranks in place (flat gradients ++ loss numerator ++ confusion counts; and, when

@@ -109,7 +109,7 @@ class OracleNet:
             return torch.relu(x)
         return torch.maximum(0.1 * x, x)                   # isprs:620-621
 
-    def forward(self, x_flat, crop, is_training, p=None, update_stats=True, taps=None):
+    def forward(self, x_flat, crop, is_training, p=None, update_stats=True, taps=None, ztaps=None):
         """x_flat: [B, crop*crop*C] (isprs:763 reshape).  Returns logits NHWC [B,crop,crop,K]."""
         p = self.p if p is None else p
         B = x_flat.shape[0]
@@ -117,6 +117,8 @@ class OracleNet:
         feats = None
         for i, (scope, k, r, ci, co) in enumerate(self.plan):
             z = _conv_same(x, p[scope + "/weights"], r) + p[scope + "/biases"].view(1, -1, 1, 1)
+            if ztaps is not None:
+                ztaps[scope] = z
             if is_training:
                 mean = z.mean(dim=(0, 2, 3))
                 var = z.var(dim=(0, 2, 3), unbiased=False)
