@@ -1,0 +1,81 @@
+"""One-process-per-GPU plumbing (torch.distributed is used for rendezvous and the NCCL communicator only).
+
+The reference is single-process; the two shardings below are what its hot path offers:
+
+* training shards by batch: every rank runs the same host policy (same seeds -> same patch size, same batch
+  selection) on its slice of the global batch; ``libdrs`` calls back ONE sum-allreduce per step over the flat
+  buffer [gradients ++ loss numerator ++ confusion counts] (plus the per-layer BN sums when ``sync_bn``),
+  and every rank applies the identical momentum update.
+* full-scene inference shards by output row stripe: a rank evaluates every patch that intersects its stripe, so
+  each pixel's contributions are all local and are added in the reference's visiting order (bit-exact, no halo
+  exchange); the uint8 label stripes are then gathered to rank 0.
+"""
+import numpy as np
+
+
+class _DevBuf:
+    """Expose a raw device pointer through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def stripe_bounds(H, world, rank=None):
+    """Row stripes [r*H/world, (r+1)*H/world)."""
+    cuts = [(r * H) // world for r in range(world + 1)]
+    if rank is None:
+        return cuts
+    return cuts[rank], cuts[rank + 1]
+
+
+def attach_allreduce(session, group=None, sync_bn=False):
+    """Route the library's exchange step through torch.distributed (NCCL on GPUs, gloo in CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    cache = {}
+
+    def allreduce(ptr, count, stream):
+        key = (ptr, count)
+        t = cache.get(key)
+        if t is None:
+            t = torch.as_tensor(_DevBuf(ptr, count), device="cuda")
+            cache[key] = t
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+    session.set_allreduce(allreduce if world > 1 else None, world, sync_bn)
+    return world
+
+
+def rank_slice(batch, rank, world):
+    """This rank's share of a global batch (contiguous, equal sizes)."""
+    per = len(batch) // world
+    return batch[rank * per:(rank + 1) * per]
+
+
+def gather_label_stripes(stripe, H, W, rank, world, device=None, group=None):
+    """Collect every rank's uint8 label stripe on rank 0 -> [H, W] (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return stripe
+    cuts = stripe_bounds(H, world)
+    rows = max(b - a for a, b in zip(cuts[:-1], cuts[1:]))
+    backend = dist.get_backend(group)
+    dev = device if device is not None else ("cuda" if backend == "nccl" else "cpu")
+    mine = torch.zeros((rows, W), dtype=torch.uint8, device=dev)
+    mine[:stripe.shape[0]].copy_(torch.from_numpy(np.ascontiguousarray(stripe)))
+    if backend == "nccl":
+        out = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(out, mine, group=group)
+        if rank != 0:
+            return None
+    else:
+        out = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, out, dst=0, group=group)
+        if rank != 0:
+            return None
+    full = np.empty((H, W), dtype=np.uint8)
+    for r in range(world):
+        full[cuts[r]:cuts[r + 1]] = out[r][:cuts[r + 1] - cuts[r]].cpu().numpy()
+    return full

@@ -295,3 +295,42 @@ def select_best_patch_size(distribution_type, values, patch_acc_loss, patch_occu
                     patch_chosen_values[arg_sort_out[i]] += 1
                 break
     return cur_patch_val
+
+
+# --------------------------------------------------------------------------------------
+# gather + augment + normalise as ONE step: what the fed ``x`` / ``y`` of a batch must be
+# (isprs:245-334 then 74-81 then the float32 feed; contest:192-254; coffee:241-293)
+# --------------------------------------------------------------------------------------
+def apply_plan(scenes, label_maps, inst, flips, crop, mean_full, std_full, noise=None, noise_on=None,
+               over_x=None, over_y=None, over_on=None, cast=True):
+    """Checker for the gather kernel.  ``inst`` rows are (map, row, col) AFTER shift-back.
+
+    Order of operations is the reference's: crop (or host-rotated override, isprs:292-296) -> + noise
+    (isprs:298-301) -> flip (isprs:304-318) -> normalise channels 0..2 in the scene dtype (isprs:74-81) ->
+    cast to float32 (feed_dict).  Returns x float32 [B,crop,crop,C], y float32 [B,crop,crop]."""
+    xs, ys = [], []
+    for b in range(len(inst)):
+        m, r, c = int(inst[b][0]), int(inst[b][1]), int(inst[b][2])
+        if over_on is not None and over_on[b]:
+            p = np.array(over_x[b], dtype=np.float64)
+            l = np.array(over_y[b])
+        else:
+            p = np.array(scenes[m][r:r + crop, c:c + crop, :])
+            l = np.array(label_maps[m][r:r + crop, c:c + crop]) if label_maps is not None else np.zeros((crop, crop))
+        if noise_on is not None and noise_on[b]:
+            p = p + noise[b]
+        f = 0 if flips is None else int(flips[b])
+        if f == FLIP_UD:
+            p, l = np.flipud(p), np.flipud(l)
+        elif f == FLIP_LR:
+            p, l = np.fliplr(p), np.fliplr(l)
+        xs.append(p)
+        ys.append(l)
+    x = np.array(xs)
+    if x.dtype == np.float32:
+        mean_full = np.asarray(mean_full, dtype=np.float32)
+        std_full = np.asarray(std_full, dtype=np.float32)
+    normalize_images(x, mean_full, std_full)
+    if not cast:
+        return x, np.array(ys)
+    return x.astype(np.float32), np.array(ys).astype(np.float32)

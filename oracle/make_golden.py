@@ -24,20 +24,9 @@ from contextlib import redirect_stdout
 import numpy as np
 
 from oracle import ref_import
+from oracle.fake_net import fake_logits
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "host_golden.npz")
-
-
-def fake_logits(bx, crop, channels, num_classes):
-    """Closed-form stand-in for the network: IEEE-exact ops only (add, mul, fmod)."""
-    x = np.asarray(bx, dtype=np.float64).reshape(-1, crop, crop, channels)
-    s = np.zeros(x.shape[:3], dtype=np.float64)
-    for c in range(channels):
-        s = s + x[..., c] * float(c + 1)
-    out = np.empty(x.shape[:3] + (num_classes,), dtype=np.float32)
-    for k in range(num_classes):
-        out[..., k] = np.fmod(np.abs(s) * (3.0 + 2.0 * k) + 0.61 * k, 5.0).astype(np.float32)
-    return out
 
 
 class FakeSession:

@@ -1,0 +1,76 @@
+"""CPU: the product's host-side mirror (dynamic-rs-segmentation_b200/host.py) against reference-generated vectors.
+
+host.py keeps the reference's L3 policy and the *decisions* of the L2 data path (which window, which flip,
+which noise) on the host with the reference's RNG consumption; pixels are moved by the GPU gather kernel.
+Here the decisions are checked by applying them with the NumPy checker (oracle.host_np.apply_plan).
+"""
+import random
+
+import numpy as np
+
+from oracle import host_np
+
+
+def test_policy_functions_match_reference(golden, drs):
+    from drs_b200 import host
+    random.seed(7)
+    total, bs = 50, 8
+    shuffle = np.asarray(random.sample(range(total), total))
+    it = 0
+    for n in range(20):
+        shuffle, batch, it = host.select_batch(shuffle, bs, it, total)
+        assert np.array_equal(batch, golden["select_batch_batches"][n]) and it == golden["select_batch_its"][n]
+    assert np.array_equal(host.define_multinomial_probs([25, 29, 33, 37, 41, 45, 49]), golden["probs_25_49"])
+    for case in range(8):
+        dist = ["multi_fixed", "uniform"][case % 2]
+        upd = ["acc", "loss"][(case // 2) % 2]
+        values = [25, 33, 41, 49] if dist == "multi_fixed" else [25, 32]
+        pal = golden["best_%d_in" % case][0].astype(np.float32)
+        occ = golden["best_%d_in" % case][1].astype(np.int32)
+        chosen = np.zeros(len(occ), dtype=np.int32)
+        assert int(host.select_best_patch_size(dist, values, pal, occ, upd, chosen)) == int(golden["best_vals"][case])
+        assert np.array_equal(occ, golden["best_%d_occ_out" % case])
+        assert np.array_equal(chosen, golden["best_%d_chosen_out" % case])
+
+
+def test_isprs_batch_plan_reproduces_reference_augmentation(golden, drs):
+    """dynamically_create_patches (isprs:245-334) incl. rotation, noise and flips under a fixed np.random seed."""
+    from drs_b200 import host
+    scenes, labs, inst = golden["gather_scenes"], golden["gather_labels"], golden["gather_inst"]
+    for crop in (9, 12):
+        np.random.seed(100 + crop)
+        plan = host.plan_isprs_batch(scenes, labs, inst, crop, is_train=True)
+        x, y = host_np.apply_plan(scenes, labs, plan.inst, plan.flips, crop, np.zeros(4), np.ones(4), plan.noise,
+                                  plan.noise_on, plan.over_x, plan.over_y, plan.over_on, cast=False)
+        assert np.array_equal(x, golden["gather_train_%d_p" % crop])
+        assert np.array_equal(y.astype(np.int64), golden["gather_train_%d_l" % crop])
+        am = np.ones(y.shape, dtype=bool) if plan.acc_mask is None else plan.acc_mask.astype(bool)
+        assert np.array_equal(am, golden["gather_train_%d_m" % crop])
+        # eval mode: no RNG consumed, no augmentation
+        state = np.random.get_state()[1].copy()
+        plan = host.plan_isprs_batch(scenes, labs, inst, crop, is_train=False)
+        assert np.array_equal(np.random.get_state()[1], state)
+        x, y = host_np.apply_plan(scenes, labs, plan.inst, plan.flips, crop, np.zeros(4), np.ones(4), cast=False)
+        assert np.array_equal(x, golden["gather_eval_%d_p" % crop])
+
+
+def test_index_flip_plans(golden, drs):
+    from drs_b200 import host
+    img, lab = golden["contest_scene"], golden["contest_labels"]
+    plan = host.plan_index_flip_batch([tuple(r) for r in golden["contest_distr"]], golden["contest_shuf"], 11,
+                                      [img.shape[:2]])
+    x, y = host_np.apply_plan([img], [lab], plan.inst, plan.flips, 11, np.zeros(3), np.ones(3), cast=False)
+    assert np.array_equal(x, golden["contest_gather_p"])
+    assert np.array_equal(y.astype(np.int8), golden["contest_gather_l"])
+    imgs, labs = golden["coffee_scenes"], golden["coffee_labels"]
+    cd = [(int(m), (int(a), int(b))) for m, a, b in golden["coffee_distr"]]
+    plan = host.plan_index_flip_batch(cd, golden["coffee_shuf"], 9, [im.shape[:2] for im in imgs], with_map=True)
+    x, y = host_np.apply_plan(imgs, labs, plan.inst, plan.flips, 9, np.zeros(3), np.ones(3), cast=False)
+    assert np.array_equal(x.astype(np.float16), golden["coffee_gather_p"])
+
+
+def test_acc_norm_from_confusion(golden, drs):
+    from drs_b200 import host
+    assert host.acc_norm_from_cm(golden["cm_out"], 6) == golden["cm_acc"][1]
+    assert host.acc_norm_from_cm(golden["cm_nomask_out"], 6) == golden["cm_nomask_acc"][1]
+    assert host.sliding_stride(25) == 12 and host.sliding_stride(30) == 15
