@@ -7,6 +7,7 @@
 #include "drs_common.cuh"
 #include "ops.cuh"
 #include "scene.cuh"
+#include "wgrad_tc.cuh"
 
 thread_local char g_drs_err[1024] = {0};
 
@@ -485,9 +486,7 @@ static void forward_eval_t(Handle* h, const float* x_dev, int B, int crop, float
     }
     if (n.pool) {
       ActBuf pout{bufs[(xi + 2) % 3], fs, 0};
-      maxpool3_fwd_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>((const TA*)out.p, out.cs, out.co, (TA*)pout.p,
-                                                                                 pout.cs, pout.co, nullptr, c.co, M, crop);
-      LAUNCH_CHECK(h);
+      launch_maxpool3_fwd<TA>(h, (const TA*)out.p, out.cs, out.co, (TA*)pout.p, pout.cs, pout.co, nullptr, c.co, B, crop);
       cur = pout;
       xi = (xi + 2) % 3;
     } else if (n.dense) {
@@ -498,11 +497,8 @@ static void forward_eval_t(Handle* h, const float* x_dev, int B, int crop, float
     }
     h->taps[c.scope] = {n.dense ? out.p : cur.p, ElemTag<TA>::v, fs, n.dense ? c.out_coff : 0, c.co, M};
   }
-  const int threads = 256;
-  int blocks = (int)std::min<int64_t>(ceil_div(M, threads / 32), (int64_t)h->sm_count * 8);
-  classifier_fwd_kernel<TA><<<blocks, threads, n.cls_in * n.classes * 4, h->stream>>>(
-      (const TA*)cur.p, cur.cs, cur.co, n.cls_in, h->params + n.cls_w_off, h->params + n.cls_b_off, n.classes, logits, pred_dev, M);
-  LAUNCH_CHECK(h);
+  launch_classifier_fwd<TA>(h, (const TA*)cur.p, cur.cs, cur.co, n.cls_in, h->params + n.cls_w_off, h->params + n.cls_b_off, n.classes,
+                            logits, pred_dev, M);
 }
 
 static void forward_eval(Handle* h, const float* x_dev, int B, int crop, float* logits_dev, uint8_t* pred_dev) {

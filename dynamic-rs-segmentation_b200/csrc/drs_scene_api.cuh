@@ -418,3 +418,47 @@ extern "C" int drs_debug_conv(drs_handle_t h, const float* x_host, const float* 
   cleanup();
   API_END
 }
+
+// Filter gradient of one convolution through the production kernels (unit tests)
+extern "C" int drs_debug_wgrad(drs_handle_t h, const float* x_host, const float* dy_host, int32_t B, int32_t crop, int32_t k,
+                               int32_t rate, int32_t Ci, int32_t Co, int32_t precision, float* dw_host) {
+  API_BEGIN
+  DRS_CHECK(h && x_host && dy_host && dw_host, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  const int64_t M = (int64_t)B * crop * crop;
+  const int64_t nw = (int64_t)k * k * Ci * Co;
+  const int pad_b = ((k - 1) * rate) / 2;
+  const int max_splits = 48;
+  float *x32 = nullptr, *dy32 = nullptr, *dw = nullptr, *part = nullptr;
+  void *xa = nullptr, *dya = nullptr;
+  auto cleanup = [&]() { cudaFree(x32); cudaFree(dy32); cudaFree(dw); cudaFree(part); cudaFree(xa); cudaFree(dya); };
+  try {
+    CUDA_CHECK(cudaMalloc(&x32, M * Ci * 4));
+    CUDA_CHECK(cudaMalloc(&dy32, M * Co * 4));
+    CUDA_CHECK(cudaMalloc(&dw, nw * 4));
+    CUDA_CHECK(cudaMalloc(&part, nw * 4 * max_splits));
+    CUDA_CHECK(cudaMemcpyAsync(x32, x_host, M * Ci * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(dy32, dy_host, M * Co * 4, cudaMemcpyHostToDevice, h->stream));
+    if (precision == DRS_PREC_FP32) {
+      launch_wgrad_simt<float, float>(h, x32, Ci, 0, Ci, dy32, Co, 0, Co, dw, part, max_splits, B, crop, k, rate, pad_b);
+    } else {
+      DRS_CHECK(precision == DRS_PREC_BF16, "debug_wgrad: precision must be FP32 or BF16");
+      CUDA_CHECK(cudaMalloc(&xa, M * Ci * 2));
+      CUDA_CHECK(cudaMalloc(&dya, M * Co * 2));
+      cast_kernel<float, __nv_bfloat16><<<nblk(M * Ci, 256), 256, 0, h->stream>>>(x32, (__nv_bfloat16*)xa, M * Ci);
+      cast_kernel<float, __nv_bfloat16><<<nblk(M * Co, 256), 256, 0, h->stream>>>(dy32, (__nv_bfloat16*)dya, M * Co);
+      h->launches += 2;
+      WgradTcArgs wa;
+      wa.x = xa; wa.in_cstride = Ci; wa.in_coff = 0; wa.ci = Ci;
+      wa.dy = dya; wa.dy_cstride = Co; wa.dy_coff = 0; wa.co = Co;
+      wa.B = B; wa.crop = crop; wa.k = k; wa.rate = rate; wa.pad_b = pad_b;
+      wa.dw = dw; wa.part = part; wa.part_capacity = (size_t)nw * max_splits;
+      launch_wgrad_tc(h, wa);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(dw_host, dw, nw * 4, cudaMemcpyDeviceToHost, h->stream));
+    int rc = drs_synchronize(h);
+    if (rc) throw DrsError{rc};
+  } catch (...) { cleanup(); throw; }
+  cleanup();
+  API_END
+}

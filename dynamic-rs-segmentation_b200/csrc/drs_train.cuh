@@ -42,11 +42,13 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   add(M * maxc * es * 2);                     // G ping-pong / dense dgrad temp
   add(M * K * 4 * 2);                         // logits, dlogits
   add(M * 2);                                 // labels u8, pred
-  const int nb_bn = (int)ceil_div(M, BN_ROWS_PER_BLOCK);
+  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 4);
+  const int bn_rows = (int)ceil_div(M, nb_bn);
   add((size_t)nb_bn * 2 * 256 * 4);
   const int nb_ce = (int)ceil_div(M, CE_THREADS);
   add((size_t)nb_ce * 4);
-  const int nb_cls = (int)ceil_div(M, CLS_ROWS_PER_BLOCK);
+  const int nb_cls = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 4);
+  const int cls_rows = (int)ceil_div(M, nb_cls);
   add((size_t)nb_cls * (n.cls_in + 1) * K * 4);
   const int max_splits = 48;
   size_t max_w = 0;
@@ -111,31 +113,32 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     // batch statistics (biased variance), moving-average update          (isprs:658-660)
     float* mean = x->mean + c.mm_off;
     float* istd = x->inv_std + c.mm_off;
-    bn_partial_kernel<TA, TA, 0><<<nb_bn, c.co, 0, h->stream>>>(Z[l], c.co, 0, nullptr, 0, 0, nullptr, nullptr, 0, part_bn, c.co, M);
+    bn_partial_kernel<TA, TA, 0><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, nullptr, 0, 0, nullptr, nullptr, 0, part_bn, c.co, M, bn_rows);
     LAUNCH_CHECK(h);
-    bn_reduce_kernel<<<nblk(c.co, 128), 128, 0, h->stream>>>(part_bn, x->sums, c.co, nb_bn);
-    LAUNCH_CHECK(h);
-    if (h->sync_bn) do_allreduce(h, x->sums, 2 * c.co);
-    bn_finalize_kernel<<<nblk(c.co, 128), 128, 0, h->stream>>>(x->sums, mean, istd, h->bnstat + c.mm_off, h->bnstat + c.mv_off, c.co,
-                                                                bn_count, h->cfg.bn_eps, h->cfg.bn_decay, h->cfg.bn_unbiased_ema);
-    LAUNCH_CHECK(h);
+    if (h->sync_bn) {
+      bn_reduce_kernel<<<nblk(c.co, 32), 256, 0, h->stream>>>(part_bn, x->sums, c.co, nb_bn, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0f, 0.0f, 0);
+      LAUNCH_CHECK(h);
+      do_allreduce(h, x->sums, 2 * c.co);
+      bn_finalize_kernel<<<nblk(c.co, 128), 128, 0, h->stream>>>(x->sums, mean, istd, h->bnstat + c.mm_off, h->bnstat + c.mv_off, c.co,
+                                                                  bn_count, h->cfg.bn_eps, h->cfg.bn_decay, h->cfg.bn_unbiased_ema);
+      LAUNCH_CHECK(h);
+    } else {
+      bn_reduce_kernel<<<nblk(c.co, 32), 256, 0, h->stream>>>(part_bn, x->sums, c.co, nb_bn, mean, istd, h->bnstat + c.mm_off, h->bnstat + c.mv_off,
+                                                               bn_count, h->cfg.bn_eps, h->cfg.bn_decay, h->cfg.bn_unbiased_ema);
+      LAUNCH_CHECK(h);
+    }
     // normalise + activation (+ pool)
     ActBuf ab = n.pool ? ActBuf{T, c.co, 0} : (n.dense ? ActBuf{F, n.feat_stride, c.out_coff} : ActBuf{Xn[l], c.co, 0});
     bn_apply_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>(Z[l], c.co, 0, mean, istd, n.act, (TA*)ab.p, ab.cs, ab.co, c.co, M);
     LAUNCH_CHECK(h);
     if (n.pool) {
-      maxpool3_fwd_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>(T, c.co, 0, Xn[l], c.co, 0, idx[l], c.co, M, crop);
-      LAUNCH_CHECK(h);
+      launch_maxpool3_fwd<TA>(h, T, c.co, 0, Xn[l], c.co, 0, idx[l], c.co, B, crop);
     }
     h->taps[c.scope] = {n.dense ? (void*)F : (void*)Xn[l], ElemTag<TA>::v, n.dense ? n.feat_stride : c.co, n.dense ? c.out_coff : 0, c.co, M};
   }
   ActBuf feat = n.dense ? ActBuf{F, n.feat_stride, 0} : ActBuf{Xn[L - 1], n.convs[L - 1].co, 0};
-  {
-    int blocks = (int)std::min<int64_t>(ceil_div(M, 8), (int64_t)h->sm_count * 8);
-    classifier_fwd_kernel<TA><<<blocks, 256, n.cls_in * K * 4, h->stream>>>((const TA*)feat.p, feat.cs, feat.co, n.cls_in,
-                                                                            h->params + n.cls_w_off, h->params + n.cls_b_off, K, logits, pred, M);
-    LAUNCH_CHECK(h);
-  }
+  launch_classifier_fwd<TA>(h, (const TA*)feat.p, feat.cs, feat.co, n.cls_in, h->params + n.cls_w_off, h->params + n.cls_b_off, K, logits,
+                            pred, M);
 
   // ---------------------------------------------------------------- loss (isprs:1089-1099, contest:881-901)
   double count = (double)M;
@@ -170,8 +173,8 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
 
   // ---------------------------------------------------------------- backward
   // classifier: dW, db, dX
-  classifier_bwd_weight_kernel<TA><<<nb_cls, (unsigned)round_up(std::max(n.cls_in, K), 32), 0, h->stream>>>(
-      (const TA*)feat.p, feat.cs, feat.co, n.cls_in, dlogits, K, part_cls, part_clsb, M);
+  classifier_bwd_weight_kernel<TA><<<nb_cls, CLSW_THREADS, 0, h->stream>>>((const TA*)feat.p, feat.cs, feat.co, n.cls_in, dlogits, K, part_cls,
+                                                                           part_clsb, M, cls_rows);
   LAUNCH_CHECK(h);
   reduce_partials_kernel<<<nblk((int64_t)n.cls_in * K, 256), 256, 0, h->stream>>>(part_cls, h->grads + n.cls_w_off, (int64_t)n.cls_in * K, nb_cls);
   LAUNCH_CHECK(h);
@@ -197,9 +200,9 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     }
     float* mean = x->mean + c.mm_off;
     float* istd = x->inv_std + c.mm_off;
-    bn_partial_kernel<TA, TA, 1><<<nb_bn, c.co, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, n.act, part_bn, c.co, M);
+    bn_partial_kernel<TA, TA, 1><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, n.act, part_bn, c.co, M, bn_rows);
     LAUNCH_CHECK(h);
-    bn_reduce_kernel<<<nblk(c.co, 128), 128, 0, h->stream>>>(part_bn, x->sums, c.co, nb_bn);
+    bn_reduce_kernel<<<nblk(c.co, 32), 256, 0, h->stream>>>(part_bn, x->sums, c.co, nb_bn, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0f, 0.0f, 0);
     LAUNCH_CHECK(h);
     if (h->sync_bn) do_allreduce(h, x->sums, 2 * c.co);
     bn_bwd_apply_kernel<TA, TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, x->sums,
@@ -211,6 +214,18 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     ActBuf xin = input_of(l);
     if (l == 0) {
       launch_wgrad_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, DZ, c.co, 0, c.co, h->grads + c.w_off, part_w, max_splits, B, crop, c.k, c.rate, c.pad_b);
+    } else if (ElemTag<TA>::v == ET_BF16 && wgrad_tc_supported(c.ci, c.co)) {
+      WgradTcArgs wa;
+      wa.x = xin.p; wa.in_cstride = xin.cs; wa.in_coff = xin.co; wa.ci = c.ci;
+      wa.dy = DZ; wa.dy_cstride = c.co; wa.dy_coff = 0; wa.co = c.co;
+      wa.B = B; wa.crop = crop; wa.k = c.k; wa.rate = c.rate; wa.pad_b = c.pad_b;
+      wa.dw = h->grads + c.w_off; wa.part = part_w; wa.part_capacity = max_w * max_splits;
+      cudaEvent_t ea = nullptr, eb = nullptr;
+      prof_begin(h, &ea, &eb);
+      launch_wgrad_tc(h, wa);
+      prof_end(h, eb);
+      x->conv_flops += 2.0 * (double)M * c.k * c.k * c.ci * c.co;
+      x->conv_launches += 1;
     } else {
       launch_wgrad_simt<TA, TA>(h, (const TA*)xin.p, xin.cs, xin.co, c.ci, DZ, c.co, 0, c.co, h->grads + c.w_off, part_w, max_splits, B, crop, c.k, c.rate, c.pad_b);
     }

@@ -4,6 +4,8 @@
 // result is run-to-run deterministic.  Activations are NHWC with a channel stride/offset so that the
 // dense net's concat (isprs:921-948) is a view, never a copy.
 #pragma once
+#include <algorithm>
+
 #include "drs_common.cuh"
 
 template <typename T>
@@ -15,48 +17,87 @@ struct alignas(16) Vec8 {
 // _max_pool(kernel 3x3, stride 1, SAME)  isprs:745-750.  Padding never wins (window clipped).
 // idx (optional, training): position 0..8 of the first maximum in row-major window order.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void maxpool3_fwd_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __restrict__ out, int out_cs,
-                                    int out_co, uint8_t* __restrict__ idx, int C, int64_t M, int crop) {
-  const int cv = C >> 3;
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= M * cv) return;
-  const int64_t m = gid / cv;
-  const int c0 = (int)(gid - m * cv) << 3;
-  const int cc = crop * crop;
-  const int r = (int)(m % cc);
-  const int y = r / crop, x = r - y * crop;
-  float best[8];
-  int bi[8];
+// Column-sliding formulation: a thread owns (image, column x, 8 channels) and walks down a segment of rows keeping
+// the horizontal 3-max of the two previous rows in registers, so every input element is loaded 3 times (from L1)
+// instead of 9.  Adjacent threads cover adjacent channel groups, then adjacent columns: each row access of a warp is
+// one contiguous run.
+template <typename T, bool WITH_IDX>
+__device__ __forceinline__ void pool_row_max(const T* __restrict__ in, int in_cs, int64_t pix_row0, int x, int crop, int y,
+                                             float (&v)[8], int (&d)[8]) {
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bi[e] = 0; }
+  for (int e = 0; e < 8; ++e) { v[e] = -INFINITY; d[e] = 0; }
+  if (y < 0 || y >= crop) return;
 #pragma unroll
-  for (int dy = -1; dy <= 1; ++dy) {
-    const int yy = y + dy;
-    if (yy < 0 || yy >= crop) continue;
+  for (int dx = -1; dx <= 1; ++dx) {
+    const int xx = x + dx;
+    if (xx < 0 || xx >= crop) continue;
+    const Vec8<T> q = *reinterpret_cast<const Vec8<T>*>(in + (pix_row0 + (int64_t)y * crop + xx) * in_cs);
 #pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int xx = x + dx;
-      if (xx < 0 || xx >= crop) continue;
-      const Vec8<T> v = *reinterpret_cast<const Vec8<T>*>(in + (m + dy * crop + dx) * in_cs + in_co + c0);
-      const int code = (dy + 1) * 3 + (dx + 1);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float f = to_f32(v.v[e]);
-        if (f > best[e]) { best[e] = f; bi[e] = code; }
-      }
+    for (int e = 0; e < 8; ++e) {
+      const float f = to_f32(q.v[e]);
+      if (f > v[e]) { v[e] = f; if (WITH_IDX) d[e] = dx + 1; }
     }
   }
-  Vec8<T> o;
+}
+
+template <typename T, bool WITH_IDX>
+__global__ void __launch_bounds__(256)
+maxpool3_fwd_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __restrict__ out, int out_cs, int out_co,
+                    uint8_t* __restrict__ idx, int C, int B, int crop, int seg, int nseg) {
+  const int cv = C >> 3;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)B * nseg * crop * cv) return;
+  const int cg = (int)(gid % cv);
+  int64_t t = gid / cv;
+  const int x = (int)(t % crop);
+  t /= crop;
+  const int sg = (int)(t % nseg);
+  const int b = (int)(t / nseg);
+  const int y0 = sg * seg, y1 = min(crop, y0 + seg);
+  const int64_t img0 = (int64_t)b * crop * crop;
+  const T* inp = in + in_co + cg * 8;
+  float r0[8], r1[8], r2[8];
+  int d0[8], d1[8], d2[8];
+  pool_row_max<T, WITH_IDX>(inp, in_cs, img0, x, crop, y0 - 1, r0, d0);
+  pool_row_max<T, WITH_IDX>(inp, in_cs, img0, x, crop, y0, r1, d1);
+  for (int y = y0; y < y1; ++y) {
+    pool_row_max<T, WITH_IDX>(inp, in_cs, img0, x, crop, y + 1, r2, d2);
+    Vec8<T> o;
+    int code[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) o.v[e] = from_f32<T>(best[e]);
-  *reinterpret_cast<Vec8<T>*>(out + m * out_cs + out_co + c0) = o;
-  if (idx) {
-    uint2 pk;
-    pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
-    pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
-    *reinterpret_cast<uint2*>(idx + m * C + c0) = pk;
+    for (int e = 0; e < 8; ++e) {
+      // rows in order dy = -1, 0, +1; a later row wins only when strictly greater (first maximum, row-major)
+      float best = r0[e];
+      int c = d0[e];
+      if (r1[e] > best) { best = r1[e]; c = 3 + d1[e]; }
+      if (r2[e] > best) { best = r2[e]; c = 6 + d2[e]; }
+      o.v[e] = from_f32<T>(best);
+      code[e] = c;
+    }
+    const int64_t m = img0 + (int64_t)y * crop + x;
+    *reinterpret_cast<Vec8<T>*>(out + m * out_cs + out_co + cg * 8) = o;
+    if (WITH_IDX) {
+      uint2 pk;
+      pk.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+      pk.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
+      *reinterpret_cast<uint2*>(idx + m * C + cg * 8) = pk;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { r0[e] = r1[e]; r1[e] = r2[e]; d0[e] = d1[e]; d1[e] = d2[e]; }
   }
+}
+
+template <typename T>
+static void launch_maxpool3_fwd(Handle* h, const T* in, int in_cs, int in_co, T* out, int out_cs, int out_co, uint8_t* idx, int C,
+                                int B, int crop) {
+  const int64_t base = (int64_t)B * crop * (C / 8);
+  int nseg = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div((int64_t)h->sm_count * 2048, base)), std::max(1, crop / 4));
+  const int seg = (int)ceil_div(crop, nseg);
+  nseg = (int)ceil_div(crop, seg);
+  const int64_t total = base * nseg;
+  if (idx) maxpool3_fwd_kernel<T, true><<<(unsigned)ceil_div(total, 256), 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, idx, C, B, crop, seg, nseg);
+  else maxpool3_fwd_kernel<T, false><<<(unsigned)ceil_div(total, 256), 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, nullptr, C, B, crop, seg, nseg);
+  LAUNCH_CHECK(h);
 }
 
 // dIn[q] = sum over the (<=9) windows o that contain q and whose recorded maximum is q, of dOut[o]
@@ -102,51 +143,104 @@ __global__ void maxpool3_bwd_kernel(const T* __restrict__ dout, int do_cs, int d
 // ------------------------------------------------------------------------------------------------
 // _batch_norm (isprs:655-663): tf.contrib.layers.batch_norm(center=False, scale=False)
 // ------------------------------------------------------------------------------------------------
-constexpr int BN_ROWS_PER_BLOCK = 256;
+constexpr int BN_THREADS = 256;
 
-// part[blk][0][c] = sum_m a, part[blk][1][c] = sum_m a*b over the block's rows.
+// part[blk][0][c] = sum_m a, part[blk][1][c] = sum_m a*b over the block's contiguous slab of rows.
 //   MODE 0 (forward statistics):  a = z,            b = z
 //   MODE 1 (backward sums):       a = g = dA*act'(xh), b = xh        (xh = (z-mean)*inv_std)
+// Thread = (channel group of 8, row lane): 16-byte loads, per-thread fp32 partials, then a fixed-order reduction over the
+// row lanes in shared memory.  The row -> (block, lane) assignment is static, so the result is run-to-run identical.
 template <typename TZ, typename TG, int MODE>
-__global__ void bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __restrict__ dA, int g_cs,
-                                  int g_co, const float* __restrict__ mean, const float* __restrict__ inv_std, int act,
-                                  float* __restrict__ part, int C, int64_t M) {
-  const int c = threadIdx.x;
-  if (c >= C) return;
-  const int64_t r0 = (int64_t)blockIdx.x * BN_ROWS_PER_BLOCK;
-  const int64_t r1 = min(M, r0 + BN_ROWS_PER_BLOCK);
-  float s0 = 0.0f, s1 = 0.0f;
-  float mu = 0.0f, is = 1.0f;
-  if (MODE == 1) { mu = mean[c]; is = inv_std[c]; }
-  for (int64_t m = r0; m < r1; ++m) {
-    const float zv = to_f32(z[m * z_cs + z_co + c]);
-    if (MODE == 0) {
-      s0 += zv;
-      s1 = fmaf(zv, zv, s1);
-    } else {
-      const float xh = (zv - mu) * is;
-      float g = to_f32(dA[m * g_cs + g_co + c]);
-      if (act == ACT_RELU) g = xh > 0.0f ? g : 0.0f;
-      else if (act == ACT_LRELU) g = xh > 0.0f ? g : 0.1f * g;
-      s0 += g;
-      s1 = fmaf(g, xh, s1);
+__global__ void __launch_bounds__(BN_THREADS)
+bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __restrict__ dA, int g_cs, int g_co,
+                  const float* __restrict__ mean, const float* __restrict__ inv_std, int act, float* __restrict__ part, int C,
+                  int64_t M, int rows_per_block) {
+  __shared__ float s_red[BN_THREADS * 16];
+  const int cv = C >> 3;
+  const int lanes_r = BN_THREADS / cv;
+  const int cg = threadIdx.x % cv, rl = threadIdx.x / cv;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(M, r0 + rows_per_block);
+  float s0[8], s1[8], mu[8], is[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s0[e] = 0.0f; s1[e] = 0.0f; mu[e] = 0.0f; is[e] = 1.0f; }
+  if (rl < lanes_r) {
+    if (MODE == 1) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { mu[e] = mean[cg * 8 + e]; is[e] = inv_std[cg * 8 + e]; }
+    }
+    for (int64_t m = r0 + rl; m < r1; m += lanes_r) {
+      const Vec8<TZ> zv = *reinterpret_cast<const Vec8<TZ>*>(z + m * z_cs + z_co + cg * 8);
+      if (MODE == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float f = to_f32(zv.v[e]);
+          s0[e] += f;
+          s1[e] = fmaf(f, f, s1[e]);
+        }
+      } else {
+        const Vec8<TG> gv = *reinterpret_cast<const Vec8<TG>*>(dA + m * g_cs + g_co + cg * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (to_f32(zv.v[e]) - mu[e]) * is[e];
+          float g = to_f32(gv.v[e]);
+          if (act == ACT_RELU) g = xh > 0.0f ? g : 0.0f;
+          else if (act == ACT_LRELU) g = xh > 0.0f ? g : 0.1f * g;
+          s0[e] += g;
+          s1[e] = fmaf(g, xh, s1[e]);
+        }
+      }
     }
   }
-  part[((int64_t)blockIdx.x * 2 + 0) * C + c] = s0;
-  part[((int64_t)blockIdx.x * 2 + 1) * C + c] = s1;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    s_red[threadIdx.x * 16 + e] = s0[e];
+    s_red[threadIdx.x * 16 + 8 + e] = s1[e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) {
+    const int which = i / C, c = i - which * C;
+    const int g = c >> 3, e = c & 7;
+    float a = 0.0f;
+    for (int r = 0; r < lanes_r; ++r) a += s_red[(r * cv + g) * 16 + which * 8 + e];
+    part[((int64_t)blockIdx.x * 2 + which) * C + c] = a;
+  }
 }
 
-// sums[0][c], sums[1][c] = fixed-order (double) reduction over blocks
-__global__ void bn_reduce_kernel(const float* __restrict__ part, float* __restrict__ sums, int C, int nblk) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// sums[0][c], sums[1][c] = fixed-order (double) reduction over blocks: 8 interleaved lanes per channel, then a fixed-order
+// combine.  When `mean` is given (single process, or sync_bn off) the finalize step is fused in.
+__global__ void __launch_bounds__(256)
+bn_reduce_kernel(const float* __restrict__ part, float* __restrict__ sums, int C, int nblk, float* __restrict__ mean,
+                 float* __restrict__ inv_std, float* __restrict__ mov_mean, float* __restrict__ mov_var, double count, float eps,
+                 float decay, int unbiased_ema) {
+  __shared__ double s_a[8][32], s_b[8][32];
+  const int cl = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double a = 0.0, b = 0.0;
-  for (int k = 0; k < nblk; ++k) {
-    a += (double)part[((int64_t)k * 2 + 0) * C + c];
-    b += (double)part[((int64_t)k * 2 + 1) * C + c];
+  if (c < C) {
+    for (int k = j; k < nblk; k += 8) {
+      a += (double)part[((int64_t)k * 2 + 0) * C + c];
+      b += (double)part[((int64_t)k * 2 + 1) * C + c];
+    }
   }
-  sums[c] = (float)a;
-  sums[C + c] = (float)b;
+  s_a[j][cl] = a;
+  s_b[j][cl] = b;
+  __syncthreads();
+  if (j == 0 && c < C) {
+    for (int r = 1; r < 8; ++r) { a += s_a[r][cl]; b += s_b[r][cl]; }
+    sums[c] = (float)a;
+    sums[C + c] = (float)b;
+    if (mean) {
+      const double mu = (double)(float)a / count;
+      double var = (double)(float)b / count - mu * mu;
+      if (var < 0.0) var = 0.0;
+      mean[c] = (float)mu;
+      inv_std[c] = (float)(1.0 / sqrt(var + (double)eps));
+      const double var_ema = unbiased_ema ? var * (count / fmax(count - 1.0, 1.0)) : var;
+      mov_mean[c] = decay * mov_mean[c] + (1.0f - decay) * (float)mu;
+      mov_var[c] = decay * mov_var[c] + (1.0f - decay) * (float)var_ema;
+    }
+  }
 }
 
 // mean / inv_std from (possibly all-reduced) sums; moving-average update (decay 0.999, isprs:658 defaults)
@@ -234,46 +328,62 @@ __global__ void add_slice_kernel(T* __restrict__ dst, int d_cs, int d_co, const 
 // ------------------------------------------------------------------------------------------------
 constexpr int MAX_CLASSES = 8;
 
-template <typename T>
-__global__ void classifier_fwd_kernel(const T* __restrict__ x, int x_cs, int x_co, int Ci, const float* __restrict__ w,
-                                      const float* __restrict__ b, int K, float* __restrict__ logits,
-                                      uint8_t* __restrict__ pred, int64_t M) {
-  extern __shared__ float s_w[];   // [Ci][K]
-  for (int i = threadIdx.x; i < Ci * K; i += blockDim.x) s_w[i] = w[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  for (int64_t m = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < M;
-       m += (int64_t)gridDim.x * warps_per_block) {
-    float acc[MAX_CLASSES];
+// Tile kernel: a block stages [CLS_TILE pixels x Ci] in shared memory with coalesced 16-byte loads (128B-swizzled
+// rows, so that the row-per-thread reads below are conflict-free), then thread r owns pixel r: Ci*K FMAs against
+// weights broadcast from shared memory, first-maximum argmax, one K-float row of logits out.  No shuffles.
+template <typename T, int CLS_TILE>
+__global__ void __launch_bounds__(CLS_TILE)
+classifier_fwd_kernel(const T* __restrict__ x, int x_cs, int x_co, int Ci, const float* __restrict__ w,
+                      const float* __restrict__ b, int K, float* __restrict__ logits, uint8_t* __restrict__ pred, int64_t M) {
+  extern __shared__ __align__(16) uint8_t cls_smem[];
+  float* s_w = reinterpret_cast<float*>(cls_smem);                 // [Ci][8] (K padded to 8)
+  uint8_t* s_x = cls_smem + (size_t)Ci * 8 * sizeof(float);        // [CLS_TILE][Ci] elements, 16-byte chunks swizzled
+  const int tid = threadIdx.x;
+  for (int i = tid; i < Ci * 8; i += CLS_TILE) {
+    const int c = i >> 3, k = i & 7;
+    s_w[i] = k < K ? w[c * K + k] : 0.0f;
+  }
+  constexpr int EPC = 16 / sizeof(T);      // elements per 16-byte chunk
+  const int chunks = Ci / EPC;
+  const size_t row_bytes = (size_t)Ci * sizeof(T);
+  float bias[MAX_CLASSES];
 #pragma unroll
-    for (int k = 0; k < MAX_CLASSES; ++k) acc[k] = 0.0f;
-    const T* row = x + m * x_cs + x_co;
-    for (int c0 = lane * 8; c0 < Ci; c0 += 256) {
-      const Vec8<T> v = *reinterpret_cast<const Vec8<T>*>(row + c0);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float f = to_f32(v.v[e]);
-        const float* wr = s_w + (c0 + e) * K;
-#pragma unroll
-        for (int k = 0; k < MAX_CLASSES; ++k)
-          if (k < K) acc[k] = fmaf(f, wr[k], acc[k]);
-      }
+  for (int k = 0; k < MAX_CLASSES; ++k) bias[k] = k < K ? b[k] : 0.0f;
+  for (int64_t m0 = (int64_t)blockIdx.x * CLS_TILE; m0 < M; m0 += (int64_t)gridDim.x * CLS_TILE) {
+    __syncthreads();                                            // previous tile fully consumed (and s_w visible)
+    const int rows = (int)min((int64_t)CLS_TILE, M - m0);
+    for (int i = tid; i < rows * chunks; i += CLS_TILE) {
+      const int r = i / chunks, ch = i - r * chunks;
+      const uint4 v = *reinterpret_cast<const uint4*>(x + (m0 + r) * x_cs + x_co + ch * EPC);
+      const int sw = (ch & ~7) | ((ch & 7) ^ (r & 7));
+      *reinterpret_cast<uint4*>(s_x + r * row_bytes + (size_t)sw * 16) = v;
     }
+    __syncthreads();
+    if (tid < rows) {
+      float acc[MAX_CLASSES];
 #pragma unroll
-    for (int k = 0; k < MAX_CLASSES; ++k) {
-      if (k < K) {
+      for (int k = 0; k < MAX_CLASSES; ++k) acc[k] = 0.0f;
+      const uint8_t* rowp = s_x + tid * row_bytes;
+      for (int ch = 0; ch < chunks; ++ch) {
+        const int sw = (ch & ~7) | ((ch & 7) ^ (tid & 7));
+        const uint4 raw = *reinterpret_cast<const uint4*>(rowp + (size_t)sw * 16);
+        const T* e = reinterpret_cast<const T*>(&raw);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        for (int j = 0; j < EPC; ++j) {
+          const float f = to_f32(e[j]);
+          const float4 w0 = *reinterpret_cast<const float4*>(s_w + (ch * EPC + j) * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(s_w + (ch * EPC + j) * 8 + 4);
+          acc[0] = fmaf(f, w0.x, acc[0]); acc[1] = fmaf(f, w0.y, acc[1]); acc[2] = fmaf(f, w0.z, acc[2]); acc[3] = fmaf(f, w0.w, acc[3]);
+          acc[4] = fmaf(f, w1.x, acc[4]); acc[5] = fmaf(f, w1.y, acc[5]); acc[6] = fmaf(f, w1.z, acc[6]); acc[7] = fmaf(f, w1.w, acc[7]);
+        }
       }
-    }
-    if (lane == 0) {
+      const int64_t m = m0 + tid;
       float best = -INFINITY;
       int bi = 0;
 #pragma unroll
       for (int k = 0; k < MAX_CLASSES; ++k) {
         if (k < K) {
-          const float v = acc[k] + b[k];
+          const float v = acc[k] + bias[k];
           if (logits) logits[m * K + k] = v;
           if (v > best) { best = v; bi = k; }      // first maximum (Appendix B.7)
         }
@@ -282,64 +392,125 @@ __global__ void classifier_fwd_kernel(const T* __restrict__ x, int x_cs, int x_c
     }
   }
 }
+template <typename T, int TILE>
+static void launch_classifier_fwd_t(Handle* h, const T* x, int x_cs, int x_co, int Ci, const float* w, const float* b, int K,
+                                    float* logits, uint8_t* pred, int64_t M, size_t smem) {
+  auto kern = classifier_fwd_kernel<T, TILE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (smem + 1024)));
+  const int blocks = (int)std::min<int64_t>(ceil_div(M, TILE), (int64_t)h->sm_count * per_sm);
+  kern<<<blocks, TILE, smem, h->stream>>>(x, x_cs, x_co, Ci, w, b, K, logits, pred, M);
+  LAUNCH_CHECK(h);
+}
+template <typename T>
+static void launch_classifier_fwd(Handle* h, const T* x, int x_cs, int x_co, int Ci, const float* w, const float* b, int K,
+                                  float* logits, uint8_t* pred, int64_t M) {
+  DRS_CHECK(Ci % 64 == 0, "classifier: Ci=%d must be a multiple of 64", Ci);
+  auto smem_of = [&](int tile) { return (size_t)Ci * 8 * 4 + (size_t)tile * Ci * sizeof(T); };
+  if (smem_of(128) <= 112 * 1024) launch_classifier_fwd_t<T, 128>(h, x, x_cs, x_co, Ci, w, b, K, logits, pred, M, smem_of(128));
+  else if (smem_of(64) <= 112 * 1024 || smem_of(128) > 220 * 1024) launch_classifier_fwd_t<T, 64>(h, x, x_cs, x_co, Ci, w, b, K, logits, pred, M, smem_of(64));
+  else launch_classifier_fwd_t<T, 128>(h, x, x_cs, x_co, Ci, w, b, K, logits, pred, M, smem_of(128));
+}
 
-// dX[m][c] = sum_k dl[m][k] * W[c][k]
+// dX[m][c] = sum_k dl[m][k] * W[c][k].  Weights are kept transposed in shared memory ([k][Ci]) so that a warp's
+// 16-byte reads of 8 consecutive channels per lane are contiguous (no bank conflicts).
 template <typename TG>
 __global__ void classifier_bwd_data_kernel(const float* __restrict__ dl, const float* __restrict__ w, int K,
                                            TG* __restrict__ dx, int dx_cs, int dx_co, int Ci, int64_t M) {
-  extern __shared__ float s_w[];
-  for (int i = threadIdx.x; i < Ci * K; i += blockDim.x) s_w[i] = w[i];
+  extern __shared__ __align__(16) float s_wt[];   // [K][Ci]
+  for (int i = threadIdx.x; i < Ci * K; i += blockDim.x) {
+    const int c = i / K, k = i - c * K;
+    s_wt[k * Ci + c] = w[i];
+  }
   __syncthreads();
   const int cv = Ci >> 3;
   for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < M * cv;
        gid += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = gid / cv;
     const int c0 = (int)(gid - m * cv) << 3;
-    float g[MAX_CLASSES];
+    float s[8];
 #pragma unroll
-    for (int k = 0; k < MAX_CLASSES; ++k) g[k] = k < K ? dl[m * K + k] : 0.0f;
+    for (int e = 0; e < 8; ++e) s[e] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < MAX_CLASSES; ++k) {
+      if (k < K) {
+        const float g = dl[m * K + k];
+        const float4 w0 = *reinterpret_cast<const float4*>(s_wt + k * Ci + c0);
+        const float4 w1 = *reinterpret_cast<const float4*>(s_wt + k * Ci + c0 + 4);
+        s[0] = fmaf(g, w0.x, s[0]); s[1] = fmaf(g, w0.y, s[1]); s[2] = fmaf(g, w0.z, s[2]); s[3] = fmaf(g, w0.w, s[3]);
+        s[4] = fmaf(g, w1.x, s[4]); s[5] = fmaf(g, w1.y, s[5]); s[6] = fmaf(g, w1.z, s[6]); s[7] = fmaf(g, w1.w, s[7]);
+      }
+    }
     Vec8<TG> o;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float s = 0.0f;
-#pragma unroll
-      for (int k = 0; k < MAX_CLASSES; ++k)
-        if (k < K) s = fmaf(g[k], s_w[(c0 + e) * K + k], s);
-      o.v[e] = from_f32<TG>(s);
-    }
+    for (int e = 0; e < 8; ++e) o.v[e] = from_f32<TG>(s[e]);
     *reinterpret_cast<Vec8<TG>*>(dx + m * dx_cs + dx_co + c0) = o;
   }
 }
 
-// part[blk][c][k] = sum over the block's rows of x[m][c]*dl[m][k];  part_b[blk][k] = sum dl[m][k]
-constexpr int CLS_ROWS_PER_BLOCK = 512;
+// part[blk][c][k] = sum over the block's slab of rows of x[m][c]*dl[m][k];  part_b[blk][k] = sum dl[m][k].
+// Thread = (channel group of 8, row lane) with 16-byte loads; fixed-order shared-memory reduction over the row lanes.
+constexpr int CLSW_THREADS = 256;
 template <typename T>
-__global__ void classifier_bwd_weight_kernel(const T* __restrict__ x, int x_cs, int x_co, int Ci,
-                                             const float* __restrict__ dl, int K, float* __restrict__ part,
-                                             float* __restrict__ part_b, int64_t M) {
-  const int c = threadIdx.x;          // blockDim.x >= max(Ci, K)
-  const int64_t r0 = (int64_t)blockIdx.x * CLS_ROWS_PER_BLOCK;
-  const int64_t r1 = min(M, r0 + CLS_ROWS_PER_BLOCK);
-  float acc[MAX_CLASSES];
+__global__ void __launch_bounds__(CLSW_THREADS)
+classifier_bwd_weight_kernel(const T* __restrict__ x, int x_cs, int x_co, int Ci, const float* __restrict__ dl, int K,
+                             float* __restrict__ part, float* __restrict__ part_b, int64_t M, int rows_per_block) {
+  __shared__ float s_red[CLSW_THREADS * 8];
+  __shared__ float s_bias[CLSW_THREADS][MAX_CLASSES];
+  const int cv = Ci >> 3;
+  const int lanes_r = CLSW_THREADS / cv;
+  const int cg = threadIdx.x % cv, rl = threadIdx.x / cv;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(M, r0 + rows_per_block);
+  float acc[8][MAX_CLASSES], accb[MAX_CLASSES];
 #pragma unroll
-  for (int k = 0; k < MAX_CLASSES; ++k) acc[k] = 0.0f;
-  float accb = 0.0f;
-  __shared__ float s_dl[MAX_CLASSES];
-  for (int64_t m = r0; m < r1; ++m) {
-    __syncthreads();
-    if (threadIdx.x < K) s_dl[threadIdx.x] = dl[m * K + threadIdx.x];
-    __syncthreads();
-    if (c < Ci) {
-      const float xv = to_f32(x[m * x_cs + x_co + c]);
+  for (int k = 0; k < MAX_CLASSES; ++k) {
+    accb[k] = 0.0f;
 #pragma unroll
-      for (int k = 0; k < MAX_CLASSES; ++k)
-        if (k < K) acc[k] = fmaf(xv, s_dl[k], acc[k]);
-    }
-    if (c < K) accb += s_dl[c];
+    for (int e = 0; e < 8; ++e) acc[e][k] = 0.0f;
   }
-  if (c < Ci)
-    for (int k = 0; k < K; ++k) part[((int64_t)blockIdx.x * Ci + c) * K + k] = acc[k];
-  if (c < K) part_b[(int64_t)blockIdx.x * K + c] = accb;
+  if (rl < lanes_r) {
+    for (int64_t m = r0 + rl; m < r1; m += lanes_r) {
+      const Vec8<T> v = *reinterpret_cast<const Vec8<T>*>(x + m * x_cs + x_co + cg * 8);
+      float g[MAX_CLASSES];
+#pragma unroll
+      for (int k = 0; k < MAX_CLASSES; ++k) g[k] = k < K ? dl[m * K + k] : 0.0f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float f = to_f32(v.v[e]);
+#pragma unroll
+        for (int k = 0; k < MAX_CLASSES; ++k) acc[e][k] = fmaf(f, g[k], acc[e][k]);
+      }
+#pragma unroll
+      for (int k = 0; k < MAX_CLASSES; ++k) accb[k] += g[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MAX_CLASSES; ++k) s_bias[threadIdx.x][k] = accb[k];
+#pragma unroll
+  for (int k = 0; k < MAX_CLASSES; ++k) {
+    if (k < K) {                       // uniform across the block
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s_red[threadIdx.x * 8 + e] = acc[e][k];
+      __syncthreads();
+      for (int c = threadIdx.x; c < Ci; c += CLSW_THREADS) {
+        const int g = c >> 3, e = c & 7;
+        float a = 0.0f;
+        for (int r = 0; r < lanes_r; ++r) a += s_red[(r * cv + g) * 8 + e];
+        part[((int64_t)blockIdx.x * Ci + c) * K + k] = a;
+      }
+    }
+  }
+  if (threadIdx.x < K) {
+    float a = 0.0f;
+    for (int r = 0; r < lanes_r; ++r) a += s_bias[r * cv][threadIdx.x];   // thread (cg 0, row lane r)
+    part_b[(int64_t)blockIdx.x * K + threadIdx.x] = a;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

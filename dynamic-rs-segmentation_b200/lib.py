@@ -71,6 +71,7 @@ _SIGNATURES = {
     "drs_debug_activation": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
     "drs_debug_conv": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int32, _P]),
+    "drs_debug_wgrad": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
 }
 EXPORTS = sorted(_SIGNATURES)
 

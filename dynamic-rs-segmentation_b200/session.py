@@ -278,6 +278,15 @@ class Session:
                                          L.PREC[precision], L.ptr(y)))
         return y
 
+    def debug_wgrad(self, x, dy, k, rate, precision="bf16"):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        dy = np.ascontiguousarray(dy, dtype=np.float32)
+        B, crop, _, ci = x.shape
+        co = dy.shape[-1]
+        dw = np.empty((k, k, ci, co), dtype=np.float32)
+        L.check(self._lib.drs_debug_wgrad(self._h, L.ptr(x), L.ptr(dy), B, crop, k, rate, ci, co, L.PREC[precision], L.ptr(dw)))
+        return dw
+
 
 def grid_positions(H, W, crop, batch, variant="isprs"):
     """Visiting order of create_patches_per_map over a whole scene (host code inside libdrs, no GPU)."""

@@ -183,6 +183,12 @@ int drs_debug_conv(drs_handle_t h, const float* x_host, const float* w_host, con
                    const float* shift_host, int32_t B, int32_t crop, int32_t k, int32_t rate, int32_t Ci, int32_t Co,
                    int32_t act, int32_t precision, float* y_host);
 
+/* unit-test entry: filter gradient of one dilated SAME convolution (the wgrad inside isprs:1687 minimize):
+ *   x [B,crop,crop,Ci], dy [B,crop,crop,Co] fp32 host -> dw [k,k,Ci,Co] fp32 host.
+ *   precision BF16: tcgen05 MN-major path (operands rounded to bf16); FP32: CUDA-core fixed-order path. */
+int drs_debug_wgrad(drs_handle_t h, const float* x_host, const float* dy_host, int32_t B, int32_t crop, int32_t k,
+                    int32_t rate, int32_t Ci, int32_t Co, int32_t precision, float* dw_host);
+
 #ifdef __cplusplus
 }
 #endif
