@@ -213,10 +213,10 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __
 template <typename TIn, typename TG>
 static void launch_wgrad_simt(Handle* h, const TIn* in, int in_cstride, int in_coff, int ci, const TG* dy,
                               int dy_cstride, int dy_coff, int co, float* dw, float* part, int max_splits, int B,
-                              int crop, int k, int rate, int pad_b) {
+                              int crop, int k, int rate, int pad_b, int m_per_split_target = 2048) {
   const int64_t M = (int64_t)B * crop * crop;
   const int Ktot = k * k * ci;
-  int splits = (int)ceil_div(M, 2048);
+  int splits = (int)ceil_div(M, m_per_split_target);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   int m_per = (int)round_up(ceil_div(M, splits), SIMT_BK);

@@ -94,6 +94,7 @@ struct HandleExtra {
   float* loss_dev = nullptr;      // [4]: ce, l2, count, spare
   unsigned int* cm_dev = nullptr; // [K*K+1]
   unsigned int* count_dev = nullptr;
+  unsigned int* bn_counter = nullptr;   // last-block-done counter of bn_partial_kernel (self-resetting)
   float* ones = nullptr;          // [512]
   float* zeros = nullptr;         // [512]
   float* cls_w_eval = nullptr;
@@ -165,6 +166,8 @@ extern "C" int drs_create(drs_handle_t* out, const drs_config* cfg) {
   CUDA_CHECK(cudaMalloc(&x->loss_dev, 16 * 4));
   CUDA_CHECK(cudaMalloc(&x->cm_dev, (MAX_CLASSES * MAX_CLASSES + 1) * 4));
   CUDA_CHECK(cudaMalloc(&x->count_dev, 16));
+  CUDA_CHECK(cudaMemset(x->count_dev, 0, 16));
+  x->bn_counter = x->count_dev + 2;
   CUDA_CHECK(cudaMalloc(&x->ones, 512 * 4));
   CUDA_CHECK(cudaMalloc(&x->zeros, 512 * 4));
   CUDA_CHECK(cudaMemset(x->zeros, 0, 512 * 4));
@@ -455,6 +458,13 @@ static void run_conv(Handle* h, const ActBuf& in, int ci, const float* w_simt, c
 // ------------------------------------------------------------------------------------------------
 // inference forward (eval-mode BN folded into the conv epilogue)
 // ------------------------------------------------------------------------------------------------
+static size_t forward_eval_workspace(Handle* h, int B, int crop) {
+  const int64_t M = (int64_t)B * crop * crop;
+  const size_t es = h->cfg.precision == DRS_PREC_FP32 ? 4 : 2;
+  const int nbuf = h->net.dense ? 1 : 3;
+  return nbuf * ((size_t)M * h->net.feat_stride * es + 4096) + (size_t)M * h->net.classes * 4 + 65536;
+}
+
 template <typename TA>
 static void forward_eval_t(Handle* h, const float* x_dev, int B, int crop, float* logits_dev, uint8_t* pred_dev) {
   NetDesc& n = h->net;
@@ -463,7 +473,7 @@ static void forward_eval_t(Handle* h, const float* x_dev, int B, int crop, float
   const int fs = n.feat_stride;
   const size_t buf_bytes = (size_t)M * fs * sizeof(TA);
   const int nbuf = n.dense ? 1 : 3;
-  ensure_arena(h, nbuf * (buf_bytes + 4096) + (size_t)M * n.classes * 4 + 65536);
+  ensure_arena(h, forward_eval_workspace(h, B, crop));
   h->arena.reset();
   TA* bufs[3] = {nullptr, nullptr, nullptr};
   for (int i = 0; i < nbuf; ++i) bufs[i] = (TA*)arena_take(h, buf_bytes);

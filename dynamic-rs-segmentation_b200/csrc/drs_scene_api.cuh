@@ -232,6 +232,17 @@ extern "C" int drs_accumulate_argmax(drs_handle_t h, const float* logits_dev, co
   API_END
 }
 
+// Two lanes (stream + workspace each) alternate over the chunks of a scene: while lane A's tensor-core convolutions
+// run, lane B's HBM-bound kernels (gather, conv1, pooling, classifier) fill the rest of the machine.  The ordered
+// accumulation stays on the handle's stream, chunk after chunk, so per-pixel sums keep the script's visiting order.
+struct InferLane {
+  cudaStream_t stream = nullptr;
+  Arena arena;
+  float* x = nullptr;
+  float* lg = nullptr;
+  cudaEvent_t fwd_done = nullptr, acc_done = nullptr;
+};
+
 extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, int32_t batch, int32_t variant, int32_t row_begin,
                                int32_t row_end, uint8_t* labels_out_host, double* mean_out_host) {
   API_BEGIN
@@ -253,17 +264,32 @@ extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, i
   CellTables ct;
   build_cells(pos, H, W, crop, ct);
   const int rows = row_end - row_begin;
-  const int64_t max_pix = (int64_t)3 << 19;   // ~1.5 M patch pixels per forward chunk
-  int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(P, max_pix / ((int64_t)crop * crop)));
+  // chunk = a whole number of 128-pixel tiles close to a multiple of the SM count (full conv waves), ~0.75 M pixels
+  const int64_t pp = (int64_t)crop * crop;
+  const int64_t target_tiles = (int64_t)h->sm_count * 40;
+  int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(P, (target_tiles * CONV_TC_BM) / pp));
+  const int n_lanes = (P > chunk && !getenv("DRS_ONE_LANE")) ? 2 : 1;
   ScenePass sp;
   int32_t* inst_dev = nullptr;
-  float* x_dev = nullptr;
-  float* lg_dev = nullptr;
+  InferLane lanes[2];
+  cudaStream_t main_stream = h->stream;
+  Arena main_arena = h->arena;
+  cudaEvent_t ready = nullptr;
   auto cleanup = [&]() {
+    h->stream = main_stream;
+    h->arena = main_arena;
+    cudaStreamSynchronize(main_stream);
+    for (auto& L : lanes) {
+      if (L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
+      if (L.arena.base) cudaFree(L.arena.base);
+      if (L.x) cudaFree(L.x);
+      if (L.lg) cudaFree(L.lg);
+      if (L.fwd_done) cudaEventDestroy(L.fwd_done);
+      if (L.acc_done) cudaEventDestroy(L.acc_done);
+    }
+    if (ready) cudaEventDestroy(ready);
     sp.release();
     if (inst_dev) cudaFree(inst_dev);
-    if (x_dev) cudaFree(x_dev);
-    if (lg_dev) cudaFree(lg_dev);
   };
   try {
     scene_pass_begin(h, sp, ct, rows, W, K);
@@ -271,19 +297,43 @@ extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, i
     for (int p = 0; p < P; ++p) { inst[3 * p] = scene_id; inst[3 * p + 1] = pos[2 * p]; inst[3 * p + 2] = pos[2 * p + 1]; }
     CUDA_CHECK(cudaMalloc(&inst_dev, std::max<size_t>(inst.size(), 1) * 4));
     CUDA_CHECK(cudaMemcpyAsync(inst_dev, inst.data(), inst.size() * 4, cudaMemcpyHostToDevice, h->stream));
-    CUDA_CHECK(cudaMalloc(&x_dev, (size_t)chunk * crop * crop * C * 4));
-    CUDA_CHECK(cudaMalloc(&lg_dev, (size_t)chunk * crop * crop * K * 4));
-    for (int s0 = 0; s0 < P; s0 += chunk) {
+    refresh_packed(h, false);                       // packed weights / folded BN once, before the lanes start
+    CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(ready, main_stream));
+    const size_t arena_bytes = forward_eval_workspace(h, chunk, crop);
+    for (int l = 0; l < n_lanes; ++l) {
+      InferLane& L = lanes[l];
+      CUDA_CHECK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaMalloc(&L.arena.base, arena_bytes));
+      L.arena.cap = arena_bytes;
+      CUDA_CHECK(cudaMalloc(&L.x, (size_t)chunk * pp * C * 4));
+      CUDA_CHECK(cudaMalloc(&L.lg, (size_t)chunk * pp * K * 4));
+      CUDA_CHECK(cudaEventCreateWithFlags(&L.fwd_done, cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&L.acc_done, cudaEventDisableTiming));
+      CUDA_CHECK(cudaStreamWaitEvent(L.stream, ready, 0));
+    }
+    int ci = 0;
+    for (int s0 = 0; s0 < P; s0 += chunk, ++ci) {
+      InferLane& L = lanes[ci % n_lanes];
       const int nb = std::min(chunk, P - s0);
+      h->stream = L.stream;
+      h->arena = L.arena;
+      if (ci >= n_lanes) CUDA_CHECK(cudaStreamWaitEvent(L.stream, L.acc_done, 0));   // logits buffer consumed
       GatherParams gp;
       memset(&gp, 0, sizeof(gp));
       gp.inst = inst_dev + (size_t)s0 * 3;
-      gp.x_out = x_dev;
+      gp.x_out = L.x;
       gp.B = nb;
       gp.crop = crop;
       launch_gather(h, gp);
-      forward_eval(h, x_dev, nb, crop, lg_dev, nullptr);
-      accumulate_chunk(h, sp, ct, lg_dev, pos, s0, s0 + nb, H, W, K, crop, row_begin, row_end);
+      forward_eval(h, L.x, nb, crop, L.lg, nullptr);
+      CUDA_CHECK(cudaEventRecord(L.fwd_done, L.stream));
+      L.arena = h->arena;
+      h->stream = main_stream;
+      h->arena = main_arena;
+      CUDA_CHECK(cudaStreamWaitEvent(main_stream, L.fwd_done, 0));
+      accumulate_chunk(h, sp, ct, L.lg, pos, s0, s0 + nb, H, W, K, crop, row_begin, row_end);
+      CUDA_CHECK(cudaEventRecord(L.acc_done, main_stream));
     }
     scene_pass_finish(h, sp, rows, W, K, labels_out_host, mean_out_host);
   } catch (...) { cleanup(); throw; }

@@ -42,7 +42,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   add(M * maxc * es * 2);                     // G ping-pong / dense dgrad temp
   add(M * K * 4 * 2);                         // logits, dlogits
   add(M * 2);                                 // labels u8, pred
-  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 4);
+  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 2);
   const int bn_rows = (int)ceil_div(M, nb_bn);
   add((size_t)nb_bn * 2 * 256 * 4);
   const int nb_ce = (int)ceil_div(M, CE_THREADS);
@@ -113,26 +113,23 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     // batch statistics (biased variance), moving-average update          (isprs:658-660)
     float* mean = x->mean + c.mm_off;
     float* istd = x->inv_std + c.mm_off;
-    bn_partial_kernel<TA, TA, 0><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, nullptr, 0, 0, nullptr, nullptr, 0, part_bn, c.co, M, bn_rows);
+    BnFinish fin{x->bn_counter, x->sums, nullptr, nullptr, nullptr, nullptr, bn_count, h->cfg.bn_eps, h->cfg.bn_decay, h->cfg.bn_unbiased_ema};
+    if (!h->sync_bn) { fin.mean = mean; fin.inv_std = istd; fin.mov_mean = h->bnstat + c.mm_off; fin.mov_var = h->bnstat + c.mv_off; }
+    bn_partial_kernel<TA, TA, 0><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, nullptr, 0, 0, nullptr, nullptr, 0, part_bn, c.co, M, bn_rows, fin);
     LAUNCH_CHECK(h);
     if (h->sync_bn) {
-      bn_reduce_kernel<<<nblk(c.co, 32), 256, 0, h->stream>>>(part_bn, x->sums, c.co, nb_bn, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0f, 0.0f, 0);
-      LAUNCH_CHECK(h);
       do_allreduce(h, x->sums, 2 * c.co);
       bn_finalize_kernel<<<nblk(c.co, 128), 128, 0, h->stream>>>(x->sums, mean, istd, h->bnstat + c.mm_off, h->bnstat + c.mv_off, c.co,
                                                                   bn_count, h->cfg.bn_eps, h->cfg.bn_decay, h->cfg.bn_unbiased_ema);
       LAUNCH_CHECK(h);
-    } else {
-      bn_reduce_kernel<<<nblk(c.co, 32), 256, 0, h->stream>>>(part_bn, x->sums, c.co, nb_bn, mean, istd, h->bnstat + c.mm_off, h->bnstat + c.mv_off,
-                                                               bn_count, h->cfg.bn_eps, h->cfg.bn_decay, h->cfg.bn_unbiased_ema);
-      LAUNCH_CHECK(h);
     }
-    // normalise + activation (+ pool)
-    ActBuf ab = n.pool ? ActBuf{T, c.co, 0} : (n.dense ? ActBuf{F, n.feat_stride, c.out_coff} : ActBuf{Xn[l], c.co, 0});
-    bn_apply_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>(Z[l], c.co, 0, mean, istd, n.act, (TA*)ab.p, ab.cs, ab.co, c.co, M);
-    LAUNCH_CHECK(h);
+    // normalise + activation (+ pool).  Pooling nets: one kernel pools the raw conv output and normalises the winner.
     if (n.pool) {
-      launch_maxpool3_fwd<TA>(h, T, c.co, 0, Xn[l], c.co, 0, idx[l], c.co, B, crop);
+      launch_maxpool3_fwd<TA>(h, Z[l], c.co, 0, Xn[l], c.co, 0, idx[l], c.co, B, crop, mean, istd, n.act);
+    } else {
+      ActBuf ab = n.dense ? ActBuf{F, n.feat_stride, c.out_coff} : ActBuf{Xn[l], c.co, 0};
+      bn_apply_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>(Z[l], c.co, 0, mean, istd, n.act, (TA*)ab.p, ab.cs, ab.co, c.co, M);
+      LAUNCH_CHECK(h);
     }
     h->taps[c.scope] = {n.dense ? (void*)F : (void*)Xn[l], ElemTag<TA>::v, n.dense ? n.feat_stride : c.co, n.dense ? c.out_coff : 0, c.co, M};
   }
@@ -200,9 +197,8 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     }
     float* mean = x->mean + c.mm_off;
     float* istd = x->inv_std + c.mm_off;
-    bn_partial_kernel<TA, TA, 1><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, n.act, part_bn, c.co, M, bn_rows);
-    LAUNCH_CHECK(h);
-    bn_reduce_kernel<<<nblk(c.co, 32), 256, 0, h->stream>>>(part_bn, x->sums, c.co, nb_bn, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0f, 0.0f, 0);
+    BnFinish finb{x->bn_counter, x->sums, nullptr, nullptr, nullptr, nullptr, bn_count, 0.0f, 0.0f, 0};
+    bn_partial_kernel<TA, TA, 1><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, n.act, part_bn, c.co, M, bn_rows, finb);
     LAUNCH_CHECK(h);
     if (h->sync_bn) do_allreduce(h, x->sums, 2 * c.co);
     bn_bwd_apply_kernel<TA, TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, x->sums,
@@ -213,7 +209,9 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     // wgrad (bias gradient is identically zero behind a BN without beta: sum_m dZ = 0)
     ActBuf xin = input_of(l);
     if (l == 0) {
-      launch_wgrad_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, DZ, c.co, 0, c.co, h->grads + c.w_off, part_w, max_splits, B, crop, c.k, c.rate, c.pad_b);
+      // conv1: K = 25*C <= 125 rows only -> parallelism must come from many short pixel splits
+      const int conv1_splits = (int)std::min<int64_t>((int64_t)(max_w * max_splits) / ((int64_t)c.k * c.k * c.ci * c.co), 4 * h->sm_count);
+      launch_wgrad_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, DZ, c.co, 0, c.co, h->grads + c.w_off, part_w, conv1_splits, B, crop, c.k, c.rate, c.pad_b, 256);
     } else if (ElemTag<TA>::v == ET_BF16 && wgrad_tc_supported(c.ci, c.co)) {
       WgradTcArgs wa;
       wa.x = xin.p; wa.in_cstride = xin.cs; wa.in_coff = xin.co; wa.ci = c.ci;

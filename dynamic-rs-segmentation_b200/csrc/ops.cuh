@@ -43,7 +43,8 @@ __device__ __forceinline__ void pool_row_max(const T* __restrict__ in, int in_cs
 template <typename T, bool WITH_IDX>
 __global__ void __launch_bounds__(256)
 maxpool3_fwd_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __restrict__ out, int out_cs, int out_co,
-                    uint8_t* __restrict__ idx, int C, int B, int crop, int seg, int nseg) {
+                    uint8_t* __restrict__ idx, int C, int B, int crop, int seg, int nseg, const float* __restrict__ bn_mean,
+                    const float* __restrict__ bn_inv_std, int act) {
   const int cv = C >> 3;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (int64_t)B * nseg * crop * cv) return;
@@ -58,6 +59,13 @@ maxpool3_fwd_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __restric
   const T* inp = in + in_co + cg * 8;
   float r0[8], r1[8], r2[8];
   int d0[8], d1[8], d2[8];
+  // Training forward of the pooling nets: max-pool commutes with the (strictly increasing) normalise + LeakyReLU, so the
+  // pool runs on the raw conv output and act((max - mean) * inv_std) is applied to the winner only.
+  float mu[8], is[8];
+  if (bn_mean) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { mu[e] = bn_mean[cg * 8 + e]; is[e] = bn_inv_std[cg * 8 + e]; }
+  }
   pool_row_max<T, WITH_IDX>(inp, in_cs, img0, x, crop, y0 - 1, r0, d0);
   pool_row_max<T, WITH_IDX>(inp, in_cs, img0, x, crop, y0, r1, d1);
   for (int y = y0; y < y1; ++y) {
@@ -71,6 +79,7 @@ maxpool3_fwd_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __restric
       int c = d0[e];
       if (r1[e] > best) { best = r1[e]; c = 3 + d1[e]; }
       if (r2[e] > best) { best = r2[e]; c = 6 + d2[e]; }
+      if (bn_mean) best = apply_act((best - mu[e]) * is[e], act);
       o.v[e] = from_f32<T>(best);
       code[e] = c;
     }
@@ -89,14 +98,14 @@ maxpool3_fwd_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __restric
 
 template <typename T>
 static void launch_maxpool3_fwd(Handle* h, const T* in, int in_cs, int in_co, T* out, int out_cs, int out_co, uint8_t* idx, int C,
-                                int B, int crop) {
+                                int B, int crop, const float* bn_mean = nullptr, const float* bn_inv_std = nullptr, int act = 0) {
   const int64_t base = (int64_t)B * crop * (C / 8);
   int nseg = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div((int64_t)h->sm_count * 2048, base)), std::max(1, crop / 4));
   const int seg = (int)ceil_div(crop, nseg);
   nseg = (int)ceil_div(crop, seg);
   const int64_t total = base * nseg;
-  if (idx) maxpool3_fwd_kernel<T, true><<<(unsigned)ceil_div(total, 256), 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, idx, C, B, crop, seg, nseg);
-  else maxpool3_fwd_kernel<T, false><<<(unsigned)ceil_div(total, 256), 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, nullptr, C, B, crop, seg, nseg);
+  if (idx) maxpool3_fwd_kernel<T, true><<<(unsigned)ceil_div(total, 256), 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, idx, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
+  else maxpool3_fwd_kernel<T, false><<<(unsigned)ceil_div(total, 256), 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, nullptr, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
   LAUNCH_CHECK(h);
 }
 
@@ -145,6 +154,19 @@ __global__ void maxpool3_bwd_kernel(const T* __restrict__ dout, int do_cs, int d
 // ------------------------------------------------------------------------------------------------
 constexpr int BN_THREADS = 256;
 
+// what the last block of bn_partial_kernel does with the reduced sums
+struct BnFinish {
+  unsigned int* counter;   // zero before the launch; reset by the kernel
+  float* sums;             // [2][C] out
+  float* mean;             // non-null: also finalize (batch mean / inv_std, moving-average update)
+  float* inv_std;
+  float* mov_mean;
+  float* mov_var;
+  double count;
+  float eps, decay;
+  int unbiased_ema;
+};
+
 // part[blk][0][c] = sum_m a, part[blk][1][c] = sum_m a*b over the block's contiguous slab of rows.
 //   MODE 0 (forward statistics):  a = z,            b = z
 //   MODE 1 (backward sums):       a = g = dA*act'(xh), b = xh        (xh = (z-mean)*inv_std)
@@ -154,8 +176,8 @@ template <typename TZ, typename TG, int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __restrict__ dA, int g_cs, int g_co,
                   const float* __restrict__ mean, const float* __restrict__ inv_std, int act, float* __restrict__ part, int C,
-                  int64_t M, int rows_per_block) {
-  __shared__ float s_red[BN_THREADS * 16];
+                  int64_t M, int rows_per_block, BnFinish fin) {
+  __shared__ __align__(16) float s_red[BN_THREADS * 16];
   const int cv = C >> 3;
   const int lanes_r = BN_THREADS / cv;
   const int cg = threadIdx.x % cv, rl = threadIdx.x / cv;
@@ -205,42 +227,49 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
     for (int r = 0; r < lanes_r; ++r) a += s_red[(r * cv + g) * 16 + which * 8 + e];
     part[((int64_t)blockIdx.x * 2 + which) * C + c] = a;
   }
-}
-
-// sums[0][c], sums[1][c] = fixed-order (double) reduction over blocks: 8 interleaved lanes per channel, then a fixed-order
-// combine.  When `mean` is given (single process, or sync_bn off) the finalize step is fused in.
-__global__ void __launch_bounds__(256)
-bn_reduce_kernel(const float* __restrict__ part, float* __restrict__ sums, int C, int nblk, float* __restrict__ mean,
-                 float* __restrict__ inv_std, float* __restrict__ mov_mean, float* __restrict__ mov_var, double count, float eps,
-                 float decay, int unbiased_ema) {
-  __shared__ double s_a[8][32], s_b[8][32];
-  const int cl = threadIdx.x & 31, j = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  double a = 0.0, b = 0.0;
-  if (c < C) {
-    for (int k = j; k < nblk; k += 8) {
-      a += (double)part[((int64_t)k * 2 + 0) * C + c];
-      b += (double)part[((int64_t)k * 2 + 1) * C + c];
-    }
-  }
-  s_a[j][cl] = a;
-  s_b[j][cl] = b;
+  // ---- the last block to finish reduces the per-block partials in block order (fixed order => deterministic)
+  __shared__ bool s_last;
+  __threadfence();
   __syncthreads();
-  if (j == 0 && c < C) {
-    for (int r = 1; r < 8; ++r) { a += s_a[r][cl]; b += s_b[r][cl]; }
-    sums[c] = (float)a;
-    sums[C + c] = (float)b;
-    if (mean) {
-      const double mu = (double)(float)a / count;
-      double var = (double)(float)b / count - mu * mu;
+  if (threadIdx.x == 0) s_last = (atomicAdd(fin.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double* s_sum = reinterpret_cast<double*>(s_red);          // [lanes_k][2C] doubles (<= 16 KB)
+  const int groups = (2 * C) >> 2;                           // float4 column groups
+  const int lanes_k = BN_THREADS / groups;
+  const int gq = threadIdx.x % groups, lk = threadIdx.x / groups;
+  const int nblk = gridDim.x;
+  if (lk < lanes_k) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int k = lk; k < nblk; k += lanes_k) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (int64_t)k * 2 * C) + gq);
+      a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+    }
+    double* d = s_sum + ((size_t)lk * groups + gq) * 4;
+    d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += BN_THREADS) {
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < lanes_k; ++r) {
+      a += s_sum[(size_t)r * 2 * C + i];
+      b += s_sum[(size_t)r * 2 * C + C + i];
+    }
+    fin.sums[i] = (float)a;
+    fin.sums[C + i] = (float)b;
+    if (fin.mean) {
+      const double mu = (double)(float)a / fin.count;
+      double var = (double)(float)b / fin.count - mu * mu;
       if (var < 0.0) var = 0.0;
-      mean[c] = (float)mu;
-      inv_std[c] = (float)(1.0 / sqrt(var + (double)eps));
-      const double var_ema = unbiased_ema ? var * (count / fmax(count - 1.0, 1.0)) : var;
-      mov_mean[c] = decay * mov_mean[c] + (1.0f - decay) * (float)mu;
-      mov_var[c] = decay * mov_var[c] + (1.0f - decay) * (float)var_ema;
+      fin.mean[i] = (float)mu;
+      fin.inv_std[i] = (float)(1.0 / sqrt(var + (double)fin.eps));
+      const double var_ema = fin.unbiased_ema ? var * (fin.count / fmax(fin.count - 1.0, 1.0)) : var;
+      fin.mov_mean[i] = fin.decay * fin.mov_mean[i] + (1.0f - fin.decay) * (float)mu;
+      fin.mov_var[i] = fin.decay * fin.mov_var[i] + (1.0f - fin.decay) * (float)var_ema;
     }
   }
+  if (threadIdx.x == 0) *fin.counter = 0u;                   // ready for the next launch on this stream
 }
 
 // mean / inv_std from (possibly all-reduced) sums; moving-average update (decay 0.999, isprs:658 defaults)

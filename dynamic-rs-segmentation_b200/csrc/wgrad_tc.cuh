@@ -254,8 +254,9 @@ static void launch_wgrad_tc(Handle* h, const WgradTcArgs& a) {
   while (p.tmem_cols < T * p.acc_stride) p.tmem_cols *= 2;
   p.n_groups = (p.n_tiles + T - 1) / T;
   p.n_chunks = (int)ceil_div(M, WG_BPX);
-  // pixel splits: fill the machine (about two work items per SM), keep >= 8 chunks per split, fit the workspace
-  int splits = (int)ceil_div(2 * h->sm_count, p.n_groups);
+  // pixel splits: one work item per SM (every extra split costs a K*Co fp32 partial write + read), keep >= 8 chunks per
+  // split, fit the workspace
+  int splits = std::max(1, h->sm_count / p.n_groups);
   splits = std::min<int>(splits, std::max(1, p.n_chunks / 8));
   splits = std::min<int64_t>(splits, (int64_t)(a.part_capacity / ((size_t)Ktot * a.co)));
   DRS_CHECK(splits >= 1, "wgrad_tc: workspace too small");
