@@ -84,7 +84,18 @@ static void build_net(NetDesc& n, const drs_config& cfg) {
 extern "C" const char* drs_last_error(void) { return g_drs_err; }
 extern "C" int drs_version(void) { return DRS_VERSION; }
 
+struct InferLane {
+  cudaStream_t stream = nullptr;
+  Arena arena;
+  float* x = nullptr;
+  float* lg = nullptr;
+  size_t x_cap = 0, lg_cap = 0;
+  cudaEvent_t fwd_done = nullptr, acc_done = nullptr;
+};
+
 struct HandleExtra {
+  InferLane lanes[2];             // scene-inference lanes (drs_scene_api.cuh)
+  cudaEvent_t lanes_ready = nullptr;
   uint8_t* is_weight = nullptr;   // [n_trainable] 1 for `weights` variables
   SceneTable table;               // host copy of the device scene table
   // training scratch kept between calls
@@ -107,6 +118,7 @@ struct HandleExtra {
 };
 static std::map<Handle*, HandleExtra*> g_extra;
 static HandleExtra* X(Handle* h) { return g_extra[h]; }
+static void lanes_release(Handle* h);
 
 static void free_packed(Handle* h) {
   for (auto& c : h->net.convs) {
@@ -204,6 +216,7 @@ extern "C" int drs_destroy(drs_handle_t h) {
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
   HandleExtra* x = X(h);
+  if (x) lanes_release(h);
   free_packed(h);
   for (auto& kv : h->scenes) {
     if (kv.second.data) cudaFree(kv.second.data);
@@ -382,7 +395,18 @@ static void refresh_packed(Handle* h, bool training) {
     fold_bn_kernel<<<nblk(c.co, 128), 128, 0, h->stream>>>(h->params + c.b_off, h->bnstat + c.mm_off, h->bnstat + c.mv_off,
                                                             h->cfg.bn_eps, c.fold_scale, c.fold_shift, c.co);
     LAUNCH_CHECK(h);
-    if (l == 0) continue;   // conv1 always runs on the CUDA-core kernel straight from the HWIO weights
+    if (l == 0) {
+      // training and the fp32 mode run conv1 on the CUDA-core kernel straight from the HWIO weights; 16-bit inference
+      // runs it on the tensor cores with the input channels zero-padded to 32
+      if (et != ET_F32 && c.ci <= 8) {
+        const int64_t n = (int64_t)c.k * c.k * 32 * c.co;
+        if (!c.w_fprop) CUDA_CHECK(cudaMalloc(&c.w_fprop, n * 2));
+        if (et == ET_F16) pack_fprop_pad32_kernel<__half><<<nblk(n, 256), 256, 0, h->stream>>>(h->params + c.w_off, (__half*)c.w_fprop, c.k * c.k, c.ci, c.co);
+        else pack_fprop_pad32_kernel<__nv_bfloat16><<<nblk(n, 256), 256, 0, h->stream>>>(h->params + c.w_off, (__nv_bfloat16*)c.w_fprop, c.k * c.k, c.ci, c.co);
+        LAUNCH_CHECK(h);
+      }
+      continue;
+    }
     if (et == ET_F32) {
       const int taps = c.k * c.k;
       const int64_t n = (int64_t)taps * c.ci * c.co;
@@ -462,7 +486,7 @@ static size_t forward_eval_workspace(Handle* h, int B, int crop) {
   const int64_t M = (int64_t)B * crop * crop;
   const size_t es = h->cfg.precision == DRS_PREC_FP32 ? 4 : 2;
   const int nbuf = h->net.dense ? 1 : 3;
-  return nbuf * ((size_t)M * h->net.feat_stride * es + 4096) + (size_t)M * h->net.classes * 4 + 65536;
+  return nbuf * ((size_t)M * h->net.feat_stride * es + 4096) + (size_t)M * h->net.classes * 4 + (size_t)M * 32 * es + 65536;
 }
 
 template <typename TA>
@@ -487,7 +511,15 @@ static void forward_eval_t(Handle* h, const float* x_dev, int B, int crop, float
     ActBuf out;
     if (n.dense) out = {bufs[0], fs, c.out_coff};
     else out = {bufs[(xi + 1) % 3], fs, 0};
-    if (l == 0) {
+    if (l == 0 && ElemTag<TA>::v != ET_F32 && c.ci <= 8 && c.w_fprop) {
+      TA* xp = (TA*)arena_take(h, (size_t)M * 32 * sizeof(TA));
+      pad_cast32_kernel<TA><<<nblk(M * 4, 256), 256, 0, h->stream>>>(x_dev, xp, c.ci, M);
+      LAUNCH_CHECK(h);
+      const double fl0 = X(h)->conv_flops;
+      run_conv<TA>(h, ActBuf{xp, 32, 0}, 32, nullptr, c.w_fprop, out, c.co, B, crop, c.k, c.rate, c.pad_b, c.fold_scale,
+                   c.fold_shift, n.act);
+      X(h)->conv_flops = fl0 + 2.0 * (double)M * c.k * c.k * c.ci * c.co;   // algorithmic FLOPs: the real C channels
+    } else if (l == 0) {
       launch_conv_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, h->params + c.w_off, (TA*)out.p, out.cs, out.co, c.co,
                                   B, crop, c.k, c.rate, c.pad_b, c.fold_scale, c.fold_shift, n.act);
     } else {

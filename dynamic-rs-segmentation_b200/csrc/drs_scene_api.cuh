@@ -233,15 +233,48 @@ extern "C" int drs_accumulate_argmax(drs_handle_t h, const float* logits_dev, co
 }
 
 // Two lanes (stream + workspace each) alternate over the chunks of a scene: while lane A's tensor-core convolutions
-// run, lane B's HBM-bound kernels (gather, conv1, pooling, classifier) fill the rest of the machine.  The ordered
+// run, lane B's HBM-bound kernels (gather, pooling, classifier) fill the rest of the machine.  The ordered
 // accumulation stays on the handle's stream, chunk after chunk, so per-pixel sums keep the script's visiting order.
-struct InferLane {
-  cudaStream_t stream = nullptr;
-  Arena arena;
-  float* x = nullptr;
-  float* lg = nullptr;
-  cudaEvent_t fwd_done = nullptr, acc_done = nullptr;
-};
+// Lanes are kept in the handle between calls (their workspace is several GB for a Potsdam tile).
+static void lanes_release(Handle* h) {
+  HandleExtra* x = X(h);
+  for (auto& L : x->lanes) {
+    if (L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
+    if (L.arena.base) cudaFree(L.arena.base);
+    if (L.x) cudaFree(L.x);
+    if (L.lg) cudaFree(L.lg);
+    if (L.fwd_done) cudaEventDestroy(L.fwd_done);
+    if (L.acc_done) cudaEventDestroy(L.acc_done);
+    L = InferLane();
+  }
+  if (x->lanes_ready) cudaEventDestroy(x->lanes_ready);
+  x->lanes_ready = nullptr;
+}
+static void lanes_ensure(Handle* h, int n_lanes, size_t arena_bytes, size_t x_bytes, size_t lg_bytes) {
+  HandleExtra* x = X(h);
+  if (!x->lanes_ready) CUDA_CHECK(cudaEventCreateWithFlags(&x->lanes_ready, cudaEventDisableTiming));
+  for (int l = 0; l < n_lanes; ++l) {
+    InferLane& L = x->lanes[l];
+    if (!L.stream) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&L.fwd_done, cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&L.acc_done, cudaEventDisableTiming));
+    }
+    if (L.arena.cap < arena_bytes || L.x_cap < x_bytes || L.lg_cap < lg_bytes) {
+      CUDA_CHECK(cudaStreamSynchronize(L.stream));
+      if (L.arena.base) cudaFree(L.arena.base);
+      if (L.x) cudaFree(L.x);
+      if (L.lg) cudaFree(L.lg);
+      L.arena = Arena(); L.x = L.lg = nullptr; L.x_cap = L.lg_cap = 0;
+      CUDA_CHECK(cudaMalloc(&L.arena.base, arena_bytes));
+      L.arena.cap = arena_bytes;
+      CUDA_CHECK(cudaMalloc(&L.x, x_bytes));
+      L.x_cap = x_bytes;
+      CUDA_CHECK(cudaMalloc(&L.lg, lg_bytes));
+      L.lg_cap = lg_bytes;
+    }
+  }
+}
 
 extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, int32_t batch, int32_t variant, int32_t row_begin,
                                int32_t row_end, uint8_t* labels_out_host, double* mean_out_host) {
@@ -266,28 +299,21 @@ extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, i
   const int rows = row_end - row_begin;
   // chunk = a whole number of 128-pixel tiles close to a multiple of the SM count (full conv waves), ~0.75 M pixels
   const int64_t pp = (int64_t)crop * crop;
-  const int64_t target_tiles = (int64_t)h->sm_count * 40;
+  const int waves = getenv("DRS_CHUNK_WAVES") ? std::max(1, atoi(getenv("DRS_CHUNK_WAVES"))) : 40;
+  const int64_t target_tiles = (int64_t)h->sm_count * waves;
   int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(P, (target_tiles * CONV_TC_BM) / pp));
   const int n_lanes = (P > chunk && !getenv("DRS_ONE_LANE")) ? 2 : 1;
   ScenePass sp;
   int32_t* inst_dev = nullptr;
-  InferLane lanes[2];
+  HandleExtra* hx = X(h);
   cudaStream_t main_stream = h->stream;
   Arena main_arena = h->arena;
-  cudaEvent_t ready = nullptr;
   auto cleanup = [&]() {
     h->stream = main_stream;
     h->arena = main_arena;
     cudaStreamSynchronize(main_stream);
-    for (auto& L : lanes) {
-      if (L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
-      if (L.arena.base) cudaFree(L.arena.base);
-      if (L.x) cudaFree(L.x);
-      if (L.lg) cudaFree(L.lg);
-      if (L.fwd_done) cudaEventDestroy(L.fwd_done);
-      if (L.acc_done) cudaEventDestroy(L.acc_done);
-    }
-    if (ready) cudaEventDestroy(ready);
+    for (auto& L : hx->lanes)
+      if (L.stream) cudaStreamSynchronize(L.stream);
     sp.release();
     if (inst_dev) cudaFree(inst_dev);
   };
@@ -298,23 +324,12 @@ extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, i
     CUDA_CHECK(cudaMalloc(&inst_dev, std::max<size_t>(inst.size(), 1) * 4));
     CUDA_CHECK(cudaMemcpyAsync(inst_dev, inst.data(), inst.size() * 4, cudaMemcpyHostToDevice, h->stream));
     refresh_packed(h, false);                       // packed weights / folded BN once, before the lanes start
-    CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-    CUDA_CHECK(cudaEventRecord(ready, main_stream));
-    const size_t arena_bytes = forward_eval_workspace(h, chunk, crop);
-    for (int l = 0; l < n_lanes; ++l) {
-      InferLane& L = lanes[l];
-      CUDA_CHECK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
-      CUDA_CHECK(cudaMalloc(&L.arena.base, arena_bytes));
-      L.arena.cap = arena_bytes;
-      CUDA_CHECK(cudaMalloc(&L.x, (size_t)chunk * pp * C * 4));
-      CUDA_CHECK(cudaMalloc(&L.lg, (size_t)chunk * pp * K * 4));
-      CUDA_CHECK(cudaEventCreateWithFlags(&L.fwd_done, cudaEventDisableTiming));
-      CUDA_CHECK(cudaEventCreateWithFlags(&L.acc_done, cudaEventDisableTiming));
-      CUDA_CHECK(cudaStreamWaitEvent(L.stream, ready, 0));
-    }
+    lanes_ensure(h, n_lanes, forward_eval_workspace(h, chunk, crop), (size_t)chunk * pp * C * 4, (size_t)chunk * pp * K * 4);
+    CUDA_CHECK(cudaEventRecord(hx->lanes_ready, main_stream));
+    for (int l = 0; l < n_lanes; ++l) CUDA_CHECK(cudaStreamWaitEvent(hx->lanes[l].stream, hx->lanes_ready, 0));
     int ci = 0;
     for (int s0 = 0; s0 < P; s0 += chunk, ++ci) {
-      InferLane& L = lanes[ci % n_lanes];
+      InferLane& L = hx->lanes[ci % n_lanes];
       const int nb = std::min(chunk, P - s0);
       h->stream = L.stream;
       h->arena = L.arena;
@@ -328,7 +343,6 @@ extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, i
       launch_gather(h, gp);
       forward_eval(h, L.x, nb, crop, L.lg, nullptr);
       CUDA_CHECK(cudaEventRecord(L.fwd_done, L.stream));
-      L.arena = h->arena;
       h->stream = main_stream;
       h->arena = main_arena;
       CUDA_CHECK(cudaStreamWaitEvent(main_stream, L.fwd_done, 0));

@@ -21,21 +21,31 @@ struct alignas(16) Vec8 {
 // the horizontal 3-max of the two previous rows in registers, so every input element is loaded 3 times (from L1)
 // instead of 9.  Adjacent threads cover adjacent channel groups, then adjacent columns: each row access of a warp is
 // one contiguous run.
-template <typename T, bool WITH_IDX>
-__device__ __forceinline__ void pool_row_max(const T* __restrict__ in, int in_cs, int64_t pix_row0, int x, int crop, int y,
-                                             float (&v)[8], int (&d)[8]) {
-#pragma unroll
-  for (int e = 0; e < 8; ++e) { v[e] = -INFINITY; d[e] = 0; }
-  if (y < 0 || y >= crop) return;
+template <typename T>
+__device__ __forceinline__ void pool_row_load(const T* __restrict__ in, int in_cs, int64_t pix_row0, int x, int crop, int y,
+                                              Vec8<T> (&q)[3]) {
+  const T ninf = from_f32<T>(-INFINITY);
 #pragma unroll
   for (int dx = -1; dx <= 1; ++dx) {
     const int xx = x + dx;
-    if (xx < 0 || xx >= crop) continue;
-    const Vec8<T> q = *reinterpret_cast<const Vec8<T>*>(in + (pix_row0 + (int64_t)y * crop + xx) * in_cs);
+    if (y >= 0 && y < crop && xx >= 0 && xx < crop) {
+      q[dx + 1] = *reinterpret_cast<const Vec8<T>*>(in + (pix_row0 + (int64_t)y * crop + xx) * in_cs);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) q[dx + 1].v[e] = ninf;     // padding never wins (window clipped, isprs:745-750)
+    }
+  }
+}
+template <typename T, bool WITH_IDX>
+__device__ __forceinline__ void pool_row_reduce(const Vec8<T> (&q)[3], float (&v)[8], int (&d)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { v[e] = -INFINITY; d[e] = 0; }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float f = to_f32(q.v[e]);
-      if (f > v[e]) { v[e] = f; if (WITH_IDX) d[e] = dx + 1; }
+      const float f = to_f32(q[j].v[e]);
+      if (f > v[e]) { v[e] = f; if (WITH_IDX) d[e] = j; }
     }
   }
 }
@@ -66,10 +76,16 @@ maxpool3_fwd_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __restric
 #pragma unroll
     for (int e = 0; e < 8; ++e) { mu[e] = bn_mean[cg * 8 + e]; is[e] = bn_inv_std[cg * 8 + e]; }
   }
-  pool_row_max<T, WITH_IDX>(inp, in_cs, img0, x, crop, y0 - 1, r0, d0);
-  pool_row_max<T, WITH_IDX>(inp, in_cs, img0, x, crop, y0, r1, d1);
+  Vec8<T> qa[3], qb[3];
+  pool_row_load<T>(inp, in_cs, img0, x, crop, y0 - 1, qa);
+  pool_row_load<T>(inp, in_cs, img0, x, crop, y0, qb);
+  pool_row_reduce<T, WITH_IDX>(qa, r0, d0);
+  pool_row_load<T>(inp, in_cs, img0, x, crop, y0 + 1, qa);     // stays in flight while row y0 is reduced
+  pool_row_reduce<T, WITH_IDX>(qb, r1, d1);
   for (int y = y0; y < y1; ++y) {
-    pool_row_max<T, WITH_IDX>(inp, in_cs, img0, x, crop, y + 1, r2, d2);
+    // software pipeline: the loads of row y+2 are issued before row y+1 (already in registers) is consumed
+    pool_row_load<T>(inp, in_cs, img0, x, crop, (y + 1 < y1) ? y + 2 : crop, qb);
+    pool_row_reduce<T, WITH_IDX>(qa, r2, d2);
     Vec8<T> o;
     int code[8];
 #pragma unroll
@@ -93,6 +109,8 @@ maxpool3_fwd_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __restric
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) { r0[e] = r1[e]; r1[e] = r2[e]; d0[e] = d1[e]; d1[e] = d2[e]; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) qa[j] = qb[j];
   }
 }
 
