@@ -16,7 +16,7 @@ OUT = os.path.join(PKG, "libdrs.so")
 STAMP = os.path.join(PKG, ".libdrs.stamp")
 SOURCES = ["drs_api.cu"]
 DEPS = ["drs_api.cu", "drs_train.cuh", "drs_scene_api.cuh", "drs_common.cuh", "ptx_sm100.cuh", "conv_tc.cuh",
-        "conv_simt.cuh", "ops.cuh", "scene.cuh", "wgrad_tc.cuh", "../../include/drs.h"]
+        "conv_simt.cuh", "ops.cuh", "scene.cuh", "wgrad_tc.cuh", "conv1_tc.cuh", "../../include/drs.h"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler",
          "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr", "-cudart", "static"]
 

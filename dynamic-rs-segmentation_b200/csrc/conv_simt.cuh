@@ -243,30 +243,6 @@ __global__ void pack_fprop_kernel(const float* __restrict__ w, T* __restrict__ o
   const int kk = (int)(i - (int64_t)o * taps * ci);
   out[i] = from_f32<T>(w[(int64_t)kk * co + o]);
 }
-// conv1 on the tensor cores: the C = 3..5 input channels are zero-padded to 32 so that one K step is a 64-byte
-// (32 x 16-bit) im2col row.  Wf[co][tap*32 + c] = c < ci ? W[tap][c][co] : 0
-template <typename T>
-__global__ void pack_fprop_pad32_kernel(const float* __restrict__ w, T* __restrict__ out, int taps, int ci, int co) {
-  const int64_t n = (int64_t)taps * 32 * co;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int o = (int)(i / ((int64_t)taps * 32));
-  const int r = (int)(i - (int64_t)o * taps * 32);
-  const int tap = r >> 5, c = r & 31;
-  out[i] = from_f32<T>(c < ci ? w[((int64_t)tap * ci + c) * co + o] : 0.0f);
-}
-// x [M][C] fp32 -> [M][32] 16-bit, zero padded (C <= 8)
-template <typename T>
-__global__ void pad_cast32_kernel(const float* __restrict__ x, T* __restrict__ out, int C, int64_t M) {
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= M * 4) return;
-  const int64_t m = gid >> 2;
-  const int g = (int)(gid & 3);
-  alignas(16) T v[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) v[e] = from_f32<T>((g == 0 && e < C) ? x[m * C + e] : 0.0f);
-  *reinterpret_cast<uint4*>(out + m * 32 + g * 8) = *reinterpret_cast<const uint4*>(v);
-}
 // dgrad operand  Wd[c][tap'*co + o] = W[taps-1-tap'][c][o]   (K-major for the tensor-core path)
 template <typename T>
 __global__ void pack_dgrad_kernel(const float* __restrict__ w, T* __restrict__ out, int taps, int ci, int co) {

@@ -300,7 +300,10 @@ static void encode_im2col(Handle* h, CUtensorMap* tm, int etype, const void* bas
   int lower[2] = {-pad_b, -pad_b};
   int upper[2] = {-pad_b, -pad_b};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                        : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                        : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
+                                               : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = h->encodeIm2col(tm, tm_dtype(etype), 4, const_cast<void*>(base), dims, strides, lower, upper,
                                (cuuint32_t)channels_per_pixel, (cuuint32_t)pixels_per_column, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -8,6 +8,7 @@
 #include "ops.cuh"
 #include "scene.cuh"
 #include "wgrad_tc.cuh"
+#include "conv1_tc.cuh"
 
 thread_local char g_drs_err[1024] = {0};
 
@@ -106,6 +107,7 @@ struct HandleExtra {
   unsigned int* cm_dev = nullptr; // [K*K+1]
   unsigned int* count_dev = nullptr;
   unsigned int* bn_counter = nullptr;   // last-block-done counter of bn_partial_kernel (self-resetting)
+  long long* bn_acc = nullptr;          // [2*512] fixed-point accumulators of bn_partial_kernel (self-clearing)
   float* ones = nullptr;          // [512]
   float* zeros = nullptr;         // [512]
   float* cls_w_eval = nullptr;
@@ -180,6 +182,8 @@ extern "C" int drs_create(drs_handle_t* out, const drs_config* cfg) {
   CUDA_CHECK(cudaMalloc(&x->count_dev, 16));
   CUDA_CHECK(cudaMemset(x->count_dev, 0, 16));
   x->bn_counter = x->count_dev + 2;
+  CUDA_CHECK(cudaMalloc(&x->bn_acc, 2 * 512 * 8));
+  CUDA_CHECK(cudaMemset(x->bn_acc, 0, 2 * 512 * 8));
   CUDA_CHECK(cudaMalloc(&x->ones, 512 * 4));
   CUDA_CHECK(cudaMalloc(&x->zeros, 512 * 4));
   CUDA_CHECK(cudaMemset(x->zeros, 0, 512 * 4));
@@ -206,6 +210,7 @@ extern "C" int drs_create(drs_handle_t* out, const drs_config* cfg) {
   CUDA_CHECK(cudaEventCreate(&h->ev_a));
   CUDA_CHECK(cudaEventCreate(&h->ev_b));
   h->packed_dirty = true;
+  h->eval_dirty = true;
   *out = h;
   API_END
 }
@@ -229,7 +234,7 @@ extern "C" int drs_destroy(drs_handle_t h) {
   if (h->diag_host) cudaFreeHost(h->diag_host);
   if (x) {
     cudaFree(x->is_weight); cudaFree(x->mean); cudaFree(x->inv_std); cudaFree(x->sums); cudaFree(x->loss_dev);
-    cudaFree(x->cm_dev); cudaFree(x->count_dev); cudaFree(x->ones); cudaFree(x->zeros);
+    cudaFree(x->cm_dev); cudaFree(x->count_dev); cudaFree(x->bn_acc); cudaFree(x->ones); cudaFree(x->zeros);
     delete x;
     g_extra.erase(h);
   }
@@ -326,6 +331,7 @@ extern "C" int drs_set_variable(drs_handle_t h, const char* name, const float* d
   CUDA_CHECK(cudaMemcpyAsync(r.ptr, data, count * 4, cudaMemcpyHostToDevice, h->stream));
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   h->packed_dirty = true;
+  h->eval_dirty = true;
   API_END
 }
 extern "C" int drs_get_variable(drs_handle_t h, const char* name, float* data, int64_t count) {
@@ -370,57 +376,100 @@ static void do_allreduce(Handle* h, float* buf, int64_t count) {
 // ------------------------------------------------------------------------------------------------
 // packed operands / folded BN refresh (after set_variable or an optimizer step)
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-static void pack_layer_t(Handle* h, ConvLayer& c, bool need_dgrad) {
-  const int taps = c.k * c.k;
-  const int64_t n = (int64_t)taps * c.ci * c.co;
-  if (!c.w_fprop) CUDA_CHECK(cudaMalloc(&c.w_fprop, n * sizeof(T)));
-  pack_fprop_kernel<T><<<nblk(n, 256), 256, 0, h->stream>>>(h->params + c.w_off, (T*)c.w_fprop, taps, c.ci, c.co);
-  LAUNCH_CHECK(h);
-  if (need_dgrad) {
-    if (!c.w_dgrad) CUDA_CHECK(cudaMalloc(&c.w_dgrad, n * sizeof(T)));
-    pack_dgrad_kernel<T><<<nblk(n, 256), 256, 0, h->stream>>>(h->params + c.w_off, (T*)c.w_dgrad, taps, c.ci, c.co);
-    LAUNCH_CHECK(h);
+// One launch repacks the operand matrices of every tensor-core layer after set_variable / an optimizer step:
+//   kind 0  fprop operand  Wf[co][tap*ci + c]            = W[tap][c][co]
+//   kind 1  dgrad operand  Wd[c][tap'*co + o]            = W[taps-1-tap'][c][o]
+//   kind 2  dgrad operand of the fp32 CUDA-core path  [tap'*co + o][c]
+struct RepackSeg {
+  const float* w;
+  void* out;
+  int taps, ci, co, kind;
+  long long start;
+};
+struct RepackTable {
+  RepackSeg seg[18];
+  int n, etype;
+  long long total;
+};
+__global__ void repack_kernel(const __grid_constant__ RepackTable t) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= t.total) return;
+  int si = 0;
+  while (si + 1 < t.n && gid >= t.seg[si + 1].start) ++si;
+  const RepackSeg& s = t.seg[si];
+  const long long i = gid - s.start;
+  float v;
+  if (s.kind == 0) {
+    const int o = (int)(i / ((long long)s.taps * s.ci));
+    const int kk = (int)(i - (long long)o * s.taps * s.ci);
+    v = s.w[(long long)kk * s.co + o];
+  } else if (s.kind == 1) {
+    const int c = (int)(i / ((long long)s.taps * s.co));
+    const int r = (int)(i - (long long)c * s.taps * s.co);
+    const int tp = r / s.co, o = r - tp * s.co;
+    v = s.w[((long long)(s.taps - 1 - tp) * s.ci + c) * s.co + o];
+  } else {
+    const int c = (int)(i % s.ci);
+    const int r = (int)(i / s.ci);
+    const int tp = r / s.co, o = r - tp * s.co;
+    v = s.w[((long long)(s.taps - 1 - tp) * s.ci + c) * s.co + o];
   }
+  if (s.kind == 2 || t.etype == ET_F32) reinterpret_cast<float*>(s.out)[i] = v;
+  else if (t.etype == ET_F16) reinterpret_cast<__half*>(s.out)[i] = __float2half_rn(v);
+  else reinterpret_cast<__nv_bfloat16*>(s.out)[i] = __float2bfloat16_rn(v);
 }
+
+// training needs only the layer operands; inference additionally the folded eval-mode BN and conv1's tensor-core operand
 static void refresh_packed(Handle* h, bool training) {
-  if (!h->packed_dirty) return;
   const int et = act_type(h);
-  for (size_t l = 0; l < h->net.convs.size(); ++l) {
-    ConvLayer& c = h->net.convs[l];
-    if (!c.fold_scale) {
-      CUDA_CHECK(cudaMalloc(&c.fold_scale, c.co * 4));
-      CUDA_CHECK(cudaMalloc(&c.fold_shift, c.co * 4));
+  if (h->packed_dirty) {
+    RepackTable t;
+    memset(&t, 0, sizeof(t));
+    t.etype = et;
+    long long off = 0;
+    for (size_t l = 1; l < h->net.convs.size(); ++l) {
+      ConvLayer& c = h->net.convs[l];
+      const int taps = c.k * c.k;
+      const long long n = (long long)taps * c.ci * c.co;
+      const size_t es = et == ET_F32 ? 4 : 2;
+      if (et != ET_F32) {
+        if (!c.w_fprop) CUDA_CHECK(cudaMalloc(&c.w_fprop, n * es));
+        t.seg[t.n++] = RepackSeg{h->params + c.w_off, c.w_fprop, taps, c.ci, c.co, 0, off};
+        off += n;
+      }
+      if (!c.w_dgrad) CUDA_CHECK(cudaMalloc(&c.w_dgrad, n * es));
+      t.seg[t.n++] = RepackSeg{h->params + c.w_off, c.w_dgrad, taps, c.ci, c.co, et == ET_F32 ? 2 : 1, off};
+      off += n;
     }
-    fold_bn_kernel<<<nblk(c.co, 128), 128, 0, h->stream>>>(h->params + c.b_off, h->bnstat + c.mm_off, h->bnstat + c.mv_off,
-                                                            h->cfg.bn_eps, c.fold_scale, c.fold_shift, c.co);
-    LAUNCH_CHECK(h);
-    if (l == 0) {
-      // training and the fp32 mode run conv1 on the CUDA-core kernel straight from the HWIO weights; 16-bit inference
-      // runs it on the tensor cores with the input channels zero-padded to 32
-      if (et != ET_F32 && c.ci <= 8) {
-        const int64_t n = (int64_t)c.k * c.k * 32 * c.co;
-        if (!c.w_fprop) CUDA_CHECK(cudaMalloc(&c.w_fprop, n * 2));
-        if (et == ET_F16) pack_fprop_pad32_kernel<__half><<<nblk(n, 256), 256, 0, h->stream>>>(h->params + c.w_off, (__half*)c.w_fprop, c.k * c.k, c.ci, c.co);
-        else pack_fprop_pad32_kernel<__nv_bfloat16><<<nblk(n, 256), 256, 0, h->stream>>>(h->params + c.w_off, (__nv_bfloat16*)c.w_fprop, c.k * c.k, c.ci, c.co);
+    t.total = off;
+    if (off > 0) {
+      repack_kernel<<<nblk(off, 256), 256, 0, h->stream>>>(t);
+      LAUNCH_CHECK(h);
+    }
+    h->packed_dirty = false;
+  }
+  if (!training && h->eval_dirty) {
+    for (size_t l = 0; l < h->net.convs.size(); ++l) {
+      ConvLayer& c = h->net.convs[l];
+      if (!c.fold_scale) {
+        CUDA_CHECK(cudaMalloc(&c.fold_scale, c.co * 4));
+        CUDA_CHECK(cudaMalloc(&c.fold_shift, c.co * 4));
+      }
+      fold_bn_kernel<<<nblk(c.co, 128), 128, 0, h->stream>>>(h->params + c.b_off, h->bnstat + c.mm_off, h->bnstat + c.mv_off,
+                                                              h->cfg.bn_eps, c.fold_scale, c.fold_shift, c.co);
+      LAUNCH_CHECK(h);
+      // 16-bit inference runs conv1 on the tensor cores (conv1_tc.cuh) from a core-matrix-ordered operand; training and the
+      // fp32 mode run it on the CUDA-core kernel straight from the HWIO weights
+      if (l == 0 && et != ET_F32 && conv1_tc_supported(c.k, c.rate, c.ci, c.co)) {
+        const int n = C1_SLOTS * c.co * 8;
+        if (!c.w_fprop) CUDA_CHECK(cudaMalloc(&c.w_fprop, (size_t)n * 2));
+        if (et == ET_F16) pack_conv1_kernel<__half><<<nblk(n, 256), 256, 0, h->stream>>>(h->params + c.w_off, (__half*)c.w_fprop, c.ci, c.co);
+        else pack_conv1_kernel<__nv_bfloat16><<<nblk(n, 256), 256, 0, h->stream>>>(h->params + c.w_off, (__nv_bfloat16*)c.w_fprop, c.ci, c.co);
         LAUNCH_CHECK(h);
       }
-      continue;
     }
-    if (et == ET_F32) {
-      const int taps = c.k * c.k;
-      const int64_t n = (int64_t)taps * c.ci * c.co;
-      if (!c.w_dgrad) CUDA_CHECK(cudaMalloc(&c.w_dgrad, n * 4));
-      pack_dgrad_simt_kernel<<<nblk(n, 256), 256, 0, h->stream>>>(h->params + c.w_off, (float*)c.w_dgrad, taps, c.ci, c.co);
-      LAUNCH_CHECK(h);
-    } else if (et == ET_F16) {
-      pack_layer_t<__half>(h, c, true);
-    } else {
-      pack_layer_t<__nv_bfloat16>(h, c, true);
-    }
+    h->eval_dirty = false;
   }
-  (void)training;
-  h->packed_dirty = false;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -511,14 +560,19 @@ static void forward_eval_t(Handle* h, const float* x_dev, int B, int crop, float
     ActBuf out;
     if (n.dense) out = {bufs[0], fs, c.out_coff};
     else out = {bufs[(xi + 1) % 3], fs, 0};
-    if (l == 0 && ElemTag<TA>::v != ET_F32 && c.ci <= 8 && c.w_fprop) {
-      TA* xp = (TA*)arena_take(h, (size_t)M * 32 * sizeof(TA));
-      pad_cast32_kernel<TA><<<nblk(M * 4, 256), 256, 0, h->stream>>>(x_dev, xp, c.ci, M);
+    if (l == 0 && ElemTag<TA>::v != ET_F32 && c.w_fprop && conv1_tc_supported(c.k, c.rate, c.ci, c.co)) {
+      TA* x8 = (TA*)arena_take(h, (size_t)M * 8 * sizeof(TA));
+      pad_cast8_kernel<TA><<<nblk(M, 256), 256, 0, h->stream>>>(x_dev, x8, c.ci, M);
       LAUNCH_CHECK(h);
-      const double fl0 = X(h)->conv_flops;
-      run_conv<TA>(h, ActBuf{xp, 32, 0}, 32, nullptr, c.w_fprop, out, c.co, B, crop, c.k, c.rate, c.pad_b, c.fold_scale,
-                   c.fold_shift, n.act);
-      X(h)->conv_flops = fl0 + 2.0 * (double)M * c.k * c.k * c.ci * c.co;   // algorithmic FLOPs: the real C channels
+      cudaEvent_t ea = nullptr, eb = nullptr;
+      prof_begin(h, &ea, &eb);
+      Conv1TcArgs a1;
+      a1.x8 = x8; a1.wpack = c.w_fprop; a1.out = out.p; a1.out_cstride = out.cs; a1.out_coff = out.co; a1.co = c.co;
+      a1.B = B; a1.crop = crop; a1.scale = c.fold_scale; a1.shift = c.fold_shift; a1.act = n.act; a1.etype = ElemTag<TA>::v;
+      launch_conv1_tc(h, a1);
+      prof_end(h, eb);
+      X(h)->conv_flops += 2.0 * (double)M * c.k * c.k * c.ci * c.co;   // algorithmic FLOPs: the real C channels
+      X(h)->conv_launches += 1;
     } else if (l == 0) {
       launch_conv_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, h->params + c.w_off, (TA*)out.p, out.cs, out.co, c.co,
                                   B, crop, c.k, c.rate, c.pad_b, c.fold_scale, c.fold_shift, n.act);

@@ -115,7 +115,8 @@ struct drs_handle_s {
   float* moms = nullptr;
   float* bnstat = nullptr;   // moving_mean / moving_variance
   int64_t global_step = 0;
-  bool packed_dirty = true;  // packed operand matrices / folded BN need refresh
+  bool packed_dirty = true;  // packed operand matrices need refresh
+  bool eval_dirty = true;    // folded eval-mode BN / conv1 tensor-core operand need refresh
 
   // workspace
   Arena arena;

@@ -49,11 +49,16 @@ extern "C" int drs_set_normalization(drs_handle_t h, const double* mean3, const 
 }
 
 // all pointer members of gp are device pointers
-static void launch_gather(Handle* h, GatherParams gp) {
+static void launch_gather(Handle* h, GatherParams gp, const GatherInline* il = nullptr) {
   for (int i = 0; i < 3; ++i) { gp.mean[i] = h->norm_mean[i]; gp.stdv[i] = h->norm_std[i]; }
   gp.C = h->net.channels;
   const int64_t n = (int64_t)gp.B * gp.crop * gp.crop * gp.C;
-  gather_kernel<<<nblk(n, 256), 256, 0, h->stream>>>(X(h)->table, gp);
+  if (il) {
+    gather_kernel<true><<<nblk(n, 256), 256, 0, h->stream>>>(X(h)->table, gp, *il);
+  } else {
+    static const GatherInline none = {};
+    gather_kernel<false><<<nblk(n, 256), 256, 0, h->stream>>>(X(h)->table, gp, none);
+  }
   LAUNCH_CHECK(h);
 }
 
@@ -73,6 +78,22 @@ extern "C" int drs_gather_dev(drs_handle_t h, const int32_t* inst_host, const ui
     DRS_CHECK(it != h->scenes.end(), "gather: scene %d not uploaded", sid);
     DRS_CHECK(r >= 0 && c >= 0 && r + crop <= it->second.H && c + crop <= it->second.W,
               "Error: Current PATCH size is out of the scene (scene %d, row %d, col %d, crop %d)", sid, r, c, crop);
+  }
+  const bool plain = !(noise_host && noise_on_host) && !(over_x_host && over_on_host);
+  if (plain && B <= GATHER_INLINE_MAX) {
+    // common case (no host-made noise / rotation overrides): everything travels in the kernel parameters
+    GatherInline il;
+    memset(&il, 0, sizeof(il));
+    memcpy(il.inst, inst_host, (size_t)B * 12);
+    if (flips_host) memcpy(il.flips, flips_host, B);
+    GatherParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.x_out = x_out_dev;
+    gp.y_out = y_out_dev;
+    gp.B = B;
+    gp.crop = crop;
+    launch_gather(h, gp, &il);
+    return 0;
   }
   size_t need = round_up((size_t)B * 3 * 4, 256) + 3 * round_up((size_t)B, 256);
   if (noise_host) need += round_up((size_t)pp * C * 8, 256);
@@ -302,7 +323,9 @@ extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, i
   const int waves = getenv("DRS_CHUNK_WAVES") ? std::max(1, atoi(getenv("DRS_CHUNK_WAVES"))) : 40;
   const int64_t target_tiles = (int64_t)h->sm_count * waves;
   int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(P, (target_tiles * CONV_TC_BM) / pp));
-  const int n_lanes = (P > chunk && !getenv("DRS_ONE_LANE")) ? 2 : 1;
+  // A second lane (DRS_TWO_LANES=1) overlaps one chunk's HBM-bound kernels with the other's convolutions; measured on
+  // B200 it loses (L2 thrash + power cap: 1174 ms vs 979 ms for a 6000x6000 tile), so one lane is the default.
+  const int n_lanes = (P > chunk && getenv("DRS_TWO_LANES")) ? 2 : 1;
   ScenePass sp;
   int32_t* inst_dev = nullptr;
   HandleExtra* hx = X(h);

@@ -113,7 +113,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     // batch statistics (biased variance), moving-average update          (isprs:658-660)
     float* mean = x->mean + c.mm_off;
     float* istd = x->inv_std + c.mm_off;
-    BnFinish fin{x->bn_counter, x->sums, nullptr, nullptr, nullptr, nullptr, bn_count, h->cfg.bn_eps, h->cfg.bn_decay, h->cfg.bn_unbiased_ema};
+    BnFinish fin{x->bn_acc, 1048576.0, x->bn_counter, x->sums, nullptr, nullptr, nullptr, nullptr, bn_count, h->cfg.bn_eps, h->cfg.bn_decay, h->cfg.bn_unbiased_ema};
     if (!h->sync_bn) { fin.mean = mean; fin.inv_std = istd; fin.mov_mean = h->bnstat + c.mm_off; fin.mov_var = h->bnstat + c.mv_off; }
     bn_partial_kernel<TA, TA, 0><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, nullptr, 0, 0, nullptr, nullptr, 0, part_bn, c.co, M, bn_rows, fin);
     LAUNCH_CHECK(h);
@@ -197,7 +197,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     }
     float* mean = x->mean + c.mm_off;
     float* istd = x->inv_std + c.mm_off;
-    BnFinish finb{x->bn_counter, x->sums, nullptr, nullptr, nullptr, nullptr, bn_count, 0.0f, 0.0f, 0};
+    BnFinish finb{x->bn_acc, 1099511627776.0, x->bn_counter, x->sums, nullptr, nullptr, nullptr, nullptr, bn_count, 0.0f, 0.0f, 0};
     bn_partial_kernel<TA, TA, 1><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, n.act, part_bn, c.co, M, bn_rows, finb);
     LAUNCH_CHECK(h);
     if (h->sync_bn) do_allreduce(h, x->sums, 2 * c.co);
@@ -262,6 +262,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   LAUNCH_CHECK(h);
   h->global_step++;
   h->packed_dirty = true;
+  h->eval_dirty = true;
   if (cm_out_dev) CUDA_CHECK(cudaMemcpyAsync(cm_out_dev, x->cm_dev, (K * K + 1) * 4, cudaMemcpyDeviceToDevice, h->stream));
   if (loss_host) {
     CUDA_CHECK(cudaMemcpyAsync(loss_host, x->loss_dev + 2, 4, cudaMemcpyDeviceToHost, h->stream));

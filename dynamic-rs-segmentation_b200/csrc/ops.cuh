@@ -21,36 +21,26 @@ struct alignas(16) Vec8 {
 // the horizontal 3-max of the two previous rows in registers, so every input element is loaded 3 times (from L1)
 // instead of 9.  Adjacent threads cover adjacent channel groups, then adjacent columns: each row access of a warp is
 // one contiguous run.
-template <typename T>
-__device__ __forceinline__ void pool_row_load(const T* __restrict__ in, int in_cs, int64_t pix_row0, int x, int crop, int y,
-                                              Vec8<T> (&q)[3]) {
-  const T ninf = from_f32<T>(-INFINITY);
+template <typename T, bool WITH_IDX>
+__device__ __forceinline__ void pool_row_max(const T* __restrict__ in, int in_cs, int64_t pix_row0, int x, int crop, int y,
+                                             float (&v)[8], int (&d)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { v[e] = -INFINITY; d[e] = 0; }
+  if (y < 0 || y >= crop) return;
 #pragma unroll
   for (int dx = -1; dx <= 1; ++dx) {
     const int xx = x + dx;
-    if (y >= 0 && y < crop && xx >= 0 && xx < crop) {
-      q[dx + 1] = *reinterpret_cast<const Vec8<T>*>(in + (pix_row0 + (int64_t)y * crop + xx) * in_cs);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) q[dx + 1].v[e] = ninf;     // padding never wins (window clipped, isprs:745-750)
-    }
-  }
-}
-template <typename T, bool WITH_IDX>
-__device__ __forceinline__ void pool_row_reduce(const Vec8<T> (&q)[3], float (&v)[8], int (&d)[8]) {
-#pragma unroll
-  for (int e = 0; e < 8; ++e) { v[e] = -INFINITY; d[e] = 0; }
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
+    if (xx < 0 || xx >= crop) continue;
+    const Vec8<T> q = *reinterpret_cast<const Vec8<T>*>(in + (pix_row0 + (int64_t)y * crop + xx) * in_cs);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float f = to_f32(q[j].v[e]);
-      if (f > v[e]) { v[e] = f; if (WITH_IDX) d[e] = j; }
+      const float f = to_f32(q.v[e]);
+      if (f > v[e]) { v[e] = f; if (WITH_IDX) d[e] = dx + 1; }
     }
   }
 }
 
-template <typename T, bool WITH_IDX>
+template <typename T, bool WITH_IDX, bool FUSE_BN>
 __global__ void __launch_bounds__(256)
 maxpool3_fwd_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __restrict__ out, int out_cs, int out_co,
                     uint8_t* __restrict__ idx, int C, int B, int crop, int seg, int nseg, const float* __restrict__ bn_mean,
@@ -72,20 +62,14 @@ maxpool3_fwd_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __restric
   // Training forward of the pooling nets: max-pool commutes with the (strictly increasing) normalise + LeakyReLU, so the
   // pool runs on the raw conv output and act((max - mean) * inv_std) is applied to the winner only.
   float mu[8], is[8];
-  if (bn_mean) {
+  if (FUSE_BN) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) { mu[e] = bn_mean[cg * 8 + e]; is[e] = bn_inv_std[cg * 8 + e]; }
   }
-  Vec8<T> qa[3], qb[3];
-  pool_row_load<T>(inp, in_cs, img0, x, crop, y0 - 1, qa);
-  pool_row_load<T>(inp, in_cs, img0, x, crop, y0, qb);
-  pool_row_reduce<T, WITH_IDX>(qa, r0, d0);
-  pool_row_load<T>(inp, in_cs, img0, x, crop, y0 + 1, qa);     // stays in flight while row y0 is reduced
-  pool_row_reduce<T, WITH_IDX>(qb, r1, d1);
+  pool_row_max<T, WITH_IDX>(inp, in_cs, img0, x, crop, y0 - 1, r0, d0);
+  pool_row_max<T, WITH_IDX>(inp, in_cs, img0, x, crop, y0, r1, d1);
   for (int y = y0; y < y1; ++y) {
-    // software pipeline: the loads of row y+2 are issued before row y+1 (already in registers) is consumed
-    pool_row_load<T>(inp, in_cs, img0, x, crop, (y + 1 < y1) ? y + 2 : crop, qb);
-    pool_row_reduce<T, WITH_IDX>(qa, r2, d2);
+    pool_row_max<T, WITH_IDX>(inp, in_cs, img0, x, crop, y + 1, r2, d2);
     Vec8<T> o;
     int code[8];
 #pragma unroll
@@ -95,7 +79,7 @@ maxpool3_fwd_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __restric
       int c = d0[e];
       if (r1[e] > best) { best = r1[e]; c = 3 + d1[e]; }
       if (r2[e] > best) { best = r2[e]; c = 6 + d2[e]; }
-      if (bn_mean) best = apply_act((best - mu[e]) * is[e], act);
+      if (FUSE_BN) best = apply_act((best - mu[e]) * is[e], act);
       o.v[e] = from_f32<T>(best);
       code[e] = c;
     }
@@ -109,8 +93,66 @@ maxpool3_fwd_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __restric
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) { r0[e] = r1[e]; r1[e] = r2[e]; d0[e] = d1[e]; d1[e] = d2[e]; }
+  }
+}
+
+// Inference variant (no winner codes, no fused normalisation): the 16-bit types are reduced with packed 2-wide max
+// instructions and never converted, which takes the kernel from issue-bound to memory-bound.
+__device__ __forceinline__ void vmax8(Vec8<float>& a, const Vec8<float>& b) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) qa[j] = qb[j];
+  for (int e = 0; e < 8; ++e) a.v[e] = fmaxf(a.v[e], b.v[e]);
+}
+__device__ __forceinline__ void vmax8(Vec8<__half>& a, const Vec8<__half>& b) {
+  __half2* pa = reinterpret_cast<__half2*>(a.v);
+  const __half2* pb = reinterpret_cast<const __half2*>(b.v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) pa[e] = __hmax2(pa[e], pb[e]);
+}
+__device__ __forceinline__ void vmax8(Vec8<__nv_bfloat16>& a, const Vec8<__nv_bfloat16>& b) {
+  __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(a.v);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(b.v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) pa[e] = __hmax2(pa[e], pb[e]);
+}
+
+template <typename T>
+__device__ __forceinline__ bool pool_row_vmax(const T* __restrict__ in, int in_cs, int64_t pix_row0, int x, int crop, int y,
+                                              Vec8<T>& v) {
+  if (y < 0 || y >= crop) return false;
+  const T* row = in + (pix_row0 + (int64_t)y * crop) * in_cs;
+  v = *reinterpret_cast<const Vec8<T>*>(row + (int64_t)x * in_cs);
+  if (x > 0) vmax8(v, *reinterpret_cast<const Vec8<T>*>(row + (int64_t)(x - 1) * in_cs));
+  if (x + 1 < crop) vmax8(v, *reinterpret_cast<const Vec8<T>*>(row + (int64_t)(x + 1) * in_cs));
+  return true;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool3_fwd_packed_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __restrict__ out, int out_cs, int out_co, int C,
+                           int B, int crop, int seg, int nseg) {
+  const int cv = C >> 3;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)B * nseg * crop * cv) return;
+  const int cg = (int)(gid % cv);
+  int64_t t = gid / cv;
+  const int x = (int)(t % crop);
+  t /= crop;
+  const int sg = (int)(t % nseg);
+  const int b = (int)(t / nseg);
+  const int y0 = sg * seg, y1 = min(crop, y0 + seg);
+  const int64_t img0 = (int64_t)b * crop * crop;
+  const T* inp = in + in_co + cg * 8;
+  Vec8<T> r0, r1, r2;
+  bool v0 = pool_row_vmax<T>(inp, in_cs, img0, x, crop, y0 - 1, r0);
+  bool v1 = pool_row_vmax<T>(inp, in_cs, img0, x, crop, y0, r1);      // always valid
+  for (int y = y0; y < y1; ++y) {
+    const bool v2 = pool_row_vmax<T>(inp, in_cs, img0, x, crop, y + 1, r2);
+    Vec8<T> o = r1;
+    if (v0) vmax8(o, r0);
+    if (v2) vmax8(o, r2);
+    *reinterpret_cast<Vec8<T>*>(out + (img0 + (int64_t)y * crop + x) * out_cs + out_co + cg * 8) = o;
+    r0 = r1; v0 = v1;
+    r1 = r2; v1 = v2;
   }
 }
 
@@ -122,8 +164,11 @@ static void launch_maxpool3_fwd(Handle* h, const T* in, int in_cs, int in_co, T*
   const int seg = (int)ceil_div(crop, nseg);
   nseg = (int)ceil_div(crop, seg);
   const int64_t total = base * nseg;
-  if (idx) maxpool3_fwd_kernel<T, true><<<(unsigned)ceil_div(total, 256), 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, idx, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
-  else maxpool3_fwd_kernel<T, false><<<(unsigned)ceil_div(total, 256), 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, nullptr, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
+  const unsigned nb = (unsigned)ceil_div(total, 256);
+  if (idx && bn_mean) maxpool3_fwd_kernel<T, true, true><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, idx, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
+  else if (idx) maxpool3_fwd_kernel<T, true, false><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, idx, C, B, crop, seg, nseg, nullptr, nullptr, 0);
+  else if (bn_mean) maxpool3_fwd_kernel<T, false, true><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, nullptr, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
+  else maxpool3_fwd_packed_kernel<T><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, C, B, crop, seg, nseg);
   LAUNCH_CHECK(h);
 }
 
@@ -174,6 +219,8 @@ constexpr int BN_THREADS = 256;
 
 // what the last block of bn_partial_kernel does with the reduced sums
 struct BnFinish {
+  long long* acc;          // [2][C] fixed-point accumulators, zero before the launch; cleared by the kernel
+  double fx_scale;         // fixed-point scale (2^20 forward statistics, 2^40 backward sums)
   unsigned int* counter;   // zero before the launch; reset by the kernel
   float* sums;             // [2][C] out
   float* mean;             // non-null: also finalize (batch mean / inv_std, moving-average update)
@@ -238,14 +285,17 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
     s_red[threadIdx.x * 16 + 8 + e] = s1[e];
   }
   __syncthreads();
+  // Block partial (fixed order) -> 64-bit fixed point -> integer atomicAdd: integer addition is associative, so the grid-wide
+  // sum does not depend on the order in which blocks arrive (deterministic without a serial reduction pass).
   for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) {
     const int which = i / C, c = i - which * C;
     const int g = c >> 3, e = c & 7;
     float a = 0.0f;
     for (int r = 0; r < lanes_r; ++r) a += s_red[(r * cv + g) * 16 + which * 8 + e];
-    part[((int64_t)blockIdx.x * 2 + which) * C + c] = a;
+    const long long q = __double2ll_rn((double)a * fin.fx_scale);
+    atomicAdd(reinterpret_cast<unsigned long long*>(fin.acc) + i, static_cast<unsigned long long>(q));
   }
-  // ---- the last block to finish reduces the per-block partials in block order (fixed order => deterministic)
+  // ---- the last block to finish converts the sums, finalizes and clears the accumulators for the next launch
   __shared__ bool s_last;
   __threadfence();
   __syncthreads();
@@ -253,27 +303,12 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  double* s_sum = reinterpret_cast<double*>(s_red);          // [lanes_k][2C] doubles (<= 16 KB)
-  const int groups = (2 * C) >> 2;                           // float4 column groups
-  const int lanes_k = BN_THREADS / groups;
-  const int gq = threadIdx.x % groups, lk = threadIdx.x / groups;
-  const int nblk = gridDim.x;
-  if (lk < lanes_k) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    for (int k = lk; k < nblk; k += lanes_k) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (int64_t)k * 2 * C) + gq);
-      a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
-    }
-    double* d = s_sum + ((size_t)lk * groups + gq) * 4;
-    d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
-  }
-  __syncthreads();
+  const double inv_scale = 1.0 / fin.fx_scale;
   for (int i = threadIdx.x; i < C; i += BN_THREADS) {
-    double a = 0.0, b = 0.0;
-    for (int r = 0; r < lanes_k; ++r) {
-      a += s_sum[(size_t)r * 2 * C + i];
-      b += s_sum[(size_t)r * 2 * C + C + i];
-    }
+    const double a = (double)__ldcg(fin.acc + i) * inv_scale;
+    const double b = (double)__ldcg(fin.acc + C + i) * inv_scale;
+    fin.acc[i] = 0;
+    fin.acc[C + i] = 0;
     fin.sums[i] = (float)a;
     fin.sums[C + i] = (float)b;
     if (fin.mean) {
@@ -399,12 +434,16 @@ classifier_fwd_kernel(const T* __restrict__ x, int x_cs, int x_co, int Ci, const
   for (int64_t m0 = (int64_t)blockIdx.x * CLS_TILE; m0 < M; m0 += (int64_t)gridDim.x * CLS_TILE) {
     __syncthreads();                                            // previous tile fully consumed (and s_w visible)
     const int rows = (int)min((int64_t)CLS_TILE, M - m0);
+    // asynchronous 16-byte global->shared copies: every chunk of the tile is in flight at once (a register-staged
+    // loop would keep one load per thread outstanding and leave the kernel latency-bound)
     for (int i = tid; i < rows * chunks; i += CLS_TILE) {
       const int r = i / chunks, ch = i - r * chunks;
-      const uint4 v = *reinterpret_cast<const uint4*>(x + (m0 + r) * x_cs + x_co + ch * EPC);
       const int sw = (ch & ~7) | ((ch & 7) ^ (r & 7));
-      *reinterpret_cast<uint4*>(s_x + r * row_bytes + (size_t)sw * 16) = v;
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s_x + r * row_bytes + (size_t)sw * 16));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(x + (m0 + r) * x_cs + x_co + ch * EPC) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (tid < rows) {
       float acc[MAX_CLASSES];

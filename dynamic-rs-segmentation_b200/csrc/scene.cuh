@@ -17,6 +17,13 @@ struct SceneTable {
   SceneDesc s[MAX_SCENES];
 };
 
+constexpr int GATHER_INLINE_MAX = 256;
+// Small batches carry their instance table inside the kernel parameters: no staging copy, no host synchronisation.
+struct GatherInline {
+  int32_t inst[GATHER_INLINE_MAX * 3];
+  uint8_t flips[GATHER_INLINE_MAX];
+};
+
 struct GatherParams {
   const int32_t* inst;        // [B,3] scene, row, col
   const uint8_t* flips;       // [B] 0 none, 1 flipud, 2 fliplr
@@ -33,7 +40,8 @@ struct GatherParams {
 
 // One thread per output element.  Adjacent threads walk the channels then the columns of a scene row,
 // so reads of the (H,W,C) scene are contiguous runs of crop*C elements.
-__global__ void gather_kernel(const __grid_constant__ SceneTable tab, const GatherParams p) {
+template <bool INLINE>
+__global__ void gather_kernel(const __grid_constant__ SceneTable tab, const GatherParams p, const __grid_constant__ GatherInline il) {
   const int64_t n = (int64_t)p.B * p.crop * p.crop * p.C;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n) return;
@@ -43,8 +51,9 @@ __global__ void gather_kernel(const __grid_constant__ SceneTable tab, const Gath
   r /= p.crop;
   const int i = (int)(r % p.crop);
   const int b = (int)(r / p.crop);
-  const int sid = p.inst[b * 3 + 0], row0 = p.inst[b * 3 + 1], col0 = p.inst[b * 3 + 2];
-  const int flip = p.flips ? p.flips[b] : 0;
+  const int32_t* inst = INLINE ? il.inst : p.inst;
+  const int sid = inst[b * 3 + 0], row0 = inst[b * 3 + 1], col0 = inst[b * 3 + 2];
+  const int flip = INLINE ? il.flips[b] : (p.flips ? p.flips[b] : 0);
   const int si = flip == 1 ? p.crop - 1 - i : i;    // np.flipud (isprs:309-312)
   const int sj = flip == 2 ? p.crop - 1 - j : j;    // np.fliplr (isprs:314-317)
   const SceneDesc& sc = tab.s[sid];

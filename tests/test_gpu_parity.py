@@ -438,3 +438,21 @@ def test_training_reduces_loss_like_the_oracle(drs):
     assert lo[-1] < 0.7 * lo[0], lo
     assert lg[-1] < 0.7 * lg[0], lg
     assert max(abs(a - b) for a, b in zip(lo, lg)) < 0.05 * lo[0], (lo, lg)
+
+
+def test_training_is_run_to_run_deterministic(drs):
+    """No float atomics anywhere: two sessions fed the same data produce identical bits (loss, weights, BN statistics)."""
+    rs = np.random.RandomState(21)
+    B, crop, C, K = 16, 27, 4, 6
+    x = rs.randn(B, crop * crop * C).astype(np.float32)
+    y = rs.randint(0, K, size=(B, crop * crop)).astype(np.float32)
+    outs = []
+    for _ in range(2):
+        s = drs.Session("dilated_grsl", C, K, precision="bf16", seed=4)
+        losses = [float(s.train_step(x, y, crop)[0]) for _ in range(3)]
+        outs.append((losses, s.get_variable("conv3/weights").copy(), s.get_variable("conv6/moving_variance").copy(),
+                     s.get_variable("conv1/weights").copy()))
+        s.close()
+    assert outs[0][0] == outs[1][0]
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert np.array_equal(a, b)
