@@ -4,16 +4,18 @@ The scripts' loops call a backend with three operations; ``GpuBackend`` is the p
 (libdrs.so through ``Session``, torch only for device buffers).  Tests drive the same loops with a
 closed-form stand-in to pin the host logic against reference-generated traces without a GPU.
 
-    train_on_plan(plan)  -> (loss, cm[K,K] uint32, n_correct)   gather + normalise + sess.run(train) + per-crop confusion
-    eval_on_plan(plan)   -> (pred int64 [B,c,c], labels [B,c,c]) gather + normalise + sess.run(pred_up)
-    scene_labels(scene_id, crop, batch, H, W, variant) -> uint8 [H,W]   whole sliding-window inference
+    train_on_plan(plan, loss_mask=None)  -> (loss, cm[K,K] uint32, n_correct)   gather + normalise + sess.run(train) + confusion
+    eval_on_plan(plan, scene_offset=0)   -> (pred int64 [B,c,c], labels [B,c,c]) gather + normalise + sess.run(pred_up)
+    scene_labels(scene_id, crop, batch, variant) -> uint8 [H,W]   whole sliding-window inference
+    save(path) / restore(path)                                    tf.train.Saver stand-in (one .npz keyed by TF names)
 """
 import numpy as np
 
 
 class GpuBackend:
-    def __init__(self, session, scenes, label_maps, mean_full, std_full, device=0):
+    def __init__(self, session, scenes, label_maps, mean_full, std_full, device=0, rank=0, world=1):
         import torch
+        self.rank, self.world = rank, world
         self.torch = torch
         self.s = session
         self.dev = torch.device("cuda", device)
@@ -40,19 +42,40 @@ class GpuBackend:
             self._amask = t.empty(n, dtype=t.uint8, device=self.dev)
         return self._x, self._y, self._pred
 
-    def _gather(self, plan):
+    def _rank_rows(self, n):
+        """Data parallel: this rank's contiguous share of a global batch."""
+        per = n // self.world
+        return slice(self.rank * per, (self.rank + 1) * per) if self.world > 1 else slice(0, n)
+
+    def _gather(self, plan, scene_offset=0, shard=False):
+        if shard and self.world > 1:
+            sl = self._rank_rows(plan.inst.shape[0])
+            sub = type(plan)()
+            for k in plan.__slots__:
+                v = getattr(plan, k)
+                setattr(sub, k, v[sl] if isinstance(v, np.ndarray) else v)
+            plan = sub
+        self._plan = plan
         B, crop = plan.inst.shape[0], plan.crop
         x, y, pred = self._buffers(B, crop)
-        self.s.gather_dev(plan.inst, plan.flips, crop, x, y, noise=plan.noise, noise_on=plan.noise_on,
+        inst = plan.inst
+        if scene_offset:
+            inst = inst.copy()
+            inst[:, 0] += scene_offset
+        self.s.gather_dev(inst, plan.flips, crop, x, y, noise=plan.noise, noise_on=plan.noise_on,
                           over_x=plan.over_x, over_y=plan.over_y, over_on=plan.over_on)
         return x, y, pred, B, crop
 
     def train_on_plan(self, plan, loss_mask=None):
         t = self.torch
-        x, y, pred, B, crop = self._gather(plan)
+        x, y, pred, B, crop = self._gather(plan, shard=True)
+        plan = self._plan
         n = B * crop * crop
         mask_dev = None
-        if loss_mask is not None:
+        if isinstance(loss_mask, str):
+            # "label!=K": the session derives the mask on the device from the gathered labels (Session.set_ignore_label)
+            self.s.set_ignore_label(int(loss_mask.split("!=")[1]))
+        elif loss_mask is not None:
             self._mask[:n].copy_(t.from_numpy(np.ascontiguousarray(loss_mask, dtype=np.uint8).reshape(-1)))
             mask_dev = self._mask
         amask_dev = None
@@ -65,8 +88,8 @@ class GpuBackend:
         K = self.K
         return loss, cm[:K * K].reshape(K, K), int(cm[K * K])
 
-    def eval_on_plan(self, plan):
-        x, y, pred, B, crop = self._gather(plan)
+    def eval_on_plan(self, plan, scene_offset=0):
+        x, y, pred, B, crop = self._gather(plan, scene_offset)
         self.s.infer_dev(x, B, crop, None, pred)
         self.s.synchronize()
         n = B * crop * crop
@@ -75,4 +98,15 @@ class GpuBackend:
 
     def scene_labels(self, scene_id, crop, batch, variant="isprs"):
         H, W = self.shapes[scene_id]
-        return self.s.scene_infer(scene_id, crop, batch, H, W, variant=variant)
+        if self.world == 1:
+            return self.s.scene_infer(scene_id, crop, batch, H, W, variant=variant)
+        from . import dist as ddist
+        r0, r1 = ddist.stripe_bounds(H, self.world, self.rank)
+        stripe = self.s.scene_infer(scene_id, crop, batch, H, W, variant=variant, row_begin=r0, row_end=r1)
+        return ddist.gather_label_stripes(stripe, H, W, self.rank, self.world, device=self.dev, all_ranks=True)
+
+    def save(self, path):
+        self.s.save(path)
+
+    def restore(self, path):
+        self.s.restore(path)

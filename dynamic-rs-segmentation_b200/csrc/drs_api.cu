@@ -358,6 +358,13 @@ extern "C" int drs_get_gradient(drs_handle_t h, const char* name, float* data, i
   API_END
 }
 
+extern "C" int drs_set_ignore_label(drs_handle_t h, int32_t label) {
+  API_BEGIN
+  DRS_CHECK(h, "null handle");
+  h->ignore_label = label;
+  API_END
+}
+
 extern "C" int drs_set_allreduce(drs_handle_t h, drs_allreduce_fn fn, void* user, int32_t world, int32_t sync_bn) {
   API_BEGIN
   DRS_CHECK(h, "null handle");

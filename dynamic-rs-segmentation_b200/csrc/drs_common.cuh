@@ -115,6 +115,7 @@ struct drs_handle_s {
   float* moms = nullptr;
   float* bnstat = nullptr;   // moving_mean / moving_variance
   int64_t global_step = 0;
+  int ignore_label = -1;     // contest: label excluded from loss / confusion when no mask is passed
   bool packed_dirty = true;  // packed operand matrices need refresh
   bool eval_dirty = true;    // folded eval-mode BN / conv1 tensor-core operand need refresh
 

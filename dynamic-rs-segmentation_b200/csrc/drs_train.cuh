@@ -139,9 +139,9 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
 
   // ---------------------------------------------------------------- loss (isprs:1089-1099, contest:881-901)
   double count = (double)M;
-  if (mask_dev) {
+  if (mask_dev || h->ignore_label >= 0) {
     CUDA_CHECK(cudaMemsetAsync(x->count_dev, 0, 4, h->stream));
-    mask_count_kernel<<<(unsigned)std::min<int64_t>(ceil_div(M, 256), 1024), 256, 0, h->stream>>>(mask_dev, M, x->count_dev);
+    mask_count_kernel<<<(unsigned)std::min<int64_t>(ceil_div(M, 256), 1024), 256, 0, h->stream>>>(mask_dev, y_dev, h->ignore_label, M, x->count_dev);
     LAUNCH_CHECK(h);
     unsigned int cnt = 0;
     CUDA_CHECK(cudaMemcpyAsync(&cnt, x->count_dev, 4, cudaMemcpyDeviceToHost, h->stream));
@@ -159,13 +159,13 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     count = (double)M * h->world;
   }
   const float inv_count = count > 0 ? (float)(1.0 / count) : 0.0f;
-  ce_fwd_bwd_kernel<<<nb_ce, CE_THREADS, 0, h->stream>>>(logits, y_dev, mask_dev, K, M, inv_count, dlogits, part_ce, labels_u8);
+  ce_fwd_bwd_kernel<<<nb_ce, CE_THREADS, 0, h->stream>>>(logits, y_dev, mask_dev, K, M, inv_count, dlogits, part_ce, labels_u8, h->ignore_label);
   LAUNCH_CHECK(h);
   sum_fixed_kernel<<<1, 256, 0, h->stream>>>(part_ce, nb_ce, x->loss_dev, inv_count);
   LAUNCH_CHECK(h);
   // fused calc_accuracy_by_crop (isprs:510-531)
   CUDA_CHECK(cudaMemsetAsync(x->cm_dev, 0, (K * K + 1) * 4, h->stream));
-  confusion_kernel<<<(unsigned)std::min<int64_t>(ceil_div(M, 256), (int64_t)h->sm_count * 4), 256, 0, h->stream>>>(labels_u8, pred, acc_mask_dev ? acc_mask_dev : mask_dev, M, K, -1, x->cm_dev);
+  confusion_kernel<<<(unsigned)std::min<int64_t>(ceil_div(M, 256), (int64_t)h->sm_count * 4), 256, 0, h->stream>>>(labels_u8, pred, acc_mask_dev ? acc_mask_dev : mask_dev, M, K, h->ignore_label, x->cm_dev);
   LAUNCH_CHECK(h);
 
   // ---------------------------------------------------------------- backward

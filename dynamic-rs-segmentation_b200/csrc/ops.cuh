@@ -608,7 +608,7 @@ constexpr int CE_THREADS = 256;
 __global__ void __launch_bounds__(CE_THREADS)
 ce_fwd_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ labels_f, const uint8_t* __restrict__ mask,
                   int K, int64_t M, float inv_count, float* __restrict__ dlogits, float* __restrict__ part_loss,
-                  uint8_t* __restrict__ labels_u8) {
+                  uint8_t* __restrict__ labels_u8, int ignore_label) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float loss = 0.0f;
   if (m < M) {
@@ -626,7 +626,7 @@ ce_fwd_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ la
     const float lse = mx + logf(se);
     const int y = (int)labels_f[m];
     if (labels_u8) labels_u8[m] = (uint8_t)y;
-    const bool on = mask ? (mask[m] != 0) : true;
+    const bool on = mask ? (mask[m] != 0) : (y != ignore_label);
     if (on && y >= 0 && y < K) loss = lse - z[y];
     if (dlogits) {
 #pragma unroll
@@ -648,10 +648,11 @@ ce_fwd_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ la
 }
 
 // count of mask != 0 (contest): block partials -> single value
-__global__ void mask_count_kernel(const uint8_t* __restrict__ mask, int64_t M, unsigned int* __restrict__ out) {
+__global__ void mask_count_kernel(const uint8_t* __restrict__ mask, const float* __restrict__ labels_f, int ignore_label,
+                                  int64_t M, unsigned int* __restrict__ out) {
   unsigned int c = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x)
-    c += mask[i] != 0;
+    c += mask ? (mask[i] != 0) : ((int)labels_f[i] != ignore_label);
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);   // integer: order-independent
 }

@@ -53,8 +53,8 @@ def rank_slice(batch, rank, world):
     return batch[rank * per:(rank + 1) * per]
 
 
-def gather_label_stripes(stripe, H, W, rank, world, device=None, group=None):
-    """Collect every rank's uint8 label stripe on rank 0 -> [H, W] (None elsewhere)."""
+def gather_label_stripes(stripe, H, W, rank, world, device=None, group=None, all_ranks=False):
+    """Collect every rank's uint8 label stripe on rank 0 -> [H, W] (None elsewhere unless all_ranks)."""
     import torch
     import torch.distributed as dist
     if world == 1:
@@ -68,8 +68,11 @@ def gather_label_stripes(stripe, H, W, rank, world, device=None, group=None):
     if backend == "nccl":
         out = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(out, mine, group=group)
-        if rank != 0:
+        if rank != 0 and not all_ranks:
             return None
+    elif all_ranks:
+        out = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(out, mine, group=group)
     else:
         out = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
         dist.gather(mine, out, dst=0, group=group)

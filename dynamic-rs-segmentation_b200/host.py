@@ -350,3 +350,76 @@ def plan_index_flip_batch(class_distribution, shuffle_batch, crop_size, shapes, 
 
 def sliding_stride(crop_size):
     return int(math.floor(crop_size / 2.0))       # isprs:1243
+
+
+# ------------------------------------------------------------------------------------------------
+# contest / coffee one-off set-up (C13/C14): reference semantics incl. their quirks
+# ------------------------------------------------------------------------------------------------
+def contest_create_distributions_over_classes(labels, crop_size, stride_crop, num_classes=7, verbose=True):
+    """contest:172-189.  ``count`` has length max_label+1, so ``count[-1]`` is the highest class PRESENT in the window
+    (not label 7): single-class windows are skipped and the highest class present never wins; partial border windows
+    are dropped (no shift-back)."""
+    classes = [[] for _ in range(num_classes)]
+    w, h = labels.shape
+    for i in range(0, w, stride_crop):
+        for j in range(0, h, stride_crop):
+            patch_class = labels[i:i + crop_size, j:j + crop_size]
+            if patch_class.shape == (crop_size, crop_size):
+                count = np.bincount(patch_class.astype(int).flatten())
+                if count[-1] == crop_size * crop_size:
+                    continue
+                classes[int(np.argmax(count[:-1]))].append((i, j))
+    if verbose:
+        for i in range(len(classes)):
+            print("Class " + str(i + 1) + " has " + str(len(classes[i])) + " instances")
+    out = []
+    for c in classes:
+        out += c
+    return out
+
+
+def contest_create_mean_and_std(data, class_distribution, crop_size):
+    """contest:104-116."""
+    all_patches = [data[x:x + crop_size, y:y + crop_size, :] for (x, y) in class_distribution]
+    return compute_image_mean(np.asarray(all_patches))
+
+
+def coffee_create_distributions_over_classes(labels, crop_size, stride_crop, num_classes=2):
+    """coffee:358-372: (tile, (row, col)) of every full window, bucketed by majority class."""
+    classes = [[] for _ in range(num_classes)]
+    for k in range(len(labels)):
+        lab = np.asarray(labels[k])
+        w, h = lab.shape[0], lab.shape[1]
+        for i in range(0, w, stride_crop):
+            for j in range(0, h, stride_crop):
+                patch_class = np.squeeze(lab[i:i + crop_size, j:j + crop_size])
+                if patch_class.shape == (crop_size, crop_size):
+                    count = np.bincount(patch_class.astype(int).flatten())
+                    classes[int(np.argmax(count))].append((k, (i, j)))
+    out = []
+    for c in classes:
+        out += c
+    return out
+
+
+def coffee_create_mean_and_std(training_data, crop_size, stride_crop):
+    """coffee:352-355 over create_crops_stride(..., is_train=True) (coffee:176-238): every full window with the
+    alternating stride/stride+1 walk of odd crop sizes, plus its two mirrored copies (which leave mean/std-at-(0,0)
+    dependent on the flips, so they are generated like the reference does)."""
+    crops = []
+    for i in range(len(training_data)):
+        tile = training_data[i]
+        j, count_x = 0, 0
+        while j < tile.shape[0]:
+            k, count_y = 0, 0
+            while k < tile.shape[1]:
+                if j + crop_size <= tile.shape[0] and k + crop_size <= tile.shape[1]:
+                    crop = tile[j:j + crop_size, k:k + crop_size, :]
+                    crops.append(crop)
+                    crops.append(np.fliplr(crop))
+                    crops.append(np.flipud(crop))
+                k += (stride_crop + 1) if (crop_size % 2 != 0 and count_y % 2 != 0) else stride_crop
+                count_y += 1
+            j += (stride_crop + 1) if (crop_size % 2 != 0 and count_x % 2 != 0) else stride_crop
+            count_x += 1
+    return compute_image_mean(np.asarray(crops))

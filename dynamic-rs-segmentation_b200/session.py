@@ -172,6 +172,10 @@ class Session:
                                              C.byref(loss) if want_loss else None, L.ptr(pred_dev), L.ptr(cm_dev)))
         return np.float32(loss.value) if want_loss else None
 
+    def set_ignore_label(self, label):
+        """contest: label 7 = unlabelled pixels, excluded from loss / gradient / confusion (contest:236-239, 886-897)."""
+        L.check(self._lib.drs_set_ignore_label(self._h, -1 if label is None else int(label)))
+
     # ---------------------------------------------------------------- data-parallel hook
     def set_allreduce(self, fn, world_size, sync_bn=False):
         """fn(buf_ptr:int, count:int, stream:int) must sum ``count`` floats at ``buf_ptr`` over ranks in place."""

@@ -111,6 +111,11 @@ int drs_train_step_dev(drs_handle_t h, const float* x_dev, const float* y_dev, c
                        const uint8_t* acc_mask_dev, int32_t B, int32_t crop, float* loss_out_host, uint8_t* pred_dev,
                        uint32_t* cm_dev);
 
+/* contest: pixels whose label equals `label` (7 = unlabelled, contest:236-239) are excluded from the loss mean, the
+ * gradient and the fused confusion counts when no explicit mask is passed -- the boolean_mask of contest:886-897 derived
+ * on the device from the labels the gather kernel produced.  label < 0 (default) disables it. */
+int drs_set_ignore_label(drs_handle_t h, int32_t label);
+
 /* Data-parallel exchange hook: called on the handle's stream order with a device buffer that must be
  * summed over ranks in place (flat gradients ++ loss numerator ++ confusion counts; and, when
  * sync_bn != 0, the per-layer BN statistics).  NULL = single process.  The reference has no

@@ -1,0 +1,101 @@
+"""CPU: the drop-in training loop (dynamic-rs-segmentation_b200/loops.py) against traces produced by the reference's OWN
+``isprs.train`` driven through a closed-form fake ``sess.run`` (oracle/make_golden.py section 8).
+
+What is pinned: the RNG interleaving of patch-size draws / batch selection / augmentation, the instance sampling, the
+normalised patches fed at every step (sum of the float64 feed), the labels, the per-step score update and the saved
+``patch_*_step_N.npy`` arrays -- for all four distribution types and both update types.
+"""
+import io
+import os
+import random
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+from oracle import host_np
+from oracle.fake_net import fake_train_fetches
+
+DIST = {0: "single_fixed", 1: "multi_fixed", 2: "uniform", 3: "multinomial"}
+UPD = {0: "acc", 1: "loss"}
+
+
+class FakeBackend:
+    """Closed-form stand-in for the device: same fetches the fake session of the golden run returned."""
+
+    def __init__(self, scenes, labels, mean, std, C, K):
+        self.scenes, self.labels, self.mean, self.std, self.C, self.K = scenes, labels, mean, std, C, K
+        self.log = []
+        self.saved = []
+
+    def train_on_plan(self, plan, loss_mask=None):
+        x, y = host_np.apply_plan(self.scenes, self.labels, plan.inst, plan.flips, plan.crop, self.mean, self.std, plan.noise,
+                                  plan.noise_on, plan.over_x, plan.over_y, plan.over_on, cast=False)
+        B = len(plan.inst)
+        bx = np.reshape(x, (-1, plan.crop * plan.crop * self.C))
+        by = np.reshape(y, (-1, plan.crop * plan.crop))
+        self.log.append((1, plan.crop, B, float(np.sum(bx.astype(np.float64))), float(np.sum(by.astype(np.float64)))))
+        loss, pred = fake_train_fetches(bx, plan.crop, self.C, self.K)
+        masks = None if plan.acc_mask is None else plan.acc_mask.astype(bool)
+        acc, _, cm = host_np.confusion_by_crop(y.astype(np.int64), pred, self.K, masks)
+        return loss, cm, acc
+
+    def save(self, path):
+        self.saved.append(path)
+
+    def restore(self, path):
+        raise AssertionError("not expected")
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2, 3])
+def test_isprs_train_loop_reproduces_reference_trace(golden, drs, tmp_path, ci):
+    from drs_b200 import host, loops
+    case = golden["train_cases"][ci]
+    dist, upd = DIST[int(case[0])], UPD[int(case[1])]
+    values = [int(v) for v in case[2:] if v > 0]
+    tr_d, tr_l = golden["train_scenes"], golden["train_labels"]
+    te_d, te_l = golden["test_scenes"], golden["test_labels"]
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        np.random.seed(1000 + ci)
+        random.seed(2000 + ci)
+        with redirect_stdout(io.StringIO()):
+            tr_distr = host.create_distributions_over_classes(tr_l, 25, 5, 6)
+            te_distr = host.create_distributions_over_classes(te_l, 25, 5, 6)
+            rot = host.create_rotation_distribution(tr_distr)
+            mean_f, std_f = host.dynamically_calculate_mean_and_std(tr_d, tr_distr, 25)
+        assert np.array_equal(mean_f, golden["train_%d_mean" % ci]) and np.array_equal(std_f, golden["train_%d_std" % ci])
+        pal, occ, chosen = host.init_score_arrays(dist, values)
+        probs = host.define_multinomial_probs(values) if dist == "multinomial" else None
+        be = FakeBackend(tr_d, tr_l, mean_f, std_f, 4, 6)
+        with redirect_stdout(io.StringIO()):
+            loops.isprs_train(be, tr_d, tr_l, tr_distr, rot, te_d, te_l, te_distr, ["1"], 4, 14, upd, dist, values, pal, occ,
+                              chosen, probs, 20, str(tmp_path) + "/", 50, "vaihingen", "", final_validation=False)
+        ref = golden["train_%d_log" % ci]
+        got = np.array(be.log, dtype=np.float64)
+        assert got.shape == ref.shape
+        assert np.array_equal(got[:, :3], ref[:, :3])                      # is_training, patch size, batch size per step
+        assert np.array_equal(got[:, 4], ref[:, 4])                        # labels fed
+        assert np.allclose(got[:, 3], ref[:, 3], rtol=1e-12, atol=1e-9)    # normalised float64 patches fed
+        if dist != "single_fixed":
+            assert np.array_equal(np.load(tmp_path / "patch_acc_loss_step_14.npy"), golden["train_%d_pal" % ci])
+            assert np.array_equal(np.load(tmp_path / "patch_occur_step_14.npy"), golden["train_%d_occ" % ci])
+            assert np.array_equal(np.load(tmp_path / "patch_chosen_values_step_14.npy"), golden["train_%d_chosen" % ci])
+        assert be.saved == [str(tmp_path) + "/model-14"]
+    finally:
+        os.chdir(cwd)
+
+
+def test_metrics_from_confusion_match_sklearn():
+    from drs_b200 import loops
+    from sklearn.metrics import cohen_kappa_score, f1_score
+    rs = np.random.RandomState(0)
+    t = rs.randint(0, 6, size=5000)
+    p = np.where(rs.rand(5000) < 0.6, t, rs.randint(0, 6, size=5000))
+    cm = loops.confusion_counts(t, p, 6)
+    assert cm.sum() == 5000 and cm[2, 3] == int(((t == 2) & (p == 3)).sum())
+    assert abs(loops.kappa_from_cm(cm) - cohen_kappa_score(t, p)) < 1e-12
+    assert np.allclose(loops.f1_per_class_from_cm(cm), f1_score(t, p, average=None), atol=1e-12)
+    cm_i = loops.confusion_counts(np.where(rs.rand(5000) < 0.1, 6, t), p, 7)[:6, :6]     # eroded label 6 dropped
+    assert cm_i.sum() < 5000
