@@ -42,44 +42,63 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md), sampled every 5 ms through NVML
+    (nvidia-smi -lms cannot sample a region of a few tens of milliseconds); falls back to one nvidia-smi query."""
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.stop_flag, self.thread, self.nv = index, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        sm, mx, reasons, pw = [], [], set(), []
-        for ln in self.lines:
-            f = [t.strip() for t in ln.split(",")]
-            if len(f) < 8:
-                continue
+        if self.nv is None:
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,power.draw",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout.split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "power_w_max": float(out[2]), "samples": 1,
+                        "reasons": [], "note": "single nvidia-smi sample after the timed region (NVML unavailable)"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        nv = self.nv
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        reasons = set()
+        for _, _, r in self.samples:
+            for k, bit in names.items():
+                if r & bit:
+                    reasons.add(k)
+        sm = [s[0] for s in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "power_w_max": max([s[1] for s in self.samples]) if self.samples else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
 
 
 def dist_env():
@@ -108,6 +127,7 @@ class TrainHost:
         self.total = len(self.instances)
         self.shuffle = np.asarray(random.sample(range(self.total), self.total))
         self.it = 0
+        self.rs_flips = np.random.RandomState(seed + 1)   # own stream: the patch-size sequence must not depend on the batch size
 
     def next_plan(self):
         host = self.host
@@ -119,7 +139,7 @@ class TrainHost:
             m, r, c = int(self.instances[i][0]), int(self.instances[i][1]), int(self.instances[i][2])
             r, c = host.shift_back(r, c, int(crop), *self.shapes[m])
             inst[b] = (m, r, c)
-        flips = np.random.randint(0, 3, size=len(batch)).astype(np.uint8)      # isprs:304 flip decision per patch
+        flips = self.rs_flips.randint(0, 3, size=len(batch)).astype(np.uint8)  # isprs:304 flip decision per patch
         return int(crop), idx, inst, flips
 
     def update(self, idx, loss, cm):
