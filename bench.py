@@ -42,8 +42,9 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md), sampled every 5 ms through NVML
-    (nvidia-smi -lms cannot sample a region of a few tens of milliseconds); falls back to one nvidia-smi query."""
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md) through NVML: a burst of samples
+    10 ms apart for short regions, then one every 200 ms (NVML calls take a driver lock that kernel launches also need;
+    polling every 5 ms slowed the launch-heavy scene pass by 50 %).  Falls back to one nvidia-smi query."""
 
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.thread, self.nv = index, [], False, None, None
@@ -70,7 +71,7 @@ class ClockSampler:
                 self.samples.append((sm, pw, rs))
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.01 if len(self.samples) < 8 else 0.2)
 
     def stop(self):
         if self.nv is None:

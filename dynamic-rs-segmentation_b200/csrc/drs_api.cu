@@ -94,7 +94,28 @@ struct InferLane {
   cudaEvent_t fwd_done = nullptr, acc_done = nullptr;
 };
 
+// One captured training step (CUDA graph) per (batch, patch size, buffers, learning rate): the step is ~65 small
+// dependent launches, so replaying it as a graph removes the launch gaps between them.
+struct TrainGraphKey {
+  int B, crop, ignore_label, profiling;
+  const void *x, *y, *mask, *acc_mask, *pred, *cm;
+  uint64_t lr_bits;
+  uint64_t arena_epoch;
+  bool operator<(const TrainGraphKey& o) const { return memcmp(this, &o, sizeof(*this)) < 0; }
+};
+struct TrainGraph {
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0, conv_launches = 0;
+  double conv_flops = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;   // external event-record nodes around the tensor-core launches
+};
+
 struct HandleExtra {
+  std::map<TrainGraphKey, TrainGraph> graphs;
+  std::map<TrainGraphKey, int> graph_seen;
+  TrainGraph* capturing = nullptr;   // non-null while a training step is being captured
+  bool use_graphs = true;
+  double conv_ms_acc = 0;            // device time of profiled launches already read back
   InferLane lanes[2];             // scene-inference lanes (drs_scene_api.cuh)
   cudaEvent_t lanes_ready = nullptr;
   uint8_t* is_weight = nullptr;   // [n_trainable] 1 for `weights` variables
@@ -221,7 +242,14 @@ extern "C" int drs_destroy(drs_handle_t h) {
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
   HandleExtra* x = X(h);
-  if (x) lanes_release(h);
+  if (x) {
+    lanes_release(h);
+    for (auto& kv : x->graphs) {
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      for (auto& pr : kv.second.events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    }
+    x->graphs.clear();
+  }
   free_packed(h);
   for (auto& kv : h->scenes) {
     if (kv.second.data) cudaFree(kv.second.data);
@@ -486,6 +514,16 @@ struct ActBuf { void* p; int cs; int co; };   // pointer, channel stride, channe
 
 static void prof_begin(Handle* h, cudaEvent_t* a, cudaEvent_t* b) {
   if (!h->time_convs) return;
+  HandleExtra* x = X(h);
+  if (x->capturing) {
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    x->capturing->events.push_back({e0, e1});
+    *a = e0; *b = e1;
+    CUDA_CHECK(cudaEventRecordWithFlags(e0, h->stream, cudaEventRecordExternal));
+    return;
+  }
   if (h->conv_events_used == h->conv_events.size()) {
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0));
@@ -499,6 +537,7 @@ static void prof_begin(Handle* h, cudaEvent_t* a, cudaEvent_t* b) {
 }
 static void prof_end(Handle* h, cudaEvent_t b) {
   if (!h->time_convs) return;
+  if (X(h)->capturing) { CUDA_CHECK(cudaEventRecordWithFlags(b, h->stream, cudaEventRecordExternal)); return; }
   CUDA_CHECK(cudaEventRecord(b, h->stream));
 }
 

@@ -121,6 +121,7 @@ struct drs_handle_s {
 
   // workspace
   Arena arena;
+  uint64_t arena_epoch = 0;
   // pinned staging for *_host entry points
   void* pinned = nullptr;
   size_t pinned_cap = 0;
@@ -162,6 +163,7 @@ static inline void ensure_arena(Handle* h, size_t bytes) {
   if (h->arena.base) CUDA_CHECK(cudaFree(h->arena.base));
   h->arena.base = nullptr;
   h->arena.cap = 0;
+  h->arena_epoch++;          // cached CUDA graphs hold pointers into the old arena
   size_t want = bytes + (bytes >> 3) + (size_t(1) << 20);
   CUDA_CHECK(cudaMalloc(&h->arena.base, want));
   h->arena.cap = want;

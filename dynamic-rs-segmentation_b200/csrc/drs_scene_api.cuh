@@ -404,6 +404,7 @@ extern "C" int drs_set_profiling(drs_handle_t h, int32_t on) {
   h->conv_events_used = 0;
   X(h)->conv_flops = 0;
   X(h)->conv_launches = 0;
+  X(h)->conv_ms_acc = 0;
   API_END
 }
 // Sum of the device time of the tensor-core convolution launches recorded since drs_set_profiling(1)
@@ -412,7 +413,8 @@ extern "C" int drs_profile_read(drs_handle_t h, float* conv_ms, int64_t* conv_la
   API_BEGIN
   DRS_CHECK(h, "null handle");
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
-  float total = 0.0f;
+  float total = (float)X(h)->conv_ms_acc;
+  X(h)->conv_ms_acc = 0;
   for (size_t i = 0; i < h->conv_events_used; ++i) {
     float ms = 0.0f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, h->conv_events[i].first, h->conv_events[i].second));

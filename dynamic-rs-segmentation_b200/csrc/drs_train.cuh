@@ -14,19 +14,10 @@ __global__ void unpack_extras_kernel(const float* __restrict__ src, float* __res
 }
 __global__ void add2_kernel(const float* __restrict__ a, float* __restrict__ out) { out[2] = a[0] + a[1]; }
 
-template <typename TA>
-static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
-                         const uint8_t* acc_mask_dev, int B, int crop, float* loss_host, uint8_t* pred_out_dev,
-                         uint32_t* cm_out_dev) {
+static size_t train_workspace_bytes(Handle* h, int B, int crop, size_t es) {
   NetDesc& n = h->net;
-  HandleExtra* x = X(h);
-  const int L = (int)n.convs.size();
   const int K = n.classes;
   const int64_t M = (int64_t)B * crop * crop;
-  const size_t es = sizeof(TA);
-  refresh_packed(h, true);
-
-  // ---------------------------------------------------------------- workspace plan
   int maxc = n.cls_in;
   for (auto& c : n.convs) maxc = std::max(maxc, std::max(c.co, c.ci));
   size_t need = 1 << 20;
@@ -56,7 +47,34 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   add(max_w * 4 * max_splits);
   const int nb_opt = (int)ceil_div(n.n_trainable, 256);
   add((size_t)nb_opt * 4);
-  ensure_arena(h, need);
+  return need;
+}
+
+template <typename TA>
+static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
+                         const uint8_t* acc_mask_dev, int B, int crop, float* loss_host, uint8_t* pred_out_dev,
+                         uint32_t* cm_out_dev) {
+  NetDesc& n = h->net;
+  HandleExtra* x = X(h);
+  const int L = (int)n.convs.size();
+  const int K = n.classes;
+  const int64_t M = (int64_t)B * crop * crop;
+  const size_t es = sizeof(TA);
+  refresh_packed(h, true);
+
+  // ---------------------------------------------------------------- workspace (sized by train_workspace_bytes)
+  int maxc = n.cls_in;
+  for (auto& c : n.convs) maxc = std::max(maxc, std::max(c.co, c.ci));
+  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 2);
+  const int bn_rows = (int)ceil_div(M, nb_bn);
+  const int nb_ce = (int)ceil_div(M, CE_THREADS);
+  const int nb_cls = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 4);
+  const int cls_rows = (int)ceil_div(M, nb_cls);
+  const int max_splits = 48;
+  size_t max_w = 0;
+  for (auto& c : n.convs) max_w = std::max(max_w, (size_t)c.k * c.k * c.ci * c.co);
+  const int nb_opt = (int)ceil_div(n.n_trainable, 256);
+  ensure_arena(h, train_workspace_bytes(h, B, crop, es));
   h->arena.reset();
 
   std::vector<TA*> Z(L), Xn(L);
@@ -138,30 +156,21 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
                             pred, M);
 
   // ---------------------------------------------------------------- loss (isprs:1089-1099, contest:881-901)
-  double count = (double)M;
+  // the number of pixels in the mean stays on the device (x->loss_dev[3]); contest's mask count needs no host round trip
   if (mask_dev || h->ignore_label >= 0) {
     CUDA_CHECK(cudaMemsetAsync(x->count_dev, 0, 4, h->stream));
     mask_count_kernel<<<(unsigned)std::min<int64_t>(ceil_div(M, 256), 1024), 256, 0, h->stream>>>(mask_dev, y_dev, h->ignore_label, M, x->count_dev);
     LAUNCH_CHECK(h);
-    unsigned int cnt = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&cnt, x->count_dev, 4, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    count = (double)cnt;
-    if (h->world > 1) {
-      float fc = (float)cnt;
-      CUDA_CHECK(cudaMemcpyAsync(x->loss_dev + 3, &fc, 4, cudaMemcpyHostToDevice, h->stream));
-      do_allreduce(h, x->loss_dev + 3, 1);
-      CUDA_CHECK(cudaMemcpyAsync(&fc, x->loss_dev + 3, 4, cudaMemcpyDeviceToHost, h->stream));
-      CUDA_CHECK(cudaStreamSynchronize(h->stream));
-      count = (double)fc;
-    }
+    set_count_kernel<<<1, 1, 0, h->stream>>>(x->loss_dev + 3, x->count_dev, 0.0f);
+    LAUNCH_CHECK(h);
+    if (h->world > 1) do_allreduce(h, x->loss_dev + 3, 1);
   } else {
-    count = (double)M * h->world;
+    set_count_kernel<<<1, 1, 0, h->stream>>>(x->loss_dev + 3, nullptr, (float)((double)M * h->world));
+    LAUNCH_CHECK(h);
   }
-  const float inv_count = count > 0 ? (float)(1.0 / count) : 0.0f;
-  ce_fwd_bwd_kernel<<<nb_ce, CE_THREADS, 0, h->stream>>>(logits, y_dev, mask_dev, K, M, inv_count, dlogits, part_ce, labels_u8, h->ignore_label);
+  ce_fwd_bwd_kernel<<<nb_ce, CE_THREADS, 0, h->stream>>>(logits, y_dev, mask_dev, K, M, x->loss_dev + 3, dlogits, part_ce, labels_u8, h->ignore_label);
   LAUNCH_CHECK(h);
-  sum_fixed_kernel<<<1, 256, 0, h->stream>>>(part_ce, nb_ce, x->loss_dev, inv_count);
+  sum_fixed_kernel<<<1, 256, 0, h->stream>>>(part_ce, nb_ce, x->loss_dev, 1.0f, x->loss_dev + 3);
   LAUNCH_CHECK(h);
   // fused calc_accuracy_by_crop (isprs:510-531)
   CUDA_CHECK(cudaMemsetAsync(x->cm_dev, 0, (K * K + 1) * 4, h->stream));
@@ -256,7 +265,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   momentum_update_kernel<<<nb_opt, 256, 0, h->stream>>>(h->params, h->grads, h->moms, n.n_trainable, x->is_weight, h->cfg.weight_decay, lr,
                                                         h->cfg.momentum, 1.0f, part_l2);
   LAUNCH_CHECK(h);
-  sum_fixed_kernel<<<1, 256, 0, h->stream>>>(part_l2, nb_opt, x->loss_dev + 1, 0.5f * h->cfg.weight_decay);
+  sum_fixed_kernel<<<1, 256, 0, h->stream>>>(part_l2, nb_opt, x->loss_dev + 1, 0.5f * h->cfg.weight_decay, nullptr);
   LAUNCH_CHECK(h);
   add2_kernel<<<1, 1, 0, h->stream>>>(x->loss_dev, x->loss_dev);
   LAUNCH_CHECK(h);
@@ -271,14 +280,88 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   }
 }
 
+static void train_step_dispatch(Handle* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
+                                const uint8_t* acc_mask_dev, int B, int crop, uint8_t* pred_dev, uint32_t* cm_dev) {
+  switch (act_type(h)) {
+    case ET_F32: train_step_t<float>(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, nullptr, pred_dev, cm_dev); break;
+    case ET_BF16: train_step_t<__nv_bfloat16>(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, nullptr, pred_dev, cm_dev); break;
+    default:
+      DRS_FAIL("train_step: precision F16 is inference-only (gradients underflow in fp16); create the handle with DRS_PREC_BF16 or DRS_PREC_FP32");
+  }
+}
+
 static void train_step(Handle* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
                        const uint8_t* acc_mask_dev, int B, int crop, float* loss_host, uint8_t* pred_dev, uint32_t* cm_dev) {
   DRS_CHECK(B >= 1 && crop >= 3 && crop <= 256, "train_step: bad B=%d crop=%d", B, crop);
-  switch (act_type(h)) {
-    case ET_F32: train_step_t<float>(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, loss_host, pred_dev, cm_dev); break;
-    case ET_BF16: train_step_t<__nv_bfloat16>(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, loss_host, pred_dev, cm_dev); break;
-    default:
-      DRS_FAIL("train_step: precision F16 is inference-only (gradients underflow in fp16); create the handle with DRS_PREC_BF16 or DRS_PREC_FP32");
+  HandleExtra* x = X(h);
+  const size_t es = h->cfg.precision == DRS_PREC_FP32 ? 4 : 2;
+  TrainGraph* replay = nullptr;
+  const bool graphable = x->use_graphs && h->world <= 1 && !getenv("DRS_DEBUG_KEEP") && !getenv("DRS_NO_GRAPHS") &&
+                         h->cfg.precision != DRS_PREC_F16;
+  if (!graphable) {
+    train_step_dispatch(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, pred_dev, cm_dev);
+  } else {
+    ensure_arena(h, train_workspace_bytes(h, B, crop, es));        // before the key: a re-allocation bumps arena_epoch
+    const float lr = h->cfg.lr_initial * powf(h->cfg.decay_rate, (float)(h->global_step / (h->cfg.decay_steps > 0 ? h->cfg.decay_steps : 1)));
+    TrainGraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.B = B; key.crop = crop; key.ignore_label = h->ignore_label; key.profiling = h->time_convs ? 1 : 0;
+    key.x = x_dev; key.y = y_dev; key.mask = mask_dev; key.acc_mask = acc_mask_dev; key.pred = pred_dev; key.cm = cm_dev;
+    memcpy(&key.lr_bits, &lr, 4);
+    key.arena_epoch = h->arena_epoch;
+    auto it = x->graphs.find(key);
+    if (it != x->graphs.end()) {
+      replay = &it->second;
+      CUDA_CHECK(cudaGraphLaunch(replay->exec, h->stream));
+      h->launches += replay->launches;
+      x->conv_flops += replay->conv_flops;
+      x->conv_launches += replay->conv_launches;
+      h->global_step++;
+      h->packed_dirty = true;
+      h->eval_dirty = true;
+    } else if (x->graph_seen[key]++ == 0) {
+      // first sighting of this shape: run eagerly (allocations, function attributes), capture on the second
+      train_step_dispatch(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, pred_dev, cm_dev);
+    } else {
+      TrainGraph g;
+      const int64_t l0 = h->launches, cl0 = x->conv_launches;
+      const double f0 = x->conv_flops;
+      h->packed_dirty = true;                        // the operand repack must be part of every replay
+      CUDA_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+      x->capturing = &g;
+      cudaGraph_t graph = nullptr;
+      try {
+        train_step_dispatch(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, pred_dev, cm_dev);
+      } catch (...) {
+        x->capturing = nullptr;
+        cudaStreamEndCapture(h->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      x->capturing = nullptr;
+      CUDA_CHECK(cudaStreamEndCapture(h->stream, &graph));
+      cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      CUDA_CHECK(e);
+      g.launches = h->launches - l0;
+      g.conv_launches = x->conv_launches - cl0;
+      g.conv_flops = x->conv_flops - f0;
+      auto ins = x->graphs.emplace(key, g);
+      replay = &ins.first->second;
+      CUDA_CHECK(cudaGraphLaunch(replay->exec, h->stream));
+    }
+  }
+  if (loss_host) CUDA_CHECK(cudaMemcpyAsync(loss_host, x->loss_dev + 2, 4, cudaMemcpyDeviceToHost, h->stream));
+  if (loss_host || (replay && h->time_convs)) {
+    int rc = drs_synchronize(h);
+    if (rc) throw DrsError{rc};
+  }
+  if (replay && h->time_convs) {
+    for (auto& pr : replay->events) {
+      float ms = 0.0f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+      x->conv_ms_acc += ms;
+    }
   }
 }
 

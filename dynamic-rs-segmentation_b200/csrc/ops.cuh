@@ -607,9 +607,11 @@ classifier_bwd_weight_kernel(const T* __restrict__ x, int x_cs, int x_co, int Ci
 constexpr int CE_THREADS = 256;
 __global__ void __launch_bounds__(CE_THREADS)
 ce_fwd_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ labels_f, const uint8_t* __restrict__ mask,
-                  int K, int64_t M, float inv_count, float* __restrict__ dlogits, float* __restrict__ part_loss,
-                  uint8_t* __restrict__ labels_u8, int ignore_label) {
+                  int K, int64_t M, const float* __restrict__ count_ptr, float* __restrict__ dlogits,
+                  float* __restrict__ part_loss, uint8_t* __restrict__ labels_u8, int ignore_label) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float cnt = *count_ptr;                       // number of pixels in the mean (device scalar: no host round trip)
+  const float inv_count = cnt > 0.0f ? 1.0f / cnt : 0.0f;
   float loss = 0.0f;
   if (m < M) {
     float z[MAX_CLASSES];
@@ -658,7 +660,8 @@ __global__ void mask_count_kernel(const uint8_t* __restrict__ mask, const float*
 }
 
 // out[0] = sum of n floats in fixed order (single block)
-__global__ void sum_fixed_kernel(const float* __restrict__ in, int n, float* __restrict__ out, float scale) {
+__global__ void sum_fixed_kernel(const float* __restrict__ in, int n, float* __restrict__ out, float scale,
+                                 const float* __restrict__ divide_by) {
   __shared__ double s[256];
   double a = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) a += (double)in[i];
@@ -668,7 +671,15 @@ __global__ void sum_fixed_kernel(const float* __restrict__ in, int n, float* __r
     if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[0] = (float)(s[0] * (double)scale);
+  if (threadIdx.x == 0) {
+    double v = s[0] * (double)scale;
+    if (divide_by) v = *divide_by > 0.0f ? v * (double)(1.0f / *divide_by) : 0.0;
+    out[0] = (float)v;
+  }
+}
+// count of unmasked pixels as the float the loss kernels read
+__global__ void set_count_kernel(float* __restrict__ out, const unsigned int* __restrict__ cnt, float fixed) {
+  out[0] = cnt ? (float)cnt[0] : fixed;
 }
 
 // ------------------------------------------------------------------------------------------------
