@@ -201,13 +201,26 @@ wgrad_simt_kernel(const TIn* __restrict__ in, int in_cstride, int in_coff, int c
   }
 }
 
-// out[i] = sum_{s=0..S-1} part[s][i] (fixed order); optionally out += existing
+// out[i] = sum_{s=0..S-1} part[s][i] (fixed order).  n is a multiple of 4 for every caller (Co % 4 == 0) except the
+// classifier's bias row, which takes the scalar tail.
 __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s = 0.0f;
-  for (int k = 0; k < S; ++k) s += part[(int64_t)k * n + i];
-  out[i] = s;
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  if (i4 + 4 <= n && (n & 3) == 0) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int k = 0; k < S; ++k) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(part + (int64_t)k * n + i4));
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + i4) = a;
+  } else {
+    for (int64_t i = i4; i < min(n, i4 + 4); ++i) {
+      float s = 0.0f;
+      for (int k = 0; k < S; ++k) s += part[(int64_t)k * n + i];
+      out[i] = s;
+    }
+  }
 }
 
 template <typename TIn, typename TG>
@@ -226,7 +239,7 @@ static void launch_wgrad_simt(Handle* h, const TIn* in, int in_cstride, int in_c
                                                                    co, part, (int)M, crop, k, rate, pad_b, m_per);
   LAUNCH_CHECK(h);
   const int64_t n = (int64_t)Ktot * co;
-  reduce_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, h->stream>>>(part, dw, n, splits);
+  reduce_partials_kernel<<<(unsigned)ceil_div(n, 1024), 256, 0, h->stream>>>(part, dw, n, splits);
   LAUNCH_CHECK(h);
 }
 

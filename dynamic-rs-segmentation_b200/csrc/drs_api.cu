@@ -114,7 +114,7 @@ struct HandleExtra {
   std::map<TrainGraphKey, TrainGraph> graphs;
   std::map<TrainGraphKey, int> graph_seen;
   TrainGraph* capturing = nullptr;   // non-null while a training step is being captured
-  bool use_graphs = true;
+  bool use_graphs = false;          // opt-in (DRS_GRAPHS=1): measured 6-9 % per step in steady state, see DESIGN.md
   double conv_ms_acc = 0;            // device time of profiled launches already read back
   InferLane lanes[2];             // scene-inference lanes (drs_scene_api.cuh)
   cudaEvent_t lanes_ready = nullptr;
@@ -232,6 +232,7 @@ extern "C" int drs_create(drs_handle_t* out, const drs_config* cfg) {
   CUDA_CHECK(cudaEventCreate(&h->ev_b));
   h->packed_dirty = true;
   h->eval_dirty = true;
+  x->use_graphs = getenv("DRS_GRAPHS") != nullptr && atoi(getenv("DRS_GRAPHS")) != 0;
   *out = h;
   API_END
 }

@@ -146,7 +146,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
       launch_maxpool3_fwd<TA>(h, Z[l], c.co, 0, Xn[l], c.co, 0, idx[l], c.co, B, crop, mean, istd, n.act);
     } else {
       ActBuf ab = n.dense ? ActBuf{F, n.feat_stride, c.out_coff} : ActBuf{Xn[l], c.co, 0};
-      bn_apply_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>(Z[l], c.co, 0, mean, istd, n.act, (TA*)ab.p, ab.cs, ab.co, c.co, M);
+      bn_apply_kernel<TA><<<bne_grid(M, h->sm_count), BNE_THREADS, 0, h->stream>>>(Z[l], c.co, 0, mean, istd, n.act, (TA*)ab.p, ab.cs, ab.co, c.co, M);
       LAUNCH_CHECK(h);
     }
     h->taps[c.scope] = {n.dense ? (void*)F : (void*)Xn[l], ElemTag<TA>::v, n.dense ? n.feat_stride : c.co, n.dense ? c.out_coff : 0, c.co, M};
@@ -182,7 +182,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   classifier_bwd_weight_kernel<TA><<<nb_cls, CLSW_THREADS, 0, h->stream>>>((const TA*)feat.p, feat.cs, feat.co, n.cls_in, dlogits, K, part_cls,
                                                                            part_clsb, M, cls_rows);
   LAUNCH_CHECK(h);
-  reduce_partials_kernel<<<nblk((int64_t)n.cls_in * K, 256), 256, 0, h->stream>>>(part_cls, h->grads + n.cls_w_off, (int64_t)n.cls_in * K, nb_cls);
+  reduce_partials_kernel<<<nblk((int64_t)n.cls_in * K, 1024), 256, 0, h->stream>>>(part_cls, h->grads + n.cls_w_off, (int64_t)n.cls_in * K, nb_cls);
   LAUNCH_CHECK(h);
   reduce_partials_kernel<<<1, 256, 0, h->stream>>>(part_clsb, h->grads + n.cls_b_off, K, nb_cls);
   LAUNCH_CHECK(h);
@@ -200,8 +200,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     ActBuf dOut = n.dense ? ActBuf{GF, n.feat_stride, c.out_coff} : ActBuf{Gcur, gcs, 0};
     ActBuf dA = dOut;
     if (n.pool) {
-      maxpool3_bwd_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>((const TA*)dOut.p, dOut.cs, dOut.co, idx[l], T, c.co, 0, c.co, M, crop);
-      LAUNCH_CHECK(h);
+      launch_maxpool3_bwd<TA>(h, (const TA*)dOut.p, dOut.cs, dOut.co, idx[l], T, c.co, 0, c.co, M, crop);
       dA = ActBuf{T, c.co, 0};
     }
     float* mean = x->mean + c.mm_off;
@@ -210,7 +209,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     bn_partial_kernel<TA, TA, 1><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, n.act, part_bn, c.co, M, bn_rows, finb);
     LAUNCH_CHECK(h);
     if (h->sync_bn) do_allreduce(h, x->sums, 2 * c.co);
-    bn_bwd_apply_kernel<TA, TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, x->sums,
+    bn_bwd_apply_kernel<TA, TA><<<bne_grid(M, h->sm_count), BNE_THREADS, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, x->sums,
                                                                                    1.0 / bn_count, n.act, DZ, c.co, 0, c.co, M);
     LAUNCH_CHECK(h);
     debug_keep<TA>(h, "da:" + c.scope, (const TA*)dA.p, dA.cs, dA.co, c.co, M);
@@ -291,7 +290,8 @@ static void train_step_dispatch(Handle* h, const float* x_dev, const float* y_de
 }
 
 static void train_step(Handle* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
-                       const uint8_t* acc_mask_dev, int B, int crop, float* loss_host, uint8_t* pred_dev, uint32_t* cm_dev) {
+                       const uint8_t* acc_mask_dev, int B, int crop, float* loss_host, uint8_t* pred_dev, uint32_t* cm_dev,
+                       bool capture_only = false) {
   DRS_CHECK(B >= 1 && crop >= 3 && crop <= 256, "train_step: bad B=%d crop=%d", B, crop);
   HandleExtra* x = X(h);
   const size_t es = h->cfg.precision == DRS_PREC_FP32 ? 4 : 2;
@@ -299,6 +299,7 @@ static void train_step(Handle* h, const float* x_dev, const float* y_dev, const 
   const bool graphable = x->use_graphs && h->world <= 1 && !getenv("DRS_DEBUG_KEEP") && !getenv("DRS_NO_GRAPHS") &&
                          h->cfg.precision != DRS_PREC_F16;
   if (!graphable) {
+    if (capture_only) return;
     train_step_dispatch(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, pred_dev, cm_dev);
   } else {
     ensure_arena(h, train_workspace_bytes(h, B, crop, es));        // before the key: a re-allocation bumps arena_epoch
@@ -312,17 +313,12 @@ static void train_step(Handle* h, const float* x_dev, const float* y_dev, const 
     auto it = x->graphs.find(key);
     if (it != x->graphs.end()) {
       replay = &it->second;
-      CUDA_CHECK(cudaGraphLaunch(replay->exec, h->stream));
       h->launches += replay->launches;
       x->conv_flops += replay->conv_flops;
       x->conv_launches += replay->conv_launches;
       h->global_step++;
-      h->packed_dirty = true;
-      h->eval_dirty = true;
-    } else if (x->graph_seen[key]++ == 0) {
-      // first sighting of this shape: run eagerly (allocations, function attributes), capture on the second
-      train_step_dispatch(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, pred_dev, cm_dev);
     } else {
+      // capture (nothing executes while capturing), then launch like any later replay
       TrainGraph g;
       const int64_t l0 = h->launches, cl0 = x->conv_launches;
       const double f0 = x->conv_flops;
@@ -343,13 +339,23 @@ static void train_step(Handle* h, const float* x_dev, const float* y_dev, const 
       cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
       cudaGraphDestroy(graph);
       CUDA_CHECK(e);
+      CUDA_CHECK(cudaGraphUpload(g.exec, h->stream));   // pay the device-side set-up now, not at the first replay
       g.launches = h->launches - l0;
       g.conv_launches = x->conv_launches - cl0;
       g.conv_flops = x->conv_flops - f0;
       auto ins = x->graphs.emplace(key, g);
       replay = &ins.first->second;
-      CUDA_CHECK(cudaGraphLaunch(replay->exec, h->stream));
+      if (capture_only) {                            // drs_train_prepare: undo the host-side bookkeeping of the dry capture
+        h->launches = l0;
+        x->conv_launches = cl0;
+        x->conv_flops = f0;
+        h->global_step--;
+        return;
+      }
     }
+    CUDA_CHECK(cudaGraphLaunch(replay->exec, h->stream));
+    h->packed_dirty = true;
+    h->eval_dirty = true;
   }
   if (loss_host) CUDA_CHECK(cudaMemcpyAsync(loss_host, x->loss_dev + 2, 4, cudaMemcpyDeviceToHost, h->stream));
   if (loss_host || (replay && h->time_convs)) {
@@ -372,6 +378,15 @@ extern "C" int drs_train_step_dev(drs_handle_t h, const float* x_dev, const floa
   DRS_CHECK(h && x_dev && y_dev, "null argument");
   CUDA_CHECK(cudaSetDevice(h->cfg.device));
   train_step(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, loss_out_host, pred_dev, cm_dev);
+  API_END
+}
+
+extern "C" int drs_train_prepare(drs_handle_t h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
+                                 const uint8_t* acc_mask_dev, int32_t B, int32_t crop, uint8_t* pred_dev, uint32_t* cm_dev) {
+  API_BEGIN
+  DRS_CHECK(h && x_dev && y_dev, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  train_step(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, nullptr, pred_dev, cm_dev, true);
   API_END
 }
 

@@ -156,6 +156,135 @@ maxpool3_fwd_packed_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __
   }
 }
 
+// Training variant for bf16 (winner codes + fused normalise/activation) on packed 2-wide compare / max / select: a third
+// of the instructions of the scalar float version, same first-maximum semantics (strictly-greater replaces, row-major).
+__device__ __forceinline__ void pool_pk_row(const __nv_bfloat16* __restrict__ in, int in_cs, int64_t pix_row0, int x, int crop,
+                                            int y, __nv_bfloat162 (&rv)[4], unsigned (&ri)[4]) {
+  const unsigned ninf2 = 0xFF80FF80u;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) { rv[w] = *reinterpret_cast<const __nv_bfloat162*>(&ninf2); ri[w] = 0u; }
+  if (y < 0 || y >= crop) return;
+#pragma unroll
+  for (int dx = -1; dx <= 1; ++dx) {
+    const int xx = x + dx;
+    if (xx < 0 || xx >= crop) continue;
+    const uint4 raw = *reinterpret_cast<const uint4*>(in + (pix_row0 + (int64_t)y * crop + xx) * in_cs);
+    const __nv_bfloat162* q = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const unsigned code2 = (unsigned)(dx + 1) * 0x00010001u;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const unsigned m = __hgt2_mask(q[w], rv[w]);
+      rv[w] = __hmax2(rv[w], q[w]);
+      ri[w] = (ri[w] & ~m) | (code2 & m);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool3_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cs, int in_co, __nv_bfloat16* __restrict__ out,
+                               int out_cs, int out_co, uint8_t* __restrict__ idx, int C, int B, int crop, int seg, int nseg,
+                               const float* __restrict__ bn_mean, const float* __restrict__ bn_inv_std, int act) {
+  const int cv = C >> 3;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)B * nseg * crop * cv) return;
+  const int cg = (int)(gid % cv);
+  int64_t t = gid / cv;
+  const int x = (int)(t % crop);
+  t /= crop;
+  const int sg = (int)(t % nseg);
+  const int b = (int)(t / nseg);
+  const int y0 = sg * seg, y1 = min(crop, y0 + seg);
+  const int64_t img0 = (int64_t)b * crop * crop;
+  const __nv_bfloat16* inp = in + in_co + cg * 8;
+  float mu[8], is[8];
+  if (bn_mean) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { mu[e] = bn_mean[cg * 8 + e]; is[e] = bn_inv_std[cg * 8 + e]; }
+  }
+  __nv_bfloat162 v0[4], v1[4], v2[4];
+  unsigned i0[4], i1[4], i2[4];
+  pool_pk_row(inp, in_cs, img0, x, crop, y0 - 1, v0, i0);
+  pool_pk_row(inp, in_cs, img0, x, crop, y0, v1, i1);
+  for (int y = y0; y < y1; ++y) {
+    pool_pk_row(inp, in_cs, img0, x, crop, y + 1, v2, i2);
+    uint4 o;
+    unsigned code[4];
+    unsigned* ow = reinterpret_cast<unsigned*>(&o);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      __nv_bfloat162 best = v0[w];
+      unsigned bi = i0[w];
+      unsigned m = __hgt2_mask(v1[w], best);
+      best = __hmax2(best, v1[w]);
+      bi = (bi & ~m) | ((i1[w] + 0x00030003u) & m);
+      m = __hgt2_mask(v2[w], best);
+      best = __hmax2(best, v2[w]);
+      bi = (bi & ~m) | ((i2[w] + 0x00060006u) & m);
+      code[w] = bi;
+      if (bn_mean) {
+        const float lo = apply_act((__low2float(best) - mu[2 * w]) * is[2 * w], act);
+        const float hi = apply_act((__high2float(best) - mu[2 * w + 1]) * is[2 * w + 1], act);
+        best = __floats2bfloat162_rn(lo, hi);
+      }
+      ow[w] = *reinterpret_cast<unsigned*>(&best);
+    }
+    const int64_t m = img0 + (int64_t)y * crop + x;
+    *reinterpret_cast<uint4*>(out + m * out_cs + out_co + cg * 8) = o;
+    uint2 pk;
+    pk.x = __byte_perm(code[0], code[1], 0x6420);      // low byte of every 16-bit lane
+    pk.y = __byte_perm(code[2], code[3], 0x6420);
+    *reinterpret_cast<uint2*>(idx + m * C + cg * 8) = pk;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { v0[w] = v1[w]; v1[w] = v2[w]; i0[w] = i1[w]; i1[w] = i2[w]; }
+  }
+}
+
+// dIn for bf16: byte-wise code compare, byte mask -> 16-bit lane mask, masked values widened to fp32 by bit shifts
+__global__ void maxpool3_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dout, int do_cs, int do_co, const uint8_t* __restrict__ idx,
+                                         __nv_bfloat16* __restrict__ din, int di_cs, int di_co, int C, int64_t M, int crop) {
+  const int cv = C >> 3;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= M * cv) return;
+  const int64_t m = gid / cv;
+  const int c0 = (int)(gid - m * cv) << 3;
+  const int cc = crop * crop;
+  const int r = (int)(m % cc);
+  const int y = r / crop, x = r - y * crop;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int yo = y - dy;
+    if (yo < 0 || yo >= crop) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int xo = x - dx;
+      if (xo < 0 || xo >= crop) continue;
+      const int64_t mo = m - dy * crop - dx;
+      const uint2 pk = *reinterpret_cast<const uint2*>(idx + mo * C + c0);
+      const uint4 g = *reinterpret_cast<const uint4*>(dout + mo * do_cs + do_co + c0);
+      const unsigned code4 = (unsigned)((dy + 1) * 3 + (dx + 1)) * 0x01010101u;
+      const unsigned ex = __vcmpeq4(pk.x, code4), ey = __vcmpeq4(pk.y, code4);
+      const unsigned gw[4] = {g.x & __byte_perm(ex, 0, 0x1100), g.y & __byte_perm(ex, 0, 0x3322),
+                              g.z & __byte_perm(ey, 0, 0x1100), g.w & __byte_perm(ey, 0, 0x3322)};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        acc[2 * w] += __uint_as_float(gw[w] << 16);
+        acc[2 * w + 1] += __uint_as_float(gw[w] & 0xFFFF0000u);
+      }
+    }
+  }
+  uint4 o;
+  unsigned* ow = reinterpret_cast<unsigned*>(&o);
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(acc[2 * w], acc[2 * w + 1]);
+    ow[w] = *reinterpret_cast<const unsigned*>(&p);
+  }
+  *reinterpret_cast<uint4*>(din + m * di_cs + di_co + c0) = o;
+}
+
 template <typename T>
 static void launch_maxpool3_fwd(Handle* h, const T* in, int in_cs, int in_co, T* out, int out_cs, int out_co, uint8_t* idx, int C,
                                 int B, int crop, const float* bn_mean = nullptr, const float* bn_inv_std = nullptr, int act = 0) {
@@ -165,7 +294,9 @@ static void launch_maxpool3_fwd(Handle* h, const T* in, int in_cs, int in_co, T*
   nseg = (int)ceil_div(crop, seg);
   const int64_t total = base * nseg;
   const unsigned nb = (unsigned)ceil_div(total, 256);
-  if (idx && bn_mean) maxpool3_fwd_kernel<T, true, true><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, idx, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
+  if (idx && ElemTag<T>::v == ET_BF16)
+    maxpool3_fwd_train_bf16_kernel<<<nb, 256, 0, h->stream>>>((const __nv_bfloat16*)in, in_cs, in_co, (__nv_bfloat16*)out, out_cs, out_co, idx, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
+  else if (idx && bn_mean) maxpool3_fwd_kernel<T, true, true><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, idx, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
   else if (idx) maxpool3_fwd_kernel<T, true, false><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, idx, C, B, crop, seg, nseg, nullptr, nullptr, 0);
   else if (bn_mean) maxpool3_fwd_kernel<T, false, true><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, nullptr, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
   else maxpool3_fwd_packed_kernel<T><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, C, B, crop, seg, nseg);
@@ -210,6 +341,17 @@ __global__ void maxpool3_bwd_kernel(const T* __restrict__ dout, int do_cs, int d
 #pragma unroll
   for (int e = 0; e < 8; ++e) o.v[e] = from_f32<T>(acc[e]);
   *reinterpret_cast<Vec8<T>*>(din + m * di_cs + di_co + c0) = o;
+}
+
+template <typename T>
+static void launch_maxpool3_bwd(Handle* h, const T* dout, int do_cs, int do_co, const uint8_t* idx, T* din, int di_cs, int di_co,
+                                int C, int64_t M, int crop) {
+  const unsigned nb = (unsigned)ceil_div(M * (C / 8), 256);
+  if (ElemTag<T>::v == ET_BF16)
+    maxpool3_bwd_bf16_kernel<<<nb, 256, 0, h->stream>>>((const __nv_bfloat16*)dout, do_cs, do_co, idx, (__nv_bfloat16*)din, di_cs, di_co, C, M, crop);
+  else
+    maxpool3_bwd_kernel<T><<<nb, 256, 0, h->stream>>>(dout, do_cs, do_co, idx, din, di_cs, di_co, C, M, crop);
+  LAUNCH_CHECK(h);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -341,51 +483,65 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, float* __rest
   mov_var[c] = decay * mov_var[c] + (1.0f - decay) * (float)var_ema;
 }
 
+// Row-slab layout shared by the two element-wise BN kernels: thread = (channel group of 8, row lane); a block walks
+// its rows with the per-channel constants (mean, inv_std, reduced sums) held in registers.
+constexpr int BNE_THREADS = 256;
+static inline int bne_grid(int64_t M, int sm_count) { return (int)std::min<int64_t>(ceil_div(M, 64), (int64_t)sm_count * 8); }
+
 // out = act((z - mean) * inv_std)     (training-mode normalise + activation)
 template <typename T>
-__global__ void bn_apply_kernel(const T* __restrict__ z, int z_cs, int z_co, const float* __restrict__ mean,
-                                const float* __restrict__ inv_std, int act, T* __restrict__ out, int o_cs, int o_co,
-                                int C, int64_t M) {
+__global__ void __launch_bounds__(BNE_THREADS)
+bn_apply_kernel(const T* __restrict__ z, int z_cs, int z_co, const float* __restrict__ mean, const float* __restrict__ inv_std,
+                int act, T* __restrict__ out, int o_cs, int o_co, int C, int64_t M) {
   const int cv = C >> 3;
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= M * cv) return;
-  const int64_t m = gid / cv;
-  const int c0 = (int)(gid - m * cv) << 3;
-  const Vec8<T> v = *reinterpret_cast<const Vec8<T>*>(z + m * z_cs + z_co + c0);
-  Vec8<T> o;
+  const int lanes_r = BNE_THREADS / cv;
+  const int cg = threadIdx.x % cv, rl = threadIdx.x / cv;
+  if (rl >= lanes_r) return;
+  float mu[8], is[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e)
-    o.v[e] = from_f32<T>(apply_act((to_f32(v.v[e]) - mean[c0 + e]) * inv_std[c0 + e], act));
-  *reinterpret_cast<Vec8<T>*>(out + m * o_cs + o_co + c0) = o;
+  for (int e = 0; e < 8; ++e) { mu[e] = mean[cg * 8 + e]; is[e] = inv_std[cg * 8 + e]; }
+  for (int64_t m = (int64_t)blockIdx.x * lanes_r + rl; m < M; m += (int64_t)gridDim.x * lanes_r) {
+    const Vec8<T> v = *reinterpret_cast<const Vec8<T>*>(z + m * z_cs + z_co + cg * 8);
+    Vec8<T> o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o.v[e] = from_f32<T>(apply_act((to_f32(v.v[e]) - mu[e]) * is[e], act));
+    *reinterpret_cast<Vec8<T>*>(out + m * o_cs + o_co + cg * 8) = o;
+  }
 }
 
 // dZ = inv_std * (g - s0/M - xh * s1/M),  g = dA * act'(xh)      (no gamma/beta: SURVEY F5)
 template <typename TZ, typename TG>
-__global__ void bn_bwd_apply_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __restrict__ dA, int g_cs,
-                                    int g_co, const float* __restrict__ mean, const float* __restrict__ inv_std,
-                                    const float* __restrict__ sums, double inv_count, int act, TG* __restrict__ dZ,
-                                    int d_cs, int d_co, int C, int64_t M) {
+__global__ void __launch_bounds__(BNE_THREADS)
+bn_bwd_apply_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __restrict__ dA, int g_cs, int g_co,
+                    const float* __restrict__ mean, const float* __restrict__ inv_std, const float* __restrict__ sums,
+                    double inv_count, int act, TG* __restrict__ dZ, int d_cs, int d_co, int C, int64_t M) {
   const int cv = C >> 3;
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= M * cv) return;
-  const int64_t m = gid / cv;
-  const int c0 = (int)(gid - m * cv) << 3;
-  const Vec8<TZ> zv = *reinterpret_cast<const Vec8<TZ>*>(z + m * z_cs + z_co + c0);
-  const Vec8<TG> gv = *reinterpret_cast<const Vec8<TG>*>(dA + m * g_cs + g_co + c0);
-  Vec8<TG> o;
+  const int lanes_r = BNE_THREADS / cv;
+  const int cg = threadIdx.x % cv, rl = threadIdx.x / cv;
+  if (rl >= lanes_r) return;
+  float mu[8], is[8], m0[8], m1[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int c = c0 + e;
-    const float is = inv_std[c];
-    const float xh = (to_f32(zv.v[e]) - mean[c]) * is;
-    float g = to_f32(gv.v[e]);
-    if (act == ACT_RELU) g = xh > 0.0f ? g : 0.0f;
-    else if (act == ACT_LRELU) g = xh > 0.0f ? g : 0.1f * g;
-    const float m0 = (float)((double)sums[c] * inv_count);
-    const float m1 = (float)((double)sums[C + c] * inv_count);
-    o.v[e] = from_f32<TG>(is * (g - m0 - xh * m1));
+    const int c = cg * 8 + e;
+    mu[e] = mean[c];
+    is[e] = inv_std[c];
+    m0[e] = (float)((double)sums[c] * inv_count);
+    m1[e] = (float)((double)sums[C + c] * inv_count);
   }
-  *reinterpret_cast<Vec8<TG>*>(dZ + m * d_cs + d_co + c0) = o;
+  for (int64_t m = (int64_t)blockIdx.x * lanes_r + rl; m < M; m += (int64_t)gridDim.x * lanes_r) {
+    const Vec8<TZ> zv = *reinterpret_cast<const Vec8<TZ>*>(z + m * z_cs + z_co + cg * 8);
+    const Vec8<TG> gv = *reinterpret_cast<const Vec8<TG>*>(dA + m * g_cs + g_co + cg * 8);
+    Vec8<TG> o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (to_f32(zv.v[e]) - mu[e]) * is[e];
+      float g = to_f32(gv.v[e]);
+      if (act == ACT_RELU) g = xh > 0.0f ? g : 0.0f;
+      else if (act == ACT_LRELU) g = xh > 0.0f ? g : 0.1f * g;
+      o.v[e] = from_f32<TG>(is[e] * (g - m0[e] - xh * m1[e]));
+    }
+    *reinterpret_cast<Vec8<TG>*>(dZ + m * d_cs + d_co + cg * 8) = o;
+  }
 }
 
 // dst[:, coff:coff+C] += src (dense-net gradient accumulation into the concat gradient buffer)

@@ -284,6 +284,6 @@ static void launch_wgrad_tc(Handle* h, const WgradTcArgs& a) {
   wgrad_tc_kernel<<<grid, CONV_TC_THREADS, smem_bytes, h->stream>>>(tmX, tmDY, p);
   LAUNCH_CHECK(h);
   const int64_t n = (int64_t)Ktot * a.co;
-  reduce_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, h->stream>>>(a.part, a.dw, n, splits);
+  reduce_partials_kernel<<<(unsigned)ceil_div(n, 1024), 256, 0, h->stream>>>(a.part, a.dw, n, splits);
   LAUNCH_CHECK(h);
 }

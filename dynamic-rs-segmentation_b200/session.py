@@ -176,6 +176,12 @@ class Session:
         """contest: label 7 = unlabelled pixels, excluded from loss / gradient / confusion (contest:236-239, 886-897)."""
         L.check(self._lib.drs_set_ignore_label(self._h, -1 if label is None else int(label)))
 
+    def prepare_training(self, x_dev, y_dev, B, crops, mask_dev=None, pred_dev=None, cm_dev=None, acc_mask_dev=None):
+        """Capture the training-step graphs for the given patch sizes up front (nothing executes, no variable changes)."""
+        for crop in crops:
+            L.check(self._lib.drs_train_prepare(self._h, L.ptr(x_dev), L.ptr(y_dev), L.ptr(mask_dev), L.ptr(acc_mask_dev), B,
+                                                int(crop), L.ptr(pred_dev), L.ptr(cm_dev)))
+
     # ---------------------------------------------------------------- data-parallel hook
     def set_allreduce(self, fn, world_size, sync_bn=False):
         """fn(buf_ptr:int, count:int, stream:int) must sum ``count`` floats at ``buf_ptr`` over ranks in place."""

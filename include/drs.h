@@ -111,6 +111,12 @@ int drs_train_step_dev(drs_handle_t h, const float* x_dev, const float* y_dev, c
                        const uint8_t* acc_mask_dev, int32_t B, int32_t crop, float* loss_out_host, uint8_t* pred_dev,
                        uint32_t* cm_dev);
 
+/* Optional warm-up for the dynamic patch sizes: captures the CUDA graph of drs_train_step_dev for this (B, crop, buffers)
+ * without executing it, so that the first real step of every patch size replays instead of capturing (the analogue of
+ * TF building its graph before the loop, isprs:1652-1693).  Nothing is computed and no variable changes. */
+int drs_train_prepare(drs_handle_t h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
+                      const uint8_t* acc_mask_dev, int32_t B, int32_t crop, uint8_t* pred_dev, uint32_t* cm_dev);
+
 /* contest: pixels whose label equals `label` (7 = unlabelled, contest:236-239) are excluded from the loss mean, the
  * gradient and the fused confusion counts when no explicit mask is passed -- the boolean_mask of contest:886-897 derived
  * on the device from the labels the gather kernel produced.  label < 0 (default) disables it. */

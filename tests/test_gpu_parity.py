@@ -456,3 +456,20 @@ def test_training_is_run_to_run_deterministic(drs):
     assert outs[0][0] == outs[1][0]
     for a, b in zip(outs[0][1:], outs[1][1:]):
         assert np.array_equal(a, b)
+
+
+def test_cuda_graph_replay_matches_eager(drs, monkeypatch):
+    """DRS_GRAPHS=1 captures the training step per (batch, patch size) and replays it; same bits as the eager launches."""
+    rs = np.random.RandomState(31)
+    B, C, K = 8, 4, 6
+    batches = [(c, rs.randn(B, c * c * C).astype(np.float32), rs.randint(0, K, size=(B, c * c)).astype(np.float32))
+               for c in (13, 17, 13, 13, 17)]
+    res = []
+    for graphs in ("0", "1"):
+        monkeypatch.setenv("DRS_GRAPHS", graphs)
+        s = drs.Session("dilated_grsl", C, K, precision="bf16", seed=4)
+        losses = [float(s.train_step(x, y, c)[0]) for c, x, y in batches]
+        res.append((losses, s.get_variable("conv2/weights").copy(), s.global_step))
+        s.close()
+    assert res[0][0] == res[1][0] and res[0][2] == res[1][2] == 5
+    assert np.array_equal(res[0][1], res[1][1])
