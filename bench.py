@@ -102,6 +102,15 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def profiled_traffic(which):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return float(json.load(open(p))[which]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -261,10 +270,10 @@ def run_train_ours(args, rank, world, local):
 
     pk = peaks()
     M_total = px
-    roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 fprop + dgrad launches of the step)",
+    roof = {"bound": "tensor", "kernel": "tcgen05 kernels of the step: conv_tc_kernel (fprop + dgrad) and wgrad_tc_kernel",
             "achieved": (conv_fl / (conv_ms * 1e-3) / 1e12) if conv_ms > 0 else None, "peak": pk["tc_sustained"],
             "unit": "TFLOP/s", "frac": (conv_fl / (conv_ms * 1e-3) / 1e12 / pk["tc_sustained"]) if conv_ms > 0 else None,
-            "traffic": None, "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
+            "traffic": profiled_traffic("train"), "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
             "launches": conv_n, "kernel_ms_per_step": conv_ms / args.steps,
             "step_tflops_all_kernels": conv_flops_train(cfg["net"], cfg["C"], cfg["K"], M_total) / (ms * 1e-3) / 1e12}
     return dict(metric="train patches/s", value=value, unit="patches/s", ms_per_step=ms / args.steps, dtype="bf16",
@@ -342,7 +351,7 @@ def run_infer_ours(args, rank, world, local, steps=1):
                      "d2h_bytes_per_step": int(H * W), "api": "Session.upload_scene + Session.scene_infer (host scene in, host label map out)"},
                 gpu_launches=launches, clocks=clocks,
                 roofline={"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 fprop)", "achieved": ach, "peak": pk["tc_sustained"],
-                          "unit": "TFLOP/s", "frac": ach / pk["tc_sustained"] if ach else None, "traffic": None,
+                          "unit": "TFLOP/s", "frac": ach / pk["tc_sustained"] if ach else None, "traffic": profiled_traffic("inference"),
                           "peak_source": pk["source"] + " bf16 sustained", "launches": conv_n,
                           "kernel_ms_per_step": conv_ms / steps},
                 config={"workload": "configs[3]: dilated_grsl_rate8 full-scene sliding-window inference, Potsdam-shaped %dx%dx5 "

@@ -201,26 +201,46 @@ wgrad_simt_kernel(const TIn* __restrict__ in, int in_cstride, int in_coff, int c
   }
 }
 
-// out[i] = sum_{s=0..S-1} part[s][i] (fixed order).  n is a multiple of 4 for every caller (Co % 4 == 0) except the
-// classifier's bias row, which takes the scalar tail.
-__global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S) {
-  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i4 >= n) return;
-  if (i4 + 4 <= n && (n & 3) == 0) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+// out[i] = sum_{s=0..S-1} part[s][i].  Block = 32 float4 columns x 8 split lanes: lane j adds splits j, j+8, ... in order,
+// the 8 lane sums are combined in lane order through shared memory -> a fixed summation tree (deterministic) with 8x
+// the memory parallelism of a serial loop.  n is a multiple of 4 for every caller (Co % 4 == 0) except the classifier's
+// bias row, which takes the scalar path.
+constexpr int RP_COLS = 32, RP_LANES = 8;
+__global__ void __launch_bounds__(RP_COLS * RP_LANES)
+reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S) {
+  __shared__ float4 s_acc[RP_LANES][RP_COLS];
+  const int tx = threadIdx.x % RP_COLS, ty = threadIdx.x / RP_COLS;
+  if ((n & 3) != 0) {                                  // tiny scalar case
+    const int64_t i = (int64_t)blockIdx.x * (RP_COLS * RP_LANES) + threadIdx.x;
+    if (i < n) {
+      float a = 0.0f;
+      for (int k = 0; k < S; ++k) a += part[(int64_t)k * n + i];
+      out[i] = a;
+    }
+    return;
+  }
+  const int64_t i4 = ((int64_t)blockIdx.x * RP_COLS + tx) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i4 < n) {
 #pragma unroll 4
-    for (int k = 0; k < S; ++k) {
+    for (int k = ty; k < S; k += RP_LANES) {
       const float4 v = __ldcs(reinterpret_cast<const float4*>(part + (int64_t)k * n + i4));
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
-    *reinterpret_cast<float4*>(out + i4) = a;
-  } else {
-    for (int64_t i = i4; i < min(n, i4 + 4); ++i) {
-      float s = 0.0f;
-      for (int k = 0; k < S; ++k) s += part[(int64_t)k * n + i];
-      out[i] = s;
-    }
   }
+  s_acc[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && i4 < n) {
+#pragma unroll
+    for (int j = 1; j < RP_LANES; ++j) {
+      const float4 v = s_acc[j][tx];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + i4) = a;
+  }
+}
+static inline unsigned reduce_partials_grid(int64_t n) {
+  return (unsigned)((n & 3) ? ceil_div(n, RP_COLS * RP_LANES) : ceil_div(n, 4 * RP_COLS));
 }
 
 template <typename TIn, typename TG>
@@ -239,7 +259,7 @@ static void launch_wgrad_simt(Handle* h, const TIn* in, int in_cstride, int in_c
                                                                    co, part, (int)M, crop, k, rate, pad_b, m_per);
   LAUNCH_CHECK(h);
   const int64_t n = (int64_t)Ktot * co;
-  reduce_partials_kernel<<<(unsigned)ceil_div(n, 1024), 256, 0, h->stream>>>(part, dw, n, splits);
+  reduce_partials_kernel<<<reduce_partials_grid(n), RP_COLS * RP_LANES, 0, h->stream>>>(part, dw, n, splits);
   LAUNCH_CHECK(h);
 }
 

@@ -182,9 +182,9 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   classifier_bwd_weight_kernel<TA><<<nb_cls, CLSW_THREADS, 0, h->stream>>>((const TA*)feat.p, feat.cs, feat.co, n.cls_in, dlogits, K, part_cls,
                                                                            part_clsb, M, cls_rows);
   LAUNCH_CHECK(h);
-  reduce_partials_kernel<<<nblk((int64_t)n.cls_in * K, 1024), 256, 0, h->stream>>>(part_cls, h->grads + n.cls_w_off, (int64_t)n.cls_in * K, nb_cls);
+  reduce_partials_kernel<<<reduce_partials_grid((int64_t)n.cls_in * K), RP_COLS * RP_LANES, 0, h->stream>>>(part_cls, h->grads + n.cls_w_off, (int64_t)n.cls_in * K, nb_cls);
   LAUNCH_CHECK(h);
-  reduce_partials_kernel<<<1, 256, 0, h->stream>>>(part_clsb, h->grads + n.cls_b_off, K, nb_cls);
+  reduce_partials_kernel<<<reduce_partials_grid(K), RP_COLS * RP_LANES, 0, h->stream>>>(part_clsb, h->grads + n.cls_b_off, K, nb_cls);
   LAUNCH_CHECK(h);
   TA* Gcur = n.dense ? GF : G0;
   TA* Gnext = G1;
@@ -200,7 +200,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     ActBuf dOut = n.dense ? ActBuf{GF, n.feat_stride, c.out_coff} : ActBuf{Gcur, gcs, 0};
     ActBuf dA = dOut;
     if (n.pool) {
-      launch_maxpool3_bwd<TA>(h, (const TA*)dOut.p, dOut.cs, dOut.co, idx[l], T, c.co, 0, c.co, M, crop);
+      launch_maxpool3_bwd<TA>(h, (const TA*)dOut.p, dOut.cs, dOut.co, idx[l], T, c.co, 0, c.co, B, crop);
       dA = ActBuf{T, c.co, 0};
     }
     float* mean = x->mean + c.mm_off;

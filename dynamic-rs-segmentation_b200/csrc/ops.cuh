@@ -239,50 +239,84 @@ maxpool3_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cs, 
   }
 }
 
-// dIn for bf16: byte-wise code compare, byte mask -> 16-bit lane mask, masked values widened to fp32 by bit shifts
-__global__ void maxpool3_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dout, int do_cs, int do_co, const uint8_t* __restrict__ idx,
-                                         __nv_bfloat16* __restrict__ din, int di_cs, int di_co, int C, int64_t M, int crop) {
-  const int cv = C >> 3;
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= M * cv) return;
-  const int64_t m = gid / cv;
-  const int c0 = (int)(gid - m * cv) << 3;
-  const int cc = crop * crop;
-  const int r = (int)(m % cc);
-  const int y = r / crop, x = r - y * crop;
-  float acc[8];
+// dIn for bf16, column-sliding like the forward: a thread owns (image, column x, 8 channels) and walks down the rows with
+// the winner codes and output gradients of the three window rows it needs held in registers (3x fewer loads than a
+// gather per pixel).  Byte-wise code compare, byte mask -> 16-bit lane mask, masked values widened to fp32 by shifts.
+struct PoolBwdRow {
+  uint2 code[3];     // winner codes of windows (yo, x-1), (yo, x), (yo, x+1); 0xFF.. = window outside the image
+  uint4 g[3];        // their output gradients
+};
+__device__ __forceinline__ void pool_bwd_load(const __nv_bfloat16* __restrict__ dout, int do_cs, const uint8_t* __restrict__ idx,
+                                              int C, int64_t img0, int x, int crop, int yo, PoolBwdRow& r) {
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
-#pragma unroll
-  for (int dy = -1; dy <= 1; ++dy) {
-    const int yo = y - dy;
-    if (yo < 0 || yo >= crop) continue;
-#pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int xo = x - dx;
-      if (xo < 0 || xo >= crop) continue;
-      const int64_t mo = m - dy * crop - dx;
-      const uint2 pk = *reinterpret_cast<const uint2*>(idx + mo * C + c0);
-      const uint4 g = *reinterpret_cast<const uint4*>(dout + mo * do_cs + do_co + c0);
-      const unsigned code4 = (unsigned)((dy + 1) * 3 + (dx + 1)) * 0x01010101u;
-      const unsigned ex = __vcmpeq4(pk.x, code4), ey = __vcmpeq4(pk.y, code4);
-      const unsigned gw[4] = {g.x & __byte_perm(ex, 0, 0x1100), g.y & __byte_perm(ex, 0, 0x3322),
-                              g.z & __byte_perm(ey, 0, 0x1100), g.w & __byte_perm(ey, 0, 0x3322)};
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        acc[2 * w] += __uint_as_float(gw[w] << 16);
-        acc[2 * w + 1] += __uint_as_float(gw[w] & 0xFFFF0000u);
-      }
+  for (int j = 0; j < 3; ++j) {
+    const int xo = x + j - 1;
+    if (yo >= 0 && yo < crop && xo >= 0 && xo < crop) {
+      const int64_t mo = img0 + (int64_t)yo * crop + xo;
+      r.code[j] = *reinterpret_cast<const uint2*>(idx + mo * C);
+      r.g[j] = *reinterpret_cast<const uint4*>(dout + mo * do_cs);
+    } else {
+      r.code[j] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);   // never equals a code 0..8
+      r.g[j] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
-  uint4 o;
-  unsigned* ow = reinterpret_cast<unsigned*>(&o);
+}
+__device__ __forceinline__ void pool_bwd_acc(const PoolBwdRow& r, int dy, float (&acc)[8]) {
+  // window row yo = y - dy; window column xo = x - dx is r.*[1 - dx]; the input pixel is the window's element (dy, dx)
 #pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    const __nv_bfloat162 p = __floats2bfloat162_rn(acc[2 * w], acc[2 * w + 1]);
-    ow[w] = *reinterpret_cast<const unsigned*>(&p);
+  for (int dx = -1; dx <= 1; ++dx) {
+    const int j = 1 - dx;
+    const unsigned code4 = (unsigned)((dy + 1) * 3 + (dx + 1)) * 0x01010101u;
+    const unsigned ex = __vcmpeq4(r.code[j].x, code4), ey = __vcmpeq4(r.code[j].y, code4);
+    const unsigned gw[4] = {r.g[j].x & __byte_perm(ex, 0, 0x1100), r.g[j].y & __byte_perm(ex, 0, 0x3322),
+                            r.g[j].z & __byte_perm(ey, 0, 0x1100), r.g[j].w & __byte_perm(ey, 0, 0x3322)};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      acc[2 * w] += __uint_as_float(gw[w] << 16);
+      acc[2 * w + 1] += __uint_as_float(gw[w] & 0xFFFF0000u);
+    }
   }
-  *reinterpret_cast<uint4*>(din + m * di_cs + di_co + c0) = o;
+}
+
+__global__ void __launch_bounds__(256)
+maxpool3_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dout, int do_cs, int do_co, const uint8_t* __restrict__ idx,
+                         __nv_bfloat16* __restrict__ din, int di_cs, int di_co, int C, int B, int crop, int seg, int nseg) {
+  const int cv = C >> 3;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)B * nseg * crop * cv) return;
+  const int cg = (int)(gid % cv);
+  int64_t t = gid / cv;
+  const int x = (int)(t % crop);
+  t /= crop;
+  const int sg = (int)(t % nseg);
+  const int b = (int)(t / nseg);
+  const int y0 = sg * seg, y1 = min(crop, y0 + seg);
+  const int64_t img0 = (int64_t)b * crop * crop;
+  const __nv_bfloat16* dp = dout + do_co + cg * 8;
+  const uint8_t* ip = idx + cg * 8;
+  PoolBwdRow ra, rb, rc;                 // window rows y-1, y, y+1
+  pool_bwd_load(dp, do_cs, ip, C, img0, x, crop, y0 - 1, ra);
+  pool_bwd_load(dp, do_cs, ip, C, img0, x, crop, y0, rb);
+  for (int y = y0; y < y1; ++y) {
+    pool_bwd_load(dp, do_cs, ip, C, img0, x, crop, y + 1, rc);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+    // same summation order as the gather formulation: dy = -1 (window row y+1), 0, +1 (window row y-1); dx = -1, 0, +1
+    pool_bwd_acc(rc, -1, acc);
+    pool_bwd_acc(rb, 0, acc);
+    pool_bwd_acc(ra, 1, acc);
+    uint4 o;
+    unsigned* ow = reinterpret_cast<unsigned*>(&o);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const __nv_bfloat162 p = __floats2bfloat162_rn(acc[2 * w], acc[2 * w + 1]);
+      ow[w] = *reinterpret_cast<const unsigned*>(&p);
+    }
+    *reinterpret_cast<uint4*>(din + (img0 + (int64_t)y * crop + x) * di_cs + di_co + cg * 8) = o;
+    ra = rb;
+    rb = rc;
+  }
 }
 
 template <typename T>
@@ -345,12 +379,18 @@ __global__ void maxpool3_bwd_kernel(const T* __restrict__ dout, int do_cs, int d
 
 template <typename T>
 static void launch_maxpool3_bwd(Handle* h, const T* dout, int do_cs, int do_co, const uint8_t* idx, T* din, int di_cs, int di_co,
-                                int C, int64_t M, int crop) {
-  const unsigned nb = (unsigned)ceil_div(M * (C / 8), 256);
-  if (ElemTag<T>::v == ET_BF16)
-    maxpool3_bwd_bf16_kernel<<<nb, 256, 0, h->stream>>>((const __nv_bfloat16*)dout, do_cs, do_co, idx, (__nv_bfloat16*)din, di_cs, di_co, C, M, crop);
-  else
-    maxpool3_bwd_kernel<T><<<nb, 256, 0, h->stream>>>(dout, do_cs, do_co, idx, din, di_cs, di_co, C, M, crop);
+                                int C, int B, int crop) {
+  const int64_t M = (int64_t)B * crop * crop;
+  if (ElemTag<T>::v == ET_BF16) {
+    const int64_t base = (int64_t)B * crop * (C / 8);
+    int nseg = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div((int64_t)h->sm_count * 2048, base)), std::max(1, crop / 4));
+    const int seg = (int)ceil_div(crop, nseg);
+    nseg = (int)ceil_div(crop, seg);
+    maxpool3_bwd_bf16_kernel<<<(unsigned)ceil_div(base * nseg, 256), 256, 0, h->stream>>>((const __nv_bfloat16*)dout, do_cs, do_co, idx,
+                                                                                        (__nv_bfloat16*)din, di_cs, di_co, C, B, crop, seg, nseg);
+  } else {
+    maxpool3_bwd_kernel<T><<<(unsigned)ceil_div(M * (C / 8), 256), 256, 0, h->stream>>>(dout, do_cs, do_co, idx, din, di_cs, di_co, C, M, crop);
+  }
   LAUNCH_CHECK(h);
 }
 

@@ -226,7 +226,6 @@ struct WgradTcArgs {
 
 static inline bool wgrad_tc_supported(int ci, int co) { return ci % 64 == 0 && co % 64 == 0 && co >= 64 && co <= 256; }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S);
 
 static void launch_wgrad_tc(Handle* h, const WgradTcArgs& a) {
   DRS_CHECK(wgrad_tc_supported(a.ci, a.co), "wgrad_tc: unsupported Ci=%d Co=%d", a.ci, a.co);
@@ -284,6 +283,6 @@ static void launch_wgrad_tc(Handle* h, const WgradTcArgs& a) {
   wgrad_tc_kernel<<<grid, CONV_TC_THREADS, smem_bytes, h->stream>>>(tmX, tmDY, p);
   LAUNCH_CHECK(h);
   const int64_t n = (int64_t)Ktot * a.co;
-  reduce_partials_kernel<<<(unsigned)ceil_div(n, 1024), 256, 0, h->stream>>>(a.part, a.dw, n, splits);
+  reduce_partials_kernel<<<reduce_partials_grid(n), RP_COLS * RP_LANES, 0, h->stream>>>(a.part, a.dw, n, splits);
   LAUNCH_CHECK(h);
 }
