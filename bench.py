@@ -213,10 +213,12 @@ def run_train_ours(args, rank, world, local):
     for _ in range(args.warmup):
         step()
     barrier()
+    host_state = (np.random.get_state(), th.rs_flips.get_state(), th.shuffle.copy(), th.it)
+    import random as _random
+    py_state = _random.getstate()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    s.set_profiling(True)
     l0 = s.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -229,8 +231,6 @@ def run_train_ours(args, rank, world, local):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    conv_ms, conv_n, conv_fl = s.profile_read()
-    s.set_profiling(False)
     launches = s.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -238,6 +238,22 @@ def run_train_ours(args, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = B * world * args.steps / (ms / 1e3)
+
+    # ---- kernel timing pass: the SAME K steps again (host policy rewound to the same patch sizes and batches) with a CUDA
+    # event pair around every tensor-core launch.  Timing single launches needs them serialised, so this pass runs the
+    # filter gradients on the main stream instead of overlapping them with the backward's HBM-bound kernels (which is what
+    # the timed region above does); its step time is reported next to the kernel time.
+    np.random.set_state(host_state[0]); th.rs_flips.set_state(host_state[1]); th.shuffle = host_state[2]; th.it = host_state[3]
+    _random.setstate(py_state)
+    s.set_profiling(True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_prof = e0.elapsed_time(e1)
+    conv_ms, conv_n, conv_fl = s.profile_read()
+    s.set_profiling(False)
 
     # ---- end to end through the sess.run seam: host x / y in pinned memory, host loss / pred / confusion back
     e2e = None
@@ -274,7 +290,7 @@ def run_train_ours(args, rank, world, local):
             "achieved": (conv_fl / (conv_ms * 1e-3) / 1e12) if conv_ms > 0 else None, "peak": pk["tc_sustained"],
             "unit": "TFLOP/s", "frac": (conv_fl / (conv_ms * 1e-3) / 1e12 / pk["tc_sustained"]) if conv_ms > 0 else None,
             "traffic": profiled_traffic("train"), "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
-            "launches": conv_n, "kernel_ms_per_step": conv_ms / args.steps,
+            "launches": conv_n, "kernel_ms_per_step": conv_ms / args.steps, "ms_per_step_timing_pass": ms_prof / args.steps,
             "step_tflops_all_kernels": conv_flops_train(cfg["net"], cfg["C"], cfg["K"], M_total) / (ms * 1e-3) / 1e12}
     return dict(metric="train patches/s", value=value, unit="patches/s", ms_per_step=ms / args.steps, dtype="bf16",
                 scaling="weak", e2e=e2e, gpu_launches=launches, clocks=clocks, roofline=roof,

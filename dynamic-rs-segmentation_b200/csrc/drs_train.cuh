@@ -29,7 +29,7 @@ static size_t train_workspace_bytes(Handle* h, int B, int crop, size_t es) {
   }
   if (n.dense) add(M * n.feat_stride * es * 2);   // F and GF
   add(M * maxc * es);                         // T
-  add(M * maxc * es);                         // DZ
+  add(M * maxc * es * 2);                     // DZ (two buffers: wgrad of layer l overlaps the backward of layer l-1)
   add(M * maxc * es * 2);                     // G ping-pong / dense dgrad temp
   add(M * K * 4 * 2);                         // logits, dlogits
   add(M * 2);                                 // labels u8, pred
@@ -92,7 +92,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     GF = (TA*)arena_take(h, M * n.feat_stride * es);
   }
   TA* T = (TA*)arena_take(h, M * maxc * es);
-  TA* DZ = (TA*)arena_take(h, M * maxc * es);
+  TA* DZb[2] = {(TA*)arena_take(h, M * maxc * es), (TA*)arena_take(h, M * maxc * es)};
   TA* G0 = (TA*)arena_take(h, M * maxc * es);
   TA* G1 = (TA*)arena_take(h, M * maxc * es);
   float* logits = (float*)arena_take(h, M * K * 4);
@@ -209,32 +209,47 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     bn_partial_kernel<TA, TA, 1><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, n.act, part_bn, c.co, M, bn_rows, finb);
     LAUNCH_CHECK(h);
     if (h->sync_bn) do_allreduce(h, x->sums, 2 * c.co);
+    // The filter gradient of layer l is off the critical path (only the optimizer needs it): it runs on a side stream and
+    // overlaps the HBM-bound kernels of layer l-1's backward.  dZ is double-buffered; before a buffer is rewritten the
+    // main stream waits for the wgrad that read it two layers ago.
+    TA* DZ = DZb[l & 1];
+    if (l + 2 <= L - 1) CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->ev_wgrad[l & 1], 0));
     bn_bwd_apply_kernel<TA, TA><<<bne_grid(M, h->sm_count), BNE_THREADS, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, x->sums,
                                                                                    1.0 / bn_count, n.act, DZ, c.co, 0, c.co, M);
     LAUNCH_CHECK(h);
     debug_keep<TA>(h, "da:" + c.scope, (const TA*)dA.p, dA.cs, dA.co, c.co, M);
     debug_keep<TA>(h, "dz:" + c.scope, DZ, c.co, 0, c.co, M);
+    CUDA_CHECK(cudaEventRecord(x->ev_dz[l & 1], h->stream));
     // wgrad (bias gradient is identically zero behind a BN without beta: sum_m dZ = 0)
     ActBuf xin = input_of(l);
-    if (l == 0) {
-      // conv1: K = 25*C <= 125 rows only -> parallelism must come from many short pixel splits
-      const int conv1_splits = (int)std::min<int64_t>((int64_t)(max_w * max_splits) / ((int64_t)c.k * c.k * c.ci * c.co), 4 * h->sm_count);
-      launch_wgrad_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, DZ, c.co, 0, c.co, h->grads + c.w_off, part_w, conv1_splits, B, crop, c.k, c.rate, c.pad_b, 256);
-    } else if (ElemTag<TA>::v == ET_BF16 && wgrad_tc_supported(c.ci, c.co)) {
-      WgradTcArgs wa;
-      wa.x = xin.p; wa.in_cstride = xin.cs; wa.in_coff = xin.co; wa.ci = c.ci;
-      wa.dy = DZ; wa.dy_cstride = c.co; wa.dy_coff = 0; wa.co = c.co;
-      wa.B = B; wa.crop = crop; wa.k = c.k; wa.rate = c.rate; wa.pad_b = c.pad_b;
-      wa.dw = h->grads + c.w_off; wa.part = part_w; wa.part_capacity = max_w * max_splits;
-      cudaEvent_t ea = nullptr, eb = nullptr;
-      prof_begin(h, &ea, &eb);
-      launch_wgrad_tc(h, wa);
-      prof_end(h, eb);
-      x->conv_flops += 2.0 * (double)M * c.k * c.k * c.ci * c.co;
-      x->conv_launches += 1;
-    } else {
-      launch_wgrad_simt<TA, TA>(h, (const TA*)xin.p, xin.cs, xin.co, c.ci, DZ, c.co, 0, c.co, h->grads + c.w_off, part_w, max_splits, B, crop, c.k, c.rate, c.pad_b);
-    }
+    cudaStream_t main_stream = h->stream;
+    // (per-launch kernel timing with events needs the launches serialised: no overlap while profiling)
+    const bool overlap = !h->time_convs && !getenv("DRS_NO_OVERLAP");
+    if (overlap) h->stream = x->side_stream;
+    try {
+      if (overlap) CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->ev_dz[l & 1], 0));
+      if (l == 0) {
+        // conv1: K = 25*C <= 125 rows only -> parallelism must come from many short pixel splits
+        const int conv1_splits = (int)std::min<int64_t>((int64_t)(max_w * max_splits) / ((int64_t)c.k * c.k * c.ci * c.co), 4 * h->sm_count);
+        launch_wgrad_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, DZ, c.co, 0, c.co, h->grads + c.w_off, part_w, conv1_splits, B, crop, c.k, c.rate, c.pad_b, 256);
+      } else if (ElemTag<TA>::v == ET_BF16 && wgrad_tc_supported(c.ci, c.co)) {
+        WgradTcArgs wa;
+        wa.x = xin.p; wa.in_cstride = xin.cs; wa.in_coff = xin.co; wa.ci = c.ci;
+        wa.dy = DZ; wa.dy_cstride = c.co; wa.dy_coff = 0; wa.co = c.co;
+        wa.B = B; wa.crop = crop; wa.k = c.k; wa.rate = c.rate; wa.pad_b = c.pad_b;
+        wa.dw = h->grads + c.w_off; wa.part = part_w; wa.part_capacity = max_w * max_splits;
+        cudaEvent_t ea = nullptr, eb = nullptr;
+        prof_begin(h, &ea, &eb);
+        launch_wgrad_tc(h, wa);
+        prof_end(h, eb);
+        x->conv_flops += 2.0 * (double)M * c.k * c.k * c.ci * c.co;
+        x->conv_launches += 1;
+      } else {
+        launch_wgrad_simt<TA, TA>(h, (const TA*)xin.p, xin.cs, xin.co, c.ci, DZ, c.co, 0, c.co, h->grads + c.w_off, part_w, max_splits, B, crop, c.k, c.rate, c.pad_b);
+      }
+      CUDA_CHECK(cudaEventRecord(x->ev_wgrad[l & 1], h->stream));
+    } catch (...) { h->stream = main_stream; throw; }
+    h->stream = main_stream;
     // dgrad: dilated conv of dZ with flipped taps, padding swapped
     if (l > 0) {
       ActBuf dzb{DZ, c.co, 0};
@@ -251,6 +266,11 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
       }
     }
   }
+
+  // join: every filter gradient is complete before the exchange / the optimizer (the side stream is in order, so the
+  // two most recent events cover all layers)
+  CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->ev_wgrad[0], 0));
+  if (L > 1) CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->ev_wgrad[1], 0));
 
   // ---------------------------------------------------------------- exchange + update
   if (h->world > 1) {

@@ -83,3 +83,30 @@ def test_coffee_cli_train(tmp_path):
                                             25, 15, "dilated_icpr_rate6_densely", "uniform", "15,21", "acc"], tmp_path)
     assert "Optimization Finished!" in log and "-- Test: Overall Accuracy=" in log
     assert (out / "errorAcc_step_10.npy").exists()
+
+
+def test_isprs_cli_two_ranks_when_two_gpus(tmp_path):
+    """Data-parallel training + stripe-sharded validate_test under torchrun (skipped on a single-GPU box)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rs = np.random.RandomState(3)
+    data = tmp_path / "vaihingen"
+    out = tmp_path / "out"
+    data.mkdir()
+    out.mkdir()
+    for name in ("1", "3", "5"):
+        img, lab = _scene(rs, 150, 175, 4, 6, np.float64)
+        np.save(data / (name + "_image.npy"), img)
+        np.save(data / (name + "_labels.npy"), lab)
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    base = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+            "--master-port", "29533", os.path.join(ROOT, "isprs_dilated_random.py"), str(data) + "/", str(out) + "/"]
+    tail = ["1,3", "5", "0.01", "0.005", "8", "10", "25", "25", "dilated_icpr_rate6_densely", "uniform", "13,17", "loss"]
+    r = subprocess.run(base + [""] + tail + ["training"], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "Optimization Finished!" in r.stdout and (out / "model-10.npz").exists()
+    r = subprocess.run(base + [str(out) + "/model-10"] + tail + ["validate_test"], cwd=tmp_path, env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "Test ALL MAPS: Overall Accuracy=" in r.stdout
