@@ -189,6 +189,7 @@ def run_train_ours(args, rank, world, local):
     if world > 1:
         ddist.attach_allreduce(s, sync_bn=False)
     B = cfg["batch"]
+    s.reserve(B, cfg["values"][-1], training=True)      # the patch-size interval is known up front (probValues)
     th = TrainHost(cfg, [img.shape[:2]], B * world)
     cmax = max(cfg["values"][-1], 49)
     x = torch.empty(B * cmax * cmax * cfg["C"], dtype=torch.float32, device=dev)
@@ -269,13 +270,18 @@ def run_train_ours(args, rank, world, local):
     t0 = time.perf_counter()
     e0.record()
     bi = bo = 0
+    dbg = []
     for c in crops:
+        t1 = time.perf_counter()
         s.train_step(host_batches[c][0], host_batches[c][1], c, want_cm=True)
+        dbg.append(round((time.perf_counter() - t1) * 1e3, 1))
         bi += B * c * c * (cfg["C"] + 1) * 4
         bo += B * c * c * 8 + 4 + (cfg["K"] ** 2 + 1) * 4
     e1.record()
     barrier()
     ms2 = e0.elapsed_time(e1)
+    if os.environ.get("BENCH_DEBUG") and rank == 0:
+        print("e2e per-step ms:", dbg, file=sys.stderr)
     if world > 1:
         t = torch.tensor([ms2], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -52,7 +52,7 @@ def main():
                                                                        referenced_stride_crop, NUM_CLASSES)
     mean_full, std_full = host.coffee_create_mean_and_std(training_data, referenced_crop_size, referenced_stride_crop)
     be = cli.make_backend(net_type, 3, NUM_CLASSES, weight_decay, lr_initial, 0.1, training_data + test_data,
-                          training_mask_data + test_mask_data, mean_full, std_full, False, True)
+                          training_mask_data + test_mask_data, mean_full, std_full, False, True, train_fp16_patches=True)
     loops.coffee_train(be, training_data, test_mask_data, class_distribution, output_path, current_model, batch_size, niter,
                        distribution_type, update_type, patch_acc_loss, patch_occur, patch_chosen_values, probs, values,
                        NUM_CLASSES)

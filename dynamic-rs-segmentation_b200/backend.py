@@ -13,8 +13,9 @@ import numpy as np
 
 
 class GpuBackend:
-    def __init__(self, session, scenes, label_maps, mean_full, std_full, device=0, rank=0, world=1):
+    def __init__(self, session, scenes, label_maps, mean_full, std_full, device=0, rank=0, world=1, train_fp16_patches=False):
         import torch
+        self.train_fp16_patches = train_fp16_patches      # coffee:293
         self.rank, self.world = rank, world
         self.torch = torch
         self.s = session
@@ -68,7 +69,11 @@ class GpuBackend:
 
     def train_on_plan(self, plan, loss_mask=None):
         t = self.torch
+        if self.train_fp16_patches:
+            self.s.set_gather_fp16(True)
         x, y, pred, B, crop = self._gather(plan, shard=True)
+        if self.train_fp16_patches:
+            self.s.set_gather_fp16(False)
         plan = self._plan
         n = B * crop * crop
         mask_dev = None

@@ -45,7 +45,7 @@ def load_npy_scenes(path, instances, prefix=""):
 
 
 def make_backend(net_type, channels, num_classes, weight_decay, lr_initial, decay_rate, scenes, label_maps, mean_full, std_full,
-                 isprs_scopes, training, seed=None):
+                 isprs_scopes, training, seed=None, train_fp16_patches=False):
     """Session (libdrs.so) + GpuBackend with every scene resident in HBM.  Training runs the bf16 tensor-core path, whole-
     scene inference the fp16 one (10-bit mantissa, the TF32 class); DRS_PRECISION=fp32 selects the exact-order mode."""
     import drs_b200
@@ -56,7 +56,8 @@ def make_backend(net_type, channels, num_classes, weight_decay, lr_initial, deca
     s = drs_b200.Session(net_type, channels, num_classes, weight_decay=weight_decay, lr_initial=lr_initial, decay_rate=decay_rate,
                          precision=prec, device=local, isprs_scopes=isprs_scopes,
                          seed=int(os.environ.get("DRS_SEED", "0")) if seed is None else seed)
-    be = GpuBackend(s, scenes, label_maps, mean_full, std_full, device=local, rank=rank, world=world)
+    be = GpuBackend(s, scenes, label_maps, mean_full, std_full, device=local, rank=rank, world=world,
+                    train_fp16_patches=train_fp16_patches)
     if world > 1:
         ddist.attach_allreduce(s, sync_bn=bool(int(os.environ.get("DRS_SYNC_BN", "0"))))
     return be

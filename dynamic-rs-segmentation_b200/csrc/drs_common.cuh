@@ -135,6 +135,7 @@ struct drs_handle_s {
   // scenes
   std::map<int, Scene> scenes;
   double norm_mean[3] = {0, 0, 0}, norm_std[3] = {1, 1, 1};
+  int gather_fp16 = 0;       // coffee training patches are float16 before normalisation (coffee:293)
 
   // data parallel
   drs_allreduce_fn allreduce = nullptr;

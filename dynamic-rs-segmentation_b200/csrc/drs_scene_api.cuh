@@ -41,6 +41,13 @@ extern "C" int drs_scene_free(drs_handle_t h, int32_t scene_id) {
   API_END
 }
 
+extern "C" int drs_set_gather_fp16(drs_handle_t h, int32_t on) {
+  API_BEGIN
+  DRS_CHECK(h, "null handle");
+  h->gather_fp16 = on ? 1 : 0;
+  API_END
+}
+
 extern "C" int drs_set_normalization(drs_handle_t h, const double* mean3, const double* std3) {
   API_BEGIN
   DRS_CHECK(h && mean3 && std3, "null argument");
@@ -52,6 +59,7 @@ extern "C" int drs_set_normalization(drs_handle_t h, const double* mean3, const 
 static void launch_gather(Handle* h, GatherParams gp, const GatherInline* il = nullptr) {
   for (int i = 0; i < 3; ++i) { gp.mean[i] = h->norm_mean[i]; gp.stdv[i] = h->norm_std[i]; }
   gp.C = h->net.channels;
+  gp.fp16_patches = h->gather_fp16;
   const int64_t n = (int64_t)gp.B * gp.crop * gp.crop * gp.C;
   if (il) {
     gather_kernel<true><<<nblk(n, 256), 256, 0, h->stream>>>(X(h)->table, gp, *il);

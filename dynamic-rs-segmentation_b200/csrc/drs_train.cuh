@@ -401,6 +401,22 @@ extern "C" int drs_train_step_dev(drs_handle_t h, const float* x_dev, const floa
   API_END
 }
 
+extern "C" int drs_reserve_workspace(drs_handle_t h, int32_t B, int32_t crop_max, int32_t training) {
+  API_BEGIN
+  DRS_CHECK(h, "null handle");
+  DRS_CHECK(B >= 1 && crop_max >= 3 && crop_max <= 256, "reserve_workspace: bad B=%d crop=%d", B, crop_max);
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  const size_t es = h->cfg.precision == DRS_PREC_FP32 ? 4 : 2;
+  const int64_t M = (int64_t)B * crop_max * crop_max;
+  const int C = h->net.channels, K = h->net.classes;
+  ensure_arena(h, training ? std::max(train_workspace_bytes(h, B, crop_max, es), forward_eval_workspace(h, B, crop_max))
+                           : forward_eval_workspace(h, B, crop_max));
+  // staging of the *_host entry points (x, y, two masks, int64 + uint8 predictions, confusion counts, logits)
+  ensure_dstage(h, round_up((size_t)M * C * 4, 256) + round_up((size_t)M * 4, 256) + 2 * round_up((size_t)M, 256) +
+                       round_up((size_t)M * 9, 256) + round_up((size_t)M * K * 4, 256) + 8192);
+  API_END
+}
+
 extern "C" int drs_train_prepare(drs_handle_t h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
                                  const uint8_t* acc_mask_dev, int32_t B, int32_t crop, uint8_t* pred_dev, uint32_t* cm_dev) {
   API_BEGIN

@@ -35,6 +35,7 @@ struct GatherParams {
   float* x_out;               // [B,c,c,C]
   float* y_out;               // [B,c,c] or null
   int B, crop, C;
+  int fp16_patches;           // coffee training: patches are cast to float16 BEFORE normalisation (coffee:293)
   double mean[3], stdv[3];
 };
 
@@ -69,6 +70,15 @@ __global__ void gather_kernel(const __grid_constant__ SceneTable tab, const Gath
       v = v / p.stdv[ch];
     }
     outv = (float)v;                                                       // feed_dict cast to float32
+  } else if (p.fp16_patches) {
+    // NumPy float16 arithmetic of the reference era: operands widened to float32, one operation, result rounded to half;
+    // the float64 mean/std scalars are first cast to the array's dtype (half)
+    __half hv = __float2half_rn(reinterpret_cast<const float*>(sc.data)[sidx * sc.C + ch]);
+    if (ch < 3) {
+      hv = __float2half_rn(__half2float(hv) - __half2float(__double2half(p.mean[ch])));
+      hv = __float2half_rn(__half2float(hv) / __half2float(__double2half(p.stdv[ch])));
+    }
+    outv = __half2float(hv);
   } else {
     float v = reinterpret_cast<const float*>(sc.data)[sidx * sc.C + ch];
     if (ch < 3) {                                                          // float32 scene: float32 arithmetic

@@ -54,11 +54,13 @@ _SIGNATURES = {
     "drs_forward_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "drs_train_step_host": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P, _P]),
     "drs_train_step_dev": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P, _P]),
+    "drs_reserve_workspace": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "drs_train_prepare": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     "drs_set_ignore_label": (C.c_int, [_P, C.c_int32]),
     "drs_set_allreduce": (C.c_int, [_P, ALLREDUCE_FN, _P, C.c_int32, C.c_int32]),
     "drs_scene_upload": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "drs_scene_free": (C.c_int, [_P, C.c_int32]),
+    "drs_set_gather_fp16": (C.c_int, [_P, C.c_int32]),
     "drs_set_normalization": (C.c_int, [_P, _P, _P]),
     "drs_gather_dev": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "drs_grid_positions": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64,

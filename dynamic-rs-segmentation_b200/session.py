@@ -176,6 +176,10 @@ class Session:
         """contest: label 7 = unlabelled pixels, excluded from loss / gradient / confusion (contest:236-239, 886-897)."""
         L.check(self._lib.drs_set_ignore_label(self._h, -1 if label is None else int(label)))
 
+    def reserve(self, B, crop_max, training=True):
+        """Allocate the workspace for the largest (batch, patch size) of the run up front."""
+        L.check(self._lib.drs_reserve_workspace(self._h, int(B), int(crop_max), int(bool(training))))
+
     def prepare_training(self, x_dev, y_dev, B, crops, mask_dev=None, pred_dev=None, cm_dev=None, acc_mask_dev=None):
         """Capture the training-step graphs for the given patch sizes up front (nothing executes, no variable changes)."""
         for crop in crops:
@@ -222,6 +226,10 @@ class Session:
         m = np.ascontiguousarray(np.asarray(mean_full, dtype=np.float64)[:3])
         s = np.ascontiguousarray(np.asarray(std_full, dtype=np.float64)[:3])
         L.check(self._lib.drs_set_normalization(self._h, L.ptr(m), L.ptr(s)))
+
+    def set_gather_fp16(self, on):
+        """coffee: training patches are float16 before normalisation (coffee:293)."""
+        L.check(self._lib.drs_set_gather_fp16(self._h, int(bool(on))))
 
     def gather_dev(self, inst, flips, crop, x_out_dev, y_out_dev=None, noise=None, noise_on=None, over_x=None,
                    over_y=None, over_on=None):

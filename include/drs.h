@@ -111,6 +111,10 @@ int drs_train_step_dev(drs_handle_t h, const float* x_dev, const float* y_dev, c
                        const uint8_t* acc_mask_dev, int32_t B, int32_t crop, float* loss_out_host, uint8_t* pred_dev,
                        uint32_t* cm_dev);
 
+/* Size the workspace (and the host-path staging buffers) once for the largest batch / patch size of the run, so that no
+ * re-allocation happens when a larger patch size is drawn later (the patch-size interval is known up front: probValues). */
+int drs_reserve_workspace(drs_handle_t h, int32_t B, int32_t crop_max, int32_t training);
+
 /* Optional warm-up for the dynamic patch sizes: captures the CUDA graph of drs_train_step_dev for this (B, crop, buffers)
  * without executing it, so that the first real step of every patch size replays instead of capturing (the analogue of
  * TF building its graph before the loop, isprs:1652-1693).  Nothing is computed and no variable changes. */
@@ -137,6 +141,10 @@ int drs_scene_upload(drs_handle_t h, int32_t scene_id, const void* scene_host, i
 int drs_scene_free(drs_handle_t h, int32_t scene_id);
 /* normalize_images (isprs:74-81): (x - mean)/std on channels 0..2 only, in the scene's dtype. */
 int drs_set_normalization(drs_handle_t h, const double* mean3, const double* std3);
+
+/* coffee only: training patches are cast to float16 BEFORE normalisation (coffee:293; test patches stay float32, coffee:346);
+ * when on, the gather of float32 scenes reproduces NumPy's float16 arithmetic (half operands, float32 operation, half result). */
+int drs_set_gather_fp16(drs_handle_t h, int32_t on);
 
 /* dynamically_create_patches + normalize_images (isprs:245-334, 74-81; contest:192-254; coffee:241-293)
  *   inst   [B,3] int32 (scene_id, row, col) AFTER the caller's shift-back (host keeps RNG + border rule)

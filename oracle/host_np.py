@@ -302,7 +302,7 @@ def select_best_patch_size(distribution_type, values, patch_acc_loss, patch_occu
 # (isprs:245-334 then 74-81 then the float32 feed; contest:192-254; coffee:241-293)
 # --------------------------------------------------------------------------------------
 def apply_plan(scenes, label_maps, inst, flips, crop, mean_full, std_full, noise=None, noise_on=None,
-               over_x=None, over_y=None, over_on=None, cast=True):
+               over_x=None, over_y=None, over_on=None, cast=True, fp16_patches=False):
     """Checker for the gather kernel.  ``inst`` rows are (map, row, col) AFTER shift-back.
 
     Order of operations is the reference's: crop (or host-rotated override, isprs:292-296) -> + noise
@@ -327,6 +327,15 @@ def apply_plan(scenes, label_maps, inst, flips, crop, mean_full, std_full, noise
         xs.append(p)
         ys.append(l)
     x = np.array(xs)
+    if fp16_patches:
+        # coffee:293 -- np.asarray(patches, dtype=np.float16), then normalize_images on the float16 array.  NumPy of the
+        # reference era runs the float16 loop: scalar cast to half, operands widened to float32, result rounded to half.
+        x = x.astype(np.float16)
+        for ch in range(3):
+            x[..., ch] = (x[..., ch].astype(np.float32) - np.float32(np.float16(mean_full[ch]))).astype(np.float16)
+        for ch in range(3):
+            x[..., ch] = (x[..., ch].astype(np.float32) / np.float32(np.float16(std_full[ch]))).astype(np.float16)
+        return x.astype(np.float32), np.array(ys).astype(np.float32)
     if x.dtype == np.float32:
         mean_full = np.asarray(mean_full, dtype=np.float32)
         std_full = np.asarray(std_full, dtype=np.float32)

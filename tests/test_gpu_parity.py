@@ -170,6 +170,25 @@ def test_gather_kernel_bit_exact(drs, golden):
     with pytest.raises(lib.DrsError, match="out of the scene"):
         s.gather_dev(np.array([[0, 45, 0]]), None, 11, x, y)
     s.close()
+    # coffee training patches: float16 before normalisation (coffee:293), the patches the reference itself produced
+    imgs, labs = golden["coffee_scenes"], golden["coffee_labels"]
+    cd = [(int(m), (int(a), int(b))) for m, a, b in golden["coffee_distr"]]
+    plan = host.plan_index_flip_batch(cd, golden["coffee_shuf"], 9, [im.shape[:2] for im in imgs], with_map=True)
+    s = drs.Session("dilated_grsl", 3, 2, precision="fp32")
+    for i in range(len(imgs)):
+        s.upload_scene(i, imgs[i], labs[i])
+    s.set_gather_fp16(True)
+    n = len(plan.inst) * 9 * 9
+    x = torch.empty(n * 3, dtype=torch.float32, device="cuda")
+    y = torch.empty(n, dtype=torch.float32, device="cuda")
+    s.set_normalization(np.zeros(3), np.ones(3))
+    s.gather_dev(plan.inst, plan.flips, 9, x, y)
+    assert np.array_equal(x.cpu().numpy().reshape(golden["coffee_gather_p"].shape).astype(np.float16), golden["coffee_gather_p"])
+    s.set_normalization(mean[:3], std[:3])
+    s.gather_dev(plan.inst, plan.flips, 9, x, y)
+    xr, _ = host_np.apply_plan(imgs, labs, plan.inst, plan.flips, 9, mean[:3], std[:3], fp16_patches=True)
+    assert np.array_equal(x.cpu().numpy().reshape(xr.shape), xr)
+    s.close()
 
 
 ACC_CASES = (("isprs", 120, 150, 25, 16, 6), ("isprs", 97, 131, 33, 7, 6), ("contest", 130, 100, 25, 16, 7),
