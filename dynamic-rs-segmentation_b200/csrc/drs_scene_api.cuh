@@ -2,29 +2,42 @@
 // and the debug / profiling hooks.  Included by drs_api.cu.
 #pragma once
 
-extern "C" int drs_scene_upload(drs_handle_t h, int32_t scene_id, const void* scene_host, int32_t H, int32_t W, int32_t C,
-                                int32_t dtype, const uint8_t* labels_host) {
-  API_BEGIN
-  DRS_CHECK(h && scene_host, "null argument");
+static void scene_upload_rows(Handle* h, int32_t scene_id, const void* rows_host, int32_t H, int32_t W, int32_t C, int32_t dtype,
+                              const uint8_t* labels_rows_host, int32_t row0, int32_t rows) {
+  DRS_CHECK(h && rows_host, "null argument");
   CUDA_CHECK(cudaSetDevice(h->cfg.device));
   DRS_CHECK(scene_id >= 0 && scene_id < MAX_SCENES, "scene_id %d out of range [0,%d)", scene_id, MAX_SCENES);
   DRS_CHECK(dtype == DRS_SCENE_F64 || dtype == DRS_SCENE_F32, "bad scene dtype %d", dtype);
   DRS_CHECK(C == h->net.channels, "scene has %d channels, net expects %d", C, h->net.channels);
+  DRS_CHECK(row0 >= 0 && rows >= 1 && row0 + rows <= H, "scene rows [%d,%d) outside [0,%d)", row0, row0 + rows, H);
   Scene& s = h->scenes[scene_id];
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   if (s.data) CUDA_CHECK(cudaFree(s.data));
   if (s.labels) CUDA_CHECK(cudaFree(s.labels));
   s = Scene();
-  const size_t bytes = (size_t)H * W * C * (dtype == DRS_SCENE_F64 ? 8 : 4);
+  const size_t bytes = (size_t)rows * W * C * (dtype == DRS_SCENE_F64 ? 8 : 4);
   CUDA_CHECK(cudaMalloc(&s.data, bytes));
-  CUDA_CHECK(cudaMemcpyAsync(s.data, scene_host, bytes, cudaMemcpyHostToDevice, h->stream));
-  if (labels_host) {
-    CUDA_CHECK(cudaMalloc(&s.labels, (size_t)H * W));
-    CUDA_CHECK(cudaMemcpyAsync(s.labels, labels_host, (size_t)H * W, cudaMemcpyHostToDevice, h->stream));
+  CUDA_CHECK(cudaMemcpyAsync(s.data, rows_host, bytes, cudaMemcpyHostToDevice, h->stream));
+  if (labels_rows_host) {
+    CUDA_CHECK(cudaMalloc(&s.labels, (size_t)rows * W));
+    CUDA_CHECK(cudaMemcpyAsync(s.labels, labels_rows_host, (size_t)rows * W, cudaMemcpyHostToDevice, h->stream));
   }
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
-  s.H = H; s.W = W; s.C = C; s.dtype = dtype;
-  X(h)->table.s[scene_id] = SceneDesc{s.data, s.labels, H, W, C, dtype};
+  s.H = H; s.W = W; s.C = C; s.dtype = dtype; s.row0 = row0; s.rows = rows;
+  X(h)->table.s[scene_id] = SceneDesc{s.data, s.labels, H, W, C, dtype, row0, rows};
+}
+
+extern "C" int drs_scene_upload(drs_handle_t h, int32_t scene_id, const void* scene_host, int32_t H, int32_t W, int32_t C,
+                                int32_t dtype, const uint8_t* labels_host) {
+  API_BEGIN
+  scene_upload_rows(h, scene_id, scene_host, H, W, C, dtype, labels_host, 0, H);
+  API_END
+}
+
+extern "C" int drs_scene_upload_rows(drs_handle_t h, int32_t scene_id, const void* rows_host, int32_t H, int32_t W, int32_t C,
+                                     int32_t dtype, const uint8_t* labels_rows_host, int32_t row0, int32_t rows) {
+  API_BEGIN
+  scene_upload_rows(h, scene_id, rows_host, H, W, C, dtype, labels_rows_host, row0, rows);
   API_END
 }
 
@@ -86,6 +99,9 @@ extern "C" int drs_gather_dev(drs_handle_t h, const int32_t* inst_host, const ui
     DRS_CHECK(it != h->scenes.end(), "gather: scene %d not uploaded", sid);
     DRS_CHECK(r >= 0 && c >= 0 && r + crop <= it->second.H && c + crop <= it->second.W,
               "Error: Current PATCH size is out of the scene (scene %d, row %d, col %d, crop %d)", sid, r, c, crop);
+    DRS_CHECK(r >= it->second.row0 && r + crop <= it->second.row0 + it->second.rows,
+              "gather: rows [%d,%d) of scene %d are not resident (uploaded rows [%d,%d))", r, r + crop, sid, it->second.row0,
+              it->second.row0 + it->second.rows);
   }
   const bool plain = !(noise_host && noise_on_host) && !(over_x_host && over_on_host);
   if (plain && B <= GATHER_INLINE_MAX) {
@@ -323,6 +339,10 @@ extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, i
   for (size_t p = 0; p < all.size() / 2; ++p)
     if (all[2 * p] < row_end && all[2 * p] + crop > row_begin) { pos.push_back(all[2 * p]); pos.push_back(all[2 * p + 1]); }
   const int P = (int)(pos.size() / 2);
+  for (int p = 0; p < P; ++p)
+    DRS_CHECK(pos[2 * p] >= sc.row0 && pos[2 * p] + crop <= sc.row0 + sc.rows,
+              "scene_infer: stripe [%d,%d) needs scene rows [%d,%d) but only [%d,%d) are resident", row_begin, row_end, pos[2 * p],
+              pos[2 * p] + crop, sc.row0, sc.row0 + sc.rows);
   CellTables ct;
   build_cells(pos, H, W, crop, ct);
   const int rows = row_end - row_begin;

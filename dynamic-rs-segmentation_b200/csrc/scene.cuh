@@ -9,9 +9,10 @@
 
 constexpr int MAX_SCENES = 64;
 struct SceneDesc {
-  const void* data;
+  const void* data;       // rows [row0, row0 + rows) of the scene
   const uint8_t* labels;
   int H, W, C, dtype;
+  int row0, rows;
 };
 struct SceneTable {
   SceneDesc s[MAX_SCENES];
@@ -60,7 +61,7 @@ __global__ void gather_kernel(const __grid_constant__ SceneTable tab, const Gath
   const SceneDesc& sc = tab.s[sid];
   const bool over = p.over_on && p.over_on[b];
   const int64_t pidx = (((int64_t)b * p.crop + si) * p.crop + sj);
-  const int64_t sidx = ((int64_t)(row0 + si) * sc.W + (col0 + sj));
+  const int64_t sidx = ((int64_t)(row0 + si - sc.row0) * sc.W + (col0 + sj));
   float outv;
   if (sc.dtype == DRS_SCENE_F64 || over) {
     double v = over ? p.over_x[pidx * p.C + ch] : reinterpret_cast<const double*>(sc.data)[sidx * sc.C + ch];

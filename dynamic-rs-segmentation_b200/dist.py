@@ -28,6 +28,15 @@ def stripe_bounds(H, world, rank=None):
     return cuts[rank], cuts[rank + 1]
 
 
+def stripe_rows_needed(H, crop, row_begin, row_end):
+    """Scene rows a rank must hold to evaluate every patch that intersects its output stripe [row_begin, row_end):
+    patch origins lie on the lattice {i*stride} U {H-crop} (isprs:1243, 366-375)."""
+    stride = crop // 2
+    origins = sorted(set(list(range(0, max(H - crop, 0) + 1, stride)) + [H - crop]))
+    hit = [o for o in origins if o < row_end and o + crop > row_begin]
+    return (min(hit), max(hit) + crop) if hit else (row_begin, row_end)
+
+
 def attach_allreduce(session, group=None, sync_bn=False):
     """Route the library's exchange step through torch.distributed (NCCL on GPUs, gloo in CPU tests)."""
     import torch

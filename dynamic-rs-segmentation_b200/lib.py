@@ -59,6 +59,7 @@ _SIGNATURES = {
     "drs_set_ignore_label": (C.c_int, [_P, C.c_int32]),
     "drs_set_allreduce": (C.c_int, [_P, ALLREDUCE_FN, _P, C.c_int32, C.c_int32]),
     "drs_scene_upload": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "drs_scene_upload_rows": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32]),
     "drs_scene_free": (C.c_int, [_P, C.c_int32]),
     "drs_set_gather_fp16": (C.c_int, [_P, C.c_int32]),
     "drs_set_normalization": (C.c_int, [_P, _P, _P]),

@@ -207,7 +207,19 @@ class Session:
         L.check(self._lib.drs_set_allreduce(self._h, self._cb, None, int(world_size), int(bool(sync_bn))))
 
     # ---------------------------------------------------------------- scene path
-    def upload_scene(self, scene_id, scene, labels=None):
+    def upload_scene(self, scene_id, scene, labels=None, row_begin=None, row_end=None):
+        """Keep a scene resident in HBM.  With row_begin/row_end only those rows are uploaded (a rank's stripe + halo,
+        see dist.stripe_rows_needed); coordinates stay those of the whole scene."""
+        if row_begin is not None:
+            H, W, Cc = scene.shape
+            sub = np.ascontiguousarray(scene[row_begin:row_end])
+            dt = L.SCENE_F64 if sub.dtype == np.float64 else L.SCENE_F32
+            if sub.dtype not in (np.float64, np.float32):
+                raise ValueError("scene dtype must be float64 or float32, got %s" % sub.dtype)
+            lab = None if labels is None else np.ascontiguousarray(np.asarray(labels, dtype=np.uint8).reshape(H, W)[row_begin:row_end])
+            L.check(self._lib.drs_scene_upload_rows(self._h, scene_id, L.ptr(sub), H, W, Cc, dt, L.ptr(lab), row_begin,
+                                                    row_end - row_begin))
+            return
         scene = np.ascontiguousarray(scene)
         if scene.dtype == np.float64:
             dt = L.SCENE_F64

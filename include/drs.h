@@ -138,6 +138,10 @@ int drs_set_allreduce(drs_handle_t h, drs_allreduce_fn fn, void* user, int32_t w
  * scene [H,W,C] float64 (isprs img_as_float) or float32 (contest/coffee); labels [H,W] uint8 or NULL. */
 int drs_scene_upload(drs_handle_t h, int32_t scene_id, const void* scene_host, int32_t H, int32_t W, int32_t C,
                      int32_t dtype, const uint8_t* labels_host);
+/* Stripe-sharded inference: keep only rows [row0, row0+rows) of the H-row scene resident (the rank's output stripe plus the
+ * patch rows that straddle its borders).  rows_host points at the first resident row. */
+int drs_scene_upload_rows(drs_handle_t h, int32_t scene_id, const void* rows_host, int32_t H, int32_t W, int32_t C,
+                          int32_t dtype, const uint8_t* labels_rows_host, int32_t row0, int32_t rows);
 int drs_scene_free(drs_handle_t h, int32_t scene_id);
 /* normalize_images (isprs:74-81): (x - mean)/std on channels 0..2 only, in the scene's dtype. */
 int drs_set_normalization(drs_handle_t h, const double* mean3, const double* std3);

@@ -492,3 +492,28 @@ def test_cuda_graph_replay_matches_eager(drs, monkeypatch):
         s.close()
     assert res[0][0] == res[1][0] and res[0][2] == res[1][2] == 5
     assert np.array_equal(res[0][1], res[1][1])
+
+
+def test_stripe_with_partial_scene_upload(drs):
+    """A rank that holds only the scene rows its stripe needs (dist.stripe_rows_needed) produces the same stripe."""
+    from drs_b200 import dist as ddist, lib
+    rs = np.random.RandomState(13)
+    H, W, C, K, crop, batch = 97, 80, 5, 6, 25, 16
+    scene = rs.randint(0, 256, size=(H, W, C)).astype(np.uint8) / 255.0
+    s = drs.Session("dilated_grsl_rate8", C, K, precision="f16", seed=3)
+    s.set_normalization(np.full(3, 0.5), np.full(3, 0.3))
+    s.upload_scene(0, scene, None)
+    full = s.scene_infer(0, crop, batch, H, W)
+    for world in (2, 3):
+        parts = []
+        for r in range(world):
+            a, b = ddist.stripe_bounds(H, world, r)
+            lo, hi = ddist.stripe_rows_needed(H, crop, a, b)
+            assert lo <= a and hi >= b and (hi - lo) < H
+            s.upload_scene(0, scene, None, lo, hi)
+            parts.append(s.scene_infer(0, crop, batch, H, W, row_begin=a, row_end=b))
+        assert np.array_equal(np.concatenate(parts, 0), full), world
+    s.upload_scene(0, scene, None, 30, 70)
+    with pytest.raises(lib.DrsError, match="resident"):
+        s.scene_infer(0, crop, batch, H, W, row_begin=0, row_end=40)
+    s.close()
