@@ -289,7 +289,8 @@ extern "C" int drs_destroy(drs_handle_t h) {
 extern "C" int drs_set_stream(drs_handle_t h, void* s) {
   API_BEGIN
   DRS_CHECK(h, "null handle");
-  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  // (void*)-1 selects the handle's own non-blocking stream; any other value is a cudaStream_t, 0 = the legacy default stream
+  h->stream = (s == (void*)(intptr_t)-1) ? h->own_stream : (cudaStream_t)s;
   API_END
 }
 extern "C" int drs_synchronize(drs_handle_t h) {

@@ -44,13 +44,24 @@ def attach_allreduce(session, group=None, sync_bn=False):
     world = dist.get_world_size(group)
     cache = {}
 
+    streams = {}
+
     def allreduce(ptr, count, stream):
         key = (ptr, count)
         t = cache.get(key)
         if t is None:
             t = torch.as_tensor(_DevBuf(ptr, count), device="cuda")
             cache[key] = t
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        # NCCL orders itself after torch's CURRENT stream: make that the stream libdrs enqueues on (0 = legacy default)
+        if stream:
+            ext = streams.get(stream)
+            if ext is None:
+                ext = streams[stream] = torch.cuda.ExternalStream(stream)
+            with torch.cuda.stream(ext):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        else:
+            with torch.cuda.stream(torch.cuda.default_stream()):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
     session.set_allreduce(allreduce if world > 1 else None, world, sync_bn)
     return world

@@ -60,7 +60,9 @@ class Session:
         self.close()
 
     def set_stream(self, cuda_stream):
-        L.check(self._lib.drs_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+        """Enqueue on this cudaStream_t (0 = the legacy default stream torch uses by default); None = the handle's own stream."""
+        v = C.c_void_p(-1) if cuda_stream is None else C.c_void_p(int(cuda_stream))
+        L.check(self._lib.drs_set_stream(self._h, v))
 
     def synchronize(self):
         L.check(self._lib.drs_synchronize(self._h))

@@ -70,7 +70,8 @@ int drs_create(drs_handle_t* out, const drs_config* cfg);
 int drs_destroy(drs_handle_t h);
 const char* drs_last_error(void);
 int drs_version(void);
-/* cudaStream_t to enqueue on (NULL = the handle's own stream). */
+/* cudaStream_t to enqueue on: any stream handle incl. 0 (the legacy default stream, what torch uses unless told otherwise);
+ * (void*)-1 = back to the handle's own non-blocking stream, which is the initial state. */
 int drs_set_stream(drs_handle_t h, void* cuda_stream);
 int drs_synchronize(drs_handle_t h);
 

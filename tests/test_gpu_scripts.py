@@ -110,3 +110,16 @@ def test_isprs_cli_two_ranks_when_two_gpus(tmp_path):
                        text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "Test ALL MAPS: Overall Accuracy=" in r.stdout
+
+
+def test_data_parallel_sync_bn_equals_single_process_when_two_gpus():
+    """2-rank sharded training step with sync_bn == single-process step on the whole batch (fp32 exact-order mode)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    for net in ("dilated_grsl", "dilated_icpr_rate6_densely"):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                            "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "dp_parity.py"), net, "fp32"],
+                           env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "DP_PARITY ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

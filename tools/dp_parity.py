@@ -1,0 +1,54 @@
+"""Data-parallel parity (run under torchrun, 2+ ranks): with sync_bn the sharded step equals the single-process step on the
+whole batch.  Prints 'DP_PARITY ok' on rank 0."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import torch.distributed as dist
+import drs_b200
+from drs_b200 import dist as ddist, nets
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+net, C, K, GB, crop = sys.argv[1] if len(sys.argv) > 1 else "dilated_grsl", 4, 6, 8, 19
+prec = sys.argv[2] if len(sys.argv) > 2 else "fp32"
+rs = np.random.RandomState(5)
+x = rs.randn(GB, crop * crop * C).astype(np.float32)
+y = rs.randint(0, K, size=(GB, crop * crop)).astype(np.float32)
+variables = nets.initial_variables(net, C, K, seed=3)
+
+
+def run(world_size, rows, sync_bn):
+    s = drs_b200.Session(net, C, K, precision=prec, device=local, weight_decay=0.005, lr_initial=0.01)
+    s.set_stream(torch.cuda.current_stream().cuda_stream)
+    s.load_variables(variables)
+    if world_size > 1:
+        ddist.attach_allreduce(s, sync_bn=sync_bn)
+    xd = torch.from_numpy(x[rows]).cuda()
+    yd = torch.from_numpy(y[rows]).cuda()
+    B = xd.shape[0]
+    cm = torch.zeros(K * K + 1, dtype=torch.int32, device="cuda")
+    losses = []
+    for _ in range(2):
+        losses.append(float(s.train_step_dev(xd, yd, B, crop, cm_dev=cm)))
+    if os.environ.get("DP_DEBUG"):
+        print("rank", rank, "world", world_size, "losses", losses, "mm1", s.get_variable("conv1/moving_mean")[:4],
+              "mv1", s.get_variable("conv1/moving_variance")[:4], "mm2", s.get_variable("conv2/moving_mean")[:3], flush=True)
+    out = (losses, s.get_variable("conv_classifier/weights").copy(), s.get_variable("conv1/weights").copy(),
+           s.get_variable("conv3/moving_variance").copy(), cm.cpu().numpy().copy())
+    s.close()
+    return out
+
+per = GB // world
+dp = run(world, slice(rank * per, (rank + 1) * per), True)
+if rank == 0:
+    ref = run(1, slice(0, GB), False)
+    tol = 2e-5 if prec == "fp32" else 3e-2
+    assert all(abs(a - b) < tol * max(1, abs(b)) for a, b in zip(dp[0], ref[0])), (dp[0], ref[0])
+    for a, b, name in zip(dp[1:4], ref[1:4], ("classifier", "conv1", "moving_variance")):
+        err = float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+        assert err < (5e-4 if prec == "fp32" else 5e-2), (name, err)
+    assert np.array_equal(dp[4], ref[4]) or prec != "fp32", (dp[4], ref[4])
+    print("DP_PARITY ok", prec, net, "losses", dp[0], ref[0], flush=True)
+dist.barrier()
+dist.destroy_process_group()

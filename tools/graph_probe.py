@@ -7,9 +7,9 @@ B, C, K = 64, 4, 6
 for crop in (25, 37, 49):
     for mode in ("eager", "graph", "graph+prof"):
         if mode == "eager":
-            os.environ["DRS_NO_GRAPHS"] = "1"
+            os.environ.pop("DRS_GRAPHS", None)
         else:
-            os.environ.pop("DRS_NO_GRAPHS", None)
+            os.environ["DRS_GRAPHS"] = "1"
         s = drs_b200.Session("dilated_grsl", C, K, precision="bf16", seed=1)
         s.set_stream(torch.cuda.current_stream().cuda_stream)
         s.set_profiling(mode == "graph+prof")
