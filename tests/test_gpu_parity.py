@@ -517,3 +517,58 @@ def test_stripe_with_partial_scene_upload(drs):
     with pytest.raises(lib.DrsError, match="resident"):
         s.scene_infer(0, crop, batch, H, W, row_begin=0, row_end=40)
     s.close()
+
+
+def test_full_size_scene_properties(drs, monkeypatch):
+    """BASELINE configs[0] size (Vaihingen-shaped 2000x2500x4, Dilated6, crop 25, 34 528 patches): size-independent
+    properties -- the label map does not depend on the chunking of the patch stream nor on the stripe decomposition, and
+    the ordered accumulation equals NumPy's sequential loop bit for bit at full size."""
+    import torch
+    from drs_b200 import synth
+    from oracle import host_np
+    img, _ = synth.scene("vaihingen")
+    H, W = img.shape[:2]
+    mean, std = synth.normalisation(img)
+    s = drs.Session("dilated_icpr_original", 4, 6, precision="f16", seed=11)
+    s.set_normalization(mean, std)
+    s.upload_scene(0, img, None)
+    full = s.scene_infer(0, 25, 16, H, W)
+    assert full.shape == (H, W) and full.max() <= 5
+    monkeypatch.setenv("DRS_CHUNK_WAVES", "7")
+    assert np.array_equal(s.scene_infer(0, 25, 16, H, W), full)                    # chunking invariance
+    monkeypatch.delenv("DRS_CHUNK_WAVES")
+    cuts = (0, 667, 1333, H)
+    parts = [s.scene_infer(0, 25, 16, H, W, row_begin=a, row_end=b) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.array_equal(np.concatenate(parts, 0), full)                          # stripes need no exchange
+    s.close()
+    # ordered accumulation at full size against the NumPy loop (isprs:1276-1284)
+    pos = drs.grid_positions(H, W, 25, 16)
+    assert len(pos) == 166 * 208
+    g = torch.Generator(device="cuda").manual_seed(5)
+    logits = torch.randn(len(pos), 25, 25, 6, device="cuda", generator=g)
+    s = drs.Session("dilated_grsl", 4, 6, precision="fp32")
+    labels, mean_map = s.accumulate_argmax(logits, pos, 25, H, W, want_mean=True)
+    s.close()
+    ref_l, ref_m = host_np.accumulate_argmax(logits.cpu().numpy(), pos, H, W, 25, return_mean=True)
+    assert np.array_equal(labels, ref_l.astype(np.uint8)) and np.array_equal(mean_map, ref_m)
+
+
+def test_full_size_training_step_properties(drs):
+    """BASELINE configs[1] at its largest shape (Dilated6Pooling, batch 64, crop 49, M = 153 664): finite loss, confusion
+    counts sum to the number of pixels, run-to-run identical bits, moving statistics move."""
+    rs = np.random.RandomState(17)
+    B, crop, C, K = 64, 49, 4, 6
+    x = rs.randn(B, crop * crop * C).astype(np.float32)
+    y = rs.randint(0, K, size=(B, crop * crop)).astype(np.float32)
+    out = []
+    for _ in range(2):
+        s = drs.Session("dilated_grsl", C, K, precision="bf16", seed=4)
+        loss, pred, cm, nc = s.train_step(x, y, crop, want_cm=True)
+        out.append((float(loss), pred.copy(), cm.copy(), s.get_variable("conv6/weights").copy(),
+                    s.get_variable("conv6/moving_mean").copy()))
+        s.close()
+    assert np.isfinite(out[0][0]) and 1.0 < out[0][0] < 10.0
+    assert int(out[0][2].sum()) == B * crop * crop and nc == int(np.trace(out[0][2]))
+    assert np.array_equal(out[0][2], np.bincount((y.reshape(-1).astype(int) * K + out[0][1].reshape(-1)), minlength=K * K).reshape(K, K))
+    assert out[0][0] == out[1][0] and all(np.array_equal(a, b) for a, b in zip(out[0][1:], out[1][1:]))
+    assert np.abs(out[0][4]).max() > 0
