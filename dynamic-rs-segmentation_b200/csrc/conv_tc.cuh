@@ -42,6 +42,9 @@ struct ConvTcParams {
   const float* scale; // [co]
   const float* shift; // [co]
   uint32_t* diag;     // host-mapped diagnostics
+  // training forward: per-channel sum / sum of squares of the stored (rounded) outputs, reduced in the epilogue so that
+  // train-mode batch norm needs no extra pass over Z (stats.acc == nullptr: off)
+  BnFinish stats;
 };
 
 constexpr int CONV_TC_THREADS = 256;
@@ -96,6 +99,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  // [row group][2][co] running column sums; present (and counted in smem_needed) only in the training forward
+  float* s_stat = reinterpret_cast<float*>(tmem_holder + 4);
+  constexpr int STAT_GROUPS = CONV_TC_BM / EPI_C;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,6 +113,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     s_scale[i] = p.scale[i];
     s_shift[i] = p.shift[i];
   }
+  if (p.stats.acc)
+    for (int i = threadIdx.x; i < STAT_GROUPS * 2 * p.co; i += CONV_TC_THREADS) s_stat[i] = 0.0f;
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
@@ -234,6 +242,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::tma_store_2d(&tmC, stg + sbuf * STG_BYTES, p.out_coff + ch * EPI_C, tile * CONV_TC_BM);
           ptx::tma_store_commit();
         }
+        if (p.stats.acc) {
+          // column sums of the staged (already rounded) tile: thread = (channel, row group); rows past the end of the
+          // tensor (clipped by the TMA store) are skipped.  s_stat[group][.][channel] is owned by exactly one thread.
+          constexpr int GROUPS = CONV_TC_BM / EPI_C, ROWS = EPI_C;
+          const int c = epi_tid % EPI_C, grp = epi_tid / EPI_C;
+          const int rows_valid = min(CONV_TC_BM, p.M_total - tile * CONV_TC_BM);
+          const uint8_t* col = stg + sbuf * STG_BYTES + (c & 7) * 2;
+          const int c16 = c >> 3;
+          float a0 = 0.0f, a1 = 0.0f;
+          const int r_end = min(rows_valid, (grp + 1) * ROWS);
+          for (int r = grp * ROWS; r < r_end; ++r) {
+            const int swr = (EPI_C == 64) ? (r & 7) : ((r >> 1) & 3);
+            const float f = to_f32(*reinterpret_cast<const OutT*>(col + r * (EPI_C * 2) + ((c16 ^ swr) << 4)));
+            a0 += f;
+            a1 = fmaf(f, f, a1);
+          }
+          float* st = s_stat + (grp * 2) * p.co + ch * EPI_C + c;
+          st[0] += a0;
+          st[p.co] += a1;
+          (void)GROUPS;
+        }
         sbuf ^= 1;
       }
       // all TMEM reads of this accumulator stage are complete (wait::ld above)
@@ -243,6 +272,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (epi_tid == 0) ptx::tma_store_wait_all();
+    if (p.stats.acc) {
+      // CTA partial (row groups combined in fixed order) -> 64-bit fixed point -> integer atomicAdd (order-independent);
+      // the last CTA to arrive converts, finalizes mean / inv_std / moving averages and clears the accumulators.
+      constexpr int GROUPS = CONV_TC_BM / EPI_C;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = epi_tid; i < 2 * p.co; i += 128) {
+        const int which = i / p.co, c = i - which * p.co;
+        float a = 0.0f;
+#pragma unroll
+        for (int g = 0; g < GROUPS; ++g) a += s_stat[(g * 2 + which) * p.co + c];
+        const long long q = __double2ll_rn((double)a * p.stats.fx_scale);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.stats.acc) + i, static_cast<unsigned long long>(q));
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      uint32_t* s_flag = reinterpret_cast<uint32_t*>(s_stat);       // s_stat is dead now
+      if (epi_tid == 0) *s_flag = (atomicAdd(p.stats.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*s_flag) {
+        __threadfence();
+        const double inv_scale = 1.0 / p.stats.fx_scale;
+        const int C = p.co;
+        for (int i = epi_tid; i < C; i += 128) {
+          const double a = (double)__ldcg(p.stats.acc + i) * inv_scale;
+          const double b = (double)__ldcg(p.stats.acc + C + i) * inv_scale;
+          p.stats.acc[i] = 0;
+          p.stats.acc[C + i] = 0;
+          p.stats.sums[i] = (float)a;
+          p.stats.sums[C + i] = (float)b;
+          if (p.stats.mean) {
+            const double mu = (double)(float)a / p.stats.count;
+            double var = (double)(float)b / p.stats.count - mu * mu;
+            if (var < 0.0) var = 0.0;
+            p.stats.mean[i] = (float)mu;
+            p.stats.inv_std[i] = (float)(1.0 / sqrt(var + (double)p.stats.eps));
+            const double var_ema = p.stats.unbiased_ema ? var * (p.stats.count / fmax(p.stats.count - 1.0, 1.0)) : var;
+            p.stats.mov_mean[i] = p.stats.decay * p.stats.mov_mean[i] + (1.0f - p.stats.decay) * (float)mu;
+            p.stats.mov_var[i] = p.stats.decay * p.stats.mov_var[i] + (1.0f - p.stats.decay) * (float)var_ema;
+          }
+        }
+        if (epi_tid == 0) *p.stats.counter = 0u;
+      }
+    }
   }
 
   ptx::tcgen05_fence_before();
@@ -267,6 +339,7 @@ struct ConvTcArgs {
   const float* shift;
   int act;
   int etype;           // ET_F16 / ET_BF16 (operands and output)
+  const BnFinish* stats = nullptr;   // training forward: reduce the BN statistics of the output in the epilogue
 };
 
 static inline CUtensorMapDataType tm_dtype(int etype) {
@@ -347,9 +420,11 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   p.scale = a.scale;
   p.shift = a.shift;
   p.diag = h->diag_dev;
+  if (a.stats) p.stats = *a.stats; else memset(&p.stats, 0, sizeof(p.stats));
 
   const int stage_bytes = CONV_TC_BM * BLOCK_K * 2 + a.co * BLOCK_K * 2;
-  const int fixed = 2 * CONV_TC_BM * EPI_C * 2 + 2 * 256 * 4 + (2 * 8 + 4) * 8 + 16;
+  const int fixed = 2 * CONV_TC_BM * EPI_C * 2 + 2 * 256 * 4 + (2 * 8 + 4) * 8 + 16 +
+                    (a.stats ? (CONV_TC_BM / EPI_C) * 2 * a.co * 4 : 0);
   const int budget = 227 * 1024;
   int stages = (budget - fixed) / stage_bytes;
   if (stages > 8) stages = 8;

@@ -558,7 +558,8 @@ static void prof_end(Handle* h, cudaEvent_t b) {
 // generic conv over activation type TA.  w_simt: HWIO fp32 [k*k*ci][co]; w_tc: packed [co][k*k*ci].
 template <typename TA>
 static void run_conv(Handle* h, const ActBuf& in, int ci, const float* w_simt, const void* w_tc, const ActBuf& out, int co,
-                     int B, int crop, int k, int rate, int pad_b, const float* scale, const float* shift, int act) {
+                     int B, int crop, int k, int rate, int pad_b, const float* scale, const float* shift, int act,
+                     const BnFinish* stats = nullptr) {
   if (ElemTag<TA>::v == ET_F32) {
     launch_conv_simt<TA, TA>(h, (const TA*)in.p, in.cs, in.co, ci, w_simt, (TA*)out.p, out.cs, out.co, co, B, crop, k, rate,
                              pad_b, scale, shift, act);
@@ -572,6 +573,7 @@ static void run_conv(Handle* h, const ActBuf& in, int ci, const float* w_simt, c
     ++nsplit;
     DRS_CHECK(nsplit <= 8, "cannot tile N=%d", co);
   }
+  DRS_CHECK(!stats || nsplit == 1, "fused BN statistics need a single N tile (Co=%d)", co);
   const int nt = co / nsplit;
   for (int s = 0; s < nsplit; ++s) {
     ConvTcArgs a;
@@ -581,6 +583,7 @@ static void run_conv(Handle* h, const ActBuf& in, int ci, const float* w_simt, c
     a.B = B; a.crop = crop; a.k = k; a.rate = rate; a.pad_b = pad_b;
     a.scale = scale + s * nt; a.shift = shift + s * nt; a.act = act;
     a.etype = ElemTag<TA>::v;
+    a.stats = stats;
     launch_conv_tc(h, a);
   }
   prof_end(h, eb);

@@ -194,6 +194,22 @@ static inline void ensure_dstage(Handle* h, size_t bytes) {
   h->dstage_cap = want;
 }
 
+// Train-mode BN statistics: what the last block of a statistics-producing kernel (bn_partial_kernel, or the conv epilogue)
+// does with the grid-wide sums.
+struct BnFinish {
+  long long* acc;          // [2][C] fixed-point accumulators, zero before the launch; cleared by the kernel
+  double fx_scale;         // fixed-point scale (2^20 forward statistics, 2^40 backward sums)
+  unsigned int* counter;   // zero before the launch; reset by the kernel
+  float* sums;             // [2][C] out
+  float* mean;             // non-null: also finalize (batch mean / inv_std, moving-average update)
+  float* inv_std;
+  float* mov_mean;
+  float* mov_var;
+  double count;
+  float eps, decay;
+  int unbiased_ema;
+};
+
 #define LAUNCH_CHECK(h)                 \
   do {                                  \
     (h)->launches++;                    \

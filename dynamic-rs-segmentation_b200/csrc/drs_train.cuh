@@ -121,20 +121,24 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     ConvLayer& c = n.convs[l];
     ActBuf zb{Z[l], c.co, 0};
     // conv + bias (raw): scale = 1, shift = bias, no activation   (isprs:710-713)
+    // batch statistics (biased variance), moving-average update          (isprs:658-660): reduced inside the tensor-core
+    // kernel's epilogue; conv1 and the fp32 mode (CUDA-core convolutions) use the separate statistics kernel
+    float* mean = x->mean + c.mm_off;
+    float* istd = x->inv_std + c.mm_off;
+    BnFinish fin{x->bn_acc, 1048576.0, x->bn_counter, x->sums, nullptr, nullptr, nullptr, nullptr, bn_count, h->cfg.bn_eps, h->cfg.bn_decay, h->cfg.bn_unbiased_ema};
+    if (!h->sync_bn) { fin.mean = mean; fin.inv_std = istd; fin.mov_mean = h->bnstat + c.mm_off; fin.mov_var = h->bnstat + c.mv_off; }
+    const bool fused_stats = l > 0 && ElemTag<TA>::v != ET_F32 && !getenv("DRS_NO_FUSED_STATS");
     if (l == 0) {
       launch_conv_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, h->params + c.w_off, Z[l], c.co, 0, c.co, B, crop, c.k,
                                   c.rate, c.pad_b, x->ones, h->params + c.b_off, ACT_NONE);
     } else {
       run_conv<TA>(h, input_of(l), c.ci, h->params + c.w_off, c.w_fprop, zb, c.co, B, crop, c.k, c.rate, c.pad_b, x->ones,
-                   h->params + c.b_off, ACT_NONE);
+                   h->params + c.b_off, ACT_NONE, fused_stats ? &fin : nullptr);
     }
-    // batch statistics (biased variance), moving-average update          (isprs:658-660)
-    float* mean = x->mean + c.mm_off;
-    float* istd = x->inv_std + c.mm_off;
-    BnFinish fin{x->bn_acc, 1048576.0, x->bn_counter, x->sums, nullptr, nullptr, nullptr, nullptr, bn_count, h->cfg.bn_eps, h->cfg.bn_decay, h->cfg.bn_unbiased_ema};
-    if (!h->sync_bn) { fin.mean = mean; fin.inv_std = istd; fin.mov_mean = h->bnstat + c.mm_off; fin.mov_var = h->bnstat + c.mv_off; }
-    bn_partial_kernel<TA, TA, 0><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, nullptr, 0, 0, nullptr, nullptr, 0, part_bn, c.co, M, bn_rows, fin);
-    LAUNCH_CHECK(h);
+    if (!fused_stats) {
+      bn_partial_kernel<TA, TA, 0><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, nullptr, 0, 0, nullptr, nullptr, 0, part_bn, c.co, M, bn_rows, fin);
+      LAUNCH_CHECK(h);
+    }
     if (h->sync_bn) {
       do_allreduce(h, x->sums, 2 * c.co);
       bn_finalize_kernel<<<nblk(c.co, 128), 128, 0, h->stream>>>(x->sums, mean, istd, h->bnstat + c.mm_off, h->bnstat + c.mv_off, c.co,
@@ -316,8 +320,9 @@ static void train_step(Handle* h, const float* x_dev, const float* y_dev, const 
   HandleExtra* x = X(h);
   const size_t es = h->cfg.precision == DRS_PREC_FP32 ? 4 : 2;
   TrainGraph* replay = nullptr;
+  // (the legacy default stream cannot be captured)
   const bool graphable = x->use_graphs && h->world <= 1 && !getenv("DRS_DEBUG_KEEP") && !getenv("DRS_NO_GRAPHS") &&
-                         h->cfg.precision != DRS_PREC_F16;
+                         h->cfg.precision != DRS_PREC_F16 && h->stream != nullptr;
   if (!graphable) {
     if (capture_only) return;
     train_step_dispatch(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, pred_dev, cm_dev);

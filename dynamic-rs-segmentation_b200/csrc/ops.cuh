@@ -399,20 +399,6 @@ static void launch_maxpool3_bwd(Handle* h, const T* dout, int do_cs, int do_co, 
 // ------------------------------------------------------------------------------------------------
 constexpr int BN_THREADS = 256;
 
-// what the last block of bn_partial_kernel does with the reduced sums
-struct BnFinish {
-  long long* acc;          // [2][C] fixed-point accumulators, zero before the launch; cleared by the kernel
-  double fx_scale;         // fixed-point scale (2^20 forward statistics, 2^40 backward sums)
-  unsigned int* counter;   // zero before the launch; reset by the kernel
-  float* sums;             // [2][C] out
-  float* mean;             // non-null: also finalize (batch mean / inv_std, moving-average update)
-  float* inv_std;
-  float* mov_mean;
-  float* mov_var;
-  double count;
-  float eps, decay;
-  int unbiased_ema;
-};
 
 // part[blk][0][c] = sum_m a, part[blk][1][c] = sum_m a*b over the block's contiguous slab of rows.
 //   MODE 0 (forward statistics):  a = z,            b = z

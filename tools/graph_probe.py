@@ -11,7 +11,9 @@ for crop in (25, 37, 49):
         else:
             os.environ["DRS_GRAPHS"] = "1"
         s = drs_b200.Session("dilated_grsl", C, K, precision="bf16", seed=1)
-        s.set_stream(torch.cuda.current_stream().cuda_stream)
+        st = torch.cuda.Stream()
+        torch.cuda.set_stream(st)
+        s.set_stream(st.cuda_stream)
         s.set_profiling(mode == "graph+prof")
         x = torch.randn(B * crop * crop * C, device="cuda")
         y = torch.randint(0, K, (B * crop * crop,), device="cuda").float()
