@@ -348,6 +348,10 @@ static inline CUtensorMapDataType tm_dtype(int etype) {
 
 static void encode_tiled_2d(Handle* h, CUtensorMap* tm, int etype, const void* base, uint64_t inner, uint64_t outer,
                             uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+  const TmKey key{{1, (uint64_t)(uintptr_t)base, inner, outer, row_stride_bytes, ((uint64_t)box_inner << 32) | box_outer,
+                   ((uint64_t)etype << 32) | (uint32_t)swizzle_bytes, 0}};
+  auto it = h->tm_cache.find(key);
+  if (it != h->tm_cache.end()) { *tm = it->second; return; }
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
@@ -362,11 +366,18 @@ static void encode_tiled_2d(Handle* h, CUtensorMap* tm, int etype, const void* b
   DRS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu stride=%llu box=%ux%u", (int)r,
             (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner,
             box_outer);
+  if (h->tm_cache.size() > 4096) h->tm_cache.clear();
+  h->tm_cache[key] = *tm;
 }
 
 // NHWC activation tensor seen as (C, W, H, N); the bounding box of base pixels is the output raster.
 static void encode_im2col(Handle* h, CUtensorMap* tm, int etype, const void* base, int cstride, int crop, int B,
                           int pad_b, int channels_per_pixel, int pixels_per_column, int swizzle_bytes) {
+  const TmKey key{{2, (uint64_t)(uintptr_t)base, (uint64_t)cstride, ((uint64_t)crop << 32) | (uint32_t)B, (uint64_t)(uint32_t)pad_b,
+                   ((uint64_t)channels_per_pixel << 32) | (uint32_t)pixels_per_column,
+                   ((uint64_t)etype << 32) | (uint32_t)swizzle_bytes, 0}};
+  auto it = h->tm_cache.find(key);
+  if (it != h->tm_cache.end()) { *tm = it->second; return; }
   cuuint64_t dims[4] = {(cuuint64_t)cstride, (cuuint64_t)crop, (cuuint64_t)crop, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)cstride * 2, (cuuint64_t)cstride * 2 * crop, (cuuint64_t)cstride * 2 * crop * crop};
   // SAME, stride 1: lower = -pad_before; upper = pad_after - (k-1)*rate = -pad_before  (W, H order)
@@ -388,6 +399,8 @@ static void encode_im2col(Handle* h, CUtensorMap* tm, int etype, const void* bas
     size_t bytes = (size_t)cstride * 2 * crop * crop * B;
     if (bytes < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
   }
+  if (h->tm_cache.size() > 4096) h->tm_cache.clear();
+  h->tm_cache[key] = *tm;
 }
 
 template <int BLOCK_K, int EPI_C, typename OutT>

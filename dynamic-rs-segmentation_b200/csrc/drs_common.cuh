@@ -101,6 +101,13 @@ typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// Tensor maps are pure functions of (base pointer, geometry); encoding one costs a few microseconds on the host and every
+// convolution launch needs three, so they are memoised per handle (workspace addresses repeat from step to step).
+struct TmKey {
+  uint64_t v[8];
+  bool operator<(const TmKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
+};
+
 struct drs_handle_s {
   drs_config cfg;
   NetDesc net;
@@ -156,6 +163,7 @@ struct drs_handle_s {
 
   PFN_encodeTiled encodeTiled = nullptr;
   PFN_encodeIm2col encodeIm2col = nullptr;
+  std::map<TmKey, CUtensorMap> tm_cache;
 };
 typedef drs_handle_s Handle;
 
