@@ -39,6 +39,7 @@ struct ConvTcParams {
   int smem_needed;    // bytes used from the 1024B-aligned base
   int smem_provided;  // dynamic shared memory bytes of the launch
   uint32_t idesc;
+  int exp_mode;       // DRS_EXP_MODE timing experiments (results are garbage): 1 half of the A rows, 2 no A loads, 3 no B loads
   const float* scale; // [co]
   const float* shift; // [co]
   uint32_t* diag;     // host-mapped diagnostics
@@ -158,10 +159,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.diag, 0x100 + stage);
             uint8_t* sa = smem + stage * stage_bytes;
             uint8_t* sb = sa + A_BYTES;
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-            ptx::tma_load_im2col_4d(sa, &tmA, &full_bar[stage], p.in_coff + kb * BLOCK_K, px - p.pad_b, py - p.pad_b,
-                                    n_img, static_cast<uint16_t>(kx * p.rate), static_cast<uint16_t>(ky * p.rate));
-            ptx::tma_load_2d(sb, &tmB, &full_bar[stage], (t * kb_per_tap + kb) * BLOCK_K, 0);
+            if (p.exp_mode == 0) {
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+              ptx::tma_load_im2col_4d(sa, &tmA, &full_bar[stage], p.in_coff + kb * BLOCK_K, px - p.pad_b, py - p.pad_b,
+                                      n_img, static_cast<uint16_t>(kx * p.rate), static_cast<uint16_t>(ky * p.rate));
+              ptx::tma_load_2d(sb, &tmB, &full_bar[stage], (t * kb_per_tap + kb) * BLOCK_K, 0);
+            } else {
+              const uint32_t a_bytes = p.exp_mode == 1 ? A_BYTES / 2 : (p.exp_mode == 2 ? 0 : A_BYTES);
+              const uint32_t b_bytes = p.exp_mode == 3 ? 0 : static_cast<uint32_t>(B_BYTES);
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+              if (a_bytes)
+                ptx::tma_load_im2col_4d(sa, &tmA, &full_bar[stage], p.in_coff + kb * BLOCK_K, px - p.pad_b, py - p.pad_b,
+                                        n_img, static_cast<uint16_t>(kx * p.rate), static_cast<uint16_t>(ky * p.rate));
+              if (b_bytes) ptx::tma_load_2d(sb, &tmB, &full_bar[stage], (t * kb_per_tap + kb) * BLOCK_K, 0);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -213,7 +224,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_wait(&tmem_full[as], aphase, p.diag, 0x400 + as);
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.acc_stride);
-      for (int ch = 0; ch < n_chunks; ++ch) {
+      for (int ch = 0; ch < (p.exp_mode == 4 ? 0 : n_chunks); ++ch) {
         uint32_t v[EPI_C];
         ptx::tmem_ld_32x32b_x32(t_row + ch * EPI_C, v);
         if (EPI_C == 64) ptx::tmem_ld_32x32b_x32(t_row + ch * EPI_C + 32, v + (EPI_C == 64 ? 32 : 0));
@@ -238,7 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         ptx::fence_proxy_async_smem();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (epi_tid == 0) {
+        if (epi_tid == 0 && p.exp_mode != 5) {
           ptx::tma_store_2d(&tmC, stg + sbuf * STG_BYTES, p.out_coff + ch * EPI_C, tile * CONV_TC_BM);
           ptx::tma_store_commit();
         }
@@ -409,7 +420,8 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   const int64_t M = (int64_t)a.B * a.crop * a.crop;
   const int taps = a.k * a.k;
   const int sw_op = BLOCK_K * 2;
-  encode_im2col(h, &tmA, a.etype, a.in, a.in_cstride, a.crop, a.B, a.pad_b, BLOCK_K, CONV_TC_BM, sw_op);
+  const int exp_mode = getenv("DRS_EXP_MODE") ? atoi(getenv("DRS_EXP_MODE")) : 0;
+  encode_im2col(h, &tmA, a.etype, a.in, a.in_cstride, a.crop, a.B, a.pad_b, BLOCK_K, exp_mode == 1 ? CONV_TC_BM / 2 : CONV_TC_BM, sw_op);
   encode_tiled_2d(h, &tmB, a.etype, a.w, (uint64_t)taps * a.ci, (uint64_t)a.co, (uint64_t)taps * a.ci * 2, BLOCK_K,
                   (uint32_t)a.co, sw_op);
   encode_tiled_2d(h, &tmC, a.etype, a.out, (uint64_t)a.out_cstride, (uint64_t)M, (uint64_t)a.out_cstride * 2, EPI_C,
@@ -433,6 +445,7 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   p.scale = a.scale;
   p.shift = a.shift;
   p.diag = h->diag_dev;
+  p.exp_mode = exp_mode;
   if (a.stats) p.stats = *a.stats; else memset(&p.stats, 0, sizeof(p.stats));
 
   const int stage_bytes = CONV_TC_BM * BLOCK_K * 2 + a.co * BLOCK_K * 2;

@@ -111,6 +111,10 @@ struct TrainGraph {
 };
 
 struct HandleExtra {
+  // persistent scene-pass buffers (score map, occurrence counts, cell tables, label map ...): cudaMalloc / cudaFree of
+  // gigabyte-sized buffers per call costs hundreds of milliseconds, so each named slot only ever grows
+  void* slot_ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t slot_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::map<TrainGraphKey, TrainGraph> graphs;
   std::map<TrainGraphKey, int> graph_seen;
   TrainGraph* capturing = nullptr;   // non-null while a training step is being captured
@@ -143,6 +147,19 @@ struct HandleExtra {
 };
 static std::map<Handle*, HandleExtra*> g_extra;
 static HandleExtra* X(Handle* h) { return g_extra[h]; }
+static void* slot_buf(Handle* h, int slot, size_t bytes) {
+  HandleExtra* x = X(h);
+  if (bytes == 0) bytes = 16;
+  if (x->slot_cap[slot] < bytes) {
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (x->slot_ptr[slot]) CUDA_CHECK(cudaFree(x->slot_ptr[slot]));
+    x->slot_ptr[slot] = nullptr;
+    x->slot_cap[slot] = 0;
+    CUDA_CHECK(cudaMalloc(&x->slot_ptr[slot], bytes));
+    x->slot_cap[slot] = bytes;
+  }
+  return x->slot_ptr[slot];
+}
 static void lanes_release(Handle* h);
 
 static void free_packed(Handle* h) {
@@ -257,6 +274,8 @@ extern "C" int drs_destroy(drs_handle_t h) {
       if (x->ev_wgrad[i]) cudaEventDestroy(x->ev_wgrad[i]);
     }
     lanes_release(h);
+    for (int i = 0; i < 8; ++i)
+      if (x->slot_ptr[i]) cudaFree(x->slot_ptr[i]);
     for (auto& kv : x->graphs) {
       if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
       for (auto& pr : kv.second.events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }

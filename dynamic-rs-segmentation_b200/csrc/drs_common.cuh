@@ -78,6 +78,7 @@ struct Scene {
   void* data = nullptr;   // [H,W,C] f64 or f32
   uint8_t* labels = nullptr;
   int H = 0, W = 0, C = 0, dtype = 0;
+  size_t data_cap = 0, labels_cap = 0;   // allocation sizes (re-uploads of the same shape reuse the buffers)
   int row0 = 0, rows = 0;   // resident rows [row0, row0+rows) of the H-row scene (a rank keeps only its stripe + halo)
 };
 

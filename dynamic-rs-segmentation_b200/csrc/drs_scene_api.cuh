@@ -12,15 +12,25 @@ static void scene_upload_rows(Handle* h, int32_t scene_id, const void* rows_host
   DRS_CHECK(row0 >= 0 && rows >= 1 && row0 + rows <= H, "scene rows [%d,%d) outside [0,%d)", row0, row0 + rows, H);
   Scene& s = h->scenes[scene_id];
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
-  if (s.data) CUDA_CHECK(cudaFree(s.data));
-  if (s.labels) CUDA_CHECK(cudaFree(s.labels));
-  s = Scene();
   const size_t bytes = (size_t)rows * W * C * (dtype == DRS_SCENE_F64 ? 8 : 4);
-  CUDA_CHECK(cudaMalloc(&s.data, bytes));
+  if (s.data_cap < bytes) {
+    if (s.data) CUDA_CHECK(cudaFree(s.data));
+    s.data = nullptr; s.data_cap = 0;
+    CUDA_CHECK(cudaMalloc(&s.data, bytes));
+    s.data_cap = bytes;
+  }
   CUDA_CHECK(cudaMemcpyAsync(s.data, rows_host, bytes, cudaMemcpyHostToDevice, h->stream));
   if (labels_rows_host) {
-    CUDA_CHECK(cudaMalloc(&s.labels, (size_t)rows * W));
+    if (s.labels_cap < (size_t)rows * W) {
+      if (s.labels) CUDA_CHECK(cudaFree(s.labels));
+      s.labels = nullptr; s.labels_cap = 0;
+      CUDA_CHECK(cudaMalloc(&s.labels, (size_t)rows * W));
+      s.labels_cap = (size_t)rows * W;
+    }
     CUDA_CHECK(cudaMemcpyAsync(s.labels, labels_rows_host, (size_t)rows * W, cudaMemcpyHostToDevice, h->stream));
+  } else if (s.labels) {
+    CUDA_CHECK(cudaFree(s.labels));
+    s.labels = nullptr; s.labels_cap = 0;
   }
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   s.H = H; s.W = W; s.C = C; s.dtype = dtype; s.row0 = row0; s.rows = rows;
@@ -203,13 +213,7 @@ struct ScenePass {
   uint32_t* occur = nullptr;
   int32_t* cell_off = nullptr;
   int32_t* cell_seq = nullptr;
-  void release() {
-    if (prob) cudaFree(prob);
-    if (occur) cudaFree(occur);
-    if (cell_off) cudaFree(cell_off);
-    if (cell_seq) cudaFree(cell_seq);
-    prob = nullptr; occur = nullptr; cell_off = cell_seq = nullptr;
-  }
+  void release() { prob = nullptr; occur = nullptr; cell_off = cell_seq = nullptr; }   // buffers live in the handle's slots
 };
 
 static void accumulate_chunk(Handle* h, const ScenePass& sp, const CellTables& ct, const float* logits, const std::vector<int32_t>& pos,
@@ -232,10 +236,10 @@ static void accumulate_chunk(Handle* h, const ScenePass& sp, const CellTables& c
 }
 
 static void scene_pass_begin(Handle* h, ScenePass& sp, const CellTables& ct, int rows, int W, int K) {
-  CUDA_CHECK(cudaMalloc(&sp.prob, (size_t)rows * W * K * 4));
-  CUDA_CHECK(cudaMalloc(&sp.occur, (size_t)rows * W * 4));
-  CUDA_CHECK(cudaMalloc(&sp.cell_off, ct.off.size() * 4));
-  CUDA_CHECK(cudaMalloc(&sp.cell_seq, std::max<size_t>(ct.seq.size(), 1) * 4));
+  sp.prob = (float*)slot_buf(h, 0, (size_t)rows * W * K * 4);
+  sp.occur = (uint32_t*)slot_buf(h, 1, (size_t)rows * W * 4);
+  sp.cell_off = (int32_t*)slot_buf(h, 2, ct.off.size() * 4);
+  sp.cell_seq = (int32_t*)slot_buf(h, 3, std::max<size_t>(ct.seq.size(), 1) * 4);
   CUDA_CHECK(cudaMemsetAsync(sp.prob, 0, (size_t)rows * W * K * 4, h->stream));
   CUDA_CHECK(cudaMemsetAsync(sp.occur, 0, (size_t)rows * W * 4, h->stream));
   CUDA_CHECK(cudaMemcpyAsync(sp.cell_off, ct.off.data(), ct.off.size() * 4, cudaMemcpyHostToDevice, h->stream));
@@ -244,18 +248,13 @@ static void scene_pass_begin(Handle* h, ScenePass& sp, const CellTables& ct, int
 
 static void scene_pass_finish(Handle* h, ScenePass& sp, int rows, int W, int K, uint8_t* labels_host, double* mean_host) {
   const int64_t npix = (int64_t)rows * W;
-  uint8_t* lab_dev = nullptr;
-  double* mean_dev = nullptr;
-  CUDA_CHECK(cudaMalloc(&lab_dev, npix));
-  if (mean_host) CUDA_CHECK(cudaMalloc(&mean_dev, npix * K * 8));
+  uint8_t* lab_dev = (uint8_t*)slot_buf(h, 4, npix);
+  double* mean_dev = mean_host ? (double*)slot_buf(h, 5, npix * K * 8) : nullptr;
   scene_argmax_kernel<<<nblk(npix, 256), 256, 0, h->stream>>>(sp.prob, sp.occur, npix, K, lab_dev, mean_dev);
   LAUNCH_CHECK(h);
   CUDA_CHECK(cudaMemcpyAsync(labels_host, lab_dev, npix, cudaMemcpyDeviceToHost, h->stream));
   if (mean_host) CUDA_CHECK(cudaMemcpyAsync(mean_host, mean_dev, npix * K * 8, cudaMemcpyDeviceToHost, h->stream));
-  cudaError_t e = cudaStreamSynchronize(h->stream);
-  cudaFree(lab_dev);
-  if (mean_dev) cudaFree(mean_dev);
-  CUDA_CHECK(e);
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
 }
 
 extern "C" int drs_accumulate_argmax(drs_handle_t h, const float* logits_dev, const int32_t* pos_host, int32_t P, int32_t crop,
@@ -366,13 +365,12 @@ extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, i
     for (auto& L : hx->lanes)
       if (L.stream) cudaStreamSynchronize(L.stream);
     sp.release();
-    if (inst_dev) cudaFree(inst_dev);
   };
   try {
     scene_pass_begin(h, sp, ct, rows, W, K);
     std::vector<int32_t> inst((size_t)P * 3);
     for (int p = 0; p < P; ++p) { inst[3 * p] = scene_id; inst[3 * p + 1] = pos[2 * p]; inst[3 * p + 2] = pos[2 * p + 1]; }
-    CUDA_CHECK(cudaMalloc(&inst_dev, std::max<size_t>(inst.size(), 1) * 4));
+    inst_dev = (int32_t*)slot_buf(h, 6, std::max<size_t>(inst.size(), 1) * 4);
     CUDA_CHECK(cudaMemcpyAsync(inst_dev, inst.data(), inst.size() * 4, cudaMemcpyHostToDevice, h->stream));
     refresh_packed(h, false);                       // packed weights / folded BN once, before the lanes start
     lanes_ensure(h, n_lanes, forward_eval_workspace(h, chunk, crop), (size_t)chunk * pp * C * 4, (size_t)chunk * pp * K * 4);
