@@ -39,7 +39,8 @@ struct ConvTcParams {
   int smem_needed;    // bytes used from the 1024B-aligned base
   int smem_provided;  // dynamic shared memory bytes of the launch
   uint32_t idesc;
-  int exp_mode;       // DRS_EXP_MODE timing experiments (results are garbage): 1 half of the A rows, 2 no A loads, 3 no B loads
+  int exp_mode;       // DRS_EXP_MODE timing experiments (results are garbage): 1 half of the A rows, 2 no A loads, 3 no B loads,
+                      // 4 no epilogue, 5 no TMA store, 7 one MMA per stage
   const float* scale; // [co]
   const float* shift; // [co]
   uint32_t* diag;     // host-mapped diagnostics
@@ -198,6 +199,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t bdesc = ptx::make_smem_desc(sb, 16, OP_SBO, OP_LAYOUT);
 #pragma unroll
           for (int j = 0; j < BLOCK_K / 16; ++j) {
+            if (p.exp_mode == 7 && j > 0) break;   // timing experiment: one MMA per stage
             // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the >>4 address field
             ptx::umma_f16(d_tmem, adesc + static_cast<uint64_t>(j * 2), bdesc + static_cast<uint64_t>(j * 2), p.idesc,
                           static_cast<uint32_t>((kb | j) != 0));
