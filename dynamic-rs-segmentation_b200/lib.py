@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdrs.so")
+LIB_PATH = os.environ.get("DRS_LIB", os.path.join(_HERE, "libdrs.so"))    # DRS_LIB: an alternative build (experiments)
 
 NET_TYPES = {
     "dilated_icpr_original": 0,        # isprs:761
