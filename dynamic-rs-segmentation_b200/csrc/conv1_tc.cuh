@@ -118,7 +118,9 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer: 25 taps per tile
-    if (lane == 0) {
+    // (convergent warp, elected lane issues: see conv_tc.cuh)
+    {
+      const bool leader = ptx::elect_one_sync();
       int stage = 0;
       uint32_t phase = 0;
       const int cc = p.crop * p.crop;
@@ -130,18 +132,20 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int px = rem - py * p.crop;
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.diag, 0x900 + stage);
         uint8_t* sa = smem + stage * C1_STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(C1_TAPS * C1_SLOT_BYTES));
-        for (int t = 0; t < C1_TAPS; ++t) {
-          const int ky = t / 5, kx = t - ky * 5;
-          ptx::tma_load_im2col_4d(sa + t * C1_SLOT_BYTES, &tmA, &full_bar[stage], 0, px - 2, py - 2, n_img,
-                                  static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
+        if (leader) {
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(C1_TAPS * C1_SLOT_BYTES));
+#pragma unroll
+          for (int t = 0; t < C1_TAPS; ++t)
+            ptx::tma_load_im2col_4d(sa + t * C1_SLOT_BYTES, &tmA, &full_bar[stage], 0, px - 2, py - 2, n_img,
+                                    static_cast<uint16_t>(t % 5), static_cast<uint16_t>(t / 5));
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer: 13 x (M128, N=Co, K16)
-    if (lane == 0) {
+    {
+      const bool leader = ptx::elect_one_sync();
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -154,15 +158,17 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         ptx::tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.acc_stride);
         const uint32_t sa = ptx::smem_u32(smem + stage * C1_STAGE_BYTES);
+        if (leader) {
 #pragma unroll
-        for (int j = 0; j < C1_SLOTS / 2; ++j) {
-          // no swizzle, K-major: LBO = distance between the two K core matrices, SBO = next 8 rows (128 B)
-          const uint64_t adesc = ptx::make_smem_desc(sa + j * 2 * C1_SLOT_BYTES, C1_SLOT_BYTES, 128, 0u);
-          const uint64_t bdesc = ptx::make_smem_desc(sb + j * 2 * b_lbo, b_lbo, 128, 0u);
-          ptx::umma_f16(d_tmem, adesc, bdesc, p.idesc, static_cast<uint32_t>(j != 0));
+          for (int j = 0; j < C1_SLOTS / 2; ++j) {
+            // no swizzle, K-major: LBO = distance between the two K core matrices, SBO = next 8 rows (128 B)
+            const uint64_t adesc = ptx::make_smem_desc(sa + j * 2 * C1_SLOT_BYTES, C1_SLOT_BYTES, 128, 0u);
+            const uint64_t bdesc = ptx::make_smem_desc(sb + j * 2 * b_lbo, b_lbo, 128, 0u);
+            ptx::umma_f16(d_tmem, adesc, bdesc, p.idesc, static_cast<uint32_t>(j != 0));
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          ptx::umma_commit(&tmem_full[as]);
         }
-        ptx::umma_commit(&empty_bar[stage]);
-        ptx::umma_commit(&tmem_full[as]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
@@ -172,6 +178,8 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int epi_tid = threadIdx.x - 128;
+    // one elected lane of warp 4 owns the TMA stores (bulk groups are per thread: elect.sync picks the same lane for the
+    // same member mask every time); elected at each site so that ptxas sees a single active thread
     constexpr int CHUNK16 = EPI_C / 8;
     const int sw = (EPI_C == 64) ? (row & 7) : ((row >> 1) & 3);
     const int n_chunks = p.co / EPI_C;
@@ -187,7 +195,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         ptx::tmem_ld_32x32b_x32(t_row + ch * EPI_C, v);
         if (EPI_C == 64) ptx::tmem_ld_32x32b_x32(t_row + ch * EPI_C + 32, v + (EPI_C == 64 ? 32 : 0));
         ptx::tmem_wait_ld();
-        if (epi_tid == 0) ptx::tma_store_wait_read<1>();
+        if (warp == 4 && ptx::elect_one_sync()) ptx::tma_store_wait_read<1>();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         uint8_t* srow = stg + sbuf * STG_BYTES + row * (EPI_C * 2);
         const float* sc = s_scale + ch * EPI_C;
@@ -206,7 +214,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         ptx::fence_proxy_async_smem();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (epi_tid == 0) {
+        if (warp == 4 && ptx::elect_one_sync()) {
           ptx::tma_store_2d(&tmC, stg + sbuf * STG_BYTES, p.out_coff + ch * EPI_C, tile * CONV_TC_BM);
           ptx::tma_store_commit();
         }
@@ -217,7 +225,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if (epi_tid == 0) ptx::tma_store_wait_all();
+    if (warp == 4 && ptx::elect_one_sync()) ptx::tma_store_wait_all();
   }
 
   ptx::tcgen05_fence_before();

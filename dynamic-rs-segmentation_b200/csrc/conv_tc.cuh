@@ -18,9 +18,10 @@
 //   swizzled staging in shared memory -> TMA store into a channel slice of the NHWC output
 //   (dense nets write straight into the concat buffer: tf.concat, isprs:921-948, costs nothing).
 //
-// Warp roles (256 threads, persistent, one CTA per SM):
-//   warp 0 lane 0 : TMA producer          warp 1 lane 0 : tcgen05.mma issuer
-//   warp 2        : TMEM allocator        warps 4..7    : epilogue (TMEM lane quadrant = warp % 4)
+// Warp roles (256 threads, persistent, one CTA per SM; role warps stay converged, an elected lane issues):
+//   warp 0 : TMA producer, im2col tiles     warp 1 : tcgen05.mma issuer
+//   warp 3 : TMA producer, filter slices    warp 2 : TMEM allocator
+//   warps 4..7 : epilogue (TMEM lane quadrant = warp % 4)
 #pragma once
 #include "drs_common.cuh"
 #include "ptx_sm100.cuh"
@@ -33,14 +34,15 @@ struct ConvTcParams {
   int co, out_coff;   // N, channel offset inside the output buffer
   int num_tiles;      // ceil(M_total / 128)
   int stages;         // smem pipeline depth
+  int kps;            // K blocks (BLOCK_K channels of one tap) per pipeline stage: one barrier round trip per kps blocks
   int acc_stride;     // TMEM columns between the two accumulator stages
   int tmem_cols;      // allocated TMEM columns (power of two >= 32)
   int act;
   int smem_needed;    // bytes used from the 1024B-aligned base
   int smem_provided;  // dynamic shared memory bytes of the launch
   uint32_t idesc;
-  int exp_mode;       // DRS_EXP_MODE timing experiments (results are garbage): 1 half of the A rows, 2 no A loads, 3 no B loads,
-                      // 4 no epilogue, 5 no TMA store, 7 one MMA per stage
+  int exp_mode;       // DRS_EXP_MODE timing experiments (results are garbage): 4 no epilogue, 5 no TMA store, 8 no loads,
+                      // 9 no MMA, 10 neither and no epilogue (barrier hand-shake only)
   const float* scale; // [co]
   const float* shift; // [co]
   uint32_t* diag;     // host-mapped diagnostics
@@ -67,7 +69,7 @@ __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
 
 // BLOCK_K: channels per K step (64 -> 128B swizzle, 32 -> 64B swizzle).  EPI_C: channels per epilogue
 // store box (64 -> 128B swizzle, 32 -> 64B swizzle).
-template <int BLOCK_K, int EPI_C, typename OutT>
+template <int BLOCK_K, int EPI_C, typename OutT, bool INSTR>
 __global__ void __launch_bounds__(CONV_TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const ConvTcParams p) {
@@ -92,7 +94,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __trap();
   }
   const int B_BYTES = p.co * BLOCK_K * 2;
-  const int stage_bytes = A_BYTES + B_BYTES;
+  const int kb_bytes = A_BYTES + B_BYTES;                      // one K block: im2col tile + filter slice
+  const int stage_bytes = p.kps * kb_bytes;
   uint8_t* stg = smem + p.stages * stage_bytes;                // 2 staging buffers (1024B aligned)
   float* s_scale = reinterpret_cast<float*>(stg + 2 * STG_BYTES);
   float* s_shift = s_scale + 256;
@@ -124,7 +127,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&full_bar[s], 2);     // one arrive.expect_tx per producer warp (A tiles, B tiles)
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -142,73 +145,129 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int cc = p.crop * p.crop;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m0 = tile * CONV_TC_BM;
-        const int n_img = m0 / cc;
-        const int rem = m0 - n_img * cc;
-        const int py = rem / p.crop;
-        const int px = rem - py * p.crop;
-        for (int t = 0; t < taps; ++t) {
-          const int ky = t / p.ksize, kx = t - ky * p.ksize;
-          for (int kb = 0; kb < kb_per_tap; ++kb) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.diag, 0x100 + stage);
-            uint8_t* sa = smem + stage * stage_bytes;
-            uint8_t* sb = sa + A_BYTES;
-            if (p.exp_mode == 0) {
-              ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-              ptx::tma_load_im2col_4d(sa, &tmA, &full_bar[stage], p.in_coff + kb * BLOCK_K, px - p.pad_b, py - p.pad_b,
-                                      n_img, static_cast<uint16_t>(kx * p.rate), static_cast<uint16_t>(ky * p.rate));
-              ptx::tma_load_2d(sb, &tmB, &full_bar[stage], (t * kb_per_tap + kb) * BLOCK_K, 0);
-            } else {
-              const uint32_t a_bytes = p.exp_mode == 1 ? A_BYTES / 2 : (p.exp_mode == 2 ? 0 : A_BYTES);
-              const uint32_t b_bytes = p.exp_mode == 3 ? 0 : static_cast<uint32_t>(B_BYTES);
-              ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-              if (a_bytes)
-                ptx::tma_load_im2col_4d(sa, &tmA, &full_bar[stage], p.in_coff + kb * BLOCK_K, px - p.pad_b, py - p.pad_b,
-                                        n_img, static_cast<uint16_t>(kx * p.rate), static_cast<uint16_t>(ky * p.rate));
-              if (b_bytes) ptx::tma_load_2d(sb, &tmB, &full_bar[stage], (t * kb_per_tap + kb) * BLOCK_K, 0);
-            }
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          }
+  // The two single-thread roles are issue-bound (measured: every instruction in these loops shows in the kernel time
+  // for Co <= 192), so they are written for a minimal dependent instruction stream: running shared-memory addresses,
+  // 32-bit descriptor arithmetic, a per-K-block table instead of divisions, kps K blocks per barrier round trip.
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t full0 = ptx::smem_u32(full_bar), empty0 = ptx::smem_u32(empty_bar);
+  const uint32_t ring_bytes = static_cast<uint32_t>(p.stages * stage_bytes);
+  const bool no_loads = p.exp_mode == 8 || p.exp_mode == 10;
+  const bool no_mma = p.exp_mode == 9 || p.exp_mode == 10;
+  if (warp == 0 || warp == 3) {
+    // ------------------------------------------------------------------ TMA producers: warp 0 loads the im2col tiles (A),
+    // warp 3 the filter slices (B); each arrives on the stage's full barrier with its own byte count (barrier count 2).
+    // The whole warp runs the loop (convergent) and one *elected* lane issues: under `if (lane == 0)` ptxas cannot tell
+    // that a single thread is active and wraps every UTMALDG / UTCHMMA in an ELECT + BRA.U.ANY loop fed by R2UR moves
+    // (~100 cycles per instruction, measured); with elect.sync the warp-level instructions are issued directly.
+    // Two warps because the issue loop itself is the bottleneck of the pipeline for Co <= 192 (~160 cycles per UTMALDG
+    // with its operand set-up, measured with the INSTR twin): A and B issue in parallel on different schedulers.
+    const bool is_a = warp == 0;
+    const bool leader = ptx::elect_one_sync();
+    uint32_t soff = 0, boff = 0, phase = 0;     // byte offset of the stage in the ring / of its barrier
+    long long t_begin = 0, t_wait = 0, t_exp = 0, t_tma = 0;
+    uint32_t n_stage = 0;
+    if (INSTR) t_begin = clock64();
+    const int cc = p.crop * p.crop;
+    const uint32_t kb_tx = is_a ? A_BYTES : static_cast<uint32_t>(B_BYTES);
+    const int w_end = p.ksize * p.rate;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m0 = tile * CONV_TC_BM;
+      const int n_img = m0 / cc;
+      const int rem = m0 - n_img * cc;
+      const int py = rem / p.crop;
+      const int cw = rem - py * p.crop - p.pad_b, chh = py - p.pad_b;
+      int cb = p.in_coff, offw = 0, offh = 0, kcol = 0;   // channel block of the tap, tap offsets, filter-matrix column
+      for (int kb0 = 0; kb0 < num_kb; kb0 += p.kps) {
+        const int nk = min(p.kps, num_kb - kb0);
+        long long t0 = 0, t1 = 0, t2 = 0;
+        if (INSTR) t0 = clock64();
+        ptx::mbar_wait_addr(empty0 + boff, phase ^ 1, p.diag, 0x100);
+        if (INSTR) { t1 = clock64(); t_wait += t1 - t0; ++n_stage; }
+        const uint32_t fb = full0 + boff;
+        if (leader) {
+          if (no_loads) ptx::mbar_arrive_addr(fb);                     // timing experiment: barrier hand-shake only
+          else ptx::mbar_arrive_expect_tx_addr(fb, static_cast<uint32_t>(nk) * kb_tx);
         }
+        if (INSTR) { t2 = clock64(); t_exp += t2 - t1; }
+        uint32_t dst = smem_base + soff + (is_a ? 0u : A_BYTES);
+        if (is_a) {
+          for (int j = 0; j < nk; ++j, dst += kb_bytes) {
+            if (leader && !no_loads)
+              ptx::tma_load_im2col_4d_addr(dst, &tmA, fb, cb, cw, chh, n_img, static_cast<uint16_t>(offw), static_cast<uint16_t>(offh));
+            cb += BLOCK_K;
+            if (cb == p.in_coff + p.ci) {
+              cb = p.in_coff;
+              offw += p.rate;
+              if (offw == w_end) { offw = 0; offh += p.rate; }
+            }
+          }
+        } else {
+          for (int j = 0; j < nk; ++j, dst += kb_bytes, kcol += BLOCK_K)
+            if (leader && !no_loads) ptx::tma_load_2d_addr(dst, &tmB, fb, kcol, 0);
+        }
+        if (INSTR) t_tma += clock64() - t2;
+        soff += stage_bytes;
+        boff += 8;
+        if (soff == ring_bytes) { soff = 0; boff = 0; phase ^= 1; }
       }
     }
+    if (INSTR && is_a && leader && blockIdx.x == 0 && p.diag) {
+      p.diag[4] = static_cast<uint32_t>(clock64() - t_begin);
+      p.diag[5] = static_cast<uint32_t>(t_wait);
+      p.diag[6] = n_stage;
+      p.diag[7] = static_cast<uint32_t>(t_exp);
+      p.diag[8] = static_cast<uint32_t>(t_tma);
+    }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+    // ------------------------------------------------------------------ MMA issuer (convergent warp, elected lane issues)
+    {
+      const bool leader = ptx::elect_one_sync();
+      uint32_t soff = 0, boff = 0, phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      long long t_begin = 0, t_wait = 0, t_wait_acc = 0, t_mma = 0, t_commit = 0;
+      if (INSTR) t_begin = clock64();
+      // descriptor words: low = address >> 4 | LBO(16 B) << 16, high = SBO >> 4 | version | layout
+      const uint32_t desc_lo0 = ((smem_base >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t desc_hi = ((OP_SBO >> 4) & 0x3FFFu) | (1u << 14) | (OP_LAYOUT << 29);
+      const uint32_t kb_step = static_cast<uint32_t>(kb_bytes) >> 4;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&tmem_empty[as], aphase ^ 1, p.diag, 0x200 + as);
-        ptx::tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.acc_stride);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase, p.diag, 0x300 + stage);
-          ptx::tcgen05_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb = sa + A_BYTES;
-          const uint64_t adesc = ptx::make_smem_desc(sa, 16, OP_SBO, OP_LAYOUT);
-          const uint64_t bdesc = ptx::make_smem_desc(sb, 16, OP_SBO, OP_LAYOUT);
-#pragma unroll
-          for (int j = 0; j < BLOCK_K / 16; ++j) {
-            if (p.exp_mode == 7 && j > 0) break;   // timing experiment: one MMA per stage
-            // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the >>4 address field
-            ptx::umma_f16(d_tmem, adesc + static_cast<uint64_t>(j * 2), bdesc + static_cast<uint64_t>(j * 2), p.idesc,
-                          static_cast<uint32_t>((kb | j) != 0));
-          }
-          ptx::umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (INSTR) {
+          const long long t0 = clock64();
+          ptx::mbar_wait(&tmem_empty[as], aphase ^ 1, p.diag, 0x200 + as);
+          t_wait_acc += clock64() - t0;
+        } else {
+          ptx::mbar_wait(&tmem_empty[as], aphase ^ 1, p.diag, 0x200 + as);
         }
-        ptx::umma_commit(&tmem_full[as]);        // accumulator complete -> epilogue
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.acc_stride);
+        for (int kb0 = 0; kb0 < num_kb; kb0 += p.kps) {
+          const int nk = min(p.kps, num_kb - kb0);
+          long long t0 = 0, t1 = 0, t2 = 0;
+          if (INSTR) t0 = clock64();
+          ptx::mbar_wait_addr(full0 + boff, phase, p.diag, 0x300);
+          ptx::tcgen05_fence_after();
+          if (INSTR) { t1 = clock64(); t_wait += t1 - t0; }
+          if (leader && !no_mma) {
+            uint32_t a_lo = desc_lo0 + (soff >> 4);
+            for (int j = 0; j < nk; ++j, a_lo += kb_step)
+              ptx::umma_f16_kblock<BLOCK_K / 16>(d_tmem, a_lo, a_lo + (A_BYTES >> 4), desc_hi, p.idesc, (kb0 | j) != 0 ? 1u : 0u);
+          }
+          if (INSTR) { t2 = clock64(); t_mma += t2 - t1; }
+          if (leader) ptx::umma_commit_addr(empty0 + boff);   // frees the smem slot when these MMAs retire
+          if (INSTR) t_commit += clock64() - t2;
+          soff += stage_bytes;
+          boff += 8;
+          if (soff == ring_bytes) { soff = 0; boff = 0; phase ^= 1; }
+        }
+        if (leader) ptx::umma_commit(&tmem_full[as]);        // accumulator complete -> epilogue
         if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+      if (INSTR && leader && blockIdx.x == 0 && p.diag) {
+        p.diag[9] = static_cast<uint32_t>(clock64() - t_begin);
+        p.diag[10] = static_cast<uint32_t>(t_wait);
+        p.diag[11] = static_cast<uint32_t>(t_mma);
+        p.diag[12] = static_cast<uint32_t>(t_commit);
+        p.diag[13] = static_cast<uint32_t>(t_wait_acc);
       }
     }
   } else if (warp >= 4) {
@@ -216,6 +275,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quad = warp & 3;
     const int row = quad * 32 + lane;            // accumulator row == pixel within the tile
     const int epi_tid = threadIdx.x - 128;
+    // one elected lane of warp 4 owns the TMA stores (bulk groups are per thread: elect.sync picks the same lane for the
+    // same member mask every time); elected at each site so that ptxas sees a single active thread
     constexpr int CHUNK16 = EPI_C / 8;           // 16-byte chunks per staged row
     const int sw = (EPI_C == 64) ? (row & 7) : ((row >> 1) & 3);
     const int n_chunks = p.co / EPI_C;
@@ -226,13 +287,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_wait(&tmem_full[as], aphase, p.diag, 0x400 + as);
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.acc_stride);
-      for (int ch = 0; ch < (p.exp_mode == 4 ? 0 : n_chunks); ++ch) {
+      for (int ch = 0; ch < ((p.exp_mode == 4 || p.exp_mode == 10) ? 0 : n_chunks); ++ch) {
         uint32_t v[EPI_C];
         ptx::tmem_ld_32x32b_x32(t_row + ch * EPI_C, v);
         if (EPI_C == 64) ptx::tmem_ld_32x32b_x32(t_row + ch * EPI_C + 32, v + (EPI_C == 64 ? 32 : 0));
         ptx::tmem_wait_ld();
         // the TMA store that last read staging buffer `sbuf` (two chunks ago) must have drained
-        if (epi_tid == 0) ptx::tma_store_wait_read<1>();
+        if (warp == 4 && ptx::elect_one_sync()) ptx::tma_store_wait_read<1>();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         uint8_t* srow = stg + sbuf * STG_BYTES + row * (EPI_C * 2);
         const float* sc = s_scale + ch * EPI_C;
@@ -251,7 +312,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         ptx::fence_proxy_async_smem();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (epi_tid == 0 && p.exp_mode != 5) {
+        if (warp == 4 && p.exp_mode != 5 && ptx::elect_one_sync()) {
           ptx::tma_store_2d(&tmC, stg + sbuf * STG_BYTES, p.out_coff + ch * EPI_C, tile * CONV_TC_BM);
           ptx::tma_store_commit();
         }
@@ -284,7 +345,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if (epi_tid == 0) ptx::tma_store_wait_all();
+    if (warp == 4 && ptx::elect_one_sync()) ptx::tma_store_wait_all();
     if (p.stats.acc) {
       // CTA partial (row groups combined in fixed order) -> 64-bit fixed point -> integer atomicAdd (order-independent);
       // the last CTA to arrive converts, finalizes mean / inv_std / moving averages and clears the accumulators.
@@ -416,14 +477,25 @@ static void encode_im2col(Handle* h, CUtensorMap* tm, int etype, const void* bas
   h->tm_cache[key] = *tm;
 }
 
+static int g_conv_exp_mode = -1;   // drs_bench_conv override of DRS_EXP_MODE
+#ifndef CONV_TC_KPS2_MAX_CO
+#define CONV_TC_KPS2_MAX_CO 128      // two K blocks per stage for Co <= this
+#endif
+
 template <int BLOCK_K, int EPI_C, typename OutT>
 static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   alignas(64) CUtensorMap tmA, tmB, tmC;
   const int64_t M = (int64_t)a.B * a.crop * a.crop;
   const int taps = a.k * a.k;
   const int sw_op = BLOCK_K * 2;
-  const int exp_mode = getenv("DRS_EXP_MODE") ? atoi(getenv("DRS_EXP_MODE")) : 0;
-  encode_im2col(h, &tmA, a.etype, a.in, a.in_cstride, a.crop, a.B, a.pad_b, BLOCK_K, exp_mode == 1 ? CONV_TC_BM / 2 : CONV_TC_BM, sw_op);
+  // experiment word: bits 0-7 timing mode, bits 8-11 pipeline variant + 1 (0 = default), bits 12-15 K blocks per stage (0 = default)
+  const int exp_word = g_conv_exp_mode >= 0 ? g_conv_exp_mode : (getenv("DRS_EXP_MODE") ? atoi(getenv("DRS_EXP_MODE")) : 0);
+  const int exp_mode = exp_word & 0xff;
+  const bool instr = ((exp_word >> 16) & 1) != 0;
+  const int taps_kb = taps * (a.ci / BLOCK_K);
+  int kps = ((exp_word >> 12) & 0xf) ? ((exp_word >> 12) & 0xf) : (a.co <= CONV_TC_KPS2_MAX_CO ? 2 : 1);
+  if (kps > taps_kb) kps = taps_kb;
+  encode_im2col(h, &tmA, a.etype, a.in, a.in_cstride, a.crop, a.B, a.pad_b, BLOCK_K, CONV_TC_BM, sw_op);
   encode_tiled_2d(h, &tmB, a.etype, a.w, (uint64_t)taps * a.ci, (uint64_t)a.co, (uint64_t)taps * a.ci * 2, BLOCK_K,
                   (uint32_t)a.co, sw_op);
   encode_tiled_2d(h, &tmC, a.etype, a.out, (uint64_t)a.out_cstride, (uint64_t)M, (uint64_t)a.out_cstride * 2, EPI_C,
@@ -450,26 +522,40 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   p.exp_mode = exp_mode;
   if (a.stats) p.stats = *a.stats; else memset(&p.stats, 0, sizeof(p.stats));
 
-  const int stage_bytes = CONV_TC_BM * BLOCK_K * 2 + a.co * BLOCK_K * 2;
+  const int kb_bytes = CONV_TC_BM * BLOCK_K * 2 + a.co * BLOCK_K * 2;
   const int fixed = 2 * CONV_TC_BM * EPI_C * 2 + 2 * 256 * 4 + (2 * 8 + 4) * 8 + 16 +
                     (a.stats ? (CONV_TC_BM / EPI_C) * 2 * a.co * 4 : 0);
   const int budget = 227 * 1024;
+  if ((budget - fixed) / (kps * kb_bytes) < 2) kps = 1;
+  const int stage_bytes = kps * kb_bytes;
   int stages = (budget - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   DRS_CHECK(stages >= 2, "conv_tc: tile does not fit shared memory (co=%d)", a.co);
   p.stages = stages;
+  p.kps = kps;
   p.smem_needed = fixed + stages * stage_bytes;
   const int smem_bytes = p.smem_needed + 1024 <= budget ? p.smem_needed + 1024 : budget;
   p.smem_provided = smem_bytes;
 
-  auto kern = conv_tc_kernel<BLOCK_K, EPI_C, OutT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-    attr_set = true;
-  }
   int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
-  kern<<<grid, CONV_TC_THREADS, smem_bytes, h->stream>>>(tmA, tmB, tmC, p);
+  if (instr && BLOCK_K == 64 && EPI_C == 64) {
+    // instrumented twin (clock64 around every barrier wait of CTA 0, written to the diagnostic words): bench only
+    auto kern = conv_tc_kernel<64, 64, OutT, true>;
+    static bool attr_set_i = false;
+    if (!attr_set_i) {
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+      attr_set_i = true;
+    }
+    kern<<<grid, CONV_TC_THREADS, smem_bytes, h->stream>>>(tmA, tmB, tmC, p);
+  } else {
+    auto kern = conv_tc_kernel<BLOCK_K, EPI_C, OutT, false>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+      attr_set = true;
+    }
+    kern<<<grid, CONV_TC_THREADS, smem_bytes, h->stream>>>(tmA, tmB, tmC, p);
+  }
   LAUNCH_CHECK(h);
 }
 

@@ -534,6 +534,70 @@ extern "C" int drs_debug_conv(drs_handle_t h, const float* x_host, const float* 
   API_END
 }
 
+// Kernel micro-benchmark (tools/conv_bench.py): `reps` back-to-back launches of one tcgen05 convolution on pseudo-random
+// resident operands, timed with events on the handle's stream.  exp_mode >= 0 overrides DRS_EXP_MODE for these launches.
+__global__ void bench_fill_kernel(uint16_t* __restrict__ p, int64_t n, uint32_t seed, int bf16) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t v = (uint32_t)i * 2654435761u + seed;
+    v ^= v >> 15; v *= 2246822519u; v ^= v >> 13;
+    const float f = ((float)(v & 0xffff) / 65536.0f - 0.5f) * 0.5f;
+    p[i] = bf16 ? __bfloat16_as_ushort(__float2bfloat16(f)) : __half_as_ushort(__float2half(f));
+  }
+}
+extern "C" int drs_bench_conv(drs_handle_t h, int32_t B, int32_t crop, int32_t k, int32_t rate, int32_t Ci, int32_t Co,
+                              int32_t precision, int32_t exp_mode, int32_t reps, float* ms_out, uint32_t* instr_out) {
+  API_BEGIN
+  DRS_CHECK(h && ms_out && reps >= 1, "bad argument");
+  DRS_CHECK(precision == DRS_PREC_F16 || precision == DRS_PREC_BF16, "bench_conv: tensor-core precisions only");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  const int64_t M = (int64_t)B * crop * crop;
+  const int64_t nw = (int64_t)k * k * Ci * Co;
+  const int pad_b = ((k - 1) * rate) / 2;
+  void *xa = nullptr, *wp = nullptr, *ya = nullptr;
+  float* sc = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(xa); cudaFree(wp); cudaFree(ya); cudaFree(sc);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    g_conv_exp_mode = -1;
+  };
+  try {
+    const int bf = precision == DRS_PREC_BF16;
+    CUDA_CHECK(cudaMalloc(&xa, M * Ci * 2));
+    CUDA_CHECK(cudaMalloc(&wp, nw * 2));
+    CUDA_CHECK(cudaMalloc(&ya, M * Co * 2));
+    CUDA_CHECK(cudaMalloc(&sc, 2 * 256 * 4));
+    bench_fill_kernel<<<1024, 256, 0, h->stream>>>((uint16_t*)xa, M * Ci, 1u, bf);
+    bench_fill_kernel<<<256, 256, 0, h->stream>>>((uint16_t*)wp, nw, 2u, bf);
+    {
+      std::vector<float> one_zero(512, 0.0f);
+      for (int i = 0; i < 256; ++i) one_zero[i] = 1.0f;
+      CUDA_CHECK(cudaMemcpy(sc, one_zero.data(), 512 * 4, cudaMemcpyHostToDevice));
+    }
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    ConvTcArgs a;
+    a.in = xa; a.in_cstride = Ci; a.in_coff = 0; a.ci = Ci; a.w = wp; a.out = ya; a.out_cstride = Co; a.out_coff = 0; a.co = Co;
+    a.B = B; a.crop = crop; a.k = k; a.rate = rate; a.pad_b = pad_b; a.scale = sc; a.shift = sc + 256; a.act = ACT_RELU;
+    a.etype = bf ? ET_BF16 : ET_F16;
+    g_conv_exp_mode = exp_mode;
+    launch_conv_tc(h, a);                       // warm-up (tensor maps, module load)
+    CUDA_CHECK(cudaEventRecord(e0, h->stream));
+    for (int r = 0; r < reps; ++r) launch_conv_tc(h, a);
+    CUDA_CHECK(cudaEventRecord(e1, h->stream));
+    int rc = drs_synchronize(h);
+    if (rc) throw DrsError{rc};
+    float ms = 0.0f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / reps;
+    // instrumented launches (exp_mode bit 16): cycle counters of CTA 0's last launch
+    if (instr_out) for (int i = 0; i < 10; ++i) instr_out[i] = h->diag_host[4 + i];
+  } catch (...) { cleanup(); throw; }
+  cleanup();
+  API_END
+}
+
 // Filter gradient of one convolution through the production kernels (unit tests)
 extern "C" int drs_debug_wgrad(drs_handle_t h, const float* x_host, const float* dy_host, int32_t B, int32_t crop, int32_t k,
                                int32_t rate, int32_t Ci, int32_t Co, int32_t precision, float* dw_host) {

@@ -11,6 +11,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp (the canonical way to issue warp-level TMA / tcgen05 instructions: ptxas knows
+// that exactly one thread is active behind this predicate).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -43,14 +55,19 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// Bounded wait: a pipeline bug must not hang the GPU box.  After ~2 s the waiting thread records
-// where it was stuck in the (host-mapped) diagnostic words and traps.
+// Bounded wait: a pipeline bug must not hang the GPU box.  After DRS_MBAR_SPIN_LIMIT failed try_waits (each suspends
+// for a hardware-defined interval: seconds in total) the waiting thread records where it was stuck in the
+// (host-mapped) diagnostic words and traps.
+#ifndef DRS_MBAR_SPIN_LIMIT
+#define DRS_MBAR_SPIN_LIMIT (1u << 26)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* diag, uint32_t tag) {
   if (mbar_try_wait(bar, parity)) return;
-  uint64_t t0 = globaltimer_ns();
+  // The bound is a spin count, not a clock: ptxas if-converts a conditional %globaltimer read into an unconditional
+  // one, and that read (hundreds of ns) then sits in every iteration of the wait loop of the producer / MMA threads.
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 2000000000ull) {
+    if (++spins == DRS_MBAR_SPIN_LIMIT) {
       if (diag) {
         diag[0] = 0xDEAD0000u | tag;
         diag[1] = blockIdx.x;
@@ -61,6 +78,41 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volati
       __trap();
     }
   }
+}
+
+// address-based variants (shared-memory addresses kept as running 32-bit values in the issue loops)
+__device__ __forceinline__ uint32_t mbar_try_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t" DRS_MBAR_WAIT_OP
+      " p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity, volatile uint32_t* diag, uint32_t tag) {
+  if (mbar_try_wait_addr(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait_addr(bar, parity)) {
+    if (++spins == DRS_MBAR_SPIN_LIMIT) {
+      if (diag) {
+        diag[0] = 0xDEAD0000u | tag;
+        diag[1] = blockIdx.x;
+        diag[2] = bar;
+        diag[3] = parity;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_addr(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 
 // ---------------------------------------------------------------- TMA
@@ -82,6 +134,20 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap*
       "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_addr(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_addr(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c, int32_t w,
+                                                        int32_t h, int32_t n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int32_t c0, int32_t c1) {
@@ -122,6 +188,44 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 // mbarrier arrive when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// One K block = NMMA consecutive K=16 MMAs (descriptor address field += 2 per step: 32 bytes inside the swizzle span).
+// Descriptors are passed as 32-bit halves (a_lo / b_lo carry the address, `hi` is common to both operands); `acc` = 0
+// makes the first MMA overwrite the accumulator.
+template <int NMMA>
+__device__ __forceinline__ void umma_f16_kblock(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc);
+template <>
+__device__ __forceinline__ void umma_f16_kblock<4>(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, t;\n\t.reg .b64 da, db;\n\t.reg .b32 x, y;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.eq.b32 t, %5, %5;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "add.u32 x, %1, 2;\n\tadd.u32 y, %2, 2;\n\tmov.b64 da, {x, %3};\n\tmov.b64 db, {y, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, t;\n\t"
+      "add.u32 x, %1, 4;\n\tadd.u32 y, %2, 4;\n\tmov.b64 da, {x, %3};\n\tmov.b64 db, {y, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, t;\n\t"
+      "add.u32 x, %1, 6;\n\tadd.u32 y, %2, 6;\n\tmov.b64 da, {x, %3};\n\tmov.b64 db, {y, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, t;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void umma_f16_kblock<2>(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, t;\n\t.reg .b64 da, db;\n\t.reg .b32 x, y;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.eq.b32 t, %5, %5;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "add.u32 x, %1, 2;\n\tadd.u32 y, %2, 2;\n\tmov.b64 da, {x, %3};\n\tmov.b64 db, {y, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, t;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+      : "memory");
 }
 // 32 lanes x 32 columns of fp32: thread `lane` receives row (taddr.lane + lane), columns [col, col+32)
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {

@@ -95,8 +95,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (convergent warp, elected lane
+    // issues: see conv_tc.cuh)
+    {
+      const bool leader = ptx::elect_one_sync();
       int stage = 0;
       uint32_t phase = 0;
       const int cc = p.crop * p.crop;
@@ -114,27 +116,34 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.diag, 0x500 + stage);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + a_bytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-          for (int t = 0; t < p.T; ++t) {
-#pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
-              int rb = (tile0 + t) * 2 + hb;
-              if (rb >= p.n_rb) rb = p.n_rb - 1;          // padding block of an odd last tile: rows are discarded
-              const int tap = rb / cb_per_tap, cb = rb - tap * cb_per_tap;
-              const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-              ptx::tma_load_im2col_4d(sa + (t * 2 + hb) * RB_BYTES, &tmX, &full_bar[stage], p.in_coff + cb * 64, px - p.pad_b,
-                                      py - p.pad_b, n_img, static_cast<uint16_t>(kx * p.rate), static_cast<uint16_t>(ky * p.rate));
+          if (leader) {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+            int rb = tile0 * 2;
+            int tap = rb / cb_per_tap, cb = rb - tap * cb_per_tap;
+            int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+            for (int i = 0; i < 2 * p.T; ++i) {
+              // (the padding block of an odd last tile repeats the last row block: its rows are discarded)
+              ptx::tma_load_im2col_4d(sa + i * RB_BYTES, &tmX, &full_bar[stage], p.in_coff + cb * 64, px - p.pad_b, py - p.pad_b,
+                                      n_img, static_cast<uint16_t>(kx * p.rate), static_cast<uint16_t>(ky * p.rate));
+              if (rb + 1 < p.n_rb) {
+                ++rb;
+                if (++cb == cb_per_tap) {
+                  cb = 0;
+                  if (++kx == p.ksize) { kx = 0; ++ky; }
+                }
+              }
             }
+            for (int nb = 0; nb < nb_boxes; ++nb)
+              ptx::tma_load_2d(sb + nb * RB_BYTES, &tmDY, &full_bar[stage], p.dy_coff + nb * 64, m0);
           }
-          for (int nb = 0; nb < nb_boxes; ++nb)
-            ptx::tma_load_2d(sb + nb * RB_BYTES, &tmDY, &full_bar[stage], p.dy_coff + nb * 64, m0);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (convergent warp, elected lane issues)
+    {
+      const bool leader = ptx::elect_one_sync();
       int stage = 0;
       uint32_t phase = 0, aphase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -150,20 +159,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const uint32_t sb = sa + a_bytes;
           // MN-major, 128B swizzle: LBO = distance between 64-element M/N blocks, SBO = 8 K-rows (1024 B)
           const uint64_t bdesc = ptx::make_smem_desc(sb, RB_BYTES, 1024, 2u);
-          for (int t = 0; t < p.T; ++t) {
-            const uint64_t adesc = ptx::make_smem_desc(sa + t * 2 * RB_BYTES, RB_BYTES, 1024, 2u);
-            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(t * p.acc_stride);
+          if (leader) {
+            for (int t = 0; t < p.T; ++t) {
+              const uint64_t adesc = ptx::make_smem_desc(sa + t * 2 * RB_BYTES, RB_BYTES, 1024, 2u);
+              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(t * p.acc_stride);
 #pragma unroll
-            for (int j = 0; j < WG_BPX / 16; ++j) {
-              // 16 pixels = 2048 bytes along K: +128 in the (>>4) start-address field
-              ptx::umma_f16(d_tmem, adesc + static_cast<uint64_t>(j * 128), bdesc + static_cast<uint64_t>(j * 128), p.idesc,
-                            static_cast<uint32_t>((q != q0) || (j != 0)));
+              for (int j = 0; j < WG_BPX / 16; ++j) {
+                // 16 pixels = 2048 bytes along K: +128 in the (>>4) start-address field
+                ptx::umma_f16(d_tmem, adesc + static_cast<uint64_t>(j * 128), bdesc + static_cast<uint64_t>(j * 128), p.idesc,
+                              static_cast<uint32_t>((q != q0) || (j != 0)));
+              }
             }
+            ptx::umma_commit(&empty_bar[stage]);
           }
-          ptx::umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(tmem_full);
+        if (leader) ptx::umma_commit(tmem_full);
         aphase ^= 1;
         (void)g;
       }

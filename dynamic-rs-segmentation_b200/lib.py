@@ -76,6 +76,8 @@ _SIGNATURES = {
     "drs_debug_activation": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
     "drs_debug_conv": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int32, _P]),
+    "drs_bench_conv": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, C.POINTER(C.c_float), _P]),
     "drs_debug_wgrad": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
 }
 EXPORTS = sorted(_SIGNATURES)
@@ -93,6 +95,8 @@ def load():
                        "there is no CPU fallback" % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
+        if "DRS_LIB" in os.environ and not hasattr(lib, name):
+            continue                 # A/B runs against an older build (tools/ab_lib.py)
         fn = getattr(lib, name)      # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args

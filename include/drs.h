@@ -207,6 +207,15 @@ int drs_debug_conv(drs_handle_t h, const float* x_host, const float* w_host, con
                    const float* shift_host, int32_t B, int32_t crop, int32_t k, int32_t rate, int32_t Ci, int32_t Co,
                    int32_t act, int32_t precision, float* y_host);
 
+/* kernel micro-benchmark: average milliseconds of `reps` launches of one tcgen05 convolution (the kernel behind
+ * _conv_layer, isprs:700-723) on pseudo-random resident operands; exp_mode >= 0 selects a DRS_EXP_MODE timing
+ * experiment (outputs are then meaningless), -1 the production kernel.  exp_mode bit 16 runs the instrumented twin of
+ * the kernel; instr_out (10 words, may be NULL) then receives CTA 0's cycle counters: producer {total, waiting for a
+ * free slot, stages, expect_tx issue, TMA issue}, MMA issuer {total, waiting for operands, MMA issue, commit issue,
+ * waiting for an accumulator}. */
+int drs_bench_conv(drs_handle_t h, int32_t B, int32_t crop, int32_t k, int32_t rate, int32_t Ci, int32_t Co,
+                   int32_t precision, int32_t exp_mode, int32_t reps, float* ms_out, uint32_t* instr_out);
+
 /* unit-test entry: filter gradient of one dilated SAME convolution (the wgrad inside isprs:1687 minimize):
  *   x [B,crop,crop,Ci], dy [B,crop,crop,Co] fp32 host -> dw [k,k,Ci,Co] fp32 host.
  *   precision BF16: tcgen05 MN-major path (operands rounded to bf16); FP32: CUDA-core fixed-order path. */
