@@ -210,13 +210,15 @@ __global__ void __launch_bounds__(RP_COLS * RP_LANES)
 reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S) {
   __shared__ float4 s_acc[RP_LANES][RP_COLS];
   const int tx = threadIdx.x % RP_COLS, ty = threadIdx.x / RP_COLS;
-  if ((n & 3) != 0) {                                  // tiny scalar case
-    const int64_t i = (int64_t)blockIdx.x * (RP_COLS * RP_LANES) + threadIdx.x;
-    if (i < n) {
-      float a = 0.0f;
-      for (int k = 0; k < S; ++k) a += part[(int64_t)k * n + i];
-      out[i] = a;
-    }
+  if ((n & 3) != 0) {                                  // tiny scalar case: one warp per column, fixed shuffle tree
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * RP_LANES + (threadIdx.x >> 5);
+    float a = 0.0f;
+    if (i < n)
+      for (int k = lane; k < S; k += 32) a += part[(int64_t)k * n + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (i < n && lane == 0) out[i] = a;
     return;
   }
   const int64_t i4 = ((int64_t)blockIdx.x * RP_COLS + tx) * 4;
@@ -240,7 +242,7 @@ reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, 
   }
 }
 static inline unsigned reduce_partials_grid(int64_t n) {
-  return (unsigned)((n & 3) ? ceil_div(n, RP_COLS * RP_LANES) : ceil_div(n, 4 * RP_COLS));
+  return (unsigned)((n & 3) ? ceil_div(n, RP_LANES) : ceil_div(n, 4 * RP_COLS));
 }
 
 template <typename TIn, typename TG>

@@ -33,7 +33,7 @@ static size_t train_workspace_bytes(Handle* h, int B, int crop, size_t es) {
   add(M * maxc * es * 2);                     // G ping-pong / dense dgrad temp
   add(M * K * 4 * 2);                         // logits, dlogits
   add(M * 2);                                 // labels u8, pred
-  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 2);
+  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 64), (int64_t)h->sm_count * 8);   // 8 blocks of 256 threads per SM
   const int bn_rows = (int)ceil_div(M, nb_bn);
   add((size_t)nb_bn * 2 * 256 * 4);
   const int nb_ce = (int)ceil_div(M, CE_THREADS);
@@ -65,7 +65,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   // ---------------------------------------------------------------- workspace (sized by train_workspace_bytes)
   int maxc = n.cls_in;
   for (auto& c : n.convs) maxc = std::max(maxc, std::max(c.co, c.ci));
-  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 2);
+  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 64), (int64_t)h->sm_count * 8);   // 8 blocks of 256 threads per SM
   const int bn_rows = (int)ceil_div(M, nb_bn);
   const int nb_ce = (int)ceil_div(M, CE_THREADS);
   const int nb_cls = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 4);

@@ -424,8 +424,13 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
 #pragma unroll
       for (int e = 0; e < 8; ++e) { mu[e] = mean[cg * 8 + e]; is[e] = inv_std[cg * 8 + e]; }
     }
-    for (int64_t m = r0 + rl; m < r1; m += lanes_r) {
+    // two rows per iteration: both pairs of 16-byte loads are in flight before the first is consumed
+    for (int64_t m = r0 + rl; m < r1; m += 2 * lanes_r) {
+      const int64_t m2 = m + lanes_r;
+      const bool two = m2 < r1;
       const Vec8<TZ> zv = *reinterpret_cast<const Vec8<TZ>*>(z + m * z_cs + z_co + cg * 8);
+      Vec8<TZ> zw = zv;
+      if (two) zw = *reinterpret_cast<const Vec8<TZ>*>(z + m2 * z_cs + z_co + cg * 8);
       if (MODE == 0) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -433,8 +438,18 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
           s0[e] += f;
           s1[e] = fmaf(f, f, s1[e]);
         }
+        if (two) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float f = to_f32(zw.v[e]);
+            s0[e] += f;
+            s1[e] = fmaf(f, f, s1[e]);
+          }
+        }
       } else {
         const Vec8<TG> gv = *reinterpret_cast<const Vec8<TG>*>(dA + m * g_cs + g_co + cg * 8);
+        Vec8<TG> gw = gv;
+        if (two) gw = *reinterpret_cast<const Vec8<TG>*>(dA + m2 * g_cs + g_co + cg * 8);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float xh = (to_f32(zv.v[e]) - mu[e]) * is[e];
@@ -443,6 +458,17 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
           else if (act == ACT_LRELU) g = xh > 0.0f ? g : 0.1f * g;
           s0[e] += g;
           s1[e] = fmaf(g, xh, s1[e]);
+        }
+        if (two) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float xh = (to_f32(zw.v[e]) - mu[e]) * is[e];
+            float g = to_f32(gw.v[e]);
+            if (act == ACT_RELU) g = xh > 0.0f ? g : 0.0f;
+            else if (act == ACT_LRELU) g = xh > 0.0f ? g : 0.1f * g;
+            s0[e] += g;
+            s1[e] = fmaf(g, xh, s1[e]);
+          }
         }
       }
     }
