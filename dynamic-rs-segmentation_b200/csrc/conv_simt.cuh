@@ -266,6 +266,109 @@ static void launch_wgrad_simt(Handle* h, const TIn* in, int in_cstride, int in_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// conv1 filter gradient (5x5, rate 1, Ci = C <= 8 image channels, Co = 64; isprs:767 / 1687): K = 25*C rows only, so the
+// generic tiled kernel above runs at a few % of anything.  Here a CTA owns (image, band of rows): the band of the fp32
+// input patch with its 2-pixel zero halo sits in shared memory, thread = (output channel, tap group of <= 7 taps) keeps
+// 7 x C accumulators in registers and walks the band's pixels: one dZ load and 7 broadcast LDS.128 per pixel.
+// Partials part[cta][tap*C + c][co] are reduced in CTA order by reduce_partials_kernel (deterministic).
+// ------------------------------------------------------------------------------------------------
+template <typename TG, int CP>
+__global__ void __launch_bounds__(256)
+wgrad_conv1_kernel(const float* __restrict__ x, int C, const TG* __restrict__ dy, int dy_cs, int dy_co, float* __restrict__ part,
+                   int crop, int bands, int rows_per_band) {
+  extern __shared__ __align__(16) float xs[];          // [(rows + 4)][crop + 4][CP]
+  const int img = blockIdx.x / bands, band = blockIdx.x - img * bands;
+  const int y0 = band * rows_per_band, y1 = min(crop, y0 + rows_per_band);
+  const int W = crop + 4;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (y1 - y0 + 4) * W; i += 256) {
+    const int ry = i / W, rx = i - ry * W;
+    const int gy = y0 - 2 + ry, gx = rx - 2;
+    const bool in = gy >= 0 && gy < crop && gx >= 0 && gx < crop;
+    const float* src = x + ((int64_t)(img * crop + gy) * crop + gx) * C;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) xs[i * CP + c] = (in && c < C) ? src[c] : 0.0f;
+  }
+  __syncthreads();
+  const int co = tid & 63, tg = tid >> 6;
+  int off[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int tap = min(tg + 4 * j, 24);
+    off[j] = ((tap / 5) * W + (tap % 5)) * CP;
+  }
+  float acc[7][CP];
+#pragma unroll
+  for (int j = 0; j < 7; ++j)
+#pragma unroll
+    for (int c = 0; c < CP; ++c) acc[j][c] = 0.0f;
+  for (int y = y0; y < y1; ++y) {
+    const TG* dyp = dy + (int64_t)(img * crop + y) * crop * dy_cs + dy_co + co;
+    const float* row = xs + (y - y0) * W * CP;
+#pragma unroll 2
+    for (int xx = 0; xx < crop; ++xx) {
+      const float dz = to_f32(dyp[(int64_t)xx * dy_cs]);
+      const float* p = row + xx * CP;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+#pragma unroll
+        for (int q = 0; q < CP / 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(p + off[j] + 4 * q);
+          acc[j][4 * q + 0] = fmaf(v.x, dz, acc[j][4 * q + 0]);
+          acc[j][4 * q + 1] = fmaf(v.y, dz, acc[j][4 * q + 1]);
+          acc[j][4 * q + 2] = fmaf(v.z, dz, acc[j][4 * q + 2]);
+          acc[j][4 * q + 3] = fmaf(v.w, dz, acc[j][4 * q + 3]);
+        }
+      }
+    }
+  }
+  float* dst = part + (int64_t)blockIdx.x * 25 * C * 64;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int tap = tg + 4 * j;
+    if (tap < 25) {
+#pragma unroll
+      for (int c = 0; c < CP; ++c)
+        if (c < C) dst[(tap * C + c) * 64 + co] = acc[j][c];
+    }
+  }
+}
+
+// returns false when the shape is not the conv1 shape (caller falls back to the generic kernel)
+template <typename TG>
+static bool launch_wgrad_conv1(Handle* h, const float* x, int C, const TG* dy, int dy_cs, int dy_co, int co, float* dw, float* part,
+                               size_t part_capacity, int B, int crop, int k, int rate) {
+  if (k != 5 || rate != 1 || co != 64 || C < 1 || C > 8) return false;
+  const int CP = C <= 4 ? 4 : 8;
+  int bands = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div((int64_t)h->sm_count * 2, B)), std::max(1, crop / 4));
+  int rows = (int)ceil_div(crop, bands);
+  bands = (int)ceil_div(crop, rows);
+  const int64_t n = (int64_t)25 * C * 64;
+  while (bands > 1 && (size_t)B * bands * n > part_capacity) {
+    rows *= 2;
+    bands = (int)ceil_div(crop, rows);
+  }
+  if ((size_t)B * bands * n > part_capacity) return false;
+  const size_t smem = (size_t)(rows + 4) * (crop + 4) * CP * 4;
+  if (smem > 200 * 1024) return false;
+  if (CP == 4) {
+    auto kern = wgrad_conv1_kernel<TG, 4>;
+    static size_t attr4 = 0;
+    if (smem > 48 * 1024 && smem > attr4) { CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr4 = 200 * 1024; }
+    kern<<<B * bands, 256, smem, h->stream>>>(x, C, dy, dy_cs, dy_co, part, crop, bands, rows);
+  } else {
+    auto kern = wgrad_conv1_kernel<TG, 8>;
+    static size_t attr8 = 0;
+    if (smem > 48 * 1024 && smem > attr8) { CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr8 = 200 * 1024; }
+    kern<<<B * bands, 256, smem, h->stream>>>(x, C, dy, dy_cs, dy_co, part, crop, bands, rows);
+  }
+  LAUNCH_CHECK(h);
+  reduce_partials_kernel<<<reduce_partials_grid(n), RP_COLS * RP_LANES, 0, h->stream>>>(part, dw, n, B * bands);
+  LAUNCH_CHECK(h);
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight packing: master fp32 HWIO -> operand matrices
 // ------------------------------------------------------------------------------------------------
 // fprop operand  Wf[co][tap*ci + c] = W[tap][c][co]

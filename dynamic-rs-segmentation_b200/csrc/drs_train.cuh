@@ -33,7 +33,7 @@ static size_t train_workspace_bytes(Handle* h, int B, int crop, size_t es) {
   add(M * maxc * es * 2);                     // G ping-pong / dense dgrad temp
   add(M * K * 4 * 2);                         // logits, dlogits
   add(M * 2);                                 // labels u8, pred
-  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 64), (int64_t)h->sm_count * 8);   // 8 blocks of 256 threads per SM
+  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 2);   // one wave: 2 blocks of 256 threads per SM
   const int bn_rows = (int)ceil_div(M, nb_bn);
   add((size_t)nb_bn * 2 * 256 * 4);
   const int nb_ce = (int)ceil_div(M, CE_THREADS);
@@ -65,7 +65,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   // ---------------------------------------------------------------- workspace (sized by train_workspace_bytes)
   int maxc = n.cls_in;
   for (auto& c : n.convs) maxc = std::max(maxc, std::max(c.co, c.ci));
-  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 64), (int64_t)h->sm_count * 8);   // 8 blocks of 256 threads per SM
+  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 2);   // one wave: 2 blocks of 256 threads per SM
   const int bn_rows = (int)ceil_div(M, nb_bn);
   const int nb_ce = (int)ceil_div(M, CE_THREADS);
   const int nb_cls = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 4);
@@ -234,8 +234,13 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
       if (overlap) CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->ev_dz[l & 1], 0));
       if (l == 0) {
         // conv1: K = 25*C <= 125 rows only -> parallelism must come from many short pixel splits
-        const int conv1_splits = (int)std::min<int64_t>((int64_t)(max_w * max_splits) / ((int64_t)c.k * c.k * c.ci * c.co), 4 * h->sm_count);
-        launch_wgrad_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, DZ, c.co, 0, c.co, h->grads + c.w_off, part_w, conv1_splits, B, crop, c.k, c.rate, c.pad_b, 256);
+        // (fp32 mode keeps the generic kernel: its summation order is what the fp32 parity tests pin)
+        const bool fast1 = ElemTag<TA>::v != ET_F32 && !getenv("DRS_NO_WGRAD_CONV1") &&
+                           launch_wgrad_conv1<TA>(h, x_dev, n.channels, DZ, c.co, 0, c.co, h->grads + c.w_off, part_w, max_w * max_splits, B, crop, c.k, c.rate);
+        if (!fast1) {
+          const int conv1_splits = (int)std::min<int64_t>((int64_t)(max_w * max_splits) / ((int64_t)c.k * c.k * c.ci * c.co), 4 * h->sm_count);
+          launch_wgrad_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, DZ, c.co, 0, c.co, h->grads + c.w_off, part_w, conv1_splits, B, crop, c.k, c.rate, c.pad_b, 256);
+        }
       } else if (ElemTag<TA>::v == ET_BF16 && wgrad_tc_supported(c.ci, c.co)) {
         WgradTcArgs wa;
         wa.x = xin.p; wa.in_cstride = xin.cs; wa.in_coff = xin.co; wa.ci = c.ci;

@@ -406,11 +406,32 @@ constexpr int BN_THREADS = 256;
 // Thread = (channel group of 8, row lane): 16-byte loads, per-thread fp32 partials, then a fixed-order reduction over the
 // row lanes in shared memory.  The row -> (block, lane) assignment is static, so the result is run-to-run identical.
 template <typename TZ, typename TG, int MODE>
-__global__ void __launch_bounds__(BN_THREADS)
+__device__ __forceinline__ void bn_partial_row(const Vec8<TZ>& zv, const Vec8<TG>& gv, const float (&mu)[8], const float (&is)[8],
+                                               int act, float (&s0)[8], float (&s1)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (MODE == 0) {
+      const float f = to_f32(zv.v[e]);
+      s0[e] += f;
+      s1[e] = fmaf(f, f, s1[e]);
+    } else {
+      const float xh = (to_f32(zv.v[e]) - mu[e]) * is[e];
+      float g = to_f32(gv.v[e]);
+      if (act == ACT_RELU) g = xh > 0.0f ? g : 0.0f;
+      else if (act == ACT_LRELU) g = xh > 0.0f ? g : 0.1f * g;
+      s0[e] += g;
+      s1[e] = fmaf(g, xh, s1[e]);
+    }
+  }
+}
+
+constexpr int BN_UNROLL = 4;     // rows in flight per thread (8 x 16-byte loads in the backward mode)
+template <typename TZ, typename TG, int MODE>
+__global__ void __launch_bounds__(BN_THREADS, 2)
 bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __restrict__ dA, int g_cs, int g_co,
                   const float* __restrict__ mean, const float* __restrict__ inv_std, int act, float* __restrict__ part, int C,
                   int64_t M, int rows_per_block, BnFinish fin) {
-  __shared__ __align__(16) float s_red[BN_THREADS * 16];
+  __shared__ float s_red[16][BN_THREADS + 1];          // [which * 8 + e][thread]: conflict-free stores and column sums
   const int cv = C >> 3;
   const int lanes_r = BN_THREADS / cv;
   const int cg = threadIdx.x % cv, rl = threadIdx.x / cv;
@@ -424,70 +445,43 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
 #pragma unroll
       for (int e = 0; e < 8; ++e) { mu[e] = mean[cg * 8 + e]; is[e] = inv_std[cg * 8 + e]; }
     }
-    // two rows per iteration: both pairs of 16-byte loads are in flight before the first is consumed
-    for (int64_t m = r0 + rl; m < r1; m += 2 * lanes_r) {
-      const int64_t m2 = m + lanes_r;
-      const bool two = m2 < r1;
-      const Vec8<TZ> zv = *reinterpret_cast<const Vec8<TZ>*>(z + m * z_cs + z_co + cg * 8);
-      Vec8<TZ> zw = zv;
-      if (two) zw = *reinterpret_cast<const Vec8<TZ>*>(z + m2 * z_cs + z_co + cg * 8);
-      if (MODE == 0) {
+    const TZ* zp = z + z_co + cg * 8;
+    const TG* gp = MODE == 1 ? dA + g_co + cg * 8 : nullptr;
+    int64_t m = r0 + rl;
+    // BN_UNROLL rows per iteration: every load is issued before the first one is consumed
+    for (; m + (int64_t)(BN_UNROLL - 1) * lanes_r < r1; m += (int64_t)BN_UNROLL * lanes_r) {
+      Vec8<TZ> zv[BN_UNROLL];
+      Vec8<TG> gv[BN_UNROLL];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float f = to_f32(zv.v[e]);
-          s0[e] += f;
-          s1[e] = fmaf(f, f, s1[e]);
-        }
-        if (two) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float f = to_f32(zw.v[e]);
-            s0[e] += f;
-            s1[e] = fmaf(f, f, s1[e]);
-          }
-        }
-      } else {
-        const Vec8<TG> gv = *reinterpret_cast<const Vec8<TG>*>(dA + m * g_cs + g_co + cg * 8);
-        Vec8<TG> gw = gv;
-        if (two) gw = *reinterpret_cast<const Vec8<TG>*>(dA + m2 * g_cs + g_co + cg * 8);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float xh = (to_f32(zv.v[e]) - mu[e]) * is[e];
-          float g = to_f32(gv.v[e]);
-          if (act == ACT_RELU) g = xh > 0.0f ? g : 0.0f;
-          else if (act == ACT_LRELU) g = xh > 0.0f ? g : 0.1f * g;
-          s0[e] += g;
-          s1[e] = fmaf(g, xh, s1[e]);
-        }
-        if (two) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float xh = (to_f32(zw.v[e]) - mu[e]) * is[e];
-            float g = to_f32(gw.v[e]);
-            if (act == ACT_RELU) g = xh > 0.0f ? g : 0.0f;
-            else if (act == ACT_LRELU) g = xh > 0.0f ? g : 0.1f * g;
-            s0[e] += g;
-            s1[e] = fmaf(g, xh, s1[e]);
-          }
-        }
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        zv[u] = *reinterpret_cast<const Vec8<TZ>*>(zp + (m + (int64_t)u * lanes_r) * z_cs);
+        if (MODE == 1) gv[u] = *reinterpret_cast<const Vec8<TG>*>(gp + (m + (int64_t)u * lanes_r) * g_cs);
       }
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) bn_partial_row<TZ, TG, MODE>(zv[u], gv[u], mu, is, act, s0, s1);
+    }
+    for (; m < r1; m += lanes_r) {
+      const Vec8<TZ> zv = *reinterpret_cast<const Vec8<TZ>*>(zp + m * z_cs);
+      Vec8<TG> gv;
+      if (MODE == 1) gv = *reinterpret_cast<const Vec8<TG>*>(gp + m * g_cs);
+      bn_partial_row<TZ, TG, MODE>(zv, gv, mu, is, act, s0, s1);
     }
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    s_red[threadIdx.x * 16 + e] = s0[e];
-    s_red[threadIdx.x * 16 + 8 + e] = s1[e];
+    s_red[e][threadIdx.x] = s0[e];
+    s_red[8 + e][threadIdx.x] = s1[e];
   }
   __syncthreads();
   // Block partial (fixed order) -> 64-bit fixed point -> integer atomicAdd: integer addition is associative, so the grid-wide
   // sum does not depend on the order in which blocks arrive (deterministic without a serial reduction pass).
   for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) {
-    const int which = i / C, c = i - which * C;
-    const int g = c >> 3, e = c & 7;
+    const int which = i / C, rem = i - which * C;
+    const int e = rem / cv, g = rem - e * cv;            // consecutive threads -> consecutive channel groups (no conflicts)
     float a = 0.0f;
-    for (int r = 0; r < lanes_r; ++r) a += s_red[(r * cv + g) * 16 + which * 8 + e];
+    for (int r = 0; r < lanes_r; ++r) a += s_red[which * 8 + e][r * cv + g];
     const long long q = __double2ll_rn((double)a * fin.fx_scale);
-    atomicAdd(reinterpret_cast<unsigned long long*>(fin.acc) + i, static_cast<unsigned long long>(q));
+    atomicAdd(reinterpret_cast<unsigned long long*>(fin.acc) + which * C + g * 8 + e, static_cast<unsigned long long>(q));
   }
   // ---- the last block to finish converts the sums, finalizes and clears the accumulators for the next launch
   __shared__ bool s_last;
@@ -580,10 +574,20 @@ bn_bwd_apply_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __re
     m0[e] = (float)((double)sums[c] * inv_count);
     m1[e] = (float)((double)sums[C + c] * inv_count);
   }
-  for (int64_t m = (int64_t)blockIdx.x * lanes_r + rl; m < M; m += (int64_t)gridDim.x * lanes_r) {
+  // two rows per iteration (four 16-byte loads in flight per thread)
+  const int64_t step = (int64_t)gridDim.x * lanes_r;
+  for (int64_t m = (int64_t)blockIdx.x * lanes_r + rl; m < M; m += 2 * step) {
+    const int64_t m2 = m + step;
+    const bool two = m2 < M;
     const Vec8<TZ> zv = *reinterpret_cast<const Vec8<TZ>*>(z + m * z_cs + z_co + cg * 8);
     const Vec8<TG> gv = *reinterpret_cast<const Vec8<TG>*>(dA + m * g_cs + g_co + cg * 8);
-    Vec8<TG> o;
+    Vec8<TZ> zw = zv;
+    Vec8<TG> gw = gv;
+    if (two) {
+      zw = *reinterpret_cast<const Vec8<TZ>*>(z + m2 * z_cs + z_co + cg * 8);
+      gw = *reinterpret_cast<const Vec8<TG>*>(dA + m2 * g_cs + g_co + cg * 8);
+    }
+    Vec8<TG> o, o2;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float xh = (to_f32(zv.v[e]) - mu[e]) * is[e];
@@ -591,8 +595,14 @@ bn_bwd_apply_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __re
       if (act == ACT_RELU) g = xh > 0.0f ? g : 0.0f;
       else if (act == ACT_LRELU) g = xh > 0.0f ? g : 0.1f * g;
       o.v[e] = from_f32<TG>(is[e] * (g - m0[e] - xh * m1[e]));
+      const float xh2 = (to_f32(zw.v[e]) - mu[e]) * is[e];
+      float g2 = to_f32(gw.v[e]);
+      if (act == ACT_RELU) g2 = xh2 > 0.0f ? g2 : 0.0f;
+      else if (act == ACT_LRELU) g2 = xh2 > 0.0f ? g2 : 0.1f * g2;
+      o2.v[e] = from_f32<TG>(is[e] * (g2 - m0[e] - xh2 * m1[e]));
     }
     *reinterpret_cast<Vec8<TG>*>(dZ + m * d_cs + d_co + cg * 8) = o;
+    if (two) *reinterpret_cast<Vec8<TG>*>(dZ + m2 * d_cs + d_co + cg * 8) = o2;
   }
 }
 

@@ -12,6 +12,10 @@ LAYERS = [("conv2", 5, 1, 64, 64), ("conv3", 4, 2, 64, 128), ("conv4", 4, 2, 128
           ("conv6", 3, 3, 192, 192), ("conv7", 3, 4, 192, 256), ("conv8", 3, 4, 256, 256)]
 
 
+DENSE = [("d2", 5, 1, 32, 32), ("d3", 4, 2, 64, 64), ("d4", 4, 2, 128, 64), ("d5", 3, 3, 192, 128), ("d6", 3, 3, 320, 128),
+         ("g6", 3, 3, 128, 320), ("g5", 3, 3, 128, 192), ("g4", 4, 2, 64, 128), ("g3", 4, 2, 64, 64), ("g2", 5, 1, 32, 32)]
+
+
 def word(spec):
     """'-1' production default; otherwise tokens m<mode> k<K blocks per stage> i1 (instrumented), e.g. k2 or k2m10i1."""
     import re
@@ -41,6 +45,8 @@ def main():
             prec = "bf16"
         elif a == "--reps":
             reps = int(args.pop(0))
+        elif a == "--dense":
+            LAYERS[:] = DENSE
         elif a == "--layers":
             only = args.pop(0).split(",")
     B = max(1, pixels // (crop * crop))
