@@ -153,7 +153,11 @@ class TrainHost:
         inst[:, 1] = np.minimum(sel[:, 1], hw[:, 0] - int(crop))
         inst[:, 2] = np.minimum(sel[:, 2], hw[:, 1] - int(crop))
         flips = self.rs_flips.randint(0, 3, size=len(batch)).astype(np.uint8)  # isprs:304 flip decision per patch
-        return int(crop), idx, inst, flips
+        # isprs:289-296 rotation decision per patch; the nearest-neighbour rotation itself runs in the gather kernel
+        rot_on = self.rs_flips.randint(0, 2, size=len(batch)).astype(np.uint8)
+        rot = host.rotation_table(int(crop))[sel[:, 3] % 360]
+        self.angles = sel[:, 3] % 360
+        return int(crop), idx, inst, flips, rot, rot_on
 
     def update(self, idx, loss, cm):
         acc_norm = self.host.acc_norm_from_cm(cm, self.cfg["K"])
@@ -199,12 +203,16 @@ def run_train_ours(args, rank, world, local):
     y = torch.empty(B * cmax * cmax, dtype=torch.float32, device=dev)
     pred = torch.empty(B * cmax * cmax, dtype=torch.uint8, device=dev)
     cm_dev = torch.zeros(cfg["K"] ** 2 + 1, dtype=torch.int32, device=dev)
+    amask = torch.empty(B * cmax * cmax, dtype=torch.uint8, device=dev)
+    from drs_b200 import host as _host
+    for c in range(cfg["values"][0], cfg["values"][-1] + 1):
+        _host.rotation_table(c)                          # affine maps of the 360 angles per patch size of the interval
 
     def step():
-        crop, idx, inst, flips = th.next_plan()
+        crop, idx, inst, flips, rot, rot_on = th.next_plan()
         sl = slice(rank * B, (rank + 1) * B)
-        s.gather_dev(inst[sl], flips[sl], crop, x, y)
-        loss = s.train_step_dev(x, y, B, crop, pred_dev=pred, cm_dev=cm_dev)
+        s.gather_rot_dev(inst[sl], flips[sl], crop, x, y, rot=rot[sl], rot_on=rot_on[sl], amask_out_dev=amask)
+        loss = s.train_step_dev(x, y, B, crop, pred_dev=pred, cm_dev=cm_dev, acc_mask_dev=amask)
         cm = cm_dev.cpu().numpy()[:cfg["K"] ** 2].reshape(cfg["K"], cfg["K"])
         th.update(idx, float(loss), cm)
         return crop
@@ -308,7 +316,8 @@ def run_train_ours(args, rank, world, local):
                         "patch_sizes_drawn": crops, "parallelism": "dp%d" % world, "sync_bn": False,
                         "l2": "per-step working set (activations %.0f-%.0f MB) exceeds the 126 MB L2; no explicit flush" %
                               (B * 25 * 25 * 896 * 6 / 1e6, B * 49 * 49 * 896 * 6 / 1e6),
-                        "augment": "flips on GPU; rotation/noise (host, SURVEY N1) not in the timed step"})
+                        "augment": "flips and nearest-neighbour rotation (scipy order 0, SURVEY N1) in the gather kernel, decisions drawn on the "
+                                   "host; the additive np.random.normal noise (host RNG stream) is not in the timed step"})
 
 
 def run_infer_ours(args, rank, world, local, steps=1):
@@ -405,8 +414,16 @@ def cpu_train_baseline(steps, warmup, budget_s=25.0):
     orc = nets_torch.OracleNet(cfg["net"], cfg["C"], cfg["K"], nets_torch.init_params(cfg["net"], cfg["C"], cfg["K"], seed=5))
 
     def step():
-        crop, idx, inst, flips = th.next_plan()
-        xs, ys = host_np.apply_plan([img], [lab], inst, flips, crop, mean, std)
+        crop, idx, inst, flips, _, rot_on = th.next_plan()
+        # the reference's own rotation (isprs:294-296) for the patches the plan rotates
+        import scipy.ndimage
+        over_x = np.zeros((B, crop, crop, cfg["C"]), dtype=np.float64)
+        over_y = np.zeros((B, crop, crop), dtype=np.uint8)
+        for b in np.nonzero(rot_on)[0]:
+            r, c = int(inst[b, 1]), int(inst[b, 2])
+            over_x[b] = scipy.ndimage.rotate(img[r:r + crop, c:c + crop], int(th.angles[b]), order=0, reshape=False)
+            over_y[b] = scipy.ndimage.rotate(lab[r:r + crop, c:c + crop], int(th.angles[b]), order=0, reshape=False)
+        xs, ys = host_np.apply_plan([img], [lab], inst, flips, crop, mean, std, None, None, over_x, over_y, rot_on)
         loss, pred, _ = orc.train_step(torch.from_numpy(xs.reshape(B, -1)), torch.from_numpy(ys.reshape(B, -1)), crop,
                                        cfg["lr"], cfg["wd"])
         acc, acc_norm, cm = host_np.confusion_by_crop(ys.astype(np.int64), pred.numpy(), cfg["K"])

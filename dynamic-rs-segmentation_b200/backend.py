@@ -23,12 +23,15 @@ class GpuBackend:
         self.K = session.num_classes
         self.C = session.channels
         self.shapes = []
+        self.has_labels = label_maps is not None
         for i, sc in enumerate(scenes):
             lab = None if label_maps is None else label_maps[i]
             session.upload_scene(i, np.ascontiguousarray(sc), lab)
             self.shapes.append(sc.shape[:2])
         session.set_normalization(mean_full, std_full)
         self._x = self._y = self._pred = self._mask = None
+        self._amask_on_dev = False
+        self.rotate_on_device = True      # isprs rotation augmentation in the gather kernel (plan_isprs_batch flag)
         self._cm = torch.zeros(self.K * self.K + 1, dtype=torch.int32, device=self.dev)
         session.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
 
@@ -63,8 +66,15 @@ class GpuBackend:
         if scene_offset:
             inst = inst.copy()
             inst[:, 0] += scene_offset
-        self.s.gather_dev(inst, plan.flips, crop, x, y, noise=plan.noise, noise_on=plan.noise_on,
-                          over_x=plan.over_x, over_y=plan.over_y, over_on=plan.over_on)
+        self._amask_on_dev = False
+        if getattr(plan, "rot", None) is not None:
+            # rotation on the device: the kernel also writes the accuracy mask
+            self.s.gather_rot_dev(inst, plan.flips, crop, x, y, noise=plan.noise, noise_on=plan.noise_on, rot=plan.rot,
+                                  rot_on=plan.rot_on, amask_out_dev=self._amask)
+            self._amask_on_dev = True
+        else:
+            self.s.gather_dev(inst, plan.flips, crop, x, y, noise=plan.noise, noise_on=plan.noise_on,
+                              over_x=plan.over_x, over_y=plan.over_y, over_on=plan.over_on)
         return x, y, pred, B, crop
 
     def train_on_plan(self, plan, loss_mask=None):
@@ -83,7 +93,7 @@ class GpuBackend:
         elif loss_mask is not None:
             self._mask[:n].copy_(t.from_numpy(np.ascontiguousarray(loss_mask, dtype=np.uint8).reshape(-1)))
             mask_dev = self._mask
-        amask_dev = None
+        amask_dev = self._amask if self._amask_on_dev else None
         if plan.acc_mask is not None:
             self._amask[:n].copy_(t.from_numpy(np.ascontiguousarray(plan.acc_mask, dtype=np.uint8).reshape(-1)))
             amask_dev = self._amask
@@ -109,6 +119,14 @@ class GpuBackend:
         r0, r1 = ddist.stripe_bounds(H, self.world, self.rank)
         stripe = self.s.scene_infer(scene_id, crop, batch, H, W, variant=variant, row_begin=r0, row_end=r1)
         return ddist.gather_label_stripes(stripe, H, W, self.rank, self.world, device=self.dev, all_ranks=True)
+
+    def scene_confusion(self, scene_id, num_classes, ignore_label=None):
+        """Confusion counts of the label map scene_labels() just produced against the resident ground truth, on the device
+        (isprs:1289-1296).  None when the ground truth is not resident or the map is striped over ranks (host path then)."""
+        if not self.has_labels or self.world != 1:
+            return None
+        cm, _ = self.s.scene_confusion(scene_id, num_classes, ignore_label)
+        return cm.astype(np.uint32)
 
     def save(self, path):
         self.s.save(path)

@@ -34,6 +34,9 @@ static void build_net(NetDesc& n, const drs_config& cfg) {
   static const ConvSpec d6p[] = {{5, 1, 64}, {5, 2, 64}, {4, 3, 128}, {4, 4, 128}, {3, 5, 256}, {3, 6, 256}};
   static const ConvSpec dd6[] = {{5, 1, 32}, {5, 2, 32}, {4, 3, 64}, {4, 4, 64}, {3, 5, 128}, {3, 6, 128}};
   static const ConvSpec d8p[] = {{5, 1, 64}, {5, 2, 64}, {4, 3, 128}, {4, 4, 128}, {3, 5, 192}, {3, 6, 192}, {3, 7, 256}, {3, 8, 256}};
+  static const ConvSpec r6[] = {{5, 1, 64}, {5, 2, 64}, {4, 3, 128}, {4, 4, 128}, {3, 5, 256}, {3, 6, 256}};
+  static const ConvSpec r6s[] = {{5, 1, 64}, {5, 2, 64}, {4, 3, 64}, {4, 4, 128}, {3, 5, 128}, {3, 6, 128}};
+  static const ConvSpec r6n[] = {{5, 1, 64}, {5, 1, 64}, {4, 1, 128}, {4, 1, 128}, {3, 1, 256}, {3, 1, 256}};
   const ConvSpec* sp = nullptr;
   int L = 0;
   n.net_type = cfg.net_type;
@@ -46,6 +49,9 @@ static void build_net(NetDesc& n, const drs_config& cfg) {
     case DRS_NET_DILATED6_POOLING: sp = d6p; L = 6; n.act = ACT_LRELU; n.pool = true; break;
     case DRS_NET_DENSE_DILATED6: sp = dd6; L = 6; n.act = ACT_RELU; n.dense = true; break;
     case DRS_NET_DILATED8_POOLING: sp = d8p; L = 8; n.act = ACT_LRELU; n.pool = true; break;
+    case DRS_NET_RATE6: sp = r6; L = 6; n.act = ACT_RELU; break;
+    case DRS_NET_RATE6_SMALL: sp = r6s; L = 6; n.act = ACT_RELU; break;
+    case DRS_NET_RATE6_NODILATION: sp = r6n; L = 6; n.act = ACT_RELU; break;
     default: DRS_FAIL("Error! Net type not identified: %d", cfg.net_type);
   }
   DRS_CHECK(cfg.channels >= 1 && cfg.channels <= 16, "channels=%d out of range", cfg.channels);
@@ -113,6 +119,8 @@ struct TrainGraph {
 struct HandleExtra {
   // persistent scene-pass buffers (score map, occurrence counts, cell tables, label map ...): cudaMalloc / cudaFree of
   // gigabyte-sized buffers per call costs hundreds of milliseconds, so each named slot only ever grows
+  // the label map of the last scene pass stays in slot 4 for drs_scene_confusion
+  int last_scene = -1, last_row_begin = 0, last_rows = 0, last_W = 0;
   void* slot_ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t slot_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::map<TrainGraphKey, TrainGraph> graphs;

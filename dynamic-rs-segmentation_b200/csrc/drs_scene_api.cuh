@@ -93,10 +93,10 @@ static void launch_gather(Handle* h, GatherParams gp, const GatherInline* il = n
   LAUNCH_CHECK(h);
 }
 
-extern "C" int drs_gather_dev(drs_handle_t h, const int32_t* inst_host, const uint8_t* flips_host, int32_t B, int32_t crop,
-                              const double* noise_host, const uint8_t* noise_on_host, const double* over_x_host,
-                              const uint8_t* over_y_host, const uint8_t* over_on_host, float* x_out_dev, float* y_out_dev) {
-  API_BEGIN
+static void gather_dev_impl(drs_handle_t h, const int32_t* inst_host, const uint8_t* flips_host, int32_t B, int32_t crop,
+                            const double* noise_host, const uint8_t* noise_on_host, const double* over_x_host,
+                            const uint8_t* over_y_host, const uint8_t* over_on_host, const double* rot_host,
+                            const uint8_t* rot_on_host, float* x_out_dev, float* y_out_dev, uint8_t* amask_out_dev) {
   DRS_CHECK(h && inst_host && x_out_dev, "null argument");
   CUDA_CHECK(cudaSetDevice(h->cfg.device));
   const int C = h->net.channels;
@@ -113,7 +113,7 @@ extern "C" int drs_gather_dev(drs_handle_t h, const int32_t* inst_host, const ui
               "gather: rows [%d,%d) of scene %d are not resident (uploaded rows [%d,%d))", r, r + crop, sid, it->second.row0,
               it->second.row0 + it->second.rows);
   }
-  const bool plain = !(noise_host && noise_on_host) && !(over_x_host && over_on_host);
+  const bool plain = !(noise_host && noise_on_host) && !(over_x_host && over_on_host) && !(rot_host && rot_on_host);
   if (plain && B <= GATHER_INLINE_MAX) {
     // common case (no host-made noise / rotation overrides): everything travels in the kernel parameters
     GatherInline il;
@@ -124,12 +124,13 @@ extern "C" int drs_gather_dev(drs_handle_t h, const int32_t* inst_host, const ui
     memset(&gp, 0, sizeof(gp));
     gp.x_out = x_out_dev;
     gp.y_out = y_out_dev;
+    gp.amask_out = amask_out_dev;
     gp.B = B;
     gp.crop = crop;
     launch_gather(h, gp, &il);
-    return 0;
+    return;
   }
-  size_t need = round_up((size_t)B * 3 * 4, 256) + 3 * round_up((size_t)B, 256);
+  size_t need = round_up((size_t)B * 3 * 4, 256) + 4 * round_up((size_t)B, 256) + round_up((size_t)B * 48, 256);
   if (noise_host) need += round_up((size_t)pp * C * 8, 256);
   if (over_x_host) need += round_up((size_t)pp * C * 8, 256) + round_up((size_t)pp, 256);
   ensure_dstage(h, need + 1024);
@@ -153,13 +154,35 @@ extern "C" int drs_gather_dev(drs_handle_t h, const int32_t* inst_host, const ui
     gp.over_x = (const double*)put(over_x_host, (size_t)pp * C * 8);
     if (over_y_host) gp.over_y = (const uint8_t*)put(over_y_host, (size_t)pp);
   }
+  if (rot_host && rot_on_host) {
+    gp.rot_on = (const uint8_t*)put(rot_on_host, B);
+    gp.rot = (const double*)put(rot_host, (size_t)B * 48);
+  }
   gp.x_out = x_out_dev;
   gp.y_out = y_out_dev;
+  gp.amask_out = amask_out_dev;
   gp.B = B;
   gp.crop = crop;
   launch_gather(h, gp);
   // the staging buffer is reused by the next call: the copies above must have been consumed
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
+extern "C" int drs_gather_dev(drs_handle_t h, const int32_t* inst_host, const uint8_t* flips_host, int32_t B, int32_t crop,
+                              const double* noise_host, const uint8_t* noise_on_host, const double* over_x_host,
+                              const uint8_t* over_y_host, const uint8_t* over_on_host, float* x_out_dev, float* y_out_dev) {
+  API_BEGIN
+  gather_dev_impl(h, inst_host, flips_host, B, crop, noise_host, noise_on_host, over_x_host, over_y_host, over_on_host, nullptr,
+                  nullptr, x_out_dev, y_out_dev, nullptr);
+  API_END
+}
+
+extern "C" int drs_gather_rot_dev(drs_handle_t h, const int32_t* inst_host, const uint8_t* flips_host, int32_t B, int32_t crop,
+                                  const double* noise_host, const uint8_t* noise_on_host, const double* rot_host,
+                                  const uint8_t* rot_on_host, float* x_out_dev, float* y_out_dev, uint8_t* amask_out_dev) {
+  API_BEGIN
+  gather_dev_impl(h, inst_host, flips_host, B, crop, noise_host, noise_on_host, nullptr, nullptr, nullptr, rot_host, rot_on_host,
+                  x_out_dev, y_out_dev, amask_out_dev);
   API_END
 }
 
@@ -399,8 +422,36 @@ extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, i
       CUDA_CHECK(cudaEventRecord(L.acc_done, main_stream));
     }
     scene_pass_finish(h, sp, rows, W, K, labels_out_host, mean_out_host);
+    hx->last_scene = scene_id; hx->last_row_begin = row_begin; hx->last_rows = rows; hx->last_W = W;
   } catch (...) { cleanup(); throw; }
   cleanup();
+  API_END
+}
+
+// Scene-level confusion matrix (isprs:1289-1296, contest:944-951): the label map of the last drs_scene_infer pass over
+// `scene_id` (still resident) against the ground truth uploaded with the scene; pixels whose truth is `ignore_label`
+// (the eroded class 6 of isprs, the unlabelled class 7 of the contest) or >= K are skipped.
+extern "C" int drs_scene_confusion(drs_handle_t h, int32_t scene_id, int32_t K, int32_t ignore_label, uint32_t* cm_out_host) {
+  API_BEGIN
+  DRS_CHECK(h && cm_out_host, "null argument");
+  DRS_CHECK(K >= 1 && K <= MAX_CLASSES, "K=%d out of range", K);
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  HandleExtra* x = X(h);
+  auto it = h->scenes.find(scene_id);
+  DRS_CHECK(it != h->scenes.end(), "scene_confusion: scene %d not uploaded", scene_id);
+  const Scene& sc = it->second;
+  DRS_CHECK(sc.labels, "scene_confusion: scene %d was uploaded without labels", scene_id);
+  DRS_CHECK(x->last_scene == scene_id && x->slot_ptr[4], "scene_confusion: no label map of scene %d is resident (run drs_scene_infer first)", scene_id);
+  DRS_CHECK(x->last_W == sc.W && x->last_row_begin >= sc.row0 && x->last_row_begin + x->last_rows <= sc.row0 + sc.rows,
+            "scene_confusion: label rows [%d,%d) outside the resident ground truth", x->last_row_begin, x->last_row_begin + x->last_rows);
+  const int64_t n = (int64_t)x->last_rows * sc.W;
+  const uint8_t* truth = sc.labels + (int64_t)(x->last_row_begin - sc.row0) * sc.W;
+  CUDA_CHECK(cudaMemsetAsync(x->cm_dev, 0, (K * K + 1) * 4, h->stream));
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(std::max<int64_t>(n, 1), 256), (int64_t)h->sm_count * 8);
+  confusion_kernel<<<blocks, 256, 0, h->stream>>>(truth, (const uint8_t*)x->slot_ptr[4], nullptr, n, K, ignore_label, x->cm_dev);
+  LAUNCH_CHECK(h);
+  CUDA_CHECK(cudaMemcpyAsync(cm_out_host, x->cm_dev, (K * K + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
   API_END
 }
 

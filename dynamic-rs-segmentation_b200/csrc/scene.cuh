@@ -33,6 +33,9 @@ struct GatherParams {
   const double* over_x;       // [B,c,c,C] patch replacing the scene crop (host-rotated), or null
   const uint8_t* over_y;      // [B,c,c]
   const uint8_t* over_on;     // [B] or null
+  const double* rot;          // [B,6] m00 m01 m10 m11 off0 off1 of scipy.ndimage.rotate's affine map (isprs:292-296), or null
+  const uint8_t* rot_on;      // [B] or null
+  uint8_t* amask_out;         // [B,c,c] accuracy mask (rotate(np.ones) then flip, isprs:287, 296, 308-317), or null
   float* x_out;               // [B,c,c,C]
   float* y_out;               // [B,c,c] or null
   int B, crop, C;
@@ -60,11 +63,29 @@ __global__ void gather_kernel(const __grid_constant__ SceneTable tab, const Gath
   const int sj = flip == 2 ? p.crop - 1 - j : j;    // np.fliplr (isprs:314-317)
   const SceneDesc& sc = tab.s[sid];
   const bool over = p.over_on && p.over_on[b];
+  // scipy.ndimage.rotate(order=0, reshape=False, mode='constant', cval=0): output (si, sj) <- input at
+  // floor(cc + 0.5), cc = (off + si*m_0) + sj*m_1 evaluated in this order in float64 (no contraction), and the
+  // constant 0 when cc < 0 or cc > crop - 1 on either axis.  Pinned against scipy for every integer angle.
+  int ri = si, rj = sj;
+  bool outside = false;
+  if (p.rot_on && p.rot_on[b]) {
+    const double* m = p.rot + (int64_t)b * 6;
+    const double c0 = __dadd_rn(__dadd_rn(m[4], __dmul_rn((double)si, m[0])), __dmul_rn((double)sj, m[1]));
+    const double c1 = __dadd_rn(__dadd_rn(m[5], __dmul_rn((double)si, m[2])), __dmul_rn((double)sj, m[3]));
+    const double hi = (double)(p.crop - 1);
+    outside = c0 < 0.0 || c0 > hi || c1 < 0.0 || c1 > hi;
+    if (!outside) {
+      ri = (int)floor(__dadd_rn(c0, 0.5));
+      rj = (int)floor(__dadd_rn(c1, 0.5));
+    }
+  }
   const int64_t pidx = (((int64_t)b * p.crop + si) * p.crop + sj);
-  const int64_t sidx = ((int64_t)(row0 + si - sc.row0) * sc.W + (col0 + sj));
+  const int64_t sidx = ((int64_t)(row0 + ri - sc.row0) * sc.W + (col0 + rj));
   float outv;
-  if (sc.dtype == DRS_SCENE_F64 || over) {
-    double v = over ? p.over_x[pidx * p.C + ch] : reinterpret_cast<const double*>(sc.data)[sidx * sc.C + ch];
+  if (sc.dtype == DRS_SCENE_F64 || over || (p.rot_on && p.rot_on[b])) {
+    double v = over ? p.over_x[pidx * p.C + ch]
+                    : (outside ? 0.0 : (sc.dtype == DRS_SCENE_F64 ? reinterpret_cast<const double*>(sc.data)[sidx * sc.C + ch]
+                                                                  : (double)reinterpret_cast<const float*>(sc.data)[sidx * sc.C + ch]));
     if (p.noise_on && p.noise_on[b]) v = v + p.noise[pidx * p.C + ch];    // isprs:301
     if (ch < 3) {                                                          // isprs:75-81 (channels 0..2 only)
       v = v - p.mean[ch];
@@ -90,9 +111,10 @@ __global__ void gather_kernel(const __grid_constant__ SceneTable tab, const Gath
   }
   p.x_out[gid] = outv;
   if (p.y_out && ch == 0) {
-    const uint8_t lab = over ? p.over_y[pidx] : (sc.labels ? sc.labels[sidx] : 0);
+    const uint8_t lab = over ? p.over_y[pidx] : ((sc.labels && !outside) ? sc.labels[sidx] : 0);
     p.y_out[((int64_t)b * p.crop + i) * p.crop + j] = (float)lab;
   }
+  if (p.amask_out && ch == 0) p.amask_out[((int64_t)b * p.crop + i) * p.crop + j] = outside ? 0 : 1;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -254,14 +254,46 @@ def dynamically_calculate_mean_and_std(data, indexes, crop_size):
 # ------------------------------------------------------------------------------------------------
 class BatchPlan:
     """What ``dynamically_create_patches`` decided for one batch; consumed by Session.gather_dev."""
-    __slots__ = ("inst", "flips", "noise", "noise_on", "over_x", "over_y", "over_on", "acc_mask", "crop")
+    __slots__ = ("inst", "flips", "noise", "noise_on", "over_x", "over_y", "over_on", "acc_mask", "crop", "rot", "rot_on")
+
+    def __init__(self):
+        self.rot = self.rot_on = None
 
 
-def plan_isprs_batch(data, mask_data, training_instances_batch, crop_size, is_train=True):
+def rotate_affine(angle, crop_size):
+    """The affine map scipy.ndimage.rotate(x, angle, reshape=False) hands to its C loop for a crop x crop plane:
+    [m00, m01, m10, m11, off0, off1] (same functions, same operation order as scipy's Python front end), consumed by the
+    gather kernel (drs_gather_rot_dev)."""
+    from scipy import special
+    c, s = special.cosdg(angle), special.sindg(angle)
+    m = np.array([[c, s], [-s, c]])
+    shp = np.asarray([crop_size, crop_size])
+    out_center = m @ ((shp - 1) / 2)
+    in_center = (shp - 1) / 2
+    off = in_center - out_center
+    return np.array([m[0, 0], m[0, 1], m[1, 0], m[1, 1], off[0], off[1]], dtype=np.float64)
+
+
+_ROT_TABLES = {}
+
+
+def rotation_table(crop_size):
+    """[360, 6] rotate_affine of every integer angle create_rotation_distribution can draw (isprs:489), built once per patch
+    size with the scalar code path above (so the values are the ones scipy itself would compute) and then only indexed."""
+    t = _ROT_TABLES.get(crop_size)
+    if t is None:
+        t = np.stack([rotate_affine(a, crop_size) for a in range(360)])
+        _ROT_TABLES[crop_size] = t
+    return t
+
+
+def plan_isprs_batch(data, mask_data, training_instances_batch, crop_size, is_train=True, rotate_on_device=False):
     """isprs:245-334.  Consumes np.random exactly like the reference, per patch:
     randint(0,2) rotate?  randint(0,2) noise? (+ normal(0,0.01,shape) if yes)  randint(0,3) flip.
-    Rotated patches (scipy nearest-neighbour, isprs:294-296) are produced here and handed to the gather as
-    overrides; every other patch is cut from the HBM-resident scene by the gather kernel."""
+    Rotated patches (scipy nearest-neighbour, isprs:294-296): with rotate_on_device the plan only carries the affine map
+    per patch and the gather kernel rotates patch, labels and accuracy mask (acc_mask stays None: it is produced on the
+    device); otherwise they are produced here with scipy and handed to the gather as overrides.  Every other patch is
+    cut from the HBM-resident scene by the gather kernel."""
     import scipy.ndimage
     B = len(training_instances_batch)
     C = data[0].shape[-1]
@@ -287,7 +319,14 @@ def plan_isprs_batch(data, mask_data, training_instances_batch, crop_size, is_tr
             continue
         cur_rot = training_instances_batch[i][3]
         possible_rotation = np.random.randint(0, 2)
-        if possible_rotation == 1:
+        if possible_rotation == 1 and rotate_on_device:
+            if p.rot is None:
+                p.rot = np.zeros((B, 6), dtype=np.float64)
+                p.rot_on = np.zeros(B, dtype=np.uint8)
+            a = int(cur_rot)
+            p.rot[i] = rotation_table(crop_size)[a] if (a == cur_rot and 0 <= a < 360) else rotate_affine(cur_rot, crop_size)
+            p.rot_on[i] = 1
+        elif possible_rotation == 1:
             if p.over_x is None:
                 p.over_x = np.zeros((B, crop_size, crop_size, C), dtype=np.float64)
                 p.over_y = np.zeros((B, crop_size, crop_size), dtype=np.uint8)

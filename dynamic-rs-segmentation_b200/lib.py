@@ -17,6 +17,9 @@ NET_TYPES = {
     "dilated_icpr_rate6_densely": 2,   # isprs:914
     "dilated_grsl_rate8": 3,           # isprs:996 (contest / coffee key)
     "dilated8_grsl": 3,                # isprs CLI key (isprs:1672-1673)
+    "dilated_icpr_rate6": 4,           # isprs:886
+    "dilated_icpr_rate6_small": 5,     # isprs:791
+    "dilated_icpr_rate6_nodilation": 6,  # isprs:852
 }
 PREC = {"fp32": 0, "f16": 1, "bf16": 2}
 SCENE_F64, SCENE_F32 = 0, 1
@@ -64,11 +67,13 @@ _SIGNATURES = {
     "drs_set_gather_fp16": (C.c_int, [_P, C.c_int32]),
     "drs_set_normalization": (C.c_int, [_P, _P, _P]),
     "drs_gather_dev": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    "drs_gather_rot_dev": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "drs_grid_positions": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64,
                                      C.POINTER(C.c_int64)]),
     "drs_accumulate_argmax": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "drs_scene_infer": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "drs_confusion_dev": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "drs_scene_confusion": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "drs_launch_count": (C.c_int64, [_P]),
     "drs_set_profiling": (C.c_int, [_P, C.c_int32]),
     "drs_profile_read": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),

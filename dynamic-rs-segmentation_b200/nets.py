@@ -1,4 +1,4 @@
-"""Network specifications of the four dilated FCNs and their variable initialisation.
+"""Network specifications of the dilated FCNs and their variable initialisation.
 
 Mirrors the reference's net builders (isprs_dilated_random.py:761-788, 914-959, 962-993, 996-1033)
 and ``_conv_layer`` defaults (isprs:700-723): xavier-uniform conv weights, conv biases 0.1, classifier
@@ -21,6 +21,13 @@ SPECS = {
     "dilated_grsl_rate8": dict(act="lrelu", pool=True, dense=False,
                                convs=[(5, 1, 64), (5, 2, 64), (4, 3, 128), (4, 4, 128), (3, 5, 192), (3, 6, 192),
                                       (3, 7, 256), (3, 8, 256)]),
+    # plain six-layer stacks: isprs:886-911, 791-816, 852-883
+    "dilated_icpr_rate6": dict(act="relu", pool=False, dense=False,
+                               convs=[(5, 1, 64), (5, 2, 64), (4, 3, 128), (4, 4, 128), (3, 5, 256), (3, 6, 256)]),
+    "dilated_icpr_rate6_small": dict(act="relu", pool=False, dense=False,
+                                     convs=[(5, 1, 64), (5, 2, 64), (4, 3, 64), (4, 4, 128), (3, 5, 128), (3, 6, 128)]),
+    "dilated_icpr_rate6_nodilation": dict(act="relu", pool=False, dense=False,
+                                          convs=[(5, 1, 64), (5, 1, 64), (4, 1, 128), (4, 1, 128), (3, 1, 256), (3, 1, 256)]),
 }
 SPECS["dilated8_grsl"] = SPECS["dilated_grsl_rate8"]
 NET_TYPES = tuple(SPECS)

@@ -258,6 +258,20 @@ class Session:
         L.check(self._lib.drs_gather_dev(self._h, L.ptr(inst), L.ptr(f), B, crop, L.ptr(nz), L.ptr(nzo), L.ptr(ox),
                                          L.ptr(oy), L.ptr(oo), L.ptr(x_out_dev), L.ptr(y_out_dev)))
 
+    def gather_rot_dev(self, inst, flips, crop, x_out_dev, y_out_dev=None, noise=None, noise_on=None, rot=None, rot_on=None,
+                       amask_out_dev=None):
+        """gather_dev with the nearest-neighbour rotation of isprs:287-296 done by the kernel (host.rotate_affine gives
+        the per-patch affine map); amask_out_dev receives the accuracy mask (rotate(np.ones) then flip)."""
+        inst = np.ascontiguousarray(np.asarray(inst, dtype=np.int32).reshape(-1, 3))
+        B = inst.shape[0]
+        f = None if flips is None else np.ascontiguousarray(np.asarray(flips, dtype=np.uint8))
+        nz = None if noise is None else np.ascontiguousarray(np.asarray(noise, dtype=np.float64))
+        nzo = None if noise_on is None else np.ascontiguousarray(np.asarray(noise_on, dtype=np.uint8))
+        r = None if rot is None else np.ascontiguousarray(np.asarray(rot, dtype=np.float64).reshape(B, 6))
+        ro = None if rot_on is None else np.ascontiguousarray(np.asarray(rot_on, dtype=np.uint8))
+        L.check(self._lib.drs_gather_rot_dev(self._h, L.ptr(inst), L.ptr(f), B, crop, L.ptr(nz), L.ptr(nzo), L.ptr(r), L.ptr(ro),
+                                             L.ptr(x_out_dev), L.ptr(y_out_dev), L.ptr(amask_out_dev)))
+
     def accumulate_argmax(self, logits_dev, positions, crop, H, W, want_mean=False):
         pos = np.ascontiguousarray(np.asarray(positions, dtype=np.int32).reshape(-1, 2))
         K = self.num_classes
@@ -276,6 +290,14 @@ class Session:
         L.check(self._lib.drs_scene_infer(self._h, scene_id, crop, batch, L.GRID[variant], row_begin, row_end,
                                           L.ptr(labels), L.ptr(mean)))
         return (labels, mean) if want_mean else labels
+
+    def scene_confusion(self, scene_id, num_classes, ignore_label=-1):
+        """K x K confusion counts [truth, pred] of the last scene_infer pass over scene_id against the labels uploaded with
+        the scene, computed on the device (isprs:1289-1296); also returns the number of correct pixels."""
+        cm = np.zeros(num_classes * num_classes + 1, dtype=np.uint32)
+        L.check(self._lib.drs_scene_confusion(self._h, int(scene_id), int(num_classes), -1 if ignore_label is None else int(ignore_label),
+                                              L.ptr(cm)))
+        return cm[:-1].reshape(num_classes, num_classes).astype(np.int64), int(cm[-1])
 
     def confusion_dev(self, truth_dev, pred_dev, n, mask_dev=None, ignore_label=-1):
         K = self.num_classes

@@ -33,7 +33,11 @@ enum drs_net_type {
   DRS_NET_DILATED6 = 0,          /* dilated_icpr_original      isprs:761-788  */
   DRS_NET_DILATED6_POOLING = 1,  /* dilated_grsl               isprs:962-993  */
   DRS_NET_DENSE_DILATED6 = 2,    /* dilated_icpr_rate6_densely isprs:914-959  */
-  DRS_NET_DILATED8_POOLING = 3   /* dilated_grsl_rate8 / dilated8_grsl isprs:996-1033 */
+  DRS_NET_DILATED8_POOLING = 3,  /* dilated_grsl_rate8 / dilated8_grsl isprs:996-1033 */
+  /* plain six-layer stacks of the same primitives */
+  DRS_NET_RATE6 = 4,             /* dilated_icpr_rate6            isprs:886-911  rates 1..6, ReLU, no pooling */
+  DRS_NET_RATE6_SMALL = 5,       /* dilated_icpr_rate6_small      isprs:791-816  64,64,64,128,128,128 */
+  DRS_NET_RATE6_NODILATION = 6   /* dilated_icpr_rate6_nodilation isprs:852-883  tf.nn.conv2d (rate 1) */
 };
 
 /* arithmetic of the convolution stack */
@@ -162,6 +166,17 @@ int drs_gather_dev(drs_handle_t h, const int32_t* inst_host, const uint8_t* flip
                    const double* noise_host, const uint8_t* noise_on_host, const double* over_x_host,
                    const uint8_t* over_y_host, const uint8_t* over_on_host, float* x_out_dev, float* y_out_dev);
 
+/* The same gather with the nearest-neighbour rotation of isprs:287-296 done on the device:
+ *   rot    [B,6] float64 per patch: m00 m01 m10 m11 off0 off1 of scipy.ndimage.rotate(angle, order=0, reshape=False)'s
+ *          affine map (built on the host exactly as scipy builds it: cosdg/sindg of the integer angle, centre offsets);
+ *          the kernel evaluates cc = (off + i*m_0) + j*m_1 in float64 in scipy's order, takes floor(cc + 0.5), and
+ *          writes the constant 0 (patch, label) where cc < 0 or cc > crop-1 -- bit-identical to scipy for all 360 angles.
+ *   rot_on [B] uint8, rotation applied where != 0 (before noise, normalisation and flip, as in the reference)
+ *   amask_out [B,crop,crop] uint8 device or NULL: rotate(np.ones) then flip = the mask calc_accuracy_by_crop receives. */
+int drs_gather_rot_dev(drs_handle_t h, const int32_t* inst_host, const uint8_t* flips_host, int32_t B, int32_t crop,
+                       const double* noise_host, const uint8_t* noise_on_host, const double* rot_host,
+                       const uint8_t* rot_on_host, float* x_out_dev, float* y_out_dev, uint8_t* amask_out_dev);
+
 /* create_patches_per_map index arithmetic (isprs:344-375, contest:267-301 incl. the offset_h bug, coffee:302-322):
  * (row, col) of every patch in visiting order, batch after batch.  Pure host code (no device needed).
  *   pos_out [cap_pairs,2] int32 or NULL (query the count through n_out). */
@@ -189,6 +204,12 @@ int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, int32_t batc
  *   cm_out [K*K+1] uint32 host: counts[true][pred] then #correct. */
 int drs_confusion_dev(drs_handle_t h, const uint8_t* truth_dev, const uint8_t* pred_dev, const uint8_t* mask_dev,
                       int64_t n, int32_t K, int32_t ignore_label, uint32_t* cm_out_host);
+
+/* Scene-level confusion matrix on the device (isprs:1289-1296, contest:944-951): the label map of
+ * the last drs_scene_infer pass over scene_id against the ground truth uploaded with that scene.  Pixels whose truth is
+ * ignore_label (isprs: eroded class 6, contest: unlabelled class 7; -1 = none) or >= K are skipped.
+ * cm_out_host: K*K counts [truth][pred] followed by the number of correct pixels. */
+int drs_scene_confusion(drs_handle_t h, int32_t scene_id, int32_t K, int32_t ignore_label, uint32_t* cm_out_host);
 
 /* ---- introspection for bench / tests ---------------------------------------------------- */
 /* number of kernels this library has launched since creation (bench.py "gpu_launches") */

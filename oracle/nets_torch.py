@@ -36,6 +36,13 @@ NET_SPECS = {
     "dilated_grsl_rate8": dict(act="lrelu", pool=True, dense=False, scope="conv",
                                convs=[(5, 1, 64), (5, 2, 64), (4, 3, 128), (4, 4, 128), (3, 5, 192), (3, 6, 192),
                                       (3, 7, 256), (3, 8, 256)]),
+    # isprs:886-911, 791-816, 852-883 (the last one calls tf.nn.conv2d: rate 1)
+    "dilated_icpr_rate6": dict(act="relu", pool=False, dense=False, scope="conv",
+                               convs=[(5, 1, 64), (5, 2, 64), (4, 3, 128), (4, 4, 128), (3, 5, 256), (3, 6, 256)]),
+    "dilated_icpr_rate6_small": dict(act="relu", pool=False, dense=False, scope="conv",
+                                     convs=[(5, 1, 64), (5, 2, 64), (4, 3, 64), (4, 4, 128), (3, 5, 128), (3, 6, 128)]),
+    "dilated_icpr_rate6_nodilation": dict(act="relu", pool=False, dense=False, scope="conv",
+                                          convs=[(5, 1, 64), (5, 1, 64), (4, 1, 128), (4, 1, 128), (3, 1, 256), (3, 1, 256)]),
 }
 NET_SPECS["dilated8_grsl"] = NET_SPECS["dilated_grsl_rate8"]   # isprs CLI key (isprs:1672-1673)
 

@@ -12,7 +12,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 NETS = (("dilated_icpr_original", 4, 6), ("dilated_grsl", 4, 6), ("dilated_icpr_rate6_densely", 5, 6),
-        ("dilated_grsl_rate8", 5, 6), ("dilated_grsl", 3, 7), ("dilated_icpr_original", 3, 2))
+        ("dilated_grsl_rate8", 5, 6), ("dilated_grsl", 3, 7), ("dilated_icpr_original", 3, 2),
+        ("dilated_icpr_rate6", 4, 6), ("dilated_icpr_rate6_small", 5, 6), ("dilated_icpr_rate6_nodilation", 4, 6))
 
 
 def torch_conv(x, w, rate):
@@ -191,6 +192,47 @@ def test_gather_kernel_bit_exact(drs, golden):
     s.close()
 
 
+def test_rotation_on_device_equals_scipy(drs, golden):
+    """scipy.ndimage.rotate(order=0, reshape=False) of patch, labels and accuracy mask inside the gather
+    kernel (drs_gather_rot_dev) -- bit-identical to the host-rotated overrides for the same RNG stream, every crop."""
+    import torch
+    from drs_b200 import host
+    scenes, labs = golden["gather_scenes"], golden["gather_labels"]
+    mean, std = golden["norm_mean"], golden["norm_std"]
+    s = drs.Session("dilated_grsl", 4, 6, precision="fp32")
+    for i in range(2):
+        s.upload_scene(i, scenes[i], labs[i])
+    s.set_normalization(mean, std)
+    rs = np.random.RandomState(5)
+    n_rot = 0
+    for crop in (9, 12, 25, 26, 31):
+        H, W = scenes[0].shape[:2]
+        B = 48
+        inst = [(int(rs.randint(0, 2)), int(rs.randint(0, H - crop + 1)), int(rs.randint(0, W - crop + 1)), int(rs.randint(0, 360)))
+                for _ in range(B)]
+        np.random.seed(300 + crop)
+        plan_h = host.plan_isprs_batch(scenes, labs, inst, crop, is_train=True)
+        np.random.seed(300 + crop)
+        plan_d = host.plan_isprs_batch(scenes, labs, inst, crop, is_train=True, rotate_on_device=True)
+        assert plan_d.over_x is None and plan_d.rot is not None and np.array_equal(plan_d.flips, plan_h.flips)
+        assert np.array_equal(plan_d.rot_on, plan_h.over_on)
+        n_rot += int(plan_d.rot_on.sum())
+        n = B * crop * crop
+        xh = torch.empty(n * 4, dtype=torch.float32, device="cuda")
+        yh = torch.empty(n, dtype=torch.float32, device="cuda")
+        xd, yd = torch.empty_like(xh), torch.empty_like(yh)
+        am = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
+        s.gather_dev(plan_h.inst, plan_h.flips, crop, xh, yh, noise=plan_h.noise, noise_on=plan_h.noise_on, over_x=plan_h.over_x,
+                     over_y=plan_h.over_y, over_on=plan_h.over_on)
+        s.gather_rot_dev(plan_d.inst, plan_d.flips, crop, xd, yd, noise=plan_d.noise, noise_on=plan_d.noise_on, rot=plan_d.rot,
+                         rot_on=plan_d.rot_on, amask_out_dev=am)
+        assert torch.equal(xh, xd)
+        assert torch.equal(yh, yd)
+        assert np.array_equal(am.cpu().numpy().reshape(B, crop, crop), plan_h.acc_mask)
+    assert n_rot > 50
+    s.close()
+
+
 ACC_CASES = (("isprs", 120, 150, 25, 16, 6), ("isprs", 97, 131, 33, 7, 6), ("contest", 130, 100, 25, 16, 7),
              ("contest", 100, 130, 25, 16, 7), ("coffee", 64, 64, 25, 16, 2), ("isprs", 100, 100, 50, 4, 6),
              ("isprs", 61, 90, 30, 5, 3), ("isprs", 25, 25, 25, 4, 6))
@@ -327,6 +369,29 @@ WGRAD_TC_CASES = [(2, 9, 3, 1, 64, 64), (3, 13, 5, 2, 64, 64), (2, 17, 4, 3, 64,
                   (1, 30, 3, 7, 192, 256), (4, 25, 3, 6, 320, 128), (16, 25, 5, 1, 64, 64), (64, 25, 3, 4, 256, 256)]
 
 
+def test_scene_confusion_on_device(drs):
+    """drs_scene_confusion (isprs:1289-1296): label map of the last scene pass vs the resident ground truth, with the
+    eroded / unlabelled class skipped -- equal to the host bincount."""
+    from drs_b200 import loops, synth
+    img, lab = synth.scene("vaihingen", H=150, W=170, block=16, unlabelled=True)
+    lab = lab.copy()
+    lab[::7, ::5] = 6                                   # eroded boundary pixels (isprs:1294)
+    with drs.Session("dilated_grsl", 4, 6, precision="f16", seed=3) as s:
+        mean, std = synth.normalisation(img)
+        s.set_normalization(mean, std)
+        s.upload_scene(0, img, lab)
+        pred = s.scene_infer(0, 25, 16, 150, 170)
+        cm, correct = s.scene_confusion(0, 6, 6)
+        ref = loops.confusion_counts(lab, pred, 7, None)[:6, :6]
+        assert np.array_equal(cm, ref.astype(np.int64))
+        assert correct == int(np.trace(ref))
+        # a stripe pass: only the stripe's rows are compared
+        pred2 = s.scene_infer(0, 25, 16, 150, 170, row_begin=40, row_end=101)
+        cm2, _ = s.scene_confusion(0, 6, 6)
+        ref2 = loops.confusion_counts(lab[40:101], pred2, 7, None)[:6, :6]
+        assert np.array_equal(cm2, ref2.astype(np.int64))
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_filter_gradient(drs, prec):
     """wgrad of one dilated convolution: CUDA-core fixed-order path and the tcgen05 MN-major path."""
@@ -345,7 +410,8 @@ def test_filter_gradient(drs, prec):
 
 
 TRAIN_NETS = (("dilated_icpr_original", 4, 6, False), ("dilated_grsl", 4, 6, False),
-              ("dilated_icpr_rate6_densely", 5, 6, False), ("dilated_grsl_rate8", 3, 7, True))
+              ("dilated_icpr_rate6_densely", 5, 6, False), ("dilated_grsl_rate8", 3, 7, True),
+              ("dilated_icpr_rate6_small", 4, 6, False))
 
 
 def _grad_report(orc, s):

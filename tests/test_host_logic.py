@@ -74,3 +74,23 @@ def test_acc_norm_from_confusion(golden, drs):
     assert host.acc_norm_from_cm(golden["cm_out"], 6) == golden["cm_acc"][1]
     assert host.acc_norm_from_cm(golden["cm_nomask_out"], 6) == golden["cm_nomask_acc"][1]
     assert host.sliding_stride(25) == 12 and host.sliding_stride(30) == 15
+
+
+def test_rotate_affine_reproduces_scipy_rotate():
+    """The index arithmetic the gather kernel uses for the isprs rotation augmentation, restated in NumPy:
+    cc = (off + i*m_0) + j*m_1 in float64, floor(cc + 0.5), constant 0 outside [0, crop-1] -- equal to
+    scipy.ndimage.rotate(order=0, reshape=False) for every integer angle the reference can draw (isprs:489)."""
+    import scipy.ndimage
+    from drs_b200 import host
+    rs = np.random.RandomState(0)
+    for crop in (25, 26, 37, 49):
+        patch = rs.rand(crop, crop, 2) + 1.0
+        ii, jj = np.meshgrid(np.arange(crop, dtype=np.float64), np.arange(crop, dtype=np.float64), indexing="ij")
+        for angle in range(0, 360, 1 if crop == 25 else 7):
+            m = host.rotate_affine(angle, crop)
+            c0 = (m[4] + ii * m[0]) + jj * m[1]
+            c1 = (m[5] + ii * m[2]) + jj * m[3]
+            ok = ~((c0 < 0) | (c0 > crop - 1) | (c1 < 0) | (c1 > crop - 1))
+            out = np.zeros_like(patch)
+            out[ok] = patch[np.floor(c0 + 0.5).astype(np.int64)[ok], np.floor(c1 + 0.5).astype(np.int64)[ok]]
+            assert np.array_equal(out, scipy.ndimage.rotate(patch, angle, order=0, reshape=False)), (crop, angle)
