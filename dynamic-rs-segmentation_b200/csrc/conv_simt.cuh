@@ -268,7 +268,7 @@ static void launch_wgrad_simt(Handle* h, const TIn* in, int in_cstride, int in_c
 // ------------------------------------------------------------------------------------------------
 // conv1 filter gradient (5x5, rate 1, Ci = C <= 8 image channels, Co = 64; isprs:767 / 1687): K = 25*C rows only, so the
 // generic tiled kernel above runs at a few % of anything.  Here a CTA owns (image, band of rows): the band of the fp32
-// input patch with its 2-pixel zero halo sits in shared memory, thread = (output channel, tap group of <= 7 taps) keeps
+// input patch with its 2-pixel zero halo and the band's dZ rows sit in shared memory, thread = (output channel, tap group of <= 7 taps) keeps
 // 7 x C accumulators in registers and walks the band's pixels: one dZ load and 7 broadcast LDS.128 per pixel.
 // Partials part[cta][tap*C + c][co] are reduced in CTA order by reduce_partials_kernel (deterministic).
 // ------------------------------------------------------------------------------------------------
@@ -289,6 +289,18 @@ wgrad_conv1_kernel(const float* __restrict__ x, int C, const TG* __restrict__ dy
 #pragma unroll
     for (int c = 0; c < CP; ++c) xs[i * CP + c] = (in && c < C) ? src[c] : 0.0f;
   }
+  // the band's dZ rows, staged with 16-byte loads (a per-pixel global load in the loop below would be latency-bound)
+  TG* dzs = reinterpret_cast<TG*>(xs + (size_t)(rows_per_band + 4) * W * CP);
+  {
+    constexpr int V = 16 / sizeof(TG);                 // elements per 16-byte vector
+    const int per_px = 64 / V;
+    const int npx = (y1 - y0) * crop;
+    const TG* src = dy + (int64_t)(img * crop + y0) * crop * dy_cs + dy_co;
+    for (int i = tid; i < npx * per_px; i += 256) {
+      const int px = i / per_px, v = i - px * per_px;
+      *reinterpret_cast<uint4*>(dzs + px * 64 + v * V) = *reinterpret_cast<const uint4*>(src + (int64_t)px * dy_cs + v * V);
+    }
+  }
   __syncthreads();
   const int co = tid & 63, tg = tid >> 6;
   int off[7];
@@ -303,11 +315,11 @@ wgrad_conv1_kernel(const float* __restrict__ x, int C, const TG* __restrict__ dy
 #pragma unroll
     for (int c = 0; c < CP; ++c) acc[j][c] = 0.0f;
   for (int y = y0; y < y1; ++y) {
-    const TG* dyp = dy + (int64_t)(img * crop + y) * crop * dy_cs + dy_co + co;
+    const TG* dyp = dzs + (y - y0) * crop * 64 + co;
     const float* row = xs + (y - y0) * W * CP;
 #pragma unroll 2
     for (int xx = 0; xx < crop; ++xx) {
-      const float dz = to_f32(dyp[(int64_t)xx * dy_cs]);
+      const float dz = to_f32(dyp[xx * 64]);
       const float* p = row + xx * CP;
 #pragma unroll
       for (int j = 0; j < 7; ++j) {
@@ -349,7 +361,7 @@ static bool launch_wgrad_conv1(Handle* h, const float* x, int C, const TG* dy, i
     bands = (int)ceil_div(crop, rows);
   }
   if ((size_t)B * bands * n > part_capacity) return false;
-  const size_t smem = (size_t)(rows + 4) * (crop + 4) * CP * 4;
+  const size_t smem = (size_t)(rows + 4) * (crop + 4) * CP * 4 + (size_t)rows * crop * 64 * sizeof(TG);
   if (smem > 200 * 1024) return false;
   if (CP == 4) {
     auto kern = wgrad_conv1_kernel<TG, 4>;
