@@ -120,6 +120,15 @@ class GpuBackend:
         stripe = self.s.scene_infer(scene_id, crop, batch, H, W, variant=variant, row_begin=r0, row_end=r1)
         return ddist.gather_label_stripes(stripe, H, W, self.rank, self.world, device=self.dev, all_ranks=True)
 
+    def scene_mean_logits(self, scene_id, crop, batch, variant="isprs"):
+        """``prob_im / occur_im`` (float64 [H,W,K]) of one sliding-window pass: the per-scale map of the multi-scale
+        evaluation (isprs:1380-1411)."""
+        H, W = self.shapes[scene_id]
+        if self.world != 1:
+            raise NotImplementedError("multi-scale evaluation runs on one rank")
+        _, mean = self.s.scene_infer(scene_id, crop, batch, H, W, variant=variant, want_mean=True)
+        return mean
+
     def scene_confusion(self, scene_id, num_classes, ignore_label=None):
         """Confusion counts of the label map scene_labels() just produced against the resident ground truth, on the device
         (isprs:1289-1296).  None when the ground truth is not resident or the map is striped over ranks (host path then)."""

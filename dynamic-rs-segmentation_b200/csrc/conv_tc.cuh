@@ -35,7 +35,9 @@ struct ConvTcParams {
   int num_tiles;      // ceil(M_total / 128)
   int stages;         // smem pipeline depth
   int kps;            // K blocks (BLOCK_K channels of one tap) per pipeline stage: one barrier round trip per kps blocks
-  int acc_stride;     // TMEM columns between the two accumulator stages
+  int dual;           // two MMA-issuing warps (Co <= 128): even / odd stages of a tile accumulate into two TMEM
+                      // accumulators that the epilogue adds (the issue loop, not the tensor pipe, bounds these layers)
+  int acc_stride;     // TMEM columns of one accumulator
   int tmem_cols;      // allocated TMEM columns (power of two >= 32)
   int act;
   int smem_needed;    // bytes used from the 1024B-aligned base
@@ -131,7 +133,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_full[s], p.dual ? 2 : 1);   // one commit per issuing warp
       ptx::mbar_init(&tmem_empty[s], 4);   // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
@@ -218,9 +220,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       p.diag[7] = static_cast<uint32_t>(t_exp);
       p.diag[8] = static_cast<uint32_t>(t_tma);
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (warp == 2 && p.dual)) {
     // ------------------------------------------------------------------ MMA issuer (convergent warp, elected lane issues)
+    // dual mode: warp 1 takes the even stages of every tile, warp 2 the odd ones, each into its own accumulator (the
+    // assignment depends on the stage index inside the tile only, so the summation order of a pixel never depends on
+    // where its tile runs: results stay batch-invariant and run-to-run identical)
     {
+      const int pipe = warp == 1 ? 0 : 1;
       const bool leader = ptx::elect_one_sync();
       uint32_t soff = 0, boff = 0, phase = 0;
       int as = 0;
@@ -239,22 +245,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           ptx::mbar_wait(&tmem_empty[as], aphase ^ 1, p.diag, 0x200 + as);
         }
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.acc_stride);
-        for (int kb0 = 0; kb0 < num_kb; kb0 += p.kps) {
-          const int nk = min(p.kps, num_kb - kb0);
-          long long t0 = 0, t1 = 0, t2 = 0;
-          if (INSTR) t0 = clock64();
-          ptx::mbar_wait_addr(full0 + boff, phase, p.diag, 0x300);
-          ptx::tcgen05_fence_after();
-          if (INSTR) { t1 = clock64(); t_wait += t1 - t0; }
-          if (leader && !no_mma) {
-            uint32_t a_lo = desc_lo0 + (soff >> 4);
-            for (int j = 0; j < nk; ++j, a_lo += kb_step)
-              ptx::umma_f16_kblock<BLOCK_K / 16>(d_tmem, a_lo, a_lo + (A_BYTES >> 4), desc_hi, p.idesc, (kb0 | j) != 0 ? 1u : 0u);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((p.dual ? as * 2 + pipe : as) * p.acc_stride);
+        uint32_t fresh = 0;                                  // 0 until this warp's first MMA of the tile (overwrites D)
+        int g = 0;
+        for (int kb0 = 0; kb0 < num_kb; kb0 += p.kps, ++g) {
+          if (!p.dual || (g & 1) == pipe) {
+            const int nk = min(p.kps, num_kb - kb0);
+            long long t0 = 0, t1 = 0, t2 = 0;
+            if (INSTR) t0 = clock64();
+            ptx::mbar_wait_addr(full0 + boff, phase, p.diag, 0x300);
+            ptx::tcgen05_fence_after();
+            if (INSTR) { t1 = clock64(); t_wait += t1 - t0; }
+            if (leader && !no_mma) {
+              uint32_t a_lo = desc_lo0 + (soff >> 4);
+              for (int j = 0; j < nk; ++j, a_lo += kb_step) {
+                ptx::umma_f16_kblock<BLOCK_K / 16>(d_tmem, a_lo, a_lo + (A_BYTES >> 4), desc_hi, p.idesc, fresh);
+                fresh = 1;
+              }
+            }
+            if (INSTR) { t2 = clock64(); t_mma += t2 - t1; }
+            if (leader) ptx::umma_commit_addr(empty0 + boff);   // frees the smem slot when these MMAs retire
+            if (INSTR) t_commit += clock64() - t2;
           }
-          if (INSTR) { t2 = clock64(); t_mma += t2 - t1; }
-          if (leader) ptx::umma_commit_addr(empty0 + boff);   // frees the smem slot when these MMAs retire
-          if (INSTR) t_commit += clock64() - t2;
           soff += stage_bytes;
           boff += 8;
           if (soff == ring_bytes) { soff = 0; boff = 0; phase ^= 1; }
@@ -262,7 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (leader) ptx::umma_commit(&tmem_full[as]);        // accumulator complete -> epilogue
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
-      if (INSTR && leader && blockIdx.x == 0 && p.diag) {
+      if (INSTR && pipe == 0 && leader && blockIdx.x == 0 && p.diag) {
         p.diag[9] = static_cast<uint32_t>(clock64() - t_begin);
         p.diag[10] = static_cast<uint32_t>(t_wait);
         p.diag[11] = static_cast<uint32_t>(t_mma);
@@ -286,12 +298,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       ptx::mbar_wait(&tmem_full[as], aphase, p.diag, 0x400 + as);
       ptx::tcgen05_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.acc_stride);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             static_cast<uint32_t>((p.dual ? as * 2 : as) * p.acc_stride);
       for (int ch = 0; ch < ((p.exp_mode == 4 || p.exp_mode == 10) ? 0 : n_chunks); ++ch) {
         uint32_t v[EPI_C];
         ptx::tmem_ld_32x32b_x32(t_row + ch * EPI_C, v);
         if (EPI_C == 64) ptx::tmem_ld_32x32b_x32(t_row + ch * EPI_C + 32, v + (EPI_C == 64 ? 32 : 0));
         ptx::tmem_wait_ld();
+        if (p.dual) {
+          // second accumulator (odd stages): even + odd, always in this order
+#pragma unroll
+          for (int hf = 0; hf < EPI_C / 32; ++hf) {
+            uint32_t w[32];
+            ptx::tmem_ld_32x32b_x32(t_row + p.acc_stride + ch * EPI_C + hf * 32, w);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[hf * 32 + i] = __float_as_uint(__uint_as_float(v[hf * 32 + i]) + __uint_as_float(w[i]));
+          }
+        }
         // the TMA store that last read staging buffer `sbuf` (two chunks ago) must have drained
         if (warp == 4 && ptx::elect_one_sync()) ptx::tma_store_wait_read<1>();
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -478,6 +502,12 @@ static void encode_im2col(Handle* h, CUtensorMap* tm, int etype, const void* bas
 }
 
 static int g_conv_exp_mode = -1;   // drs_bench_conv override of DRS_EXP_MODE
+#ifndef CONV_TC_DUAL_MAX_CO
+// Two MMA-issuing warps (experiment, OFF): after the issue-path fixes the Co <= 128 layers are bound by L2 -> SM operand
+// traffic (16-19 TB/s), so a second issuing warp buys 8 % on N=64 and nothing on N=128 (profiles/r1b_conv_dual_issuer.txt),
+// and a batch-64 DenseDilated6 training step dead-locked with it.  Reachable only through experiment bit 18.
+#define CONV_TC_DUAL_MAX_CO 0
+#endif
 #ifndef CONV_TC_KPS2_MAX_CO
 #define CONV_TC_KPS2_MAX_CO 128      // two K blocks per stage for Co <= this
 #endif
@@ -488,7 +518,7 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   const int64_t M = (int64_t)a.B * a.crop * a.crop;
   const int taps = a.k * a.k;
   const int sw_op = BLOCK_K * 2;
-  // experiment word: bits 0-7 timing mode, bits 8-11 pipeline variant + 1 (0 = default), bits 12-15 K blocks per stage (0 = default)
+  // experiment word: bits 0-7 timing mode, bits 12-15 K blocks per stage (0 = default), bit 16 instrumented twin, bit 18 dual MMA warps
   const int exp_word = g_conv_exp_mode >= 0 ? g_conv_exp_mode : (getenv("DRS_EXP_MODE") ? atoi(getenv("DRS_EXP_MODE")) : 0);
   const int exp_mode = exp_word & 0xff;
   const bool instr = ((exp_word >> 16) & 1) != 0;
@@ -513,7 +543,6 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   p.out_coff = a.out_coff;
   p.num_tiles = (int)ceil_div(M, CONV_TC_BM);
   p.acc_stride = a.co <= 32 ? 32 : a.co <= 64 ? 64 : a.co <= 128 ? 128 : 256;
-  p.tmem_cols = 2 * p.acc_stride;
   p.act = a.act;
   p.idesc = make_idesc_f16(128, a.co, a.etype == ET_BF16, a.etype == ET_BF16, 0, 0);
   p.scale = a.scale;
@@ -535,6 +564,9 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   DRS_CHECK(stages >= 2, "conv_tc: tile does not fit shared memory (co=%d)", a.co);
   p.stages = stages;
   p.kps = kps;
+  const int dual_max_co = ((exp_word >> 18) & 1) ? 128 : CONV_TC_DUAL_MAX_CO;   // experiment bit 18: dual MMA warps for Co <= 128
+  p.dual = (a.co <= dual_max_co && (taps_kb + kps - 1) / kps >= 2) ? 1 : 0;
+  p.tmem_cols = (p.dual ? 4 : 2) * p.acc_stride;
   p.smem_needed = fixed + stages * stage_bytes;
   const int smem_bytes = p.smem_needed + 1024 <= budget ? p.smem_needed + 1024 : budget;
   p.smem_provided = smem_bytes;

@@ -59,7 +59,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 // for a hardware-defined interval: seconds in total) the waiting thread records where it was stuck in the
 // (host-mapped) diagnostic words and traps.
 #ifndef DRS_MBAR_SPIN_LIMIT
-#define DRS_MBAR_SPIN_LIMIT (1u << 26)
+#define DRS_MBAR_SPIN_LIMIT (1u << 22)   // ~4 us per failed try_wait: traps after ~15 s
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* diag, uint32_t tag) {
   if (mbar_try_wait(bar, parity)) return;

@@ -392,6 +392,36 @@ def test_scene_confusion_on_device(drs):
         assert np.array_equal(cm2, ref2.astype(np.int64))
 
 
+def test_multiscale_evaluation_on_device(drs, tmp_path):
+    """isprs:1347-1474 through the GPU backend: per-scale mean-logit maps from scene passes (prob_im / occur_im, float64),
+    reference softmax, sum, argmax.  The composition equals the same formula applied to the oracle-checked mean maps, and
+    one scale reduces to the single-scale label map wherever the top-2 softmax margin is not a float32 tie."""
+    import io
+    from contextlib import redirect_stdout
+    from drs_b200 import backend, loops, synth
+    img, lab = synth.scene("vaihingen", H=110, W=130, block=16)
+    mean, std = synth.normalisation(img)
+    with drs.Session("dilated_grsl", 4, 6, precision="f16", seed=4) as s:
+        be = backend.GpuBackend(s, [img], [lab], mean, std)
+        out = str(tmp_path) + "/"
+        np.save(out + "patch_acc_loss_step_3.npy", np.array([2.0, 4.5, 3.0], dtype=np.float32))
+        np.save(out + "patch_occur_step_3.npy", np.array([4, 5, 5], dtype=np.int32))
+        values = np.array([25, 31, 40])
+        with redirect_stdout(io.StringIO()):
+            maps = loops.isprs_validate_test_multiscale(be, [img], [lab], ["1"], 16, 3, "multi_fixed", values.copy(), "acc", 2,
+                                                        False, out)
+        m31 = be.scene_mean_logits(0, 31, 16)
+        m40 = be.scene_mean_logits(0, 40, 16)
+        assert m31.dtype == np.float64 and m31.shape == (110, 130, 6)
+        ref = np.argmax(loops.reference_softmax(m31.astype(np.float32), 6) + loops.reference_softmax(m40.astype(np.float32), 6), axis=2)
+        assert np.array_equal(maps[0], ref)
+        with redirect_stdout(io.StringIO()):
+            one = loops.isprs_validate_test_multiscale(be, [img], [lab], ["1"], 16, 3, "multi_fixed", values.copy(), "acc", 1,
+                                                       False, out)
+        single = be.scene_labels(0, 31, 16)
+        assert (one[0] == single).mean() > 0.999
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_filter_gradient(drs, prec):
     """wgrad of one dilated convolution: CUDA-core fixed-order path and the tcgen05 MN-major path."""

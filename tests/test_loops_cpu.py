@@ -99,3 +99,39 @@ def test_metrics_from_confusion_match_sklearn():
     assert np.allclose(loops.f1_per_class_from_cm(cm), f1_score(t, p, average=None), atol=1e-12)
     cm_i = loops.confusion_counts(np.where(rs.rand(5000) < 0.1, 6, t), p, 7)[:6, :6]     # eroded label 6 dropped
     assert cm_i.sum() < 5000
+
+
+def test_multiscale_validation_reproduces_reference_label_maps(tmp_path):
+    """loops.isprs_validate_test_multiscale against the label maps the reference's own validate_test_multiscale
+    (isprs:1347-1474) produced through the closed-form fake sess.run (oracle/make_golden_multiscale.py)."""
+    from drs_b200 import loops
+    from oracle.fake_net import fake_logits
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "multiscale_golden.npz"))
+    img, lab, mean, std, values = g["ms_scene"], g["ms_gt"], g["ms_mean"], g["ms_std"], g["ms_values"]
+
+    class Backend:
+        crops = []
+
+        def scene_mean_logits(self, scene_id, crop, batch, variant="isprs"):
+            self.crops.append(crop)
+            h, w = img.shape[:2]
+            pos = host_np.all_patch_positions(h, w, crop, batch)
+            inst = np.array([[0, r, c] for r, c in pos], dtype=np.int32)
+            x, _ = host_np.apply_plan([img], [lab], inst, None, crop, mean, std, cast=False)
+            logits = fake_logits(x.reshape(len(inst), -1), crop, 4, 6)
+            _, m = host_np.accumulate_argmax(logits, pos, h, w, crop, return_mean=True)
+            return m
+
+    for ci in (0, 1):
+        out = str(tmp_path) + "/"
+        np.save(out + "patch_acc_loss_step_5.npy", g["ms_%d_pal" % ci])
+        np.save(out + "patch_occur_step_5.npy", g["ms_%d_occ" % ci])
+        be = Backend()
+        be.crops = []
+        with redirect_stdout(io.StringIO()):
+            maps = loops.isprs_validate_test_multiscale(be, [img], [lab], ["1"], 7, 5, "multi_fixed", values.copy(),
+                                                        str(g["ms_updates"][ci]), 3, False, out)
+        ref_crops = g["ms_%d_crops" % ci]
+        order = [int(c) for i, c in enumerate(ref_crops) if i == 0 or c != ref_crops[i - 1]]
+        assert be.crops == order
+        assert np.array_equal(maps[0].astype(np.uint8), g["ms_%d_labels" % ci])

@@ -17,14 +17,14 @@ DENSE = [("d2", 5, 1, 32, 32), ("d3", 4, 2, 64, 64), ("d4", 4, 2, 128, 64), ("d5
 
 
 def word(spec):
-    """'-1' production default; otherwise tokens m<mode> k<K blocks per stage> i1 (instrumented), e.g. k2 or k2m10i1."""
+    """'-1' production default; otherwise tokens m<mode> k<K blocks per stage> i1 (instrumented) s1 (dual MMA warps, experiment), e.g. k2 or k2m10i1."""
     import re
     if re.fullmatch(r"-?\d+", spec):
         return int(spec)
     w = 0
-    for key, val in re.findall(r"([mki])(\d+)", spec):
+    for key, val in re.findall(r"([mkis])(\d+)", spec):
         val = int(val)
-        w |= val if key == "m" else (val << 12 if key == "k" else (val & 1) << 16)
+        w |= val if key == "m" else (val << 12 if key == "k" else ((val & 1) << 16 if key == "i" else (val & 1) << 18))
     return w
 
 
@@ -62,7 +62,7 @@ def main():
             ins = (C.c_uint32 * 10)()
             L.check(lib.drs_bench_conv(s._h, B, crop, k, rate, ci, co, L.PREC[prec], m, reps, C.byref(ms), ins))
             fl = 2.0 * B * crop * crop * k * k * ci * co
-            tag = "prod" if m < 0 else "m%d%s" % (m & 0xff, "k%d" % ((m >> 12) & 0xf) if (m >> 12) & 0xf else "")
+            tag = "prod" if m < 0 else "m%d%s%s" % (m & 0xff, "k%d" % ((m >> 12) & 0xf) if (m >> 12) & 0xf else "", "dual" if (m >> 18) & 1 else "")
             txt = "%s %.0fus %.0fTF" % (tag, ms.value * 1e3, fl / ms.value / 1e9)
             if m >= 0 and (m >> 16) & 1:
                 v = list(ins)
