@@ -441,7 +441,7 @@ def cpu_train_baseline(steps, warmup, budget_s=25.0):
             break
     dt = time.perf_counter() - t0
     return dict(value=B * done / dt, unit="patches/s", cores=cores, kind="port", ms_per_step=dt / done * 1e3, steps=done,
-                sample="%d full steps (batch 64, crops %s) of the same seeded loop: NumPy gather+normalise, PyTorch-CPU fp32 graph "
+                sample="%d full steps (batch 64, crops %s) of the same seeded loop: NumPy gather + scipy order-0 rotation + normalise, PyTorch-CPU fp32 graph "
                        "fwd+bwd+momentum, Python-loop calc_accuracy_by_crop; TensorFlow not installable (SURVEY F13)" % (done, crops))
 
 
