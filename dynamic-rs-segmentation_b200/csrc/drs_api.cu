@@ -132,6 +132,9 @@ struct HandleExtra {
   double conv_ms_acc = 0;            // device time of profiled launches already read back
   InferLane lanes[2];             // scene-inference lanes (drs_scene_api.cuh)
   cudaEvent_t lanes_ready = nullptr;
+  // streamed scene upload (drs_scene_infer_host): copy stream + "rows uploaded" event
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t up_ev[1] = {nullptr};
   uint8_t* is_weight = nullptr;   // [n_trainable] 1 for `weights` variables
   SceneTable table;               // host copy of the device scene table
   // training scratch kept between calls
@@ -277,6 +280,8 @@ extern "C" int drs_destroy(drs_handle_t h) {
   HandleExtra* x = X(h);
   if (x) {
     if (x->side_stream) { cudaStreamSynchronize(x->side_stream); cudaStreamDestroy(x->side_stream); }
+    if (x->copy_stream) { cudaStreamSynchronize(x->copy_stream); cudaStreamDestroy(x->copy_stream); }
+    if (x->up_ev[0]) cudaEventDestroy(x->up_ev[0]);
     for (int i = 0; i < 2; ++i) {
       if (x->ev_dz[i]) cudaEventDestroy(x->ev_dz[i]);
       if (x->ev_wgrad[i]) cudaEventDestroy(x->ev_wgrad[i]);

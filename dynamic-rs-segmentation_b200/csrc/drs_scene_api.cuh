@@ -343,9 +343,79 @@ static void lanes_ensure(Handle* h, int n_lanes, size_t arena_bytes, size_t x_by
   }
 }
 
+// Streamed upload of a host scene during a scene pass: rows are copied on a separate stream, in ~8 MB pieces, just ahead of
+// the chunk that first reads them, so the host->device transfer of a fresh tile (1.44 GB for a Potsdam tile) overlaps the
+// convolutions instead of preceding them.
+struct HostSceneFeed {
+  const char* host = nullptr;    // [H,W,C] in the scene dtype, row-major
+  size_t row_bytes = 0;
+  int uploaded = 0;              // rows [0, uploaded) are enqueued
+};
+
+static void feed_rows(Handle* h, HostSceneFeed& f, const Scene& sc, int rows_needed, cudaStream_t consumer) {
+  HandleExtra* x = X(h);
+  if (rows_needed > sc.H) rows_needed = sc.H;
+  bool any = false;
+  const int rows_per_piece = (int)std::max<size_t>(1, ((size_t)8 << 20) / f.row_bytes);
+  while (f.uploaded < rows_needed) {
+    const int n = std::min(rows_per_piece, rows_needed - f.uploaded);
+    // Pageable source: the driver stages the piece itself (measured faster than a memcpy into our own pinned ring) and
+    // returns once the source has been read; kernels already queued keep the GPU busy meanwhile.
+    CUDA_CHECK(cudaMemcpyAsync((char*)sc.data + (size_t)f.uploaded * f.row_bytes, f.host + (size_t)f.uploaded * f.row_bytes,
+                               (size_t)n * f.row_bytes, cudaMemcpyHostToDevice, x->copy_stream));
+    f.uploaded += n;
+    any = true;
+  }
+  if (any) {
+    CUDA_CHECK(cudaEventRecord(x->up_ev[0], x->copy_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(consumer, x->up_ev[0], 0));   // copies on one stream complete in order
+  }
+}
+
+static void scene_infer_impl(drs_handle_t h, int32_t scene_id, int32_t crop, int32_t batch, int32_t variant, int32_t row_begin,
+                             int32_t row_end, uint8_t* labels_out_host, double* mean_out_host, HostSceneFeed* feed);
+
 extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, int32_t batch, int32_t variant, int32_t row_begin,
                                int32_t row_end, uint8_t* labels_out_host, double* mean_out_host) {
   API_BEGIN
+  scene_infer_impl(h, scene_id, crop, batch, variant, row_begin, row_end, labels_out_host, mean_out_host, nullptr);
+  API_END
+}
+
+extern "C" int drs_scene_infer_host(drs_handle_t h, int32_t scene_id, const void* scene_host, int32_t H, int32_t W, int32_t C,
+                                    int32_t dtype, int32_t crop, int32_t batch, int32_t variant, uint8_t* labels_out_host,
+                                    double* mean_out_host) {
+  API_BEGIN
+  DRS_CHECK(h && scene_host && labels_out_host, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  DRS_CHECK(scene_id >= 0 && scene_id < MAX_SCENES, "scene_id %d out of range [0,%d)", scene_id, MAX_SCENES);
+  DRS_CHECK(dtype == DRS_SCENE_F64 || dtype == DRS_SCENE_F32, "bad scene dtype %d", dtype);
+  DRS_CHECK(C == h->net.channels, "scene has %d channels, net expects %d", C, h->net.channels);
+  HandleExtra* x = X(h);
+  Scene& s = h->scenes[scene_id];
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  const size_t row_bytes = (size_t)W * C * (dtype == DRS_SCENE_F64 ? 8 : 4);
+  const size_t bytes = row_bytes * H;
+  if (s.data_cap < bytes) {
+    if (s.data) CUDA_CHECK(cudaFree(s.data));
+    s.data = nullptr; s.data_cap = 0;
+    CUDA_CHECK(cudaMalloc(&s.data, bytes));
+    s.data_cap = bytes;
+  }
+  if (s.labels) { CUDA_CHECK(cudaFree(s.labels)); s.labels = nullptr; s.labels_cap = 0; }
+  s.H = H; s.W = W; s.C = C; s.dtype = dtype; s.row0 = 0; s.rows = H;
+  x->table.s[scene_id] = SceneDesc{s.data, s.labels, H, W, C, dtype, 0, H};
+  if (!x->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&x->copy_stream, cudaStreamNonBlocking));
+  if (!x->up_ev[0]) CUDA_CHECK(cudaEventCreateWithFlags(&x->up_ev[0], cudaEventDisableTiming));
+  HostSceneFeed feed;
+  feed.host = (const char*)scene_host;
+  feed.row_bytes = row_bytes;
+  scene_infer_impl(h, scene_id, crop, batch, variant, 0, H, labels_out_host, mean_out_host, &feed);
+  API_END
+}
+
+static void scene_infer_impl(drs_handle_t h, int32_t scene_id, int32_t crop, int32_t batch, int32_t variant, int32_t row_begin,
+                             int32_t row_end, uint8_t* labels_out_host, double* mean_out_host, HostSceneFeed* feed) {
   DRS_CHECK(h && labels_out_host, "null argument");
   CUDA_CHECK(cudaSetDevice(h->cfg.device));
   auto it = h->scenes.find(scene_id);
@@ -406,6 +476,13 @@ extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, i
       h->stream = L.stream;
       h->arena = L.arena;
       if (ci >= n_lanes) CUDA_CHECK(cudaStreamWaitEvent(L.stream, L.acc_done, 0));   // logits buffer consumed
+      if (feed) {
+        // rows this chunk's patches read, plus one more chunk's worth so that the copy runs ahead of the compute
+        int need = 0;
+        const int s1 = std::min(P, s0 + 2 * chunk);
+        for (int s = s0; s < s1; ++s) need = std::max(need, pos[2 * s] + crop);
+        feed_rows(h, *feed, sc, need, L.stream);
+      }
       GatherParams gp;
       memset(&gp, 0, sizeof(gp));
       gp.inst = inst_dev + (size_t)s0 * 3;
@@ -423,9 +500,12 @@ extern "C" int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, i
     }
     scene_pass_finish(h, sp, rows, W, K, labels_out_host, mean_out_host);
     hx->last_scene = scene_id; hx->last_row_begin = row_begin; hx->last_rows = rows; hx->last_W = W;
+    if (feed) {                                      // rows no patch reads (none for the grids of the scripts) and the tail
+      feed_rows(h, *feed, sc, sc.H, main_stream);
+      CUDA_CHECK(cudaStreamSynchronize(hx->copy_stream));
+    }
   } catch (...) { cleanup(); throw; }
   cleanup();
-  API_END
 }
 
 // Scene-level confusion matrix (isprs:1289-1296, contest:944-951): the label map of the last drs_scene_infer pass over

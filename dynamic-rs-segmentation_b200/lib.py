@@ -73,6 +73,8 @@ _SIGNATURES = {
     "drs_accumulate_argmax": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "drs_scene_infer": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "drs_confusion_dev": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "drs_scene_infer_host": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_int32, _P, _P]),
     "drs_scene_confusion": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "drs_launch_count": (C.c_int64, [_P]),
     "drs_set_profiling": (C.c_int, [_P, C.c_int32]),

@@ -291,6 +291,23 @@ class Session:
                                           L.ptr(labels), L.ptr(mean)))
         return (labels, mean) if want_mean else labels
 
+    def scene_infer_host(self, scene_id, scene, crop, batch, variant="isprs", want_mean=False):
+        """scene_infer for a scene that is still a host array (a fresh tile): the upload is streamed just ahead of the
+        chunks that read it and overlaps the convolutions.  The scene stays resident as scene_id."""
+        scene = np.ascontiguousarray(scene)
+        if scene.dtype == np.float64:
+            dt = L.SCENE_F64
+        elif scene.dtype == np.float32:
+            dt = L.SCENE_F32
+        else:
+            raise ValueError("scene dtype must be float64 (isprs) or float32 (contest/coffee), got %s" % scene.dtype)
+        H, W, Cc = scene.shape
+        labels = np.empty((H, W), dtype=np.uint8)
+        mean = np.empty((H, W, self.num_classes), dtype=np.float64) if want_mean else None
+        L.check(self._lib.drs_scene_infer_host(self._h, scene_id, L.ptr(scene), H, W, Cc, dt, crop, batch, L.GRID[variant],
+                                               L.ptr(labels), L.ptr(mean)))
+        return (labels, mean) if want_mean else labels
+
     def scene_confusion(self, scene_id, num_classes, ignore_label=-1):
         """K x K confusion counts [truth, pred] of the last scene_infer pass over scene_id against the labels uploaded with
         the scene, computed on the device (isprs:1289-1296); also returns the number of correct pixels."""

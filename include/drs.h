@@ -199,6 +199,14 @@ int drs_accumulate_argmax(drs_handle_t h, const float* logits_dev, const int32_t
 int drs_scene_infer(drs_handle_t h, int32_t scene_id, int32_t crop, int32_t batch, int32_t variant,
                     int32_t row_begin, int32_t row_end, uint8_t* labels_out_host, double* mean_out_host);
 
+/* The same pass over a scene that is still in host memory (a fresh tile): scene rows are copied on a separate stream,
+ * in pieces, just ahead of the chunk that first reads them, so the upload (1.44 GB for a
+ * 6000x6000x5 float64 tile) overlaps the convolutions instead of preceding them.  Equivalent to drs_scene_upload (without
+ * labels) followed by drs_scene_infer over all rows; the scene stays resident as scene_id afterwards. */
+int drs_scene_infer_host(drs_handle_t h, int32_t scene_id, const void* scene_host, int32_t H, int32_t W, int32_t C,
+                         int32_t dtype, int32_t crop, int32_t batch, int32_t variant, uint8_t* labels_out_host,
+                         double* mean_out_host);
+
 /* calc_accuracy_by_crop (isprs:510-531) / per-pixel scene confusion (isprs:1289-1296, contest:944-948):
  *   truth, pred [n] uint8 device; mask [n] or NULL; ignore_label <0 = none.
  *   cm_out [K*K+1] uint32 host: counts[true][pred] then #correct. */

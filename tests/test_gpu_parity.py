@@ -392,6 +392,24 @@ def test_scene_confusion_on_device(drs):
         assert np.array_equal(cm2, ref2.astype(np.int64))
 
 
+def test_streamed_upload_scene_pass_equals_resident_pass(drs, monkeypatch):
+    """drs_scene_infer_host (rows copied on a second stream just ahead of the chunks that read them) gives
+    the label map and mean-logit map of upload + scene_infer bit for bit, for float64 and float32 scenes, several chunks."""
+    from drs_b200 import synth
+    monkeypatch.setenv("DRS_CHUNK_WAVES", "3")          # ~90 patches per chunk: the 768-patch grid takes 9 chunks
+    for kind, C, K, variant in (("vaihingen", 4, 6, "isprs"), ("contest", 3, 7, "contest")):
+        img, _ = synth.scene(kind, H=400, W=300, block=16)
+        mean, std = synth.normalisation(img)
+        with drs.Session("dilated_grsl", C, K, precision="f16", seed=6) as s:
+            s.set_normalization(mean, std)
+            s.upload_scene(0, img)
+            ref_l, ref_m = s.scene_infer(0, 25, 16, 400, 300, variant=variant, want_mean=True)
+            got_l, got_m = s.scene_infer_host(1, img, 25, 16, variant=variant, want_mean=True)
+            assert np.array_equal(ref_l, got_l) and np.array_equal(ref_m, got_m)
+            again = s.scene_infer(1, 25, 16, 400, 300, variant=variant)          # the scene stayed resident
+            assert np.array_equal(again, ref_l)
+
+
 def test_multiscale_evaluation_on_device(drs, tmp_path):
     """isprs:1347-1474 through the GPU backend: per-scale mean-logit maps from scene passes (prob_im / occur_im, float64),
     reference softmax, sum, argmax.  The composition equals the same formula applied to the oracle-checked mean maps, and
