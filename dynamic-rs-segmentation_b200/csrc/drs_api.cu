@@ -128,6 +128,9 @@ struct HandleExtra {
   TrainGraph* capturing = nullptr;   // non-null while a training step is being captured
   cudaStream_t side_stream = nullptr;     // filter gradients run here, overlapped with the backward's HBM-bound kernels
   cudaEvent_t ev_dz[2] = {nullptr, nullptr}, ev_wgrad[2] = {nullptr, nullptr};
+  // data-parallel exchange of the late layers' gradients, overlapped with the rest of the backward
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_bucket_ready = nullptr, ev_bucket_done = nullptr;
   bool use_graphs = false;          // opt-in (DRS_GRAPHS=1): measured 6-9 % per step in steady state, see DESIGN.md
   double conv_ms_acc = 0;            // device time of profiled launches already read back
   InferLane lanes[2];             // scene-inference lanes (drs_scene_api.cuh)
@@ -264,6 +267,9 @@ extern "C" int drs_create(drs_handle_t* out, const drs_config* cfg) {
   h->eval_dirty = true;
   x->use_graphs = getenv("DRS_GRAPHS") != nullptr && atoi(getenv("DRS_GRAPHS")) != 0;
   CUDA_CHECK(cudaStreamCreateWithFlags(&x->side_stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&x->comm_stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_bucket_ready, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_bucket_done, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_dz[i], cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_wgrad[i], cudaEventDisableTiming));
@@ -280,6 +286,9 @@ extern "C" int drs_destroy(drs_handle_t h) {
   HandleExtra* x = X(h);
   if (x) {
     if (x->side_stream) { cudaStreamSynchronize(x->side_stream); cudaStreamDestroy(x->side_stream); }
+    if (x->comm_stream) { cudaStreamSynchronize(x->comm_stream); cudaStreamDestroy(x->comm_stream); }
+    if (x->ev_bucket_ready) cudaEventDestroy(x->ev_bucket_ready);
+    if (x->ev_bucket_done) cudaEventDestroy(x->ev_bucket_done);
     if (x->copy_stream) { cudaStreamSynchronize(x->copy_stream); cudaStreamDestroy(x->copy_stream); }
     if (x->up_ev[0]) cudaEventDestroy(x->up_ev[0]);
     for (int i = 0; i < 2; ++i) {
@@ -448,9 +457,10 @@ extern "C" int drs_set_allreduce(drs_handle_t h, drs_allreduce_fn fn, void* user
   h->sync_bn = fn ? sync_bn : 0;
   API_END
 }
-static void do_allreduce(Handle* h, float* buf, int64_t count) {
+static void do_allreduce(Handle* h, float* buf, int64_t count, cudaStream_t on_stream = (cudaStream_t)(uintptr_t)1) {
   if (!h->allreduce || h->world <= 1) return;
-  int rc = h->allreduce(h->allreduce_user, buf, count, (void*)h->stream);
+  const cudaStream_t st = on_stream == (cudaStream_t)(uintptr_t)1 ? h->stream : on_stream;
+  int rc = h->allreduce(h->allreduce_user, buf, count, (void*)st);
   DRS_CHECK(rc == 0, "allreduce callback failed with %d", rc);
 }
 

@@ -182,6 +182,11 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   LAUNCH_CHECK(h);
 
   // ---------------------------------------------------------------- backward
+  // Data parallel: the gradients of the last layers are complete long before the backward ends (they are computed first)
+  // and hold most of the bytes (conv4..conv6 + classifier = 83 % of Dilated6Pooling), so that bucket -- with the loss
+  // numerator and the confusion counts behind it -- is summed over ranks on a third stream while the backward of the
+  // earlier layers runs; only the small front part of the buffer is exchanged at the end.
+  const int l_split = (h->world > 1 && !h->time_convs && !getenv("DRS_NO_BUCKETS") && L >= 4) ? L - 3 : -1;
   // classifier: dW, db, dX
   classifier_bwd_weight_kernel<TA><<<nb_cls, CLSW_THREADS, 0, h->stream>>>((const TA*)feat.p, feat.cs, feat.co, n.cls_in, dlogits, K, part_cls,
                                                                            part_clsb, M, cls_rows);
@@ -190,6 +195,11 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   LAUNCH_CHECK(h);
   reduce_partials_kernel<<<reduce_partials_grid(K), RP_COLS * RP_LANES, 0, h->stream>>>(part_clsb, h->grads + n.cls_b_off, K, nb_cls);
   LAUNCH_CHECK(h);
+  if (l_split >= 0) {
+    pack_extras_kernel<<<1, 128, 0, h->stream>>>(h->grads + n.n_trainable, x->loss_dev, x->cm_dev, K * K + 1);
+    LAUNCH_CHECK(h);
+    CUDA_CHECK(cudaEventRecord(x->ev_bucket_ready, h->stream));      // classifier gradients + extras are in the buffer
+  }
   TA* Gcur = n.dense ? GF : G0;
   TA* Gnext = G1;
   const int gcs0 = n.dense ? n.feat_stride : n.cls_in;
@@ -257,6 +267,13 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
         launch_wgrad_simt<TA, TA>(h, (const TA*)xin.p, xin.cs, xin.co, c.ci, DZ, c.co, 0, c.co, h->grads + c.w_off, part_w, max_splits, B, crop, c.k, c.rate, c.pad_b);
       }
       CUDA_CHECK(cudaEventRecord(x->ev_wgrad[l & 1], h->stream));
+      if (l == l_split) {
+        // h->stream is the stream the filter gradients run on (in order: layers L-1..l_split are all complete behind it)
+        CUDA_CHECK(cudaStreamWaitEvent(x->comm_stream, x->ev_wgrad[l & 1], 0));
+        CUDA_CHECK(cudaStreamWaitEvent(x->comm_stream, x->ev_bucket_ready, 0));
+        do_allreduce(h, h->grads + c.w_off, n.n_trainable + 2 + K * K - c.w_off, x->comm_stream);
+        CUDA_CHECK(cudaEventRecord(x->ev_bucket_done, x->comm_stream));
+      }
     } catch (...) { h->stream = main_stream; throw; }
     h->stream = main_stream;
     // dgrad: dilated conv of dZ with flipped taps, padding swapped
@@ -283,9 +300,14 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
 
   // ---------------------------------------------------------------- exchange + update
   if (h->world > 1) {
-    pack_extras_kernel<<<1, 128, 0, h->stream>>>(h->grads + n.n_trainable, x->loss_dev, x->cm_dev, K * K + 1);
-    LAUNCH_CHECK(h);
-    do_allreduce(h, h->grads, n.n_trainable + 2 + K * K);
+    if (l_split >= 0) {
+      do_allreduce(h, h->grads, n.convs[l_split].w_off);             // conv1 .. conv(l_split): the small front part
+      CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->ev_bucket_done, 0));
+    } else {
+      pack_extras_kernel<<<1, 128, 0, h->stream>>>(h->grads + n.n_trainable, x->loss_dev, x->cm_dev, K * K + 1);
+      LAUNCH_CHECK(h);
+      do_allreduce(h, h->grads, n.n_trainable + 2 + K * K);
+    }
     unpack_extras_kernel<<<1, 128, 0, h->stream>>>(h->grads + n.n_trainable, x->loss_dev, x->cm_dev, K * K + 1);
     LAUNCH_CHECK(h);
   }
