@@ -33,6 +33,7 @@ static size_t train_workspace_bytes(Handle* h, int B, int crop, size_t es) {
   add(M * maxc * es * 2);                     // G ping-pong / dense dgrad temp
   add(M * K * 4 * 2);                         // logits, dlogits
   add(M * 2);                                 // labels u8, pred
+  add(M * 8 * es);                            // conv1 input padded to 8 channels (tensor-core conv1)
   const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 2);   // one wave: 2 blocks of 256 threads per SM
   const int bn_rows = (int)ceil_div(M, nb_bn);
   add((size_t)nb_bn * 2 * 256 * 4);
@@ -117,6 +118,8 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     if (n.dense) return ActBuf{F, n.feat_stride, 0};
     return ActBuf{Xn[l - 1], n.convs[l - 1].co, 0};
   };
+  const bool conv1_on_tc = ElemTag<TA>::v == ET_BF16 && !getenv("DRS_NO_CONV1_TC_TRAIN") &&
+                           conv1_tc_supported(n.convs[0].k, n.convs[0].rate, n.convs[0].ci, n.convs[0].co);
   for (int l = 0; l < L; ++l) {
     ConvLayer& c = n.convs[l];
     ActBuf zb{Z[l], c.co, 0};
@@ -128,7 +131,20 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     BnFinish fin{x->bn_acc, 1048576.0, x->bn_counter, x->sums, nullptr, nullptr, nullptr, nullptr, bn_count, h->cfg.bn_eps, h->cfg.bn_decay, h->cfg.bn_unbiased_ema};
     if (!h->sync_bn) { fin.mean = mean; fin.inv_std = istd; fin.mov_mean = h->bnstat + c.mm_off; fin.mov_var = h->bnstat + c.mv_off; }
     const bool fused_stats = l > 0 && ElemTag<TA>::v != ET_F32 && !getenv("DRS_NO_FUSED_STATS");
-    if (l == 0) {
+    if (l == 0 && conv1_on_tc) {
+      // conv1 on the tensor cores as in inference (conv1_tc.cuh): input and filter rounded to bf16 like every other layer's
+      // operands; the filter is re-packed every step (13 K elements).  The filter gradient keeps the fp32 input.
+      if (!c.w_fprop) CUDA_CHECK(cudaMalloc(&c.w_fprop, (size_t)C1_SLOTS * c.co * 8 * 2));
+      pack_conv1_kernel<TA><<<nblk(C1_SLOTS * c.co * 8, 256), 256, 0, h->stream>>>(h->params + c.w_off, (TA*)c.w_fprop, c.ci, c.co);
+      LAUNCH_CHECK(h);
+      TA* x8 = (TA*)arena_take(h, (size_t)M * 8 * sizeof(TA));
+      pad_cast8_kernel<TA><<<nblk(M, 256), 256, 0, h->stream>>>(x_dev, x8, c.ci, M);
+      LAUNCH_CHECK(h);
+      Conv1TcArgs a1;
+      a1.x8 = x8; a1.wpack = c.w_fprop; a1.out = Z[l]; a1.out_cstride = c.co; a1.out_coff = 0; a1.co = c.co;
+      a1.B = B; a1.crop = crop; a1.scale = x->ones; a1.shift = h->params + c.b_off; a1.act = ACT_NONE; a1.etype = ElemTag<TA>::v;
+      launch_conv1_tc(h, a1);
+    } else if (l == 0) {
       launch_conv_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, h->params + c.w_off, Z[l], c.co, 0, c.co, B, crop, c.k,
                                   c.rate, c.pad_b, x->ones, h->params + c.b_off, ACT_NONE);
     } else {
