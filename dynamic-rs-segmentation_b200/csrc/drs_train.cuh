@@ -229,15 +229,22 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     ConvLayer& c = n.convs[l];
     ActBuf dOut = n.dense ? ActBuf{GF, n.feat_stride, c.out_coff} : ActBuf{Gcur, gcs, 0};
     ActBuf dA = dOut;
-    if (n.pool) {
-      launch_maxpool3_bwd<TA>(h, (const TA*)dOut.p, dOut.cs, dOut.co, idx[l], T, c.co, 0, c.co, B, crop);
-      dA = ActBuf{T, c.co, 0};
-    }
     float* mean = x->mean + c.mm_off;
     float* istd = x->inv_std + c.mm_off;
     BnFinish finb{x->bn_acc, 1099511627776.0, x->bn_counter, x->sums, nullptr, nullptr, nullptr, nullptr, bn_count, 0.0f, 0.0f, 0};
-    bn_partial_kernel<TA, TA, 1><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, n.act, part_bn, c.co, M, bn_rows, finb);
-    LAUNCH_CHECK(h);
+    // Experiment (off): the pool backward can also reduce the BN-backward sums of the dIn it produces (one pass over Z
+    // and dIn less per layer).  Measured slower: the pool backward is issue-bound already and the extra registers cost it
+    // a resident CTA (batch 64: crop 37 1.684 vs 1.643 ms/step, crop 49 2.586 vs 2.515).
+    const bool fused_bwd_stats = n.pool && ElemTag<TA>::v == ET_BF16 && getenv("DRS_FUSED_BWD_STATS");
+    if (n.pool) {
+      if (fused_bwd_stats) launch_maxpool3_bwd<TA>(h, (const TA*)dOut.p, dOut.cs, dOut.co, idx[l], T, c.co, 0, c.co, B, crop, &finb, Z[l], mean, istd, n.act);
+      else launch_maxpool3_bwd<TA>(h, (const TA*)dOut.p, dOut.cs, dOut.co, idx[l], T, c.co, 0, c.co, B, crop);
+      dA = ActBuf{T, c.co, 0};
+    }
+    if (!fused_bwd_stats) {
+      bn_partial_kernel<TA, TA, 1><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, n.act, part_bn, c.co, M, bn_rows, finb);
+      LAUNCH_CHECK(h);
+    }
     if (h->sync_bn) do_allreduce(h, x->sums, 2 * c.co);
     // The filter gradient of layer l is off the critical path (only the optimizer needs it): it runs on a side stream and
     // overlaps the HBM-bound kernels of layer l-1's backward.  dZ is double-buffered; before a buffer is rewritten the

@@ -278,45 +278,116 @@ __device__ __forceinline__ void pool_bwd_acc(const PoolBwdRow& r, int dy, float 
   }
 }
 
+// STATS: the same pass also reduces the two sums of the batch-norm backward of the layer below the pool,
+//   s0 = sum_m g, s1 = sum_m g * xh,  g = dIn * act'(xh), xh = (z - mean) * inv_std
+// over the (bf16-rounded) dIn it has just produced -- bn_partial_kernel<MODE 1> needs no pass of its own (it re-read Z and
+// dIn: M*C*4 bytes per layer).  Per-thread sums -> fixed-order block sums in shared memory -> 64-bit fixed point -> integer
+// atomics (order-independent), last block publishes them (same protocol as bn_partial_kernel).
+template <bool STATS>
 __global__ void __launch_bounds__(256)
 maxpool3_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dout, int do_cs, int do_co, const uint8_t* __restrict__ idx,
-                         __nv_bfloat16* __restrict__ din, int di_cs, int di_co, int C, int B, int crop, int seg, int nseg) {
+                         __nv_bfloat16* __restrict__ din, int di_cs, int di_co, int C, int B, int crop, int seg, int nseg,
+                         const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ inv_std,
+                         int act, BnFinish fin) {
   const int cv = C >> 3;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (int64_t)B * nseg * crop * cv) return;
+  const bool live = gid < (int64_t)B * nseg * crop * cv;
+  if (!STATS && !live) return;
   const int cg = (int)(gid % cv);
-  int64_t t = gid / cv;
-  const int x = (int)(t % crop);
-  t /= crop;
-  const int sg = (int)(t % nseg);
-  const int b = (int)(t / nseg);
-  const int y0 = sg * seg, y1 = min(crop, y0 + seg);
-  const int64_t img0 = (int64_t)b * crop * crop;
-  const __nv_bfloat16* dp = dout + do_co + cg * 8;
-  const uint8_t* ip = idx + cg * 8;
-  PoolBwdRow ra, rb, rc;                 // window rows y-1, y, y+1
-  pool_bwd_load(dp, do_cs, ip, C, img0, x, crop, y0 - 1, ra);
-  pool_bwd_load(dp, do_cs, ip, C, img0, x, crop, y0, rb);
-  for (int y = y0; y < y1; ++y) {
-    pool_bwd_load(dp, do_cs, ip, C, img0, x, crop, y + 1, rc);
-    float acc[8];
+  float s0[8], s1[8];
+  if (STATS) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
-    // same summation order as the gather formulation: dy = -1 (window row y+1), 0, +1 (window row y-1); dx = -1, 0, +1
-    pool_bwd_acc(rc, -1, acc);
-    pool_bwd_acc(rb, 0, acc);
-    pool_bwd_acc(ra, 1, acc);
-    uint4 o;
-    unsigned* ow = reinterpret_cast<unsigned*>(&o);
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const __nv_bfloat162 p = __floats2bfloat162_rn(acc[2 * w], acc[2 * w + 1]);
-      ow[w] = *reinterpret_cast<const unsigned*>(&p);
-    }
-    *reinterpret_cast<uint4*>(din + (img0 + (int64_t)y * crop + x) * di_cs + di_co + cg * 8) = o;
-    ra = rb;
-    rb = rc;
+    for (int e = 0; e < 8; ++e) { s0[e] = 0.0f; s1[e] = 0.0f; }
   }
+  if (live) {
+    int64_t t = gid / cv;
+    const int x = (int)(t % crop);
+    t /= crop;
+    const int sg = (int)(t % nseg);
+    const int b = (int)(t / nseg);
+    const int y0 = sg * seg, y1 = min(crop, y0 + seg);
+    const int64_t img0 = (int64_t)b * crop * crop;
+    const __nv_bfloat16* dp = dout + do_co + cg * 8;
+    const uint8_t* ip = idx + cg * 8;
+    float mu[8], is[8];
+    if (STATS) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { mu[e] = mean[cg * 8 + e]; is[e] = inv_std[cg * 8 + e]; }
+    }
+    PoolBwdRow ra, rb, rc;                 // window rows y-1, y, y+1
+    pool_bwd_load(dp, do_cs, ip, C, img0, x, crop, y0 - 1, ra);
+    pool_bwd_load(dp, do_cs, ip, C, img0, x, crop, y0, rb);
+    for (int y = y0; y < y1; ++y) {
+      pool_bwd_load(dp, do_cs, ip, C, img0, x, crop, y + 1, rc);
+      uint4 zraw = make_uint4(0u, 0u, 0u, 0u);
+      if (STATS) zraw = *reinterpret_cast<const uint4*>(z + (img0 + (int64_t)y * crop + x) * C + cg * 8);
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+      // same summation order as the gather formulation: dy = -1 (window row y+1), 0, +1 (window row y-1); dx = -1, 0, +1
+      pool_bwd_acc(rc, -1, acc);
+      pool_bwd_acc(rb, 0, acc);
+      pool_bwd_acc(ra, 1, acc);
+      uint4 o;
+      unsigned* ow = reinterpret_cast<unsigned*>(&o);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const __nv_bfloat162 p = __floats2bfloat162_rn(acc[2 * w], acc[2 * w + 1]);
+        ow[w] = *reinterpret_cast<const unsigned*>(&p);
+      }
+      *reinterpret_cast<uint4*>(din + (img0 + (int64_t)y * crop + x) * di_cs + di_co + cg * 8) = o;
+      if (STATS) {
+        const unsigned* zw = reinterpret_cast<const unsigned*>(&zraw);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const unsigned gw = ow[e >> 1], zz = zw[e >> 1];
+          float g = __uint_as_float((e & 1) ? (gw & 0xFFFF0000u) : (gw << 16));          // the rounded dIn, as stored
+          const float zf = __uint_as_float((e & 1) ? (zz & 0xFFFF0000u) : (zz << 16));
+          const float xh = (zf - mu[e]) * is[e];
+          if (act == ACT_RELU) g = xh > 0.0f ? g : 0.0f;
+          else if (act == ACT_LRELU) g = xh > 0.0f ? g : 0.1f * g;
+          s0[e] += g;
+          s1[e] = fmaf(g, xh, s1[e]);
+        }
+      }
+      ra = rb;
+      rb = rc;
+    }
+  }
+  if (!STATS) return;
+  __shared__ float s_red[16][256 + 1];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    s_red[e][threadIdx.x] = s0[e];
+    s_red[8 + e][threadIdx.x] = s1[e];
+  }
+  __syncthreads();
+  // threads of this block that hold channel group g: t = t0 + r*cv with t0 = (g - first_gid) mod cv
+  const int first = (int)(((int64_t)blockIdx.x * blockDim.x) % cv);
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    const int which = i / C, rem = i - which * C;
+    const int e = rem / cv, g = rem - e * cv;
+    int t0 = g - first;
+    if (t0 < 0) t0 += cv;
+    float a = 0.0f;
+    for (int t = t0; t < 256; t += cv) a += s_red[which * 8 + e][t];
+    const long long q = __double2ll_rn((double)a * fin.fx_scale);
+    atomicAdd(reinterpret_cast<unsigned long long*>(fin.acc) + which * C + g * 8 + e, static_cast<unsigned long long>(q));
+  }
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(fin.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double inv_scale = 1.0 / fin.fx_scale;
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    const double a = (double)__ldcg(fin.acc + i) * inv_scale;
+    fin.acc[i] = 0;
+    fin.sums[i] = (float)a;
+  }
+  if (threadIdx.x == 0) *fin.counter = 0u;
 }
 
 template <typename T>
@@ -379,15 +450,22 @@ __global__ void maxpool3_bwd_kernel(const T* __restrict__ dout, int do_cs, int d
 
 template <typename T>
 static void launch_maxpool3_bwd(Handle* h, const T* dout, int do_cs, int do_co, const uint8_t* idx, T* din, int di_cs, int di_co,
-                                int C, int B, int crop) {
+                                int C, int B, int crop, const BnFinish* stats = nullptr, const T* stats_z = nullptr,
+                                const float* stats_mean = nullptr, const float* stats_inv_std = nullptr, int stats_act = 0) {
   const int64_t M = (int64_t)B * crop * crop;
   if (ElemTag<T>::v == ET_BF16) {
     const int64_t base = (int64_t)B * crop * (C / 8);
     int nseg = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div((int64_t)h->sm_count * 2048, base)), std::max(1, crop / 4));
     const int seg = (int)ceil_div(crop, nseg);
     nseg = (int)ceil_div(crop, seg);
-    maxpool3_bwd_bf16_kernel<<<(unsigned)ceil_div(base * nseg, 256), 256, 0, h->stream>>>((const __nv_bfloat16*)dout, do_cs, do_co, idx,
-                                                                                        (__nv_bfloat16*)din, di_cs, di_co, C, B, crop, seg, nseg);
+    if (stats)
+      maxpool3_bwd_bf16_kernel<true><<<(unsigned)ceil_div(base * nseg, 256), 256, 0, h->stream>>>(
+          (const __nv_bfloat16*)dout, do_cs, do_co, idx, (__nv_bfloat16*)din, di_cs, di_co, C, B, crop, seg, nseg,
+          (const __nv_bfloat16*)stats_z, stats_mean, stats_inv_std, stats_act, *stats);
+    else
+      maxpool3_bwd_bf16_kernel<false><<<(unsigned)ceil_div(base * nseg, 256), 256, 0, h->stream>>>(
+          (const __nv_bfloat16*)dout, do_cs, do_co, idx, (__nv_bfloat16*)din, di_cs, di_co, C, B, crop, seg, nseg, nullptr, nullptr,
+          nullptr, 0, BnFinish{});
   } else {
     maxpool3_bwd_kernel<T><<<(unsigned)ceil_div(M * (C / 8), 256), 256, 0, h->stream>>>(dout, do_cs, do_co, idx, din, di_cs, di_co, C, M, crop);
   }
