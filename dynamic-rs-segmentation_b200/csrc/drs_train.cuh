@@ -220,8 +220,15 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   TA* Gnext = G1;
   const int gcs0 = n.dense ? n.feat_stride : n.cls_in;
   {
-    int blocks = (int)std::min<int64_t>(ceil_div(M * (n.cls_in / 8), 256), (int64_t)h->sm_count * 16);
-    classifier_bwd_data_kernel<TA><<<blocks, 256, n.cls_in * K * 4, h->stream>>>(dlogits, h->params + n.cls_w_off, K, Gcur, gcs0, 0, n.cls_in, M);
+    const int cvc = n.cls_in / 8;
+    if (cvc <= 256 && 256 % cvc == 0 && ElemTag<TA>::v != ET_F32 && !getenv("DRS_NO_CLS_REG")) {
+      const int rows = 256 / cvc;
+      int blocks = (int)std::min<int64_t>(ceil_div(M, 2 * rows), (int64_t)h->sm_count * 8);
+      classifier_bwd_data_reg_kernel<TA><<<blocks, 256, 0, h->stream>>>(dlogits, h->params + n.cls_w_off, K, Gcur, gcs0, 0, n.cls_in, M);
+    } else {
+      int blocks = (int)std::min<int64_t>(ceil_div(M * (n.cls_in / 8), 256), (int64_t)h->sm_count * 16);
+      classifier_bwd_data_kernel<TA><<<blocks, 256, n.cls_in * K * 4, h->stream>>>(dlogits, h->params + n.cls_w_off, K, Gcur, gcs0, 0, n.cls_in, M);
+    }
     LAUNCH_CHECK(h);
   }
   int gcs = gcs0;   // channel stride of Gcur (non-dense)
