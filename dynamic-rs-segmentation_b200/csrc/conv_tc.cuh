@@ -35,8 +35,8 @@ struct ConvTcParams {
   int num_tiles;      // ceil(M_total / 128)
   int stages;         // smem pipeline depth
   int kps;            // K blocks (BLOCK_K channels of one tap) per pipeline stage: one barrier round trip per kps blocks
-  int dual;           // two MMA-issuing warps (Co <= 128): even / odd stages of a tile accumulate into two TMEM
-                      // accumulators that the epilogue adds (the issue loop, not the tensor pipe, bounds these layers)
+  int dual;           // experiment (off, see CONV_TC_DUAL_MAX_CO): two MMA-issuing warps, even / odd stages of a tile
+                      // accumulate into two TMEM accumulators that the epilogue adds
   int acc_stride;     // TMEM columns of one accumulator
   int tmem_cols;      // allocated TMEM columns (power of two >= 32)
   int act;
