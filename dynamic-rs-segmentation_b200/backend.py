@@ -1,10 +1,12 @@
 """GPU backend of the drop-in scripts: executes a host ``BatchPlan`` (host.py) on the device.
 
-The scripts' loops call a backend with three operations; ``GpuBackend`` is the product implementation
+The scripts' loops call a backend with these operations; ``GpuBackend`` is the product implementation
 (libdrs.so through ``Session``, torch only for device buffers).  Tests drive the same loops with a
 closed-form stand-in to pin the host logic against reference-generated traces without a GPU.
 
-    train_on_plan(plan, loss_mask=None)  -> (loss, cm[K,K] uint32, n_correct)   gather + normalise + sess.run(train) + confusion
+    submit_train(plan, loss_mask=None)   -> ticket   gather + normalise + sess.run(train) + confusion, nothing waited for
+    train_result(ticket)                 -> (loss, cm[K,K] uint32, n_correct)
+    train_on_plan(plan, loss_mask=None)  == train_result(submit_train(...))
     eval_on_plan(plan, scene_offset=0)   -> (pred int64 [B,c,c], labels [B,c,c]) gather + normalise + sess.run(pred_up)
     scene_labels(scene_id, crop, batch, variant) -> uint8 [H,W]   whole sliding-window inference
     save(path) / restore(path)                                    tf.train.Saver stand-in (one .npz keyed by TF names)
@@ -32,6 +34,7 @@ class GpuBackend:
         self._x = self._y = self._pred = self._mask = None
         self._amask_on_dev = False
         self.rotate_on_device = True      # isprs rotation augmentation in the gather kernel (plan_isprs_batch flag)
+        self.pinned_plans = True          # plan slots are page-locked (asynchronous uploads, host.PlanSlot)
         self._cm = torch.zeros(self.K * self.K + 1, dtype=torch.int32, device=self.dev)
         session.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
 
@@ -48,8 +51,30 @@ class GpuBackend:
 
     def _rank_rows(self, n):
         """Data parallel: this rank's contiguous share of a global batch."""
+        if self.world <= 1:
+            return slice(0, n)
+        if n % self.world != 0:
+            raise ValueError("data-parallel training needs batch_size %% world_size == 0 (batch %d over %d ranks): the reference's "
+                             "batch would otherwise lose its remainder every step" % (n, self.world))
         per = n // self.world
-        return slice(self.rank * per, (self.rank + 1) * per) if self.world > 1 else slice(0, n)
+        return slice(self.rank * per, (self.rank + 1) * per)
+
+    def own_rows(self, n):
+        sl = self._rank_rows(n)
+        return sl.start, sl.stop
+
+    def prepare_training(self, batch_size, crops, isprs=True, loss_mask=None):
+        """Before the loop, like TF building its graph (isprs:1652-1693): size every buffer for the largest patch size of the
+        interval and capture the step's CUDA graph for each size (nothing executes)."""
+        crops = sorted(set(int(c) for c in crops))
+        per = batch_size // max(self.world, 1)
+        x, y, pred = self._buffers(per, crops[-1])
+        self.s.reserve(per, crops[-1], training=True)
+        if isinstance(loss_mask, str):
+            self.s.set_ignore_label(int(loss_mask.split("!=")[1]))
+        if self.world > 1:
+            return          # the exchange goes through a host callback: not capturable
+        self.s.prepare_training(x, y, per, crops, pred_dev=pred, acc_mask_dev=self._amask if isprs else None)
 
     def _gather(self, plan, scene_offset=0, shard=False):
         if shard and self.world > 1:
@@ -57,7 +82,19 @@ class GpuBackend:
             sub = type(plan)()
             for k in plan.__slots__:
                 v = getattr(plan, k)
-                setattr(sub, k, v[sl] if isinstance(v, np.ndarray) else v)
+                setattr(sub, k, v[sl] if isinstance(v, np.ndarray) and k not in ("noise",) else v)
+            if plan.noise_slot is None and plan.noise is not None:
+                sub.noise = plan.noise[sl]               # dense per-patch noise (Python planner)
+            elif plan.noise_slot is not None and plan.noise is not None:
+                # compact noise (native planner): upload only the blocks of this rank's patches
+                own = sub.noise_slot[sub.noise_slot >= 0]
+                if own.size:
+                    per = plan.crop * plan.crop * self.C
+                    s0, s1 = int(own.min()), int(own.max()) + 1
+                    sub.noise = plan.noise[s0 * per:s1 * per]
+                    sub.noise_slot = np.where(sub.noise_slot >= 0, sub.noise_slot - s0, -1).astype(np.int32)
+                else:
+                    sub.noise = None
             plan = sub
         self._plan = plan
         B, crop = plan.inst.shape[0], plan.crop
@@ -67,7 +104,11 @@ class GpuBackend:
             inst = inst.copy()
             inst[:, 0] += scene_offset
         self._amask_on_dev = False
-        if getattr(plan, "rot", None) is not None:
+        if getattr(plan, "noise_slot", None) is not None:
+            # natively planned batch: asynchronous uploads from the plan's pinned buffers, rotation on the device
+            self.s.gather_plan_dev(plan, x, y, self._amask)
+            self._amask_on_dev = True
+        elif getattr(plan, "rot", None) is not None:
             # rotation on the device: the kernel also writes the accuracy mask
             self.s.gather_rot_dev(inst, plan.flips, crop, x, y, noise=plan.noise, noise_on=plan.noise_on, rot=plan.rot,
                                   rot_on=plan.rot_on, amask_out_dev=self._amask)
@@ -77,13 +118,14 @@ class GpuBackend:
                               over_x=plan.over_x, over_y=plan.over_y, over_on=plan.over_on)
         return x, y, pred, B, crop
 
-    def train_on_plan(self, plan, loss_mask=None):
+    def submit_train(self, plan, loss_mask=None):
         t = self.torch
         if self.train_fp16_patches:
             self.s.set_gather_fp16(True)
         x, y, pred, B, crop = self._gather(plan, shard=True)
         if self.train_fp16_patches:
             self.s.set_gather_fp16(False)
+        sl = self._rank_rows(plan.inst.shape[0])
         plan = self._plan
         n = B * crop * crop
         mask_dev = None
@@ -91,17 +133,21 @@ class GpuBackend:
             # "label!=K": the session derives the mask on the device from the gathered labels (Session.set_ignore_label)
             self.s.set_ignore_label(int(loss_mask.split("!=")[1]))
         elif loss_mask is not None:
-            self._mask[:n].copy_(t.from_numpy(np.ascontiguousarray(loss_mask, dtype=np.uint8).reshape(-1)))
+            m = np.ascontiguousarray(loss_mask, dtype=np.uint8).reshape(-1, crop * crop)[sl]
+            self._mask[:n].copy_(t.from_numpy(np.ascontiguousarray(m).reshape(-1)))
             mask_dev = self._mask
         amask_dev = self._amask if self._amask_on_dev else None
         if plan.acc_mask is not None:
             self._amask[:n].copy_(t.from_numpy(np.ascontiguousarray(plan.acc_mask, dtype=np.uint8).reshape(-1)))
             amask_dev = self._amask
-        loss = self.s.train_step_dev(x, y, B, crop, mask_dev=mask_dev, pred_dev=pred, cm_dev=self._cm,
-                                     acc_mask_dev=amask_dev)
-        cm = self._cm.cpu().numpy().astype(np.uint32)
-        K = self.K
-        return loss, cm[:K * K].reshape(K, K), int(cm[K * K])
+        return self.s.train_step_async(x, y, B, crop, mask_dev=mask_dev, pred_dev=pred, acc_mask_dev=amask_dev)
+
+    def train_result(self, ticket):
+        loss, cm, acc = self.s.train_result(ticket)
+        return loss, cm, acc
+
+    def train_on_plan(self, plan, loss_mask=None):
+        return self.train_result(self.submit_train(plan, loss_mask))
 
     def eval_on_plan(self, plan, scene_offset=0):
         x, y, pred, B, crop = self._gather(plan, scene_offset)
@@ -110,6 +156,25 @@ class GpuBackend:
         n = B * crop * crop
         return (pred[:n].cpu().numpy().astype(np.int64).reshape(B, crop, crop),
                 y[:n].cpu().numpy().astype(np.int64).reshape(B, crop, crop))
+
+    def sync_bn_stats(self):
+        """Data parallel without SyncBN: every rank has normalised with its own batch statistics, so the moving averages
+        differ across ranks.  Average them (one small allreduce) before anything evaluates or saves the model, so that every
+        rank -- and every stripe of a sharded scene pass -- uses the same statistics."""
+        if self.world <= 1:
+            return
+        import torch.distributed as dist
+        t = self.torch
+        names = [n for n, _ in self.s.variable_names() if n.endswith("/moving_mean") or n.endswith("/moving_variance")]
+        flat = np.concatenate([self.s.get_variable(n) for n in names]).astype(np.float32)
+        buf = t.from_numpy(flat).to(self.dev)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        flat = (buf / self.world).cpu().numpy()
+        off = 0
+        for n in names:
+            cnt = self.s.get_variable(n).size
+            self.s.set_variable(n, flat[off:off + cnt])
+            off += cnt
 
     def scene_labels(self, scene_id, crop, batch, variant="isprs"):
         H, W = self.shapes[scene_id]

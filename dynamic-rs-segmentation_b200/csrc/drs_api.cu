@@ -116,6 +116,7 @@ struct TrainGraph {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;   // external event-record nodes around the tensor-core launches
 };
 
+constexpr int RESULT_STRIDE = 64 + MAX_CLASSES * MAX_CLASSES;   // floats per pinned result slot: loss, then K*K+1 counts
 struct HandleExtra {
   // persistent scene-pass buffers (score map, occurrence counts, cell tables, label map ...): cudaMalloc / cudaFree of
   // gigabyte-sized buffers per call costs hundreds of milliseconds, so each named slot only ever grows
@@ -155,6 +156,19 @@ struct HandleExtra {
   // profiling
   double conv_flops = 0;
   int64_t conv_launches = 0;
+  // pipelined training loop (drs_gather_plan_dev / drs_train_step_async / drs_train_result): the plan of step i+1 is
+  // uploaded on plan_stream into a two-slot device staging ring while step i runs; loss + confusion counts of each step
+  // land in a ring of pinned result slots behind an event, so the host never blocks on the step it has just enqueued
+  cudaStream_t plan_stream = nullptr;
+  void* plan_stage[2] = {nullptr, nullptr};
+  size_t plan_stage_cap[2] = {0, 0};
+  cudaEvent_t plan_uploaded[2] = {nullptr, nullptr}, plan_consumed[2] = {nullptr, nullptr};
+  bool plan_consumed_valid[2] = {false, false};
+  int64_t plan_calls = 0;
+  static constexpr int RESULT_RING = 8;
+  float* result_host = nullptr;     // pinned [RESULT_RING][RESULT_STRIDE]
+  cudaEvent_t result_ev[RESULT_RING] = {};
+  int64_t next_ticket = 0;
   // DRS_DEBUG_KEEP=1: fp32 copies of backward intermediates ("dz:<scope>", "da:<scope>")
   std::vector<float*> keep;
   bool debug_keep = false;
@@ -265,7 +279,16 @@ extern "C" int drs_create(drs_handle_t* out, const drs_config* cfg) {
   CUDA_CHECK(cudaEventCreate(&h->ev_b));
   h->packed_dirty = true;
   h->eval_dirty = true;
-  x->use_graphs = getenv("DRS_GRAPHS") != nullptr && atoi(getenv("DRS_GRAPHS")) != 0;
+  // whole-step CUDA graphs per (batch, patch size, buffers, lr): on by default (DRS_GRAPHS=0 turns them off); the drop-in
+  // loops pre-capture the patch-size interval at start-up (drs_train_prepare), like TF building its graph before the loop
+  x->use_graphs = getenv("DRS_GRAPHS") == nullptr || atoi(getenv("DRS_GRAPHS")) != 0;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&x->plan_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CUDA_CHECK(cudaEventCreateWithFlags(&x->plan_uploaded[i], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&x->plan_consumed[i], cudaEventDisableTiming));
+  }
+  CUDA_CHECK(cudaHostAlloc((void**)&x->result_host, (size_t)HandleExtra::RESULT_RING * RESULT_STRIDE * 4, cudaHostAllocDefault));
+  for (int i = 0; i < HandleExtra::RESULT_RING; ++i) CUDA_CHECK(cudaEventCreateWithFlags(&x->result_ev[i], cudaEventDisableTiming));
   CUDA_CHECK(cudaStreamCreateWithFlags(&x->side_stream, cudaStreamNonBlocking));
   CUDA_CHECK(cudaStreamCreateWithFlags(&x->comm_stream, cudaStreamNonBlocking));
   CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_bucket_ready, cudaEventDisableTiming));
@@ -290,6 +313,15 @@ extern "C" int drs_destroy(drs_handle_t h) {
     if (x->ev_bucket_ready) cudaEventDestroy(x->ev_bucket_ready);
     if (x->ev_bucket_done) cudaEventDestroy(x->ev_bucket_done);
     if (x->copy_stream) { cudaStreamSynchronize(x->copy_stream); cudaStreamDestroy(x->copy_stream); }
+    if (x->plan_stream) { cudaStreamSynchronize(x->plan_stream); cudaStreamDestroy(x->plan_stream); }
+    for (int i = 0; i < 2; ++i) {
+      if (x->plan_uploaded[i]) cudaEventDestroy(x->plan_uploaded[i]);
+      if (x->plan_consumed[i]) cudaEventDestroy(x->plan_consumed[i]);
+      if (x->plan_stage[i]) cudaFree(x->plan_stage[i]);
+    }
+    for (int i = 0; i < HandleExtra::RESULT_RING; ++i)
+      if (x->result_ev[i]) cudaEventDestroy(x->result_ev[i]);
+    if (x->result_host) cudaFreeHost(x->result_host);
     if (x->up_ev[0]) cudaEventDestroy(x->up_ev[0]);
     for (int i = 0; i < 2; ++i) {
       if (x->ev_dz[i]) cudaEventDestroy(x->ev_dz[i]);

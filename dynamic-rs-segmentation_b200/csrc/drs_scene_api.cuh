@@ -186,6 +186,76 @@ extern "C" int drs_gather_rot_dev(drs_handle_t h, const int32_t* inst_host, cons
   API_END
 }
 
+// The gather of a planned batch (drs_plan_isprs_batch) without any host synchronisation: the plan's arrays (page-locked
+// host memory owned by the caller, untouched until the step's result has been fetched) are copied on plan_stream into one
+// of two device staging slots and the gather is ordered behind that copy with an event; a staging slot is rewritten only
+// after the gather that read it two calls ago has run.
+extern "C" int drs_gather_plan_dev(drs_handle_t h, const int32_t* inst_host, const uint8_t* flips_host, int32_t B, int32_t crop,
+                                   const uint8_t* rot_on_host, const double* rot_host, const uint8_t* noise_on_host,
+                                   const int32_t* noise_slot_host, const double* noise_host, int64_t noise_count,
+                                   float* x_out_dev, float* y_out_dev, uint8_t* amask_out_dev) {
+  API_BEGIN
+  DRS_CHECK(h && inst_host && x_out_dev, "null argument");
+  DRS_CHECK(B >= 1 && crop >= 1, "gather_plan: bad B=%d crop=%d", B, crop);
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  HandleExtra* x = X(h);
+  for (int b = 0; b < B; ++b) {
+    const int sid = inst_host[b * 3], r = inst_host[b * 3 + 1], c = inst_host[b * 3 + 2];
+    auto it = h->scenes.find(sid);
+    DRS_CHECK(it != h->scenes.end(), "gather: scene %d not uploaded", sid);
+    DRS_CHECK(r >= it->second.row0 && r + crop <= it->second.row0 + it->second.rows && c >= 0 && c + crop <= it->second.W,
+              "Error: Current PATCH size is out of the resident scene rows (scene %d, row %d, col %d, crop %d)", sid, r, c, crop);
+  }
+  const bool has_noise = noise_host && noise_on_host && noise_slot_host && noise_count > 0;
+  const bool has_rot = rot_host && rot_on_host;
+  const size_t small = round_up((size_t)B * 12, 256) + 3 * round_up((size_t)B, 256) + round_up((size_t)B * 4, 256) +
+                       round_up((size_t)B * 48, 256);
+  const size_t need = small + (has_noise ? round_up((size_t)noise_count * 8, 256) : 0) + 1024;
+  const int s = (int)(x->plan_calls++ & 1);
+  if (x->plan_consumed_valid[s]) CUDA_CHECK(cudaStreamWaitEvent(x->plan_stream, x->plan_consumed[s], 0));
+  if (x->plan_stage_cap[s] < need) {
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(x->plan_stream));
+    if (x->plan_stage[s]) CUDA_CHECK(cudaFree(x->plan_stage[s]));
+    x->plan_stage[s] = nullptr;
+    x->plan_stage_cap[s] = 0;
+    const size_t want = need + (need >> 1);
+    CUDA_CHECK(cudaMalloc(&x->plan_stage[s], want));
+    x->plan_stage_cap[s] = want;
+  }
+  char* d = (char*)x->plan_stage[s];
+  auto put = [&](const void* src, size_t bytes) -> void* {
+    void* dst = d;
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, x->plan_stream));
+    d += round_up(bytes, 256);
+    return dst;
+  };
+  GatherParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.inst = (const int32_t*)put(inst_host, (size_t)B * 12);
+  if (flips_host) gp.flips = (const uint8_t*)put(flips_host, B);
+  if (has_rot) {
+    gp.rot_on = (const uint8_t*)put(rot_on_host, B);
+    gp.rot = (const double*)put(rot_host, (size_t)B * 48);
+  }
+  if (has_noise) {
+    gp.noise_on = (const uint8_t*)put(noise_on_host, B);
+    gp.noise_slot = (const int32_t*)put(noise_slot_host, (size_t)B * 4);
+    gp.noise = (const double*)put(noise_host, (size_t)noise_count * 8);
+  }
+  CUDA_CHECK(cudaEventRecord(x->plan_uploaded[s], x->plan_stream));
+  CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->plan_uploaded[s], 0));
+  gp.x_out = x_out_dev;
+  gp.y_out = y_out_dev;
+  gp.amask_out = amask_out_dev;
+  gp.B = B;
+  gp.crop = crop;
+  launch_gather(h, gp);
+  CUDA_CHECK(cudaEventRecord(x->plan_consumed[s], h->stream));
+  x->plan_consumed_valid[s] = true;
+  API_END
+}
+
 // host-only: the visiting order of create_patches_per_map (no GPU needed)
 extern "C" int drs_grid_positions(int32_t H, int32_t W, int32_t crop, int32_t batch, int32_t variant, int32_t* pos_out,
                                   int64_t cap_pairs, int64_t* n_out) {

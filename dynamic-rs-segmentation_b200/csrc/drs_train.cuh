@@ -463,6 +463,42 @@ extern "C" int drs_train_step_dev(drs_handle_t h, const float* x_dev, const floa
   API_END
 }
 
+// The same step without a host round trip: loss and confusion counts are copied into a pinned result slot behind an event
+// and fetched later with drs_train_result(ticket) -- the reference's loop only needs them for the score update and the
+// log lines (isprs:1754-1778), neither of which feeds the next step's draws.
+extern "C" int drs_train_step_async(drs_handle_t h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
+                                    const uint8_t* acc_mask_dev, int32_t B, int32_t crop, uint8_t* pred_dev, int64_t* ticket_out) {
+  API_BEGIN
+  DRS_CHECK(h && x_dev && y_dev && ticket_out, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  HandleExtra* x = X(h);
+  const int K = h->net.classes;
+  train_step(h, x_dev, y_dev, mask_dev, acc_mask_dev, B, crop, nullptr, pred_dev, nullptr);
+  const int64_t t = x->next_ticket++;
+  float* slot = x->result_host + (size_t)(t % HandleExtra::RESULT_RING) * RESULT_STRIDE;
+  CUDA_CHECK(cudaMemcpyAsync(slot, x->loss_dev + 2, 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaMemcpyAsync(slot + 1, x->cm_dev, (K * K + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaEventRecord(x->result_ev[t % HandleExtra::RESULT_RING], h->stream));
+  *ticket_out = t;
+  API_END
+}
+
+extern "C" int drs_train_result(drs_handle_t h, int64_t ticket, float* loss_out, uint32_t* cm_out) {
+  API_BEGIN
+  DRS_CHECK(h, "null handle");
+  HandleExtra* x = X(h);
+  DRS_CHECK(ticket >= 0 && ticket < x->next_ticket && ticket >= x->next_ticket - HandleExtra::RESULT_RING,
+            "train_result: ticket %lld is not one of the last %d steps (next ticket %lld)", (long long)ticket,
+            HandleExtra::RESULT_RING, (long long)x->next_ticket);
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  CUDA_CHECK(cudaEventSynchronize(x->result_ev[ticket % HandleExtra::RESULT_RING]));
+  const float* slot = x->result_host + (size_t)(ticket % HandleExtra::RESULT_RING) * RESULT_STRIDE;
+  const int K = h->net.classes;
+  if (loss_out) *loss_out = slot[0];
+  if (cm_out) memcpy(cm_out, slot + 1, (K * K + 1) * 4);
+  API_END
+}
+
 extern "C" int drs_reserve_workspace(drs_handle_t h, int32_t B, int32_t crop_max, int32_t training) {
   API_BEGIN
   DRS_CHECK(h, "null handle");

@@ -30,6 +30,7 @@ struct GatherParams {
   const uint8_t* flips;       // [B] 0 none, 1 flipud, 2 fliplr
   const double* noise;        // [B,c,c,C] or null
   const uint8_t* noise_on;    // [B] or null
+  const int32_t* noise_slot;  // [B] or null: compact noise, block noise_slot[b] of `noise` belongs to patch b (-1: none)
   const double* over_x;       // [B,c,c,C] patch replacing the scene crop (host-rotated), or null
   const uint8_t* over_y;      // [B,c,c]
   const uint8_t* over_on;     // [B] or null
@@ -86,7 +87,10 @@ __global__ void gather_kernel(const __grid_constant__ SceneTable tab, const Gath
     double v = over ? p.over_x[pidx * p.C + ch]
                     : (outside ? 0.0 : (sc.dtype == DRS_SCENE_F64 ? reinterpret_cast<const double*>(sc.data)[sidx * sc.C + ch]
                                                                   : (double)reinterpret_cast<const float*>(sc.data)[sidx * sc.C + ch]));
-    if (p.noise_on && p.noise_on[b]) v = v + p.noise[pidx * p.C + ch];    // isprs:301
+    if (p.noise_on && p.noise_on[b]) {                                    // isprs:301
+      const int64_t nidx = p.noise_slot ? (((int64_t)p.noise_slot[b] * p.crop + si) * p.crop + sj) : pidx;
+      v = v + p.noise[nidx * p.C + ch];
+    }
     if (ch < 3) {                                                          // isprs:75-81 (channels 0..2 only)
       v = v - p.mean[ch];
       v = v / p.stdv[ch];

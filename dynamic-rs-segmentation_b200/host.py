@@ -254,10 +254,13 @@ def dynamically_calculate_mean_and_std(data, indexes, crop_size):
 # ------------------------------------------------------------------------------------------------
 class BatchPlan:
     """What ``dynamically_create_patches`` decided for one batch; consumed by Session.gather_dev."""
-    __slots__ = ("inst", "flips", "noise", "noise_on", "over_x", "over_y", "over_on", "acc_mask", "crop", "rot", "rot_on")
+    __slots__ = ("inst", "flips", "noise", "noise_on", "over_x", "over_y", "over_on", "acc_mask", "crop", "rot", "rot_on",
+                 "noise_slot", "slot")
 
     def __init__(self):
         self.rot = self.rot_on = None
+        self.noise_slot = None      # compact noise: block noise_slot[b] of ``noise`` belongs to patch b (-1: none)
+        self.slot = None            # the PlanSlot whose (pinned) buffers the arrays above are views of
 
 
 def rotate_affine(angle, crop_size):
@@ -354,6 +357,125 @@ def plan_isprs_batch(data, mask_data, training_instances_batch, crop_size, is_tr
             elif p.flips[i] == FLIP_LR:
                 p.acc_mask[i] = np.fliplr(p.acc_mask[i])
     return p
+
+
+class PlanSlot:
+    """Reusable buffers for one native plan; page-locked when a CUDA device is present so that the gather's uploads are
+    asynchronous copies straight from here (drs_gather_plan_dev)."""
+
+    def __init__(self, batch_max, crop_max, channels, pinned=None):
+        self.B, self.crop_max, self.C = int(batch_max), int(crop_max), int(channels)
+        n_noise = self.B * self.crop_max * self.crop_max * self.C + 2
+
+        def buf(n, dtype):
+            if pinned is None:
+                return np.zeros(n, dtype=dtype)
+            import torch
+            t = torch.zeros(n, dtype=getattr(torch, np.dtype(dtype).name)).pin_memory()
+            self._keep.append(t)
+            return t.numpy()
+
+        self._keep = []
+        self.inst = buf(self.B * 3, np.int32).reshape(self.B, 3)
+        self.flips = buf(self.B, np.uint8)
+        self.rot_on = buf(self.B, np.uint8)
+        self.rot = buf(self.B * 6, np.float64).reshape(self.B, 6)
+        self.noise_on = buf(self.B, np.uint8)
+        self.noise_slot = buf(self.B, np.int32)
+        self.noise = buf(n_noise, np.float64)
+
+
+class NativePlanner:
+    """``plan_isprs_batch`` (isprs:245-334) through the library's host planner (csrc/host_plan.cpp).
+
+    Same decisions, same consumption of the global ``np.random`` stream and bit-identical noise values as the Python
+    function above (tests/test_host_plan.py), at ~1/10 of the cost: the state of the legacy global generator is handed to
+    the C code and written back afterwards.  Rotation always runs on the device with this planner."""
+
+    def __init__(self, threads=None):
+        import ctypes as C
+        import os
+        from . import lib as L
+        self._C, self._L = C, L
+        self._lib = L.load()
+        self._h = C.c_void_p()
+        if self._lib.drs_planner_create(C.byref(self._h)) != 0:
+            raise L.DrsError("drs_planner_create failed")
+        self.threads = int(threads if threads is not None else os.environ.get("DRS_PLAN_THREADS", min(4, os.cpu_count() or 1)))
+        self._ms = L.MtState()
+        self._key_view = np.frombuffer(self._ms.key, dtype=np.uint32)
+
+    def close(self):
+        if self._h:
+            self._lib.drs_planner_destroy(self._h)
+            self._h = self._C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _load_state(self):
+        st = np.random.get_state()
+        self._key_view[:] = st[1]
+        self._ms.pos, self._ms.has_gauss, self._ms.gauss = int(st[2]), int(st[3]), float(st[4])
+
+    def _store_state(self):
+        np.random.set_state(('MT19937', self._key_view.copy(), int(self._ms.pos), int(self._ms.has_gauss), float(self._ms.gauss)))
+
+    def normal(self, loc, scale, n):
+        """np.random.normal(loc, scale, n) on the global stream (test entry)."""
+        out = np.empty(int(n), dtype=np.float64)
+        self._load_state()
+        rc = self._lib.drs_mt_normal(self._h, self._C.byref(self._ms), float(loc), float(scale), out.ctypes.data, int(n), self.threads)
+        if rc:
+            raise self._L.DrsError("drs_mt_normal failed (%d)" % rc)
+        self._store_state()
+        return out
+
+    def randint(self, n, count):
+        out = np.empty(int(count), dtype=np.int32)
+        self._load_state()
+        rc = self._lib.drs_mt_randint(self._C.byref(self._ms), int(n), out.ctypes.data, int(count))
+        if rc:
+            raise self._L.DrsError("drs_mt_randint failed (%d)" % rc)
+        self._store_state()
+        return out
+
+    def plan(self, scene_hw, training_instances_batch, crop_size, channels, slot=None, own=None):
+        """-> BatchPlan with rotate_on_device semantics.  scene_hw: int32 [n_scenes, 2]; own = (b0, b1): the patches whose
+        noise values are needed (data-parallel rank slice), default all."""
+        C = self._C
+        inst_in = np.ascontiguousarray(training_instances_batch, dtype=np.int64)
+        B = inst_in.shape[0]
+        if inst_in.ndim != 2 or inst_in.shape[1] != 4:
+            raise ValueError("training instances must be (map, x, y, rotation) rows")
+        if slot is None or slot.B < B or slot.crop_max < crop_size or slot.C != channels:
+            slot = PlanSlot(B, crop_size, channels)
+        b0, b1 = (0, B) if own is None else own
+        n_noise = C.c_int32()
+        self._load_state()
+        rc = self._lib.drs_plan_isprs_batch(self._h, C.byref(self._ms), inst_in.ctypes.data, B, scene_hw.ctypes.data, scene_hw.shape[0],
+                                            int(crop_size), int(channels), 1, rotation_table(int(crop_size)).ctypes.data,
+                                            slot.inst.ctypes.data, slot.flips.ctypes.data, slot.rot_on.ctypes.data, slot.rot.ctypes.data,
+                                            slot.noise_on.ctypes.data, slot.noise_slot.ctypes.data, slot.noise.ctypes.data,
+                                            slot.noise.size, C.byref(n_noise), self.threads, int(b0), int(b1))
+        if rc == 3:
+            raise ValueError(BatchColors.FAIL + "Error: Current PATCH size is out of the scene" + BatchColors.ENDC)
+        if rc:
+            raise self._L.DrsError("drs_plan_isprs_batch failed (%d)" % rc)
+        self._store_state()
+        p = BatchPlan()
+        p.crop = int(crop_size)
+        p.inst, p.flips = slot.inst[:B], slot.flips[:B]
+        p.rot, p.rot_on = slot.rot[:B], slot.rot_on[:B]
+        p.noise_on, p.noise_slot = slot.noise_on[:B], slot.noise_slot[:B]
+        nn = int(n_noise.value)
+        p.noise = slot.noise[:nn * crop_size * crop_size * channels] if nn else None
+        p.over_x = p.over_y = p.over_on = p.acc_mask = None
+        p.slot = slot
+        return p
 
 
 def plan_index_flip_batch(class_distribution, shuffle_batch, crop_size, shapes, with_map=False):

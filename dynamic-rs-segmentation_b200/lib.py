@@ -38,6 +38,11 @@ class Config(C.Structure):
                 ("device", C.c_int32), ("isprs_scopes", C.c_int32)]
 
 
+class MtState(C.Structure):
+    """np.random.get_state() as include/drs.h:drs_mt_state."""
+    _fields_ = [("key", C.c_uint32 * 624), ("pos", C.c_int32), ("has_gauss", C.c_int32), ("gauss", C.c_double)]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 _P = C.c_void_p
@@ -57,6 +62,9 @@ _SIGNATURES = {
     "drs_forward_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "drs_train_step_host": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P, _P]),
     "drs_train_step_dev": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P, _P]),
+    "drs_train_step_async": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.POINTER(C.c_int64)]),
+    "drs_train_result": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_float), _P]),
+    "drs_gather_plan_dev": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P]),
     "drs_reserve_workspace": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "drs_train_prepare": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     "drs_set_ignore_label": (C.c_int, [_P, C.c_int32]),
@@ -68,6 +76,12 @@ _SIGNATURES = {
     "drs_set_normalization": (C.c_int, [_P, _P, _P]),
     "drs_gather_dev": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "drs_gather_rot_dev": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    "drs_planner_create": (C.c_int, [C.POINTER(_P)]),
+    "drs_planner_destroy": (C.c_int, [_P]),
+    "drs_mt_normal": (C.c_int, [_P, C.POINTER(MtState), C.c_double, C.c_double, _P, C.c_int64, C.c_int32]),
+    "drs_mt_randint": (C.c_int, [C.POINTER(MtState), C.c_uint32, _P, C.c_int64]),
+    "drs_plan_isprs_batch": (C.c_int, [_P, C.POINTER(MtState), _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P,
+                                       _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32]),
     "drs_grid_positions": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64,
                                      C.POINTER(C.c_int64)]),
     "drs_accumulate_argmax": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),

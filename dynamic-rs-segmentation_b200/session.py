@@ -174,6 +174,21 @@ class Session:
                                              C.byref(loss) if want_loss else None, L.ptr(pred_dev), L.ptr(cm_dev)))
         return np.float32(loss.value) if want_loss else None
 
+    def train_step_async(self, x_dev, y_dev, B, crop, mask_dev=None, pred_dev=None, acc_mask_dev=None):
+        """The train step without a host round trip -> ticket for train_result (at most 8 outstanding)."""
+        t = C.c_int64()
+        L.check(self._lib.drs_train_step_async(self._h, L.ptr(x_dev), L.ptr(y_dev), L.ptr(mask_dev), L.ptr(acc_mask_dev), B, crop,
+                                               L.ptr(pred_dev), C.byref(t)))
+        return int(t.value)
+
+    def train_result(self, ticket):
+        """(loss fp32, cm uint32 [K,K], n_correct) of the step behind ``ticket``; waits for that step only."""
+        K = self.num_classes
+        cm = np.empty(K * K + 1, dtype=np.uint32)
+        loss = C.c_float()
+        L.check(self._lib.drs_train_result(self._h, int(ticket), C.byref(loss), L.ptr(cm)))
+        return np.float32(loss.value), cm[:K * K].reshape(K, K).copy(), int(cm[K * K])
+
     def set_ignore_label(self, label):
         """contest: label 7 = unlabelled pixels, excluded from loss / gradient / confusion (contest:236-239, 886-897)."""
         L.check(self._lib.drs_set_ignore_label(self._h, -1 if label is None else int(label)))
@@ -271,6 +286,15 @@ class Session:
         ro = None if rot_on is None else np.ascontiguousarray(np.asarray(rot_on, dtype=np.uint8))
         L.check(self._lib.drs_gather_rot_dev(self._h, L.ptr(inst), L.ptr(f), B, crop, L.ptr(nz), L.ptr(nzo), L.ptr(r), L.ptr(ro),
                                              L.ptr(x_out_dev), L.ptr(y_out_dev), L.ptr(amask_out_dev)))
+
+    def gather_plan_dev(self, plan, x_out_dev, y_out_dev=None, amask_out_dev=None):
+        """Gather of a natively planned batch (host.NativePlanner): asynchronous uploads from the plan's pinned buffers."""
+        B = plan.inst.shape[0]
+        nz = plan.noise
+        L.check(self._lib.drs_gather_plan_dev(self._h, L.ptr(plan.inst), L.ptr(plan.flips), B, plan.crop, L.ptr(plan.rot_on),
+                                              L.ptr(plan.rot), L.ptr(plan.noise_on), L.ptr(plan.noise_slot), L.ptr(nz),
+                                              0 if nz is None else int(nz.size), L.ptr(x_out_dev), L.ptr(y_out_dev),
+                                              L.ptr(amask_out_dev)))
 
     def accumulate_argmax(self, logits_dev, positions, crop, H, W, want_mean=False):
         pos = np.ascontiguousarray(np.asarray(positions, dtype=np.int32).reshape(-1, 2))

@@ -116,6 +116,14 @@ int drs_train_step_dev(drs_handle_t h, const float* x_dev, const float* y_dev, c
                        const uint8_t* acc_mask_dev, int32_t B, int32_t crop, float* loss_out_host, uint8_t* pred_dev,
                        uint32_t* cm_dev);
 
+/* The train step of the pipelined loop: identical work, but nothing is waited for.  The loss and the confusion counts of
+ * the step are copied into a pinned result slot behind an event; drs_train_result(ticket) waits for that event only and
+ * returns them.  At most 8 steps may be outstanding (the result ring); tickets count up from 0.  The reference's loop
+ * needs loss / counts only for the score update and the log lines (isprs:1754-1778), which do not feed the next draws. */
+int drs_train_step_async(drs_handle_t h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
+                         const uint8_t* acc_mask_dev, int32_t B, int32_t crop, uint8_t* pred_dev, int64_t* ticket_out);
+int drs_train_result(drs_handle_t h, int64_t ticket, float* loss_out, uint32_t* cm_out);
+
 /* Size the workspace (and the host-path staging buffers) once for the largest batch / patch size of the run, so that no
  * re-allocation happens when a larger patch size is drawn later (the patch-size interval is known up front: probValues). */
 int drs_reserve_workspace(drs_handle_t h, int32_t B, int32_t crop_max, int32_t training);
@@ -176,6 +184,52 @@ int drs_gather_dev(drs_handle_t h, const int32_t* inst_host, const uint8_t* flip
 int drs_gather_rot_dev(drs_handle_t h, const int32_t* inst_host, const uint8_t* flips_host, int32_t B, int32_t crop,
                        const double* noise_host, const uint8_t* noise_on_host, const double* rot_host,
                        const uint8_t* rot_on_host, float* x_out_dev, float* y_out_dev, uint8_t* amask_out_dev);
+
+/* ---- host-side step planner (no device needed) ------------------------------------------------------------------
+ * dynamically_create_patches (isprs:245-334) draws, per patch, randint(0,2) rotate? / randint(0,2) noise? /
+ * normal(0, 0.01, patch.shape) / randint(0,3) flip from the legacy global NumPy generator, which the patch-size draw of
+ * the next step shares.  These entry points restate NumPy's MT19937, randint and legacy_gauss bit for bit
+ * (csrc/host_plan.cpp) on a generator state the caller takes from np.random.get_state() and writes back with
+ * np.random.set_state(), so a seeded run consumes the stream exactly like the reference at a fraction of the cost. */
+typedef struct drs_mt_state {
+  uint32_t key[624];  /* np.random.get_state()[1] */
+  int32_t pos;        /* [2] */
+  int32_t has_gauss;  /* [3] */
+  double gauss;       /* [4] cached_gaussian */
+} drs_mt_state;
+typedef struct drs_planner_s* drs_planner_t;   /* scratch + worker pool of the deferred Gaussian transform */
+int drs_planner_create(drs_planner_t* out);
+int drs_planner_destroy(drs_planner_t p);
+/* np.random.normal(loc, scale, n) / np.random.randint(0, n, count) on the caller's state (unit tests, building blocks) */
+int drs_mt_normal(drs_planner_t p, drs_mt_state* st, double loc, double scale, double* out, int64_t n, int32_t threads);
+int drs_mt_randint(drs_mt_state* st, uint32_t n, int32_t* out, int64_t count);
+/* One batch of dynamically_create_patches' decisions (isprs:255-318):
+ *   batch_inst [B,4] int64 (map, x, y, rotation angle) = selected_training_instances[batch]
+ *   scene_hw   [n_scenes,2] int32 scene heights / widths (border rule isprs:259-269)
+ *   rot_table  [360,6] float64: scipy.ndimage.rotate's affine map per integer angle for THIS crop (host.rotation_table)
+ *   inst_out [B,3] int32 (scene, row, col after the shift-back); flips_out [B] (0 none, 1 flipud, 2 fliplr);
+ *   rot_on_out [B], rot_out [B,6]; noise_on_out [B]; noise_slot_out [B] int32 = index of the patch's noise block
+ *   in noise_out or -1; noise_out: compact float64 noise, block k = values [k*crop*crop*C, (k+1)*crop*crop*C)
+ *   (noise_cap >= n_noise*crop*crop*C + 2 doubles); *n_noise_out = number of noisy patches.
+ *   is_train == 0: only inst_out is produced and the generator is not touched (validation batches, isprs:1586).
+ *   threads: workers of the deferred transform.  [own_b0, own_b1): patches whose noise values the caller needs (data
+ *   parallel ranks scan the whole batch but transform only their slice); pass 0, B for all.
+ * Returns 0, or 2 bad scene index, 3 window outside the scene (the reference prints an error, isprs:273-280),
+ * 4 rotation angle outside [0,360), 5 noise_out too small, 1 bad argument. */
+int drs_plan_isprs_batch(drs_planner_t p, drs_mt_state* st, const int64_t* batch_inst, int32_t B, const int32_t* scene_hw,
+                         int32_t n_scenes, int32_t crop, int32_t C, int32_t is_train, const double* rot_table,
+                         int32_t* inst_out, uint8_t* flips_out, uint8_t* rot_on_out, double* rot_out, uint8_t* noise_on_out,
+                         int32_t* noise_slot_out, double* noise_out, int64_t noise_cap, int32_t* n_noise_out, int32_t threads,
+                         int32_t own_b0, int32_t own_b1);
+
+/* Gather of a planned batch (drs_plan_isprs_batch) with no host synchronisation: the plan arrays must be page-locked host
+ * memory that stays untouched until the step's result has been fetched; they are uploaded on a separate stream into a
+ * two-slot device staging ring and the gather kernel is ordered behind the copy.  noise_host is the compact noise
+ * (noise_count doubles, block noise_slot[b] belongs to patch b); rotation and the accuracy mask as drs_gather_rot_dev. */
+int drs_gather_plan_dev(drs_handle_t h, const int32_t* inst_host, const uint8_t* flips_host, int32_t B, int32_t crop,
+                        const uint8_t* rot_on_host, const double* rot_host, const uint8_t* noise_on_host,
+                        const int32_t* noise_slot_host, const double* noise_host, int64_t noise_count, float* x_out_dev,
+                        float* y_out_dev, uint8_t* amask_out_dev);
 
 /* create_patches_per_map index arithmetic (isprs:344-375, contest:267-301 incl. the offset_h bug, coffee:302-322):
  * (row, col) of every patch in visiting order, batch after batch.  Pure host code (no device needed).

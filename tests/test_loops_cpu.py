@@ -47,6 +47,120 @@ class FakeBackend:
         raise AssertionError("not expected")
 
 
+class FakeDeviceBackend(FakeBackend):
+    """The stand-in with the product backend's contract: rotation happens on the "device" (the plan carries scipy's affine map
+    per patch, the stand-in applies the kernel's index arithmetic in NumPy), noise arrives compact (native planner), and the
+    step is asynchronous (submit_train / train_result), so the loop's prefetching, one-step-late result handling and flush
+    points are all exercised against the reference's trace."""
+    rotate_on_device = True
+
+    def __init__(self, *a):
+        super().__init__(*a)
+        self.outstanding = {}
+        self.ticket = 0
+        self.max_outstanding = 0
+
+    def _as_overrides(self, plan):
+        from drs_b200 import host
+        B, crop = len(plan.inst), plan.crop
+        q = host.BatchPlan()
+        q.crop, q.inst, q.flips = crop, np.array(plan.inst), np.array(plan.flips)
+        q.noise_on = None if plan.noise_on is None else np.array(plan.noise_on)
+        q.noise = None
+        if plan.noise is not None:
+            q.noise = np.zeros((B, crop, crop, self.C))
+            for b in range(B):
+                if plan.noise_on[b]:
+                    if plan.noise_slot is not None:
+                        k, n = int(plan.noise_slot[b]), crop * crop * self.C
+                        q.noise[b] = plan.noise[k * n:(k + 1) * n].reshape(crop, crop, self.C)
+                    else:
+                        q.noise[b] = plan.noise[b]
+        q.over_x = q.over_y = q.over_on = q.acc_mask = None
+        if plan.rot_on is not None and np.any(plan.rot_on):
+            q.over_x = np.zeros((B, crop, crop, self.C))
+            q.over_y = np.zeros((B, crop, crop), dtype=np.uint8)
+            q.over_on = np.array(plan.rot_on)
+            q.acc_mask = np.ones((B, crop, crop), dtype=np.uint8)
+            ii, jj = np.meshgrid(np.arange(crop, dtype=np.float64), np.arange(crop, dtype=np.float64), indexing="ij")
+            for b in np.nonzero(plan.rot_on)[0]:
+                m = plan.rot[b]
+                c0 = (m[4] + ii * m[0]) + jj * m[1]
+                c1 = (m[5] + ii * m[2]) + jj * m[3]
+                ok = ~((c0 < 0) | (c0 > crop - 1) | (c1 < 0) | (c1 > crop - 1))
+                r0, r1 = np.floor(c0 + 0.5).astype(np.int64), np.floor(c1 + 0.5).astype(np.int64)
+                sm, sr, sc = int(plan.inst[b][0]), int(plan.inst[b][1]), int(plan.inst[b][2])
+                src = self.scenes[sm][sr:sr + crop, sc:sc + crop]
+                lab = self.labels[sm][sr:sr + crop, sc:sc + crop]
+                q.over_x[b][ok] = src[r0[ok], r1[ok]]
+                q.over_y[b][ok] = lab[r0[ok], r1[ok]]
+                q.acc_mask[b] = ok
+            for b in range(B):          # the accuracy mask is flipped together with the patch (isprs:308-317)
+                if q.flips[b] == 1:
+                    q.acc_mask[b] = np.flipud(q.acc_mask[b])
+                elif q.flips[b] == 2:
+                    q.acc_mask[b] = np.fliplr(q.acc_mask[b])
+        return q
+
+    def submit_train(self, plan, loss_mask=None):
+        # evaluated at submission (the plan's buffers are recycled later, like pinned slots behind an async upload)
+        self.outstanding[self.ticket] = FakeBackend.train_on_plan(self, self._as_overrides(plan), loss_mask)
+        self.max_outstanding = max(self.max_outstanding, len(self.outstanding))
+        self.ticket += 1
+        return self.ticket - 1
+
+    def train_result(self, ticket):
+        return self.outstanding.pop(ticket)
+
+    def train_on_plan(self, plan, loss_mask=None):
+        return self.train_result(self.submit_train(plan, loss_mask))
+
+    def own_rows(self, n):
+        return 0, n
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2, 3])
+@pytest.mark.parametrize("native", [True, False])
+def test_pipelined_loop_with_device_rotation_reproduces_reference_trace(golden, drs, tmp_path, ci, native, monkeypatch):
+    """The product configuration of the loop -- native planner (csrc/host_plan.cpp), rotation on the device, asynchronous
+    steps with results taken one step late -- fed to the closed-form stand-in must reproduce the trace of the reference's
+    own ``isprs.train`` bit for bit: same sizes, same fed patches (rotated, noisy, flipped, normalised), same score files."""
+    from drs_b200 import host, loops
+    monkeypatch.setenv("DRS_NATIVE_PLAN", "1" if native else "0")
+    case = golden["train_cases"][ci]
+    dist, upd = DIST[int(case[0])], UPD[int(case[1])]
+    values = [int(v) for v in case[2:] if v > 0]
+    tr_d, tr_l = golden["train_scenes"], golden["train_labels"]
+    te_d, te_l = golden["test_scenes"], golden["test_labels"]
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(1000 + ci)
+    random.seed(2000 + ci)
+    with redirect_stdout(io.StringIO()):
+        tr_distr = host.create_distributions_over_classes(tr_l, 25, 5, 6)
+        te_distr = host.create_distributions_over_classes(te_l, 25, 5, 6)
+        rot = host.create_rotation_distribution(tr_distr)
+        mean_f, std_f = host.dynamically_calculate_mean_and_std(tr_d, tr_distr, 25)
+    pal, occ, chosen = host.init_score_arrays(dist, values)
+    probs = host.define_multinomial_probs(values) if dist == "multinomial" else None
+    be = FakeDeviceBackend(tr_d, tr_l, mean_f, std_f, 4, 6)
+    out = io.StringIO()
+    with redirect_stdout(out):
+        loops.isprs_train(be, tr_d, tr_l, tr_distr, rot, te_d, te_l, te_distr, ["1"], 4, 14, upd, dist, values, pal, occ,
+                          chosen, probs, 20, str(tmp_path) + "/", 5, "vaihingen", "", final_validation=False)
+    ref = golden["train_%d_log" % ci]
+    got = np.array(be.log, dtype=np.float64)
+    assert got.shape == ref.shape
+    assert np.array_equal(got[:, :3], ref[:, :3])
+    assert np.array_equal(got[:, 4], ref[:, 4])
+    assert np.allclose(got[:, 3], ref[:, 3], rtol=1e-12, atol=1e-9)
+    if dist != "single_fixed":
+        assert np.array_equal(np.load(tmp_path / "patch_acc_loss_step_14.npy"), golden["train_%d_pal" % ci])
+        assert np.array_equal(np.load(tmp_path / "patch_occur_step_14.npy"), golden["train_%d_occ" % ci])
+        assert np.array_equal(np.load(tmp_path / "patch_chosen_values_step_14.npy"), golden["train_%d_chosen" % ci])
+    assert be.max_outstanding == 2 and not be.outstanding        # one step in flight behind the one being submitted
+    assert out.getvalue().count("Training Minibatch") == 2       # display_step 5: flushed at steps 5 and 10
+
+
 @pytest.mark.parametrize("ci", [0, 1, 2, 3])
 def test_isprs_train_loop_reproduces_reference_trace(golden, drs, tmp_path, ci):
     from drs_b200 import host, loops
