@@ -119,49 +119,51 @@ def dist_env():
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# shared host-side step logic (the reference's policy, seeded identically on every rank)
+# the workload both arms run: the drop-in training loop (loops.isprs_train == isprs:1621-1851) on one synthetic scene
 # ----------------------------------------------------------------------------------------------------------------
-class TrainHost:
-    """Patch-size draws, batch selection and flips of the training loop (isprs:1726-1763), seeded."""
+SEED = 77
 
-    def __init__(self, cfg, shapes, global_batch, seed=77):
-        import random
-        from drs_b200 import host, synth
-        self.host, self.cfg, self.shapes, self.gb = host, cfg, shapes, global_batch
-        np.random.seed(seed)
-        random.seed(seed)
-        self.values = cfg["values"]
-        self.probs = host.define_multinomial_probs(self.values)
-        self.pal, self.occ, self.chosen = host.init_score_arrays(cfg["distribution"], self.values)
-        self.instances = synth.random_instances(np.random.RandomState(seed), global_batch * 100, shapes)
-        self.total = len(self.instances)
-        self.shuffle = np.asarray(random.sample(range(self.total), self.total))
-        self.it = 0
-        self.shape_arr = np.asarray(shapes, dtype=np.int64)
-        self.rs_flips = np.random.RandomState(seed + 1)   # own stream: the patch-size sequence must not depend on the batch size
 
-    def next_plan(self):
-        host = self.host
-        # the multinomial spreads 44 % of its mass over the unlisted sizes of [25, 49], exactly like the reference
-        crop, idx = host.draw_patch_size(self.cfg["distribution"], self.values, self.probs)
-        self.shuffle, batch, self.it = host.select_batch(self.shuffle, self.gb, self.it, self.total)
-        # border rule of every gather in the reference (isprs:259-269), vectorised: a window that sticks out is moved back
-        sel = self.instances[batch]
-        hw = self.shape_arr[sel[:, 0]]
-        inst = np.empty((len(batch), 3), dtype=np.int32)
-        inst[:, 0] = sel[:, 0]
-        inst[:, 1] = np.minimum(sel[:, 1], hw[:, 0] - int(crop))
-        inst[:, 2] = np.minimum(sel[:, 2], hw[:, 1] - int(crop))
-        flips = self.rs_flips.randint(0, 3, size=len(batch)).astype(np.uint8)  # isprs:304 flip decision per patch
-        # isprs:289-296 rotation decision per patch; the nearest-neighbour rotation itself runs in the gather kernel
-        rot_on = self.rs_flips.randint(0, 2, size=len(batch)).astype(np.uint8)
-        rot = host.rotation_table(int(crop))[sel[:, 3] % 360]
-        self.angles = sel[:, 3] % 360
-        return int(crop), idx, inst, flips, rot, rot_on
+def isprs_workload(cfg, test_hw=(300, 300)):
+    """What isprs_dilated_random.py builds before it calls train (isprs:2066-2115), on a synthetic Vaihingen-shaped scene:
+    class distributions, rotation table, normalisation, score arrays -- under the seeds both arms share."""
+    import random
+    from drs_b200 import host, synth
+    img, lab = synth.scene(cfg["dataset"])
+    timg, tlab = synth.scene(cfg["dataset"], H=test_hw[0], W=test_hw[1], seed=4321)
+    np.random.seed(SEED)
+    random.seed(SEED)
+    tr_distr = host.create_distributions_over_classes([lab], 25, 25, cfg["K"], verbose=False)
+    te_distr = host.create_distributions_over_classes([tlab], 25, 25, cfg["K"], verbose=False)
+    rot = host.create_rotation_distribution(tr_distr, verbose=False)
+    mean, std = synth.normalisation(img)
+    values = cfg["values"]
+    probs = host.define_multinomial_probs(values) if cfg["distribution"] == "multinomial" else None
+    pal, occ, chosen = host.init_score_arrays(cfg["distribution"], values)
+    return dict(train_data=[img], train_labels=[lab], test_data=[timg], test_labels=[tlab], tr_distr=tr_distr, te_distr=te_distr,
+                rot=rot, mean=mean, std=std, probs=probs, pal=pal, occ=occ, chosen=chosen)
 
-    def update(self, idx, loss, cm):
-        acc_norm = self.host.acc_norm_from_cm(cm, self.cfg["K"])
-        self.host.update_scores(self.pal, self.occ, idx, self.cfg["update"], loss, acc_norm)
+
+def run_isprs_loop(backend, wl, cfg, batch_size, niter, hook, depth=None):
+    """loops.isprs_train with the log lines discarded (the JSON line must be the only output) and its cache/checkpoint files in
+    a scratch directory; display / epoch / validation intervals beyond niter, so that every iteration is a plain training step."""
+    import contextlib
+    import tempfile
+    from drs_b200 import loops
+    far = 10 ** 9
+    cwd = os.getcwd()
+    if depth is not None:
+        os.environ["DRS_PREFETCH"] = str(depth)
+    with tempfile.TemporaryDirectory() as tmp, open(os.devnull, "w") as null:
+        os.chdir(tmp)
+        try:
+            with contextlib.redirect_stdout(null):
+                loops.isprs_train(backend, wl["train_data"], wl["train_labels"], wl["tr_distr"], wl["rot"], wl["test_data"],
+                                  wl["test_labels"], wl["te_distr"], ["t"], batch_size, niter, cfg["update"], cfg["distribution"],
+                                  cfg["values"], wl["pal"], wl["occ"], wl["chosen"], wl["probs"], 20, tmp + "/", far, "bench", "",
+                                  cfg["K"], epoch_number=far, val_inteval=far, final_validation=False, step_hook=hook)
+        finally:
+            os.chdir(cwd)
 
 
 def conv_flops_train(net, C, K, M):
@@ -178,146 +180,201 @@ def conv_flops_train(net, C, K, M):
 # ----------------------------------------------------------------------------------------------------------------
 # ours
 # ----------------------------------------------------------------------------------------------------------------
-def run_train_ours(args, rank, world, local):
+def run_train_ours(args, rank, world, local, cfg=None, sync_bn=False, extras=True):
     import torch
     import torch.distributed as dist
     import drs_b200
-    from drs_b200 import dist as ddist, nets, synth
-    cfg = TRAIN_CFG
+    from drs_b200 import dist as ddist, host
+    from drs_b200.backend import GpuBackend
+    cfg = cfg or TRAIN_CFG
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    img, lab = synth.scene(cfg["dataset"])
-    mean, std = synth.normalisation(img)
+    wl = isprs_workload(cfg)
     s = drs_b200.Session(cfg["net"], cfg["C"], cfg["K"], weight_decay=cfg["wd"], lr_initial=cfg["lr"], precision="bf16",
                          device=local, seed=5)
-    s.set_stream(torch.cuda.current_stream(dev).cuda_stream)
-    s.upload_scene(0, img, lab)
-    s.set_normalization(mean, std)
+    be = GpuBackend(s, wl["train_data"] + wl["test_data"], wl["train_labels"] + wl["test_labels"], wl["mean"], wl["std"],
+                    device=local, rank=rank, world=world)
     if world > 1:
-        ddist.attach_allreduce(s, sync_bn=False)
+        ddist.attach_allreduce(s, sync_bn=sync_bn)
     B = cfg["batch"]
-    s.reserve(B, cfg["values"][-1], training=True)      # the patch-size interval is known up front (probValues)
-    th = TrainHost(cfg, [img.shape[:2]], B * world)
-    cmax = max(cfg["values"][-1], 49)
-    x = torch.empty(B * cmax * cmax * cfg["C"], dtype=torch.float32, device=dev)
-    y = torch.empty(B * cmax * cmax, dtype=torch.float32, device=dev)
-    pred = torch.empty(B * cmax * cmax, dtype=torch.uint8, device=dev)
-    cm_dev = torch.zeros(cfg["K"] ** 2 + 1, dtype=torch.int32, device=dev)
-    amask = torch.empty(B * cmax * cmax, dtype=torch.uint8, device=dev)
-    from drs_b200 import host as _host
-    for c in range(cfg["values"][0], cfg["values"][-1] + 1):
-        _host.rotation_table(c)                          # affine maps of the 360 angles per patch size of the interval
+    W, K = args.warmup, args.steps
+    depth = int(os.environ.get("DRS_PREFETCH", "2"))
+    tail = depth + 2                 # untimed steps behind the timed ones: the planner thread runs ahead of the device by the
+    niter = W + K + tail             # same margin at both ends of the timed region (steady state, K plans per K steps)
+    crops, launches = [], [0, 0]
+    ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    sampler = ClockSampler(local)
+    clocks = [None]
+    orig_submit = be.submit_train
 
-    def step():
-        crop, idx, inst, flips, rot, rot_on = th.next_plan()
-        sl = slice(rank * B, (rank + 1) * B)
-        s.gather_rot_dev(inst[sl], flips[sl], crop, x, y, rot=rot[sl], rot_on=rot_on[sl], amask_out_dev=amask)
-        loss = s.train_step_dev(x, y, B, crop, pred_dev=pred, cm_dev=cm_dev, acc_mask_dev=amask)
-        cm = cm_dev.cpu().numpy()[:cfg["K"] ** 2].reshape(cfg["K"], cfg["K"])
-        th.update(idx, float(loss), cm)
-        return crop
+    def submit(plan, loss_mask=None):
+        crops.append(int(plan.crop))
+        return orig_submit(plan, loss_mask)
+
+    be.submit_train = submit
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    host_state = (np.random.get_state(), th.rs_flips.get_state(), th.shuffle.copy(), th.it)
-    import random as _random
-    py_state = _random.getstate()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    l0 = s.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    px = 0
-    crops = []
-    for _ in range(args.steps):
-        c = step()
-        crops.append(c)
-        px += B * c * c
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = s.launch_count - l0
-    clocks = sampler.stop() if rank == 0 else None
+    def hook(step, pipe):
+        # called after step `step` has been enqueued and before step+1 is: the event recorded here fires when `step` is done
+        if step == W:
+            pipe.flush()
+            barrier()
+            if rank == 0:
+                sampler.start()
+            launches[0] = s.launch_count
+            ev[0].record()
+        elif step == W + K:
+            ev[1].record()
+            launches[1] = s.launch_count
+            pipe.flush()
+            barrier()
+            clocks[0] = sampler.stop() if rank == 0 else None
+
+    run_isprs_loop(be, wl, cfg, B * world, niter, hook)
+    ms = ev[0].elapsed_time(ev[1])
+    timed_crops = crops[W:W + K]
+    px = sum(B * c * c for c in timed_crops)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = B * world * args.steps / (ms / 1e3)
+    value = B * world * K / (ms / 1e3)
+    out = dict(metric="train patches/s", value=value, unit="patches/s", ms_per_step=ms / K, dtype="bf16", scaling="weak",
+               gpu_launches=launches[1] - launches[0], clocks=clocks[0])
+    if not extras:
+        s.close()
+        return out
 
-    # ---- kernel timing pass: the SAME K steps again (host policy rewound to the same patch sizes and batches) with a CUDA
-    # event pair around every tensor-core launch.  Timing single launches needs them serialised, so this pass runs the
-    # filter gradients on the main stream instead of overlapping them with the backward's HBM-bound kernels (which is what
-    # the timed region above does); its step time is reported next to the kernel time.
-    np.random.set_state(host_state[0]); th.rs_flips.set_state(host_state[1]); th.shuffle = host_state[2]; th.it = host_state[3]
-    _random.setstate(py_state)
+    # ---- data-parallel check: every rank must hold bit-identical variables and optimizer slots after the run
+    if world > 1:
+        out["dp_check"] = dp_check(s, be, cfg, rank, world, dev, sync_bn)
+
+    # ---- kernel timing pass: the same patch sizes again with a CUDA event pair around every tensor-core launch.  Timing
+    # single launches needs them serialised, so this pass runs the filter gradients on the main stream instead of overlapping
+    # them with the backward's HBM-bound kernels (which is what the timed region above does); its step time is reported too.
+    planner = host.NativePlanner()
+    hw = np.asarray([wl["train_data"][0].shape[:2]], dtype=np.int32)
+    rs = np.random.RandomState(1)
+    inst = np.zeros((B * world, 4), dtype=np.int64)
+    inst[:, 1], inst[:, 2], inst[:, 3] = rs.randint(0, 1900, B * world), rs.randint(0, 2400, B * world), rs.randint(0, 360, B * world)
     s.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s.profile_read()
     e0.record()
-    for _ in range(args.steps):
-        step()
+    for c in timed_crops:
+        be.train_on_plan(planner.plan(hw, inst, c, cfg["C"], own=be.own_rows(B * world)))
     e1.record()
     barrier()
     ms_prof = e0.elapsed_time(e1)
     conv_ms, conv_n, conv_fl = s.profile_read()
     s.set_profiling(False)
+    planner.close()
 
     # ---- end to end through the sess.run seam: host x / y in pinned memory, host loss / pred / confusion back
-    e2e = None
     host_batches = {}
     rs = np.random.RandomState(3)
-    for c in sorted(set(crops)):
+    for c in sorted(set(timed_crops)):
         xh = torch.from_numpy(rs.randn(B, c * c * cfg["C"]).astype(np.float32)).pin_memory()
         yh = torch.from_numpy(rs.randint(0, cfg["K"], size=(B, c * c)).astype(np.float32)).pin_memory()
         host_batches[c] = (xh.numpy(), yh.numpy(), xh, yh)
-    for c in crops[:max(1, min(3, len(crops)))]:
+    for c in timed_crops[:3]:
         s.train_step(host_batches[c][0], host_batches[c][1], c, want_cm=True)
     barrier()
-    t0 = time.perf_counter()
     e0.record()
     bi = bo = 0
-    dbg = []
-    for c in crops:
-        t1 = time.perf_counter()
+    for c in timed_crops:
         s.train_step(host_batches[c][0], host_batches[c][1], c, want_cm=True)
-        dbg.append(round((time.perf_counter() - t1) * 1e3, 1))
         bi += B * c * c * (cfg["C"] + 1) * 4
         bo += B * c * c * 8 + 4 + (cfg["K"] ** 2 + 1) * 4
     e1.record()
     barrier()
     ms2 = e0.elapsed_time(e1)
-    if os.environ.get("BENCH_DEBUG") and rank == 0:
-        print("e2e per-step ms:", dbg, file=sys.stderr)
     if world > 1:
         t = torch.tensor([ms2], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms2 = float(t.item())
-    e2e = {"value": B * world * args.steps / (ms2 / 1e3), "unit": "patches/s", "h2d_bytes_per_step": bi // len(crops),
-           "d2h_bytes_per_step": bo // len(crops), "api": "Session.train_step == drs_train_step_host (sess.run seam, host feeds/fetches)"}
+    out["e2e"] = {"value": B * world * K / (ms2 / 1e3), "unit": "patches/s", "h2d_bytes_per_step": bi // K, "d2h_bytes_per_step": bo // K,
+                  "api": "Session.train_step == drs_train_step_host (sess.run seam, host feeds/fetches)"}
     s.close()
 
     pk = peaks()
-    M_total = px
-    roof = {"bound": "tensor", "kernel": "tcgen05 kernels of the step: conv_tc_kernel (fprop + dgrad) and wgrad_tc_kernel",
-            "achieved": (conv_fl / (conv_ms * 1e-3) / 1e12) if conv_ms > 0 else None, "peak": pk["tc_sustained"],
-            "unit": "TFLOP/s", "frac": (conv_fl / (conv_ms * 1e-3) / 1e12 / pk["tc_sustained"]) if conv_ms > 0 else None,
-            "traffic": profiled_traffic("train"), "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
-            "launches": conv_n, "kernel_ms_per_step": conv_ms / args.steps, "ms_per_step_timing_pass": ms_prof / args.steps,
-            "step_tflops_all_kernels": conv_flops_train(cfg["net"], cfg["C"], cfg["K"], M_total) / (ms * 1e-3) / 1e12}
-    return dict(metric="train patches/s", value=value, unit="patches/s", ms_per_step=ms / args.steps, dtype="bf16",
-                scaling="weak", e2e=e2e, gpu_launches=launches, clocks=clocks, roofline=roof,
-                config={"workload": "configs[1]: dilated_grsl multinomial {25..49} acc, batch 64/GPU, Vaihingen-shaped 2000x2500x4 "
-                                    "float64 scene resident in HBM", "net": cfg["net"], "batch_per_gpu": B, "global_batch": B * world,
-                        "patch_sizes_drawn": crops, "parallelism": "dp%d" % world, "sync_bn": False,
-                        "l2": "per-step working set (activations %.0f-%.0f MB) exceeds the 126 MB L2; no explicit flush" %
-                              (B * 25 * 25 * 896 * 6 / 1e6, B * 49 * 49 * 896 * 6 / 1e6),
-                        "augment": "flips and nearest-neighbour rotation (scipy order 0, SURVEY N1) in the gather kernel, decisions drawn on the "
-                                   "host; the additive np.random.normal noise (host RNG stream) is not in the timed step"})
+    capped = bool(clocks[0] and "sw_power_cap" in (clocks[0].get("reasons") or []))
+    peak = pk["tc_sustained"] if capped else pk["tc_burst"]
+    ach = (conv_fl / (conv_ms * 1e-3) / 1e12) if conv_ms > 0 else None
+    out["roofline"] = {"bound": "tensor", "kernel": "tcgen05 kernels of the step: conv_tc_kernel (fprop + dgrad) and wgrad_tc_kernel",
+                       "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
+                       "traffic": profiled_traffic("train"),
+                       "peak_source": pk["source"] + (" bf16 sustained (sw_power_cap seen during the timed region)" if capped
+                                                      else " bf16 burst (no power cap during the timed region)"),
+                       "launches": conv_n, "kernel_ms_per_step": conv_ms / K, "ms_per_step_timing_pass": ms_prof / K,
+                       "step_tflops_all_kernels": conv_flops_train(cfg["net"], cfg["C"], cfg["K"], px) / (ms * 1e-3) / 1e12}
+    out["config"] = {"workload": "configs[1]: isprs_dilated_random.py dilated_grsl multinomial {25..49} acc, batch 64/GPU, Vaihingen-shaped "
+                                 "2000x2500x4 float64 scene resident in HBM; one step = one iteration of the drop-in loop "
+                                 "(loops.isprs_train: draw size, select_batch, dynamically_create_patches decisions incl. np.random.normal "
+                                 "noise, gather+rotate+flip+normalise, sess.run(train), calc_accuracy_by_crop, score update)",
+                     "net": cfg["net"], "batch_per_gpu": B, "global_batch": B * world, "patch_sizes_drawn": timed_crops,
+                     "parallelism": "dp%d" % world, "sync_bn": bool(sync_bn), "cuda_graphs": os.environ.get("DRS_GRAPHS", "1") != "0",
+                     "host_plan": "native planner thread %d steps ahead (bit-exact np.random stream), results taken one step late; "
+                                  "%d untimed tail steps keep the planner's lead equal at both ends of the timed region" % (depth, tail),
+                     "l2": "per-step working set (activations %.0f-%.0f MB) exceeds the 126 MB L2; no explicit flush" %
+                           (B * 25 * 25 * 896 * 6 / 1e6, B * 49 * 49 * 896 * 6 / 1e6)}
+    return out
+
+
+def dp_check(s, be, cfg, rank, world, dev, sync_bn):
+    """(1) After the timed steps every rank's variables, BN statistics and momentum slots must be bit-identical: one checksum per
+    rank, all-gathered.  (2) One SyncBN fp32 step on a global batch split over the ranks against the same step done by a single
+    process on the whole batch (the parity mode of SURVEY 8e): loss and every updated variable."""
+    import torch
+    import torch.distributed as dist
+    import drs_b200
+    from drs_b200 import dist as ddist
+    import hashlib
+    names = [n for n, _ in s.variable_names()]
+    local_stats = [n for n in names if n.endswith("/moving_mean") or n.endswith("/moving_variance")]
+    h = hashlib.sha256()
+    for n in names:
+        if n in local_stats and not sync_bn:
+            continue                      # rank-local by design without SyncBN (averaged before evaluation / save)
+        h.update(np.ascontiguousarray(s.get_variable(n)).tobytes())
+    digest = np.frombuffer(h.digest()[:8], dtype=np.int64).copy()
+    t = torch.from_numpy(digest).to(dev)
+    allv = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(allv, t)
+    replicas_equal = all(bool((v == allv[0]).all().item()) for v in allv)
+    # (2) SyncBN parity step in fp32
+    B, crop, C, K = 4 * world, 25, cfg["C"], cfg["K"]
+    rs = np.random.RandomState(11)
+    x = rs.randn(B, crop * crop * C).astype(np.float32)
+    y = rs.randint(0, K, size=(B, crop * crop)).astype(np.float32)
+    sp = drs_b200.Session(cfg["net"], C, K, weight_decay=cfg["wd"], lr_initial=cfg["lr"], precision="fp32", device=dev.index, seed=5)
+    sp.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    ddist.attach_allreduce(sp, sync_bn=True)
+    per = B // world
+    loss_dp, _ = sp.train_step(x[rank * per:(rank + 1) * per], y[rank * per:(rank + 1) * per], crop)
+    worst = 0.0
+    loss_ref = None
+    if rank == 0:
+        s1 = drs_b200.Session(cfg["net"], C, K, weight_decay=cfg["wd"], lr_initial=cfg["lr"], precision="fp32", device=dev.index, seed=5)
+        s1.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        loss_ref, _ = s1.train_step(x, y, crop)
+        for n, _ in s1.variable_names():
+            a, b = s1.get_variable(n), sp.get_variable(n)
+            worst = max(worst, float(np.abs(a - b).max() / (np.abs(a).max() + 1e-12)))
+        s1.close()
+    sp.close()
+    ok = replicas_equal
+    res = {"replicas_bit_identical": bool(replicas_equal)}
+    if rank == 0:
+        res.update(syncbn_loss=float(loss_dp), single_process_loss=float(loss_ref), syncbn_worst_rel_diff=worst)
+        ok = ok and abs(float(loss_dp) - float(loss_ref)) < 2e-5 * max(1.0, abs(float(loss_ref))) and worst < 1e-4
+    res["result"] = "ok" if ok else "FAILED"
+    return res
 
 
 def run_infer_ours(args, rank, world, local, steps=1):
@@ -409,49 +466,109 @@ def run_infer_ours(args, rank, world, local, steps=1):
 # ----------------------------------------------------------------------------------------------------------------
 # reference-equivalent CPU path (oracle): the checker timed as the baseline
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_train_baseline(steps, warmup, budget_s=25.0):
-    import torch
+def cli_rate(cfg, iters=300, first=100):
+    """The drop-in command line itself: ``isprs_dilated_random.py ... training`` on the same synthetic scene written as .npy,
+    rate taken from the script's own "Iter N -- Time ..." log lines (isprs:1766-1772) between iteration `first` and `iters`."""
+    import datetime
+    import re
+    import tempfile
     from drs_b200 import synth
-    from oracle import host_np, nets_torch
-    cfg = TRAIN_CFG
+    with tempfile.TemporaryDirectory() as tmp:
+        data, out = os.path.join(tmp, "vaihingen"), os.path.join(tmp, "out")
+        os.makedirs(data)
+        os.makedirs(out)
+        img, lab = synth.scene(cfg["dataset"])
+        timg, tlab = synth.scene(cfg["dataset"], H=300, W=300, seed=4321)
+        np.save(os.path.join(data, "1_image.npy"), img)
+        np.save(os.path.join(data, "1_labels.npy"), lab)
+        np.save(os.path.join(data, "2_image.npy"), timg)
+        np.save(os.path.join(data, "2_labels.npy"), tlab)
+        argv = [sys.executable, os.path.join(ROOT, "isprs_dilated_random.py"), data + "/", out + "/", "", "1", "2", str(cfg["lr"]),
+                str(cfg["wd"]), str(cfg["batch"]), str(iters), "25", "25", cfg["net"], cfg["distribution"],
+                ",".join(str(v) for v in cfg["values"]), cfg["update"], "training"]
+        env = dict(os.environ, PYTHONPATH=ROOT, DRS_SEED="5")
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        t0 = time.perf_counter()
+        r = subprocess.run(argv, cwd=tmp, env=env, capture_output=True, text=True, timeout=900)
+        wall = time.perf_counter() - t0
+    if r.returncode != 0:
+        return {"error": (r.stdout[-400:] + r.stderr[-400:])}
+    stamps = {}
+    for m in re.finditer(r"^Iter (\d+) -- Time (\d+):(\d+):(\d+\.?\d*)", r.stdout, re.M):
+        stamps[int(m.group(1))] = int(m.group(2)) * 3600 + int(m.group(3)) * 60 + float(m.group(4))
+    if first not in stamps or iters not in stamps:
+        return {"error": "log lines of iterations %d / %d not found" % (first, iters)}
+    dt = (stamps[iters] - stamps[first]) % 86400
+    return {"patches_per_s": cfg["batch"] * (iters - first) / dt, "iterations": iters - first, "ms_per_step": dt / (iters - first) * 1e3,
+            "wall_s_whole_command": wall,
+            "cmd": "isprs_dilated_random.py <data>/ <out>/ '' 1 2 %g %g %d %d 25 25 %s %s %s %s training" %
+                   (cfg["lr"], cfg["wd"], cfg["batch"], iters, cfg["net"], cfg["distribution"], ",".join(str(v) for v in cfg["values"]),
+                    cfg["update"]),
+            "how": "timestamps of the script's own 'Iter N -- Time' lines, iterations %d..%d" % (first, iters)}
+
+
+class OracleBackend:
+    """The reference-equivalent CPU path behind the loop's backend interface (checker code timed as the baseline): NumPy
+    gather / flip / normalise of the plan (scipy rotation already applied by the Python planner, as the reference does it on
+    the host), the PyTorch-CPU fp32 restatement of the TF graph for sess.run(train), and the reference's Python-loop
+    calc_accuracy_by_crop."""
+
+    def __init__(self, cfg, wl):
+        import torch
+        from oracle import nets_torch
+        self.cfg, self.wl, self.torch = cfg, wl, torch
+        self.net = nets_torch.OracleNet(cfg["net"], cfg["C"], cfg["K"], nets_torch.init_params(cfg["net"], cfg["C"], cfg["K"], seed=5))
+        self.crops = []
+
+    def train_on_plan(self, plan, loss_mask=None):
+        from oracle import host_np
+        cfg, wl, torch = self.cfg, self.wl, self.torch
+        self.crops.append(int(plan.crop))
+        xs, ys = host_np.apply_plan(wl["train_data"], wl["train_labels"], plan.inst, plan.flips, plan.crop, wl["mean"], wl["std"],
+                                    plan.noise, plan.noise_on, plan.over_x, plan.over_y, plan.over_on)
+        B = len(plan.inst)
+        loss, pred, _ = self.net.train_step(torch.from_numpy(xs.reshape(B, -1)), torch.from_numpy(ys.reshape(B, -1)), plan.crop,
+                                            cfg["lr"], cfg["wd"])
+        masks = None if plan.acc_mask is None else plan.acc_mask.astype(bool)
+        acc, _, cm = host_np.confusion_by_crop(ys.astype(np.int64), pred.numpy(), cfg["K"], masks)
+        return loss, cm, acc
+
+    def save(self, path):
+        pass
+
+
+def cpu_train_baseline(steps, warmup, cfg=None):
+    """The SAME seeded loop as the GPU arm (same scene, same seeds -> same patch sizes, batches and augmentations), strictly
+    sequential like the reference (no planner thread), on the host cores."""
+    import torch
+    cfg = cfg or TRAIN_CFG
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    img, lab = synth.scene(cfg["dataset"], H=600, W=700)     # gather cost does not depend on scene size
-    mean, std = synth.normalisation(img)
+    wl = isprs_workload(cfg)
+    be = OracleBackend(cfg, wl)
     B = cfg["batch"]
-    th = TrainHost(cfg, [img.shape[:2]], B)
-    orc = nets_torch.OracleNet(cfg["net"], cfg["C"], cfg["K"], nets_torch.init_params(cfg["net"], cfg["C"], cfg["K"], seed=5))
+    t = [0.0, 0.0]
 
-    def step():
-        crop, idx, inst, flips, _, rot_on = th.next_plan()
-        # the reference's own rotation (isprs:294-296) for the patches the plan rotates
-        import scipy.ndimage
-        over_x = np.zeros((B, crop, crop, cfg["C"]), dtype=np.float64)
-        over_y = np.zeros((B, crop, crop), dtype=np.uint8)
-        for b in np.nonzero(rot_on)[0]:
-            r, c = int(inst[b, 1]), int(inst[b, 2])
-            over_x[b] = scipy.ndimage.rotate(img[r:r + crop, c:c + crop], int(th.angles[b]), order=0, reshape=False)
-            over_y[b] = scipy.ndimage.rotate(lab[r:r + crop, c:c + crop], int(th.angles[b]), order=0, reshape=False)
-        xs, ys = host_np.apply_plan([img], [lab], inst, flips, crop, mean, std, None, None, over_x, over_y, rot_on)
-        loss, pred, _ = orc.train_step(torch.from_numpy(xs.reshape(B, -1)), torch.from_numpy(ys.reshape(B, -1)), crop,
-                                       cfg["lr"], cfg["wd"])
-        acc, acc_norm, cm = host_np.confusion_by_crop(ys.astype(np.int64), pred.numpy(), cfg["K"])
-        th.update(idx, loss, cm)
-        return crop
+    def hook(step, pipe):
+        if step == warmup:
+            pipe.flush()
+            t[0] = time.perf_counter()
+        elif step == warmup + steps:
+            pipe.flush()
+            t[1] = time.perf_counter()
 
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    done, crops = 0, []
-    for _ in range(steps):
-        crops.append(step())
-        done += 1
-        if time.perf_counter() - t0 > budget_s:
-            break
-    dt = time.perf_counter() - t0
-    return dict(value=B * done / dt, unit="patches/s", cores=cores, kind="port", ms_per_step=dt / done * 1e3, steps=done,
-                sample="%d full steps (batch 64, crops %s) of the same seeded loop: NumPy gather + scipy order-0 rotation + normalise, PyTorch-CPU fp32 graph "
-                       "fwd+bwd+momentum, Python-loop calc_accuracy_by_crop; TensorFlow not installable (SURVEY F13)" % (done, crops))
+    if warmup == 0:
+        t[0] = time.perf_counter()
+    run_isprs_loop(be, wl, cfg, B, warmup + steps, hook, depth=0)
+    dt = t[1] - t[0]
+    crops = be.crops[warmup:warmup + steps]
+    return dict(value=B * steps / dt, unit="patches/s", cores=cores, kind="port", ms_per_step=dt / steps * 1e3, steps=steps,
+                patch_sizes_drawn=crops,
+                sample="%d full iterations (batch 64, crops %s) of the same seeded drop-in loop on the same 2000x2500x4 scene: Python "
+                       "dynamically_create_patches decisions + scipy order-0 rotation + np.random.normal noise + NumPy gather/normalise, "
+                       "PyTorch-CPU fp32 graph fwd+bwd+momentum, Python-loop calc_accuracy_by_crop; TensorFlow not installable "
+                       "(SURVEY F13)" % (steps, crops))
 
 
 def cpu_infer_baseline(batches=6):
@@ -499,9 +616,11 @@ def run_reference(args, rank, world):
         line = dict(metric="full-scene inference Mpixel/s", value=b["value"], unit=b["unit"], ms_per_step=None, dtype="f32",
                     scaling="strong", config={"workload": "configs[3] on the host cores (bounded sample, extrapolated)"})
     else:
-        b = cpu_train_baseline(args.steps, min(args.warmup, 1), budget_s=150.0)
+        b = cpu_train_baseline(args.steps, args.warmup)
         line = dict(metric="train patches/s", value=b["value"], unit=b["unit"], ms_per_step=b["ms_per_step"], dtype="f32",
-                    scaling="weak", config={"workload": "configs[1] on the host cores: " + b["sample"]})
+                    scaling="weak", config={"workload": "configs[1] on the host cores: " + b["sample"], "net": TRAIN_CFG["net"],
+                                            "batch_per_gpu": TRAIN_CFG["batch"], "global_batch": TRAIN_CFG["batch"],
+                                            "patch_sizes_drawn": b["patch_sizes_drawn"]})
     line.update(impl="reference", cpu_baseline=b, gpu_launches=0,
                 e2e={"value": b["value"], "unit": b["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
     return line
@@ -516,6 +635,7 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "infer"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the second headline metric")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cli", action="store_true", help="skip the command-line level rate")
     ap.add_argument("--small", action="store_true", help="1500x1500 inference scene (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -548,8 +668,10 @@ def main():
             base["impl"] = "ours"
             if second is not None:
                 base["inference"] = second
+            if world == 1 and not args.no_cli and args.workload == "train":
+                base["cli"] = cli_rate(TRAIN_CFG)
             if world == 1 and not args.no_cpu:
-                base["cpu_baseline"] = cpu_train_baseline(4, 1, budget_s=20.0) if args.workload == "train" else cpu_infer_baseline()
+                base["cpu_baseline"] = cpu_train_baseline(8, 2) if args.workload == "train" else cpu_infer_baseline()
                 if second is not None:
                     base["inference"]["cpu_baseline"] = cpu_infer_baseline()
             print(json.dumps(base), flush=True)

@@ -35,6 +35,8 @@ class GpuBackend:
         self._amask_on_dev = False
         self.rotate_on_device = True      # isprs rotation augmentation in the gather kernel (plan_isprs_batch flag)
         self.pinned_plans = True          # plan slots are page-locked (asynchronous uploads, host.PlanSlot)
+        import os
+        self._dp_debug = os.environ.get("DRS_DP_DEBUG", "0") != "0"
         self._cm = torch.zeros(self.K * self.K + 1, dtype=torch.int32, device=self.dev)
         session.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
 
@@ -118,8 +120,54 @@ class GpuBackend:
                               over_x=plan.over_x, over_y=plan.over_y, over_on=plan.over_on)
         return x, y, pred, B, crop
 
+    def sync_host_rng(self):
+        """Data parallel: every rank must run the SAME host policy (patch size, batch selection, augmentation draws), i.e. the
+        same two random streams.  The reference never seeds, and cache files created by rank 0 only make the ranks
+        consume different amounts of the streams, so the loops call this before the first draw and after every cache block:
+        rank 0 draws one seed from its own stream and every rank re-seeds ``random`` and ``np.random`` with it."""
+        if self.world <= 1:
+            return
+        import random
+        import zlib
+        import torch.distributed as dist
+        st = np.random.get_state()
+        h = zlib.crc32(st[1].tobytes() + repr(st[2:]).encode() + repr(random.getstate()).encode())
+        v = self.torch.tensor([h, -h], dtype=self.torch.int64, device=self.dev)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        if int(v[0]) == -int(v[1]):
+            return                       # already on the same streams (a harness seeded every rank alike)
+        t = self.torch.tensor([np.random.randint(0, 2 ** 31 - 1) if self.rank == 0 else 0], dtype=self.torch.int64, device=self.dev)
+        dist.broadcast(t, src=0)
+        seed = int(t.item())
+        np.random.seed(seed)
+        random.seed(seed)
+
+    def rank0_first(self, fn):
+        """Cache files in the working directory (isprs:2087-2115, 1634-1639): rank 0 creates them, the others wait and load."""
+        if self.world <= 1:
+            return fn()
+        import torch.distributed as dist
+        if self.rank == 0:
+            r = fn()
+            dist.barrier()
+            return r
+        dist.barrier()
+        return fn()
+
+    def _check_same_plan(self, plan):
+        """DRS_DP_DEBUG=1: assert that patch size and batch are identical on every rank before the step is enqueued."""
+        import zlib
+        import torch.distributed as dist
+        h = zlib.crc32(np.ascontiguousarray(plan.inst).tobytes() + np.ascontiguousarray(plan.flips).tobytes())
+        v = self.torch.tensor([plan.crop, h, -plan.crop, -h], dtype=self.torch.int64, device=self.dev)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        if int(v[0]) != -int(v[2]) or int(v[1]) != -int(v[3]):
+            raise RuntimeError("data-parallel ranks disagree on the step plan (patch size / batch): host RNG streams diverged")
+
     def submit_train(self, plan, loss_mask=None):
         t = self.torch
+        if self.world > 1 and self._dp_debug:
+            self._check_same_plan(plan)
         if self.train_fp16_patches:
             self.s.set_gather_fp16(True)
         x, y, pred, B, crop = self._gather(plan, shard=True)

@@ -26,6 +26,28 @@ def dist_setup():
     return rank, world, local
 
 
+def rank0_first(fn):
+    """Cache files in the working directory (isprs:2087-2115): under torchrun rank 0 runs ``fn`` (which may create and save),
+    the others wait at a barrier and run it afterwards (finding the files and loading them).  Writers save to a temporary
+    name and os.replace it, so a reader never sees a half-written file."""
+    rank, world, _ = dist_setup()
+    if world <= 1:
+        return fn()
+    import torch.distributed as dist
+    if rank == 0:
+        r = fn()
+        dist.barrier()
+        return r
+    dist.barrier()
+    return fn()
+
+
+def save_atomic(path, array, **kw):
+    tmp = path + '.tmp.npy'
+    np.save(tmp, array, **kw)
+    os.replace(tmp, path)
+
+
 def load_npy_scenes(path, instances, prefix=""):
     """Scenes as ``<path>/<prefix><instance>_image.npy`` ([H,W,C] float64/float32) + ``..._labels.npy`` ([H,W] uint8).
 

@@ -323,6 +323,7 @@ static void accumulate_chunk(Handle* h, const ScenePass& sp, const CellTables& c
   ap.logits = logits; ap.cell_off = sp.cell_off; ap.cell_seq = sp.cell_seq; ap.prob = sp.prob; ap.occur = sp.occur;
   ap.H = H; ap.W = W; ap.K = K; ap.crop = crop; ap.stride = ct.stride; ap.nh = ct.nh; ap.nw = ct.nw;
   ap.row_begin = row_begin; ap.row_end = row_end; ap.y_lo = y_lo; ap.y_hi = y_hi; ap.seq0 = seq0; ap.seq1 = seq1;
+  ap.overflow = h->diag_dev + 15;
   dim3 grid(nblk(W, 128), (unsigned)(y_hi - y_lo));
   accumulate_kernel<<<grid, 128, 0, h->stream>>>(ap);
   LAUNCH_CHECK(h);
@@ -348,6 +349,10 @@ static void scene_pass_finish(Handle* h, ScenePass& sp, int rows, int W, int K, 
   CUDA_CHECK(cudaMemcpyAsync(labels_host, lab_dev, npix, cudaMemcpyDeviceToHost, h->stream));
   if (mean_host) CUDA_CHECK(cudaMemcpyAsync(mean_host, mean_dev, npix * K * 8, cudaMemcpyDeviceToHost, h->stream));
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (h->diag_host[15]) {
+    h->diag_host[15] = 0;
+    DRS_FAIL("accumulate: a pixel is covered by more than %d patch visits of one chunk; the label map would be wrong", ACCUM_MAX_CONTRIB);
+  }
 }
 
 extern "C" int drs_accumulate_argmax(drs_handle_t h, const float* logits_dev, const int32_t* pos_host, int32_t P, int32_t crop,
@@ -420,6 +425,7 @@ struct HostSceneFeed {
   const char* host = nullptr;    // [H,W,C] in the scene dtype, row-major
   size_t row_bytes = 0;
   int uploaded = 0;              // rows [0, uploaded) are enqueued
+  bool recorded = false;         // up_ev[0] has been recorded at least once during this pass
 };
 
 static void feed_rows(Handle* h, HostSceneFeed& f, const Scene& sc, int rows_needed, cudaStream_t consumer) {
@@ -438,8 +444,12 @@ static void feed_rows(Handle* h, HostSceneFeed& f, const Scene& sc, int rows_nee
   }
   if (any) {
     CUDA_CHECK(cudaEventRecord(x->up_ev[0], x->copy_stream));
-    CUDA_CHECK(cudaStreamWaitEvent(consumer, x->up_ev[0], 0));   // copies on one stream complete in order
+    f.recorded = true;
   }
+  // Every consumer waits for the latest "rows uploaded" event, also when this call enqueued nothing: with two lanes the
+  // rows a lane needs may have been enqueued by the OTHER lane's look-ahead, and that lane's stream never saw the event.
+  // (Copies on one stream complete in order, so the latest event covers every earlier piece.)
+  if (f.recorded) CUDA_CHECK(cudaStreamWaitEvent(consumer, x->up_ev[0], 0));
 }
 
 static void scene_infer_impl(drs_handle_t h, int32_t scene_id, int32_t crop, int32_t batch, int32_t variant, int32_t row_begin,

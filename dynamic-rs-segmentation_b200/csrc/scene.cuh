@@ -180,7 +180,9 @@ struct AccumParams {
   int row_begin, row_end;   // stripe owned by this rank
   int y_lo, y_hi;           // pixel rows touched by this chunk (clipped to the stripe)
   int seq0, seq1;           // visit numbers held in `logits`
+  uint32_t* overflow;       // host-mapped flag: a pixel had more contributions in one chunk than the kernel can order
 };
+constexpr int ACCUM_MAX_CONTRIB = 32;   // 4 x 4 covering lattice cells (odd crop + shifted border row/col), each visited at most twice (contest)
 
 __device__ __forceinline__ int cover_range(int y, int L, int crop, int stride, int n, int* first, int* extra) {
   // regular origins i*s for i in [0, n-2] (and n-1 when the last origin is not shifted), last origin L-crop
@@ -204,7 +206,7 @@ __global__ void accumulate_kernel(const AccumParams p) {
   const int ni = cover_range(y, p.H, p.crop, p.stride, p.nh, &i0, &iex);
   const int nj = cover_range(x, p.W, p.crop, p.stride, p.nw, &j0, &jex);
   const int ti = (ni > 0 ? ni : 0) + iex, tj = (nj > 0 ? nj : 0) + jex;
-  int seqs[32], oy[32], ox[32];
+  int seqs[ACCUM_MAX_CONTRIB], oy[ACCUM_MAX_CONTRIB], ox[ACCUM_MAX_CONTRIB];
   int n = 0;
   for (int a = 0; a < ti; ++a) {
     const int i = (a < ni) ? i0 + a : p.nh - 1;
@@ -215,7 +217,9 @@ __global__ void accumulate_kernel(const AccumParams p) {
       const int cell = i * p.nw + j;
       for (int v = p.cell_off[cell]; v < p.cell_off[cell + 1]; ++v) {
         const int s = p.cell_seq[v];
-        if (s >= p.seq0 && s < p.seq1 && n < 32) {
+        if (s >= p.seq0 && s < p.seq1 && n >= ACCUM_MAX_CONTRIB) {
+          *p.overflow = 1u;        // never dropped silently: the pass fails (scene_pass_finish)
+        } else if (s >= p.seq0 && s < p.seq1) {
           // insertion keeps ascending visit order
           int k = n++;
           while (k > 0 && seqs[k - 1] > s) {

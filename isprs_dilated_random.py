@@ -66,24 +66,35 @@ def main():
         print(BatchColors.WARNING + 'Creating TESTING class distribution...' + BatchColors.ENDC)
         testing_class_distribution = host.create_distributions_over_classes(testing_labels, reference_crop_size,
                                                                             reference_stride_crop, NUM_CLASSES)
-    if os.path.isfile(tag + '_rotation.npy'):
-        training_rotation_distribution = np.load(tag + '_rotation.npy', allow_pickle=True)
-        print(BatchColors.OKGREEN + 'Loaded training instance rotations' + BatchColors.ENDC)
-    elif training_class_distribution is not None:
-        training_rotation_distribution = host.create_rotation_distribution(training_class_distribution)
-        np.save(tag + '_rotation.npy', np.asarray(training_rotation_distribution, dtype=object), allow_pickle=True)
-        print(BatchColors.OKGREEN + 'Created training instance rotations' + BatchColors.ENDC)
-    if os.path.isfile(tag + '_mean.npy'):
-        mean_full, std_full = np.load(tag + '_mean.npy'), np.load(tag + '_std.npy')
-        print(BatchColors.OKGREEN + 'Loaded Mean/Std from training instances' + BatchColors.ENDC)
-    else:
+    def _rotation():
+        if os.path.isfile(tag + '_rotation.npy'):
+            r = np.load(tag + '_rotation.npy', allow_pickle=True)
+            print(BatchColors.OKGREEN + 'Loaded training instance rotations' + BatchColors.ENDC)
+            return r
         if training_class_distribution is None:
-            training_class_distribution = host.create_distributions_over_classes(training_labels, reference_crop_size,
-                                                                                 reference_stride_crop, NUM_CLASSES, verbose=False)
-        mean_full, std_full = host.dynamically_calculate_mean_and_std(training_data, training_class_distribution, crop_size=25)
-        np.save(tag + '_mean.npy', mean_full)
-        np.save(tag + '_std.npy', std_full)
+            return None
+        r = host.create_rotation_distribution(training_class_distribution)
+        cli.save_atomic(tag + '_rotation.npy', np.asarray(r, dtype=object), allow_pickle=True)
+        print(BatchColors.OKGREEN + 'Created training instance rotations' + BatchColors.ENDC)
+        return r
+
+    def _mean_std():
+        if os.path.isfile(tag + '_mean.npy') and os.path.isfile(tag + '_std.npy'):
+            print(BatchColors.OKGREEN + 'Loaded Mean/Std from training instances' + BatchColors.ENDC)
+            return np.load(tag + '_mean.npy'), np.load(tag + '_std.npy')
+        distr = training_class_distribution
+        if distr is None:
+            distr = host.create_distributions_over_classes(training_labels, reference_crop_size, reference_stride_crop, NUM_CLASSES,
+                                                           verbose=False)
+        m, sd = host.dynamically_calculate_mean_and_std(training_data, distr, crop_size=25)
+        cli.save_atomic(tag + '_std.npy', sd)
+        cli.save_atomic(tag + '_mean.npy', m)
         print(BatchColors.OKGREEN + 'Created Mean/Std from training instances' + BatchColors.ENDC)
+        return m, sd
+
+    # under torchrun rank 0 creates the cache files, the other ranks wait and load them (no half-written reads, one table)
+    training_rotation_distribution = cli.rank0_first(_rotation)
+    mean_full, std_full = cli.rank0_first(_mean_std)
 
     channels = training_data[0].shape[-1]
     if process == 'training':

@@ -233,6 +233,67 @@ def test_rotation_on_device_equals_scipy(drs, golden):
     s.close()
 
 
+def test_native_plan_async_path_equals_host_rotated_reference_path(drs, golden):
+    """The product configuration of one training iteration -- native planner (csrc/host_plan.cpp), pinned plan slot uploaded
+    asynchronously (drs_gather_plan_dev, compact noise), rotation on the device, drs_train_step_async / drs_train_result --
+    against the path the reference takes: Python planner with scipy rotation on the host, dense noise, synchronous step.
+    Gathered patches, labels and accuracy masks must be bit-identical; loss and confusion counts of the step identical."""
+    import torch
+    from drs_b200 import host
+    scenes, labs = golden["gather_scenes"], golden["gather_labels"]
+    mean, std = golden["norm_mean"], golden["norm_std"]
+    K = 6
+    sa = drs.Session("dilated_grsl", 4, K, precision="bf16", seed=3)
+    sb = drs.Session("dilated_grsl", 4, K, precision="bf16", seed=3)
+    for s in (sa, sb):
+        for i in range(2):
+            s.upload_scene(i, scenes[i], labs[i])
+        s.set_normalization(mean, std)
+    planner = host.NativePlanner(threads=2)
+    hw = np.asarray([sc.shape[:2] for sc in scenes], dtype=np.int32)
+    rs = np.random.RandomState(8)
+    B = 32
+    slots = [host.PlanSlot(B, 31, 4, pinned=True) for _ in range(3)]
+    tickets, want = [], []
+    for it, crop in enumerate((25, 31, 26, 25, 31)):
+        H, W = scenes[0].shape[:2]
+        inst = np.array([(int(rs.randint(0, 2)), int(rs.randint(0, H)), int(rs.randint(0, W)), int(rs.randint(0, 360)))
+                         for _ in range(B)], dtype=np.int64)
+        np.random.seed(500 + it)
+        plan_h = host.plan_isprs_batch(scenes, labs, inst, crop, is_train=True)
+        st_py = np.random.get_state()
+        np.random.seed(500 + it)
+        plan_n = planner.plan(hw, inst, crop, 4, slot=slots[it % 3])
+        st_n = np.random.get_state()
+        assert np.array_equal(st_py[1], st_n[1]) and st_py[2:] == st_n[2:]
+        n = B * crop * crop
+        xh, yh = torch.empty(n * 4, dtype=torch.float32, device="cuda"), torch.empty(n, dtype=torch.float32, device="cuda")
+        xn, yn = torch.empty_like(xh), torch.empty_like(yh)
+        am = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
+        pa, pb = torch.empty(n, dtype=torch.uint8, device="cuda"), torch.empty(n, dtype=torch.uint8, device="cuda")
+        sb.gather_dev(plan_h.inst, plan_h.flips, crop, xh, yh, noise=plan_h.noise, noise_on=plan_h.noise_on, over_x=plan_h.over_x,
+                      over_y=plan_h.over_y, over_on=plan_h.over_on)
+        sa.gather_plan_dev(plan_n, xn, yn, am)
+        assert torch.equal(xh, xn) and torch.equal(yh, yn)
+        acc_mask = plan_h.acc_mask if plan_h.acc_mask is not None else np.ones((B, crop, crop), dtype=np.uint8)
+        assert np.array_equal(am.cpu().numpy().reshape(B, crop, crop), acc_mask)
+        tickets.append(sa.train_step_async(xn, yn, B, crop, pred_dev=pa, acc_mask_dev=am))
+        amh = torch.from_numpy(np.ascontiguousarray(acc_mask.reshape(-1))).cuda()
+        cm_dev = torch.zeros(K * K + 1, dtype=torch.int32, device="cuda")
+        loss = sb.train_step_dev(xh, yh, B, crop, pred_dev=pb, cm_dev=cm_dev, acc_mask_dev=amh)
+        want.append((float(loss), cm_dev.cpu().numpy().astype(np.uint32)))
+        assert torch.equal(pa, pb)
+    for t, (loss, cm) in zip(tickets, want):          # results fetched late, in order (the ring holds 8)
+        l2, cm2, acc2 = sa.train_result(t)
+        assert float(l2) == loss
+        assert np.array_equal(cm2.reshape(-1), cm[:K * K]) and acc2 == int(cm[K * K])
+    with pytest.raises(drs.lib.DrsError):
+        sa.train_result(99)
+    planner.close()
+    sa.close()
+    sb.close()
+
+
 ACC_CASES = (("isprs", 120, 150, 25, 16, 6), ("isprs", 97, 131, 33, 7, 6), ("contest", 130, 100, 25, 16, 7),
              ("contest", 100, 130, 25, 16, 7), ("coffee", 64, 64, 25, 16, 2), ("isprs", 100, 100, 50, 4, 6),
              ("isprs", 61, 90, 30, 5, 3), ("isprs", 25, 25, 25, 4, 6))
