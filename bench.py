@@ -195,7 +195,7 @@ def run_train_ours(args, rank, world, local, cfg=None, sync_bn=False, extras=Tru
     be = GpuBackend(s, wl["train_data"] + wl["test_data"], wl["train_labels"] + wl["test_labels"], wl["mean"], wl["std"],
                     device=local, rank=rank, world=world)
     if world > 1:
-        ddist.attach_allreduce(s, sync_bn=sync_bn)
+        ddist.attach_nccl(s, sync_bn=sync_bn)
     B = cfg["batch"]
     W, K = args.warmup, args.steps
     depth = int(os.environ.get("DRS_PREFETCH", "2"))
@@ -354,7 +354,7 @@ def dp_check(s, be, cfg, rank, world, dev, sync_bn):
     y = rs.randint(0, K, size=(B, crop * crop)).astype(np.float32)
     sp = drs_b200.Session(cfg["net"], C, K, weight_decay=cfg["wd"], lr_initial=cfg["lr"], precision="fp32", device=dev.index, seed=5)
     sp.set_stream(torch.cuda.current_stream(dev).cuda_stream)
-    ddist.attach_allreduce(sp, sync_bn=True)
+    ddist.attach_nccl(sp, sync_bn=True)
     per = B // world
     loss_dp, _ = sp.train_step(x[rank * per:(rank + 1) * per], y[rank * per:(rank + 1) * per], crop)
     worst = 0.0
@@ -377,12 +377,14 @@ def dp_check(s, be, cfg, rank, world, dev, sync_bn):
     return res
 
 
-def run_infer_ours(args, rank, world, local, steps=1):
+def run_infer_ours(args, rank, world, local, steps=3, cfg=None):
+    """Full-scene sliding-window inference (isprs:1241-1284), row stripes over the ranks, label map assembled on rank 0.
+    `steps` whole passes are timed one by one (barrier + synchronize on both sides of each); value = median pass."""
     import torch
     import torch.distributed as dist
     import drs_b200
-    from drs_b200 import dist as ddist, nets, synth
-    cfg = INFER_CFG
+    from drs_b200 import dist as ddist, synth
+    cfg = cfg or INFER_CFG
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     H, W = cfg["H"], cfg["W"]
@@ -393,72 +395,87 @@ def run_infer_ours(args, rank, world, local, steps=1):
     s = drs_b200.Session(cfg["net"], cfg["C"], cfg["K"], precision="f16", device=local, seed=9)
     s.set_stream(torch.cuda.current_stream(dev).cuda_stream)
     s.set_normalization(mean, std)
-    r0, r1 = ddist.stripe_bounds(H, world, rank)
+    if world > 1:
+        ddist.attach_nccl(s)
+    cuts = ddist.stripe_bounds(H, world)
+    r0, r1 = cuts[rank], cuts[rank + 1]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def one_pass():
+        if world == 1:
+            return s.scene_infer(0, cfg["crop"], cfg["batch"], H, W)
+        # the stripe stays on the device; NCCL send/recv assembles the map on rank 0, one device-to-host copy there
+        s.scene_infer(0, cfg["crop"], cfg["batch"], H, W, row_begin=r0, row_end=r1, keep_on_device=True)
+        return s.scene_gather_labels(H, W, cuts, rank)
+
     # a rank keeps only the scene rows its stripe needs (the stripe plus the patch rows straddling its borders)
     u0, u1 = ddist.stripe_rows_needed(H, cfg["crop"], r0, r1) if world > 1 else (None, None)
     s.upload_scene(0, img, None, u0, u1)
     s.scene_infer(0, cfg["crop"], cfg["batch"], H, W, row_begin=r0, row_end=min(r1, r0 + 40))   # warm-up stripe (kernels)
-    s.scene_infer(0, cfg["crop"], cfg["batch"], H, W, row_begin=r0, row_end=r1)   # warm-up pass: stripe-sized buffers allocated
+    one_pass()                                   # warm-up pass: stripe-sized buffers, geometry tables, first collective
     barrier()
-    l0 = s.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0.record()
+    times, launches = [], 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(steps):
-        stripe = s.scene_infer(0, cfg["crop"], cfg["batch"], H, W, row_begin=r0, row_end=r1)
-        full = ddist.gather_label_stripes(stripe, H, W, rank, world, device=dev)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / steps
-    launches = s.launch_count - l0
+        barrier()
+        l0 = s.launch_count
+        e0.record()
+        one_pass()
+        e1.record()
+        barrier()
+        times.append(e0.elapsed_time(e1))
+        launches = s.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
     # kernel timing pass (roofline): the same pass once more with a CUDA-event pair around every tensor-core launch
     s.set_profiling(True)
-    s.scene_infer(0, cfg["crop"], cfg["batch"], H, W, row_begin=r0, row_end=r1)
+    s.scene_infer(0, cfg["crop"], cfg["batch"], H, W, row_begin=r0, row_end=r1, keep_on_device=True)
     barrier()
     conv_ms, conv_n, conv_fl = s.profile_read()
-    conv_ms, conv_n, conv_fl = conv_ms * steps, conv_n * steps, conv_fl * steps      # (reported per step below)
     s.set_profiling(False)
     # end to end: host scene -> HBM -> label map on the host
-    barrier()
-    e0.record()
-    if world == 1:
-        # a fresh tile: the upload is streamed ahead of the chunks that read it (drs_scene_infer_host)
-        stripe = s.scene_infer_host(0, img, cfg["crop"], cfg["batch"])
-    else:
-        s.upload_scene(0, img, None, u0, u1)
-        stripe = s.scene_infer(0, cfg["crop"], cfg["batch"], H, W, row_begin=r0, row_end=r1)
-    full = ddist.gather_label_stripes(stripe, H, W, rank, world, device=dev)
-    e1.record()
-    barrier()
-    ms2 = e0.elapsed_time(e1)
+    e2e_times = []
+    for _ in range(max(1, min(steps, 2))):
+        barrier()
+        e0.record()
+        if world == 1:
+            # a fresh tile: the upload is streamed ahead of the chunks that read it (drs_scene_infer_host)
+            s.scene_infer_host(0, img, cfg["crop"], cfg["batch"])
+        else:
+            s.upload_scene(0, img, None, u0, u1)
+            one_pass()
+        e1.record()
+        barrier()
+        e2e_times.append(e0.elapsed_time(e1))
+    ms, ms2 = float(np.median(times)), float(np.median(e2e_times))
     if world > 1:
         t = torch.tensor([ms, ms2], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms2 = float(t[0].item()), float(t[1].item())
     s.close()
     pk = peaks()
-    ach = (conv_fl / steps / (conv_ms / steps * 1e-3) / 1e12) if conv_ms > 0 else None
+    capped = bool(clocks and "sw_power_cap" in (clocks.get("reasons") or []))
+    peak = pk["tc_sustained"] if capped else pk["tc_burst"]
+    ach = (conv_fl / (conv_ms * 1e-3) / 1e12) if conv_ms > 0 else None
     return dict(metric="full-scene inference Mpixel/s", value=H * W / 1e6 / (ms / 1e3), unit="Mpixel/s", ms_per_step=ms,
-                dtype="f16", scaling="strong",
+                passes_ms=[round(t, 2) for t in times], dtype="f16", scaling="strong",
                 e2e={"value": H * W / 1e6 / (ms2 / 1e3), "unit": "Mpixel/s", "h2d_bytes_per_step": int(img.nbytes if u0 is None else img[u0:u1].nbytes),
                      "d2h_bytes_per_step": int(H * W), "api": "Session.scene_infer_host (host scene in, upload streamed under the pass, host label map out)" if world == 1 else
-                            "Session.upload_scene + Session.scene_infer (host stripe in, host label map out)"},
+                            "Session.upload_scene + Session.scene_infer + scene_gather_labels (host stripe in, host label map out on rank 0)"},
                 gpu_launches=launches, clocks=clocks,
-                roofline={"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 fprop)", "achieved": ach, "peak": pk["tc_sustained"],
-                          "unit": "TFLOP/s", "frac": ach / pk["tc_sustained"] if ach else None, "traffic": profiled_traffic("inference"),
-                          "peak_source": pk["source"] + " bf16 sustained", "launches": conv_n,
-                          "kernel_ms_per_step": conv_ms / steps},
-                config={"workload": "configs[3]: dilated_grsl_rate8 full-scene sliding-window inference, Potsdam-shaped %dx%dx5 "
-                                    "float64, crop 25 stride 12, row stripes over %d GPU(s)" % (H, W, world),
+                roofline={"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 fprop)", "achieved": ach, "peak": peak,
+                          "unit": "TFLOP/s", "frac": ach / peak if ach else None, "traffic": profiled_traffic("inference"),
+                          "peak_source": pk["source"] + (" bf16 sustained (sw_power_cap seen)" if capped else " bf16 burst"), "launches": conv_n,
+                          "kernel_ms_per_step": conv_ms},
+                config={"workload": "configs[3]: %s full-scene sliding-window inference, %s-shaped %dx%dx%d "
+                                    "float64, crop %d stride %d, row stripes over %d GPU(s); median of %d passes" %
+                                    (cfg["net"], cfg["dataset"], H, W, cfg["C"], cfg["crop"], cfg["crop"] // 2, world, steps),
                         "net": cfg["net"], "crop": cfg["crop"], "patches": int(len(drs_b200.grid_positions(H, W, cfg["crop"], cfg["batch"]))),
                         "parallelism": "stripes%d" % world, "l2": "scene (%.0f MB) and activations exceed L2" % (img.nbytes / 1e6)})
 
@@ -659,9 +676,13 @@ def main():
     try:
         if args.workload == "train":
             line = run_train_ours(args, rank, world, local)
+            if world > 1 and not args.no_secondary:
+                # the parity mode of data parallelism: BN statistics over the global batch, forward and backward
+                sb = run_train_ours(args, rank, world, local, sync_bn=True, extras=False)
+                line["sync_bn"] = {k: sb[k] for k in ("value", "unit", "ms_per_step", "gpu_launches")}
             second = None if args.no_secondary else run_infer_ours(args, rank, world, local)
         else:
-            line = run_infer_ours(args, rank, world, local, steps=max(1, min(args.steps, 3)))
+            line = run_infer_ours(args, rank, world, local, steps=max(3, min(args.steps, 5)))
             second = None
         if rank == 0:
             base.update(line)

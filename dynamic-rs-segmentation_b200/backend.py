@@ -74,7 +74,7 @@ class GpuBackend:
         self.s.reserve(per, crops[-1], training=True)
         if isinstance(loss_mask, str):
             self.s.set_ignore_label(int(loss_mask.split("!=")[1]))
-        if self.world > 1:
+        if self.world > 1 and not self.s.has_nccl:
             return          # the exchange goes through a host callback: not capturable
         self.s.prepare_training(x, y, per, crops, pred_dev=pred, acc_mask_dev=self._amask if isprs else None)
 
@@ -230,6 +230,10 @@ class GpuBackend:
             return self.s.scene_infer(scene_id, crop, batch, H, W, variant=variant)
         from . import dist as ddist
         r0, r1 = ddist.stripe_bounds(H, self.world, self.rank)
+        if self.s.has_nccl:
+            # stripes stay on the device: NCCL send/recv to rank 0, broadcast of the assembled map (every rank prints metrics)
+            self.s.scene_infer(scene_id, crop, batch, H, W, variant=variant, row_begin=r0, row_end=r1, keep_on_device=True)
+            return self.s.scene_gather_labels(H, W, ddist.stripe_bounds(H, self.world), self.rank, all_ranks=True)
         stripe = self.s.scene_infer(scene_id, crop, batch, H, W, variant=variant, row_begin=r0, row_end=r1)
         return ddist.gather_label_stripes(stripe, H, W, self.rank, self.world, device=self.dev, all_ranks=True)
 

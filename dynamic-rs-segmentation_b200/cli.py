@@ -81,5 +81,9 @@ def make_backend(net_type, channels, num_classes, weight_decay, lr_initial, deca
     be = GpuBackend(s, scenes, label_maps, mean_full, std_full, device=local, rank=rank, world=world,
                     train_fp16_patches=train_fp16_patches)
     if world > 1:
-        ddist.attach_allreduce(s, sync_bn=bool(int(os.environ.get("DRS_SYNC_BN", "0"))))
+        sync_bn = bool(int(os.environ.get("DRS_SYNC_BN", "0")))
+        if os.environ.get("DRS_COMM", "nccl") == "torch":
+            ddist.attach_allreduce(s, sync_bn=sync_bn)       # exchange through a torch.distributed callback
+        else:
+            ddist.attach_nccl(s, sync_bn=sync_bn)            # the library's own NCCL communicator (csrc/drs_comm.cuh)
     return be

@@ -159,6 +159,8 @@ struct HandleExtra {
   // pipelined training loop (drs_gather_plan_dev / drs_train_step_async / drs_train_result): the plan of step i+1 is
   // uploaded on plan_stream into a two-slot device staging ring while step i runs; loss + confusion counts of each step
   // land in a ring of pinned result slots behind an event, so the host never blocks on the step it has just enqueued
+  void* nccl = nullptr;             // ncclComm_t of drs_comm_init (drs_comm.cuh); null: single process or callback exchange
+  int rank = 0;
   cudaStream_t plan_stream = nullptr;
   void* plan_stage[2] = {nullptr, nullptr};
   size_t plan_stage_cap[2] = {0, 0};
@@ -189,6 +191,7 @@ static void* slot_buf(Handle* h, int slot, size_t bytes) {
   return x->slot_ptr[slot];
 }
 static void lanes_release(Handle* h);
+static void pass_geometry_release(Handle* h);
 
 static void free_packed(Handle* h) {
   for (auto& c : h->net.convs) {
@@ -308,6 +311,8 @@ extern "C" int drs_destroy(drs_handle_t h) {
   cudaStreamSynchronize(h->stream);
   HandleExtra* x = X(h);
   if (x) {
+    if (x->nccl) { drs_comm_destroy(h); }
+    pass_geometry_release(h);
     if (x->side_stream) { cudaStreamSynchronize(x->side_stream); cudaStreamDestroy(x->side_stream); }
     if (x->comm_stream) { cudaStreamSynchronize(x->comm_stream); cudaStreamDestroy(x->comm_stream); }
     if (x->ev_bucket_ready) cudaEventDestroy(x->ev_bucket_ready);
@@ -489,12 +494,7 @@ extern "C" int drs_set_allreduce(drs_handle_t h, drs_allreduce_fn fn, void* user
   h->sync_bn = fn ? sync_bn : 0;
   API_END
 }
-static void do_allreduce(Handle* h, float* buf, int64_t count, cudaStream_t on_stream = (cudaStream_t)(uintptr_t)1) {
-  if (!h->allreduce || h->world <= 1) return;
-  const cudaStream_t st = on_stream == (cudaStream_t)(uintptr_t)1 ? h->stream : on_stream;
-  int rc = h->allreduce(h->allreduce_user, buf, count, (void*)st);
-  DRS_CHECK(rc == 0, "allreduce callback failed with %d", rc);
-}
+#include "drs_comm.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // packed operands / folded BN refresh (after set_variable or an optimizer step)

@@ -346,7 +346,7 @@ static void scene_pass_finish(Handle* h, ScenePass& sp, int rows, int W, int K, 
   double* mean_dev = mean_host ? (double*)slot_buf(h, 5, npix * K * 8) : nullptr;
   scene_argmax_kernel<<<nblk(npix, 256), 256, 0, h->stream>>>(sp.prob, sp.occur, npix, K, lab_dev, mean_dev);
   LAUNCH_CHECK(h);
-  CUDA_CHECK(cudaMemcpyAsync(labels_host, lab_dev, npix, cudaMemcpyDeviceToHost, h->stream));
+  if (labels_host) CUDA_CHECK(cudaMemcpyAsync(labels_host, lab_dev, npix, cudaMemcpyDeviceToHost, h->stream));
   if (mean_host) CUDA_CHECK(cudaMemcpyAsync(mean_host, mean_dev, npix * K * 8, cudaMemcpyDeviceToHost, h->stream));
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   if (h->diag_host[15]) {
@@ -494,9 +494,38 @@ extern "C" int drs_scene_infer_host(drs_handle_t h, int32_t scene_id, const void
   API_END
 }
 
+struct PassGeometry {
+  int key[8];
+  std::vector<int32_t> pos, inst;
+  CellTables ct;
+};
+static std::map<Handle*, std::vector<PassGeometry>> g_pass_geometry;
+static void pass_geometry_release(Handle* h) { g_pass_geometry.erase(h); }
+
+static PassGeometry& pass_geometry(Handle* h, int scene_id, int H, int W, int crop, int batch, int variant, int row_begin, int row_end) {
+  std::vector<PassGeometry>& cache = g_pass_geometry[h];
+  const int key[8] = {scene_id, H, W, crop, batch, variant, row_begin, row_end};
+  for (auto& g : cache)
+    if (memcmp(g.key, key, sizeof(key)) == 0) return g;
+  if (cache.size() >= 8) cache.erase(cache.begin());
+  cache.emplace_back();
+  PassGeometry& g = cache.back();
+  memcpy(g.key, key, sizeof(key));
+  std::vector<int32_t> all;
+  grid_positions(H, W, crop, batch, variant, all);
+  for (size_t p = 0; p < all.size() / 2; ++p)
+    if (all[2 * p] < row_end && all[2 * p] + crop > row_begin) { g.pos.push_back(all[2 * p]); g.pos.push_back(all[2 * p + 1]); }
+  build_cells(g.pos, H, W, crop, g.ct);
+  const size_t P = g.pos.size() / 2;
+  g.inst.resize(P * 3);
+  for (size_t p = 0; p < P; ++p) { g.inst[3 * p] = scene_id; g.inst[3 * p + 1] = g.pos[2 * p]; g.inst[3 * p + 2] = g.pos[2 * p + 1]; }
+  return g;
+}
+
 static void scene_infer_impl(drs_handle_t h, int32_t scene_id, int32_t crop, int32_t batch, int32_t variant, int32_t row_begin,
                              int32_t row_end, uint8_t* labels_out_host, double* mean_out_host, HostSceneFeed* feed) {
-  DRS_CHECK(h && labels_out_host, "null argument");
+  // labels_out_host may be NULL: the stripe stays on the device for drs_scene_gather_labels / drs_scene_confusion
+  DRS_CHECK(h, "null argument");
   CUDA_CHECK(cudaSetDevice(h->cfg.device));
   auto it = h->scenes.find(scene_id);
   DRS_CHECK(it != h->scenes.end(), "scene_infer: scene %d not uploaded", scene_id);
@@ -505,18 +534,17 @@ static void scene_infer_impl(drs_handle_t h, int32_t scene_id, int32_t crop, int
   if (row_end <= 0 || row_end > H) row_end = H;
   if (row_begin < 0) row_begin = 0;
   DRS_CHECK(row_begin < row_end, "scene_infer: empty stripe");
-  // visiting order of the script, restricted to patches that touch the stripe (order preserved)
-  std::vector<int32_t> all, pos;
-  grid_positions(H, W, crop, batch, variant, all);
-  for (size_t p = 0; p < all.size() / 2; ++p)
-    if (all[2 * p] < row_end && all[2 * p] + crop > row_begin) { pos.push_back(all[2 * p]); pos.push_back(all[2 * p + 1]); }
+  // visiting order of the script, restricted to patches that touch the stripe (order preserved), with its per-cell visit
+  // tables: pure functions of the geometry, memoised (a validation run visits the same scenes with the same crop again
+  // and again; for a 6000x6000 tile they take several milliseconds of host time per call)
+  PassGeometry& pg = pass_geometry(h, scene_id, H, W, crop, batch, variant, row_begin, row_end);
+  const std::vector<int32_t>& pos = pg.pos;
+  const CellTables& ct = pg.ct;
   const int P = (int)(pos.size() / 2);
   for (int p = 0; p < P; ++p)
     DRS_CHECK(pos[2 * p] >= sc.row0 && pos[2 * p] + crop <= sc.row0 + sc.rows,
               "scene_infer: stripe [%d,%d) needs scene rows [%d,%d) but only [%d,%d) are resident", row_begin, row_end, pos[2 * p],
               pos[2 * p] + crop, sc.row0, sc.row0 + sc.rows);
-  CellTables ct;
-  build_cells(pos, H, W, crop, ct);
   const int rows = row_end - row_begin;
   // chunk = a whole number of 128-pixel tiles close to a multiple of the SM count (full conv waves), ~0.75 M pixels
   const int64_t pp = (int64_t)crop * crop;
@@ -541,8 +569,7 @@ static void scene_infer_impl(drs_handle_t h, int32_t scene_id, int32_t crop, int
   };
   try {
     scene_pass_begin(h, sp, ct, rows, W, K);
-    std::vector<int32_t> inst((size_t)P * 3);
-    for (int p = 0; p < P; ++p) { inst[3 * p] = scene_id; inst[3 * p + 1] = pos[2 * p]; inst[3 * p + 2] = pos[2 * p + 1]; }
+    const std::vector<int32_t>& inst = pg.inst;
     inst_dev = (int32_t*)slot_buf(h, 6, std::max<size_t>(inst.size(), 1) * 4);
     CUDA_CHECK(cudaMemcpyAsync(inst_dev, inst.data(), inst.size() * 4, cudaMemcpyHostToDevice, h->stream));
     refresh_packed(h, false);                       // packed weights / folded BN once, before the lanes start

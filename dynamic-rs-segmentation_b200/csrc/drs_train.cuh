@@ -378,7 +378,8 @@ static void train_step(Handle* h, const float* x_dev, const float* y_dev, const 
   const size_t es = h->cfg.precision == DRS_PREC_FP32 ? 4 : 2;
   TrainGraph* replay = nullptr;
   // (the legacy default stream cannot be captured)
-  const bool graphable = x->use_graphs && h->world <= 1 && !getenv("DRS_DEBUG_KEEP") && !getenv("DRS_NO_GRAPHS") &&
+  // (data parallel: capturable only when the exchange is the in-library NCCL call, not a host callback)
+  const bool graphable = x->use_graphs && (h->world <= 1 || x->nccl) && !getenv("DRS_DEBUG_KEEP") && !getenv("DRS_NO_GRAPHS") &&
                          h->cfg.precision != DRS_PREC_F16 && h->stream != nullptr;
   if (!graphable) {
     if (capture_only) return;

@@ -67,6 +67,32 @@ def attach_allreduce(session, group=None, sync_bn=False):
     return world
 
 
+def comm_unique_id():
+    import ctypes as C
+    from . import lib as L
+    buf = (C.c_uint8 * 128)()
+    L.check(L.load().drs_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def attach_nccl(session, sync_bn=False, group=None):
+    """The library's own NCCL communicator (csrc/drs_comm.cuh): rank 0 creates the id, torch.distributed only carries the 128
+    bytes to the other ranks.  Every exchange of the step is then an ncclAllReduce enqueued by the library itself."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world <= 1:
+        return world
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=0, group=group)
+    session.comm_init(bytes(t.cpu().numpy().tobytes()), rank, world, sync_bn)
+    return world
+
+
 def rank_slice(batch, rank, world):
     """This rank's share of a global batch (contiguous, equal sizes)."""
     per = len(batch) // world

@@ -69,6 +69,10 @@ _SIGNATURES = {
     "drs_train_prepare": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     "drs_set_ignore_label": (C.c_int, [_P, C.c_int32]),
     "drs_set_allreduce": (C.c_int, [_P, ALLREDUCE_FN, _P, C.c_int32, C.c_int32]),
+    "drs_comm_unique_id": (C.c_int, [_P]),
+    "drs_comm_init": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32]),
+    "drs_comm_destroy": (C.c_int, [_P]),
+    "drs_scene_gather_labels": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
     "drs_scene_upload": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "drs_scene_upload_rows": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32]),
     "drs_scene_free": (C.c_int, [_P, C.c_int32]),

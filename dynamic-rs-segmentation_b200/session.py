@@ -38,6 +38,7 @@ class Session:
         L.check(self._lib.drs_create(C.byref(self._h), C.byref(cfg)))
         self._cb = None
         self._keep = []
+        self.has_nccl = False
         if seed is not None:
             self.init_variables(seed)
 
@@ -223,6 +224,23 @@ class Session:
         self._cb = L.ALLREDUCE_FN(_cb)
         L.check(self._lib.drs_set_allreduce(self._h, self._cb, None, int(world_size), int(bool(sync_bn))))
 
+    def comm_init(self, id128, rank, world, sync_bn=False):
+        """In-library NCCL communicator (drs_comm_init); ``id128`` from comm_unique_id() on rank 0, distributed by the host."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(id128))
+        L.check(self._lib.drs_comm_init(self._h, buf, int(rank), int(world), int(bool(sync_bn))))
+        self.has_nccl = True
+
+    def comm_destroy(self):
+        L.check(self._lib.drs_comm_destroy(self._h))
+
+    def scene_gather_labels(self, H, W, row_cuts, rank, all_ranks=False):
+        """Label stripes of the last scene_infer -> [H, W] on rank 0 (None elsewhere unless all_ranks), device to device over
+        NCCL."""
+        cuts = np.ascontiguousarray(np.asarray(row_cuts, dtype=np.int32))
+        out = np.empty((H, W), dtype=np.uint8) if (rank == 0 or all_ranks) else None
+        L.check(self._lib.drs_scene_gather_labels(self._h, int(H), int(W), L.ptr(cuts), int(bool(all_ranks)), L.ptr(out)))
+        return out
+
     # ---------------------------------------------------------------- scene path
     def upload_scene(self, scene_id, scene, labels=None, row_begin=None, row_end=None):
         """Keep a scene resident in HBM.  With row_begin/row_end only those rows are uploaded (a rank's stripe + halo,
@@ -305,11 +323,13 @@ class Session:
                                                 L.ptr(labels), L.ptr(mean)))
         return (labels, mean) if want_mean else labels
 
-    def scene_infer(self, scene_id, crop, batch, H, W, variant="isprs", row_begin=0, row_end=None, want_mean=False):
-        """The inner loop of validate_test / test / generate_final_maps (isprs:1249-1284) for one scene (stripe)."""
+    def scene_infer(self, scene_id, crop, batch, H, W, variant="isprs", row_begin=0, row_end=None, want_mean=False,
+                    keep_on_device=False):
+        """The inner loop of validate_test / test / generate_final_maps (isprs:1249-1284) for one scene (stripe).
+        keep_on_device: do not copy the label stripe back (scene_gather_labels / scene_confusion read it on the device)."""
         row_end = H if row_end is None else row_end
         rows = row_end - row_begin
-        labels = np.empty((rows, W), dtype=np.uint8)
+        labels = None if keep_on_device else np.empty((rows, W), dtype=np.uint8)
         mean = np.empty((rows, W, self.num_classes), dtype=np.float64) if want_mean else None
         L.check(self._lib.drs_scene_infer(self._h, scene_id, crop, batch, L.GRID[variant], row_begin, row_end,
                                           L.ptr(labels), L.ptr(mean)))

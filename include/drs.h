@@ -146,6 +146,22 @@ int drs_set_ignore_label(drs_handle_t h, int32_t label);
 typedef int (*drs_allreduce_fn)(void* user, float* buf_dev, int64_t count, void* cuda_stream);
 int drs_set_allreduce(drs_handle_t h, drs_allreduce_fn fn, void* user, int32_t world_size, int32_t sync_bn);
 
+/* In-library exchange (csrc/drs_comm.cuh): NCCL over NVLink / NVSwitch, dlopen'ed at run time (libnccl.so.2; a process that
+ * already holds torch's bundled copy gets the same instance).  Rank 0 obtains a 128-byte id, the host distributes it (any
+ * transport: torch.distributed, MPI, a file), every rank calls drs_comm_init.  From then on the step's exchanges are
+ * ncclAllReduce calls on the handle's streams -- no host callback, so the data-parallel step is captured as a CUDA graph
+ * like the single-GPU one -- and drs_set_allreduce is ignored.  sync_bn != 0: the per-layer BN sums are reduced over the
+ * global batch forward and backward (single-process parity mode). */
+int drs_comm_unique_id(uint8_t* id128_out);
+int drs_comm_init(drs_handle_t h, const uint8_t* id128, int32_t rank, int32_t world, int32_t sync_bn);
+int drs_comm_destroy(drs_handle_t h);
+/* Stripe-sharded scene pass: after drs_scene_infer over this rank's rows [row_cuts[rank], row_cuts[rank+1]) (labels_out_host
+ * may be NULL there), every rank sends its uint8 label stripe to rank 0 device-to-device; rank 0 receives [H, W] and copies it
+ * to labels_out_host once (NULL on the other ranks; with all_ranks != 0 the assembled map is broadcast and every rank
+ * receives it).  row_cuts has world+1 entries. */
+int drs_scene_gather_labels(drs_handle_t h, int32_t H, int32_t W, const int32_t* row_cuts, int32_t all_ranks,
+                            uint8_t* labels_out_host);
+
 /* ---- scene path: NumPy loops around sess.run ----------------------------------------- */
 /* Keep a scene resident in HBM (replaces the per-batch NumPy slicing of isprs:259, 364).
  * scene [H,W,C] float64 (isprs img_as_float) or float32 (contest/coffee); labels [H,W] uint8 or NULL. */

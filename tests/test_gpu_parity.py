@@ -274,6 +274,8 @@ def test_native_plan_async_path_equals_host_rotated_reference_path(drs, golden):
         sb.gather_dev(plan_h.inst, plan_h.flips, crop, xh, yh, noise=plan_h.noise, noise_on=plan_h.noise_on, over_x=plan_h.over_x,
                       over_y=plan_h.over_y, over_on=plan_h.over_on)
         sa.gather_plan_dev(plan_n, xn, yn, am)
+        sa.synchronize()                       # (the handles run on their own streams here; torch compares on its own)
+        sb.synchronize()
         assert torch.equal(xh, xn) and torch.equal(yh, yn)
         acc_mask = plan_h.acc_mask if plan_h.acc_mask is not None else np.ones((B, crop, crop), dtype=np.uint8)
         assert np.array_equal(am.cpu().numpy().reshape(B, crop, crop), acc_mask)
@@ -281,6 +283,7 @@ def test_native_plan_async_path_equals_host_rotated_reference_path(drs, golden):
         amh = torch.from_numpy(np.ascontiguousarray(acc_mask.reshape(-1))).cuda()
         cm_dev = torch.zeros(K * K + 1, dtype=torch.int32, device="cuda")
         loss = sb.train_step_dev(xh, yh, B, crop, pred_dev=pb, cm_dev=cm_dev, acc_mask_dev=amh)
+        sa.synchronize()
         want.append((float(loss), cm_dev.cpu().numpy().astype(np.uint32)))
         assert torch.equal(pa, pb)
     for t, (loss, cm) in zip(tickets, want):          # results fetched late, in order (the ring holds 8)

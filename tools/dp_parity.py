@@ -12,6 +12,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 net, C, K, GB, crop = sys.argv[1] if len(sys.argv) > 1 else "dilated_grsl", 4, 6, 8, 19
 prec = sys.argv[2] if len(sys.argv) > 2 else "fp32"
+comm = sys.argv[3] if len(sys.argv) > 3 else "nccl"      # nccl: the library's own communicator; torch: callback exchange
 rs = np.random.RandomState(5)
 x = rs.randn(GB, crop * crop * C).astype(np.float32)
 y = rs.randint(0, K, size=(GB, crop * crop)).astype(np.float32)
@@ -23,7 +24,10 @@ def run(world_size, rows, sync_bn):
     s.set_stream(torch.cuda.current_stream().cuda_stream)
     s.load_variables(variables)
     if world_size > 1:
-        ddist.attach_allreduce(s, sync_bn=sync_bn)
+        if comm == "nccl":
+            ddist.attach_nccl(s, sync_bn=sync_bn)
+        else:
+            ddist.attach_allreduce(s, sync_bn=sync_bn)
     xd = torch.from_numpy(x[rows]).cuda()
     yd = torch.from_numpy(y[rows]).cuda()
     B = xd.shape[0]
@@ -35,7 +39,7 @@ def run(world_size, rows, sync_bn):
         print("rank", rank, "world", world_size, "losses", losses, "mm1", s.get_variable("conv1/moving_mean")[:4],
               "mv1", s.get_variable("conv1/moving_variance")[:4], "mm2", s.get_variable("conv2/moving_mean")[:3], flush=True)
     out = (losses, s.get_variable("conv_classifier/weights").copy(), s.get_variable("conv1/weights").copy(),
-           s.get_variable("conv3/moving_variance").copy(), cm.cpu().numpy().copy())
+           s.get_variable("conv3/moving_variance").copy(), cm.cpu().numpy().copy(), s.variables())
     s.close()
     return out
 
@@ -49,6 +53,13 @@ if rank == 0:
         err = float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
         assert err < (5e-4 if prec == "fp32" else 5e-2), (name, err)
     assert np.array_equal(dp[4], ref[4]) or prec != "fp32", (dp[4], ref[4])
-    print("DP_PARITY ok", prec, net, "losses", dp[0], ref[0], flush=True)
+    worst = ("", 0.0)
+    for name, b in ref[5].items():          # every variable: weights, biases, moving statistics, momentum slots, global_step
+        a = dp[5][name]
+        err = float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+        if err > worst[1]:
+            worst = (name, err)
+        assert err < (5e-4 if prec == "fp32" else 5e-2), (name, err)
+    print("DP_PARITY ok", prec, net, comm, "world", world, "losses", dp[0], ref[0], "worst variable", worst, "of", len(ref[5]), flush=True)
 dist.barrier()
 dist.destroy_process_group()
