@@ -42,12 +42,15 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md) through NVML: a burst of samples
-    10 ms apart for short regions, then one every 200 ms (NVML calls take a driver lock that kernel launches also need;
-    polling every 5 ms slowed the launch-heavy scene pass by 50 %).  Falls back to one nvidia-smi query."""
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md) through NVML.  The thread is started
+    well before the region (NVML initialisation and the first queries take a driver lock that kernel launches also need: inside
+    a 40 ms region they cost up to a second) and polls every 25 ms; begin() / stop() mark the region and only the samples between
+    them are reported (the nearest one if the region was shorter than a period).  Falls back to one nvidia-smi query."""
+    PERIOD = 0.025
 
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.thread, self.nv = index, [], False, None, None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
@@ -55,25 +58,33 @@ class ClockSampler:
             pynvml.nvmlInit()
             self.nv = pynvml
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._query()
             self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
         except Exception:
             self.nv = None
 
-    def _loop(self):
+    def _query(self):
         nv = self.nv
+        sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        return (time.perf_counter(), sm, pw, rs)
+
+    def _loop(self):
         while not self.stop_flag:
             try:
-                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
-                pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
-                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                self.samples.append((sm, pw, rs))
+                self.samples.append(self._query())
             except Exception:
                 pass
-            time.sleep(0.01 if len(self.samples) < 8 else 0.2)
+            time.sleep(self.PERIOD)
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
 
     def stop(self):
+        self.t_end = time.perf_counter()
         if self.nv is None:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,power.draw",
@@ -89,17 +100,26 @@ class ClockSampler:
             mx = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
         except Exception:
             mx = None
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        inside = [x for x in self.samples if t0 <= x[0] <= self.t_end]
+        note = None
+        if not inside and self.samples:
+            mid = 0.5 * (t0 + self.t_end)
+            inside = [min(self.samples, key=lambda x: abs(x[0] - mid))]
+            note = "timed region shorter than the %.0f ms polling period: nearest sample" % (self.PERIOD * 1e3)
         names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                  "hw_power_brake_slowdown": 0x80}
         reasons = set()
-        for _, _, r in self.samples:
+        for _, _, _, r in inside:
             for k, bit in names.items():
                 if r & bit:
                     reasons.add(k)
-        sm = [s[0] for s in self.samples]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "power_w_max": max([s[1] for s in self.samples]) if self.samples else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        sm = [x[1] for x in inside]
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+               "power_w_max": max([x[2] for x in inside]) if inside else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def profiled_traffic(which):
@@ -204,6 +224,8 @@ def run_train_ours(args, rank, world, local, cfg=None, sync_bn=False, extras=Tru
     crops, launches = [], [0, 0]
     ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
     sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()              # before the warm-up steps: NVML initialisation stays out of the timed region
     clocks = [None]
     orig_submit = be.submit_train
 
@@ -223,8 +245,7 @@ def run_train_ours(args, rank, world, local, cfg=None, sync_bn=False, extras=Tru
         if step == W:
             pipe.flush()
             barrier()
-            if rank == 0:
-                sampler.start()
+            sampler.begin()
             launches[0] = s.launch_count
             ev[0].record()
         elif step == W + K:
@@ -363,16 +384,22 @@ def dp_check(s, be, cfg, rank, world, dev, sync_bn):
         s1 = drs_b200.Session(cfg["net"], C, K, weight_decay=cfg["wd"], lr_initial=cfg["lr"], precision="fp32", device=dev.index, seed=5)
         s1.set_stream(torch.cuda.current_stream(dev).cuda_stream)
         loss_ref, _ = s1.train_step(x, y, crop)
+        from drs_b200 import nets
+        within = True
         for n, _ in s1.variable_names():
             a, b = s1.get_variable(n), sp.get_variable(n)
-            worst = max(worst, float(np.abs(a - b).max() / (np.abs(a).max() + 1e-12)))
+            err = float(np.abs(a - b).max() / (np.abs(a).max() + 1e-12))
+            within = within and err < ddist.dp_tolerance(n, nets.is_pooling(cfg["net"]))
+            if not n.endswith("/Momentum"):
+                worst = max(worst, err)
         s1.close()
     sp.close()
     ok = replicas_equal
     res = {"replicas_bit_identical": bool(replicas_equal)}
     if rank == 0:
         res.update(syncbn_loss=float(loss_dp), single_process_loss=float(loss_ref), syncbn_worst_rel_diff=worst)
-        ok = ok and abs(float(loss_dp) - float(loss_ref)) < 2e-5 * max(1.0, abs(float(loss_ref))) and worst < 1e-4
+        res["tolerance"] = "dist.dp_tolerance per variable; syncbn_worst_rel_diff = worst over weights, biases, BN statistics"
+        ok = ok and abs(float(loss_dp) - float(loss_ref)) < 2e-5 * max(1.0, abs(float(loss_ref))) and within
     res["result"] = "ok" if ok else "FAILED"
     return res
 
@@ -416,11 +443,12 @@ def run_infer_ours(args, rank, world, local, steps=3, cfg=None):
     u0, u1 = ddist.stripe_rows_needed(H, cfg["crop"], r0, r1) if world > 1 else (None, None)
     s.upload_scene(0, img, None, u0, u1)
     s.scene_infer(0, cfg["crop"], cfg["batch"], H, W, row_begin=r0, row_end=min(r1, r0 + 40))   # warm-up stripe (kernels)
-    one_pass()                                   # warm-up pass: stripe-sized buffers, geometry tables, first collective
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    one_pass()                                   # warm-up pass: stripe-sized buffers, geometry tables, first collective
+    barrier()
+    sampler.begin()
     times, launches = [], 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(steps):

@@ -79,7 +79,7 @@ class GpuBackend:
         self.s.prepare_training(x, y, per, crops, pred_dev=pred, acc_mask_dev=self._amask if isprs else None)
 
     def _gather(self, plan, scene_offset=0, shard=False):
-        if shard and self.world > 1:
+        if shard and self.world > 1 and not getattr(plan, "local", False):
             sl = self._rank_rows(plan.inst.shape[0])
             sub = type(plan)()
             for k in plan.__slots__:
@@ -158,7 +158,8 @@ class GpuBackend:
         """DRS_DP_DEBUG=1: assert that patch size and batch are identical on every rank before the step is enqueued."""
         import zlib
         import torch.distributed as dist
-        h = zlib.crc32(np.ascontiguousarray(plan.inst).tobytes() + np.ascontiguousarray(plan.flips).tobytes())
+        h = 0 if getattr(plan, "local", False) else \
+            zlib.crc32(np.ascontiguousarray(plan.inst).tobytes() + np.ascontiguousarray(plan.flips).tobytes())
         v = self.torch.tensor([plan.crop, h, -plan.crop, -h], dtype=self.torch.int64, device=self.dev)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         if int(v[0]) != -int(v[2]) or int(v[1]) != -int(v[3]):
@@ -173,7 +174,7 @@ class GpuBackend:
         x, y, pred, B, crop = self._gather(plan, shard=True)
         if self.train_fp16_patches:
             self.s.set_gather_fp16(False)
-        sl = self._rank_rows(plan.inst.shape[0])
+        sl = slice(0, plan.inst.shape[0]) if getattr(plan, "local", False) else self._rank_rows(plan.inst.shape[0])
         plan = self._plan
         n = B * crop * crop
         mask_dev = None

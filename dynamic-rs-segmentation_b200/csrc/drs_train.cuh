@@ -510,6 +510,21 @@ extern "C" int drs_reserve_workspace(drs_handle_t h, int32_t B, int32_t crop_max
   const int C = h->net.channels, K = h->net.classes;
   ensure_arena(h, training ? std::max(train_workspace_bytes(h, B, crop_max, es), forward_eval_workspace(h, B, crop_max))
                            : forward_eval_workspace(h, B, crop_max));
+  if (training) {
+    // both device staging slots of the planned gather (drs_gather_plan_dev): worst case = every patch noisy
+    HandleExtra* x = X(h);
+    const size_t need = (size_t)M * C * 8 + (size_t)B * 128 + 8192;
+    for (int s = 0; s < 2; ++s) {
+      if (x->plan_stage_cap[s] >= need) continue;
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      CUDA_CHECK(cudaStreamSynchronize(x->plan_stream));
+      if (x->plan_stage[s]) CUDA_CHECK(cudaFree(x->plan_stage[s]));
+      x->plan_stage[s] = nullptr;
+      x->plan_stage_cap[s] = 0;
+      CUDA_CHECK(cudaMalloc(&x->plan_stage[s], need));
+      x->plan_stage_cap[s] = need;
+    }
+  }
   // staging of the *_host entry points (x, y, two masks, int64 + uint8 predictions, confusion counts, logits)
   ensure_dstage(h, round_up((size_t)M * C * 4, 256) + round_up((size_t)M * 4, 256) + 2 * round_up((size_t)M, 256) +
                        round_up((size_t)M * 9, 256) + round_up((size_t)M * K * 4, 256) + 8192);

@@ -70,16 +70,16 @@ def init_score_arrays(distribution_type, values, occur_init=0):
     return patch_acc_loss, patch_occur, patch_chosen_values
 
 
-def draw_patch_size(distribution_type, values, probs=None):
+def draw_patch_size(distribution_type, values, probs=None, rng=np.random):
     """isprs:1727-1737: one draw from the legacy global ``np.random`` stream.  -> (size, index|None)"""
     if distribution_type == 'multi_fixed':
-        cur_size_int = np.random.randint(len(values))
+        cur_size_int = rng.randint(len(values))
         return int(values[cur_size_int]), cur_size_int
     if distribution_type == 'uniform':
-        cur_patch_size = int(np.random.uniform(values[0], values[-1] + 1, 1)[0])
+        cur_patch_size = int(rng.uniform(values[0], values[-1] + 1, 1)[0])
         return cur_patch_size, cur_patch_size - values[0]
     if distribution_type == 'multinomial':
-        cur_size_int = np.random.multinomial(1, probs).argmax()
+        cur_size_int = rng.multinomial(1, probs).argmax()
         return values[0] + cur_size_int, cur_size_int
     if distribution_type == 'single_fixed':
         return int(values[0]), None
@@ -255,10 +255,11 @@ def dynamically_calculate_mean_and_std(data, indexes, crop_size):
 class BatchPlan:
     """What ``dynamically_create_patches`` decided for one batch; consumed by Session.gather_dev."""
     __slots__ = ("inst", "flips", "noise", "noise_on", "over_x", "over_y", "over_on", "acc_mask", "crop", "rot", "rot_on",
-                 "noise_slot", "slot")
+                 "noise_slot", "slot", "local")
 
     def __init__(self):
         self.rot = self.rot_on = None
+        self.local = False          # True: the plan already holds only this rank's patches (data-parallel local planning)
         self.noise_slot = None      # compact noise: block noise_slot[b] of ``noise`` belongs to patch b (-1: none)
         self.slot = None            # the PlanSlot whose (pinned) buffers the arrays above are views of
 
@@ -443,9 +444,19 @@ class NativePlanner:
         self._store_state()
         return out
 
-    def plan(self, scene_hw, training_instances_batch, crop_size, channels, slot=None, own=None):
+    def local_stream(self, seed):
+        """A generator state of its own (not the global ``np.random`` one) for data-parallel local planning: every rank draws
+        the augmentation of ITS patches from its own stream, so no rank has to scan the noise of the whole global batch."""
+        st = np.random.RandomState(int(seed) & 0xffffffff).get_state()
+        ms = self._L.MtState()
+        np.frombuffer(ms.key, dtype=np.uint32)[:] = st[1]
+        ms.pos, ms.has_gauss, ms.gauss = int(st[2]), int(st[3]), float(st[4])
+        return ms
+
+    def plan(self, scene_hw, training_instances_batch, crop_size, channels, slot=None, own=None, stream=None):
         """-> BatchPlan with rotate_on_device semantics.  scene_hw: int32 [n_scenes, 2]; own = (b0, b1): the patches whose
-        noise values are needed (data-parallel rank slice), default all."""
+        noise values are needed (data-parallel rank slice), default all.  stream: an MtState from local_stream() to draw from
+        instead of the global generator."""
         C = self._C
         inst_in = np.ascontiguousarray(training_instances_batch, dtype=np.int64)
         B = inst_in.shape[0]
@@ -455,8 +466,10 @@ class NativePlanner:
             slot = PlanSlot(B, crop_size, channels)
         b0, b1 = (0, B) if own is None else own
         n_noise = C.c_int32()
-        self._load_state()
-        rc = self._lib.drs_plan_isprs_batch(self._h, C.byref(self._ms), inst_in.ctypes.data, B, scene_hw.ctypes.data, scene_hw.shape[0],
+        ms = stream if stream is not None else self._ms
+        if stream is None:
+            self._load_state()
+        rc = self._lib.drs_plan_isprs_batch(self._h, C.byref(ms), inst_in.ctypes.data, B, scene_hw.ctypes.data, scene_hw.shape[0],
                                             int(crop_size), int(channels), 1, rotation_table(int(crop_size)).ctypes.data,
                                             slot.inst.ctypes.data, slot.flips.ctypes.data, slot.rot_on.ctypes.data, slot.rot.ctypes.data,
                                             slot.noise_on.ctypes.data, slot.noise_slot.ctypes.data, slot.noise.ctypes.data,
@@ -465,7 +478,8 @@ class NativePlanner:
             raise ValueError(BatchColors.FAIL + "Error: Current PATCH size is out of the scene" + BatchColors.ENDC)
         if rc:
             raise self._L.DrsError("drs_plan_isprs_batch failed (%d)" % rc)
-        self._store_state()
+        if stream is None:
+            self._store_state()
         p = BatchPlan()
         p.crop = int(crop_size)
         p.inst, p.flips = slot.inst[:B], slot.flips[:B]

@@ -33,6 +33,10 @@ SPECS["dilated8_grsl"] = SPECS["dilated_grsl_rate8"]
 NET_TYPES = tuple(SPECS)
 
 
+def is_pooling(net_type):
+    return bool(SPECS[net_type]["pool"])
+
+
 def scope_prefix(net_type, isprs_scopes):
     # isprs names Dilated6's layers main_conv1..6 (isprs:766-777); coffee uses conv1..6 (coffee:635-662)
     return "main_conv" if (net_type == "dilated_icpr_original" and isprs_scopes) else "conv"
