@@ -381,24 +381,32 @@ def dp_check(s, be, cfg, rank, world, dev, sync_bn):
     worst = 0.0
     loss_ref = None
     if rank == 0:
-        s1 = drs_b200.Session(cfg["net"], C, K, weight_decay=cfg["wd"], lr_initial=cfg["lr"], precision="fp32", device=dev.index, seed=5)
-        s1.set_stream(torch.cuda.current_stream(dev).cuda_stream)
-        loss_ref, _ = s1.train_step(x, y, crop)
-        from drs_b200 import nets
-        within = True
-        for n, _ in s1.variable_names():
-            a, b = s1.get_variable(n), sp.get_variable(n)
-            err = float(np.abs(a - b).max() / (np.abs(a).max() + 1e-12))
-            within = within and err < ddist.dp_tolerance(n, nets.is_pooling(cfg["net"]))
-            if not n.endswith("/Momentum"):
-                worst = max(worst, err)
-        s1.close()
+        def single(xx):
+            s1 = drs_b200.Session(cfg["net"], C, K, weight_decay=cfg["wd"], lr_initial=cfg["lr"], precision="fp32", device=dev.index, seed=5)
+            s1.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+            l1, _ = s1.train_step(xx, y, crop)
+            v = {n: s1.get_variable(n) for n, _ in s1.variable_names()}
+            s1.close()
+            return l1, v
+
+        loss_ref, ref = single(x)
+        # the conditioning of the step itself: the same single-process step with x perturbed by 1e-7 relative (the size of the
+        # only difference data parallelism introduces, the summation order of the BN statistics); see tools/dp_parity.py
+        _, ptb = single((x * (1.0 + 1e-7 * np.random.RandomState(9).randn(*x.shape))).astype(np.float32))
+        within, worst_p = True, 0.0
+        for n in ref:
+            den = np.abs(ref[n]).max() + 1e-12
+            err = float(np.abs(ref[n] - sp.get_variable(n)).max() / den)
+            err_p = float(np.abs(ref[n] - ptb[n]).max() / den)
+            within = within and err < max(5e-4, 3.0 * err_p)
+            worst, worst_p = max(worst, err), max(worst_p, err_p)
     sp.close()
     ok = replicas_equal
     res = {"replicas_bit_identical": bool(replicas_equal)}
     if rank == 0:
-        res.update(syncbn_loss=float(loss_dp), single_process_loss=float(loss_ref), syncbn_worst_rel_diff=worst)
-        res["tolerance"] = "dist.dp_tolerance per variable; syncbn_worst_rel_diff = worst over weights, biases, BN statistics"
+        res.update(syncbn_loss=float(loss_dp), single_process_loss=float(loss_ref), syncbn_worst_rel_diff=worst,
+                   perturbation_1e7_worst_rel_diff=worst_p)
+        res["tolerance"] = "every variable incl. momentum slots: max(5e-4, 3 x what a 1e-7 input perturbation of the single-process step moves it by)"
         ok = ok and abs(float(loss_dp) - float(loss_ref)) < 2e-5 * max(1.0, abs(float(loss_ref))) and within
     res["result"] = "ok" if ok else "FAILED"
     return res

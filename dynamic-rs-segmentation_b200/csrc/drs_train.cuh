@@ -464,6 +464,142 @@ extern "C" int drs_train_step_dev(drs_handle_t h, const float* x_dev, const floa
   API_END
 }
 
+// ------------------------------------------------------------------------------------------------
+// unit-test entries for the backward pieces of the step (tests/test_gpu_parity.py): each runs exactly the launch sequence
+// train_step_t uses for one layer, on caller-supplied tensors
+// ------------------------------------------------------------------------------------------------
+template <typename TA>
+static void debug_dgrad_t(Handle* h, const float* dy32, const float* w32, int B, int crop, int k, int rate, int ci, int co, float* dx32) {
+  const int64_t M = (int64_t)B * crop * crop;
+  const int taps = k * k;
+  const int64_t nw = (int64_t)taps * ci * co;
+  const int pad_b = ((k - 1) * rate) / 2, pad_a = (k - 1) * rate - pad_b;
+  HandleExtra* x = X(h);
+  TA* dy = (TA*)arena_take(h, M * co * sizeof(TA));
+  TA* dx = (TA*)arena_take(h, M * ci * sizeof(TA));
+  void* wd = arena_take(h, nw * 4);
+  cast_kernel<float, TA><<<nblk(M * co, 256), 256, 0, h->stream>>>(dy32, dy, M * co);
+  LAUNCH_CHECK(h);
+  // the dgrad operand exactly as refresh_packed builds it: taps flipped, Ci/Co transposed (kind 1 tensor cores, kind 2 fp32)
+  RepackTable t;
+  memset(&t, 0, sizeof(t));
+  t.etype = ElemTag<TA>::v;
+  t.seg[t.n++] = RepackSeg{w32, wd, taps, ci, co, ElemTag<TA>::v == ET_F32 ? 2 : 1, 0};
+  t.total = nw;
+  repack_kernel<<<nblk(nw, 256), 256, 0, h->stream>>>(t);
+  LAUNCH_CHECK(h);
+  // dgrad: dilated conv of dZ with flipped taps, before/after padding swapped (train_step_t)
+  run_conv<TA>(h, ActBuf{dy, co, 0}, co, (const float*)wd, wd, ActBuf{dx, ci, 0}, ci, B, crop, k, rate, pad_a, x->ones, x->zeros, ACT_NONE);
+  cast_kernel<TA, float><<<nblk(M * ci, 256), 256, 0, h->stream>>>(dx, dx32, M * ci);
+  LAUNCH_CHECK(h);
+}
+
+extern "C" int drs_debug_dgrad(drs_handle_t h, const float* dy_host, const float* w_host, int32_t B, int32_t crop, int32_t k,
+                               int32_t rate, int32_t Ci, int32_t Co, int32_t precision, float* dx_host) {
+  API_BEGIN
+  DRS_CHECK(h && dy_host && w_host && dx_host, "null argument");
+  DRS_CHECK(precision == DRS_PREC_FP32 || precision == DRS_PREC_BF16, "debug_dgrad: fp32 or bf16");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  const int64_t M = (int64_t)B * crop * crop;
+  const int64_t nw = (int64_t)k * k * Ci * Co;
+  ensure_arena(h, (size_t)M * (Ci + Co) * 8 + nw * 8 + (1 << 20));
+  h->arena.reset();
+  float* dy32 = (float*)arena_take(h, M * Co * 4);
+  float* w32 = (float*)arena_take(h, nw * 4);
+  float* dx32 = (float*)arena_take(h, M * Ci * 4);
+  CUDA_CHECK(cudaMemcpyAsync(dy32, dy_host, M * Co * 4, cudaMemcpyHostToDevice, h->stream));
+  CUDA_CHECK(cudaMemcpyAsync(w32, w_host, nw * 4, cudaMemcpyHostToDevice, h->stream));
+  if (precision == DRS_PREC_FP32) debug_dgrad_t<float>(h, dy32, w32, B, crop, k, rate, Ci, Co, dx32);
+  else debug_dgrad_t<__nv_bfloat16>(h, dy32, w32, B, crop, k, rate, Ci, Co, dx32);
+  CUDA_CHECK(cudaMemcpyAsync(dx_host, dx32, M * Ci * 4, cudaMemcpyDeviceToHost, h->stream));
+  int rc = drs_synchronize(h);
+  if (rc) return rc;
+  API_END
+}
+
+// One layer's normalise / activate / pool forward and its backward: z [M,C] is the raw conv output, dout the gradient with
+// respect to the layer output.  Returns the layer output and dZ.  Same kernels, same order as train_step_t.
+template <typename TA>
+static void debug_layer_t(Handle* h, const float* z32, const float* dout32, int B, int crop, int C, int pool, int act, float* out32,
+                          float* dz32, float* mean_out, float* istd_out) {
+  const int64_t M = (int64_t)B * crop * crop;
+  HandleExtra* x = X(h);
+  TA* Z = (TA*)arena_take(h, M * C * sizeof(TA));
+  TA* Xo = (TA*)arena_take(h, M * C * sizeof(TA));
+  TA* G = (TA*)arena_take(h, M * C * sizeof(TA));
+  TA* T = (TA*)arena_take(h, M * C * sizeof(TA));
+  TA* DZ = (TA*)arena_take(h, M * C * sizeof(TA));
+  uint8_t* idx = (uint8_t*)arena_take(h, M * C);
+  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 2);
+  const int bn_rows = (int)ceil_div(M, nb_bn);
+  float* part_bn = (float*)arena_take(h, (size_t)nb_bn * 2 * 256 * 4);
+  float* mean = x->mean;
+  float* istd = x->inv_std;
+  float* scratch_stats = (float*)arena_take(h, 4 * 512 * 4);      // moving statistics the finish step updates (discarded)
+  CUDA_CHECK(cudaMemsetAsync(scratch_stats, 0, 4 * 512 * 4, h->stream));
+  cast_kernel<float, TA><<<nblk(M * C, 256), 256, 0, h->stream>>>(z32, Z, M * C);
+  LAUNCH_CHECK(h);
+  cast_kernel<float, TA><<<nblk(M * C, 256), 256, 0, h->stream>>>(dout32, G, M * C);
+  LAUNCH_CHECK(h);
+  const double bn_count = (double)M;
+  BnFinish fin{x->bn_acc, 1048576.0, x->bn_counter, x->sums, mean, istd, scratch_stats, scratch_stats + 512, bn_count, h->cfg.bn_eps,
+               h->cfg.bn_decay, h->cfg.bn_unbiased_ema};
+  bn_partial_kernel<TA, TA, 0><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z, C, 0, nullptr, 0, 0, nullptr, nullptr, 0, part_bn, C, M, bn_rows, fin);
+  LAUNCH_CHECK(h);
+  if (pool) {
+    launch_maxpool3_fwd<TA>(h, Z, C, 0, Xo, C, 0, idx, C, B, crop, mean, istd, act);
+  } else {
+    bn_apply_kernel<TA><<<bne_grid(M, h->sm_count), BNE_THREADS, 0, h->stream>>>(Z, C, 0, mean, istd, act, Xo, C, 0, C, M);
+    LAUNCH_CHECK(h);
+  }
+  const TA* dA = G;
+  if (pool) {
+    launch_maxpool3_bwd<TA>(h, G, C, 0, idx, T, C, 0, C, B, crop);
+    dA = T;
+  }
+  BnFinish finb{x->bn_acc, 1099511627776.0, x->bn_counter, x->sums, nullptr, nullptr, nullptr, nullptr, bn_count, 0.0f, 0.0f, 0};
+  bn_partial_kernel<TA, TA, 1><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z, C, 0, dA, C, 0, mean, istd, act, part_bn, C, M, bn_rows, finb);
+  LAUNCH_CHECK(h);
+  bn_bwd_apply_kernel<TA, TA><<<bne_grid(M, h->sm_count), BNE_THREADS, 0, h->stream>>>(Z, C, 0, dA, C, 0, mean, istd, x->sums, 1.0 / bn_count, act,
+                                                                                 DZ, C, 0, C, M);
+  LAUNCH_CHECK(h);
+  cast_kernel<TA, float><<<nblk(M * C, 256), 256, 0, h->stream>>>(Xo, out32, M * C);
+  LAUNCH_CHECK(h);
+  cast_kernel<TA, float><<<nblk(M * C, 256), 256, 0, h->stream>>>(DZ, dz32, M * C);
+  LAUNCH_CHECK(h);
+  CUDA_CHECK(cudaMemcpyAsync(mean_out, mean, C * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_CHECK(cudaMemcpyAsync(istd_out, istd, C * 4, cudaMemcpyDeviceToDevice, h->stream));
+}
+
+extern "C" int drs_debug_layer(drs_handle_t h, const float* z_host, const float* dout_host, int32_t B, int32_t crop, int32_t C,
+                               int32_t pool, int32_t act, int32_t precision, float* out_host, float* dz_host, float* mean_host,
+                               float* inv_std_host) {
+  API_BEGIN
+  DRS_CHECK(h && z_host && dout_host && out_host && dz_host, "null argument");
+  DRS_CHECK(precision == DRS_PREC_FP32 || precision == DRS_PREC_BF16, "debug_layer: fp32 or bf16");
+  DRS_CHECK(C % 8 == 0 && C <= 256, "debug_layer: C=%d must be a multiple of 8, at most 256", C);
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  const int64_t M = (int64_t)B * crop * crop;
+  ensure_arena(h, (size_t)M * C * (4 * 4 + 6 * 4 + 1) + (8 << 20));
+  h->arena.reset();
+  float* z32 = (float*)arena_take(h, M * C * 4);
+  float* g32 = (float*)arena_take(h, M * C * 4);
+  float* o32 = (float*)arena_take(h, M * C * 4);
+  float* dz32 = (float*)arena_take(h, M * C * 4);
+  float* ms = (float*)arena_take(h, 2 * C * 4);
+  CUDA_CHECK(cudaMemcpyAsync(z32, z_host, M * C * 4, cudaMemcpyHostToDevice, h->stream));
+  CUDA_CHECK(cudaMemcpyAsync(g32, dout_host, M * C * 4, cudaMemcpyHostToDevice, h->stream));
+  if (precision == DRS_PREC_FP32) debug_layer_t<float>(h, z32, g32, B, crop, C, pool, act, o32, dz32, ms, ms + C);
+  else debug_layer_t<__nv_bfloat16>(h, z32, g32, B, crop, C, pool, act, o32, dz32, ms, ms + C);
+  CUDA_CHECK(cudaMemcpyAsync(out_host, o32, M * C * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaMemcpyAsync(dz_host, dz32, M * C * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (mean_host) CUDA_CHECK(cudaMemcpyAsync(mean_host, ms, C * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (inv_std_host) CUDA_CHECK(cudaMemcpyAsync(inv_std_host, ms + C, C * 4, cudaMemcpyDeviceToHost, h->stream));
+  int rc = drs_synchronize(h);
+  if (rc) return rc;
+  API_END
+}
+
 // The same step without a host round trip: loss and confusion counts are copied into a pinned result slot behind an event
 // and fetched later with drs_train_result(ticket) -- the reference's loop only needs them for the score update and the
 // log lines (isprs:1754-1778), neither of which feeds the next step's draws.

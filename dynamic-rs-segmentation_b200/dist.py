@@ -93,20 +93,6 @@ def attach_nccl(session, sync_bn=False, group=None):
     return world
 
 
-def dp_tolerance(name, pooled_net):
-    """Relative (max-norm) tolerance when a data-parallel SyncBN step is compared with the single-process step on the whole
-    batch.  The two differ only in floating-point summation order (NCCL sums), i.e. by ~1e-7 relative in the BN statistics.
-    For nets without pooling every variable then agrees to ~1e-6.  In the pooling nets the early-layer gradients are
-    ill-conditioned on random data: a 1e-7 perturbation flips a handful of max-pool winners / LeakyReLU signs, and because a
-    filter gradient is a heavily cancelling sum over all pixels each flip moves it by ~1/sqrt(pixels); the oracle itself
-    (PyTorch CPU, fp32 vs fp64 of the same graph) differs by 0.6-2 % on conv1..conv5 gradients and by 5 % under a 1e-7 input
-    perturbation (tools/dp_parity.py prints the measurement).  Hence: momentum slots (= gradients) of pooling nets 8e-2,
-    everything else -- weights, biases, BN moving statistics, classifier, losses -- 5e-4."""
-    if pooled_net and name.endswith("/Momentum") and not name.startswith("conv_classifier"):
-        return 8e-2
-    return 5e-4
-
-
 def rank_slice(batch, rank, world):
     """This rank's share of a global batch (contiguous, equal sizes)."""
     per = len(batch) // world

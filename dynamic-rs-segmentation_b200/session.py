@@ -393,6 +393,26 @@ class Session:
                                          L.PREC[precision], L.ptr(y)))
         return y
 
+    def debug_dgrad(self, dy, w, rate, precision="bf16"):
+        dy = np.ascontiguousarray(dy, dtype=np.float32)
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        B, crop, _, co = dy.shape
+        k, _, ci, _ = w.shape
+        dx = np.empty((B, crop, crop, ci), dtype=np.float32)
+        L.check(self._lib.drs_debug_dgrad(self._h, L.ptr(dy), L.ptr(w), B, crop, k, rate, ci, co, L.PREC[precision], L.ptr(dx)))
+        return dx
+
+    def debug_layer(self, z, dout, pool, act, precision="bf16"):
+        """(out, dz, batch mean, batch inverse std) of one train-mode BN + activation (+ max-pool) layer."""
+        z = np.ascontiguousarray(z, dtype=np.float32)
+        dout = np.ascontiguousarray(dout, dtype=np.float32)
+        B, crop, _, c = z.shape
+        out, dz = np.empty_like(z), np.empty_like(z)
+        mean, istd = np.empty(c, dtype=np.float32), np.empty(c, dtype=np.float32)
+        L.check(self._lib.drs_debug_layer(self._h, L.ptr(z), L.ptr(dout), B, crop, c, int(bool(pool)), int(act), L.PREC[precision],
+                                          L.ptr(out), L.ptr(dz), L.ptr(mean), L.ptr(istd)))
+        return out, dz, mean, istd
+
     def debug_wgrad(self, x, dy, k, rate, precision="bf16"):
         x = np.ascontiguousarray(x, dtype=np.float32)
         dy = np.ascontiguousarray(dy, dtype=np.float32)

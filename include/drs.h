@@ -321,6 +321,18 @@ int drs_bench_conv(drs_handle_t h, int32_t B, int32_t crop, int32_t k, int32_t r
 int drs_debug_wgrad(drs_handle_t h, const float* x_host, const float* dy_host, int32_t B, int32_t crop, int32_t k,
                     int32_t rate, int32_t Ci, int32_t Co, int32_t precision, float* dw_host);
 
+/* unit-test entry: data gradient of one dilated SAME convolution exactly as the step computes it (a convolution of dy
+ * with tap-flipped, Ci/Co-transposed weights and the before/after padding swapped):
+ *   dy [B,crop,crop,Co], w HWIO [k,k,Ci,Co] fp32 host -> dx [B,crop,crop,Ci] fp32 host.  precision BF16 (tcgen05) or FP32. */
+int drs_debug_dgrad(drs_handle_t h, const float* dy_host, const float* w_host, int32_t B, int32_t crop, int32_t k, int32_t rate,
+                    int32_t Ci, int32_t Co, int32_t precision, float* dx_host);
+
+/* unit-test entry: one layer's train-mode batch-norm (no gamma/beta, isprs:655-663) + activation (+ 3x3 max-pool, isprs:745-750)
+ * forward and backward with the step's own kernels: z [B,crop,crop,C] raw conv output, dout = gradient w.r.t. the layer
+ * output -> out (layer output), dz (gradient w.r.t. z), batch mean / inverse std.  act: 0 none, 1 ReLU, 2 LeakyReLU(0.1). */
+int drs_debug_layer(drs_handle_t h, const float* z_host, const float* dout_host, int32_t B, int32_t crop, int32_t C, int32_t pool,
+                    int32_t act, int32_t precision, float* out_host, float* dz_host, float* mean_host, float* inv_std_host);
+
 #ifdef __cplusplus
 }
 #endif

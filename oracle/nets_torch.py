@@ -92,10 +92,33 @@ def _conv_same(x_nchw, w_hwio, rate):
     return F.conv2d(x, w, dilation=rate)
 
 
-class OracleNet:
-    """Holds fp32 parameters as torch tensors; forward in train or eval mode."""
+class _RoundBf16(torch.autograd.Function):
+    """Storage rounding of the tensor-core path, forward AND backward: the CUDA step keeps Z, the layer outputs and their
+    gradients in bf16 (fp32 accumulation in between), so the emulating oracle rounds at the same points."""
 
-    def __init__(self, net_type, channels, num_classes, params, bn_unbiased_ema=True):
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def _rb(x, on):
+    return _RoundBf16.apply(x) if on else x
+
+
+class OracleNet:
+    """Holds fp32 parameters as torch tensors; forward in train or eval mode.
+
+    ``emulate_bf16``: round conv operands (input, filter), the raw conv output Z, the layer output and the gradients
+    flowing through those points to bf16, like the tensor-core training path stores them.  The arithmetic in between stays
+    fp32.  Activation gates and max-pool winners are then decided on the same rounded values as on the GPU, which removes
+    the chaotic gate flips from a gradient comparison (tests/test_gpu_parity.py::test_train_step_bf16_vs_emulating_oracle)."""
+
+    def __init__(self, net_type, channels, num_classes, params, bn_unbiased_ema=True, emulate_bf16=False):
+        self.emulate_bf16 = bool(emulate_bf16)
         self.net_type = net_type
         self.spec = NET_SPECS[net_type]
         self.channels = channels
@@ -120,10 +143,11 @@ class OracleNet:
         """x_flat: [B, crop*crop*C] (isprs:763 reshape).  Returns logits NHWC [B,crop,crop,K]."""
         p = self.p if p is None else p
         B = x_flat.shape[0]
-        x = x_flat.reshape(B, crop, crop, self.channels).permute(0, 3, 1, 2)
+        e = self.emulate_bf16
+        x = _rb(x_flat.reshape(B, crop, crop, self.channels).permute(0, 3, 1, 2), e)
         feats = None
         for i, (scope, k, r, ci, co) in enumerate(self.plan):
-            z = _conv_same(x, p[scope + "/weights"], r) + p[scope + "/biases"].view(1, -1, 1, 1)
+            z = _rb(_conv_same(x, _rb(p[scope + "/weights"], e), r) + p[scope + "/biases"].view(1, -1, 1, 1), e)
             if ztaps is not None:
                 ztaps[scope] = z
             if is_training:
@@ -142,6 +166,7 @@ class OracleNet:
             a = self._act(zh)
             if self.spec["pool"]:
                 a = F.max_pool2d(a, 3, 1, 1)                # SAME: -inf padding (Appendix B.4)
+            a = _rb(a, e)
             if taps is not None:
                 taps[scope] = a.permute(0, 2, 3, 1).detach()
             if self.spec["dense"]:

@@ -521,6 +521,183 @@ def test_filter_gradient(drs, prec):
     s.close()
 
 
+def torch_dgrad(dy, w, rate):
+    """d(sum(conv_same(x, w) * dy)) / dx in float64 (autograd through the SAME-padded dilated cross-correlation)."""
+    import torch
+    import torch.nn.functional as F
+    k, _, ci, co = w.shape
+    total = (k - 1) * rate
+    pb, pa = total // 2, total - total // 2
+    B, crop = dy.shape[0], dy.shape[1]
+    x = torch.zeros(B, ci, crop, crop, dtype=torch.float64, requires_grad=True)
+    wt = torch.from_numpy(w).permute(3, 2, 0, 1).contiguous().double()
+    y = F.conv2d(F.pad(x, (pb, pa, pb, pa)), wt, dilation=rate)
+    (y * torch.from_numpy(dy).permute(0, 3, 1, 2).double()).sum().backward()
+    return x.grad.permute(0, 2, 3, 1).contiguous().numpy()
+
+
+# (B, crop, k, rate, Ci, Co) of the conv whose data gradient is taken: every (k, rate) of the nets incl. the asymmetric pads
+# 1/2 (k4 r1), 3/3 (k4 r2), 4/5 (k4 r3), 6/6 (k4 r4) -- swapped in the backward --, Ci != Co both ways, M not a tile multiple
+DGRAD_CASES = [(2, 9, 3, 1, 64, 64), (1, 25, 5, 2, 64, 64), (3, 13, 4, 3, 64, 128), (2, 17, 4, 3, 128, 64), (2, 11, 4, 4, 128, 128),
+               (2, 12, 4, 1, 64, 128), (2, 25, 3, 5, 128, 256), (1, 25, 3, 6, 256, 256), (5, 7, 3, 8, 256, 192), (1, 30, 3, 7, 192, 256),
+               (2, 15, 4, 2, 128, 64), (4, 25, 3, 6, 320, 128), (1, 33, 5, 1, 64, 64)]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_data_gradient(drs, prec):
+    """dgrad of one dilated convolution as the step computes it: a convolution of dZ with tap-flipped, Ci/Co-transposed
+    weights and before/after padding swapped (tcgen05 path for bf16, CUDA cores for fp32) vs float64 autograd on identically
+    rounded operands.  A wrong pad swap of the even 4x4 kernels (4/5 <-> 5/4) shifts the result by a whole dilation step."""
+    s = drs.Session("dilated_grsl", 4, 6, precision=prec)
+    rs = np.random.RandomState(2)
+    for (B, crop, k, rate, ci, co) in DGRAD_CASES:
+        dy = rs.randn(B, crop, crop, co).astype(np.float32)
+        w = (rs.randn(k, k, ci, co) / np.sqrt(k * k * co)).astype(np.float32)
+        ref = torch_dgrad(rounded(dy, prec), rounded(w, prec), rate)
+        got = s.debug_dgrad(dy, w, rate, prec)
+        assert got.shape == ref.shape
+        if prec == "fp32":
+            assert np.abs(got - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()), (B, crop, k, rate, ci, co)
+        else:
+            # fp32 accumulation, ONE bf16 rounding of the stored result: |err| <= 2^-8 |ref| (+ accumulation noise)
+            assert np.all(np.abs(got - ref) <= 2.0 ** -8 * np.abs(ref) + 2e-4 * np.abs(ref).max()), (B, crop, k, rate, ci, co)
+    s.close()
+
+
+def torch_layer(z, dout, pool, act):
+    """Train-mode batch_norm(center=False, scale=False) -> activation -> optional 3x3 SAME max-pool, and its backward, in
+    float64 (isprs:655-663, 719-721, 745-750)."""
+    import torch
+    import torch.nn.functional as F
+    zt = torch.from_numpy(z).permute(0, 3, 1, 2).double().requires_grad_(True)
+    mean = zt.mean(dim=(0, 2, 3))
+    var = zt.var(dim=(0, 2, 3), unbiased=False)
+    zh = (zt - mean.view(1, -1, 1, 1)) * torch.rsqrt(var.view(1, -1, 1, 1) + 0.001)
+    a = torch.relu(zh) if act == 1 else (torch.maximum(0.1 * zh, zh) if act == 2 else zh)
+    if pool:
+        a = F.max_pool2d(a, 3, 1, 1)
+    (a * torch.from_numpy(dout).permute(0, 3, 1, 2).double()).sum().backward()
+    return a.detach().permute(0, 2, 3, 1).numpy(), zt.grad.permute(0, 2, 3, 1).numpy()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_layer_normalise_activate_pool_forward_and_backward(drs, prec):
+    """The HBM-bound half of a layer on its own: train-mode BN + ReLU / LeakyReLU (+ max-pool) forward, pool backward by winner
+    code, BN backward (two passes) -- the fp32 kernels and the separate packed-bf16 ones (maxpool3_fwd_train_bf16*,
+    maxpool3_bwd_bf16, bn_*<bf16>).  Includes inputs quantised to a few levels, so that most pooling windows hold ties: the
+    gradient must go to the FIRST maximum in row-major window order (TF / the oracle), nowhere else."""
+    s = drs.Session("dilated_grsl", 4, 6, precision=prec)
+    rs = np.random.RandomState(4)
+    cases = [(2, 9, 64, 1, 2, False), (3, 13, 128, 1, 2, True), (1, 25, 256, 1, 2, False), (2, 12, 64, 0, 1, False),
+             (4, 7, 32, 0, 2, False), (2, 25, 192, 1, 2, True), (1, 31, 64, 1, 1, True), (64, 5, 128, 1, 2, False)]
+    for (B, crop, C, pool, act, ties) in cases:
+        z = rs.randn(B, crop, crop, C).astype(np.float32) * 1.5 + 0.3
+        if ties:
+            z = np.round(z * 2) / 2                           # levels 0.5 apart (exact in bf16): ties in most windows
+        dout = rs.randn(B, crop, crop, C).astype(np.float32)
+        z, dout = rounded(z, prec), rounded(dout, prec)
+        ref_out, ref_dz = torch_layer(z, dout, pool, act)
+        out, dz, mean, istd = s.debug_layer(z, dout, pool, act, prec)
+        assert np.abs(mean - z.reshape(-1, C).mean(0)).max() < 1e-5
+        assert np.abs(istd - 1.0 / np.sqrt(z.reshape(-1, C).astype(np.float64).var(0) + 0.001)).max() < 1e-4
+        if prec == "fp32":
+            assert np.abs(out - ref_out).max() < 1e-5, (B, crop, C, pool, act, ties)
+            assert np.abs(dz - ref_dz).max() < 2e-5 * max(1.0, np.abs(ref_dz).max()), (B, crop, C, pool, act, ties)
+        else:
+            # stored in bf16: one rounding of the output; the backward rounds dA (pool backward) and dZ
+            assert np.all(np.abs(out - ref_out) <= 2.0 ** -8 * np.abs(ref_out) + 1e-6), (B, crop, C, pool, act, ties)
+            scale = np.abs(ref_dz).max()
+            bad = np.abs(dz - ref_dz) > 2.0 ** -6 * np.abs(ref_dz) + 2e-3 * scale
+            assert not bad.any(), (B, crop, C, pool, act, ties, int(bad.sum()), float(np.abs(dz - ref_dz).max() / scale))
+    s.close()
+
+
+@pytest.mark.parametrize("net,C,K,use_mask", (("dilated_icpr_original", 4, 6, False), ("dilated_grsl", 4, 6, False),
+                                              ("dilated_icpr_rate6_densely", 5, 6, False), ("dilated_grsl_rate8", 3, 7, True)))
+def test_train_step_bf16_vs_emulating_oracle(drs, net, C, K, use_mask):
+    """The product precision against an oracle that rounds at the same storage points (conv operands, Z, layer outputs and
+    the gradients through them in bf16; fp32 arithmetic in between; oracle/nets_torch.py emulate_bf16).  Gates and pool winners
+    are then decided on the same values, so the comparison is no longer at the mercy of flipped gates: every filter gradient
+    must agree in direction and size, and EVERY variable after the update (weights, biases, moving statistics, momentum slots)
+    must agree."""
+    import torch
+    from oracle import nets_torch
+    params = nets_torch.init_params(net, C, K, seed=5)
+    orc = nets_torch.OracleNet(net, C, K, params, emulate_bf16=True)
+    s = drs.Session(net, C, K, precision="bf16", weight_decay=0.005, lr_initial=0.01)
+    s.load_variables(params)
+    rs = np.random.RandomState(6)
+    report = []
+    for step, (B, crop) in enumerate(((8, 13), (6, 20), (4, 25))):
+        x = rs.randn(B, crop * crop * C).astype(np.float32)
+        y = rs.randint(0, K, size=(B, crop * crop)).astype(np.float32)
+        mask = (rs.rand(B, crop * crop) > 0.3) if use_mask else None
+        lo, po, _ = orc.train_step(torch.from_numpy(x), torch.from_numpy(y), crop, 0.01, 0.005,
+                                   mask=None if mask is None else torch.from_numpy(mask))
+        lg, pg = s.train_step(x, y, crop, mask=mask)
+        assert abs(float(lg) - lo) < 2e-3 * max(1.0, abs(lo)), (step, lg, lo)
+        assert (pg == po.numpy()).mean() > 0.99
+        for name, (l2, med, cos) in _grad_report(orc, s).items():
+            report.append((step, name, round(l2, 4), round(cos, 5)))
+            assert cos > 0.995 and l2 < 0.1, (step, name, l2, med, cos, report)
+        ref = orc.export_params()
+        for name, v in s.variables().items():
+            if name == "global_step":
+                assert int(v[0]) == orc.global_step
+                continue
+            want = orc.momentum[name[:-len("/Momentum")]].numpy() if name.endswith("/Momentum") else ref[name]
+            den = np.abs(want).max() + 1e-12
+            err = float(np.abs(v.reshape(want.shape) - want).max() / den)
+            tol = 0.15 if name.endswith("/Momentum") else 5e-3
+            assert err < tol, (step, name, err)
+        _resync(s, orc)
+    print("bf16 vs emulating oracle (step, tensor, rel-L2, cosine):", report)
+    s.close()
+
+
+def test_trained_weights_inference_argmax_agreement(drs):
+    """north_star: argmax agreement >= 99.9 % of pixels.  On random-init nets most pixels have top-2 margins below any
+    16-bit tolerance, so this is asserted where it means something: after 80 training steps on a learnable task (GPU
+    training path), the f16 (TF32-class) and bf16 inference paths must pick the oracle's class on >= 99.9 % / 99.5 % of pixels
+    and keep the softmax probabilities within 1e-3 / 1e-2."""
+    import torch
+    from oracle import nets_torch
+    net, C, K, B, crop = "dilated_grsl", 4, 6, 16, 25
+    s = drs.Session(net, C, K, precision="bf16", weight_decay=0.0005, lr_initial=0.05, seed=2)
+    rs = np.random.RandomState(3)
+
+    def batch(n):
+        x = rs.randn(n, crop, crop, C).astype(np.float32)
+        # smooth fields (block-constant 5x5) so that the dilated context is informative; label = a function of channels 0/1
+        x = np.repeat(np.repeat(x[:, ::5, ::5], 5, axis=1), 5, axis=2)[:, :crop, :crop]
+        y = (x[..., 0] > 0).astype(np.int64) + 2 * (x[..., 1] > 0.5) + 2 * (x[..., 1] > -0.5)
+        return x.reshape(n, -1), np.minimum(y, K - 1).astype(np.float32).reshape(n, -1)
+
+    losses = []
+    for _ in range(80):
+        x, y = batch(B)
+        losses.append(float(s.train_step(x, y, crop)[0]))
+    assert losses[-1] < 0.5 * losses[0], (losses[0], losses[-1])
+    trained = {k: v for k, v in s.variables().items() if not k.endswith("/Momentum") and k != "global_step"}
+    s.close()
+    orc = nets_torch.OracleNet(net, C, K, trained)
+    x, _ = batch(24)
+    po, lo = orc.infer(torch.from_numpy(x), crop)
+    po, pr_o = po.numpy(), softmax(lo.numpy().astype(np.float64))
+    out = {}
+    for prec, agree_min, ptol in (("f16", 0.999, 1e-3), ("bf16", 0.995, 1e-2)):
+        si = drs.Session(net, C, K, precision=prec)
+        si.load_variables(trained)
+        pg, lg = si.infer(x, crop)
+        si.close()
+        agree = float((pg == po).mean())
+        perr = float(np.abs(softmax(lg.astype(np.float64)) - pr_o).max())
+        out[prec] = (agree, perr)
+        assert agree >= agree_min, out
+        assert np.quantile(np.abs(softmax(lg.astype(np.float64)) - pr_o), 0.999) < ptol, out
+    print("trained-weights inference agreement / max probability error:", out)
+
+
 TRAIN_NETS = (("dilated_icpr_original", 4, 6, False), ("dilated_grsl", 4, 6, False),
               ("dilated_icpr_rate6_densely", 5, 6, False), ("dilated_grsl_rate8", 3, 7, True),
               ("dilated_icpr_rate6_small", 4, 6, False))
@@ -653,6 +830,36 @@ def test_training_is_run_to_run_deterministic(drs):
     assert outs[0][0] == outs[1][0]
     for a, b in zip(outs[0][1:], outs[1][1:]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("net,prec", [("dilated_grsl", "bf16"), ("dilated_icpr_rate6_densely", "bf16"), ("dilated_icpr_original", "fp32")])
+def test_checkpoint_round_trip_continues_bit_identically(drs, tmp_path, net, prec):
+    """tf.train.Saver stand-in (isprs:1693-1717, 1797-1802): train 3 steps, save, restore into a NEW session, train 3 more
+    == 6 uninterrupted steps, bit for bit -- weights, biases, BN moving statistics, momentum slots, global_step, losses."""
+    C, K, B = 4, 6, 8
+    rs = np.random.RandomState(17)
+    batches = []
+    for crop in (17, 25, 21, 25, 13, 17):
+        batches.append((rs.randn(B, crop * crop * C).astype(np.float32), rs.randint(0, K, size=(B, crop * crop)).astype(np.float32), crop))
+    kw = dict(precision=prec, weight_decay=0.005, lr_initial=0.01, decay_steps=4, decay_rate=0.5)   # the lr drops at step 4
+    a = drs.Session(net, C, K, seed=9, **kw)
+    la = [float(a.train_step(x, y, c)[0]) for x, y, c in batches]
+    va = a.variables()
+    a.close()
+    b = drs.Session(net, C, K, seed=9, **kw)
+    lb = [float(b.train_step(x, y, c)[0]) for x, y, c in batches[:3]]
+    b.save(str(tmp_path / "model-3"))
+    b.close()
+    c2 = drs.Session(net, C, K, seed=1234, **kw)          # different initial values: everything must come from the file
+    c2.restore(str(tmp_path / "model-3"))
+    assert c2.global_step == 3
+    lb += [float(c2.train_step(x, y, c)[0]) for x, y, c in batches[3:]]
+    vc = c2.variables()
+    c2.close()
+    assert la == lb
+    assert set(va) == set(vc)
+    for k in va:
+        assert np.array_equal(va[k], vc[k]), k
 
 
 def test_cuda_graph_replay_matches_eager(drs, monkeypatch):

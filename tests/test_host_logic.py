@@ -94,3 +94,21 @@ def test_rotate_affine_reproduces_scipy_rotate():
             out = np.zeros_like(patch)
             out[ok] = patch[np.floor(c0 + 0.5).astype(np.int64)[ok], np.floor(c1 + 0.5).astype(np.int64)[ok]]
             assert np.array_equal(out, scipy.ndimage.rotate(patch, angle, order=0, reshape=False)), (crop, angle)
+
+
+def test_score_files_are_byte_identical_to_numpy_save(tmp_path):
+    """isprs:1800-1802 / coffee:1341-1343: the per-patch-size score arrays are written with np.save under the reference's
+    file names; the bytes on disk are those np.save produces for the same arrays (dtype float32 / int32 as isprs:2054-2064)."""
+    from drs_b200 import host, loops
+    pal, occ, chosen = host.init_score_arrays("multinomial", [25, 29, 33])
+    pal[:] = np.arange(len(pal), dtype=np.float32) * 0.37
+    occ[3], chosen[2] = 5, 1
+    out = str(tmp_path) + "/"
+    loops._save_scores(out, 1000, pal, occ, chosen)
+    loops._save_scores(out, 1000, pal, occ, chosen, names=("errorAcc", "errorOccur", "chosenValues"))
+    for name, arr in (("patch_acc_loss", pal), ("patch_occur", occ), ("patch_chosen_values", chosen), ("errorAcc", pal),
+                      ("errorOccur", occ), ("chosenValues", chosen)):
+        ref = tmp_path / ("ref_" + name + ".npy")
+        np.save(ref, arr)
+        assert open(out + name + "_step_1000.npy", "rb").read() == open(ref, "rb").read()
+        assert arr.dtype == (np.float32 if arr is pal else np.int32)
