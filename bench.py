@@ -347,6 +347,142 @@ def run_train_ours(args, rank, world, local, cfg=None, sync_bn=False, extras=Tru
     return out
 
 
+class TimedLoop:
+    """The timing protocol of run_train_ours as a reusable piece: wraps a backend, records the patch sizes it is fed, and
+    provides the step hook that brackets steps W+1 .. W+K with CUDA events (barrier + synchronize on both sides)."""
+
+    def __init__(self, be, session, W, K, local, world=1):
+        import torch
+        self.torch, self.be, self.s, self.W, self.K, self.world = torch, be, session, W, K, world
+        self.crops, self.launches = [], [0, 0]
+        self.ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+        self.depth = int(os.environ.get("DRS_PREFETCH", "2"))
+        self.niter = W + K + self.depth + 2
+        orig = be.submit_train
+
+        def submit(plan, loss_mask=None):
+            self.crops.append(int(plan.crop))
+            return orig(plan, loss_mask)
+
+        be.submit_train = submit
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def hook(self, step, pipe):
+        if step == self.W:
+            pipe.flush()
+            self.barrier()
+            self.launches[0] = self.s.launch_count
+            self.ev[0].record()
+        elif step == self.W + self.K:
+            self.ev[1].record()
+            self.launches[1] = self.s.launch_count
+            pipe.flush()
+            self.barrier()
+
+    def result(self, batch, unit="patches/s"):
+        ms = self.ev[0].elapsed_time(self.ev[1])
+        crops = self.crops[self.W:self.W + self.K]
+        return {"value": batch * self.K / (ms / 1e3), "unit": unit, "us_per_step": ms / self.K * 1e3, "steps": self.K,
+                "gpu_launches_per_step": (self.launches[1] - self.launches[0]) / self.K, "patch_sizes_drawn": crops,
+                "patch_pixels_per_step": int(sum(batch * c * c for c in crops) / self.K)}
+
+
+def quiet_loop(fn):
+    """Run a training loop of loops.py with its log lines discarded and its files in a scratch directory."""
+    import contextlib
+    import tempfile
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp, open(os.devnull, "w") as null:
+        os.chdir(tmp)
+        try:
+            with contextlib.redirect_stdout(null):
+                fn(tmp + "/")
+        finally:
+            os.chdir(cwd)
+
+
+def run_extra_configs(args, local):
+    """The other BASELINE.json configs as extra keys of the line (1 GPU, short runs of the same drop-in loops):
+    configs[0] Dilated6 single_fixed 25 batch 16 (the launch-bound case), configs[2] DenseDilated6 uniform 25..65 on a
+    Potsdam-shaped tile, configs[4] contest + coffee multi_fixed / loss, and configs[3] at crop 65."""
+    import random
+    import torch
+    import drs_b200
+    from drs_b200 import host, loops, synth
+    from drs_b200.backend import GpuBackend
+    dev = torch.device("cuda", local)
+    W, K = 5, max(20, min(args.steps, 50))
+    far = 10 ** 9
+    out = {}
+
+    def isprs_case(key, cfg, note):
+        wl = isprs_workload(cfg)
+        s = drs_b200.Session(cfg["net"], cfg["C"], cfg["K"], weight_decay=cfg["wd"], lr_initial=cfg["lr"], precision="bf16", device=local, seed=5)
+        be = GpuBackend(s, wl["train_data"] + wl["test_data"], wl["train_labels"] + wl["test_labels"], wl["mean"], wl["std"], device=local)
+        tl = TimedLoop(be, s, W, K, local)
+        run_isprs_loop(be, wl, cfg, cfg["batch"], tl.niter, tl.hook)
+        r = tl.result(cfg["batch"])
+        r["tflops_all_kernels"] = conv_flops_train(cfg["net"], cfg["C"], cfg["K"], r["patch_pixels_per_step"]) / (r["us_per_step"] * 1e-6) / 1e12
+        r["workload"] = note
+        s.close()
+        out[key] = r
+
+    isprs_case("configs[0]", dict(net="dilated_icpr_original", dataset="vaihingen", C=4, K=6, batch=16, values=[25], distribution="single_fixed",
+                                  update="acc", lr=0.01, wd=0.005),
+               "isprs_dilated_random.py dilated_icpr_original single_fixed 25, batch 16, Vaihingen-shaped 2000x2500x4 scene (the reference's "
+               "CPU-runnable case; launch-bound on a B200: whole-step CUDA graph)")
+    isprs_case("configs[2]", dict(net="dilated_icpr_rate6_densely", dataset="potsdam", C=5, K=6, batch=16, values=[25, 65], distribution="uniform",
+                                  update="acc", lr=0.01, wd=0.005),
+               "isprs_dilated_random.py dilated_icpr_rate6_densely uniform 25..65, batch 16 per GPU (global 128 on 8 GPUs), Potsdam-shaped "
+               "6000x6000x5 tile")
+
+    # ---- contest (contest_dilated_random.py ... multi_fixed loss): one training scene, label 7 = unlabelled
+    np.random.seed(SEED); random.seed(SEED)
+    img, lab = synth.scene("contest", unlabelled=True)
+    timg, tlab = synth.scene("contest", H=600, W=500, seed=99, unlabelled=True)
+    distr = host.contest_create_distributions_over_classes(lab, 25, 50, 7, verbose=False)
+    mean, std = synth.normalisation(img)
+    values = [25, 33, 41, 49]
+    pal, occ, chosen = host.init_score_arrays("multi_fixed", values, occur_init=1)
+    s = drs_b200.Session("dilated_grsl_rate8", 3, 7, weight_decay=0.005, lr_initial=0.01, decay_rate=0.1, precision="bf16", device=local, seed=5)
+    be = GpuBackend(s, [img, timg], [lab, tlab], mean, std, device=local)
+    tl = TimedLoop(be, s, W, K, local)
+    quiet_loop(lambda outp: loops.contest_train(be, img, lab, tlab, distr, outp, "", 64, tl.niter, "multi_fixed", "loss", pal, occ, chosen,
+                                                None, values, 7, display_step=far, epoch_number=far, val_inteval=far, final_test=False,
+                                                step_hook=tl.hook))
+    r = tl.result(64)
+    r["tflops_all_kernels"] = conv_flops_train("dilated_grsl_rate8", 3, 7, r["patch_pixels_per_step"]) / (r["us_per_step"] * 1e-6) / 1e12
+    r["workload"] = "contest_dilated_random.py dilated_grsl_rate8 multi_fixed 25,33,41,49 loss, batch 64, GRSS-DFC2014-shaped 3989x2830x3 float32 scene"
+    s.close()
+    out["configs[4] contest"] = r
+
+    # ---- coffee (coffee_dilated_random.py ... multi_fixed loss): 500x500x3 float32 tiles, float16 training patches
+    np.random.seed(SEED); random.seed(SEED)
+    tiles = [synth.scene("coffee", seed=200 + i) for i in range(4)]
+    tdata, tlabs = [t[0] for t in tiles[:3]], [t[1] for t in tiles[:3]]
+    distr = host.coffee_create_distributions_over_classes(tlabs, 25, 25, 2)
+    mean, std = synth.normalisation(tdata[0])
+    values = [25, 33, 41]
+    pal, occ, chosen = host.init_score_arrays("multi_fixed", values)
+    s = drs_b200.Session("dilated_grsl", 3, 2, weight_decay=0.005, lr_initial=0.01, decay_rate=0.1, precision="bf16", device=local, seed=5)
+    be = GpuBackend(s, tdata + [tiles[3][0]], tlabs + [tiles[3][1]], mean, std, device=local, train_fp16_patches=True)
+    tl = TimedLoop(be, s, W, K, local)
+    quiet_loop(lambda outp: loops.coffee_train(be, tdata, [tiles[3][1]], distr, outp, "", 64, tl.niter, "multi_fixed", "loss", pal, occ, chosen,
+                                               None, values, 2, display_step=far, epoch_number=far, val_inteval=far, final_test=False,
+                                               step_hook=tl.hook))
+    r = tl.result(64)
+    r["tflops_all_kernels"] = conv_flops_train("dilated_grsl", 3, 2, r["patch_pixels_per_step"]) / (r["us_per_step"] * 1e-6) / 1e12
+    r["workload"] = "coffee_dilated_random.py dilated_grsl multi_fixed 25,33,41 loss, batch 64, three 500x500x3 float32 tiles, float16 training patches"
+    s.close()
+    out["configs[4] coffee"] = r
+    return out
+
+
 def dp_check(s, be, cfg, rank, world, dev, sync_bn):
     """(1) After the timed steps every rank's variables, BN statistics and momentum slots must be bit-identical: one checksum per
     rank, all-gathered.  (2) One SyncBN fp32 step on a global batch split over the ranks against the same step done by a single
@@ -689,6 +825,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the second headline metric")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-cli", action="store_true", help="skip the command-line level rate")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (configs[0], [2], [4], [3] at crop 65)")
     ap.add_argument("--small", action="store_true", help="1500x1500 inference scene (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -725,6 +862,12 @@ def main():
             base["impl"] = "ours"
             if second is not None:
                 base["inference"] = second
+            if world == 1 and not args.no_extra and args.workload == "train":
+                base["configs"] = run_extra_configs(args, local)
+                if second is not None:
+                    c65 = run_infer_ours(args, rank, world, local, steps=3, cfg=dict(INFER_CFG, crop=65))
+                    base["configs"]["configs[3] crop 65"] = {k: c65[k] for k in ("value", "unit", "ms_per_step", "passes_ms", "gpu_launches")}
+                    base["configs"]["configs[3] crop 65"]["roofline_frac"] = c65["roofline"]["frac"]
             if world == 1 and not args.no_cli and args.workload == "train":
                 base["cli"] = cli_rate(TRAIN_CFG)
             if world == 1 and not args.no_cpu:
