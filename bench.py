@@ -443,9 +443,11 @@ def run_extra_configs(args, local):
 
     # ---- contest (contest_dilated_random.py ... multi_fixed loss): one training scene, label 7 = unlabelled
     np.random.seed(SEED); random.seed(SEED)
-    img, lab = synth.scene("contest", unlabelled=True)
-    timg, tlab = synth.scene("contest", H=600, W=500, seed=99, unlabelled=True)
+    # (label blocks of 20 px: the contest's class distribution skips single-class windows, contest:172-189)
+    img, lab = synth.scene("contest", unlabelled=True, block=20)
+    timg, tlab = synth.scene("contest", H=600, W=500, seed=99, unlabelled=True, block=20)
     distr = host.contest_create_distributions_over_classes(lab, 25, 50, 7, verbose=False)
+    assert len(distr) > 64 * 3, "synthetic contest scene has too few multi-class windows"
     mean, std = synth.normalisation(img)
     values = [25, 33, 41, 49]
     pal, occ, chosen = host.init_score_arrays("multi_fixed", values, occur_init=1)

