@@ -37,6 +37,11 @@ static void build_net(NetDesc& n, const drs_config& cfg) {
   static const ConvSpec r6[] = {{5, 1, 64}, {5, 2, 64}, {4, 3, 128}, {4, 4, 128}, {3, 5, 256}, {3, 6, 256}};
   static const ConvSpec r6s[] = {{5, 1, 64}, {5, 2, 64}, {4, 3, 64}, {4, 4, 128}, {3, 5, 128}, {3, 6, 128}};
   static const ConvSpec r6n[] = {{5, 1, 64}, {5, 1, 64}, {4, 1, 128}, {4, 1, 128}, {3, 1, 256}, {3, 1, 256}};
+  static const ConvSpec r1[] = {{5, 1, 64}, {5, 1, 64}, {4, 1, 128}, {4, 1, 128}, {3, 1, 256}, {3, 1, 256}};    // coffee:788-813
+  static const ConvSpec vr[] = {{5, 1, 64}, {5, 2, 64}, {4, 4, 128}, {4, 1, 128}, {3, 2, 256}, {3, 4, 256}};    // coffee:816-841
+  static const ConvSpec old3[] = {{5, 1, 64}, {4, 2, 128}, {3, 4, 256}};                                         // contest:574-603
+  static const int old3_scope[] = {1, 3, 5};        // the reference kept the scope numbers of the layers it commented out
+  const int* scope_no = nullptr;
   const ConvSpec* sp = nullptr;
   int L = 0;
   n.net_type = cfg.net_type;
@@ -52,6 +57,9 @@ static void build_net(NetDesc& n, const drs_config& cfg) {
     case DRS_NET_RATE6: sp = r6; L = 6; n.act = ACT_RELU; break;
     case DRS_NET_RATE6_SMALL: sp = r6s; L = 6; n.act = ACT_RELU; break;
     case DRS_NET_RATE6_NODILATION: sp = r6n; L = 6; n.act = ACT_RELU; break;
+    case DRS_NET_RATE1: sp = r1; L = 6; n.act = ACT_RELU; break;
+    case DRS_NET_VARY_RATE: sp = vr; L = 6; n.act = ACT_RELU; break;
+    case DRS_NET_ICPR_OLD: sp = old3; L = 3; n.act = ACT_RELU; scope_no = old3_scope; break;
     default: DRS_FAIL("Error! Net type not identified: %d", cfg.net_type);
   }
   DRS_CHECK(cfg.channels >= 1 && cfg.channels <= 16, "channels=%d out of range", cfg.channels);
@@ -62,7 +70,7 @@ static void build_net(NetDesc& n, const drs_config& cfg) {
   n.convs.clear();
   for (int i = 0; i < L; ++i) {
     ConvLayer c;
-    c.scope = std::string(prefix) + std::to_string(i + 1);
+    c.scope = std::string(prefix) + std::to_string(scope_no ? scope_no[i] : i + 1);
     c.k = sp[i].k; c.rate = sp[i].rate; c.ci = cin; c.co = sp[i].co;
     const int total = (c.k - 1) * c.rate;
     c.pad_b = total / 2; c.pad_a = total - c.pad_b;

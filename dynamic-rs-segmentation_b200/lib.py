@@ -20,6 +20,10 @@ NET_TYPES = {
     "dilated_icpr_rate6": 4,           # isprs:886
     "dilated_icpr_rate6_small": 5,     # isprs:791
     "dilated_icpr_rate6_nodilation": 6,  # isprs:852
+    "dilated_icpr_rate1": 7,           # coffee:788
+    "dilated_icpr_vary_rate": 8,       # coffee:816
+    "dilated_icpr_old": 9,             # contest:574
+    "dilated_grsl_old": 1,             # contest:606 == dilated_grsl
 }
 PREC = {"fp32": 0, "f16": 1, "bf16": 2}
 SCENE_F64, SCENE_F32 = 0, 1

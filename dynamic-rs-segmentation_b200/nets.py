@@ -29,6 +29,14 @@ SPECS = {
     "dilated_icpr_rate6_nodilation": dict(act="relu", pool=False, dense=False,
                                           convs=[(5, 1, 64), (5, 1, 64), (4, 1, 128), (4, 1, 128), (3, 1, 256), (3, 1, 256)]),
 }
+# further plain stacks of the other two scripts (same primitives)
+SPECS["dilated_icpr_rate1"] = dict(act="relu", pool=False, dense=False,                    # coffee:788-813
+                                   convs=[(5, 1, 64), (5, 1, 64), (4, 1, 128), (4, 1, 128), (3, 1, 256), (3, 1, 256)])
+SPECS["dilated_icpr_vary_rate"] = dict(act="relu", pool=False, dense=False,                # coffee:816-841
+                                       convs=[(5, 1, 64), (5, 2, 64), (4, 4, 128), (4, 1, 128), (3, 2, 256), (3, 4, 256)])
+SPECS["dilated_icpr_old"] = dict(act="relu", pool=False, dense=False, scopes=(1, 3, 5),    # contest:574-603
+                                 convs=[(5, 1, 64), (4, 2, 128), (3, 4, 256)])
+SPECS["dilated_grsl_old"] = SPECS["dilated_grsl"]                                          # contest:606-636 (3 input channels)
 SPECS["dilated8_grsl"] = SPECS["dilated_grsl_rate8"]
 NET_TYPES = tuple(SPECS)
 
@@ -48,7 +56,7 @@ def layer_plan(net_type, channels, isprs_scopes=True):
     prefix = scope_prefix(net_type, isprs_scopes)
     plan, cin = [], channels
     for i, (k, r, co) in enumerate(spec["convs"]):
-        plan.append(("%s%d" % (prefix, i + 1), k, r, cin, co))
+        plan.append(("%s%d" % (prefix, spec.get("scopes", range(1, 99))[i]), k, r, cin, co))
         if spec["dense"]:
             cin = co if i == 0 else cin + co
         else:

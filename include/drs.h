@@ -37,7 +37,11 @@ enum drs_net_type {
   /* plain six-layer stacks of the same primitives */
   DRS_NET_RATE6 = 4,             /* dilated_icpr_rate6            isprs:886-911  rates 1..6, ReLU, no pooling */
   DRS_NET_RATE6_SMALL = 5,       /* dilated_icpr_rate6_small      isprs:791-816  64,64,64,128,128,128 */
-  DRS_NET_RATE6_NODILATION = 6   /* dilated_icpr_rate6_nodilation isprs:852-883  tf.nn.conv2d (rate 1) */
+  DRS_NET_RATE6_NODILATION = 6,  /* dilated_icpr_rate6_nodilation isprs:852-883  tf.nn.conv2d (rate 1) */
+  DRS_NET_RATE1 = 7,             /* dilated_icpr_rate1            coffee:788-813 every rate 1 */
+  DRS_NET_VARY_RATE = 8,         /* dilated_icpr_vary_rate        coffee:816-841 rates 1,2,4,1,2,4 */
+  DRS_NET_ICPR_OLD = 9           /* dilated_icpr_old              contest:574-603 three layers, scopes conv1/conv3/conv5 */
+  /* contest's dilated_grsl_old (contest:606-636) is dilated_grsl with 3 input channels: DRS_NET_DILATED6_POOLING */
 };
 
 /* arithmetic of the convolution stack */

@@ -44,7 +44,14 @@ NET_SPECS = {
     "dilated_icpr_rate6_nodilation": dict(act="relu", pool=False, dense=False, scope="conv",
                                           convs=[(5, 1, 64), (5, 1, 64), (4, 1, 128), (4, 1, 128), (3, 1, 256), (3, 1, 256)]),
 }
-NET_SPECS["dilated8_grsl"] = NET_SPECS["dilated_grsl_rate8"]   # isprs CLI key (isprs:1672-1673)
+NET_SPECS["dilated_icpr_rate1"] = dict(act="relu", pool=False, dense=False, scope="conv",       # coffee:788-813
+                                       convs=[(5, 1, 64), (5, 1, 64), (4, 1, 128), (4, 1, 128), (3, 1, 256), (3, 1, 256)])
+NET_SPECS["dilated_icpr_vary_rate"] = dict(act="relu", pool=False, dense=False, scope="conv",   # coffee:816-841
+                                           convs=[(5, 1, 64), (5, 2, 64), (4, 4, 128), (4, 1, 128), (3, 2, 256), (3, 4, 256)])
+NET_SPECS["dilated_icpr_old"] = dict(act="relu", pool=False, dense=False, scope="conv", scopes=(1, 3, 5),   # contest:574-603
+                                     convs=[(5, 1, 64), (4, 2, 128), (3, 4, 256)])
+NET_SPECS["dilated_grsl_old"] = NET_SPECS["dilated_grsl"]                                       # contest:606-636
+NET_SPECS["dilated8_grsl"] = NET_SPECS["dilated_grsl_rate8"]   # isprs CLI key (isprs:1672-1673)   # isprs CLI key (isprs:1672-1673)
 
 
 def same_pad(k, rate):
@@ -59,7 +66,7 @@ def layer_plan(net_type, channels):
     plan = []
     cin = channels
     for i, (k, r, co) in enumerate(spec["convs"]):
-        plan.append(("%s%d" % (spec["scope"], i + 1), k, r, cin, co))
+        plan.append(("%s%d" % (spec["scope"], spec.get("scopes", range(1, 99))[i]), k, r, cin, co))
         if spec["dense"]:
             cin = co if i == 0 else cin + co     # c1=[conv1,conv2], c2=[c1,conv3] ... (isprs:921-948)
         else:
@@ -117,8 +124,13 @@ class OracleNet:
     fp32.  Activation gates and max-pool winners are then decided on the same rounded values as on the GPU, which removes
     the chaotic gate flips from a gradient comparison (tests/test_gpu_parity.py::test_train_step_bf16_vs_emulating_oracle)."""
 
-    def __init__(self, net_type, channels, num_classes, params, bn_unbiased_ema=True, emulate_bf16=False):
+    def __init__(self, net_type, channels, num_classes, params, bn_unbiased_ema=True, emulate_bf16=False, conv_noise=0.0):
         self.emulate_bf16 = bool(emulate_bf16)
+        # relative Gaussian noise on every convolution output BEFORE it is rounded: stands for a different fp32 summation
+        # order (tensor cores vs CPU, ~1e-6).  Used by the tests to measure how ill-conditioned a step is: with bf16 storage a
+        # 1e-6 perturbation crosses rounding boundaries and moves the filter gradients by several per cent.
+        self.conv_noise = float(conv_noise)
+        self._noise_gen = torch.Generator().manual_seed(12345)
         self.net_type = net_type
         self.spec = NET_SPECS[net_type]
         self.channels = channels
@@ -147,7 +159,10 @@ class OracleNet:
         x = _rb(x_flat.reshape(B, crop, crop, self.channels).permute(0, 3, 1, 2), e)
         feats = None
         for i, (scope, k, r, ci, co) in enumerate(self.plan):
-            z = _rb(_conv_same(x, _rb(p[scope + "/weights"], e), r) + p[scope + "/biases"].view(1, -1, 1, 1), e)
+            z = _conv_same(x, _rb(p[scope + "/weights"], e), r) + p[scope + "/biases"].view(1, -1, 1, 1)
+            if self.conv_noise:
+                z = z * (1.0 + self.conv_noise * torch.randn(z.shape, generator=self._noise_gen))
+            z = _rb(z, e)
             if ztaps is not None:
                 ztaps[scope] = z
             if is_training:
