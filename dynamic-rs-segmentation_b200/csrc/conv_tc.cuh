@@ -512,6 +512,14 @@ static int g_conv_exp_mode = -1;   // drs_bench_conv override of DRS_EXP_MODE
 #define CONV_TC_KPS2_MAX_CO 128      // two K blocks per stage for Co <= this
 #endif
 
+// two CTAs per SM for the small-N layers (DRS_CONV_2CTA=0 turns it off, =128 extends it to Co <= 128).  Measured per
+// 0.76 M-pixel chunk (profiles/r2_conv_two_cta.txt): N=32 161 -> 119 us, N=64 208 -> 190 / 138 -> 130 / 253 -> 237 us; at
+// N=128 the halved shared memory leaves only two 32 KB K blocks in flight per CTA and it loses (184 -> 199, 341 -> 371 us).
+static inline bool conv_tc_two_cta(int co) {
+  static const int lim = getenv("DRS_CONV_2CTA") ? atoi(getenv("DRS_CONV_2CTA")) : 64;
+  return co <= (lim == 1 ? 64 : lim);
+}
+
 template <int BLOCK_K, int EPI_C, typename OutT>
 static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   alignas(64) CUtensorMap tmA, tmB, tmC;
@@ -554,7 +562,12 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   const int kb_bytes = CONV_TC_BM * BLOCK_K * 2 + a.co * BLOCK_K * 2;
   const int fixed = 2 * CONV_TC_BM * EPI_C * 2 + 2 * 256 * 4 + (2 * 8 + 4) * 8 + 16 +
                     (a.stats ? (CONV_TC_BM / EPI_C) * 2 * a.co * 4 : 0);
-  const int budget = 227 * 1024;
+  // Co <= 64: two CTAs per SM.  One CTA's two single-thread roles (TMA issue, MMA issue) need ~600 cycles per stage whatever
+  // the layer, against 256 (N=64) / 512 (N=128) cycles of tensor work: a second resident CTA, with its own producers, issuer
+  // and accumulators, fills the tensor pipe in the gaps.  Needs <= 128 registers (the EPI_C=32 instantiation: 106), half
+  // the shared memory (113 KB) and half the TMEM (2 x 128 columns) per CTA.
+  const bool two_cta = conv_tc_two_cta(a.co) && EPI_C == 32;
+  const int budget = two_cta ? 113 * 1024 : 227 * 1024;
   if ((budget - fixed) / (kps * kb_bytes) < 2) kps = 1;
   const int stage_bytes = kps * kb_bytes;
   int stages = (budget - fixed) / stage_bytes;
@@ -571,7 +584,8 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   const int smem_bytes = p.smem_needed + 1024 <= budget ? p.smem_needed + 1024 : budget;
   p.smem_provided = smem_bytes;
 
-  int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
+  const int max_ctas = two_cta ? 2 * h->sm_count : h->sm_count;
+  int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
   if (instr && BLOCK_K == 64 && EPI_C == 64) {
     // instrumented twin (clock64 around every barrier wait of CTA 0, written to the diagnostic words): bench only
     auto kern = conv_tc_kernel<64, 64, OutT, true>;
@@ -585,7 +599,7 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
     auto kern = conv_tc_kernel<BLOCK_K, EPI_C, OutT, false>;
     static bool attr_set = false;
     if (!attr_set) {
-      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_set = true;
     }
     kern<<<grid, CONV_TC_THREADS, smem_bytes, h->stream>>>(tmA, tmB, tmC, p);
@@ -600,7 +614,7 @@ static void launch_conv_tc(Handle* h, const ConvTcArgs& a) {
   DRS_CHECK(a.in_cstride % 8 == 0 && a.out_cstride % 8 == 0, "conv_tc: channel strides must be multiples of 8");
   DRS_CHECK(a.in_coff % 8 == 0 && a.out_coff % 8 == 0, "conv_tc: channel offsets must be multiples of 8");
   const bool k64 = (a.ci % 64 == 0);
-  const bool e64 = (a.co % 64 == 0);
+  const bool e64 = (a.co % 64 == 0) && !conv_tc_two_cta(a.co);     // two CTAs per SM use the 32-channel epilogue box
   if (a.etype == ET_F16) {
     if (k64 && e64) launch_conv_tc_t<64, 64, __half>(h, a);
     else if (k64) launch_conv_tc_t<64, 32, __half>(h, a);
