@@ -34,7 +34,7 @@ static size_t train_workspace_bytes(Handle* h, int B, int crop, size_t es) {
   add(M * K * 4 * 2);                         // logits, dlogits
   add(M * 2);                                 // labels u8, pred
   add(M * 8 * es);                            // conv1 input padded to 8 channels (tensor-core conv1)
-  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 2);   // one wave: 2 blocks of 256 threads per SM
+  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * DRS_BN_MINBLK);   // one wave of resident blocks
   const int bn_rows = (int)ceil_div(M, nb_bn);
   add((size_t)nb_bn * 2 * 256 * 4);
   const int nb_ce = (int)ceil_div(M, CE_THREADS);
@@ -66,7 +66,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   // ---------------------------------------------------------------- workspace (sized by train_workspace_bytes)
   int maxc = n.cls_in;
   for (auto& c : n.convs) maxc = std::max(maxc, std::max(c.co, c.ci));
-  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 2);   // one wave: 2 blocks of 256 threads per SM
+  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * DRS_BN_MINBLK);   // one wave of resident blocks
   const int bn_rows = (int)ceil_div(M, nb_bn);
   const int nb_ce = (int)ceil_div(M, CE_THREADS);
   const int nb_cls = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 4);
@@ -530,7 +530,7 @@ static void debug_layer_t(Handle* h, const float* z32, const float* dout32, int 
   TA* T = (TA*)arena_take(h, M * C * sizeof(TA));
   TA* DZ = (TA*)arena_take(h, M * C * sizeof(TA));
   uint8_t* idx = (uint8_t*)arena_take(h, M * C);
-  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 2);
+  const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * DRS_BN_MINBLK);
   const int bn_rows = (int)ceil_div(M, nb_bn);
   float* part_bn = (float*)arena_take(h, (size_t)nb_bn * 2 * 256 * 4);
   float* mean = x->mean;

@@ -8,6 +8,17 @@
 
 #include "drs_common.cuh"
 
+// resident blocks per SM the HBM-side training kernels are compiled for (register cap = 65536 / (256 * n)); A/B knobs
+#ifndef DRS_BN_MINBLK
+#define DRS_BN_MINBLK 2      // resident blocks per SM the statistics kernel is compiled for (register cap 65536 / (256 * n))
+#endif
+#ifndef DRS_BNE_MINBLK
+#define DRS_BNE_MINBLK 1
+#endif
+#ifndef DRS_POOL_MINBLK
+#define DRS_POOL_MINBLK 1
+#endif
+
 template <typename T>
 struct alignas(16) Vec8 {
   T v[8];
@@ -273,7 +284,7 @@ __device__ __forceinline__ void pool_hmax_raw(const PoolRawRow& r, __nv_bfloat16
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, DRS_POOL_MINBLK)
 maxpool3_fwd_train_bf16_pipelined_kernel(const __nv_bfloat16* __restrict__ in, int in_cs, int in_co, __nv_bfloat16* __restrict__ out,
                                          int out_cs, int out_co, uint8_t* __restrict__ idx, int C, int B, int crop, int seg, int nseg,
                                          const float* __restrict__ bn_mean, const float* __restrict__ bn_inv_std, int act) {
@@ -383,7 +394,7 @@ __device__ __forceinline__ void pool_bwd_acc(const PoolBwdRow& r, int dy, float 
 // dIn: M*C*4 bytes per layer).  Per-thread sums -> fixed-order block sums in shared memory -> 64-bit fixed point -> integer
 // atomics (order-independent), last block publishes them (same protocol as bn_partial_kernel).
 template <bool STATS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, DRS_POOL_MINBLK)
 maxpool3_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dout, int do_cs, int do_co, const uint8_t* __restrict__ idx,
                          __nv_bfloat16* __restrict__ din, int di_cs, int di_co, int C, int B, int crop, int seg, int nseg,
                          const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ inv_std,
@@ -606,7 +617,7 @@ __device__ __forceinline__ void bn_partial_row(const Vec8<TZ>& zv, const Vec8<TG
 
 constexpr int BN_UNROLL = 4;     // rows in flight per thread (8 x 16-byte loads in the backward mode)
 template <typename TZ, typename TG, int MODE>
-__global__ void __launch_bounds__(BN_THREADS, 2)
+__global__ void __launch_bounds__(BN_THREADS, DRS_BN_MINBLK)
 bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __restrict__ dA, int g_cs, int g_co,
                   const float* __restrict__ mean, const float* __restrict__ inv_std, int act, float* __restrict__ part, int C,
                   int64_t M, int rows_per_block, BnFinish fin) {
@@ -736,7 +747,7 @@ bn_apply_kernel(const T* __restrict__ z, int z_cs, int z_co, const float* __rest
 
 // dZ = inv_std * (g - s0/M - xh * s1/M),  g = dA * act'(xh)      (no gamma/beta: SURVEY F5)
 template <typename TZ, typename TG>
-__global__ void __launch_bounds__(BNE_THREADS)
+__global__ void __launch_bounds__(BNE_THREADS, DRS_BNE_MINBLK)
 bn_bwd_apply_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __restrict__ dA, int g_cs, int g_co,
                     const float* __restrict__ mean, const float* __restrict__ inv_std, const float* __restrict__ sums,
                     double inv_count, int act, TG* __restrict__ dZ, int d_cs, int d_co, int C, int64_t M) {
