@@ -124,7 +124,7 @@ class ClockSampler:
 
 def profiled_traffic(which):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
         return float(json.load(open(p))[which]["dram_bytes_per_launch"])
     except Exception:
@@ -265,7 +265,9 @@ def run_train_ours(args, rank, world, local, cfg=None, sync_bn=False, extras=Tru
         ms = float(t.item())
     value = B * world * K / (ms / 1e3)
     out = dict(metric="train patches/s", value=value, unit="patches/s", ms_per_step=ms / K, dtype="bf16", scaling="weak",
-               gpu_launches=launches[1] - launches[0], clocks=clocks[0])
+               gpu_launches=launches[1] - launches[0], clocks=clocks[0],
+               # the drawn patch sizes differ from run to run (and with the global batch): the pixel rate is the size-neutral view
+               patch_mpixels_per_s=px * world / (ms / 1e3) / 1e6)
     if not extras:
         s.close()
         return out
