@@ -121,49 +121,25 @@ class GpuBackend:
         return x, y, pred, B, crop
 
     def sync_host_rng(self):
-        """Data parallel: every rank must run the SAME host policy (patch size, batch selection, augmentation draws), i.e. the
-        same two random streams.  The reference never seeds, and cache files created by rank 0 only make the ranks
-        consume different amounts of the streams, so the loops call this before the first draw and after every cache block:
-        rank 0 draws one seed from its own stream and every rank re-seeds ``random`` and ``np.random`` with it."""
-        if self.world <= 1:
-            return
-        import random
-        import zlib
-        import torch.distributed as dist
-        st = np.random.get_state()
-        h = zlib.crc32(st[1].tobytes() + repr(st[2:]).encode() + repr(random.getstate()).encode())
-        v = self.torch.tensor([h, -h], dtype=self.torch.int64, device=self.dev)
-        dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        if int(v[0]) == -int(v[1]):
-            return                       # already on the same streams (a harness seeded every rank alike)
-        t = self.torch.tensor([np.random.randint(0, 2 ** 31 - 1) if self.rank == 0 else 0], dtype=self.torch.int64, device=self.dev)
-        dist.broadcast(t, src=0)
-        seed = int(t.item())
-        np.random.seed(seed)
-        random.seed(seed)
+        """Data parallel: same host policy streams on every rank (dist.sync_host_rng); no-op for one process."""
+        if self.world > 1:
+            from . import dist as ddist
+            ddist.sync_host_rng()
 
     def rank0_first(self, fn):
-        """Cache files in the working directory (isprs:2087-2115, 1634-1639): rank 0 creates them, the others wait and load."""
+        """Cache files in the working directory: rank 0 creates them, the others wait and load (dist.rank0_first)."""
         if self.world <= 1:
             return fn()
-        import torch.distributed as dist
-        if self.rank == 0:
-            r = fn()
-            dist.barrier()
-            return r
-        dist.barrier()
-        return fn()
+        from . import dist as ddist
+        return ddist.rank0_first(fn)
 
     def _check_same_plan(self, plan):
         """DRS_DP_DEBUG=1: assert that patch size and batch are identical on every rank before the step is enqueued."""
         import zlib
-        import torch.distributed as dist
+        from . import dist as ddist
         h = 0 if getattr(plan, "local", False) else \
             zlib.crc32(np.ascontiguousarray(plan.inst).tobytes() + np.ascontiguousarray(plan.flips).tobytes())
-        v = self.torch.tensor([plan.crop, h, -plan.crop, -h], dtype=self.torch.int64, device=self.dev)
-        dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        if int(v[0]) != -int(v[2]) or int(v[1]) != -int(v[3]):
-            raise RuntimeError("data-parallel ranks disagree on the step plan (patch size / batch): host RNG streams diverged")
+        ddist.check_same_plan(int(plan.crop), int(h))
 
     def submit_train(self, plan, loss_mask=None):
         t = self.torch

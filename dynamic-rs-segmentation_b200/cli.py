@@ -30,16 +30,11 @@ def rank0_first(fn):
     """Cache files in the working directory (isprs:2087-2115): under torchrun rank 0 runs ``fn`` (which may create and save),
     the others wait at a barrier and run it afterwards (finding the files and loading them).  Writers save to a temporary
     name and os.replace it, so a reader never sees a half-written file."""
-    rank, world, _ = dist_setup()
+    _, world, _ = dist_setup()
     if world <= 1:
         return fn()
-    import torch.distributed as dist
-    if rank == 0:
-        r = fn()
-        dist.barrier()
-        return r
-    dist.barrier()
-    return fn()
+    from . import dist as ddist
+    return ddist.rank0_first(fn)
 
 
 def save_atomic(path, array, **kw):

@@ -93,6 +93,62 @@ def attach_nccl(session, sync_bn=False, group=None):
     return world
 
 
+def _dist_device(group=None):
+    import torch
+    import torch.distributed as dist
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def sync_host_rng(group=None):
+    """Every data-parallel rank must run the SAME host policy (patch size, batch selection), i.e. the same two random
+    streams.  The reference never seeds and cache files created by rank 0 only make the ranks consume different
+    amounts of the streams: if the ranks' ``random`` / ``np.random`` states differ, rank 0 draws one seed from its own stream
+    and every rank re-seeds both with it; if they already agree (a harness seeded every rank alike) nothing is touched.
+    Returns True when a re-seed happened."""
+    import random
+    import zlib
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) <= 1:
+        return False
+    dev = _dist_device(group)
+    st = np.random.get_state()
+    h = zlib.crc32(st[1].tobytes() + repr(st[2:]).encode() + repr(random.getstate()).encode())
+    v = torch.tensor([h, -h], dtype=torch.int64, device=dev)
+    dist.all_reduce(v, op=dist.ReduceOp.MAX, group=group)
+    if int(v[0]) == -int(v[1]):
+        return False
+    t = torch.tensor([np.random.randint(0, 2 ** 31 - 1) if dist.get_rank(group) == 0 else 0], dtype=torch.int64, device=dev)
+    dist.broadcast(t, src=0, group=group)
+    np.random.seed(int(t.item()))
+    random.seed(int(t.item()))
+    return True
+
+
+def rank0_first(fn, group=None):
+    """Cache files in the working directory (isprs:2087-2115, 1634-1639): rank 0 runs ``fn`` (which may create and save), the
+    other ranks wait at a barrier and run it afterwards (finding the files and loading them)."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) <= 1:
+        return fn()
+    if dist.get_rank(group) == 0:
+        r = fn()
+        dist.barrier(group=group)
+        return r
+    dist.barrier(group=group)
+    return fn()
+
+
+def check_same_plan(crop, digest, group=None):
+    """DRS_DP_DEBUG: raise unless patch size and batch digest are identical on every rank."""
+    import torch
+    import torch.distributed as dist
+    v = torch.tensor([crop, digest, -crop, -digest], dtype=torch.int64, device=_dist_device(group))
+    dist.all_reduce(v, op=dist.ReduceOp.MAX, group=group)
+    if int(v[0]) != -int(v[2]) or int(v[1]) != -int(v[3]):
+        raise RuntimeError("data-parallel ranks disagree on the step plan (patch size / batch): host RNG streams diverged")
+
+
 def rank_slice(batch, rank, world):
     """This rank's share of a global batch (contiguous, equal sizes)."""
     per = len(batch) // world

@@ -129,3 +129,64 @@ def test_stripe_bounds_cover_the_scene():
             cuts = ddist.stripe_bounds(H, world)
             assert cuts[0] == 0 and cuts[-1] == H and all(a <= b for a, b in zip(cuts[:-1], cuts[1:]))
             assert [ddist.stripe_bounds(H, world, r) for r in range(world)] == list(zip(cuts[:-1], cuts[1:]))
+
+
+def _rng_worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import random
+    import torch.distributed as dist
+    import drs_b200  # noqa: F401
+    from drs_b200 import dist as ddist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = []
+    # (1) a harness seeded every rank alike: nothing may be touched (the draws stay those of the single-process run)
+    np.random.seed(5); random.seed(5)
+    res.append(int(ddist.sync_host_rng()))
+    res.append(int(np.random.randint(0, 1 << 30)))
+    # (2) unseeded / diverged ranks (rank 0 created a cache file and consumed draws the others did not): re-seeded from rank 0
+    np.random.seed(100 + rank); random.seed(200 + rank)
+    res.append(int(ddist.sync_host_rng()))
+    res += [int(np.random.randint(0, 1 << 30)), int(random.randrange(1 << 30))]
+    # (3) only the python stream differs
+    random.seed(300 + rank)
+    res.append(int(ddist.sync_host_rng()))
+    res += [int(np.random.randint(0, 1 << 30)), int(random.randrange(1 << 30))]
+    # (4) cache files: rank 0 creates (atomically), the others wait and load -- one table for everybody
+    cache = os.path.join(out_dir, "table.npy")
+
+    def table():
+        if os.path.isfile(cache):
+            return np.load(cache)
+        t = np.random.RandomState(rank + 1).randint(0, 360, size=1000)
+        np.save(cache + ".tmp.npy", t)
+        os.replace(cache + ".tmp.npy", cache)
+        return t
+
+    t = ddist.rank0_first(table)
+    res.append(int(t.sum()))
+    # (5) the per-step plan check
+    ddist.check_same_plan(37, 12345)
+    try:
+        ddist.check_same_plan(37 + rank, 12345)
+        res.append(0)
+    except RuntimeError:
+        res.append(1)
+    np.save(os.path.join(out_dir, "rng_%d.npy" % rank), np.array(res, dtype=np.int64))
+    dist.destroy_process_group()
+
+
+def test_host_rng_sync_and_cache_files_world2(tmp_path):
+    """Data-parallel host rules: same streams on every rank, cache files created once, plan agreement checked."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_rng_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "rng_0.npy"), np.load(tmp_path / "rng_1.npy")
+    assert a[0] == 0 and b[0] == 0 and a[1] == b[1]                  # already equal: untouched
+    np.random.seed(5)
+    assert a[1] == int(np.random.randint(0, 1 << 30))                # ... and still the single-process draw
+    assert a[2] == 1 and b[2] == 1 and a[3] == b[3] and a[4] == b[4]  # diverged: re-seeded, both streams equal afterwards
+    assert a[5] == 1 and b[5] == 1 and a[6] == b[6] and a[7] == b[7]
+    assert a[8] == b[8]                                              # one cache table
+    assert a[9] == 1 and b[9] == 1                                   # disagreement detected on every rank

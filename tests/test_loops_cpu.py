@@ -161,6 +161,61 @@ def test_pipelined_loop_with_device_rotation_reproduces_reference_trace(golden, 
     assert out.getvalue().count("Training Minibatch") == 2       # display_step 5: flushed at steps 5 and 10
 
 
+def test_data_parallel_local_planning_shares_sizes_and_batches(golden, drs, tmp_path, monkeypatch):
+    """Data-parallel host rules: with rank-local augmentation streams every rank still draws the same patch
+    size and the same global batch per step (shared streams) and plans only ITS slice; the augmentation of different ranks
+    comes from different generators.  DRS_DP_PLAN=shared plans the whole global batch on the shared stream instead."""
+    from drs_b200 import host, loops
+    tr_d, tr_l = golden["train_scenes"], golden["train_labels"]
+    te_d, te_l = golden["test_scenes"], golden["test_labels"]
+    monkeypatch.chdir(tmp_path)
+
+    class RankBackend(FakeDeviceBackend):
+        def __init__(self, rank, world, *a):
+            super().__init__(*a)
+            self.rank, self.world, self.plans = rank, world, []
+
+        def own_rows(self, n):
+            per = n // self.world
+            return self.rank * per, (self.rank + 1) * per
+
+        def submit_train(self, plan, loss_mask=None):
+            self.plans.append((plan.crop, bool(plan.local), np.array(plan.inst), np.array(plan.flips), np.array(plan.noise_on)))
+            if not plan.local:         # shared mode: the backend slices (GpuBackend._gather); emulate it for the stand-in
+                return super().submit_train(plan, loss_mask)
+            return super().submit_train(plan, loss_mask)
+
+    def run(rank, mode):
+        monkeypatch.setenv("DRS_DP_PLAN", mode)
+        d = tmp_path / ("%s_%d" % (mode, rank))      # own working directory: the loop caches its test instances there, and a
+        d.mkdir()                                    # run that loads the cache consumes fewer draws than the one that made it
+        monkeypatch.chdir(d)                         # (under torchrun: dist.rank0_first + dist.sync_host_rng)
+        np.random.seed(77)
+        random.seed(78)
+        with redirect_stdout(io.StringIO()):
+            tr_distr = host.create_distributions_over_classes(tr_l, 25, 5, 6)
+            te_distr = host.create_distributions_over_classes(te_l, 25, 5, 6)
+            rot = host.create_rotation_distribution(tr_distr)
+        values = [13, 17, 21]
+        pal, occ, chosen = host.init_score_arrays("multi_fixed", values)
+        be = RankBackend(rank, 2, tr_d, tr_l, np.full(4, 0.5), np.full(4, 0.3), 4, 6)
+        with redirect_stdout(io.StringIO()):
+            loops.isprs_train(be, tr_d, tr_l, tr_distr, rot, te_d, te_l, te_distr, ["1"], 8, 6, "acc", "multi_fixed", values, pal, occ,
+                              chosen, None, 20, str(tmp_path) + "/", 50, "dp", "", final_validation=False)
+        return be.plans
+
+    a, b = run(0, "local"), run(1, "local")
+    full = run(0, "shared")
+    assert len(a) == len(b) == len(full) == 6
+    differs = False
+    for (ca, la, ia, fa, na), (cb, lb, ib, fb, nb), (cf, lf, i_f, ff, nf) in zip(a, b, full):
+        assert la and lb and not lf
+        assert ca == cb                                     # same patch size on every rank
+        assert len(ia) == len(ib) == 4 and len(i_f) == 8     # a rank plans its half of the global batch of 8
+        differs = differs or not (np.array_equal(fa, fb) and np.array_equal(na, nb))
+    assert differs                                          # different augmentation draws on different ranks
+
+
 @pytest.mark.parametrize("ci", [0, 1, 2, 3])
 def test_isprs_train_loop_reproduces_reference_trace(golden, drs, tmp_path, ci):
     from drs_b200 import host, loops
