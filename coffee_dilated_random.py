@@ -19,7 +19,8 @@ from drs_b200.host import BatchColors  # noqa: E402
 
 NUM_CLASSES = 2
 NET_TYPES = ('dilated_icpr_original', 'dilated_grsl', 'dilated_icpr_rate6_densely', 'dilated_grsl_rate8', 'dilated8_grsl',
-             'dilated_icpr_rate6', 'dilated_icpr_rate6_small', 'dilated_icpr_rate1', 'dilated_icpr_vary_rate', 'dilated_icpr_rate6_nodilation')
+             'dilated_icpr_rate6', 'dilated_icpr_rate6_small', 'dilated_icpr_rate1', 'dilated_icpr_vary_rate', 'dilated_icpr_rate6_nodilation',
+             'dilated_icpr_rate6_avgpool', 'dilated_icpr_rate6_SE', 'dilated_icpr_rate6_squeeze')
 
 
 def load_tiles(path):

@@ -20,7 +20,7 @@ from drs_b200.host import BatchColors  # noqa: E402
 
 NUM_CLASSES = 7
 NET_TYPES = ('dilated_icpr_old', 'dilated_grsl_old', 'dilated_grsl', 'dilated_icpr_rate6_densely', 'dilated_grsl_rate8', 'dilated8_grsl',
-             'dilated_icpr_rate6', 'dilated_icpr_rate6_nodilation')
+             'dilated_icpr_rate6', 'dilated_icpr_rate6_nodilation', 'dilated_icpr_rate6_SE', 'dilated_icpr_rate6_squeeze')
 
 
 def main():

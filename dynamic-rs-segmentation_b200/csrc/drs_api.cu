@@ -23,6 +23,7 @@ thread_local char g_drs_err[1024] = {0};
   return 0;
 
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)ceil_div(n, t); }
+#include "variants.cuh"
 static inline int act_type(const Handle* h) { return h->cfg.precision == DRS_PREC_FP32 ? ET_F32 : (h->cfg.precision == DRS_PREC_F16 ? ET_F16 : ET_BF16); }
 
 // ------------------------------------------------------------------------------------------------
@@ -48,6 +49,8 @@ static void build_net(NetDesc& n, const drs_config& cfg) {
   n.channels = cfg.channels;
   n.classes = cfg.num_classes;
   n.pool = n.dense = false;
+  n.squeeze = false;
+  n.se.clear();
   const char* prefix = "conv";
   switch (cfg.net_type) {
     case DRS_NET_DILATED6: sp = d6; L = 6; n.act = ACT_RELU; if (cfg.isprs_scopes) prefix = "main_conv"; break;
@@ -60,6 +63,9 @@ static void build_net(NetDesc& n, const drs_config& cfg) {
     case DRS_NET_RATE1: sp = r1; L = 6; n.act = ACT_RELU; break;
     case DRS_NET_VARY_RATE: sp = vr; L = 6; n.act = ACT_RELU; break;
     case DRS_NET_ICPR_OLD: sp = old3; L = 3; n.act = ACT_RELU; scope_no = old3_scope; break;
+    case DRS_NET_RATE6_AVGPOOL: sp = r6; L = 6; n.act = ACT_RELU; break;
+    case DRS_NET_RATE6_SE: sp = r6; L = 6; n.act = ACT_RELU; break;
+    case DRS_NET_RATE6_SQUEEZE: sp = r6; L = 1; n.act = ACT_RELU; n.squeeze = true; break;
     default: DRS_FAIL("Error! Net type not identified: %d", cfg.net_type);
   }
   DRS_CHECK(cfg.channels >= 1 && cfg.channels <= 16, "channels=%d out of range", cfg.channels);
@@ -80,8 +86,54 @@ static void build_net(NetDesc& n, const drs_config& cfg) {
     c.b_off = off; off += c.co;
     c.mm_off = boff; boff += c.co;
     c.mv_off = boff; boff += c.co;
+    if (cfg.net_type == DRS_NET_RATE6_AVGPOOL && i < 5) { c.post = 1; c.post_k = i < 3 ? 5 : 7; }     // isprs:824-837
+    if (cfg.net_type == DRS_NET_RATE6_SE && (i & 1)) {                                               // isprs:1042-1051
+      SeBlock sb;
+      sb.name = "se" + std::to_string(i / 2 + 1);
+      sb.c = c.co; sb.r = c.co / 4;
+      sb.w1_off = off; off += (int64_t)sb.c * sb.r;
+      sb.b1_off = off; off += sb.r;
+      sb.w2_off = off; off += (int64_t)sb.r * sb.c;
+      sb.b2_off = off; off += sb.c;
+      c.post = 2; c.se = (int)n.se.size();
+      n.se.push_back(sb);
+    }
     n.convs.push_back(c);
     if (n.dense) { feat += c.co; cin = feat; } else cin = c.co;
+  }
+  if (n.squeeze) {
+    // _squeeze_conv_layer (isprs:726-742, 1068-1075): name, in, out, k_dim, kernel, rate
+    struct Sq { const char* name; int in, out, kd, ks, rate; };
+    static const Sq sq[] = {{"conv2", 64, 64, 32, 5, 2}, {"conv3", 64, 128, 64, 4, 3}, {"conv4", 128, 128, 64, 4, 4},
+                            {"conv5", 128, 256, 64, 3, 5}, {"conv6", 256, 256, 128, 3, 6}};
+    int prev_group = 0, prev_cs = n.convs[0].co;
+    for (const Sq& q : sq) {
+      const int s1 = (int)n.convs.size();
+      for (int part = 0; part < 3; ++part) {
+        ConvLayer c;
+        c.scope = std::string(q.name) + (part == 0 ? "_s1" : part == 1 ? "_s2_1" : "_s2_2");
+        c.k = part == 2 ? q.ks : 1;
+        c.rate = q.rate;
+        c.ci = part == 0 ? q.in : q.kd;
+        c.co = part == 0 ? q.kd : q.out / 2;
+        const int total = (c.k - 1) * c.rate;
+        c.pad_b = total / 2; c.pad_a = total - c.pad_b;
+        c.in_coff = 0;
+        c.in_group = part == 0 ? prev_group : s1;
+        c.in_cs = part == 0 ? prev_cs : q.kd;
+        c.out_group = part == 0 ? s1 : s1 + 1;
+        c.out_cs = part == 0 ? q.kd : q.out;
+        c.out_coff = part == 2 ? q.out / 2 : 0;
+        c.w_off = off; off += (int64_t)c.k * c.k * c.ci * c.co;
+        c.b_off = off; off += c.co;
+        c.mm_off = boff; boff += c.co;
+        c.mv_off = boff; boff += c.co;
+        n.convs.push_back(c);
+      }
+      prev_group = s1 + 1;
+      prev_cs = q.out;
+      cin = q.out;
+    }
   }
   n.cls_in = cin;
   n.cls_w_off = off; off += (int64_t)cin * cfg.num_classes;
@@ -89,7 +141,7 @@ static void build_net(NetDesc& n, const drs_config& cfg) {
   n.n_trainable = off;
   n.n_bnstat = boff;
   n.feat_stride = 0;
-  for (auto& c : n.convs) n.feat_stride = std::max(n.feat_stride, c.co);
+  for (auto& c : n.convs) n.feat_stride = std::max(n.feat_stride, std::max(c.co, c.out_cs));
   if (n.dense) n.feat_stride = feat;
 }
 
@@ -246,6 +298,10 @@ extern "C" int drs_create(drs_handle_t* out, const drs_config* cfg) {
     for (auto& c : h->net.convs)
       for (int64_t i = c.w_off; i < c.b_off; ++i) isw[i] = 1;
     for (int64_t i = h->net.cls_w_off; i < h->net.cls_b_off; ++i) isw[i] = 1;
+    for (auto& sb : h->net.se) {                         // _fc_layer weights carry weight decay too (isprs:668-670)
+      for (int64_t i = sb.w1_off; i < sb.b1_off; ++i) isw[i] = 1;
+      for (int64_t i = sb.w2_off; i < sb.b2_off; ++i) isw[i] = 1;
+    }
     CUDA_CHECK(cudaMemcpy(x->is_weight, isw.data(), nt, cudaMemcpyHostToDevice));
     // moving_mean = 0, moving_variance = 1 (Appendix B.3)
     std::vector<float> bn(h->net.n_bnstat, 0.0f);
@@ -411,6 +467,12 @@ static bool find_var(Handle* h, const std::string& name, VarRef& r, bool grad = 
       if (slot(c.scope + "/moving_variance", h->bnstat + c.mv_off, nullptr, c.co)) return true;
     }
   }
+  for (auto& sb : h->net.se) {
+    if (slot(sb.name + "_fc1/weights", base + sb.w1_off, h->moms + sb.w1_off, (int64_t)sb.c * sb.r)) return true;
+    if (slot(sb.name + "_fc1/biases", base + sb.b1_off, h->moms + sb.b1_off, sb.r)) return true;
+    if (slot(sb.name + "_fc2/weights", base + sb.w2_off, h->moms + sb.w2_off, (int64_t)sb.r * sb.c)) return true;
+    if (slot(sb.name + "_fc2/biases", base + sb.b2_off, h->moms + sb.b2_off, sb.c)) return true;
+  }
   if (slot("conv_classifier/weights", base + h->net.cls_w_off, h->moms + h->net.cls_w_off, (int64_t)h->net.cls_in * h->net.classes)) return true;
   if (slot("conv_classifier/biases", base + h->net.cls_b_off, h->moms + h->net.cls_b_off, h->net.classes)) return true;
   if (!grad && (name == "global_step" || name == "main_global_step")) { r = {nullptr, 1, 1}; return true; }
@@ -425,6 +487,12 @@ static void list_vars(Handle* h, std::vector<std::pair<std::string, int64_t>>& v
     v.push_back({c.scope + "/moving_variance", c.co});
     v.push_back({c.scope + "/weights/Momentum", wc});
     v.push_back({c.scope + "/biases/Momentum", c.co});
+  }
+  for (auto& sb : h->net.se) {
+    const std::pair<std::string, int64_t> vs[4] = {{sb.name + "_fc1/weights", (int64_t)sb.c * sb.r}, {sb.name + "_fc1/biases", sb.r},
+                                                    {sb.name + "_fc2/weights", (int64_t)sb.r * sb.c}, {sb.name + "_fc2/biases", sb.c}};
+    for (auto& pr : vs) v.push_back(pr);
+    for (auto& pr : vs) v.push_back({pr.first + "/Momentum", pr.second});
   }
   v.push_back({"conv_classifier/weights", (int64_t)h->net.cls_in * h->net.classes});
   v.push_back({"conv_classifier/biases", h->net.classes});
@@ -518,7 +586,7 @@ struct RepackSeg {
   long long start;
 };
 struct RepackTable {
-  RepackSeg seg[18];
+  RepackSeg seg[40];       // up to 20 tensor-core layers (the squeeze net has 15), fprop + dgrad operand each
   int n, etype;
   long long total;
 };
@@ -680,7 +748,9 @@ static size_t forward_eval_workspace(Handle* h, int B, int crop) {
   const int64_t M = (int64_t)B * crop * crop;
   const size_t es = h->cfg.precision == DRS_PREC_FP32 ? 4 : 2;
   const int nbuf = h->net.dense ? 1 : 3;
-  return nbuf * ((size_t)M * h->net.feat_stride * es + 4096) + (size_t)M * h->net.classes * 4 + (size_t)M * 32 * es + 65536;
+  size_t se_bytes = 0;
+  for (auto& sb : h->net.se) se_bytes = std::max(se_bytes, ((size_t)B * (3 * sb.c + sb.r)) * 4 + 4096);
+  return nbuf * ((size_t)M * h->net.feat_stride * es + 4096) + (size_t)M * h->net.classes * 4 + (size_t)M * 32 * es + se_bytes + 65536;
 }
 
 template <typename TA>
@@ -696,14 +766,24 @@ static void forward_eval_t(Handle* h, const float* x_dev, int B, int crop, float
   TA* bufs[3] = {nullptr, nullptr, nullptr};
   for (int i = 0; i < nbuf; ++i) bufs[i] = (TA*)arena_take(h, buf_bytes);
   float* logits = logits_dev ? logits_dev : (float*)arena_take(h, (size_t)M * n.classes * 4);
+  float* se_scratch = nullptr;
+  {
+    size_t se_floats = 0;
+    for (auto& sb : n.se) se_floats = std::max(se_floats, (size_t)B * (3 * sb.c + sb.r));
+    if (se_floats) se_scratch = (float*)arena_take(h, se_floats * 4);
+  }
   h->taps.clear();
 
   ActBuf cur{nullptr, 0, 0};
   int xi = 0;   // index of the buffer holding the current input (non-dense)
+  int sq_s = 0, sq_c = 0;   // squeeze modules: buffers of the squeeze output S and of the concatenated module output
   for (size_t l = 0; l < n.convs.size(); ++l) {
     ConvLayer& c = n.convs[l];
     ActBuf out;
+    const int sq_part = (n.squeeze && l >= 1) ? (int)((l - 1) % 3) : -1;    // 0: _s1, 1: _s2_1, 2: _s2_2 (isprs:726-742)
     if (n.dense) out = {bufs[0], fs, c.out_coff};
+    else if (sq_part == 0) { sq_s = (xi + 1) % 3; sq_c = (xi + 2) % 3; out = {bufs[sq_s], fs, 0}; }
+    else if (sq_part >= 1) { cur = {bufs[sq_s], fs, 0}; out = {bufs[sq_c], fs, c.out_coff}; }
     else out = {bufs[(xi + 1) % 3], fs, 0};
     if (l == 0 && ElemTag<TA>::v != ET_F32 && c.w_fprop && conv1_tc_supported(c.k, c.rate, c.ci, c.co)) {
       TA* x8 = (TA*)arena_take(h, (size_t)M * 8 * sizeof(TA));
@@ -730,6 +810,32 @@ static void forward_eval_t(Handle* h, const float* x_dev, int B, int crop, float
       launch_maxpool3_fwd<TA>(h, (const TA*)out.p, out.cs, out.co, (TA*)pout.p, pout.cs, pout.co, nullptr, c.co, B, crop);
       cur = pout;
       xi = (xi + 2) % 3;
+    } else if (c.post == 1) {
+      ActBuf pout{bufs[(xi + 2) % 3], fs, 0};
+      launch_avgpool_fwd<TA>(h, (const TA*)out.p, out.cs, out.co, (TA*)pout.p, pout.cs, pout.co, c.co, B, crop, c.post_k);
+      cur = pout;
+      xi = (xi + 2) % 3;
+    } else if (c.post == 2) {
+      // squeeze-and-excitation gate, in place (per-image statistics: the result depends on the patch, as in the reference)
+      const SeBlock& sb = n.se[c.se];
+      float* sum = se_scratch;
+      float* sv = sum + (size_t)B * sb.c;
+      float* ev = sv + (size_t)B * sb.c;
+      float* hv = ev + (size_t)B * sb.c;
+      se_sum_kernel<TA, 0><<<dim3(B, (unsigned)ceil_div(sb.c, 64)), 256, 0, h->stream>>>((const TA*)out.p, out.cs, out.co, nullptr, 0, 0, sb.c,
+                                                                                      crop * crop, sum);
+      LAUNCH_CHECK(h);
+      se_fc_fwd_kernel<<<B, 256, 0, h->stream>>>(sum, 1.0f / (float)(crop * crop), h->params + sb.w1_off, h->params + sb.b1_off,
+                                                h->params + sb.w2_off, h->params + sb.b2_off, sb.c, sb.r, sv, hv, ev);
+      LAUNCH_CHECK(h);
+      se_scale_fwd_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>((const TA*)out.p, out.cs, out.co, ev, (TA*)out.p, out.cs, out.co,
+                                                                              c.co, M, crop * crop);
+      LAUNCH_CHECK(h);
+      cur = out;
+      xi = (xi + 1) % 3;
+    } else if (sq_part >= 0) {
+      if (sq_part == 0) cur = out;                       // S: read by the two expand convolutions
+      else if (sq_part == 2) { cur = {bufs[sq_c], fs, 0}; xi = sq_c; }    // the module's concatenated output
     } else if (n.dense) {
       cur = {bufs[0], fs, 0};
     } else {

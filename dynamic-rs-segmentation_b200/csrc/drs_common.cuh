@@ -59,6 +59,21 @@ struct ConvLayer {
   float* fold_scale = nullptr;  // [co] eval-mode BN folded: y = act(conv*scale + shift)
   float* fold_shift = nullptr;
   float* raw_scale = nullptr;   // [co] ones
+  // structural variants (variants.cuh): a post-op behind the activation, and explicit buffer routing for the squeeze modules
+  int post = 0;           // 0 none, 1 SAME average pooling post_k x post_k (isprs:753-758), 2 squeeze-and-excitation gate
+  int post_k = 0;
+  int se = -1;            // index into NetDesc::se
+  int in_group = -1;      // layer that leads the buffer this layer reads (-1: the previous layer / the network input)
+  int in_cs = 0;          // channel stride of that buffer
+  int out_group = -1;     // layer that leads the buffer this layer writes a channel slice of (-1: its own buffer)
+  int out_cs = 0;         // channel stride of the output buffer (0: co)
+};
+
+// _squeeze_excitation_layer (isprs:682-697): two fully connected layers on the per-image channel means
+struct SeBlock {
+  std::string name;       // "se1": variables se1_fc1/{weights,biases}, se1_fc2/{weights,biases}
+  int c, r;               // channels, channels / ratio
+  int64_t w1_off, b1_off, w2_off, b2_off;   // offsets into the flat trainable buffer, in this order, right behind the layer
 };
 
 struct NetDesc {
@@ -66,6 +81,8 @@ struct NetDesc {
   int channels, classes;
   int act;            // ACT_RELU / ACT_LRELU
   bool pool, dense;
+  bool squeeze = false;   // dilated_icpr_rate6_squeeze: conv2..6 are squeeze modules (three convs, two share an output buffer)
+  std::vector<SeBlock> se;
   std::vector<ConvLayer> convs;
   int cls_in;         // classifier input width
   int64_t cls_w_off, cls_b_off;

@@ -25,9 +25,12 @@ static size_t train_workspace_bytes(Handle* h, int B, int crop, size_t es) {
   for (auto& c : n.convs) {
     add(M * c.co * es);                       // Z
     if (n.pool) add(M * c.co);                // idx
-    if (!n.dense) add(M * c.co * es);         // X_{l+1}
+    if (!n.dense) add(M * std::max(c.co, c.out_cs) * es);   // X_{l+1} (a squeeze module's two expand convs share one)
+    if (c.post) add(M * c.co * es);           // A: the activation in front of the post-op (average pool / SE gate)
+    if (n.squeeze) add(M * std::max(c.co, c.out_cs) * es);  // gradient of the layer's output buffer
   }
   if (n.dense) add(M * n.feat_stride * es * 2);   // F and GF
+  for (auto& sb : n.se) add(((size_t)B * (5 * sb.c + sb.r) + (size_t)B * (2 * sb.c * sb.r + sb.r + sb.c)) * 4 + 4096);
   add(M * maxc * es);                         // T
   add(M * maxc * es * 2);                     // DZ (two buffers: wgrad of layer l overlaps the backward of layer l-1)
   add(M * maxc * es * 2);                     // G ping-pong / dense dgrad temp
@@ -78,7 +81,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   ensure_arena(h, train_workspace_bytes(h, B, crop, es));
   h->arena.reset();
 
-  std::vector<TA*> Z(L), Xn(L);
+  std::vector<TA*> Z(L), Xn(L), Apre(L, nullptr), Gg(L, nullptr);
   std::vector<uint8_t*> idx(L, nullptr);
   TA* F = nullptr;
   TA* GF = nullptr;
@@ -86,7 +89,26 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     ConvLayer& c = n.convs[l];
     Z[l] = (TA*)arena_take(h, M * c.co * es);
     if (n.pool) idx[l] = (uint8_t*)arena_take(h, M * c.co);
-    if (!n.dense) Xn[l] = (TA*)arena_take(h, M * c.co * es);
+    // output buffer: a layer's own, or (squeeze modules) the buffer led by layer out_group that it writes a channel slice of
+    if (!n.dense) {
+      if (c.out_group < 0 || c.out_group == l) Xn[l] = (TA*)arena_take(h, M * std::max(c.co, c.out_cs) * es);
+      else Xn[l] = Xn[c.out_group];
+    }
+    if (c.post) Apre[l] = (TA*)arena_take(h, M * c.co * es);
+    if (n.squeeze) {
+      if (c.out_group < 0 || c.out_group == l) Gg[l] = (TA*)arena_take(h, M * std::max(c.co, c.out_cs) * es);
+      else Gg[l] = Gg[c.out_group];
+    }
+  }
+  // squeeze-and-excitation scratch per gate: channel sums, means, hidden, gate, d(gate), d(mean), per-image parameter partials
+  struct SeBuf { float *sum, *s, *hid, *e, *de, *ds, *part; };
+  std::vector<SeBuf> seb(n.se.size());
+  for (size_t i = 0; i < n.se.size(); ++i) {
+    const SeBlock& sb = n.se[i];
+    float* base = (float*)arena_take(h, ((size_t)B * (5 * sb.c + sb.r) + (size_t)B * (2 * sb.c * sb.r + sb.r + sb.c)) * 4);
+    seb[i].sum = base; seb[i].s = base + (size_t)B * sb.c; seb[i].e = seb[i].s + (size_t)B * sb.c;
+    seb[i].de = seb[i].e + (size_t)B * sb.c; seb[i].ds = seb[i].de + (size_t)B * sb.c; seb[i].hid = seb[i].ds + (size_t)B * sb.c;
+    seb[i].part = seb[i].hid + (size_t)B * sb.r;
   }
   if (n.dense) {
     F = (TA*)arena_take(h, M * n.feat_stride * es);
@@ -116,7 +138,14 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   auto input_of = [&](int l) -> ActBuf {
     if (l == 0) return ActBuf{(void*)x_dev, n.channels, 0};
     if (n.dense) return ActBuf{F, n.feat_stride, 0};
+    const ConvLayer& c = n.convs[l];
+    if (c.in_group >= 0) return ActBuf{Xn[c.in_group], c.in_cs, 0};      // squeeze modules: explicit routing
     return ActBuf{Xn[l - 1], n.convs[l - 1].co, 0};
+  };
+  auto output_of = [&](int l) -> ActBuf {                                  // the view of its output buffer layer l writes
+    const ConvLayer& c = n.convs[l];
+    if (n.dense) return ActBuf{F, n.feat_stride, c.out_coff};
+    return ActBuf{Xn[l], c.out_cs > 0 ? c.out_cs : c.co, c.out_cs > 0 ? c.out_coff : 0};
   };
   const bool conv1_on_tc = ElemTag<TA>::v == ET_BF16 && !getenv("DRS_NO_CONV1_TC_TRAIN") &&
                            conv1_tc_supported(n.convs[0].k, n.convs[0].rate, n.convs[0].ci, n.convs[0].co);
@@ -165,13 +194,32 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     if (n.pool) {
       launch_maxpool3_fwd<TA>(h, Z[l], c.co, 0, Xn[l], c.co, 0, idx[l], c.co, B, crop, mean, istd, n.act);
     } else {
-      ActBuf ab = n.dense ? ActBuf{F, n.feat_stride, c.out_coff} : ActBuf{Xn[l], c.co, 0};
-      bn_apply_kernel<TA><<<bne_grid(M, h->sm_count), BNE_THREADS, 0, h->stream>>>(Z[l], c.co, 0, mean, istd, n.act, (TA*)ab.p, ab.cs, ab.co, c.co, M);
+      ActBuf ab = output_of(l);
+      ActBuf act_out = c.post ? ActBuf{Apre[l], c.co, 0} : ab;        // a post-op keeps the activation in front of it
+      bn_apply_kernel<TA><<<bne_grid(M, h->sm_count), BNE_THREADS, 0, h->stream>>>(Z[l], c.co, 0, mean, istd, n.act, (TA*)act_out.p, act_out.cs, act_out.co, c.co, M);
       LAUNCH_CHECK(h);
+      if (c.post == 1) {
+        launch_avgpool_fwd<TA>(h, Apre[l], c.co, 0, (TA*)ab.p, ab.cs, ab.co, c.co, B, crop, c.post_k);
+      } else if (c.post == 2) {
+        // squeeze-and-excitation (isprs:682-697): per-image channel means -> FC -> ReLU -> FC -> sigmoid -> gate
+        const SeBlock& sb = n.se[c.se];
+        SeBuf& q = seb[c.se];
+        se_sum_kernel<TA, 0><<<dim3(B, (unsigned)ceil_div(sb.c, 64)), 256, 0, h->stream>>>(Apre[l], c.co, 0, nullptr, 0, 0, sb.c, crop * crop, q.sum);
+        LAUNCH_CHECK(h);
+        se_fc_fwd_kernel<<<B, 256, 0, h->stream>>>(q.sum, 1.0f / (float)(crop * crop), h->params + sb.w1_off, h->params + sb.b1_off,
+                                                  h->params + sb.w2_off, h->params + sb.b2_off, sb.c, sb.r, q.s, q.hid, q.e);
+        LAUNCH_CHECK(h);
+        se_scale_fwd_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>(Apre[l], c.co, 0, q.e, (TA*)ab.p, ab.cs, ab.co, c.co, M, crop * crop);
+        LAUNCH_CHECK(h);
+      }
     }
-    h->taps[c.scope] = {n.dense ? (void*)F : (void*)Xn[l], ElemTag<TA>::v, n.dense ? n.feat_stride : c.co, n.dense ? c.out_coff : 0, c.co, M};
+    {
+      const ActBuf tb = output_of(l);
+      h->taps[c.scope] = {tb.p, ElemTag<TA>::v, tb.cs, tb.co, c.co, M};
+    }
   }
-  ActBuf feat = n.dense ? ActBuf{F, n.feat_stride, 0} : ActBuf{Xn[L - 1], n.convs[L - 1].co, 0};
+  ActBuf feat = n.dense ? ActBuf{F, n.feat_stride, 0}
+                        : ActBuf{Xn[L - 1], n.convs[L - 1].out_cs > 0 ? n.convs[L - 1].out_cs : n.convs[L - 1].co, 0};
   launch_classifier_fwd<TA>(h, (const TA*)feat.p, feat.cs, feat.co, n.cls_in, h->params + n.cls_w_off, h->params + n.cls_b_off, K, logits,
                             pred, M);
 
@@ -216,9 +264,11 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     LAUNCH_CHECK(h);
     CUDA_CHECK(cudaEventRecord(x->ev_bucket_ready, h->stream));      // classifier gradients + extras are in the buffer
   }
-  TA* Gcur = n.dense ? GF : G0;
+  // squeeze net: one gradient buffer per output buffer (Gg), because a squeeze convolution's output feeds two layers
+  TA* Gcur = n.dense ? GF : (n.squeeze ? Gg[L - 1] : G0);
   TA* Gnext = G1;
   const int gcs0 = n.dense ? n.feat_stride : n.cls_in;
+  std::vector<char> grad_written(L, 0);        // squeeze: has the gradient buffer led by layer g been written in this step?
   {
     const int cvc = n.cls_in / 8;
     if (cvc <= 256 && 256 % cvc == 0 && ElemTag<TA>::v != ET_F32 && !getenv("DRS_NO_CLS_REG")) {
@@ -234,7 +284,9 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   int gcs = gcs0;   // channel stride of Gcur (non-dense)
   for (int l = L - 1; l >= 0; --l) {
     ConvLayer& c = n.convs[l];
-    ActBuf dOut = n.dense ? ActBuf{GF, n.feat_stride, c.out_coff} : ActBuf{Gcur, gcs, 0};
+    ActBuf dOut = n.dense ? ActBuf{GF, n.feat_stride, c.out_coff}
+                : n.squeeze ? ActBuf{Gg[l], c.out_cs > 0 ? c.out_cs : c.co, c.out_cs > 0 ? c.out_coff : 0}
+                            : ActBuf{Gcur, gcs, 0};
     ActBuf dA = dOut;
     float* mean = x->mean + c.mm_off;
     float* istd = x->inv_std + c.mm_off;
@@ -246,6 +298,28 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     if (n.pool) {
       if (fused_bwd_stats) launch_maxpool3_bwd<TA>(h, (const TA*)dOut.p, dOut.cs, dOut.co, idx[l], T, c.co, 0, c.co, B, crop, &finb, Z[l], mean, istd, n.act);
       else launch_maxpool3_bwd<TA>(h, (const TA*)dOut.p, dOut.cs, dOut.co, idx[l], T, c.co, 0, c.co, B, crop);
+      dA = ActBuf{T, c.co, 0};
+    }
+    if (c.post == 1) {
+      launch_avgpool_bwd<TA>(h, (const TA*)dOut.p, dOut.cs, dOut.co, T, c.co, 0, c.co, B, crop, c.post_k);
+      dA = ActBuf{T, c.co, 0};
+    } else if (c.post == 2) {
+      // gate backward: dA = dOut * e + ds,  ds from d(gate) = sum_px dOut * A through sigmoid, FC2, ReLU, FC1 and the mean;
+      // the parameter gradients are per-image partials reduced in fixed order
+      const SeBlock& sb = n.se[c.se];
+      SeBuf& q = seb[c.se];
+      se_sum_kernel<TA, 1><<<dim3(B, (unsigned)ceil_div(sb.c, 64)), 256, 0, h->stream>>>((const TA*)dOut.p, dOut.cs, dOut.co, Apre[l], c.co, 0, sb.c,
+                                                                                      crop * crop, q.de);
+      LAUNCH_CHECK(h);
+      se_fc_bwd_kernel<<<B, 256, 0, h->stream>>>(q.de, q.s, q.hid, q.e, h->params + sb.w1_off, h->params + sb.w2_off, sb.c, sb.r,
+                                                1.0f / (float)(crop * crop), q.ds, q.part);
+      LAUNCH_CHECK(h);
+      const int64_t np = (int64_t)2 * sb.c * sb.r + sb.r + sb.c;       // W1, b1, W2, b2 are contiguous in the flat buffer
+      reduce_partials_kernel<<<reduce_partials_grid(np), RP_COLS * RP_LANES, 0, h->stream>>>(q.part, h->grads + sb.w1_off, np, B);
+      LAUNCH_CHECK(h);
+      se_scale_bwd_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>((const TA*)dOut.p, dOut.cs, dOut.co, q.e, q.ds, T, c.co, 0, c.co, M,
+                                                                              crop * crop);
+      LAUNCH_CHECK(h);
       dA = ActBuf{T, c.co, 0};
     }
     if (!fused_bwd_stats) {
@@ -314,6 +388,19 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
         run_conv<TA>(h, dzb, c.co, (const float*)c.w_dgrad, c.w_dgrad, tmp, c.ci, B, crop, c.k, c.rate, c.pad_a, x->ones, x->zeros, ACT_NONE);
         add_slice_kernel<TA><<<nblk(M * (c.ci / 8), 256), 256, 0, h->stream>>>(GF, n.feat_stride, 0, G0, c.ci, 0, c.ci, M);
         LAUNCH_CHECK(h);
+      } else if (n.squeeze) {
+        // gradient of the input buffer (led by layer `ig`): the first consumer processed writes it, the second adds
+        const int ig = c.in_group >= 0 ? c.in_group : l - 1;
+        if (!grad_written[ig]) {
+          ActBuf gn{Gg[ig], c.ci, 0};
+          run_conv<TA>(h, dzb, c.co, (const float*)c.w_dgrad, c.w_dgrad, gn, c.ci, B, crop, c.k, c.rate, c.pad_a, x->ones, x->zeros, ACT_NONE);
+          grad_written[ig] = 1;
+        } else {
+          ActBuf tmp{G0, c.ci, 0};
+          run_conv<TA>(h, dzb, c.co, (const float*)c.w_dgrad, c.w_dgrad, tmp, c.ci, B, crop, c.k, c.rate, c.pad_a, x->ones, x->zeros, ACT_NONE);
+          add_slice_kernel<TA><<<nblk(M * (c.ci / 8), 256), 256, 0, h->stream>>>(Gg[ig], c.ci, 0, G0, c.ci, 0, c.ci, M);
+          LAUNCH_CHECK(h);
+        }
       } else {
         ActBuf gn{Gnext, c.ci, 0};
         run_conv<TA>(h, dzb, c.co, (const float*)c.w_dgrad, c.w_dgrad, gn, c.ci, B, crop, c.k, c.rate, c.pad_a, x->ones, x->zeros, ACT_NONE);

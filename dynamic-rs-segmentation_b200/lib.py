@@ -24,6 +24,9 @@ NET_TYPES = {
     "dilated_icpr_vary_rate": 8,       # coffee:816
     "dilated_icpr_old": 9,             # contest:574
     "dilated_grsl_old": 1,             # contest:606 == dilated_grsl
+    "dilated_icpr_rate6_avgpool": 10,  # isprs:819 (dispatched by the coffee script, coffee:1215)
+    "dilated_icpr_rate6_SE": 11,       # isprs:1036
+    "dilated_icpr_rate6_squeeze": 12,  # isprs:1064
 }
 PREC = {"fp32": 0, "f16": 1, "bf16": 2}
 SCENE_F64, SCENE_F32 = 0, 1

@@ -37,6 +37,18 @@ SPECS["dilated_icpr_vary_rate"] = dict(act="relu", pool=False, dense=False,     
 SPECS["dilated_icpr_old"] = dict(act="relu", pool=False, dense=False, scopes=(1, 3, 5),    # contest:574-603
                                  convs=[(5, 1, 64), (4, 2, 128), (3, 4, 256)])
 SPECS["dilated_grsl_old"] = SPECS["dilated_grsl"]                                          # contest:606-636 (3 input channels)
+# structural variants: same conv stack as dilated_icpr_rate6 with a post-op behind some layers
+_R6 = [(5, 1, 64), (5, 2, 64), (4, 3, 128), (4, 4, 128), (3, 5, 256), (3, 6, 256)]
+# SAME average pooling 5x5 / 7x7, stride 1, behind conv1..conv5 (isprs:819-849, coffee:721-751; dispatched by the coffee script)
+SPECS["dilated_icpr_rate6_avgpool"] = dict(act="relu", pool=False, dense=False, convs=_R6,
+                                           post=[("avg", 5), ("avg", 5), ("avg", 5), ("avg", 7), ("avg", 7), None])
+# squeeze-and-excitation gate (ratio 4) behind conv2, conv4, conv6 (isprs:1036-1061, 682-697)
+SPECS["dilated_icpr_rate6_SE"] = dict(act="relu", pool=False, dense=False, convs=_R6,
+                                      post=[None, ("se", 4, "se1"), None, ("se", 4, "se2"), None, ("se", 4, "se3")])
+# conv2..conv6 replaced by squeeze modules (isprs:1064-1086, 726-742): 1x1 in->k, then 1x1 k->out/2 and kxk dilated k->out/2, concat
+SPECS["dilated_icpr_rate6_squeeze"] = dict(act="relu", pool=False, dense=False, convs=[(5, 1, 64)],
+                                           squeeze=[("conv2", 64, 64, 32, 5, 2), ("conv3", 64, 128, 64, 4, 3), ("conv4", 128, 128, 64, 4, 4),
+                                                    ("conv5", 128, 256, 64, 3, 5), ("conv6", 256, 256, 128, 3, 6)])
 SPECS["dilated8_grsl"] = SPECS["dilated_grsl_rate8"]
 NET_TYPES = tuple(SPECS)
 
@@ -61,7 +73,23 @@ def layer_plan(net_type, channels, isprs_scopes=True):
             cin = co if i == 0 else cin + co
         else:
             cin = co
+    for (name, in_dim, out_dim, k_dim, ksz, rate) in spec.get("squeeze", ()):      # _squeeze_conv_layer (isprs:726-742)
+        plan.append((name + "_s1", 1, rate, in_dim, k_dim))
+        plan.append((name + "_s2_1", 1, rate, k_dim, out_dim // 2))
+        plan.append((name + "_s2_2", ksz, rate, k_dim, out_dim // 2))
+        cin = out_dim
     return plan, cin
+
+
+def se_blocks(net_type):
+    """[(layer index, scope, channels, channels // ratio)] of the squeeze-and-excitation gates (isprs:682-697)."""
+    spec = SPECS[net_type]
+    out = []
+    for i, po in enumerate(spec.get("post", ())):
+        if po is not None and po[0] == "se":
+            c = spec["convs"][i][2]
+            out.append((i, po[2], c, c // po[1]))
+    return out
 
 
 def variable_shapes(net_type, channels, num_classes, isprs_scopes=True):
@@ -72,6 +100,11 @@ def variable_shapes(net_type, channels, num_classes, isprs_scopes=True):
         shapes[scope + "/biases"] = (co,)
         shapes[scope + "/moving_mean"] = (co,)
         shapes[scope + "/moving_variance"] = (co,)
+    for _, name, c, r in se_blocks(net_type):            # _fc_layer (isprs:666-679)
+        shapes[name + "_fc1/weights"] = (c, r)
+        shapes[name + "_fc1/biases"] = (r,)
+        shapes[name + "_fc2/weights"] = (r, c)
+        shapes[name + "_fc2/biases"] = (c,)
     shapes["conv_classifier/weights"] = (1, 1, cls_in, num_classes)
     shapes["conv_classifier/biases"] = (num_classes,)
     return shapes
@@ -85,7 +118,14 @@ def initial_variables(net_type, channels, num_classes, seed, isprs_scopes=True):
     rs = np.random.RandomState(seed)
     out = OrderedDict()
     for name, shape in variable_shapes(net_type, channels, num_classes, isprs_scopes).items():
-        if name.endswith("/weights"):
+        if name.endswith("/weights") and len(shape) == 2:
+            # tf.truncated_normal_initializer(stddev=0.005): draws beyond two standard deviations are redrawn (isprs:669)
+            w = rs.normal(0.0, 0.005, size=shape)
+            while np.any(np.abs(w) > 0.01):
+                bad = np.abs(w) > 0.01
+                w[bad] = rs.normal(0.0, 0.005, size=int(bad.sum()))
+            out[name] = w.astype(np.float32)
+        elif name.endswith("/weights"):
             kh, kw, ci, co = shape
             lim = math.sqrt(6.0 / (kh * kw * ci + kh * kw * co))
             out[name] = rs.uniform(-lim, lim, size=shape).astype(np.float32)

@@ -40,7 +40,11 @@ enum drs_net_type {
   DRS_NET_RATE6_NODILATION = 6,  /* dilated_icpr_rate6_nodilation isprs:852-883  tf.nn.conv2d (rate 1) */
   DRS_NET_RATE1 = 7,             /* dilated_icpr_rate1            coffee:788-813 every rate 1 */
   DRS_NET_VARY_RATE = 8,         /* dilated_icpr_vary_rate        coffee:816-841 rates 1,2,4,1,2,4 */
-  DRS_NET_ICPR_OLD = 9           /* dilated_icpr_old              contest:574-603 three layers, scopes conv1/conv3/conv5 */
+  DRS_NET_ICPR_OLD = 9,          /* dilated_icpr_old              contest:574-603 three layers, scopes conv1/conv3/conv5 */
+  /* structural variants (csrc/variants.cuh): same conv stack as dilated_icpr_rate6 plus a new layer type */
+  DRS_NET_RATE6_AVGPOOL = 10,    /* dilated_icpr_rate6_avgpool    isprs:819-849  SAME average pooling 5x5 / 7x7 behind conv1..5 */
+  DRS_NET_RATE6_SE = 11,         /* dilated_icpr_rate6_SE         isprs:1036-1061 squeeze-and-excitation gate behind conv2/4/6 */
+  DRS_NET_RATE6_SQUEEZE = 12     /* dilated_icpr_rate6_squeeze    isprs:1064-1086 conv2..6 as squeeze modules (1x1 -> 1x1 || kxk) */
   /* contest's dilated_grsl_old (contest:606-636) is dilated_grsl with 3 input channels: DRS_NET_DILATED6_POOLING */
 };
 

@@ -19,7 +19,8 @@ from drs_b200.host import BatchColors  # noqa: E402
 
 NUM_CLASSES = 6
 NET_TYPES = ('dilated_icpr_original', 'dilated_grsl', 'dilated_icpr_rate6_densely', 'dilated8_grsl', 'dilated_grsl_rate8',
-             'dilated_icpr_rate6', 'dilated_icpr_rate6_small', 'dilated_icpr_rate6_nodilation')
+             'dilated_icpr_rate6', 'dilated_icpr_rate6_small', 'dilated_icpr_rate6_nodilation', 'dilated_icpr_rate6_SE',
+             'dilated_icpr_rate6_squeeze')
 
 
 def main():

@@ -51,6 +51,15 @@ NET_SPECS["dilated_icpr_vary_rate"] = dict(act="relu", pool=False, dense=False, 
 NET_SPECS["dilated_icpr_old"] = dict(act="relu", pool=False, dense=False, scope="conv", scopes=(1, 3, 5),   # contest:574-603
                                      convs=[(5, 1, 64), (4, 2, 128), (3, 4, 256)])
 NET_SPECS["dilated_grsl_old"] = NET_SPECS["dilated_grsl"]                                       # contest:606-636
+_R6 = [(5, 1, 64), (5, 2, 64), (4, 3, 128), (4, 4, 128), (3, 5, 256), (3, 6, 256)]
+NET_SPECS["dilated_icpr_rate6_avgpool"] = dict(act="relu", pool=False, dense=False, scope="conv", convs=_R6,      # isprs:819-849
+                                               post=[("avg", 5), ("avg", 5), ("avg", 5), ("avg", 7), ("avg", 7), None])
+NET_SPECS["dilated_icpr_rate6_SE"] = dict(act="relu", pool=False, dense=False, scope="conv", convs=_R6,           # isprs:1036-1061
+                                          post=[None, ("se", 4, "se1"), None, ("se", 4, "se2"), None, ("se", 4, "se3")])
+NET_SPECS["dilated_icpr_rate6_squeeze"] = dict(act="relu", pool=False, dense=False, scope="conv", convs=[(5, 1, 64)],   # isprs:1064-1086
+                                               squeeze=[("conv2", 64, 64, 32, 5, 2), ("conv3", 64, 128, 64, 4, 3),
+                                                        ("conv4", 128, 128, 64, 4, 4), ("conv5", 128, 256, 64, 3, 5),
+                                                        ("conv6", 256, 256, 128, 3, 6)])
 NET_SPECS["dilated8_grsl"] = NET_SPECS["dilated_grsl_rate8"]   # isprs CLI key (isprs:1672-1673)   # isprs CLI key (isprs:1672-1673)
 
 
@@ -71,7 +80,18 @@ def layer_plan(net_type, channels):
             cin = co if i == 0 else cin + co     # c1=[conv1,conv2], c2=[c1,conv3] ... (isprs:921-948)
         else:
             cin = co
+    for (name, in_dim, out_dim, k_dim, ksz, rate) in spec.get("squeeze", ()):      # _squeeze_conv_layer (isprs:726-742)
+        plan.append((name + "_s1", 1, rate, in_dim, k_dim))
+        plan.append((name + "_s2_1", 1, rate, k_dim, out_dim // 2))
+        plan.append((name + "_s2_2", ksz, rate, k_dim, out_dim // 2))
+        cin = out_dim
     return plan, cin
+
+
+def se_blocks(net_type):
+    spec = NET_SPECS[net_type]
+    return [(i, po[2], spec["convs"][i][2], spec["convs"][i][2] // po[1]) for i, po in enumerate(spec.get("post", ()))
+            if po is not None and po[0] == "se"]
 
 
 def init_params(net_type, channels, num_classes, seed):
@@ -86,6 +106,14 @@ def init_params(net_type, channels, num_classes, seed):
         p[scope + "/moving_mean"] = np.zeros((co,), dtype=np.float32)
         p[scope + "/moving_variance"] = np.ones((co,), dtype=np.float32)
     lim = math.sqrt(6.0 / (cls_in + num_classes))
+    for _, name, c, r in se_blocks(net_type):        # _fc_layer: truncated normal (stddev 0.005), bias 0.1 (isprs:666-679)
+        for nm, shape in ((name + "_fc1", (c, r)), (name + "_fc2", (r, c))):
+            w = rs.normal(0.0, 0.005, size=shape)
+            while np.any(np.abs(w) > 0.01):
+                bad = np.abs(w) > 0.01
+                w[bad] = rs.normal(0.0, 0.005, size=int(bad.sum()))
+            p[nm + "/weights"] = w.astype(np.float32)
+            p[nm + "/biases"] = np.full((shape[1],), 0.1, dtype=np.float32)
     p["conv_classifier/weights"] = rs.uniform(-lim, lim, size=(1, 1, cls_in, num_classes)).astype(np.float32)
     p["conv_classifier/biases"] = np.zeros((num_classes,), dtype=np.float32)
     return p
@@ -157,9 +185,10 @@ class OracleNet:
         B = x_flat.shape[0]
         e = self.emulate_bf16
         x = _rb(x_flat.reshape(B, crop, crop, self.channels).permute(0, 3, 1, 2), e)
-        feats = None
-        for i, (scope, k, r, ci, co) in enumerate(self.plan):
-            z = _conv_same(x, _rb(p[scope + "/weights"], e), r) + p[scope + "/biases"].view(1, -1, 1, 1)
+
+        def conv_bn_act(inp, scope, r):
+            """_conv_layer (isprs:700-723): atrous conv + bias -> batch_norm(center=False, scale=False) -> activation."""
+            z = _conv_same(inp, _rb(p[scope + "/weights"], e), r) + p[scope + "/biases"].view(1, -1, 1, 1)
             if self.conv_noise:
                 z = z * (1.0 + self.conv_noise * torch.randn(z.shape, generator=self._noise_gen))
             z = _rb(z, e)
@@ -178,9 +207,25 @@ class OracleNet:
                 mean = p[scope + "/moving_mean"]
                 var = p[scope + "/moving_variance"]
             zh = (z - mean.view(1, -1, 1, 1)) * torch.rsqrt(var.view(1, -1, 1, 1) + BN_EPS)
-            a = self._act(zh)
+            return self._act(zh)
+
+        feats = None
+        post = self.spec.get("post")
+        n_plain = len(self.spec["convs"])
+        for i, (scope, k, r, ci, co) in enumerate(self.plan[:n_plain]):
+            a = conv_bn_act(x, scope, r)
             if self.spec["pool"]:
                 a = F.max_pool2d(a, 3, 1, 1)                # SAME: -inf padding (Appendix B.4)
+            po = post[i] if post else None
+            if po is not None and po[0] == "avg":
+                # tf.nn.avg_pool(SAME, stride 1): the mean over the in-image part of the window (isprs:753-758)
+                a = F.avg_pool2d(a, po[1], 1, po[1] // 2, count_include_pad=False)
+            elif po is not None and po[0] == "se":
+                # _squeeze_excitation_layer (isprs:682-697): global mean -> FC -> ReLU -> FC -> sigmoid -> channel gate
+                sq = a.mean(dim=(2, 3))
+                ex = torch.relu(sq @ p[po[2] + "_fc1/weights"] + p[po[2] + "_fc1/biases"])
+                ex = torch.sigmoid(ex @ p[po[2] + "_fc2/weights"] + p[po[2] + "_fc2/biases"])
+                a = a * ex.view(ex.shape[0], -1, 1, 1)
             a = _rb(a, e)
             if taps is not None:
                 taps[scope] = a.permute(0, 2, 3, 1).detach()
@@ -189,6 +234,14 @@ class OracleNet:
                 x = feats
             else:
                 x = a
+        for (name, in_dim, out_dim, k_dim, ksz, rate) in self.spec.get("squeeze", ()):
+            # _squeeze_conv_layer (isprs:726-742): 1x1 squeeze, then a 1x1 and a kxk dilated expand branch, concatenated
+            s1 = _rb(conv_bn_act(x, name + "_s1", rate), e)
+            b1 = conv_bn_act(s1, name + "_s2_1", rate)
+            b2 = conv_bn_act(s1, name + "_s2_2", rate)
+            x = _rb(torch.cat([b1, b2], dim=1), e)
+            if taps is not None:
+                taps[name] = x.permute(0, 2, 3, 1).detach()
         wc = p["conv_classifier/weights"]
         logits = F.conv2d(x, wc.permute(3, 2, 0, 1).contiguous()) + p["conv_classifier/biases"].view(1, -1, 1, 1)
         return logits.permute(0, 2, 3, 1).contiguous()

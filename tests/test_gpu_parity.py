@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 NETS = (("dilated_icpr_original", 4, 6), ("dilated_grsl", 4, 6), ("dilated_icpr_rate6_densely", 5, 6),
         ("dilated_grsl_rate8", 5, 6), ("dilated_grsl", 3, 7), ("dilated_icpr_original", 3, 2),
         ("dilated_icpr_rate6", 4, 6), ("dilated_icpr_rate6_small", 5, 6), ("dilated_icpr_rate6_nodilation", 4, 6),
-        ("dilated_icpr_rate1", 3, 2), ("dilated_icpr_vary_rate", 3, 2), ("dilated_icpr_old", 3, 7), ("dilated_grsl_old", 3, 7))
+        ("dilated_icpr_rate1", 3, 2), ("dilated_icpr_vary_rate", 3, 2), ("dilated_icpr_old", 3, 7), ("dilated_grsl_old", 3, 7),
+        ("dilated_icpr_rate6_avgpool", 3, 2), ("dilated_icpr_rate6_SE", 4, 6), ("dilated_icpr_rate6_squeeze", 4, 6))
 
 
 def torch_conv(x, w, rate):
@@ -733,7 +734,8 @@ def test_trained_weights_inference_argmax_agreement(drs):
 
 TRAIN_NETS = (("dilated_icpr_original", 4, 6, False), ("dilated_grsl", 4, 6, False),
               ("dilated_icpr_rate6_densely", 5, 6, False), ("dilated_grsl_rate8", 3, 7, True),
-              ("dilated_icpr_rate6_small", 4, 6, False), ("dilated_icpr_vary_rate", 3, 2, False), ("dilated_icpr_old", 3, 7, True))
+              ("dilated_icpr_rate6_small", 4, 6, False), ("dilated_icpr_vary_rate", 3, 2, False), ("dilated_icpr_old", 3, 7, True),
+              ("dilated_icpr_rate6_avgpool", 3, 2, False), ("dilated_icpr_rate6_SE", 4, 6, False), ("dilated_icpr_rate6_squeeze", 4, 6, False))
 
 
 def _grad_report(orc, s):
