@@ -304,3 +304,70 @@ def test_multiscale_validation_reproduces_reference_label_maps(tmp_path):
         order = [int(c) for i, c in enumerate(ref_crops) if i == 0 or c != ref_crops[i - 1]]
         assert be.crops == order
         assert np.array_equal(maps[0].astype(np.uint8), g["ms_%d_labels" % ci])
+
+
+class FakeContestBackend:
+    """Closed-form stand-in for the contest loop: float32 scene, flips by index range, loss mask label != 7 (contest:236-239),
+    asynchronous interface like the product backend."""
+
+    def __init__(self, scene, labels, mean, std):
+        self.scene, self.labels, self.mean, self.std = scene, labels, mean, std
+        self.log, self.saved, self.out = [], [], {}
+        self.ticket = 0
+
+    def submit_train(self, plan, loss_mask=None):
+        assert loss_mask == "label!=7"
+        x, y = host_np.apply_plan([self.scene], [self.labels], plan.inst, plan.flips, plan.crop, self.mean, self.std, cast=False)
+        B = len(plan.inst)
+        bx = np.reshape(x, (-1, plan.crop * plan.crop * 3))
+        self.log.append((1, plan.crop, B, float(np.sum(bx.astype(np.float64))), float(np.sum(y.astype(np.float64)))))
+        loss, pred = fake_train_fetches(bx, plan.crop, 3, 7)
+        cm = np.zeros((7, 7), dtype=np.uint32)
+        self.out[self.ticket] = (loss, cm, 0)
+        self.ticket += 1
+        return self.ticket - 1
+
+    def train_result(self, ticket):
+        return self.out.pop(ticket)
+
+    def save(self, path):
+        self.saved.append(path)
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_contest_train_loop_reproduces_reference_trace(drs, tmp_path, ci, monkeypatch):
+    """loops.contest_train (pipelined) against the trace of the reference's own contest.train (contest:970-1158) through the
+    closed-form fake sess.run (oracle/make_golden_contest_train.py): patch sizes, batches incl. the reference's own ``it``
+    bookkeeping and epoch reshuffles, flipped + normalised float32 patches, labels, score arrays after the final
+    select_best_patch_size."""
+    from drs_b200 import host, loops
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "contest_train_golden.npz"))
+    case = g["cases"][ci]
+    dist, upd = {0: "single_fixed", 1: "multi_fixed", 2: "uniform"}[int(case[0])], UPD[int(case[1])]
+    values = [int(v) for v in case[2:] if v > 0]
+    img, lab, tlab = g["scene"], g["labels"], g["test_labels"]
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(3000 + ci)
+    random.seed(4000 + ci)
+    with redirect_stdout(io.StringIO()):
+        distr = host.contest_create_distributions_over_classes(lab, 9, 17, 7)
+        mean_f, std_f = host.contest_create_mean_and_std(img, distr, 9)
+    assert np.array_equal(np.asarray(distr, dtype=np.int64), g["c%d_distr" % ci])
+    assert np.array_equal(mean_f, g["c%d_mean" % ci]) and np.array_equal(std_f, g["c%d_std" % ci])
+    pal, occ, chosen = host.init_score_arrays(dist, values, occur_init=1)
+    if pal is None:                                   # single_fixed: the reference still passes (unused) arrays
+        pal, occ, chosen = np.zeros(1, dtype=np.float32), np.ones(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+    be = FakeContestBackend(img, lab, mean_f, std_f)
+    with redirect_stdout(io.StringIO()):
+        loops.contest_train(be, img, lab, tlab, distr, str(tmp_path) + "/", "", 4, 23, dist, upd, pal, occ, chosen, None, values, 7,
+                            final_test=False)
+    ref = g["c%d_log" % ci]
+    got = np.array(be.log, dtype=np.float64)
+    assert got.shape == ref.shape
+    assert np.array_equal(got[:, :3], ref[:, :3])
+    assert np.array_equal(got[:, 4], ref[:, 4])
+    assert np.allclose(got[:, 3], ref[:, 3], rtol=1e-6, atol=1e-4)     # float32 patches summed in float64
+    if dist != "single_fixed":
+        assert np.array_equal(pal, g["c%d_pal" % ci]) and np.array_equal(occ, g["c%d_occ" % ci])
+        assert np.array_equal(chosen, g["c%d_chosen" % ci])
+    assert be.saved == [str(tmp_path) + "/model-23"] and not be.out
