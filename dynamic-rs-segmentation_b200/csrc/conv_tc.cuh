@@ -106,9 +106,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  // [row group][2][co] running column sums; present (and counted in smem_needed) only in the training forward
-  float* s_stat = reinterpret_cast<float*>(tmem_holder + 4);
+  // Training forward: the running column sums live in registers (st0 / st1 below) and are combined through the staging
+  // buffers at the very end, so the statistics cost no shared memory: with 2-4 KB of their own they pushed the operand ring
+  // just under a stage boundary (N=128: 3 -> 2 stages, N=256: 4 -> 3) and the fused forward ran 10-17 us per layer slower
+  // than the same-shape dgrad.
   constexpr int STAT_GROUPS = CONV_TC_BM / EPI_C;
+  constexpr int STAT_MAX_CHUNKS = 256 / EPI_C;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,8 +123,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     s_scale[i] = p.scale[i];
     s_shift[i] = p.shift[i];
   }
-  if (p.stats.acc)
-    for (int i = threadIdx.x; i < STAT_GROUPS * 2 * p.co; i += CONV_TC_THREADS) s_stat[i] = 0.0f;
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
@@ -295,6 +296,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aphase = 0;
     int sbuf = 0;
+    float st0[STAT_MAX_CHUNKS], st1[STAT_MAX_CHUNKS];      // this thread's (channel, row group) sums, per output chunk
+#pragma unroll
+    for (int q = 0; q < STAT_MAX_CHUNKS; ++q) { st0[q] = 0.0f; st1[q] = 0.0f; }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       ptx::mbar_wait(&tmem_full[as], aphase, p.diag, 0x400 + as);
       ptx::tcgen05_fence_after();
@@ -342,7 +346,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (p.stats.acc) {
           // column sums of the staged (already rounded) tile: thread = (channel, row group); rows past the end of the
-          // tensor (clipped by the TMA store) are skipped.  s_stat[group][.][channel] is owned by exactly one thread.
+          // tensor (clipped by the TMA store) are skipped.  The (chunk, channel, row group) sum is owned by exactly one thread.
           constexpr int GROUPS = CONV_TC_BM / EPI_C, ROWS = EPI_C;
           const int c = epi_tid % EPI_C, grp = epi_tid / EPI_C;
           const int rows_valid = min(CONV_TC_BM, p.M_total - tile * CONV_TC_BM);
@@ -356,9 +360,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             a0 += f;
             a1 = fmaf(f, f, a1);
           }
-          float* st = s_stat + (grp * 2) * p.co + ch * EPI_C + c;
-          st[0] += a0;
-          st[p.co] += a1;
+#pragma unroll
+          for (int q = 0; q < STAT_MAX_CHUNKS; ++q)
+            if (q == ch) { st0[q] += a0; st1[q] += a1; }     // predicated: keeps the array in registers
           (void)GROUPS;
         }
         sbuf ^= 1;
@@ -374,6 +378,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // CTA partial (row groups combined in fixed order) -> 64-bit fixed point -> integer atomicAdd (order-independent);
       // the last CTA to arrive converts, finalizes mean / inv_std / moving averages and clears the accumulators.
       constexpr int GROUPS = CONV_TC_BM / EPI_C;
+      // the staging buffers are free now (every TMA store has drained): [row group][2][co] floats <= 8 KB
+      float* s_stat = reinterpret_cast<float*>(stg);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      {
+        const int c = epi_tid % EPI_C, grp = epi_tid / EPI_C;
+#pragma unroll
+        for (int q = 0; q < STAT_MAX_CHUNKS; ++q)
+          if (q < n_chunks) {
+            s_stat[(grp * 2) * p.co + q * EPI_C + c] = st0[q];
+            s_stat[(grp * 2 + 1) * p.co + q * EPI_C + c] = st1[q];
+          }
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int i = epi_tid; i < 2 * p.co; i += 128) {
         const int which = i / p.co, c = i - which * p.co;
@@ -385,7 +401,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      uint32_t* s_flag = reinterpret_cast<uint32_t*>(s_stat);       // s_stat is dead now
+      uint32_t* s_flag = reinterpret_cast<uint32_t*>(s_stat);       // s_stat is dead now (the barrier above ordered its reads)
       if (epi_tid == 0) *s_flag = (atomicAdd(p.stats.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (*s_flag) {
@@ -560,8 +576,7 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   if (a.stats) p.stats = *a.stats; else memset(&p.stats, 0, sizeof(p.stats));
 
   const int kb_bytes = CONV_TC_BM * BLOCK_K * 2 + a.co * BLOCK_K * 2;
-  const int fixed = 2 * CONV_TC_BM * EPI_C * 2 + 2 * 256 * 4 + (2 * 8 + 4) * 8 + 16 +
-                    (a.stats ? (CONV_TC_BM / EPI_C) * 2 * a.co * 4 : 0);
+  const int fixed = 2 * CONV_TC_BM * EPI_C * 2 + 2 * 256 * 4 + (2 * 8 + 4) * 8 + 16;   // (statistics: registers, no smem)
   // Co <= 64: two CTAs per SM.  One CTA's two single-thread roles (TMA issue, MMA issue) need ~600 cycles per stage whatever
   // the layer, against 256 (N=64) / 512 (N=128) cycles of tensor work: a second resident CTA, with its own producers, issuer
   // and accumulators, fills the tensor pipe in the gaps.  Needs <= 128 registers (the EPI_C=32 instantiation: 106), half
