@@ -207,7 +207,8 @@ wgrad_simt_kernel(const TIn* __restrict__ in, int in_cstride, int in_coff, int c
 // bias row, which takes the scalar path.
 constexpr int RP_COLS = 32, RP_LANES = 8;
 __global__ void __launch_bounds__(RP_COLS * RP_LANES)
-reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S) {
+reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S, int64_t stride = 0) {
+  if (stride == 0) stride = n;                         // distance between two splits (> n: only the first n entries are wanted)
   __shared__ float4 s_acc[RP_LANES][RP_COLS];
   const int tx = threadIdx.x % RP_COLS, ty = threadIdx.x / RP_COLS;
   if ((n & 3) != 0) {                                  // tiny scalar case: one warp per column, fixed shuffle tree
@@ -215,7 +216,7 @@ reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, 
     const int64_t i = (int64_t)blockIdx.x * RP_LANES + (threadIdx.x >> 5);
     float a = 0.0f;
     if (i < n)
-      for (int k = lane; k < S; k += 32) a += part[(int64_t)k * n + i];
+      for (int k = lane; k < S; k += 32) a += part[(int64_t)k * stride + i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (i < n && lane == 0) out[i] = a;
@@ -226,7 +227,7 @@ reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, 
   if (i4 < n) {
 #pragma unroll 4
     for (int k = ty; k < S; k += RP_LANES) {
-      const float4 v = __ldcs(reinterpret_cast<const float4*>(part + (int64_t)k * n + i4));
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(part + (int64_t)k * stride + i4));
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
   }

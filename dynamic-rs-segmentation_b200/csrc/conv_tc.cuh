@@ -397,7 +397,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int g = 0; g < GROUPS; ++g) a += s_stat[(g * 2 + which) * p.co + c];
         const long long q = __double2ll_rn((double)a * p.stats.fx_scale);
-        atomicAdd(reinterpret_cast<unsigned long long*>(p.stats.acc) + i, static_cast<unsigned long long>(q));
+        atomicAdd(bn_acc_mine(p.stats) + i, static_cast<unsigned long long>(q));
       }
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -409,10 +409,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const double inv_scale = 1.0 / p.stats.fx_scale;
         const int C = p.co;
         for (int i = epi_tid; i < C; i += 128) {
-          const double a = (double)__ldcg(p.stats.acc + i) * inv_scale;
-          const double b = (double)__ldcg(p.stats.acc + C + i) * inv_scale;
-          p.stats.acc[i] = 0;
-          p.stats.acc[C + i] = 0;
+          const double a = (double)bn_acc_take(p.stats, i) * inv_scale;
+          const double b = (double)bn_acc_take(p.stats, C + i) * inv_scale;
           p.stats.sums[i] = (float)a;
           p.stats.sums[C + i] = (float)b;
           if (p.stats.mean) {

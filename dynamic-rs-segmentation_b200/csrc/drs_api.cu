@@ -209,7 +209,7 @@ struct HandleExtra {
   unsigned int* cm_dev = nullptr; // [K*K+1]
   unsigned int* count_dev = nullptr;
   unsigned int* bn_counter = nullptr;   // last-block-done counter of bn_partial_kernel (self-resetting)
-  long long* bn_acc = nullptr;          // [2*512] fixed-point accumulators of bn_partial_kernel (self-clearing)
+  long long* bn_acc = nullptr;          // [BN_ACC_REPLICAS][2*512] fixed-point accumulators of bn_partial_kernel (self-clearing)
   float* ones = nullptr;          // [512]
   float* zeros = nullptr;         // [512]
   float* cls_w_eval = nullptr;
@@ -317,8 +317,8 @@ extern "C" int drs_create(drs_handle_t* out, const drs_config* cfg) {
   CUDA_CHECK(cudaMalloc(&x->count_dev, 16));
   CUDA_CHECK(cudaMemset(x->count_dev, 0, 16));
   x->bn_counter = x->count_dev + 2;
-  CUDA_CHECK(cudaMalloc(&x->bn_acc, 2 * 512 * 8));
-  CUDA_CHECK(cudaMemset(x->bn_acc, 0, 2 * 512 * 8));
+  CUDA_CHECK(cudaMalloc(&x->bn_acc, (size_t)BN_ACC_REPLICAS * BN_ACC_STRIDE * 8));
+  CUDA_CHECK(cudaMemset(x->bn_acc, 0, (size_t)BN_ACC_REPLICAS * BN_ACC_STRIDE * 8));
   CUDA_CHECK(cudaMalloc(&x->ones, 512 * 4));
   CUDA_CHECK(cudaMalloc(&x->zeros, 512 * 4));
   CUDA_CHECK(cudaMemset(x->zeros, 0, 512 * 4));

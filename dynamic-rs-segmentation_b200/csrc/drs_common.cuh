@@ -236,6 +236,26 @@ struct BnFinish {
   int unbiased_ema;
 };
 
+// The fixed-point accumulators are replicated: a block adds into replica (blockIdx.x mod BN_ACC_REPLICAS) and the finishing
+// block sums the replicas (integers: still order-independent).  With one copy, a 1184-block launch put 600 k 64-bit atomics on
+// 4 KB of addresses -- a handful of L2 slices -- and the statistics tail cost more than the pass it was fused into.
+constexpr int BN_ACC_REPLICAS = 16;
+constexpr int BN_ACC_STRIDE = 1024;      // entries per replica: [2][512 channels]
+__device__ __forceinline__ unsigned long long* bn_acc_mine(const BnFinish& f) {
+  return reinterpret_cast<unsigned long long*>(f.acc) + (size_t)(blockIdx.x & (BN_ACC_REPLICAS - 1)) * BN_ACC_STRIDE;
+}
+// finishing block only: total of entry i over the replicas; clears them for the next launch
+__device__ __forceinline__ long long bn_acc_take(const BnFinish& f, int i) {
+  long long t = 0;
+#pragma unroll
+  for (int r = 0; r < BN_ACC_REPLICAS; ++r) {
+    long long* q = f.acc + (size_t)r * BN_ACC_STRIDE + i;
+    t += __ldcg(q);
+    *q = 0;
+  }
+  return t;
+}
+
 #define LAUNCH_CHECK(h)                 \
   do {                                  \
     (h)->launches++;                    \

@@ -37,6 +37,7 @@ static size_t train_workspace_bytes(Handle* h, int B, int crop, size_t es) {
   add(M * K * 4 * 2);                         // logits, dlogits
   add(M * 2);                                 // labels u8, pred
   add(M * 8 * es);                            // conv1 input padded to 8 channels (tensor-core conv1)
+  add(M * 128 * es);                          // conv1 im2col matrix (tensor-core filter gradient)
   const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * DRS_BN_MINBLK);   // one wave of resident blocks
   const int bn_rows = (int)ceil_div(M, nb_bn);
   add((size_t)nb_bn * 2 * 256 * 4);
@@ -149,6 +150,9 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   };
   const bool conv1_on_tc = ElemTag<TA>::v == ET_BF16 && !getenv("DRS_NO_CONV1_TC_TRAIN") &&
                            conv1_tc_supported(n.convs[0].k, n.convs[0].rate, n.convs[0].ci, n.convs[0].co);
+  // conv1's filter gradient on the tensor cores needs the (bf16) im2col matrix of the input: built next to the forward
+  const bool wgrad1_on_tc = conv1_on_tc && 25 * n.convs[0].ci <= 128 && wgrad_tc_supported(128, n.convs[0].co) && !getenv("DRS_NO_WGRAD_CONV1_TC");
+  TA* xcol = nullptr;
   for (int l = 0; l < L; ++l) {
     ConvLayer& c = n.convs[l];
     ActBuf zb{Z[l], c.co, 0};
@@ -173,6 +177,11 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
       a1.x8 = x8; a1.wpack = c.w_fprop; a1.out = Z[l]; a1.out_cstride = c.co; a1.out_coff = 0; a1.co = c.co;
       a1.B = B; a1.crop = crop; a1.scale = x->ones; a1.shift = h->params + c.b_off; a1.act = ACT_NONE; a1.etype = ElemTag<TA>::v;
       launch_conv1_tc(h, a1);
+      if (wgrad1_on_tc) {
+        xcol = (TA*)arena_take(h, (size_t)M * 128 * sizeof(TA));
+        im2col_conv1_kernel<TA><<<nblk(M * 16, 256), 256, 0, h->stream>>>(x8, xcol, c.ci, crop, M);
+        LAUNCH_CHECK(h);
+      }
     } else if (l == 0) {
       launch_conv_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, h->params + c.w_off, Z[l], c.co, 0, c.co, B, crop, c.k,
                                   c.rate, c.pad_b, x->ones, h->params + c.b_off, ACT_NONE);
@@ -346,7 +355,15 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     if (overlap) h->stream = x->side_stream;
     try {
       if (overlap) CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->ev_dz[l & 1], 0));
-      if (l == 0) {
+      if (l == 0 && xcol) {
+        WgradTcArgs wa;
+        wa.x = xcol; wa.in_cstride = 128; wa.in_coff = 0; wa.ci = 128;
+        wa.dy = DZ; wa.dy_cstride = c.co; wa.dy_coff = 0; wa.co = c.co;
+        wa.B = B; wa.crop = crop; wa.k = 1; wa.rate = 1; wa.pad_b = 0;
+        wa.dw = h->grads + c.w_off; wa.part = part_w; wa.part_capacity = max_w * max_splits;
+        wa.out_rows = c.k * c.k * c.ci;
+        launch_wgrad_tc(h, wa);
+      } else if (l == 0) {
         // conv1: K = 25*C <= 125 rows only -> parallelism must come from many short pixel splits
         // (fp32 mode keeps the generic kernel: its summation order is what the fp32 parity tests pin)
         const bool fast1 = ElemTag<TA>::v != ET_F32 && !getenv("DRS_NO_WGRAD_CONV1") &&

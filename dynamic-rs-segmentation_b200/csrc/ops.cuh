@@ -482,7 +482,7 @@ maxpool3_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dout, int do_cs, int 
     float a = 0.0f;
     for (int t = t0; t < 256; t += cv) a += s_red[which * 8 + e][t];
     const long long q = __double2ll_rn((double)a * fin.fx_scale);
-    atomicAdd(reinterpret_cast<unsigned long long*>(fin.acc) + which * C + g * 8 + e, static_cast<unsigned long long>(q));
+    atomicAdd(bn_acc_mine(fin) + which * C + g * 8 + e, static_cast<unsigned long long>(q));
   }
   __shared__ bool s_last;
   __threadfence();
@@ -493,11 +493,17 @@ maxpool3_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dout, int do_cs, int 
   __threadfence();
   const double inv_scale = 1.0 / fin.fx_scale;
   for (int i = threadIdx.x; i < 2 * C; i += 256) {
-    const double a = (double)__ldcg(fin.acc + i) * inv_scale;
-    fin.acc[i] = 0;
+    const double a = (double)bn_acc_take(fin, i) * inv_scale;
     fin.sums[i] = (float)a;
   }
   if (threadIdx.x == 0) *fin.counter = 0u;
+}
+
+#include "pool_train.cuh"
+
+static bool pool_lean_enabled() {
+  static const bool on = !getenv("DRS_POOL_OLD");
+  return on;
 }
 
 template <typename T>
@@ -509,7 +515,10 @@ static void launch_maxpool3_fwd(Handle* h, const T* in, int in_cs, int in_co, T*
   nseg = (int)ceil_div(crop, seg);
   const int64_t total = base * nseg;
   const unsigned nb = (unsigned)ceil_div(total, 256);
-  if (idx && ElemTag<T>::v == ET_BF16 && !getenv("DRS_NO_POOL_PIPELINE"))
+  if (idx && ElemTag<T>::v == ET_BF16 && bn_mean && pool_lean_enabled()) {
+    auto k = act == ACT_RELU ? pool_lean::fwd_kernel<ACT_RELU> : act == ACT_LRELU ? pool_lean::fwd_kernel<ACT_LRELU> : pool_lean::fwd_kernel<ACT_NONE>;
+    k<<<nb, 256, 0, h->stream>>>((const __nv_bfloat16*)in, in_cs, in_co, (__nv_bfloat16*)out, out_cs, out_co, idx, C, B, crop, seg, nseg, bn_mean, bn_inv_std);
+  } else if (idx && ElemTag<T>::v == ET_BF16 && !getenv("DRS_NO_POOL_PIPELINE"))
     maxpool3_fwd_train_bf16_pipelined_kernel<<<nb, 256, 0, h->stream>>>((const __nv_bfloat16*)in, in_cs, in_co, (__nv_bfloat16*)out, out_cs, out_co, idx, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
   else if (idx && ElemTag<T>::v == ET_BF16)
     maxpool3_fwd_train_bf16_kernel<<<nb, 256, 0, h->stream>>>((const __nv_bfloat16*)in, in_cs, in_co, (__nv_bfloat16*)out, out_cs, out_co, idx, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
@@ -570,7 +579,18 @@ static void launch_maxpool3_bwd(Handle* h, const T* dout, int do_cs, int do_co, 
     int nseg = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div((int64_t)h->sm_count * 2048, base)), std::max(1, crop / 4));
     const int seg = (int)ceil_div(crop, nseg);
     nseg = (int)ceil_div(crop, seg);
-    if (stats)
+    const unsigned nb = (unsigned)ceil_div(base * nseg, 256);
+    if (pool_lean_enabled()) {
+      if (stats) {
+        auto k = stats_act == ACT_RELU ? pool_lean::bwd_kernel<ACT_RELU, true>
+                 : stats_act == ACT_LRELU ? pool_lean::bwd_kernel<ACT_LRELU, true> : pool_lean::bwd_kernel<ACT_NONE, true>;
+        k<<<nb, 256, 0, h->stream>>>((const __nv_bfloat16*)dout, do_cs, do_co, idx, (__nv_bfloat16*)din, di_cs, di_co, C, B, crop, seg, nseg,
+                                     (const __nv_bfloat16*)stats_z, stats_mean, stats_inv_std, *stats);
+      } else {
+        pool_lean::bwd_kernel<ACT_NONE, false><<<nb, 256, 0, h->stream>>>((const __nv_bfloat16*)dout, do_cs, do_co, idx, (__nv_bfloat16*)din, di_cs,
+                                                                           di_co, C, B, crop, seg, nseg, nullptr, nullptr, nullptr, BnFinish{});
+      }
+    } else if (stats)
       maxpool3_bwd_bf16_kernel<true><<<(unsigned)ceil_div(base * nseg, 256), 256, 0, h->stream>>>(
           (const __nv_bfloat16*)dout, do_cs, do_co, idx, (__nv_bfloat16*)din, di_cs, di_co, C, B, crop, seg, nseg,
           (const __nv_bfloat16*)stats_z, stats_mean, stats_inv_std, stats_act, *stats);
@@ -671,7 +691,7 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
     float a = 0.0f;
     for (int r = 0; r < lanes_r; ++r) a += s_red[which * 8 + e][r * cv + g];
     const long long q = __double2ll_rn((double)a * fin.fx_scale);
-    atomicAdd(reinterpret_cast<unsigned long long*>(fin.acc) + which * C + g * 8 + e, static_cast<unsigned long long>(q));
+    atomicAdd(bn_acc_mine(fin) + which * C + g * 8 + e, static_cast<unsigned long long>(q));
   }
   // ---- the last block to finish converts the sums, finalizes and clears the accumulators for the next launch
   __shared__ bool s_last;
@@ -683,10 +703,8 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
   __threadfence();
   const double inv_scale = 1.0 / fin.fx_scale;
   for (int i = threadIdx.x; i < C; i += BN_THREADS) {
-    const double a = (double)__ldcg(fin.acc + i) * inv_scale;
-    const double b = (double)__ldcg(fin.acc + C + i) * inv_scale;
-    fin.acc[i] = 0;
-    fin.acc[C + i] = 0;
+    const double a = (double)bn_acc_take(fin, i) * inv_scale;
+    const double b = (double)bn_acc_take(fin, C + i) * inv_scale;
     fin.sums[i] = (float)a;
     fin.sums[C + i] = (float)b;
     if (fin.mean) {

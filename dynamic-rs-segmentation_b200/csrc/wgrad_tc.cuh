@@ -233,7 +233,37 @@ struct WgradTcArgs {
   float* dw;            // [k*k*ci][co] fp32 (HWIO)
   float* part;          // workspace for split partials
   size_t part_capacity; // floats
+  int out_rows = 0;     // > 0: only the first out_rows rows of dW are wanted (conv1 through its materialised im2col)
 };
+
+// conv1 (5x5, Ci <= 5 image channels): its 25*Ci <= 125 reduction rows are far too few for the kernel above as a 25-tap
+// layer (Ci must be a multiple of 64), and the CUDA-core kernel that served it (wgrad_conv1_kernel, 72 + 15 us at batch 64,
+// crop 37) sat at the very end of the backward where nothing overlaps it.  Instead the im2col matrix is materialised once
+// per step -- xcol[m][tap*Ci + c], 128 bf16 per pixel, zero padded -- and the filter gradient is the 1x1 "layer" Ci = 128
+// of the tensor-core kernel: dW[0 .. 25*Ci) = xcol^T dZ.
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_conv1_kernel(const T* __restrict__ x8, T* __restrict__ xcol, int ci, int crop, int64_t M) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= M * 16) return;
+  const int64_t m = gid >> 4;
+  const int g = (int)(gid & 15);
+  const int cc = crop * crop;
+  const int r = (int)(m % cc);
+  const int y = r / crop, x = r - y * crop;
+  alignas(16) T v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = g * 8 + e;
+    const int tap = k / ci, c = k - tap * ci;
+    const int ky = tap / 5, kx = tap - ky * 5;
+    const int yy = y + ky - 2, xx = x + kx - 2;
+    T val = from_f32<T>(0.0f);
+    if (tap < 25 && yy >= 0 && yy < crop && xx >= 0 && xx < crop) val = x8[(m + (int64_t)(ky - 2) * crop + (kx - 2)) * 8 + c];
+    v[e] = val;
+  }
+  *reinterpret_cast<uint4*>(xcol + m * 128 + g * 8) = *reinterpret_cast<const uint4*>(v);
+}
 
 static inline bool wgrad_tc_supported(int ci, int co) { return ci % 64 == 0 && co % 64 == 0 && co >= 64 && co <= 256; }
 
@@ -293,7 +323,7 @@ static void launch_wgrad_tc(Handle* h, const WgradTcArgs& a) {
   const int grid = std::min(n_items, h->sm_count);
   wgrad_tc_kernel<<<grid, CONV_TC_THREADS, smem_bytes, h->stream>>>(tmX, tmDY, p);
   LAUNCH_CHECK(h);
-  const int64_t n = (int64_t)Ktot * a.co;
-  reduce_partials_kernel<<<reduce_partials_grid(n), RP_COLS * RP_LANES, 0, h->stream>>>(a.part, a.dw, n, splits);
+  const int64_t n = (int64_t)(a.out_rows > 0 ? a.out_rows : Ktot) * a.co;
+  reduce_partials_kernel<<<reduce_partials_grid(n), RP_COLS * RP_LANES, 0, h->stream>>>(a.part, a.dw, n, splits, (int64_t)Ktot * a.co);
   LAUNCH_CHECK(h);
 }
