@@ -31,6 +31,7 @@ struct Conv1TcParams {
 // W HWIO [5,5,ci,co] fp32 -> core-matrix order: out[((kc*(co/8) + n/8)*8 + n%8)*8 + c] = (kc < 25 && c < ci) ? W[kc][c][n] : 0
 template <typename T>
 __global__ void pack_conv1_kernel(const float* __restrict__ w, T* __restrict__ out, int ci, int co) {
+  pdl_sync();
   const int n_total = C1_SLOTS * co * 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_total) return;
@@ -46,6 +47,7 @@ __global__ void pack_conv1_kernel(const float* __restrict__ w, T* __restrict__ o
 // x [M][C] fp32 -> [M][8] 16-bit, zero padded
 template <typename T>
 __global__ void pad_cast8_kernel(const float* __restrict__ x, T* __restrict__ out, int C, int64_t M) {
+  pdl_sync();
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   alignas(16) T v[8];
@@ -81,6 +83,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_sync();      // the packed weights below are written by the kernel right in front of this one
   // weights (core-matrix order) and the zero slot of every stage: generic-proxy writes, fenced for the async proxy
   for (int i = threadIdx.x; i < b_bytes / 16; i += CONV_TC_THREADS)
     reinterpret_cast<uint4*>(s_b)[i] = reinterpret_cast<const uint4*>(p.wpack)[i];

@@ -208,6 +208,7 @@ wgrad_simt_kernel(const TIn* __restrict__ in, int in_cstride, int in_coff, int c
 constexpr int RP_COLS = 32, RP_LANES = 8;
 __global__ void __launch_bounds__(RP_COLS * RP_LANES)
 reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S, int64_t stride = 0) {
+  pdl_sync();
   if (stride == 0) stride = n;                         // distance between two splits (> n: only the first n entries are wanted)
   __shared__ float4 s_acc[RP_LANES][RP_COLS];
   const int tx = threadIdx.x % RP_COLS, ty = threadIdx.x / RP_COLS;

@@ -119,10 +119,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb_per_tap = p.ci / BLOCK_K;
   const int num_kb = taps * kb_per_tap;
 
-  for (int i = threadIdx.x; i < p.co; i += CONV_TC_THREADS) {
-    s_scale[i] = p.scale[i];
-    s_shift[i] = p.shift[i];
-  }
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
@@ -142,6 +138,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) {
     ptx::tmem_alloc(tmem_holder, static_cast<uint32_t>(p.tmem_cols));
     ptx::tmem_relinquish();
+  }
+  // everything above is private to the CTA; from here on global memory written by the previous kernel is read
+  pdl_sync();
+  for (int i = threadIdx.x; i < p.co; i += CONV_TC_THREADS) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
   }
   ptx::tcgen05_fence_before();
   __syncthreads();
@@ -615,7 +617,7 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
       CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_set = true;
     }
-    kern<<<grid, CONV_TC_THREADS, smem_bytes, h->stream>>>(tmA, tmB, tmC, p);
+    launch_pdl(h, kern, dim3(grid), dim3(CONV_TC_THREADS), (size_t)smem_bytes, tmA, tmB, tmC, p);
   }
   LAUNCH_CHECK(h);
 }

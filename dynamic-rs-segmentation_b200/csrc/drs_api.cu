@@ -591,6 +591,7 @@ struct RepackTable {
   long long total;
 };
 __global__ void repack_kernel(const __grid_constant__ RepackTable t) {
+  pdl_sync();
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= t.total) return;
   int si = 0;

@@ -111,6 +111,7 @@ extern "C" int drs_comm_destroy(drs_handle_t h) {
 // sum `count` floats over ranks in place, in the order of `on_stream` (default: the handle's stream)
 static void do_allreduce(Handle* h, float* buf, int64_t count, cudaStream_t on_stream = (cudaStream_t)(uintptr_t)1) {
   if (h->world <= 1) return;
+  h->pdl_prev = false;
   HandleExtra* x = X(h);
   const cudaStream_t st = on_stream == (cudaStream_t)(uintptr_t)1 ? h->stream : on_stream;
   if (x->nccl) {

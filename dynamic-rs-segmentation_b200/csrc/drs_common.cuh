@@ -134,6 +134,9 @@ struct drs_handle_s {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
+  // Programmatic dependent launch (training step, main stream): pdl_on = the step allows it, pdl_prev = the last operation
+  // enqueued on `stream` was one of our kernels (anything else -- memset, copy, collective, stream switch -- clears it)
+  bool pdl_on = false, pdl_prev = false;
 
   // variables
   float* params = nullptr;   // flat trainables: all weights & biases
@@ -256,9 +259,40 @@ __device__ __forceinline__ long long bn_acc_take(const BnFinish& f, int i) {
   return t;
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------------
+// A kernel launched through launch_pdl may be made resident while the previous kernel of the stream is still draining: its
+// blocks run up to pdl_wait() and stop there until that kernel has completed and its writes are visible.  Every kernel
+// launched this way executes pdl_wait() before its first global access (without a programmatic dependency the instruction
+// returns at once), so completion stays transitive along the stream; pdl_trigger() right behind it allows the launch of the
+// next kernel as soon as every block of this one has started.  Measured on the training step: the 1.2-3 us between two
+// consecutive kernels of the graph shrink to ~0.5 us.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+
+static bool pdl_env() {
+  static const bool on = !getenv("DRS_NO_PDL");
+  return on;
+}
+template <typename... P, typename... A>
+static void launch_pdl(drs_handle_s* h, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (h->pdl_on && h->pdl_prev && pdl_env()) ? 1 : 0;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...));
+}
+
 #define LAUNCH_CHECK(h)                 \
   do {                                  \
     (h)->launches++;                    \
+    (h)->pdl_prev = true;               \
     CUDA_CHECK(cudaGetLastError());     \
   } while (0)
 

@@ -12,7 +12,7 @@ __global__ void unpack_extras_kernel(const float* __restrict__ src, float* __res
   if (i == 0) loss[0] = src[0];
   if (i < ncm) cm[i] = (unsigned int)(src[1 + i] + 0.5f);
 }
-__global__ void add2_kernel(const float* __restrict__ a, float* __restrict__ out) { out[2] = a[0] + a[1]; }
+__global__ void add2_kernel(const float* __restrict__ a, float* __restrict__ out) { pdl_sync(); out[2] = a[0] + a[1]; }
 
 static size_t train_workspace_bytes(Handle* h, int B, int crop, size_t es) {
   NetDesc& n = h->net;
@@ -133,6 +133,9 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   debug_keep_reset(h);
 
   CUDA_CHECK(cudaMemsetAsync(h->grads, 0, (n.n_trainable + 1024) * 4, h->stream));
+  h->pdl_on = true;                    // (cleared at the end of the step; see PdlScope)
+  h->pdl_prev = false;
+  struct PdlScope { Handle* h; ~PdlScope() { h->pdl_on = false; h->pdl_prev = false; } } pdl_scope{h};
   const double bn_count = (double)M * (h->sync_bn ? h->world : 1);
 
   // ---------------------------------------------------------------- forward (train-mode BN)
@@ -168,10 +171,10 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
       // conv1 on the tensor cores as in inference (conv1_tc.cuh): input and filter rounded to bf16 like every other layer's
       // operands; the filter is re-packed every step (13 K elements).  The filter gradient keeps the fp32 input.
       if (!c.w_fprop) CUDA_CHECK(cudaMalloc(&c.w_fprop, (size_t)C1_SLOTS * c.co * 8 * 2));
-      pack_conv1_kernel<TA><<<nblk(C1_SLOTS * c.co * 8, 256), 256, 0, h->stream>>>(h->params + c.w_off, (TA*)c.w_fprop, c.ci, c.co);
+      launch_pdl(h, pack_conv1_kernel<TA>, dim3(nblk(C1_SLOTS * c.co * 8, 256)), dim3(256), 0, h->params + c.w_off, (TA*)c.w_fprop, c.ci, c.co);
       LAUNCH_CHECK(h);
       TA* x8 = (TA*)arena_take(h, (size_t)M * 8 * sizeof(TA));
-      pad_cast8_kernel<TA><<<nblk(M, 256), 256, 0, h->stream>>>(x_dev, x8, c.ci, M);
+      launch_pdl(h, pad_cast8_kernel<TA>, dim3(nblk(M, 256)), dim3(256), 0, x_dev, x8, c.ci, M);
       LAUNCH_CHECK(h);
       Conv1TcArgs a1;
       a1.x8 = x8; a1.wpack = c.w_fprop; a1.out = Z[l]; a1.out_cstride = c.co; a1.out_coff = 0; a1.co = c.co;
@@ -179,7 +182,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
       launch_conv1_tc(h, a1);
       if (wgrad1_on_tc) {
         xcol = (TA*)arena_take(h, (size_t)M * 128 * sizeof(TA));
-        im2col_conv1_kernel<TA><<<nblk(M * 16, 256), 256, 0, h->stream>>>(x8, xcol, c.ci, crop, M);
+        launch_pdl(h, im2col_conv1_kernel<TA>, dim3(nblk(M * 16, 256)), dim3(256), 0, x8, xcol, c.ci, crop, M);
         LAUNCH_CHECK(h);
       }
     } else if (l == 0) {
@@ -190,12 +193,12 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
                    h->params + c.b_off, ACT_NONE, fused_stats ? &fin : nullptr);
     }
     if (!fused_stats) {
-      bn_partial_kernel<TA, TA, 0><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, nullptr, 0, 0, nullptr, nullptr, 0, part_bn, c.co, M, bn_rows, fin);
+      launch_pdl(h, bn_partial_kernel<TA, TA, 0>, dim3(nb_bn), dim3(BN_THREADS), 0, Z[l], c.co, 0, nullptr, 0, 0, nullptr, nullptr, 0, part_bn, c.co, M, bn_rows, fin);
       LAUNCH_CHECK(h);
     }
     if (h->sync_bn) {
       do_allreduce(h, x->sums, 2 * c.co);
-      bn_finalize_kernel<<<nblk(c.co, 128), 128, 0, h->stream>>>(x->sums, mean, istd, h->bnstat + c.mm_off, h->bnstat + c.mv_off, c.co,
+      launch_pdl(h, bn_finalize_kernel, dim3(nblk(c.co, 128)), dim3(128), 0, x->sums, mean, istd, h->bnstat + c.mm_off, h->bnstat + c.mv_off, c.co,
                                                                   bn_count, h->cfg.bn_eps, h->cfg.bn_decay, h->cfg.bn_unbiased_ema);
       LAUNCH_CHECK(h);
     }
@@ -205,7 +208,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     } else {
       ActBuf ab = output_of(l);
       ActBuf act_out = c.post ? ActBuf{Apre[l], c.co, 0} : ab;        // a post-op keeps the activation in front of it
-      bn_apply_kernel<TA><<<bne_grid(M, h->sm_count), BNE_THREADS, 0, h->stream>>>(Z[l], c.co, 0, mean, istd, n.act, (TA*)act_out.p, act_out.cs, act_out.co, c.co, M);
+      launch_pdl(h, bn_apply_kernel<TA>, dim3(bne_grid(M, h->sm_count)), dim3(BNE_THREADS), 0, Z[l], c.co, 0, mean, istd, n.act, (TA*)act_out.p, act_out.cs, act_out.co, c.co, M);
       LAUNCH_CHECK(h);
       if (c.post == 1) {
         launch_avgpool_fwd<TA>(h, Apre[l], c.co, 0, (TA*)ab.p, ab.cs, ab.co, c.co, B, crop, c.post_k);
@@ -236,22 +239,24 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   // the number of pixels in the mean stays on the device (x->loss_dev[3]); contest's mask count needs no host round trip
   if (mask_dev || h->ignore_label >= 0) {
     CUDA_CHECK(cudaMemsetAsync(x->count_dev, 0, 4, h->stream));
-    mask_count_kernel<<<(unsigned)std::min<int64_t>(ceil_div(M, 256), 1024), 256, 0, h->stream>>>(mask_dev, y_dev, h->ignore_label, M, x->count_dev);
+    h->pdl_prev = false;
+    launch_pdl(h, mask_count_kernel, dim3((unsigned)std::min<int64_t>(ceil_div(M, 256), 1024)), dim3(256), 0, mask_dev, y_dev, h->ignore_label, M, x->count_dev);
     LAUNCH_CHECK(h);
-    set_count_kernel<<<1, 1, 0, h->stream>>>(x->loss_dev + 3, x->count_dev, 0.0f);
+    launch_pdl(h, set_count_kernel, dim3(1), dim3(1), 0, x->loss_dev + 3, x->count_dev, 0.0f);
     LAUNCH_CHECK(h);
     if (h->world > 1) do_allreduce(h, x->loss_dev + 3, 1);
   } else {
-    set_count_kernel<<<1, 1, 0, h->stream>>>(x->loss_dev + 3, nullptr, (float)((double)M * h->world));
+    launch_pdl(h, set_count_kernel, dim3(1), dim3(1), 0, x->loss_dev + 3, nullptr, (float)((double)M * h->world));
     LAUNCH_CHECK(h);
   }
-  ce_fwd_bwd_kernel<<<nb_ce, CE_THREADS, 0, h->stream>>>(logits, y_dev, mask_dev, K, M, x->loss_dev + 3, dlogits, part_ce, labels_u8, h->ignore_label);
+  launch_pdl(h, ce_fwd_bwd_kernel, dim3(nb_ce), dim3(CE_THREADS), 0, logits, y_dev, mask_dev, K, M, x->loss_dev + 3, dlogits, part_ce, labels_u8, h->ignore_label);
   LAUNCH_CHECK(h);
-  sum_fixed_kernel<<<1, 256, 0, h->stream>>>(part_ce, nb_ce, x->loss_dev, 1.0f, x->loss_dev + 3);
+  launch_pdl(h, sum_fixed_kernel, dim3(1), dim3(256), 0, part_ce, nb_ce, x->loss_dev, 1.0f, x->loss_dev + 3);
   LAUNCH_CHECK(h);
   // fused calc_accuracy_by_crop (isprs:510-531)
   CUDA_CHECK(cudaMemsetAsync(x->cm_dev, 0, (K * K + 1) * 4, h->stream));
-  confusion_kernel<<<(unsigned)std::min<int64_t>(ceil_div(M, 256), (int64_t)h->sm_count * 4), 256, 0, h->stream>>>(labels_u8, pred, acc_mask_dev ? acc_mask_dev : mask_dev, M, K, h->ignore_label, x->cm_dev);
+  h->pdl_prev = false;
+  launch_pdl(h, confusion_kernel, dim3((unsigned)std::min<int64_t>(ceil_div(M, 256), (int64_t)h->sm_count * 4)), dim3(256), 0, labels_u8, pred, acc_mask_dev ? acc_mask_dev : mask_dev, M, K, h->ignore_label, x->cm_dev);
   LAUNCH_CHECK(h);
 
   // ---------------------------------------------------------------- backward
@@ -261,12 +266,12 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   // earlier layers runs; only the small front part of the buffer is exchanged at the end.
   const int l_split = (h->world > 1 && !h->time_convs && !getenv("DRS_NO_BUCKETS") && L >= 4) ? L - 3 : -1;
   // classifier: dW, db, dX
-  classifier_bwd_weight_kernel<TA><<<nb_cls, CLSW_THREADS, 0, h->stream>>>((const TA*)feat.p, feat.cs, feat.co, n.cls_in, dlogits, K, part_cls,
+  launch_pdl(h, classifier_bwd_weight_kernel<TA>, dim3(nb_cls), dim3(CLSW_THREADS), 0, (const TA*)feat.p, feat.cs, feat.co, n.cls_in, dlogits, K, part_cls,
                                                                            part_clsb, M, cls_rows);
   LAUNCH_CHECK(h);
-  reduce_partials_kernel<<<reduce_partials_grid((int64_t)n.cls_in * K), RP_COLS * RP_LANES, 0, h->stream>>>(part_cls, h->grads + n.cls_w_off, (int64_t)n.cls_in * K, nb_cls);
+  launch_pdl(h, reduce_partials_kernel, dim3(reduce_partials_grid((int64_t)n.cls_in * K)), dim3(RP_COLS * RP_LANES), 0, part_cls, h->grads + n.cls_w_off, (int64_t)n.cls_in * K, nb_cls, (int64_t)0);
   LAUNCH_CHECK(h);
-  reduce_partials_kernel<<<reduce_partials_grid(K), RP_COLS * RP_LANES, 0, h->stream>>>(part_clsb, h->grads + n.cls_b_off, K, nb_cls);
+  launch_pdl(h, reduce_partials_kernel, dim3(reduce_partials_grid(K)), dim3(RP_COLS * RP_LANES), 0, part_clsb, h->grads + n.cls_b_off, K, nb_cls, (int64_t)0);
   LAUNCH_CHECK(h);
   if (l_split >= 0) {
     pack_extras_kernel<<<1, 128, 0, h->stream>>>(h->grads + n.n_trainable, x->loss_dev, x->cm_dev, K * K + 1);
@@ -283,7 +288,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     if (cvc <= 256 && 256 % cvc == 0 && ElemTag<TA>::v != ET_F32 && !getenv("DRS_NO_CLS_REG")) {
       const int rows = 256 / cvc;
       int blocks = (int)std::min<int64_t>(ceil_div(M, 2 * rows), (int64_t)h->sm_count * 8);
-      classifier_bwd_data_reg_kernel<TA><<<blocks, 256, 0, h->stream>>>(dlogits, h->params + n.cls_w_off, K, Gcur, gcs0, 0, n.cls_in, M);
+      launch_pdl(h, classifier_bwd_data_reg_kernel<TA>, dim3(blocks), dim3(256), 0, dlogits, h->params + n.cls_w_off, K, Gcur, gcs0, 0, n.cls_in, M);
     } else {
       int blocks = (int)std::min<int64_t>(ceil_div(M * (n.cls_in / 8), 256), (int64_t)h->sm_count * 16);
       classifier_bwd_data_kernel<TA><<<blocks, 256, n.cls_in * K * 4, h->stream>>>(dlogits, h->params + n.cls_w_off, K, Gcur, gcs0, 0, n.cls_in, M);
@@ -324,7 +329,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
                                                 1.0f / (float)(crop * crop), q.ds, q.part);
       LAUNCH_CHECK(h);
       const int64_t np = (int64_t)2 * sb.c * sb.r + sb.r + sb.c;       // W1, b1, W2, b2 are contiguous in the flat buffer
-      reduce_partials_kernel<<<reduce_partials_grid(np), RP_COLS * RP_LANES, 0, h->stream>>>(q.part, h->grads + sb.w1_off, np, B);
+      launch_pdl(h, reduce_partials_kernel, dim3(reduce_partials_grid(np)), dim3(RP_COLS * RP_LANES), 0, q.part, h->grads + sb.w1_off, np, B, (int64_t)0);
       LAUNCH_CHECK(h);
       se_scale_bwd_kernel<TA><<<nblk(M * (c.co / 8), 256), 256, 0, h->stream>>>((const TA*)dOut.p, dOut.cs, dOut.co, q.e, q.ds, T, c.co, 0, c.co, M,
                                                                               crop * crop);
@@ -332,7 +337,8 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
       dA = ActBuf{T, c.co, 0};
     }
     if (!fused_bwd_stats) {
-      bn_partial_kernel<TA, TA, 1><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, n.act, part_bn, c.co, M, bn_rows, finb);
+      launch_pdl(h, bn_partial_kernel<TA, TA, 1>, dim3(nb_bn), dim3(BN_THREADS), 0, (const TA*)Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co,
+                 (const float*)mean, (const float*)istd, n.act, part_bn, c.co, M, bn_rows, finb);
       LAUNCH_CHECK(h);
     }
     if (h->sync_bn) do_allreduce(h, x->sums, 2 * c.co);
@@ -340,9 +346,12 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     // overlaps the HBM-bound kernels of layer l-1's backward.  dZ is double-buffered; before a buffer is rewritten the
     // main stream waits for the wgrad that read it two layers ago.
     TA* DZ = DZb[l & 1];
-    if (l + 2 <= L - 1) CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->ev_wgrad[l & 1], 0));
-    bn_bwd_apply_kernel<TA, TA><<<bne_grid(M, h->sm_count), BNE_THREADS, 0, h->stream>>>(Z[l], c.co, 0, (const TA*)dA.p, dA.cs, dA.co, mean, istd, x->sums,
-                                                                                   1.0 / bn_count, n.act, DZ, c.co, 0, c.co, M);
+    if (l + 2 <= L - 1) {
+      CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->ev_wgrad[l & 1], 0));
+      if (!getenv("DRS_PDL_ACROSS_EVENTS")) h->pdl_prev = false;       // the next kernel also depends on another stream
+    }
+    launch_pdl(h, bn_bwd_apply_kernel<TA, TA>, dim3(bne_grid(M, h->sm_count)), dim3(BNE_THREADS), 0, (const TA*)Z[l], c.co, 0, (const TA*)dA.p, dA.cs,
+               dA.co, (const float*)mean, (const float*)istd, (const float*)x->sums, 1.0 / bn_count, n.act, DZ, c.co, 0, c.co, M);
     LAUNCH_CHECK(h);
     debug_keep<TA>(h, "da:" + c.scope, (const TA*)dA.p, dA.cs, dA.co, c.co, M);
     debug_keep<TA>(h, "dz:" + c.scope, DZ, c.co, 0, c.co, M);
@@ -352,7 +361,8 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     cudaStream_t main_stream = h->stream;
     // (per-launch kernel timing with events needs the launches serialised: no overlap while profiling)
     const bool overlap = !h->time_convs && !getenv("DRS_NO_OVERLAP");
-    if (overlap) h->stream = x->side_stream;
+    const bool pdl_main = h->pdl_prev;
+    if (overlap) { h->stream = x->side_stream; h->pdl_prev = false; }
     try {
       if (overlap) CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->ev_dz[l & 1], 0));
       if (l == 0 && xcol) {
@@ -397,13 +407,14 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
       }
     } catch (...) { h->stream = main_stream; throw; }
     h->stream = main_stream;
+    h->pdl_prev = overlap ? pdl_main : false;
     // dgrad: dilated conv of dZ with flipped taps, padding swapped
     if (l > 0) {
       ActBuf dzb{DZ, c.co, 0};
       if (n.dense) {
         ActBuf tmp{G0, c.ci, 0};
         run_conv<TA>(h, dzb, c.co, (const float*)c.w_dgrad, c.w_dgrad, tmp, c.ci, B, crop, c.k, c.rate, c.pad_a, x->ones, x->zeros, ACT_NONE);
-        add_slice_kernel<TA><<<nblk(M * (c.ci / 8), 256), 256, 0, h->stream>>>(GF, n.feat_stride, 0, G0, c.ci, 0, c.ci, M);
+        launch_pdl(h, add_slice_kernel<TA>, dim3(nblk(M * (c.ci / 8), 256)), dim3(256), 0, GF, n.feat_stride, 0, G0, c.ci, 0, c.ci, M);
         LAUNCH_CHECK(h);
       } else if (n.squeeze) {
         // gradient of the input buffer (led by layer `ig`): the first consumer processed writes it, the second adds
@@ -415,7 +426,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
         } else {
           ActBuf tmp{G0, c.ci, 0};
           run_conv<TA>(h, dzb, c.co, (const float*)c.w_dgrad, c.w_dgrad, tmp, c.ci, B, crop, c.k, c.rate, c.pad_a, x->ones, x->zeros, ACT_NONE);
-          add_slice_kernel<TA><<<nblk(M * (c.ci / 8), 256), 256, 0, h->stream>>>(Gg[ig], c.ci, 0, G0, c.ci, 0, c.ci, M);
+          launch_pdl(h, add_slice_kernel<TA>, dim3(nblk(M * (c.ci / 8), 256)), dim3(256), 0, Gg[ig], c.ci, 0, G0, c.ci, 0, c.ci, M);
           LAUNCH_CHECK(h);
         }
       } else {
@@ -431,6 +442,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   // two most recent events cover all layers)
   CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->ev_wgrad[0], 0));
   if (L > 1) CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->ev_wgrad[1], 0));
+  h->pdl_prev = false;
 
   // ---------------------------------------------------------------- exchange + update
   if (h->world > 1) {
@@ -446,12 +458,12 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     LAUNCH_CHECK(h);
   }
   const float lr = h->cfg.lr_initial * powf(h->cfg.decay_rate, (float)(h->global_step / (h->cfg.decay_steps > 0 ? h->cfg.decay_steps : 1)));
-  momentum_update_kernel<<<nb_opt, 256, 0, h->stream>>>(h->params, h->grads, h->moms, n.n_trainable, x->is_weight, h->cfg.weight_decay, lr,
+  launch_pdl(h, momentum_update_kernel, dim3(nb_opt), dim3(256), 0, h->params, h->grads, h->moms, n.n_trainable, x->is_weight, h->cfg.weight_decay, lr,
                                                         h->cfg.momentum, 1.0f, part_l2);
   LAUNCH_CHECK(h);
-  sum_fixed_kernel<<<1, 256, 0, h->stream>>>(part_l2, nb_opt, x->loss_dev + 1, 0.5f * h->cfg.weight_decay, nullptr);
+  launch_pdl(h, sum_fixed_kernel, dim3(1), dim3(256), 0, part_l2, nb_opt, x->loss_dev + 1, 0.5f * h->cfg.weight_decay, nullptr);
   LAUNCH_CHECK(h);
-  add2_kernel<<<1, 1, 0, h->stream>>>(x->loss_dev, x->loss_dev);
+  launch_pdl(h, add2_kernel, dim3(1), dim3(1), 0, x->loss_dev, x->loss_dev);
   LAUNCH_CHECK(h);
   h->global_step++;
   h->packed_dirty = true;

@@ -517,7 +517,7 @@ static void launch_maxpool3_fwd(Handle* h, const T* in, int in_cs, int in_co, T*
   const unsigned nb = (unsigned)ceil_div(total, 256);
   if (idx && ElemTag<T>::v == ET_BF16 && bn_mean && pool_lean_enabled()) {
     auto k = act == ACT_RELU ? pool_lean::fwd_kernel<ACT_RELU> : act == ACT_LRELU ? pool_lean::fwd_kernel<ACT_LRELU> : pool_lean::fwd_kernel<ACT_NONE>;
-    k<<<nb, 256, 0, h->stream>>>((const __nv_bfloat16*)in, in_cs, in_co, (__nv_bfloat16*)out, out_cs, out_co, idx, C, B, crop, seg, nseg, bn_mean, bn_inv_std);
+    launch_pdl(h, k, dim3(nb), dim3(256), 0, (const __nv_bfloat16*)in, in_cs, in_co, (__nv_bfloat16*)out, out_cs, out_co, idx, C, B, crop, seg, nseg, bn_mean, bn_inv_std);
   } else if (idx && ElemTag<T>::v == ET_BF16 && !getenv("DRS_NO_POOL_PIPELINE"))
     maxpool3_fwd_train_bf16_pipelined_kernel<<<nb, 256, 0, h->stream>>>((const __nv_bfloat16*)in, in_cs, in_co, (__nv_bfloat16*)out, out_cs, out_co, idx, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
   else if (idx && ElemTag<T>::v == ET_BF16)
@@ -584,11 +584,12 @@ static void launch_maxpool3_bwd(Handle* h, const T* dout, int do_cs, int do_co, 
       if (stats) {
         auto k = stats_act == ACT_RELU ? pool_lean::bwd_kernel<ACT_RELU, true>
                  : stats_act == ACT_LRELU ? pool_lean::bwd_kernel<ACT_LRELU, true> : pool_lean::bwd_kernel<ACT_NONE, true>;
-        k<<<nb, 256, 0, h->stream>>>((const __nv_bfloat16*)dout, do_cs, do_co, idx, (__nv_bfloat16*)din, di_cs, di_co, C, B, crop, seg, nseg,
-                                     (const __nv_bfloat16*)stats_z, stats_mean, stats_inv_std, *stats);
+        launch_pdl(h, k, dim3(nb), dim3(256), 0, (const __nv_bfloat16*)dout, do_cs, do_co, idx, (__nv_bfloat16*)din, di_cs, di_co, C, B, crop, seg,
+                   nseg, (const __nv_bfloat16*)stats_z, stats_mean, stats_inv_std, *stats);
       } else {
-        pool_lean::bwd_kernel<ACT_NONE, false><<<nb, 256, 0, h->stream>>>((const __nv_bfloat16*)dout, do_cs, do_co, idx, (__nv_bfloat16*)din, di_cs,
-                                                                           di_co, C, B, crop, seg, nseg, nullptr, nullptr, nullptr, BnFinish{});
+        launch_pdl(h, pool_lean::bwd_kernel<ACT_NONE, false>, dim3(nb), dim3(256), 0, (const __nv_bfloat16*)dout, do_cs, do_co, idx,
+                   (__nv_bfloat16*)din, di_cs, di_co, C, B, crop, seg, nseg, (const __nv_bfloat16*)nullptr, (const float*)nullptr,
+                   (const float*)nullptr, BnFinish{});
       }
     } else if (stats)
       maxpool3_bwd_bf16_kernel<true><<<(unsigned)ceil_div(base * nseg, 256), 256, 0, h->stream>>>(
@@ -642,6 +643,7 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
                   const float* __restrict__ mean, const float* __restrict__ inv_std, int act, float* __restrict__ part, int C,
                   int64_t M, int rows_per_block, BnFinish fin) {
   __shared__ float s_red[16][BN_THREADS + 1];          // [which * 8 + e][thread]: conflict-free stores and column sums
+  pdl_sync();
   const int cv = C >> 3;
   const int lanes_r = BN_THREADS / cv;
   const int cg = threadIdx.x % cv, rl = threadIdx.x / cv;
@@ -725,6 +727,7 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
 __global__ void bn_finalize_kernel(const float* __restrict__ sums, float* __restrict__ mean, float* __restrict__ inv_std,
                                    float* __restrict__ mov_mean, float* __restrict__ mov_var, int C, double count,
                                    float eps, float decay, int unbiased_ema) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mu = (double)sums[c] / count;
@@ -747,6 +750,7 @@ template <typename T>
 __global__ void __launch_bounds__(BNE_THREADS)
 bn_apply_kernel(const T* __restrict__ z, int z_cs, int z_co, const float* __restrict__ mean, const float* __restrict__ inv_std,
                 int act, T* __restrict__ out, int o_cs, int o_co, int C, int64_t M) {
+  pdl_sync();
   const int cv = C >> 3;
   const int lanes_r = BNE_THREADS / cv;
   const int cg = threadIdx.x % cv, rl = threadIdx.x / cv;
@@ -769,6 +773,7 @@ __global__ void __launch_bounds__(BNE_THREADS, DRS_BNE_MINBLK)
 bn_bwd_apply_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __restrict__ dA, int g_cs, int g_co,
                     const float* __restrict__ mean, const float* __restrict__ inv_std, const float* __restrict__ sums,
                     double inv_count, int act, TG* __restrict__ dZ, int d_cs, int d_co, int C, int64_t M) {
+  pdl_sync();
   const int cv = C >> 3;
   const int lanes_r = BNE_THREADS / cv;
   const int cg = threadIdx.x % cv, rl = threadIdx.x / cv;
@@ -818,6 +823,7 @@ bn_bwd_apply_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __re
 template <typename T>
 __global__ void add_slice_kernel(T* __restrict__ dst, int d_cs, int d_co, const T* __restrict__ src, int s_cs, int s_co,
                                  int C, int64_t M) {
+  pdl_sync();
   const int cv = C >> 3;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= M * cv) return;
@@ -843,6 +849,7 @@ template <typename T, int CLS_TILE>
 __global__ void __launch_bounds__(CLS_TILE)
 classifier_fwd_kernel(const T* __restrict__ x, int x_cs, int x_co, int Ci, const float* __restrict__ w,
                       const float* __restrict__ b, int K, float* __restrict__ logits, uint8_t* __restrict__ pred, int64_t M) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t cls_smem[];
   float* s_w = reinterpret_cast<float*>(cls_smem);                 // [Ci][8] (K padded to 8)
   uint8_t* s_x = cls_smem + (size_t)Ci * 8 * sizeof(float);        // [CLS_TILE][Ci] elements, 16-byte chunks swizzled
@@ -971,6 +978,7 @@ template <typename TG>
 __global__ void __launch_bounds__(256)
 classifier_bwd_data_reg_kernel(const float* __restrict__ dl, const float* __restrict__ w, int K, TG* __restrict__ dx, int dx_cs,
                                int dx_co, int Ci, int64_t M) {
+  pdl_sync();
   const int cv = Ci >> 3;
   const int rows = 256 / cv;
   const int cg = threadIdx.x % cv, rl = threadIdx.x / cv;
@@ -1013,6 +1021,7 @@ template <typename T>
 __global__ void __launch_bounds__(CLSW_THREADS)
 classifier_bwd_weight_kernel(const T* __restrict__ x, int x_cs, int x_co, int Ci, const float* __restrict__ dl, int K,
                              float* __restrict__ part, float* __restrict__ part_b, int64_t M, int rows_per_block) {
+  pdl_sync();
   __shared__ float s_red[CLSW_THREADS * 8];
   __shared__ float s_bias[CLSW_THREADS][MAX_CLASSES];
   const int cv = Ci >> 3;
@@ -1095,6 +1104,7 @@ __global__ void __launch_bounds__(CE_THREADS)
 ce_fwd_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ labels_f, const uint8_t* __restrict__ mask,
                   int K, int64_t M, const float* __restrict__ count_ptr, float* __restrict__ dlogits,
                   float* __restrict__ part_loss, uint8_t* __restrict__ labels_u8, int ignore_label) {
+  pdl_sync();
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float cnt = *count_ptr;                       // number of pixels in the mean (device scalar: no host round trip)
   const float inv_count = cnt > 0.0f ? 1.0f / cnt : 0.0f;
@@ -1138,6 +1148,7 @@ ce_fwd_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ la
 // count of mask != 0 (contest): block partials -> single value
 __global__ void mask_count_kernel(const uint8_t* __restrict__ mask, const float* __restrict__ labels_f, int ignore_label,
                                   int64_t M, unsigned int* __restrict__ out) {
+  pdl_sync();
   unsigned int c = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x)
     c += mask ? (mask[i] != 0) : ((int)labels_f[i] != ignore_label);
@@ -1148,6 +1159,7 @@ __global__ void mask_count_kernel(const uint8_t* __restrict__ mask, const float*
 // out[0] = sum of n floats in fixed order (single block)
 __global__ void sum_fixed_kernel(const float* __restrict__ in, int n, float* __restrict__ out, float scale,
                                  const float* __restrict__ divide_by) {
+  pdl_sync();
   __shared__ double s[256];
   double a = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) a += (double)in[i];
@@ -1165,6 +1177,7 @@ __global__ void sum_fixed_kernel(const float* __restrict__ in, int n, float* __r
 }
 // count of unmasked pixels as the float the loss kernels read
 __global__ void set_count_kernel(float* __restrict__ out, const unsigned int* __restrict__ cnt, float fixed) {
+  pdl_sync();
   out[0] = cnt ? (float)cnt[0] : fixed;
 }
 
@@ -1174,6 +1187,7 @@ __global__ void set_count_kernel(float* __restrict__ out, const unsigned int* __
 __global__ void confusion_kernel(const uint8_t* __restrict__ truth, const uint8_t* __restrict__ pred,
                                  const uint8_t* __restrict__ mask, int64_t n, int K, int ignore_label,
                                  unsigned int* __restrict__ cm /* K*K+1 */) {
+  pdl_sync();
   __shared__ unsigned int s_cm[MAX_CLASSES * MAX_CLASSES + 1];
   for (int i = threadIdx.x; i < K * K + 1; i += blockDim.x) s_cm[i] = 0;
   __syncthreads();
@@ -1197,6 +1211,7 @@ __global__ void confusion_kernel(const uint8_t* __restrict__ truth, const uint8_
 __global__ void momentum_update_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ a, int64_t n,
                                        const uint8_t* __restrict__ is_weight, float wd, float lr, float mom,
                                        float grad_scale, float* __restrict__ part_l2) {
+  pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float l2 = 0.0f;
   if (i < n) {

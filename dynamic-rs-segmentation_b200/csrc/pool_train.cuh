@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(256, DRS_POOL_MINBLK)
 fwd_kernel(const __nv_bfloat16* __restrict__ in, int in_cs, int in_co, __nv_bfloat16* __restrict__ out, int out_cs, int out_co,
            uint8_t* __restrict__ idx, int C, int B, int crop, int seg, int nseg, const float* __restrict__ bn_mean,
            const float* __restrict__ bn_inv_std) {
+  pdl_sync();
   const int cv = C >> 3;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (int64_t)B * nseg * crop * cv) return;
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(256, DRS_POOL_MINBLK)
 bwd_kernel(const __nv_bfloat16* __restrict__ dout, int do_cs, int do_co, const uint8_t* __restrict__ idx,
            __nv_bfloat16* __restrict__ din, int di_cs, int di_co, int C, int B, int crop, int seg, int nseg,
            const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ inv_std, BnFinish fin) {
+  pdl_sync();
   const int cv = C >> 3;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = gid < (int64_t)B * nseg * crop * cv;

@@ -93,6 +93,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_sync();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (convergent warp, elected lane
@@ -244,6 +245,7 @@ struct WgradTcArgs {
 template <typename T>
 __global__ void __launch_bounds__(256)
 im2col_conv1_kernel(const T* __restrict__ x8, T* __restrict__ xcol, int ci, int crop, int64_t M) {
+  pdl_sync();
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= M * 16) return;
   const int64_t m = gid >> 4;
@@ -321,9 +323,10 @@ static void launch_wgrad_tc(Handle* h, const WgradTcArgs& a) {
   }
   const int n_items = p.n_groups * p.splits;
   const int grid = std::min(n_items, h->sm_count);
-  wgrad_tc_kernel<<<grid, CONV_TC_THREADS, smem_bytes, h->stream>>>(tmX, tmDY, p);
+  launch_pdl(h, wgrad_tc_kernel, dim3(grid), dim3(CONV_TC_THREADS), (size_t)smem_bytes, tmX, tmDY, p);
   LAUNCH_CHECK(h);
   const int64_t n = (int64_t)(a.out_rows > 0 ? a.out_rows : Ktot) * a.co;
-  reduce_partials_kernel<<<reduce_partials_grid(n), RP_COLS * RP_LANES, 0, h->stream>>>(a.part, a.dw, n, splits, (int64_t)Ktot * a.co);
+  launch_pdl(h, reduce_partials_kernel, dim3(reduce_partials_grid(n)), dim3(RP_COLS * RP_LANES), 0, (const float*)a.part, a.dw, n, splits,
+             (int64_t)Ktot * a.co);
   LAUNCH_CHECK(h);
 }
