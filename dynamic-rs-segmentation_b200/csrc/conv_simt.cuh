@@ -205,16 +205,17 @@ wgrad_simt_kernel(const TIn* __restrict__ in, int in_cstride, int in_coff, int c
 // the 8 lane sums are combined in lane order through shared memory -> a fixed summation tree (deterministic) with 8x
 // the memory parallelism of a serial loop.  n is a multiple of 4 for every caller (Co % 4 == 0) except the classifier's
 // bias row, which takes the scalar path.
-constexpr int RP_COLS = 32, RP_LANES = 8;
-__global__ void __launch_bounds__(RP_COLS * RP_LANES)
+constexpr int RP_COLS = 32, RP_LANES = 8, RP_MAX_LANES = 32;
+__global__ void __launch_bounds__(RP_COLS * RP_MAX_LANES)
 reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S, int64_t stride = 0) {
   pdl_sync();
   if (stride == 0) stride = n;                         // distance between two splits (> n: only the first n entries are wanted)
-  __shared__ float4 s_acc[RP_LANES][RP_COLS];
+  __shared__ float4 s_acc[RP_MAX_LANES][RP_COLS];
+  const int lanes = blockDim.x / RP_COLS;              // 8, or 32 for a narrow result with many splits (reduce_partials_block)
   const int tx = threadIdx.x % RP_COLS, ty = threadIdx.x / RP_COLS;
   if ((n & 3) != 0) {                                  // tiny scalar case: one warp per column, fixed shuffle tree
     const int lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * RP_LANES + (threadIdx.x >> 5);
+    const int64_t i = (int64_t)blockIdx.x * lanes + (threadIdx.x >> 5);
     float a = 0.0f;
     if (i < n)
       for (int k = lane; k < S; k += 32) a += part[(int64_t)k * stride + i];
@@ -227,7 +228,7 @@ reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, 
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i4 < n) {
 #pragma unroll 4
-    for (int k = ty; k < S; k += RP_LANES) {
+    for (int k = ty; k < S; k += lanes) {
       const float4 v = __ldcs(reinterpret_cast<const float4*>(part + (int64_t)k * stride + i4));
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
@@ -235,13 +236,17 @@ reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, 
   s_acc[ty][tx] = a;
   __syncthreads();
   if (ty == 0 && i4 < n) {
-#pragma unroll
-    for (int j = 1; j < RP_LANES; ++j) {
+    for (int j = 1; j < lanes; ++j) {
       const float4 v = s_acc[j][tx];
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
     *reinterpret_cast<float4*>(out + i4) = a;
   }
+}
+// threads per block: a narrow result reduced over many splits (the classifier's 592 block partials of 1536 values) is a
+// latency chain of S / lanes dependent rounds in a dozen blocks -> 32 split lanes instead of 8
+static inline unsigned reduce_partials_block(int64_t n, int S) {
+  return (unsigned)(RP_COLS * ((n <= 16384 && S > 64 && (n & 3) == 0) ? RP_MAX_LANES : RP_LANES));
 }
 static inline unsigned reduce_partials_grid(int64_t n) {
   return (unsigned)((n & 3) ? ceil_div(n, RP_LANES) : ceil_div(n, 4 * RP_COLS));

@@ -192,6 +192,7 @@ struct HandleExtra {
   // data-parallel exchange of the late layers' gradients, overlapped with the rest of the backward
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_bucket_ready = nullptr, ev_bucket_done = nullptr;
+  cudaEvent_t ev_x8 = nullptr;          // conv1's padded input is ready: the side stream builds the im2col matrix under the forward
   bool use_graphs = false;          // opt-in (DRS_GRAPHS=1): measured 6-9 % per step in steady state, see DESIGN.md
   double conv_ms_acc = 0;            // device time of profiled launches already read back
   InferLane lanes[2];             // scene-inference lanes (drs_scene_api.cuh)
@@ -359,6 +360,7 @@ extern "C" int drs_create(drs_handle_t* out, const drs_config* cfg) {
   CUDA_CHECK(cudaStreamCreateWithFlags(&x->side_stream, cudaStreamNonBlocking));
   CUDA_CHECK(cudaStreamCreateWithFlags(&x->comm_stream, cudaStreamNonBlocking));
   CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_bucket_ready, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_x8, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_bucket_done, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_dz[i], cudaEventDisableTiming));
@@ -380,6 +382,7 @@ extern "C" int drs_destroy(drs_handle_t h) {
     if (x->side_stream) { cudaStreamSynchronize(x->side_stream); cudaStreamDestroy(x->side_stream); }
     if (x->comm_stream) { cudaStreamSynchronize(x->comm_stream); cudaStreamDestroy(x->comm_stream); }
     if (x->ev_bucket_ready) cudaEventDestroy(x->ev_bucket_ready);
+    if (x->ev_x8) cudaEventDestroy(x->ev_x8);
     if (x->ev_bucket_done) cudaEventDestroy(x->ev_bucket_done);
     if (x->copy_stream) { cudaStreamSynchronize(x->copy_stream); cudaStreamDestroy(x->copy_stream); }
     if (x->plan_stream) { cudaStreamSynchronize(x->plan_stream); cudaStreamDestroy(x->plan_stream); }

@@ -14,6 +14,12 @@ __global__ void unpack_extras_kernel(const float* __restrict__ src, float* __res
 }
 __global__ void add2_kernel(const float* __restrict__ a, float* __restrict__ out) { pdl_sync(); out[2] = a[0] + a[1]; }
 
+// blocks per SM of the classifier's filter-gradient kernel (its K-round shared-memory epilogue wants long-lived blocks)
+static int cls_w_blocks_per_sm() {
+  static const int v = getenv("DRS_CLSW_BPSM") ? atoi(getenv("DRS_CLSW_BPSM")) : 4;
+  return v;
+}
+
 static size_t train_workspace_bytes(Handle* h, int B, int crop, size_t es) {
   NetDesc& n = h->net;
   const int K = n.classes;
@@ -43,7 +49,7 @@ static size_t train_workspace_bytes(Handle* h, int B, int crop, size_t es) {
   add((size_t)nb_bn * 2 * 256 * 4);
   const int nb_ce = (int)ceil_div(M, CE_THREADS);
   add((size_t)nb_ce * 4);
-  const int nb_cls = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 4);
+  const int nb_cls = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * cls_w_blocks_per_sm());
   const int cls_rows = (int)ceil_div(M, nb_cls);
   add((size_t)nb_cls * (n.cls_in + 1) * K * 4);
   const int max_splits = 48;
@@ -73,7 +79,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   const int nb_bn = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * DRS_BN_MINBLK);   // one wave of resident blocks
   const int bn_rows = (int)ceil_div(M, nb_bn);
   const int nb_ce = (int)ceil_div(M, CE_THREADS);
-  const int nb_cls = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * 4);
+  const int nb_cls = (int)std::min<int64_t>(ceil_div(M, 128), (int64_t)h->sm_count * cls_w_blocks_per_sm());
   const int cls_rows = (int)ceil_div(M, nb_cls);
   const int max_splits = 48;
   size_t max_w = 0;
@@ -176,15 +182,28 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
       TA* x8 = (TA*)arena_take(h, (size_t)M * 8 * sizeof(TA));
       launch_pdl(h, pad_cast8_kernel<TA>, dim3(nblk(M, 256)), dim3(256), 0, x_dev, x8, c.ci, M);
       LAUNCH_CHECK(h);
+      if (wgrad1_on_tc) {
+        // the im2col matrix is only needed at the very end of the backward: built on the side stream, under the forward
+        xcol = (TA*)arena_take(h, (size_t)M * 128 * sizeof(TA));
+        const bool side = !h->time_convs && !getenv("DRS_NO_OVERLAP");
+        cudaStream_t main_stream = h->stream;
+        const bool pdl_main = h->pdl_prev;
+        if (side) {
+          CUDA_CHECK(cudaEventRecord(x->ev_x8, h->stream));
+          h->stream = x->side_stream;
+          h->pdl_prev = false;
+          CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->ev_x8, 0));
+        }
+        try {
+          launch_pdl(h, im2col_conv1_kernel<TA>, dim3(nblk(M * 16, 256)), dim3(256), 0, x8, xcol, c.ci, crop, M);
+          LAUNCH_CHECK(h);
+        } catch (...) { h->stream = main_stream; throw; }
+        if (side) { h->stream = main_stream; h->pdl_prev = pdl_main; }
+      }
       Conv1TcArgs a1;
       a1.x8 = x8; a1.wpack = c.w_fprop; a1.out = Z[l]; a1.out_cstride = c.co; a1.out_coff = 0; a1.co = c.co;
       a1.B = B; a1.crop = crop; a1.scale = x->ones; a1.shift = h->params + c.b_off; a1.act = ACT_NONE; a1.etype = ElemTag<TA>::v;
       launch_conv1_tc(h, a1);
-      if (wgrad1_on_tc) {
-        xcol = (TA*)arena_take(h, (size_t)M * 128 * sizeof(TA));
-        launch_pdl(h, im2col_conv1_kernel<TA>, dim3(nblk(M * 16, 256)), dim3(256), 0, x8, xcol, c.ci, crop, M);
-        LAUNCH_CHECK(h);
-      }
     } else if (l == 0) {
       launch_conv_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, h->params + c.w_off, Z[l], c.co, 0, c.co, B, crop, c.k,
                                   c.rate, c.pad_b, x->ones, h->params + c.b_off, ACT_NONE);
@@ -269,7 +288,8 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   launch_pdl(h, classifier_bwd_weight_kernel<TA>, dim3(nb_cls), dim3(CLSW_THREADS), 0, (const TA*)feat.p, feat.cs, feat.co, n.cls_in, dlogits, K, part_cls,
                                                                            part_clsb, M, cls_rows);
   LAUNCH_CHECK(h);
-  launch_pdl(h, reduce_partials_kernel, dim3(reduce_partials_grid((int64_t)n.cls_in * K)), dim3(RP_COLS * RP_LANES), 0, part_cls, h->grads + n.cls_w_off, (int64_t)n.cls_in * K, nb_cls, (int64_t)0);
+  launch_pdl(h, reduce_partials_kernel, dim3(reduce_partials_grid((int64_t)n.cls_in * K)), dim3(reduce_partials_block((int64_t)n.cls_in * K, nb_cls)), 0,
+             part_cls, h->grads + n.cls_w_off, (int64_t)n.cls_in * K, nb_cls, (int64_t)0);
   LAUNCH_CHECK(h);
   launch_pdl(h, reduce_partials_kernel, dim3(reduce_partials_grid(K)), dim3(RP_COLS * RP_LANES), 0, part_clsb, h->grads + n.cls_b_off, K, nb_cls, (int64_t)0);
   LAUNCH_CHECK(h);
@@ -287,7 +307,9 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     const int cvc = n.cls_in / 8;
     if (cvc <= 256 && 256 % cvc == 0 && ElemTag<TA>::v != ET_F32 && !getenv("DRS_NO_CLS_REG")) {
       const int rows = 256 / cvc;
-      int blocks = (int)std::min<int64_t>(ceil_div(M, 2 * rows), (int64_t)h->sm_count * 8);
+      // few, long-lived blocks: a thread first loads its 8 x K weights (48 scalar loads), which must be amortised
+      static const int cls_bpsm = getenv("DRS_CLS_BPSM") ? atoi(getenv("DRS_CLS_BPSM")) : 2;
+      int blocks = (int)std::min<int64_t>(ceil_div(M, 2 * rows), (int64_t)h->sm_count * cls_bpsm);
       launch_pdl(h, classifier_bwd_data_reg_kernel<TA>, dim3(blocks), dim3(256), 0, dlogits, h->params + n.cls_w_off, K, Gcur, gcs0, 0, n.cls_in, M);
     } else {
       int blocks = (int)std::min<int64_t>(ceil_div(M * (n.cls_in / 8), 256), (int64_t)h->sm_count * 16);

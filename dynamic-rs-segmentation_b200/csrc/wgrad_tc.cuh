@@ -249,22 +249,38 @@ im2col_conv1_kernel(const T* __restrict__ x8, T* __restrict__ xcol, int ci, int 
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= M * 16) return;
   const int64_t m = gid >> 4;
-  const int g = (int)(gid & 15);
+  const int g = (int)(gid & 15);           // 16-byte group of the 256-byte row: elements 8g .. 8g+7
   const int cc = crop * crop;
   const int r = (int)(m % cc);
   const int y = r / crop, x = r - y * crop;
-  alignas(16) T v[8];
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (ci == 4) {
+    // two taps per group, one 8-byte load each (x8 rows are 16 bytes: channels 0..3 are the low half)
+    uint2 v[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int k = g * 8 + e;
-    const int tap = k / ci, c = k - tap * ci;
-    const int ky = tap / 5, kx = tap - ky * 5;
-    const int yy = y + ky - 2, xx = x + kx - 2;
-    T val = from_f32<T>(0.0f);
-    if (tap < 25 && yy >= 0 && yy < crop && xx >= 0 && xx < crop) val = x8[(m + (int64_t)(ky - 2) * crop + (kx - 2)) * 8 + c];
-    v[e] = val;
+    for (int j = 0; j < 2; ++j) {
+      const int tap = 2 * g + j;
+      const int ky = tap / 5, kx = tap - ky * 5;
+      const int yy = y + ky - 2, xx = x + kx - 2;
+      if (tap < 25 && yy >= 0 && yy < crop && xx >= 0 && xx < crop)
+        v[j] = *reinterpret_cast<const uint2*>(x8 + (m + (int64_t)(ky - 2) * crop + (kx - 2)) * 8);
+    }
+    o = make_uint4(v[0].x, v[0].y, v[1].x, v[1].y);
+  } else {
+    alignas(16) T e8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = g * 8 + e;
+      const int tap = k / ci, c = k - tap * ci;
+      const int ky = tap / 5, kx = tap - ky * 5;
+      const int yy = y + ky - 2, xx = x + kx - 2;
+      T val = from_f32<T>(0.0f);
+      if (tap < 25 && yy >= 0 && yy < crop && xx >= 0 && xx < crop) val = x8[(m + (int64_t)(ky - 2) * crop + (kx - 2)) * 8 + c];
+      e8[e] = val;
+    }
+    o = *reinterpret_cast<const uint4*>(e8);
   }
-  *reinterpret_cast<uint4*>(xcol + m * 128 + g * 8) = *reinterpret_cast<const uint4*>(v);
+  *reinterpret_cast<uint4*>(xcol + m * 128 + g * 8) = o;
 }
 
 static inline bool wgrad_tc_supported(int ci, int co) { return ci % 64 == 0 && co % 64 == 0 && co >= 64 && co <= 256; }
