@@ -16,7 +16,7 @@ __global__ void add2_kernel(const float* __restrict__ a, float* __restrict__ out
 
 // blocks per SM of the classifier's filter-gradient kernel (its K-round shared-memory epilogue wants long-lived blocks)
 static int cls_w_blocks_per_sm() {
-  static const int v = getenv("DRS_CLSW_BPSM") ? atoi(getenv("DRS_CLSW_BPSM")) : 4;
+  static const int v = getenv("DRS_CLSW_BPSM") ? atoi(getenv("DRS_CLSW_BPSM")) : 2;
   return v;
 }
 
@@ -331,6 +331,25 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     // and dIn less per layer).  Measured slower: the pool backward is issue-bound already and the extra registers cost it
     // a resident CTA (batch 64: crop 37 1.684 vs 1.643 ms/step, crop 49 2.586 vs 2.515).
     const bool fused_bwd_stats = n.pool && ElemTag<TA>::v == ET_BF16 && getenv("DRS_FUSED_BWD_STATS");
+    // Pooling nets, bf16: two passes instead of four.  The BN-backward sums are taken on the pooled side (window gradients
+    // and pooled activations: bn_partial_kernel MODE 2), then ONE kernel scatters the window gradients to their winners and
+    // applies the BN backward to the finished fp32 row: the pool's input gradient is never written (it used to be stored as
+    // bf16, read by the statistics pass and read again by bn_bwd_apply_kernel).
+    const bool fused_pool_apply = n.pool && !n.dense && !n.squeeze && c.post == 0 && ElemTag<TA>::v == ET_BF16 && c.co <= 512 &&
+                                  pool_lean_enabled() && !x->debug_keep && !fused_bwd_stats && !getenv("DRS_NO_FUSED_POOL_APPLY");
+    if (fused_pool_apply) {
+      launch_pdl(h, bn_partial_kernel<TA, TA, 2>, dim3(nb_bn), dim3(BN_THREADS), 0, (const TA*)Xn[l], c.co, 0, (const TA*)dOut.p, dOut.cs, dOut.co,
+                 (const float*)mean, (const float*)istd, n.act, part_bn, c.co, M, bn_rows, finb);
+      LAUNCH_CHECK(h);
+      if (h->sync_bn) do_allreduce(h, x->sums, 2 * c.co);
+      TA* DZf = DZb[l & 1];
+      if (l + 2 <= L - 1) {
+        CUDA_CHECK(cudaStreamWaitEvent(h->stream, x->ev_wgrad[l & 1], 0));
+        if (!getenv("DRS_PDL_ACROSS_EVENTS")) h->pdl_prev = false;
+      }
+      launch_maxpool3_bwd_apply(h, (const __nv_bfloat16*)dOut.p, dOut.cs, dOut.co, idx[l], (__nv_bfloat16*)DZf, c.co, 0, c.co, B, crop,
+                                (const __nv_bfloat16*)Z[l], mean, istd, x->sums, 1.0 / bn_count, n.act);
+    } else {
     if (n.pool) {
       if (fused_bwd_stats) launch_maxpool3_bwd<TA>(h, (const TA*)dOut.p, dOut.cs, dOut.co, idx[l], T, c.co, 0, c.co, B, crop, &finb, Z[l], mean, istd, n.act);
       else launch_maxpool3_bwd<TA>(h, (const TA*)dOut.p, dOut.cs, dOut.co, idx[l], T, c.co, 0, c.co, B, crop);
@@ -376,6 +395,8 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
                dA.co, (const float*)mean, (const float*)istd, (const float*)x->sums, 1.0 / bn_count, n.act, DZ, c.co, 0, c.co, M);
     LAUNCH_CHECK(h);
     debug_keep<TA>(h, "da:" + c.scope, (const TA*)dA.p, dA.cs, dA.co, c.co, M);
+    }
+    TA* DZ = DZb[l & 1];
     debug_keep<TA>(h, "dz:" + c.scope, DZ, c.co, 0, c.co, M);
     CUDA_CHECK(cudaEventRecord(x->ev_dz[l & 1], h->stream));
     // wgrad (bias gradient is identically zero behind a BN without beta: sum_m dZ = 0)

@@ -605,6 +605,22 @@ static void launch_maxpool3_bwd(Handle* h, const T* dout, int do_cs, int do_co, 
   LAUNCH_CHECK(h);
 }
 
+// pool backward + batch-norm backward of the layer below in one pass (bf16 training, pool_train.cuh)
+static void launch_maxpool3_bwd_apply(Handle* h, const __nv_bfloat16* dout, int do_cs, int do_co, const uint8_t* idx, __nv_bfloat16* dz,
+                                      int dz_cs, int dz_co, int C, int B, int crop, const __nv_bfloat16* z, const float* mean,
+                                      const float* inv_std, const float* sums, double inv_count, int act) {
+  const int64_t base = (int64_t)B * crop * (C / 8);
+  int nseg = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div((int64_t)h->sm_count * 2048, base)), std::max(1, crop / 4));
+  const int seg = (int)ceil_div(crop, nseg);
+  nseg = (int)ceil_div(crop, seg);
+  const unsigned nb = (unsigned)ceil_div(base * nseg, 256);
+  auto k = act == ACT_RELU ? pool_lean::bwd_apply_kernel<ACT_RELU>
+           : act == ACT_LRELU ? pool_lean::bwd_apply_kernel<ACT_LRELU> : pool_lean::bwd_apply_kernel<ACT_NONE>;
+  launch_pdl(h, k, dim3(nb), dim3(256), (size_t)4 * C * sizeof(float), dout, do_cs, do_co, idx, dz, dz_cs, dz_co, C, B, crop, seg, nseg, z, mean,
+             inv_std, sums, inv_count);
+  LAUNCH_CHECK(h);
+}
+
 // ------------------------------------------------------------------------------------------------
 // _batch_norm (isprs:655-663): tf.contrib.layers.batch_norm(center=False, scale=False)
 // ------------------------------------------------------------------------------------------------
@@ -614,6 +630,7 @@ constexpr int BN_THREADS = 256;
 // part[blk][0][c] = sum_m a, part[blk][1][c] = sum_m a*b over the block's contiguous slab of rows.
 //   MODE 0 (forward statistics):  a = z,            b = z
 //   MODE 1 (backward sums):       a = g = dA*act'(xh), b = xh        (xh = (z-mean)*inv_std)
+//   MODE 2 (backward sums through a max-pool, from the pooled side): see bn_partial_row
 // Thread = (channel group of 8, row lane): 16-byte loads, per-thread fp32 partials, then a fixed-order reduction over the
 // row lanes in shared memory.  The row -> (block, lane) assignment is static, so the result is run-to-run identical.
 template <typename TZ, typename TG, int MODE>
@@ -625,11 +642,22 @@ __device__ __forceinline__ void bn_partial_row(const Vec8<TZ>& zv, const Vec8<TG
       const float f = to_f32(zv.v[e]);
       s0[e] += f;
       s1[e] = fmaf(f, f, s1[e]);
-    } else {
+    } else if (MODE == 1) {
       const float xh = (to_f32(zv.v[e]) - mu[e]) * is[e];
       float g = to_f32(gv.v[e]);
       if (act == ACT_RELU) g = xh > 0.0f ? g : 0.0f;
       else if (act == ACT_LRELU) g = xh > 0.0f ? g : 0.1f * g;
+      s0[e] += g;
+      s1[e] = fmaf(g, xh, s1[e]);
+    } else {
+      // MODE 2, pooling nets: zv is the pooled ACTIVATION act(xh of the window's winner), gv the window's gradient.  The
+      // winner's normalised value is recovered through the inverse activation (exact for ReLU where it matters -- the
+      // negative side has no gradient; within the activation's bf16 rounding for LeakyReLU).
+      const float av = to_f32(zv.v[e]);
+      float g = to_f32(gv.v[e]);
+      float xh = av;
+      if (act == ACT_RELU) g = av > 0.0f ? g : 0.0f;
+      else if (act == ACT_LRELU) { xh = av > 0.0f ? av : av * 10.0f; g = av > 0.0f ? g : 0.1f * g; }
       s0[e] += g;
       s1[e] = fmaf(g, xh, s1[e]);
     }
@@ -658,7 +686,7 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
       for (int e = 0; e < 8; ++e) { mu[e] = mean[cg * 8 + e]; is[e] = inv_std[cg * 8 + e]; }
     }
     const TZ* zp = z + z_co + cg * 8;
-    const TG* gp = MODE == 1 ? dA + g_co + cg * 8 : nullptr;
+    const TG* gp = MODE >= 1 ? dA + g_co + cg * 8 : nullptr;
     int64_t m = r0 + rl;
     // BN_UNROLL rows per iteration: every load is issued before the first one is consumed
     for (; m + (int64_t)(BN_UNROLL - 1) * lanes_r < r1; m += (int64_t)BN_UNROLL * lanes_r) {
@@ -667,7 +695,7 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
 #pragma unroll
       for (int u = 0; u < BN_UNROLL; ++u) {
         zv[u] = *reinterpret_cast<const Vec8<TZ>*>(zp + (m + (int64_t)u * lanes_r) * z_cs);
-        if (MODE == 1) gv[u] = *reinterpret_cast<const Vec8<TG>*>(gp + (m + (int64_t)u * lanes_r) * g_cs);
+        if (MODE >= 1) gv[u] = *reinterpret_cast<const Vec8<TG>*>(gp + (m + (int64_t)u * lanes_r) * g_cs);
       }
 #pragma unroll
       for (int u = 0; u < BN_UNROLL; ++u) bn_partial_row<TZ, TG, MODE>(zv[u], gv[u], mu, is, act, s0, s1);
@@ -675,7 +703,7 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
     for (; m < r1; m += lanes_r) {
       const Vec8<TZ> zv = *reinterpret_cast<const Vec8<TZ>*>(zp + m * z_cs);
       Vec8<TG> gv;
-      if (MODE == 1) gv = *reinterpret_cast<const Vec8<TG>*>(gp + m * g_cs);
+      if (MODE >= 1) gv = *reinterpret_cast<const Vec8<TG>*>(gp + m * g_cs);
       bn_partial_row<TZ, TG, MODE>(zv, gv, mu, is, act, s0, s1);
     }
   }

@@ -338,4 +338,124 @@ bwd_kernel(const __nv_bfloat16* __restrict__ dout, int do_cs, int do_co, const u
   if (threadIdx.x == 0) *fin.counter = 0u;
 }
 
+// ------------------------------------------------------------------------------------------------ backward + BN backward
+// The pool backward and the batch-norm backward of the layer below in one pass: the gradient of the pool input never
+// goes to memory (it was written as bf16 and read back twice, by the statistics pass and by bn_bwd_apply_kernel):
+//   dZ = inv_std * (g - s0/M - xh * s1/M),   g = dIn * act'(xh),   xh = (z - mean) * inv_std
+// with dIn the fp32 sum the scatter has just finished for this row.  The two sums come from bn_partial_kernel<MODE 2>,
+// which needs only the window gradients and the pooled activations (every window hands its whole gradient to its winner,
+// so sum_positions g = sum_windows dOut * act'(winner) and likewise for g * xh).  The four per-channel constants live in
+// shared memory (registers would cost the kernel a resident block).
+__device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {       // asm volatile: stays where it is written
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(static_cast<unsigned>(__cvta_generic_to_shared(p))));
+  return v;
+}
+template <int ACT>
+__device__ __forceinline__ void bwd_emit_apply(float (&acc)[8], __nv_bfloat16* __restrict__ pd, const __nv_bfloat16* __restrict__ pz,
+                                               const float* __restrict__ s_c, int C, int c0, const uint4& zraw) {
+  const unsigned* zw = reinterpret_cast<const unsigned*>(&zraw);
+  uint4 o;
+  unsigned* ow = reinterpret_cast<unsigned*>(&o);
+#pragma unroll
+  for (int hv = 0; hv < 2; ++hv) {
+    // (volatile: re-read every row -- hoisted out of the row loop the 32 values would live in registers again)
+    const float4 mu = lds_f4(s_c + c0 + 4 * hv);
+    const float4 is = lds_f4(s_c + C + c0 + 4 * hv);
+    const float4 m0 = lds_f4(s_c + 2 * C + c0 + 4 * hv);
+    const float4 m1 = lds_f4(s_c + 3 * C + c0 + 4 * hv);
+    const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
+    const float m0v[4] = {m0.x, m0.y, m0.z, m0.w}, m1v[4] = {m1.x, m1.y, m1.z, m1.w};
+    float dz[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = 4 * hv + q;
+      const unsigned zz = zw[e >> 1];
+      const float zf = __uint_as_float((e & 1) ? (zz & 0xFFFF0000u) : (zz << 16));
+      const float xh = (zf - muv[q]) * isv[q];
+      float g = acc[e];
+      if (ACT == ACT_RELU) g = xh > 0.0f ? g : 0.0f;
+      else if (ACT == ACT_LRELU) g = xh > 0.0f ? g : 0.1f * g;
+      dz[q] = isv[q] * (g - m0v[q] - xh * m1v[q]);
+      acc[e] = 0.0f;
+    }
+    const __nv_bfloat162 p0 = __floats2bfloat162_rn(dz[0], dz[1]), p1 = __floats2bfloat162_rn(dz[2], dz[3]);
+    ow[2 * hv] = *reinterpret_cast<const unsigned*>(&p0);
+    ow[2 * hv + 1] = *reinterpret_cast<const unsigned*>(&p1);
+  }
+  *reinterpret_cast<uint4*>(pd) = o;
+}
+
+#ifndef DRS_POOL_APPLY_MINBLK
+#define DRS_POOL_APPLY_MINBLK 2
+#endif
+template <int ACT>
+__global__ void __launch_bounds__(256, DRS_POOL_APPLY_MINBLK)
+bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int do_cs, int do_co, const uint8_t* __restrict__ idx,
+                 __nv_bfloat16* __restrict__ dz, int dz_cs, int dz_co, int C, int B, int crop, int seg, int nseg,
+                 const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ inv_std,
+                 const float* __restrict__ sums, double inv_count) {
+  extern __shared__ __align__(16) float s_c[];        // [4][C]: mean, inv_std, s0/M, s1/M
+  pdl_sync();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    s_c[c] = mean[c];
+    s_c[C + c] = inv_std[c];
+    s_c[2 * C + c] = (float)((double)sums[c] * inv_count);
+    s_c[3 * C + c] = (float)((double)sums[C + c] * inv_count);
+  }
+  __syncthreads();
+  const int cv = C >> 3;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)B * nseg * crop * cv) return;
+  const int cg = (int)(gid % cv);
+  int64_t t = gid / cv;
+  const int x = (int)(t % crop);
+  t /= crop;
+  const int sg = (int)(t % nseg);
+  const int b = (int)(t / nseg);
+  const int y0 = sg * seg, y1 = min(crop, y0 + seg);
+  const int64_t pix0 = (int64_t)b * crop * crop + x;
+  const bool xl = x > 0, xr = x + 1 < crop;
+  const __nv_bfloat16* pg = dout + pix0 * do_cs + do_co + cg * 8;
+  const uint8_t* pk = idx + pix0 * C + cg * 8;
+  const int64_t gs = (int64_t)crop * do_cs, ks = (int64_t)crop * C;
+  __nv_bfloat16* pd = dz + (pix0 + (int64_t)(y1 - 1) * crop) * dz_cs + dz_co + cg * 8;
+  const int64_t ds = (int64_t)crop * dz_cs;
+  const __nv_bfloat16* pz = z + (pix0 + (int64_t)(y1 - 1) * crop) * C + cg * 8;
+  const int64_t zs = (int64_t)crop * C;
+  float a0[8], a1[8], a2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a0[e] = 0.0f; a1[e] = 0.0f; a2[e] = 0.0f; }
+  BwdRow r;
+  bwd_load(pg, gs, do_cs, pk, ks, C, y1, crop, xl, xr, r);
+  bwd_scatter<true, false, false>(r, a0, a1, a2);
+  bwd_load(pg, gs, do_cs, pk, ks, C, y1 - 1, crop, xl, xr, r);
+  bwd_scatter<true, true, false>(r, a1, a0, a2);
+#define DRS_POOL_BWD_STEP(ACC_Y, ACC_1, ACC_2)                                                   \
+  {                                                                                               \
+    /* Z comes from DRAM (written in the forward): requested before the window row, consumed after the scatter */ \
+    const uint4 zraw = ldg_nc_u4(pz);                                                             \
+    bwd_load(pg, gs, do_cs, pk, ks, C, y - 1, crop, xl, xr, r);                                   \
+    if (y > y0) bwd_scatter<true, true, true>(r, ACC_2, ACC_1, ACC_Y);                            \
+    else bwd_scatter<false, false, true>(r, ACC_2, ACC_1, ACC_Y);                                 \
+    bwd_emit_apply<ACT>(ACC_Y, pd, pz, s_c, C, cg * 8, zraw);                                     \
+    pd -= ds;                                                                                     \
+    pz -= zs;                                                                                     \
+    if (--y < y0) break;                                                                          \
+  }
+  for (int y = y1 - 1;;) {
+    DRS_POOL_BWD_STEP(a0, a1, a2)
+    DRS_POOL_BWD_STEP(a1, a2, a0)
+    DRS_POOL_BWD_STEP(a2, a0, a1)
+  }
+#undef DRS_POOL_BWD_STEP
+}
+
 }  // namespace pool_lean
