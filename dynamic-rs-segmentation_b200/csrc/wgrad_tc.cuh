@@ -342,7 +342,7 @@ static void launch_wgrad_tc(Handle* h, const WgradTcArgs& a) {
   launch_pdl(h, wgrad_tc_kernel, dim3(grid), dim3(CONV_TC_THREADS), (size_t)smem_bytes, tmX, tmDY, p);
   LAUNCH_CHECK(h);
   const int64_t n = (int64_t)(a.out_rows > 0 ? a.out_rows : Ktot) * a.co;
-  launch_pdl(h, reduce_partials_kernel, dim3(reduce_partials_grid(n)), dim3(RP_COLS * RP_LANES), 0, (const float*)a.part, a.dw, n, splits,
+  launch_pdl(h, reduce_partials_kernel, dim3(reduce_partials_grid(n)), dim3(reduce_partials_block(n, splits)), 0, (const float*)a.part, a.dw, n, splits,
              (int64_t)Ktot * a.co);
   LAUNCH_CHECK(h);
 }
