@@ -670,7 +670,10 @@ __global__ void __launch_bounds__(BN_THREADS, DRS_BN_MINBLK)
 bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __restrict__ dA, int g_cs, int g_co,
                   const float* __restrict__ mean, const float* __restrict__ inv_std, int act, float* __restrict__ part, int C,
                   int64_t M, int rows_per_block, BnFinish fin) {
-  __shared__ float s_red[16][BN_THREADS + 1];          // [which * 8 + e][thread]: conflict-free stores and column sums
+  // [round slot][thread]: the 16 per-thread sums go through shared memory four at a time.  The whole set at once was 16.4 KB
+  // of static shared memory, and next to a resident wgrad_tc CTA (up to 216 KB, on the side stream) that does not fit: the
+  // statistics pass then waited for the filter gradient instead of running beside it (CUPTI timeline: 28 us holes).
+  __shared__ float s_red[4][BN_THREADS + 1];
   pdl_sync();
   const int cv = C >> 3;
   const int lanes_r = BN_THREADS / cv;
@@ -707,21 +710,24 @@ bn_partial_kernel(const TZ* __restrict__ z, int z_cs, int z_co, const TG* __rest
       bn_partial_row<TZ, TG, MODE>(zv, gv, mu, is, act, s0, s1);
     }
   }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    s_red[e][threadIdx.x] = s0[e];
-    s_red[8 + e][threadIdx.x] = s1[e];
-  }
-  __syncthreads();
   // Block partial (fixed order) -> 64-bit fixed point -> integer atomicAdd: integer addition is associative, so the grid-wide
   // sum does not depend on the order in which blocks arrive (deterministic without a serial reduction pass).
-  for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) {
-    const int which = i / C, rem = i - which * C;
-    const int e = rem / cv, g = rem - e * cv;            // consecutive threads -> consecutive channel groups (no conflicts)
-    float a = 0.0f;
-    for (int r = 0; r < lanes_r; ++r) a += s_red[which * 8 + e][r * cv + g];
-    const long long q = __double2ll_rn((double)a * fin.fx_scale);
-    atomicAdd(bn_acc_mine(fin) + which * C + g * 8 + e, static_cast<unsigned long long>(q));
+#pragma unroll
+  for (int rd = 0; rd < 4; ++rd) {                       // round rd: elements 2rd, 2rd+1 of both sums
+    if (rd) __syncthreads();
+    s_red[0][threadIdx.x] = s0[2 * rd];
+    s_red[1][threadIdx.x] = s0[2 * rd + 1];
+    s_red[2][threadIdx.x] = s1[2 * rd];
+    s_red[3][threadIdx.x] = s1[2 * rd + 1];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * cv; i += BN_THREADS) {
+      const int j = i / cv, g = i - j * cv;              // consecutive threads -> consecutive channel groups (no conflicts)
+      const int which = j >> 1, e = 2 * rd + (j & 1);
+      float a = 0.0f;
+      for (int r = 0; r < lanes_r; ++r) a += s_red[j][r * cv + g];
+      const long long q = __double2ll_rn((double)a * fin.fx_scale);
+      atomicAdd(bn_acc_mine(fin) + which * C + g * 8 + e, static_cast<unsigned long long>(q));
+    }
   }
   // ---- the last block to finish converts the sums, finalizes and clears the accumulators for the next launch
   __shared__ bool s_last;
@@ -958,7 +964,9 @@ static void launch_classifier_fwd(Handle* h, const T* x, int x_cs, int x_co, int
                                   float* logits, uint8_t* pred, int64_t M) {
   DRS_CHECK(Ci % 64 == 0, "classifier: Ci=%d must be a multiple of 64", Ci);
   auto smem_of = [&](int tile) { return (size_t)Ci * 8 * 4 + (size_t)tile * Ci * sizeof(T); };
-  if (smem_of(128) <= 112 * 1024) launch_classifier_fwd_t<T, 128>(h, x, x_cs, x_co, Ci, w, b, K, logits, pred, M, smem_of(128));
+  static const int force_tile = getenv("DRS_CLS_TILE") ? atoi(getenv("DRS_CLS_TILE")) : 0;
+  if (force_tile == 64) launch_classifier_fwd_t<T, 64>(h, x, x_cs, x_co, Ci, w, b, K, logits, pred, M, smem_of(64));
+  else if (smem_of(128) <= 112 * 1024) launch_classifier_fwd_t<T, 128>(h, x, x_cs, x_co, Ci, w, b, K, logits, pred, M, smem_of(128));
   else if (smem_of(64) <= 112 * 1024 || smem_of(128) > 220 * 1024) launch_classifier_fwd_t<T, 64>(h, x, x_cs, x_co, Ci, w, b, K, logits, pred, M, smem_of(64));
   else launch_classifier_fwd_t<T, 128>(h, x, x_cs, x_co, Ci, w, b, K, logits, pred, M, smem_of(128));
 }
