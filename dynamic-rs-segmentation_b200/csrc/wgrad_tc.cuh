@@ -283,7 +283,30 @@ im2col_conv1_kernel(const T* __restrict__ x8, T* __restrict__ xcol, int ci, int 
   *reinterpret_cast<uint4*>(xcol + m * 128 + g * 8) = o;
 }
 
-static inline bool wgrad_tc_supported(int ci, int co) { return ci % 64 == 0 && co % 64 == 0 && co >= 64 && co <= 256; }
+// Channel counts of 32 (the first layers of the ICPR nets, isprs:791-1033) run as 64: the TMA boxes are 64 channels wide
+// whatever the tensor holds -- past the end of a 32-channel tensor the box is zero-filled, inside the dense nets' 448-wide
+// concat buffer it picks up 32 foreign (finite) channels -- and the rows / columns of dW that belong to the padding are
+// dropped by the reduction (reduce_partials_remap_kernel).  Twice the MMA work of a tiny layer, instead of the CUDA-core
+// kernel that held up the whole step (CUPTI timeline, DenseDilated6 batch 16 crop 49: 695 us of a 1455 us step).
+static inline bool wgrad_tc_supported(int ci, int co) {
+  return (ci % 64 == 0 || ci == 32) && (co % 64 == 0 || co == 32) && co <= 256 && !(getenv("DRS_NO_WGRAD_PAD") && (ci == 32 || co == 32));
+}
+
+// out[(tap*ci + c)*co + o] = sum_s part[s][(tap*ci_pad + c)*co_pad + o]   (splits in ascending order: deterministic)
+__global__ void __launch_bounds__(256)
+reduce_partials_remap_kernel(const float* __restrict__ part, float* __restrict__ out, int S, int64_t stride, int rows_out, int ci,
+                             int ci_pad, int co, int co_pad) {
+  pdl_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows_out * co) return;
+  const int r = i / co, o = i - r * co;
+  const int tap = r / ci, c = r - tap * ci;
+  const float* src = part + ((int64_t)tap * ci_pad + c) * co_pad + o;
+  float a = 0.0f;
+#pragma unroll 8
+  for (int k = 0; k < S; ++k) a += __ldcs(src + (int64_t)k * stride);
+  out[i] = a;
+}
 
 
 static void launch_wgrad_tc(Handle* h, const WgradTcArgs& a) {
@@ -291,21 +314,22 @@ static void launch_wgrad_tc(Handle* h, const WgradTcArgs& a) {
   DRS_CHECK(a.in_cstride % 8 == 0 && a.dy_cstride % 8 == 0 && a.in_coff % 8 == 0 && a.dy_coff % 8 == 0, "wgrad_tc: alignment");
   const int64_t M = (int64_t)a.B * a.crop * a.crop;
   const int taps = a.k * a.k;
-  const int Ktot = taps * a.ci;
+  const int ci_pad = (a.ci + 63) / 64 * 64, co_pad = (a.co + 63) / 64 * 64;    // 32 -> 64 (see wgrad_tc_supported)
+  const int Ktot = taps * ci_pad;
   alignas(64) CUtensorMap tmX, tmDY;
   encode_im2col(h, &tmX, ET_BF16, a.x, a.in_cstride, a.crop, a.B, a.pad_b, 64, WG_BPX, 128);
   encode_tiled_2d(h, &tmDY, ET_BF16, a.dy, (uint64_t)a.dy_cstride, (uint64_t)M, (uint64_t)a.dy_cstride * 2, 64, WG_BPX, 128);
 
   WgradTcParams p;
   p.M_total = (int)M; p.crop = a.crop; p.ksize = a.k; p.rate = a.rate; p.pad_b = a.pad_b;
-  p.ci = a.ci; p.in_coff = a.in_coff; p.co = a.co; p.dy_coff = a.dy_coff;
-  p.n_rb = taps * (a.ci / 64);
+  p.ci = ci_pad; p.in_coff = a.in_coff; p.co = co_pad; p.dy_coff = a.dy_coff;
+  p.n_rb = taps * (ci_pad / 64);
   p.n_tiles = (p.n_rb + 1) / 2;
-  p.acc_stride = a.co <= 64 ? 64 : a.co <= 128 ? 128 : 256;
+  p.acc_stride = co_pad <= 64 ? 64 : co_pad <= 128 ? 128 : 256;
   // tiles per work item: bounded by TMEM (512 columns) and by a >= 3-stage shared-memory pipeline
   int T = 512 / p.acc_stride;
   const int budget = 227 * 1024 - 2048;
-  while (T > 1 && 3 * (T * 2 * 8192 + (a.co / 64) * 8192) > budget) --T;
+  while (T > 1 && 3 * (T * 2 * 8192 + (co_pad / 64) * 8192) > budget) --T;
   if (T > p.n_tiles) T = p.n_tiles;
   p.T = T;
   p.tmem_cols = 32;
@@ -316,12 +340,12 @@ static void launch_wgrad_tc(Handle* h, const WgradTcArgs& a) {
   // split, fit the workspace
   int splits = std::max(1, h->sm_count / p.n_groups);
   splits = std::min<int>(splits, std::max(1, p.n_chunks / 8));
-  splits = std::min<int64_t>(splits, (int64_t)(a.part_capacity / ((size_t)Ktot * a.co)));
+  splits = std::min<int64_t>(splits, (int64_t)(a.part_capacity / ((size_t)Ktot * co_pad)));
   DRS_CHECK(splits >= 1, "wgrad_tc: workspace too small");
   p.chunks_per_split = (int)ceil_div(p.n_chunks, splits);
   splits = (int)ceil_div(p.n_chunks, p.chunks_per_split);
   p.splits = splits;
-  const int stage_bytes = T * 2 * 8192 + (a.co / 64) * 8192;
+  const int stage_bytes = T * 2 * 8192 + (co_pad / 64) * 8192;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   DRS_CHECK(stages >= 2, "wgrad_tc: stage does not fit shared memory");
@@ -329,7 +353,7 @@ static void launch_wgrad_tc(Handle* h, const WgradTcArgs& a) {
   p.smem_needed = stages * stage_bytes + (2 * 8 + 2) * 8 + 16;
   const int smem_bytes = std::min(p.smem_needed + 1024, 227 * 1024);
   p.smem_provided = smem_bytes;
-  p.idesc = make_idesc_f16(128, a.co, 1, 1, 1, 1);   // bf16 x bf16, both operands MN-major
+  p.idesc = make_idesc_f16(128, co_pad, 1, 1, 1, 1);   // bf16 x bf16, both operands MN-major
   p.part = a.part;
   p.diag = h->diag_dev;
   static bool attr_set = false;
@@ -341,8 +365,14 @@ static void launch_wgrad_tc(Handle* h, const WgradTcArgs& a) {
   const int grid = std::min(n_items, h->sm_count);
   launch_pdl(h, wgrad_tc_kernel, dim3(grid), dim3(CONV_TC_THREADS), (size_t)smem_bytes, tmX, tmDY, p);
   LAUNCH_CHECK(h);
-  const int64_t n = (int64_t)(a.out_rows > 0 ? a.out_rows : Ktot) * a.co;
-  launch_pdl(h, reduce_partials_kernel, dim3(reduce_partials_grid(n)), dim3(reduce_partials_block(n, splits)), 0, (const float*)a.part, a.dw, n, splits,
-             (int64_t)Ktot * a.co);
+  const int rows_out = a.out_rows > 0 ? a.out_rows : taps * a.ci;
+  const int64_t n = (int64_t)rows_out * a.co;
+  if (ci_pad != a.ci || co_pad != a.co) {
+    launch_pdl(h, reduce_partials_remap_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, (const float*)a.part, a.dw, splits,
+               (int64_t)Ktot * co_pad, rows_out, a.ci, ci_pad, a.co, co_pad);
+  } else {
+    launch_pdl(h, reduce_partials_kernel, dim3(reduce_partials_grid(n)), dim3(reduce_partials_block(n, splits)), 0, (const float*)a.part, a.dw, n, splits,
+               (int64_t)Ktot * a.co);
+  }
   LAUNCH_CHECK(h);
 }

@@ -10,7 +10,7 @@ import drs_b200
 crop = int(sys.argv[1]) if len(sys.argv) > 1 else 37
 net = sys.argv[2] if len(sys.argv) > 2 else "dilated_grsl"
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-B, C, K = 64, 4, 6
+B, C, K = int(os.environ.get("TL_B", "64")), int(os.environ.get("TL_C", "4")), 6
 s = drs_b200.Session(net, C, K, precision="bf16", seed=1)
 s.set_stream(torch.cuda.current_stream().cuda_stream)
 x = torch.randn(B * crop * crop * C, device="cuda")
