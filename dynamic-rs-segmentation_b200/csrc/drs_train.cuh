@@ -712,16 +712,25 @@ static void debug_layer_t(Handle* h, const float* z32, const float* dout32, int 
     LAUNCH_CHECK(h);
   }
   const TA* dA = G;
-  if (pool) {
-    launch_maxpool3_bwd<TA>(h, G, C, 0, idx, T, C, 0, C, B, crop);
-    dA = T;
-  }
   BnFinish finb{x->bn_acc, 1099511627776.0, x->bn_counter, x->sums, nullptr, nullptr, nullptr, nullptr, bn_count, 0.0f, 0.0f, 0};
-  bn_partial_kernel<TA, TA, 1><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z, C, 0, dA, C, 0, mean, istd, act, part_bn, C, M, bn_rows, finb);
-  LAUNCH_CHECK(h);
-  bn_bwd_apply_kernel<TA, TA><<<bne_grid(M, h->sm_count), BNE_THREADS, 0, h->stream>>>(Z, C, 0, dA, C, 0, mean, istd, x->sums, 1.0 / bn_count, act,
-                                                                                 DZ, C, 0, C, M);
-  LAUNCH_CHECK(h);
+  // the training step's path for a pooling layer in bf16: sums from the pooled side, then pool backward + BN backward fused
+  const bool fused = pool && ElemTag<TA>::v == ET_BF16 && pool_lean_enabled() && !getenv("DRS_NO_FUSED_POOL_APPLY");
+  if (fused) {
+    bn_partial_kernel<TA, TA, 2><<<nb_bn, BN_THREADS, 0, h->stream>>>(Xo, C, 0, G, C, 0, mean, istd, act, part_bn, C, M, bn_rows, finb);
+    LAUNCH_CHECK(h);
+    launch_maxpool3_bwd_apply(h, (const __nv_bfloat16*)G, C, 0, idx, (__nv_bfloat16*)DZ, C, 0, C, B, crop, (const __nv_bfloat16*)Z, mean, istd,
+                              x->sums, 1.0 / bn_count, act);
+  } else {
+    if (pool) {
+      launch_maxpool3_bwd<TA>(h, G, C, 0, idx, T, C, 0, C, B, crop);
+      dA = T;
+    }
+    bn_partial_kernel<TA, TA, 1><<<nb_bn, BN_THREADS, 0, h->stream>>>(Z, C, 0, dA, C, 0, mean, istd, act, part_bn, C, M, bn_rows, finb);
+    LAUNCH_CHECK(h);
+    bn_bwd_apply_kernel<TA, TA><<<bne_grid(M, h->sm_count), BNE_THREADS, 0, h->stream>>>(Z, C, 0, dA, C, 0, mean, istd, x->sums, 1.0 / bn_count, act,
+                                                                                   DZ, C, 0, C, M);
+    LAUNCH_CHECK(h);
+  }
   cast_kernel<TA, float><<<nblk(M * C, 256), 256, 0, h->stream>>>(Xo, out32, M * C);
   LAUNCH_CHECK(h);
   cast_kernel<TA, float><<<nblk(M * C, 256), 256, 0, h->stream>>>(DZ, dz32, M * C);

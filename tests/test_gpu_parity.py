@@ -6,10 +6,13 @@ Bars (BASELINE.json north_star):
   * DRS_PREC_F16 (tcgen05 kind::f16, 10-bit mantissa operands = the TF32 class): softmax probabilities within
     1e-3 abs;  DRS_PREC_BF16: within 1e-2 abs.
 """
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 NETS = (("dilated_icpr_original", 4, 6), ("dilated_grsl", 4, 6), ("dilated_icpr_rate6_densely", 5, 6),
         ("dilated_grsl_rate8", 5, 6), ("dilated_grsl", 3, 7), ("dilated_icpr_original", 3, 2),
@@ -582,12 +585,17 @@ def torch_layer(z, dout, pool, act):
     return a.detach().permute(0, 2, 3, 1).numpy(), zt.grad.permute(0, 2, 3, 1).numpy()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
-def test_layer_normalise_activate_pool_forward_and_backward(drs, prec):
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16-unfused"])
+def test_layer_normalise_activate_pool_forward_and_backward(drs, prec, monkeypatch):
     """The HBM-bound half of a layer on its own: train-mode BN + ReLU / LeakyReLU (+ max-pool) forward, pool backward by winner
     code, BN backward (two passes) -- the fp32 kernels and the separate packed-bf16 ones (maxpool3_fwd_train_bf16*,
     maxpool3_bwd_bf16, bn_*<bf16>).  Includes inputs quantised to a few levels, so that most pooling windows hold ties: the
-    gradient must go to the FIRST maximum in row-major window order (TF / the oracle), nowhere else."""
+    gradient must go to the FIRST maximum in row-major window order (TF / the oracle), nowhere else.
+    bf16 runs the step's path for pooling layers -- BN-backward sums from the pooled side (bn_partial MODE 2), then
+    pool_lean::bwd_apply_kernel (scatter + BN backward in one pass); "bf16-unfused" the three separate kernels."""
+    if prec == "bf16-unfused":
+        monkeypatch.setenv("DRS_NO_FUSED_POOL_APPLY", "1")
+        prec = "bf16"
     s = drs.Session("dilated_grsl", 4, 6, precision=prec)
     rs = np.random.RandomState(4)
     cases = [(2, 9, 64, 1, 2, False), (3, 13, 128, 1, 2, True), (1, 25, 256, 1, 2, False), (2, 12, 64, 0, 1, False),
@@ -912,6 +920,64 @@ def test_cuda_graph_replay_matches_eager(drs, monkeypatch):
         s.close()
     assert res[0][0] == res[1][0] and res[0][2] == res[1][2] == 5
     assert np.array_equal(res[0][1], res[1][1])
+
+
+def _step_fingerprints(env, net="dilated_grsl", crops="13,25", steps=3):
+    """sha1 of all variables after a few bf16 steps, per patch size, in a fresh process with `env` set (tools/step_hash.py)."""
+    import subprocess, sys
+    e = dict(os.environ)
+    e.update(env)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "step_hash.py"), net, crops, str(steps)], env=e, capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return [l.split("sha1 ")[1].split()[0] for l in out.stdout.splitlines() if "sha1 " in l]
+
+
+def test_launch_modes_do_not_change_a_bit():
+    """Programmatic dependent launch, CUDA graphs and the side-stream overlap only move kernels in time: the variables after
+    three steps are bit-identical with each of them switched off.  (Environment switches read once per process -> subprocesses.)"""
+    ref = _step_fingerprints({})
+    assert len(ref) == 2
+    for env in ({"DRS_NO_PDL": "1"}, {"DRS_GRAPHS": "0"}, {"DRS_NO_OVERLAP": "1"}, {"DRS_NO_PDL": "1", "DRS_GRAPHS": "0"}):
+        assert _step_fingerprints(env) == ref, env
+
+
+def test_lean_pool_kernels_equal_the_gather_kernels_bit_for_bit():
+    """The instruction-diet pool kernels (scatter backward, packed predicate compares) keep the summation order of the
+    gather kernels: same bits, compared on the unfused path (the fused pool+BN backward keeps the pool gradient in fp32)."""
+    a = _step_fingerprints({"DRS_NO_FUSED_POOL_APPLY": "1"})
+    b = _step_fingerprints({"DRS_NO_FUSED_POOL_APPLY": "1", "DRS_POOL_OLD": "1"})
+    assert a == b and len(a) == 2
+
+
+@pytest.mark.parametrize("net,env", [("dilated_icpr_rate6_densely", "DRS_NO_WGRAD_PAD"), ("dilated_icpr_rate6", "DRS_NO_WGRAD_CONV1_TC")])
+def test_fused_and_tensor_core_variants_agree_with_the_plain_kernels(drs, monkeypatch, net, env):
+    """Two round-2 filter-gradient paths replace CUDA-core kernels; each is compared with the kernel it replaces on the same
+    step of a net without pooling (pooling nets amplify 1e-7 differences to per cents), within 2e-3
+    relative L2 per variable:
+      32-channel filter gradients on the tensor-core kernel (run as 64)            vs  the CUDA-core kernel;
+      conv1's filter gradient through the bf16 im2col matrix on the tensor cores  vs  the fp32-input CUDA-core kernel.
+    (The fused pool backward + BN backward is checked per layer in test_layer_normalise_activate_pool_forward_and_backward.)"""
+    rs = np.random.RandomState(5)
+    B, C, K, crop = 8, 4, 6, 25
+    x = rs.randn(B, crop * crop * C).astype(np.float32)
+    y = rs.randint(0, K, size=(B, crop * crop)).astype(np.float32)
+    res = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv(env, "1")
+        else:
+            monkeypatch.delenv(env, raising=False)
+        s = drs.Session(net, C, K, precision="bf16", seed=3)
+        loss = float(s.train_step(x, y, crop)[0])
+        res.append((loss, {n: s.get_variable(n).copy() for n, _ in s.variable_names()}))
+        s.close()
+    assert abs(res[0][0] - res[1][0]) <= 1e-5 * max(1.0, abs(res[1][0]))            # same forward
+    for n in res[0][1]:
+        a, b = res[0][1][n].astype(np.float64), res[1][1][n].astype(np.float64)
+        den = np.linalg.norm(b)
+        if den > 0:
+            assert np.linalg.norm(a - b) / den < 2e-3, (n, np.linalg.norm(a - b) / den)
 
 
 def test_stripe_with_partial_scene_upload(drs):

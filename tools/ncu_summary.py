@@ -9,7 +9,8 @@ WANT = [("gpu__time_duration.sum", "dur"), ("dram__bytes_read.sum", "dram_rd"), 
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"), ("lts__t_sector_hit_rate.pct", "l2hit%"),
         ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"), ("lts__t_bytes.sum", "l2_bytes"),
         ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"), ("launch__registers_per_thread", "regs"),
-        ("launch__grid_size", "grid"), ("smsp__cycles_active.avg", "cyc")]
+        ("launch__grid_size", "grid"), ("smsp__cycles_active.avg", "cyc"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"), ("smsp__issue_active.avg.pct", "issue%")]
 
 
 def main(path):
