@@ -305,7 +305,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
   std::vector<char> grad_written(L, 0);        // squeeze: has the gradient buffer led by layer g been written in this step?
   {
     const int cvc = n.cls_in / 8;
-    if (cvc <= 256 && 256 % cvc == 0 && ElemTag<TA>::v != ET_F32 && !getenv("DRS_NO_CLS_REG")) {
+    if (cvc <= 256 && ElemTag<TA>::v != ET_F32 && !getenv("DRS_NO_CLS_REG")) {
       const int rows = 256 / cvc;
       // few, long-lived blocks: a thread first loads its 8 x K weights (48 scalar loads), which must be amortised
       static const int cls_bpsm = getenv("DRS_CLS_BPSM") ? atoi(getenv("DRS_CLS_BPSM")) : 2;

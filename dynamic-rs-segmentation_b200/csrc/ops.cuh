@@ -1007,8 +1007,8 @@ __global__ void classifier_bwd_data_kernel(const float* __restrict__ dl, const f
   }
 }
 
-// Same product with the thread's 8 x K weights in registers (256 % (Ci/8) == 0: a thread keeps its channel group for the
-// whole kernel): no shared-memory traffic in the loop -- the shared-memory version above is bound by its 12 LDS.128 per
+// Same product with the thread's 8 x K weights in registers (a thread keeps its channel group for the whole kernel; Ci/8 <= 256,
+// threads beyond the last whole row of channel groups retire): no shared-memory traffic in the loop -- the shared-memory version above is bound by its 12 LDS.128 per
 // 16 bytes written (measured 1 TB/s).  Two pixels per iteration.
 template <typename TG>
 __global__ void __launch_bounds__(256)
@@ -1018,6 +1018,7 @@ classifier_bwd_data_reg_kernel(const float* __restrict__ dl, const float* __rest
   const int cv = Ci >> 3;
   const int rows = 256 / cv;
   const int cg = threadIdx.x % cv, rl = threadIdx.x / cv;
+  if (rl >= rows) return;                  // cv does not divide 256 (DenseDilated6: 448 channels = 56 groups): spare threads
   float wr[8][MAX_CLASSES];
 #pragma unroll
   for (int e = 0; e < 8; ++e)
