@@ -26,6 +26,7 @@ struct Conv1TcParams {
   const float* scale;
   const float* shift;
   uint32_t* diag;
+  BnFinish stats;       // training forward: batch statistics of the rounded output reduced in the epilogue (acc == nullptr: off)
 };
 
 // W HWIO [5,5,ci,co] fp32 -> core-matrix order: out[((kc*(co/8) + n/8)*8 + n%8)*8 + c] = (kc < 25 && c < ci) ? W[kc][c][n] : 0
@@ -189,6 +190,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int as = 0;
     uint32_t aphase = 0;
     int sbuf = 0;
+    float st0 = 0.0f, st1 = 0.0f;          // this thread's (channel, row group) sums of z and z^2 (statistics mode)
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       ptx::mbar_wait(&tmem_full[as], aphase, p.diag, 0xC00 + as);
       ptx::tcgen05_fence_after();
@@ -221,6 +223,25 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           ptx::tma_store_2d(&tmC, stg + sbuf * STG_BYTES, p.out_coff + ch * EPI_C, tile * CONV_TC_BM);
           ptx::tma_store_commit();
         }
+        if (p.stats.acc) {
+          // column sums of the staged (already rounded) tile, as in conv_tc.cuh: thread = (channel, row group); EPI_C == Co
+          // here, so there is a single chunk and one register pair per thread
+          constexpr int ROWS = EPI_C;
+          const int c = epi_tid % EPI_C, grp = epi_tid / EPI_C;
+          const int rows_valid = min(CONV_TC_BM, p.M_total - tile * CONV_TC_BM);
+          const uint8_t* col = stg + sbuf * STG_BYTES + (c & 7) * 2;
+          const int c16 = c >> 3;
+          float a0 = 0.0f, a1 = 0.0f;
+          const int r_end = min(rows_valid, (grp + 1) * ROWS);
+          for (int r = grp * ROWS; r < r_end; ++r) {
+            const int swr = (EPI_C == 64) ? (r & 7) : ((r >> 1) & 3);
+            const float f = to_f32(*reinterpret_cast<const OutT*>(col + r * (EPI_C * 2) + ((c16 ^ swr) << 4)));
+            a0 += f;
+            a1 = fmaf(f, f, a1);
+          }
+          st0 += a0;
+          st1 += a1;
+        }
         sbuf ^= 1;
       }
       ptx::tcgen05_fence_before();
@@ -229,6 +250,53 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (warp == 4 && ptx::elect_one_sync()) ptx::tma_store_wait_all();
+    if (p.stats.acc) {
+      // CTA partial (row groups in fixed order) -> 64-bit fixed point -> integer atomics; the last CTA finalises (conv_tc.cuh)
+      constexpr int GROUPS = CONV_TC_BM / EPI_C;
+      float* s_stat = reinterpret_cast<float*>(stg);            // the staging buffers are free: every TMA store has drained
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      {
+        const int c = epi_tid % EPI_C, grp = epi_tid / EPI_C;
+        s_stat[(grp * 2) * p.co + c] = st0;
+        s_stat[(grp * 2 + 1) * p.co + c] = st1;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = epi_tid; i < 2 * p.co; i += 128) {
+        const int which = i / p.co, c = i - which * p.co;
+        float a = 0.0f;
+#pragma unroll
+        for (int g = 0; g < GROUPS; ++g) a += s_stat[(g * 2 + which) * p.co + c];
+        const long long q = __double2ll_rn((double)a * p.stats.fx_scale);
+        atomicAdd(bn_acc_mine(p.stats) + i, static_cast<unsigned long long>(q));
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      uint32_t* s_flag = reinterpret_cast<uint32_t*>(s_stat);
+      if (epi_tid == 0) *s_flag = (atomicAdd(p.stats.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*s_flag) {
+        __threadfence();
+        const double inv_scale = 1.0 / p.stats.fx_scale;
+        const int C = p.co;
+        for (int i = epi_tid; i < C; i += 128) {
+          const double a = (double)bn_acc_take(p.stats, i) * inv_scale;
+          const double b = (double)bn_acc_take(p.stats, C + i) * inv_scale;
+          p.stats.sums[i] = (float)a;
+          p.stats.sums[C + i] = (float)b;
+          if (p.stats.mean) {
+            const double mu = (double)(float)a / p.stats.count;
+            double var = (double)(float)b / p.stats.count - mu * mu;
+            if (var < 0.0) var = 0.0;
+            p.stats.mean[i] = (float)mu;
+            p.stats.inv_std[i] = (float)(1.0 / sqrt(var + (double)p.stats.eps));
+            const double var_ema = p.stats.unbiased_ema ? var * (p.stats.count / fmax(p.stats.count - 1.0, 1.0)) : var;
+            p.stats.mov_mean[i] = p.stats.decay * p.stats.mov_mean[i] + (1.0f - p.stats.decay) * (float)mu;
+            p.stats.mov_var[i] = p.stats.decay * p.stats.mov_var[i] + (1.0f - p.stats.decay) * (float)var_ema;
+          }
+        }
+        if (epi_tid == 0) *p.stats.counter = 0u;
+      }
+    }
   }
 
   ptx::tcgen05_fence_before();
@@ -248,6 +316,7 @@ struct Conv1TcArgs {
   const float* scale;
   const float* shift;
   int act, etype;
+  const BnFinish* stats = nullptr;     // training forward: fused batch statistics
 };
 
 template <int EPI_C, typename OutT>
@@ -265,6 +334,7 @@ static void launch_conv1_tc_t(Handle* h, const Conv1TcArgs& a) {
   p.act = a.act;
   p.idesc = make_idesc_f16(128, a.co, a.etype == ET_BF16, a.etype == ET_BF16, 0, 0);
   p.wpack = a.wpack; p.scale = a.scale; p.shift = a.shift; p.diag = h->diag_dev;
+  if (a.stats) p.stats = *a.stats; else memset(&p.stats, 0, sizeof(p.stats));
   const int b_bytes = ((a.co * C1_KP * 2) + 1023) & ~1023;
   const int fixed = b_bytes + 2 * CONV_TC_BM * EPI_C * 2 + 2 * 64 * 4 + (2 * 4 + 4) * 8 + 16;
   const int budget = 227 * 1024;
@@ -282,7 +352,7 @@ static void launch_conv1_tc_t(Handle* h, const Conv1TcArgs& a) {
     attr_set = true;
   }
   const int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
-  kern<<<grid, CONV_TC_THREADS, smem_bytes, h->stream>>>(tmA, tmC, p);
+  launch_pdl(h, kern, dim3(grid), dim3(CONV_TC_THREADS), (size_t)smem_bytes, tmA, tmC, p);
   LAUNCH_CHECK(h);
 }
 

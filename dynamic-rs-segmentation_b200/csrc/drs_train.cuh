@@ -172,7 +172,8 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
     float* istd = x->inv_std + c.mm_off;
     BnFinish fin{x->bn_acc, 1048576.0, x->bn_counter, x->sums, nullptr, nullptr, nullptr, nullptr, bn_count, h->cfg.bn_eps, h->cfg.bn_decay, h->cfg.bn_unbiased_ema};
     if (!h->sync_bn) { fin.mean = mean; fin.inv_std = istd; fin.mov_mean = h->bnstat + c.mm_off; fin.mov_var = h->bnstat + c.mv_off; }
-    const bool fused_stats = l > 0 && ElemTag<TA>::v != ET_F32 && !getenv("DRS_NO_FUSED_STATS");
+    const bool fused_stats = (l > 0 || (conv1_on_tc && !getenv("DRS_NO_FUSED_STATS_CONV1"))) && ElemTag<TA>::v != ET_F32 &&
+                             !getenv("DRS_NO_FUSED_STATS");
     if (l == 0 && conv1_on_tc) {
       // conv1 on the tensor cores as in inference (conv1_tc.cuh): input and filter rounded to bf16 like every other layer's
       // operands; the filter is re-packed every step (13 K elements).  The filter gradient keeps the fp32 input.
@@ -203,6 +204,7 @@ static void train_step_t(Handle* h, const float* x_dev, const float* y_dev, cons
       Conv1TcArgs a1;
       a1.x8 = x8; a1.wpack = c.w_fprop; a1.out = Z[l]; a1.out_cstride = c.co; a1.out_coff = 0; a1.co = c.co;
       a1.B = B; a1.crop = crop; a1.scale = x->ones; a1.shift = h->params + c.b_off; a1.act = ACT_NONE; a1.etype = ElemTag<TA>::v;
+      a1.stats = fused_stats ? &fin : nullptr;
       launch_conv1_tc(h, a1);
     } else if (l == 0) {
       launch_conv_simt<float, TA>(h, x_dev, n.channels, 0, n.channels, h->params + c.w_off, Z[l], c.co, 0, c.co, B, crop, c.k,
