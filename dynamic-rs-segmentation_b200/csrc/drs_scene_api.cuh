@@ -854,7 +854,9 @@ extern "C" int drs_debug_wgrad(drs_handle_t h, const float* x_host, const float*
     CUDA_CHECK(cudaMalloc(&x32, M * Ci * 4));
     CUDA_CHECK(cudaMalloc(&dy32, M * Co * 4));
     CUDA_CHECK(cudaMalloc(&dw, nw * 4));
-    CUDA_CHECK(cudaMalloc(&part, nw * 4 * max_splits));
+    // (the tensor-core kernel runs 32-channel operands as 64: its split partials have the padded shape)
+    const int64_t nw_pad = (int64_t)k * k * ((Ci + 63) / 64 * 64) * ((Co + 63) / 64 * 64);
+    CUDA_CHECK(cudaMalloc(&part, nw_pad * 4 * max_splits));
     CUDA_CHECK(cudaMemcpyAsync(x32, x_host, M * Ci * 4, cudaMemcpyHostToDevice, h->stream));
     CUDA_CHECK(cudaMemcpyAsync(dy32, dy_host, M * Co * 4, cudaMemcpyHostToDevice, h->stream));
     if (precision == DRS_PREC_FP32) {
@@ -870,7 +872,7 @@ extern "C" int drs_debug_wgrad(drs_handle_t h, const float* x_host, const float*
       wa.x = xa; wa.in_cstride = Ci; wa.in_coff = 0; wa.ci = Ci;
       wa.dy = dya; wa.dy_cstride = Co; wa.dy_coff = 0; wa.co = Co;
       wa.B = B; wa.crop = crop; wa.k = k; wa.rate = rate; wa.pad_b = pad_b;
-      wa.dw = dw; wa.part = part; wa.part_capacity = (size_t)nw * max_splits;
+      wa.dw = dw; wa.part = part; wa.part_capacity = (size_t)nw_pad * max_splits;
       launch_wgrad_tc(h, wa);
     }
     CUDA_CHECK(cudaMemcpyAsync(dw_host, dw, nw * 4, cudaMemcpyDeviceToHost, h->stream));

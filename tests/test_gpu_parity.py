@@ -435,7 +435,9 @@ def torch_wgrad(x, dy, k, rate):
 # pixel counts that are not multiples of the 64-pixel stage, asymmetric padding (k4 r3), dilation beyond the patch
 WGRAD_TC_CASES = [(2, 9, 3, 1, 64, 64), (3, 13, 5, 2, 64, 64), (2, 17, 4, 3, 64, 128), (2, 11, 4, 4, 128, 128),
                   (2, 25, 3, 5, 128, 256), (1, 25, 3, 6, 256, 256), (5, 7, 3, 8, 256, 256), (1, 33, 3, 5, 128, 192),
-                  (1, 30, 3, 7, 192, 256), (4, 25, 3, 6, 320, 128), (16, 25, 5, 1, 64, 64), (64, 25, 3, 4, 256, 256)]
+                  (1, 30, 3, 7, 192, 256), (4, 25, 3, 6, 320, 128), (16, 25, 5, 1, 64, 64), (64, 25, 3, 4, 256, 256),
+                  # 32-channel operands (DenseDilated6 conv2, the squeeze modules): run as 64, padding dropped by the reduce
+                  (2, 13, 5, 2, 32, 32), (3, 9, 4, 3, 32, 64), (2, 11, 3, 1, 64, 32), (16, 25, 5, 2, 32, 32), (2, 9, 1, 1, 32, 32)]
 
 
 def test_scene_confusion_on_device(drs):
