@@ -11,6 +11,6 @@ Import as ``import drs_b200`` (alias module at the repo root).  Layout:
   dist.py     one-process-per-GPU plumbing: stripe-sharded inference, data-parallel training
 """
 from . import lib, nets  # noqa: F401
-from .session import Session, grid_positions  # noqa: F401
+from .session import Session, grid_positions, npz_read, npz_write  # noqa: F401
 
-__all__ = ["Session", "grid_positions", "lib", "nets"]
+__all__ = ["Session", "grid_positions", "npz_read", "npz_write", "lib", "nets"]

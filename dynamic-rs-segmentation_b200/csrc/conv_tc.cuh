@@ -32,7 +32,9 @@ struct ConvTcParams {
   int ksize, rate, pad_b;
   int ci, in_coff;    // channels consumed, channel offset inside the input buffer
   int co, out_coff;   // N, channel offset inside the output buffer
-  int num_tiles;      // ceil(M_total / 128)
+  int num_tiles;      // ceil(M_total / 128): 128-pixel units
+  int mt;             // 1: every tile is one unit.  2 (Co <= 128): a tile is two consecutive units whose im2col tiles share ONE
+                      // filter slice per K block (two accumulators), see ConvSched
   int stages;         // smem pipeline depth
   int kps;            // K blocks (BLOCK_K channels of one tap) per pipeline stage: one barrier round trip per kps blocks
   int dual;           // experiment (off, see CONV_TC_DUAL_MAX_CO): two MMA-issuing warps, even / odd stages of a tile
@@ -69,10 +71,41 @@ __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Which 128-pixel units a CTA works on, in order.  mt == 1: unit = blockIdx.x + i * gridDim.x (the round-robin sweep: at
+// any moment the CTAs read neighbouring pixels, so the 9-25 re-fetches of an input pixel by the other taps hit L2).
+// mt == 2: the same sweep over PAIRS of consecutive units for as many full rounds as there are, and one last round that
+// hands the remaining units out as pairs and singles so that no CTA gets more than a pair (small-M training layers: 4.6
+// rounds of singles become 2 rounds of pairs + 1 of singles instead of 3 rounds of pairs).  Every role of the CTA
+// walks the same list.  The order in which a pixel's K blocks are accumulated never depends on the schedule.
+struct ConvSched {
+  int G, b, rounds, base, nd, iters, m2;
+  __device__ __forceinline__ ConvSched(int num_units, int mt) {
+    G = gridDim.x; b = blockIdx.x; m2 = mt == 2;
+    if (!m2) {
+      rounds = b < num_units ? (num_units - b + G - 1) / G : 0;
+      iters = rounds; base = 0; nd = 0;
+    } else {
+      rounds = num_units / (2 * G);
+      base = 2 * G * rounds;
+      const int r = num_units - base;
+      nd = r > G ? r - G : 0;                         // pairs in the last round (CTAs 0..nd-1); the others take a single
+      iters = rounds + ((r > G || b < r) ? 1 : 0);
+    }
+  }
+  // unit index of iteration i and whether it is a pair
+  __device__ __forceinline__ int unit(int i, bool& two) const {
+    if (!m2) { two = false; return b + i * G; }
+    if (i < rounds) { two = true; return (i * G + b) * 2; }
+    if (b < nd) { two = true; return base + 2 * b; }
+    two = false;
+    return base + nd + b;                             // == base + 2 * nd + (b - nd)
+  }
+};
+
 // BLOCK_K: channels per K step (64 -> 128B swizzle, 32 -> 64B swizzle).  EPI_C: channels per epilogue
 // store box (64 -> 128B swizzle, 32 -> 64B swizzle).
 template <int BLOCK_K, int EPI_C, typename OutT, bool INSTR>
-__global__ void __launch_bounds__(CONV_TC_THREADS, 1)
+__global__ void __launch_bounds__(CONV_TC_THREADS, EPI_C == 32 ? 2 : 1)   // the 32-channel epilogue runs two CTAs per SM: <= 128 registers
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const ConvTcParams p) {
   constexpr int A_BYTES = CONV_TC_BM * BLOCK_K * 2;
@@ -96,7 +129,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __trap();
   }
   const int B_BYTES = p.co * BLOCK_K * 2;
-  const int kb_bytes = A_BYTES + B_BYTES;                      // one K block: im2col tile + filter slice
+  const int a_bytes = p.mt * A_BYTES;                          // im2col tile(s) of one K block
+  const int kb_bytes = a_bytes + B_BYTES;                      // one K block: im2col tile(s) + filter slice
+  const ConvSched sched(p.num_tiles, p.mt);
   const int stage_bytes = p.kps * kb_bytes;
   uint8_t* stg = smem + p.stages * stage_bytes;                // 2 staging buffers (1024B aligned)
   float* s_scale = reinterpret_cast<float*>(stg + 2 * STG_BYTES);
@@ -173,14 +208,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t n_stage = 0;
     if (INSTR) t_begin = clock64();
     const int cc = p.crop * p.crop;
-    const uint32_t kb_tx = is_a ? A_BYTES : static_cast<uint32_t>(B_BYTES);
     const int w_end = p.ksize * p.rate;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int m0 = tile * CONV_TC_BM;
+    for (int it = 0; it < sched.iters; ++it) {
+      bool two;
+      const int m0 = sched.unit(it, two) * CONV_TC_BM;
+      const uint32_t kb_tx = is_a ? (two ? 2u * A_BYTES : static_cast<uint32_t>(A_BYTES)) : static_cast<uint32_t>(B_BYTES);
       const int n_img = m0 / cc;
       const int rem = m0 - n_img * cc;
       const int py = rem / p.crop;
       const int cw = rem - py * p.crop - p.pad_b, chh = py - p.pad_b;
+      // second unit of a pair
+      const int m1 = m0 + CONV_TC_BM;
+      const int n_img1 = m1 / cc;
+      const int rem1 = m1 - n_img1 * cc;
+      const int py1 = rem1 / p.crop;
+      const int cw1 = rem1 - py1 * p.crop - p.pad_b, chh1 = py1 - p.pad_b;
       int cb = p.in_coff, offw = 0, offh = 0, kcol = 0;   // channel block of the tap, tap offsets, filter-matrix column
       for (int kb0 = 0; kb0 < num_kb; kb0 += p.kps) {
         const int nk = min(p.kps, num_kb - kb0);
@@ -194,11 +236,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           else ptx::mbar_arrive_expect_tx_addr(fb, static_cast<uint32_t>(nk) * kb_tx);
         }
         if (INSTR) { t2 = clock64(); t_exp += t2 - t1; }
-        uint32_t dst = smem_base + soff + (is_a ? 0u : A_BYTES);
+        uint32_t dst = smem_base + soff + (is_a ? 0u : static_cast<uint32_t>(a_bytes));
         if (is_a) {
           for (int j = 0; j < nk; ++j, dst += kb_bytes) {
-            if (leader && !no_loads)
+            if (leader && !no_loads) {
               ptx::tma_load_im2col_4d_addr(dst, &tmA, fb, cb, cw, chh, n_img, static_cast<uint16_t>(offw), static_cast<uint16_t>(offh));
+              if (two)
+                ptx::tma_load_im2col_4d_addr(dst + A_BYTES, &tmA, fb, cb, cw1, chh1, n_img1, static_cast<uint16_t>(offw), static_cast<uint16_t>(offh));
+            }
             cb += BLOCK_K;
             if (cb == p.in_coff + p.ci) {
               cb = p.in_coff;
@@ -240,7 +285,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t desc_lo0 = ((smem_base >> 4) & 0x3FFFu) | (1u << 16);
       const uint32_t desc_hi = ((OP_SBO >> 4) & 0x3FFFu) | (1u << 14) | (OP_LAYOUT << 29);
       const uint32_t kb_step = static_cast<uint32_t>(kb_bytes) >> 4;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int acc_per_stage = p.dual ? 2 : p.mt;
+      for (int it = 0; it < sched.iters; ++it) {
+        bool two;
+        (void)sched.unit(it, two);
         if (INSTR) {
           const long long t0 = clock64();
           ptx::mbar_wait(&tmem_empty[as], aphase ^ 1, p.diag, 0x200 + as);
@@ -248,7 +296,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           ptx::mbar_wait(&tmem_empty[as], aphase ^ 1, p.diag, 0x200 + as);
         }
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((p.dual ? as * 2 + pipe : as) * p.acc_stride);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((as * acc_per_stage + (p.dual ? pipe : 0)) * p.acc_stride);
         uint32_t fresh = 0;                                  // 0 until this warp's first MMA of the tile (overwrites D)
         int g = 0;
         for (int kb0 = 0; kb0 < num_kb; kb0 += p.kps, ++g) {
@@ -262,7 +310,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (leader && !no_mma) {
               uint32_t a_lo = desc_lo0 + (soff >> 4);
               for (int j = 0; j < nk; ++j, a_lo += kb_step) {
-                ptx::umma_f16_kblock<BLOCK_K / 16>(d_tmem, a_lo, a_lo + (A_BYTES >> 4), desc_hi, p.idesc, fresh);
+                const uint32_t b_lo = a_lo + (static_cast<uint32_t>(a_bytes) >> 4);
+                ptx::umma_f16_kblock<BLOCK_K / 16>(d_tmem, a_lo, b_lo, desc_hi, p.idesc, fresh);
+                if (two)      // the pair's second unit: same filter slice, its own accumulator
+                  ptx::umma_f16_kblock<BLOCK_K / 16>(d_tmem + p.acc_stride, a_lo + (A_BYTES >> 4), b_lo, desc_hi, p.idesc, fresh);
                 fresh = 1;
               }
             }
@@ -301,11 +352,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float st0[STAT_MAX_CHUNKS], st1[STAT_MAX_CHUNKS];      // this thread's (channel, row group) sums, per output chunk
 #pragma unroll
     for (int q = 0; q < STAT_MAX_CHUNKS; ++q) { st0[q] = 0.0f; st1[q] = 0.0f; }
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int acc_per_stage = p.dual ? 2 : p.mt;
+    for (int it = 0; it < sched.iters; ++it) {
+      bool two;
+      const int unit0 = sched.unit(it, two);
       ptx::mbar_wait(&tmem_full[as], aphase, p.diag, 0x400 + as);
       ptx::tcgen05_fence_after();
+      for (int sub = 0; sub < (two ? 2 : 1); ++sub) {
+      const int tile = unit0 + sub;                // 128-pixel unit of this accumulator
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                             static_cast<uint32_t>((p.dual ? as * 2 : as) * p.acc_stride);
+                             static_cast<uint32_t>((as * acc_per_stage + sub) * p.acc_stride);
       for (int ch = 0; ch < ((p.exp_mode == 4 || p.exp_mode == 10) ? 0 : n_chunks); ++ch) {
         uint32_t v[EPI_C];
         ptx::tmem_ld_32x32b_x32(t_row + ch * EPI_C, v);
@@ -368,6 +424,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           (void)GROUPS;
         }
         sbuf ^= 1;
+      }
       }
       // all TMEM reads of this accumulator stage are complete (wait::ld above)
       ptx::tcgen05_fence_before();
@@ -536,6 +593,15 @@ static inline bool conv_tc_two_cta(int co) {
   return co <= (lim == 1 ? 64 : lim);
 }
 
+// Pairs of 128-pixel units on one filter slice (mt = 2) for Co <= this (DRS_CONV_M2=0 turns it off).  The Co <= 128 layers
+// are bound by the bytes an SM takes in per MMA (an im2col K block is 16 KB of A plus Co*128 B of B for 128*64*Co MACs);
+// two units per filter slice cut them from 24 to 20 KB per unit (Co = 64) and from 32 to 24 KB (Co = 128).  Needs
+// 4 * acc_stride <= 512 TMEM columns, hence not above 128.
+static inline int conv_tc_m2_max_co() {
+  static const int lim = getenv("DRS_CONV_M2") ? atoi(getenv("DRS_CONV_M2")) : 128;
+  return lim > 128 ? 128 : lim;
+}
+
 template <int BLOCK_K, int EPI_C, typename OutT>
 static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   alignas(64) CUtensorMap tmA, tmB, tmC;
@@ -575,7 +641,14 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   p.exp_mode = exp_mode;
   if (a.stats) p.stats = *a.stats; else memset(&p.stats, 0, sizeof(p.stats));
 
-  const int kb_bytes = CONV_TC_BM * BLOCK_K * 2 + a.co * BLOCK_K * 2;
+  const int dual_max_co = ((exp_word >> 18) & 1) ? 128 : CONV_TC_DUAL_MAX_CO;   // experiment bit 18: dual MMA warps for Co <= 128
+  const bool dual_wanted = a.co <= dual_max_co;
+  // experiment bits 20-21: 1 = force single units, 2 = force pairs (Co <= 128)
+  const int m2_force = (exp_word >> 20) & 3;
+  const int mt = (!dual_wanted && a.co <= 128 && M > CONV_TC_BM && (m2_force == 2 || (m2_force == 0 && a.co <= conv_tc_m2_max_co()))) ? 2 : 1;
+  if (mt == 2 && !((exp_word >> 12) & 0xf)) kps = 1;                 // a pair is already two im2col tiles per barrier round
+  if (kps > taps_kb) kps = taps_kb;
+  const int kb_bytes = mt * CONV_TC_BM * BLOCK_K * 2 + a.co * BLOCK_K * 2;
   const int fixed = 2 * CONV_TC_BM * EPI_C * 2 + 2 * 256 * 4 + (2 * 8 + 4) * 8 + 16;   // (statistics: registers, no smem)
   // Co <= 64: two CTAs per SM.  One CTA's two single-thread roles (TMA issue, MMA issue) need ~600 cycles per stage whatever
   // the layer, against 256 (N=64) / 512 (N=128) cycles of tensor work: a second resident CTA, with its own producers, issuer
@@ -588,13 +661,13 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   int stages = (budget - fixed) / stage_bytes;
   // at most 8 K blocks in flight: small layers then leave room for a second CTA on the SM (the filter-gradient kernel
   // of the side stream in training; without it a batch-64 crop-25 DenseDilated6 step is 20 % slower)
-  if (stages > 8 / kps) stages = std::max(2, 8 / kps);
+  if (stages > 8 / (kps * mt)) stages = std::max(2, 8 / (kps * mt));
   DRS_CHECK(stages >= 2, "conv_tc: tile does not fit shared memory (co=%d)", a.co);
   p.stages = stages;
   p.kps = kps;
-  const int dual_max_co = ((exp_word >> 18) & 1) ? 128 : CONV_TC_DUAL_MAX_CO;   // experiment bit 18: dual MMA warps for Co <= 128
-  p.dual = (a.co <= dual_max_co && (taps_kb + kps - 1) / kps >= 2) ? 1 : 0;
-  p.tmem_cols = (p.dual ? 4 : 2) * p.acc_stride;
+  p.dual = (dual_wanted && (taps_kb + kps - 1) / kps >= 2) ? 1 : 0;
+  p.mt = mt;
+  p.tmem_cols = (p.dual ? 4 : 2 * mt) * p.acc_stride;
   p.smem_needed = fixed + stages * stage_bytes;
   const int smem_bytes = p.smem_needed + 1024 <= budget ? p.smem_needed + 1024 : budget;
   p.smem_provided = smem_bytes;

@@ -9,6 +9,7 @@
 #include "scene.cuh"
 #include "wgrad_tc.cuh"
 #include "conv1_tc.cuh"
+#include "npz_io.h"
 
 thread_local char g_drs_err[1024] = {0};
 
@@ -557,6 +558,132 @@ extern "C" int drs_get_gradient(drs_handle_t h, const char* name, float* data, i
   API_END
 }
 
+// ------------------------------------------------------------------------------------------------
+// checkpoints: tf.train.Saver.save / restore (isprs:1693-1717, 1797-1802) as an uncompressed .npz keyed by the TF variable
+// names ('/' written as '__', which is what numpy.savez keyword arguments allow), shapes as TF holds them (HWIO filters)
+// ------------------------------------------------------------------------------------------------
+static std::vector<int64_t> var_shape(Handle* h, const std::string& full, int64_t count) {
+  std::string name = full;
+  const std::string mom = "/Momentum";
+  if (name.size() > mom.size() && name.compare(name.size() - mom.size(), mom.size(), mom) == 0) name.resize(name.size() - mom.size());
+  for (auto& c : h->net.convs)
+    if (name == c.scope + "/weights") return {c.k, c.k, c.ci, c.co};
+  for (auto& sb : h->net.se) {
+    if (name == sb.name + "_fc1/weights") return {sb.c, sb.r};
+    if (name == sb.name + "_fc2/weights") return {sb.r, sb.c};
+  }
+  if (name == "conv_classifier/weights") return {1, 1, h->net.cls_in, h->net.classes};
+  return {count};
+}
+static std::string npz_key(std::string name) {
+  for (size_t i = 0; (i = name.find('/', i)) != std::string::npos;) name.replace(i, 1, "__");
+  return name;
+}
+static std::string npz_unkey(std::string key) {
+  for (size_t i = 0; (i = key.find("__", i)) != std::string::npos; ++i) key.replace(i, 2, "/");
+  return key;
+}
+
+extern "C" int drs_save(drs_handle_t h, const char* path) {
+  API_BEGIN
+  DRS_CHECK(h && path, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  std::vector<std::pair<std::string, int64_t>> v;
+  list_vars(h, v);
+  std::vector<drs_npz::Array> arrays(v.size());
+  for (size_t i = 0; i < v.size(); ++i) {
+    VarRef r;
+    DRS_CHECK(find_var(h, v[i].first, r), "unknown variable '%s'", v[i].first.c_str());
+    arrays[i].name = npz_key(v[i].first);
+    arrays[i].shape = var_shape(h, v[i].first, r.count);
+    arrays[i].data.resize((size_t)r.count);
+    if (r.kind == 1) arrays[i].data[0] = (float)h->global_step;
+    else CUDA_CHECK(cudaMemcpyAsync(arrays[i].data.data(), r.ptr, r.count * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  const std::string e = drs_npz::write(path, arrays);
+  DRS_CHECK(e.empty(), "%s", e.c_str());
+  API_END
+}
+
+extern "C" int drs_load(drs_handle_t h, const char* path) {
+  API_BEGIN
+  DRS_CHECK(h && path, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  std::vector<drs_npz::Array> arrays;
+  const std::string e = drs_npz::read(path, arrays);
+  DRS_CHECK(e.empty(), "%s", e.c_str());
+  // validate everything before touching the model: a checkpoint of another net must not be applied half-way
+  for (auto& a : arrays) {
+    VarRef r;
+    const std::string name = npz_unkey(a.name);
+    DRS_CHECK(find_var(h, name, r), "checkpoint '%s': unknown variable '%s'", path, name.c_str());
+    DRS_CHECK(r.count == a.count(), "checkpoint '%s': variable '%s' has %lld elements, the model expects %lld", path, name.c_str(),
+              (long long)a.count(), (long long)r.count);
+  }
+  for (auto& a : arrays) {
+    VarRef r;
+    find_var(h, npz_unkey(a.name), r);
+    if (r.kind == 1) { h->global_step = (int64_t)a.data[0]; continue; }
+    CUDA_CHECK(cudaMemcpyAsync(r.ptr, a.data.data(), r.count * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));      // the host arrays die with this scope
+  h->packed_dirty = true;
+  h->eval_dirty = true;
+  API_END
+}
+
+// the container alone, no handle and no device: inspection / conversion tools and the CPU tests
+extern "C" int drs_npz_write(const char* path, int32_t n, const char* const* names, const float* const* data, const int32_t* ndim,
+                             const int64_t* dims) {
+  API_BEGIN
+  DRS_CHECK(path && n >= 0 && (n == 0 || (names && data && ndim && dims)), "bad argument");
+  std::vector<drs_npz::Array> arrays((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    DRS_CHECK(names[i] && data[i] && ndim[i] >= 0 && ndim[i] <= 4, "array %d: bad argument", i);
+    arrays[i].name = names[i];
+    arrays[i].shape.assign(dims + 4 * i, dims + 4 * i + ndim[i]);
+    for (int64_t d : arrays[i].shape) DRS_CHECK(d >= 0, "array %d: negative dimension", i);
+    arrays[i].data.assign(data[i], data[i] + arrays[i].count());
+  }
+  const std::string e = drs_npz::write(path, arrays);
+  DRS_CHECK(e.empty(), "%s", e.c_str());
+  API_END
+}
+extern "C" int drs_npz_entry(const char* path, int32_t index, char* name_out, int32_t name_cap, int32_t* ndim_out, int64_t* dims_out,
+                             int64_t* count_out, int32_t* total_out) {
+  API_BEGIN
+  DRS_CHECK(path, "null argument");
+  std::vector<drs_npz::Array> arrays;
+  const std::string e = drs_npz::read(path, arrays);
+  DRS_CHECK(e.empty(), "%s", e.c_str());
+  if (total_out) *total_out = (int32_t)arrays.size();
+  if (index < 0) return 0;                                  // count only
+  DRS_CHECK(index < (int)arrays.size(), "entry %d out of range (%d arrays)", index, (int)arrays.size());
+  const drs_npz::Array& a = arrays[index];
+  DRS_CHECK(a.shape.size() <= 4, "array '%s' has %d dimensions", a.name.c_str(), (int)a.shape.size());
+  if (name_out && name_cap > 0) snprintf(name_out, name_cap, "%s", a.name.c_str());
+  if (ndim_out) *ndim_out = (int32_t)a.shape.size();
+  if (dims_out) for (size_t i = 0; i < a.shape.size(); ++i) dims_out[i] = a.shape[i];
+  if (count_out) *count_out = a.count();
+  API_END
+}
+extern "C" int drs_npz_read(const char* path, const char* name, float* out, int64_t count) {
+  API_BEGIN
+  DRS_CHECK(path && name && out, "null argument");
+  std::vector<drs_npz::Array> arrays;
+  const std::string e = drs_npz::read(path, arrays);
+  DRS_CHECK(e.empty(), "%s", e.c_str());
+  for (auto& a : arrays)
+    if (a.name == name) {
+      DRS_CHECK(a.count() == count, "array '%s' has %lld elements, got room for %lld", name, (long long)a.count(), (long long)count);
+      memcpy(out, a.data.data(), (size_t)count * 4);
+      return 0;
+    }
+  DRS_FAIL("checkpoint '%s' has no array '%s'", path, name);
+  API_END
+}
+
 extern "C" int drs_set_ignore_label(drs_handle_t h, int32_t label) {
   API_BEGIN
   DRS_CHECK(h, "null handle");
@@ -809,7 +936,12 @@ static void forward_eval_t(Handle* h, const float* x_dev, int B, int crop, float
       run_conv<TA>(h, cur, c.ci, h->params + c.w_off, c.w_fprop, out, c.co, B, crop, c.k, c.rate, c.pad_b, c.fold_scale,
                    c.fold_shift, n.act);
     }
-    if (n.pool) {
+    if (n.pool && l + 1 == n.convs.size() && c.co == n.cls_in && pool_classifier_fused_supported<TA>(c.co)) {
+      // last layer: pool + classifier in one pass, the pooled activations are never stored (no activation tap for this layer)
+      launch_maxpool3_classifier<TA>(h, (const TA*)out.p, out.cs, out.co, c.co, B, crop, h->params + n.cls_w_off,
+                                     h->params + n.cls_b_off, n.classes, logits, pred_dev);
+      return;
+    } else if (n.pool) {
       ActBuf pout{bufs[(xi + 2) % 3], fs, 0};
       launch_maxpool3_fwd<TA>(h, (const TA*)out.p, out.cs, out.co, (TA*)pout.p, pout.cs, pout.co, nullptr, c.co, B, crop);
       cur = pout;

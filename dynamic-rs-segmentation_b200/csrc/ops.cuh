@@ -971,6 +971,168 @@ static void launch_classifier_fwd(Handle* h, const T* x, int x_cs, int x_co, int
   else launch_classifier_fwd_t<T, 128>(h, x, x_cs, x_co, Ci, w, b, K, logits, pred, M, smem_of(128));
 }
 
+// Inference: the LAST 3x3 max-pool and the classifier (1x1 convolution Ci -> K, isprs:779-786) in one pass.  The pooled
+// activations of the last layer feed nothing but the classifier, so they are neither written nor read back: the kernel
+// reads the last convolution's output once (M*Ci*2 B) and writes M*K logits.  Same thread layout as
+// maxpool3_fwd_packed_kernel -- a thread owns (image, row segment, column, 8 channels) and walks down its rows -- so the
+// CV = Ci/8 lanes that hold one pixel are neighbours in a warp: each lane multiplies its 8 pooled channels (exactly the
+// values the unfused kernel would have stored) with its 8 x K weights held in registers, and the K partial sums are combined
+// by a transposing butterfly (4 + 2 + 1 shuffles halve the number of classes a lane carries, the remaining steps add one
+// value), after which the lanes with (lane % (CV/8)) == 0 hold one class each.  The order of the additions is the same for
+// every pixel wherever it sits, so patch-wise and scene-wise inference and every stripe agree bit for bit.
+// One row of the 3-wide horizontal maximum, as raw loads (consumed one iteration later: the next row's loads are in flight
+// while the current pixel goes through its FMAs and shuffles).
+template <typename T>
+struct PoolRowRaw { Vec8<T> c, l, r; };
+template <typename T>
+__device__ __forceinline__ void pool_row_load(const T* __restrict__ centre, int lo, int ro, PoolRowRaw<T>& v) {
+  v.c = *reinterpret_cast<const Vec8<T>*>(centre);
+  v.l = *reinterpret_cast<const Vec8<T>*>(centre + lo);          // image border: lo / ro == 0, the centre again
+  v.r = *reinterpret_cast<const Vec8<T>*>(centre + ro);
+}
+template <typename T>
+__device__ __forceinline__ Vec8<T> pool_row_reduce(const PoolRowRaw<T>& v) {
+  Vec8<T> o = v.c;
+  vmax8(o, v.l);
+  vmax8(o, v.r);
+  return o;
+}
+
+template <typename T, int CV, int KC>
+__global__ void __launch_bounds__(256)
+maxpool3_classifier_kernel(const T* __restrict__ in, int in_cs, int in_co, int B, int crop, int seg, int nseg,
+                           const float* __restrict__ w, const float* __restrict__ bias, int K, float* __restrict__ logits,
+                           uint8_t* __restrict__ pred) {
+  static_assert(CV == 8 || CV == 16 || CV == 32, "Ci must be 64, 128 or 256");
+  static_assert(KC <= 8, "the butterfly below carries 8 classes");
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)B * nseg * crop * CV) return;              // whole groups of CV lanes leave together
+  const int lane = threadIdx.x & 31;
+  const unsigned gmask = CV == 32 ? 0xffffffffu : (((1u << CV) - 1u) << (lane & ~(CV - 1)));
+  const int g = lane & (CV - 1);
+  const int cg = (int)(gid % CV);
+  int64_t t = gid / CV;
+  const int x = (int)(t % crop);
+  t /= crop;
+  const int sg = (int)(t % nseg);
+  const int b = (int)(t / nseg);
+  const int y0 = sg * seg, y1 = min(crop, y0 + seg);
+  const int64_t img0 = (int64_t)b * crop * crop;
+  const T* inp = in + in_co + cg * 8;
+  float wr[8][KC];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int k = 0; k < KC; ++k) wr[e][k] = k < K ? w[(cg * 8 + e) * K + k] : 0.0f;
+  const bool up0 = (g & (CV / 2)) != 0, up1 = (g & (CV / 4)) != 0, up2 = (g & (CV / 8)) != 0;
+  const int cls = (up0 ? 4 : 0) + (up1 ? 2 : 0) + (up2 ? 1 : 0);
+  const bool writer = (g & (CV / 8 - 1)) == 0 && cls < K;
+  const float my_bias = cls < K ? bias[cls] : 0.0f;
+  // running pointers: one add per row instead of 64-bit index arithmetic per load
+  const int lo = x > 0 ? -in_cs : 0, ro = x + 1 < crop ? in_cs : 0;
+  const int64_t rs = (int64_t)crop * in_cs;
+  const T* q = inp + (img0 + (int64_t)y0 * crop + x) * in_cs;     // centre of the next row to load
+  float* lp = logits + (img0 + (int64_t)y0 * crop + x) * K + cls;
+  uint8_t* pp = pred ? pred + img0 + (int64_t)y0 * crop + x : nullptr;
+  PoolRowRaw<T> nxt;
+  Vec8<T> r0, r1;
+  bool v0 = y0 > 0;
+  if (v0) { pool_row_load<T>(q - rs, lo, ro, nxt); r0 = pool_row_reduce<T>(nxt); }
+  pool_row_load<T>(q, lo, ro, nxt);
+  r1 = pool_row_reduce<T>(nxt);
+  q += rs;
+  bool vn = y0 + 1 < crop;
+  if (vn) pool_row_load<T>(q, lo, ro, nxt);
+  for (int y = y0; y < y1; ++y) {
+    const bool v2 = vn;
+    Vec8<T> r2;
+    if (v2) r2 = pool_row_reduce<T>(nxt);
+    q += rs;
+    vn = y + 2 < crop && y + 1 < y1;                               // the row the NEXT iteration needs below its centre
+    if (vn) pool_row_load<T>(q, lo, ro, nxt);
+    Vec8<T> o = r1;
+    if (v0) vmax8(o, r0);
+    if (v2) vmax8(o, r2);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float f = to_f32(o.v[e]);
+#pragma unroll
+      for (int k = 0; k < KC; ++k) acc[k] = fmaf(f, wr[e][k], acc[k]);
+    }
+    // 8 -> 4 classes per lane
+    float a4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up0 ? acc[i] : acc[i + 4];
+      const float keep = up0 ? acc[i + 4] : acc[i];
+      a4[i] = keep + __shfl_xor_sync(gmask, send, CV / 2);
+    }
+    float a2[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up1 ? a4[i] : a4[i + 2];
+      const float keep = up1 ? a4[i + 2] : a4[i];
+      a2[i] = keep + __shfl_xor_sync(gmask, send, CV / 4);
+    }
+    float v;
+    {
+      const float send = up2 ? a2[0] : a2[1];
+      const float keep = up2 ? a2[1] : a2[0];
+      v = keep + __shfl_xor_sync(gmask, send, CV / 8);
+    }
+#pragma unroll
+    for (int off = CV / 16; off >= 1; off >>= 1) v += __shfl_xor_sync(gmask, v, off);
+    v += my_bias;
+    if (writer) *lp = v;
+    lp += crop * K;
+    if (pp) {
+      // first maximum over the classes (Appendix B.7): the smaller index wins a tie
+      float bv = cls < K ? v : -INFINITY;
+      int bi = cls;
+#pragma unroll
+      for (int off = CV / 2; off >= CV / 8; off >>= 1) {
+        const float ov = __shfl_xor_sync(gmask, bv, off);
+        const int oi = __shfl_xor_sync(gmask, bi, off);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (g == 0) *pp = (uint8_t)bi;
+      pp += crop;
+    }
+    r0 = r1; v0 = true;
+    r1 = r2;
+  }
+}
+
+static inline bool pool_classifier_fused_enabled() {
+  static const bool on = !getenv("DRS_NO_POOL_CLS_FUSE");
+  return on;
+}
+template <typename T>
+static inline bool pool_classifier_fused_supported(int Ci) {
+  return ElemTag<T>::v != ET_F32 && (Ci == 64 || Ci == 128 || Ci == 256) && pool_classifier_fused_enabled();
+}
+template <typename T>
+static void launch_maxpool3_classifier(Handle* h, const T* in, int in_cs, int in_co, int Ci, int B, int crop, const float* w,
+                                       const float* b, int K, float* logits, uint8_t* pred) {
+  DRS_CHECK(K <= MAX_CLASSES, "classifier: K=%d exceeds %d", K, MAX_CLASSES);
+  const int64_t base = (int64_t)B * crop * (Ci / 8);
+  int nseg = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div((int64_t)h->sm_count * 2048, base)), std::max(1, crop / 4));
+  const int seg = (int)ceil_div(crop, nseg);
+  nseg = (int)ceil_div(crop, seg);
+  const unsigned nb = (unsigned)ceil_div(base * nseg, 256);
+#define DRS_PCLS(CVV, KCC) maxpool3_classifier_kernel<T, CVV, KCC><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, B, crop, seg, nseg, w, b, K, logits, pred)
+#define DRS_PCLS_K(CVV) do { if (K <= 2) DRS_PCLS(CVV, 2); else if (K <= 6) DRS_PCLS(CVV, 6); else DRS_PCLS(CVV, 8); } while (0)
+  if (Ci == 256) DRS_PCLS_K(32);
+  else if (Ci == 128) DRS_PCLS_K(16);
+  else DRS_PCLS_K(8);
+#undef DRS_PCLS_K
+#undef DRS_PCLS
+  LAUNCH_CHECK(h);
+}
+
 // dX[m][c] = sum_k dl[m][k] * W[c][k].  Weights are kept transposed in shared memory ([k][Ci]) so that a warp's
 // 16-byte reads of 8 consecutive channels per lane are contiguous (no bank conflicts).
 template <typename TG>

@@ -65,6 +65,12 @@ _SIGNATURES = {
     "drs_set_variable": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
     "drs_get_variable": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
     "drs_get_gradient": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
+    "drs_save": (C.c_int, [_P, C.c_char_p]),
+    "drs_load": (C.c_int, [_P, C.c_char_p]),
+    "drs_npz_write": (C.c_int, [C.c_char_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "drs_npz_entry": (C.c_int, [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64),
+                                C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "drs_npz_read": (C.c_int, [C.c_char_p, C.c_char_p, _P, C.c_int64]),
     "drs_forward_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "drs_forward_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "drs_train_step_host": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P, _P]),

@@ -117,13 +117,19 @@ class Session:
         return out
 
     def save(self, path):
-        """saver.save(sess, output_path + 'model', global_step=step) (isprs:1798): one .npz keyed by TF names."""
-        np.savez(path, **{k.replace("/", "__"): v for k, v in self.variables().items()})
+        """saver.save(sess, output_path + 'model', global_step=step) (isprs:1798): one uncompressed .npz keyed by the TF
+        variable names, written by the library (drs_save: temp file + rename).  Returns the file name."""
+        path = str(path)
+        if not path.endswith(".npz"):
+            path += ".npz"                    # what numpy.savez would have appended
+        L.check(self._lib.drs_save(self._h, path.encode()))
+        return path
 
     def restore(self, path):
-        with np.load(path if str(path).endswith(".npz") else str(path) + ".npz") as z:
-            for k in z.files:
-                self.set_variable(k.replace("__", "/"), z[k])
+        """saver.restore(sess, model_path) (isprs:1715): every array of the .npz is validated against the model, then applied
+        (drs_load).  Files written by numpy.savez load as well."""
+        path = str(path)
+        L.check(self._lib.drs_load(self._h, (path if path.endswith(".npz") else path + ".npz").encode()))
 
     @property
     def global_step(self):
@@ -421,6 +427,42 @@ class Session:
         dw = np.empty((k, k, ci, co), dtype=np.float32)
         L.check(self._lib.drs_debug_wgrad(self._h, L.ptr(x), L.ptr(dy), B, crop, k, rate, ci, co, L.PREC[precision], L.ptr(dw)))
         return dw
+
+
+def npz_write(path, arrays):
+    """The library's checkpoint container without a session (drs_npz_write): ``arrays`` maps member names to arrays of
+    up to four dimensions; stored as float32.  numpy.load reads the result."""
+    lib = L.load()
+    names = [k.encode() for k in arrays]
+    vals = [np.asarray(v, dtype=np.float32, order="C") for v in arrays.values()]
+    n = len(names)
+    dims = np.zeros((max(n, 1), 4), dtype=np.int64)
+    ndim = np.zeros(max(n, 1), dtype=np.int32)
+    for i, v in enumerate(vals):
+        if v.ndim > 4:
+            raise ValueError("at most four dimensions")
+        ndim[i] = v.ndim
+        dims[i, :v.ndim] = v.shape
+    L.check(lib.drs_npz_write(str(path).encode(), n, (C.c_char_p * max(n, 1))(*names),
+                              (C.c_void_p * max(n, 1))(*[v.ctypes.data for v in vals]),
+                              ndim.ctypes.data_as(C.POINTER(C.c_int32)), dims.ctypes.data_as(C.POINTER(C.c_int64))))
+
+
+def npz_read(path):
+    """Every array of a stored .npz as float32, in archive order (drs_npz_entry / drs_npz_read)."""
+    lib = L.load()
+    total = C.c_int32()
+    L.check(lib.drs_npz_entry(str(path).encode(), -1, None, 0, None, None, None, C.byref(total)))
+    out = {}
+    buf = C.create_string_buffer(512)
+    nd, cnt = C.c_int32(), C.c_int64()
+    dims = (C.c_int64 * 4)()
+    for i in range(total.value):
+        L.check(lib.drs_npz_entry(str(path).encode(), i, buf, 512, C.byref(nd), dims, C.byref(cnt), None))
+        a = np.empty(cnt.value, dtype=np.float32)
+        L.check(lib.drs_npz_read(str(path).encode(), buf.value, L.ptr(a), cnt.value))
+        out[buf.value.decode()] = a.reshape([dims[j] for j in range(nd.value)])
+    return out
 
 
 def grid_positions(H, W, crop, batch, variant="isprs"):

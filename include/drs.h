@@ -98,6 +98,28 @@ int drs_get_variable(drs_handle_t h, const char* name, float* data_host, int64_t
 /* gradient of the last train step w.r.t. a trainable variable (parity tests) */
 int drs_get_gradient(drs_handle_t h, const char* name, float* data_host, int64_t count);
 
+/* ---- checkpoints: saver.save(sess, output_path + 'model', global_step=step) (isprs:1797-1802) and
+ * saver.restore(sess, model_path) (isprs:1693-1717; contest:1035-1056; coffee:1233-1262) ------------------------------- */
+/* One uncompressed .npz (what numpy.savez writes, numpy.load reads): a float32 array per variable of drs_variable_name(),
+ * named by the TF variable with '/' written as "__" ("conv1__weights", "conv1__weights__Momentum", "conv1__moving_mean",
+ * "global_step"), filters in TF's HWIO shape, so that a TF checkpoint can be converted with tf.train.load_variable +
+ * numpy.savez alone.  drs_save writes "<path>.tmp.<pid>" and renames it over <path> (a reader never sees half a file);
+ * drs_load validates every member against the model (names, element counts, CRC-32) before it changes anything, accepts
+ * float32 / float64 / int32 / int64 payloads, any subset of the variables, and refuses compressed archives.
+ * Restoring and continuing is bit-identical to not having stopped (tests/test_gpu_parity.py). */
+int drs_save(drs_handle_t h, const char* path);
+int drs_load(drs_handle_t h, const char* path);
+/* The container without a handle or a device (inspection / conversion tools, CPU tests).
+ *   drs_npz_write: n arrays; names[i] is the member name without ".npy"; dims is n x 4 (the first ndim[i] entries used).
+ *   drs_npz_entry: *total_out = number of arrays; index < 0 asks for the count only; otherwise name / shape / element count
+ *                  of the index-th array in archive order.
+ *   drs_npz_read:  the named array converted to float32 into out[count]. */
+int drs_npz_write(const char* path, int32_t n, const char* const* names, const float* const* data, const int32_t* ndim,
+                  const int64_t* dims);
+int drs_npz_entry(const char* path, int32_t index, char* name_out, int32_t name_cap, int32_t* ndim_out, int64_t* dims_out,
+                  int64_t* count_out, int32_t* total_out);
+int drs_npz_read(const char* path, const char* name, float* out, int64_t count);
+
 /* ---- compute seam: sess.run ---------------------------------------------------------- */
 /* infer:  sess.run([pred_up, logits], is_training=False)   isprs:1274-1275, contest:929-931, coffee:1058-1059
  *   x       [B, crop*crop*C] fp32 (row-major NHWC, isprs:763)

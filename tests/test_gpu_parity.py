@@ -905,6 +905,32 @@ def test_checkpoint_round_trip_continues_bit_identically(drs, tmp_path, net, pre
     assert set(va) == set(vc)
     for k in va:
         assert np.array_equal(va[k], vc[k]), k
+    # the file the library wrote (drs_save) is a plain .npz: NumPy reads it, TF names and HWIO shapes included ...
+    with np.load(str(tmp_path / "model-3.npz")) as z:
+        saved = {k.replace("__", "/"): z[k] for k in z.files}
+    assert set(saved) == set(va) and saved["global_step"].tolist() == [3.0]
+    assert all(saved[k].dtype == np.float32 and saved[k].shape == va[k].shape for k in va), "shapes as TF holds them"
+    # ... and a file NumPy wrote (ZIP64 local headers, a float64 member, a subset of the variables) restores through drs_load
+    sub = {k.replace("/", "__"): v for k, v in va.items() if not k.endswith("/Momentum")}
+    sub["global_step"] = np.array([6], dtype=np.int64)
+    bias_name = next(k for k in va if k.endswith("/biases"))              # scope names differ between the nets
+    filt_name = next(k for k in va if k.endswith("/weights"))
+    sub[bias_name.replace("/", "__")] = va[bias_name].astype(np.float64)
+    np.savez(str(tmp_path / "from_numpy.npz"), **sub)
+    d = drs.Session(net, C, K, seed=77, **kw)
+    d.restore(str(tmp_path / "from_numpy"))
+    vd = d.variables()
+    assert d.global_step == 6
+    for k in va:
+        if not k.endswith("/Momentum"):
+            assert np.array_equal(va[k], vd[k]), k
+    # a checkpoint of another net is refused before anything is applied
+    np.savez(str(tmp_path / "wrong.npz"), **{bias_name.replace("/", "__"): np.zeros_like(va[bias_name]),
+                                             filt_name.replace("/", "__"): np.zeros((5, 5, C, 8), np.float32)})
+    with pytest.raises(drs.lib.DrsError, match=filt_name + ".*elements"):
+        d.restore(str(tmp_path / "wrong.npz"))
+    assert np.array_equal(d.get_variable(bias_name), vd[bias_name].ravel()), "nothing may be applied from a refused file"
+    d.close()
 
 
 def test_cuda_graph_replay_matches_eager(drs, monkeypatch):

@@ -17,14 +17,16 @@ DENSE = [("d2", 5, 1, 32, 32), ("d3", 4, 2, 64, 64), ("d4", 4, 2, 128, 64), ("d5
 
 
 def word(spec):
-    """'-1' production default; otherwise tokens m<mode> k<K blocks per stage> i1 (instrumented) s1 (dual MMA warps, experiment), e.g. k2 or k2m10i1."""
+    """'-1' production default; otherwise tokens m<mode> k<K blocks per stage> i1 (instrumented) s1 (dual MMA warps, experiment)
+    p1 / p2 (force single 128-pixel units / pairs of units per filter slice), e.g. k2 or k2m10i1 or p1."""
     import re
     if re.fullmatch(r"-?\d+", spec):
         return int(spec)
     w = 0
-    for key, val in re.findall(r"([mkis])(\d+)", spec):
+    for key, val in re.findall(r"([mkisp])(\d+)", spec):
         val = int(val)
-        w |= val if key == "m" else (val << 12 if key == "k" else ((val & 1) << 16 if key == "i" else (val & 1) << 18))
+        w |= val if key == "m" else (val << 12 if key == "k" else ((val & 1) << 16 if key == "i" else
+                                      ((val & 3) << 20 if key == "p" else (val & 1) << 18)))
     return w
 
 
