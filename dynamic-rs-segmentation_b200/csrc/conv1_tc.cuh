@@ -81,7 +81,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler (see conv_tc.cuh)
   const int lane = threadIdx.x & 31;
 
   pdl_sync();      // the packed weights below are written by the kernel right in front of this one

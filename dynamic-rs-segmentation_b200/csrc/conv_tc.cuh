@@ -148,7 +148,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int STAT_GROUPS = CONV_TC_BM / EPI_C;
   constexpr int STAT_MAX_CHUNKS = 256 / EPI_C;
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, role branches become uniform branches and the
+  // descriptor / address arithmetic of the single-thread roles runs on the uniform datapath (no R2UR moves per UTMALDG / UTCHMMA)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int taps = p.ksize * p.ksize;
   const int kb_per_tap = p.ci / BLOCK_K;

@@ -67,7 +67,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler (see conv_tc.cuh)
   const int lane = threadIdx.x & 31;
   const int n_items = p.n_groups * p.splits;
   const int cb_per_tap = p.ci / 64;
