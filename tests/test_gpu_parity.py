@@ -80,6 +80,36 @@ def test_single_convolution(drs, prec):
     s.close()
 
 
+def test_paired_tiles_equal_single_tiles_bit_for_bit(drs, monkeypatch):
+    """conv_tc hands 128-pixel units out as pairs on one filter slice for Co <= 128 (ConvSched): full rounds of pairs, then
+    one mixed round of pairs and singles.  The accumulation order of a pixel does not depend on the schedule, so forcing
+    single units (DRS_EXP_MODE bits 20-21 = 1) must reproduce the paired result exactly -- for unit counts U below the CTA
+    count G (singles only), between G and 2G (mixed round only), 2G*R + r with r <= G, with r > G, and r == 0, with one CTA
+    per SM (Co = 128, G = 148) and two (Co <= 64, G = 296), and a last unit that is only partly inside the tensor."""
+    s = drs.Session("dilated_grsl", 4, 6, precision="bf16")
+    rs = np.random.RandomState(5)
+    cases = [(3, 25, 3, 2, 64, 128), (41, 25, 3, 2, 64, 128), (71, 25, 4, 3, 64, 128), (102, 25, 3, 1, 64, 128),
+             (148, 16, 3, 2, 64, 128), (102, 25, 3, 2, 64, 64), (148, 16, 5, 1, 64, 64), (250, 25, 3, 1, 32, 32),
+             (64, 37, 3, 4, 128, 128)]
+    for n, (B, crop, k, rate, ci, co) in enumerate(cases):
+        x = rs.randn(B, crop, crop, ci).astype(np.float32)
+        w = (rs.randn(k, k, ci, co) / np.sqrt(k * k * ci)).astype(np.float32)
+        scale = (0.5 + rs.rand(co)).astype(np.float32)
+        shift = (rs.randn(co) * 0.1).astype(np.float32)
+        monkeypatch.setenv("DRS_EXP_MODE", str(1 << 20))
+        y_single = s.debug_conv(x, w, scale, shift, rate, 2, "bf16")
+        monkeypatch.setenv("DRS_EXP_MODE", str(2 << 20))
+        y_pair = s.debug_conv(x, w, scale, shift, rate, 2, "bf16")
+        monkeypatch.delenv("DRS_EXP_MODE")
+        y_default = s.debug_conv(x, w, scale, shift, rate, 2, "bf16")
+        assert np.array_equal(y_single, y_pair), (B, crop, k, rate, ci, co)
+        assert np.array_equal(y_default, y_pair), (B, crop, k, rate, ci, co)
+        if n in (1, 5):      # and the result is the convolution (every tile written, none twice with other data)
+            ref = act_np(torch_conv(rounded(x, "bf16"), rounded(w, "bf16"), rate) * scale + shift, 2)
+            assert np.abs(y_pair - ref).max() < 3e-2, (B, crop, k, rate, ci, co)
+    s.close()
+
+
 @pytest.mark.parametrize("net,C,K", NETS)
 def test_network_inference_vs_oracle(drs, net, C, K):
     """sess.run([pred_up, logits], is_training=False) (isprs:1274-1275) with non-trivial moving statistics."""

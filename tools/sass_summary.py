@@ -6,7 +6,7 @@ lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "dynamic-rs-segme
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 GROUPS = [("UTCHMMA", r"^UTC[HQ]?MMA"), ("UTMALDG.IM2COL", r"^UTMALDG.*IM2COL"), ("UTMALDG (tiled)", r"^UTMALDG(?!.*IM2COL)"),
           ("UTMASTG", r"^UTMASTG"), ("LDTM", r"^LDTM"), ("UTCBAR (commit)", r"^UTCBAR"), ("SYNCS (mbarrier)", r"^SYNCS"),
-          ("ELECT", r"^ELECT"), ("ATOM/RED .64", r"^(ATOMG|REDG|RED|ATOM).*64"), ("HMNMX2/HSET2 (packed bf16)", r"^(HMNMX2|HSET2)"),
+          ("ELECT", r"^ELECT"), ("R2UR (vector -> uniform register moves)", r"^R2UR"), ("ATOM/RED .64", r"^(ATOMG|REDG|RED|ATOM).*64"), ("HMNMX2/HSET2 (packed bf16)", r"^(HMNMX2|HSET2)"),
           ("HSETP2 (packed code compare)", r"^HSETP2"), ("ACQBULK/PDL (griddepcontrol)", r"^(ACQBULK|PREEXIT|DEPBAR\.LE SB0)")]
 names, cur = [], None
 counts = {}
