@@ -167,6 +167,75 @@ maxpool3_fwd_packed_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __
   }
 }
 
+// Two columns per thread, next row's loads in flight (default; DRS_POOL_INFER=1 selects the one-column kernel above).  The one-column kernel above is
+// latency-bound on its reads: a thread has one row of loads outstanding and two of its three 16-byte loads hit L1 (the
+// neighbours' centres), so only 16 unique bytes per thread are on their way from DRAM at any time.  Here a thread owns
+// columns (x0, x0+1): four loads per row for two outputs (x0-1, x0, x0+1, x0+2), three packed maxima for the two horizontal
+// results (the centre pair's maximum is shared), and the loads of row y+2 are issued before row y+1 is reduced.
+// Measured: the seven pools of a 0.76 M-pixel Dilated8Pooling chunk 722 -> ~600 us (5.2 TB/s of read + write traffic, 80 % of
+// the measured HBM peak), the scene pass -3 % (profiles/r2c_conv_pairs_uniform_ab.txt, section 7).  Same bits: max is exact.
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool3_fwd_packed2_kernel(const T* __restrict__ in, int in_cs, int in_co, T* __restrict__ out, int out_cs, int out_co, int C,
+                            int B, int crop, int seg, int nseg) {
+  const int cv = C >> 3;
+  const int xp_n = (crop + 1) >> 1;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)B * nseg * xp_n * cv) return;
+  const int cg = (int)(gid % cv);
+  int64_t t = gid / cv;
+  const int x0 = (int)(t % xp_n) * 2;
+  t /= xp_n;
+  const int sg = (int)(t % nseg);
+  const int b = (int)(t / nseg);
+  const int y0 = sg * seg, y1 = min(crop, y0 + seg);
+  const bool has1 = x0 + 1 < crop;
+  // element offsets of the four columns relative to the centre x0 (missing neighbours point at a valid column: max is idempotent)
+  const int o_l = x0 > 0 ? -in_cs : 0;
+  const int o_1 = has1 ? in_cs : 0;
+  const int o_r = x0 + 2 < crop ? 2 * in_cs : o_1;
+  const int64_t rs = (int64_t)crop * in_cs;
+  const T* q = in + in_co + cg * 8 + ((int64_t)b * crop * crop + (int64_t)y0 * crop + x0) * in_cs;   // centre of the next row to load
+  T* po = out + out_co + cg * 8 + ((int64_t)b * crop * crop + (int64_t)y0 * crop + x0) * out_cs;
+  const int64_t os = (int64_t)crop * out_cs;
+  Vec8<T> nl, n0, n1, nr;                      // raw loads of the next row
+  Vec8<T> a0, a1, b0, b1, c0, c1;              // horizontal maxima of rows y-1, y, y+1 for the two columns
+  auto load = [&](const T* c) {
+    n0 = *reinterpret_cast<const Vec8<T>*>(c);
+    nl = *reinterpret_cast<const Vec8<T>*>(c + o_l);
+    n1 = *reinterpret_cast<const Vec8<T>*>(c + o_1);
+    nr = *reinterpret_cast<const Vec8<T>*>(c + o_r);
+  };
+  auto reduce = [&](Vec8<T>& h0, Vec8<T>& h1) {
+    Vec8<T> m = n0;
+    vmax8(m, n1);
+    h0 = m; vmax8(h0, nl);
+    h1 = m; vmax8(h1, nr);
+  };
+  bool va = y0 > 0;
+  if (va) { load(q - rs); reduce(a0, a1); }
+  load(q);
+  reduce(b0, b1);
+  q += rs;
+  bool vn = y0 + 1 < crop;
+  if (vn) load(q);
+  for (int y = y0; y < y1; ++y) {
+    const bool vc = vn;
+    if (vc) reduce(c0, c1);
+    q += rs;
+    vn = y + 2 < crop && y + 1 < y1;
+    if (vn) load(q);
+    Vec8<T> r0 = b0, r1 = b1;
+    if (va) { vmax8(r0, a0); vmax8(r1, a1); }
+    if (vc) { vmax8(r0, c0); vmax8(r1, c1); }
+    *reinterpret_cast<Vec8<T>*>(po) = r0;
+    if (has1) *reinterpret_cast<Vec8<T>*>(po + out_cs) = r1;
+    po += os;
+    a0 = b0; a1 = b1; va = true;
+    b0 = c0; b1 = c1;
+  }
+}
+
 // Training variant for bf16 (winner codes + fused normalise/activation) on packed 2-wide compare / max / select: a third
 // of the instructions of the scalar float version, same first-maximum semantics (strictly-greater replaces, row-major).
 __device__ __forceinline__ void pool_pk_row(const __nv_bfloat16* __restrict__ in, int in_cs, int64_t pix_row0, int x, int crop,
@@ -525,7 +594,18 @@ static void launch_maxpool3_fwd(Handle* h, const T* in, int in_cs, int in_co, T*
   else if (idx && bn_mean) maxpool3_fwd_kernel<T, true, true><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, idx, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
   else if (idx) maxpool3_fwd_kernel<T, true, false><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, idx, C, B, crop, seg, nseg, nullptr, nullptr, 0);
   else if (bn_mean) maxpool3_fwd_kernel<T, false, true><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, nullptr, C, B, crop, seg, nseg, bn_mean, bn_inv_std, act);
-  else maxpool3_fwd_packed_kernel<T><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, C, B, crop, seg, nseg);
+  else {
+    static const int variant = getenv("DRS_POOL_INFER") ? atoi(getenv("DRS_POOL_INFER")) : 2;   // 1: one column per thread
+    if (variant == 2) {
+      const int64_t base2 = (int64_t)B * ((crop + 1) / 2) * (C / 8);
+      int nseg2 = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div((int64_t)h->sm_count * 2048, base2)), std::max(1, crop / 4));
+      const int seg2 = (int)ceil_div(crop, nseg2);
+      nseg2 = (int)ceil_div(crop, seg2);
+      maxpool3_fwd_packed2_kernel<T><<<(unsigned)ceil_div(base2 * nseg2, 256), 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, C, B, crop, seg2, nseg2);
+    } else {
+      maxpool3_fwd_packed_kernel<T><<<nb, 256, 0, h->stream>>>(in, in_cs, in_co, out, out_cs, out_co, C, B, crop, seg, nseg);
+    }
+  }
   LAUNCH_CHECK(h);
 }
 
