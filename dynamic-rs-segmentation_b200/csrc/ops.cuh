@@ -1060,45 +1060,67 @@ static void launch_classifier_fwd(Handle* h, const T* x, int x_cs, int x_co, int
 // by a transposing butterfly (4 + 2 + 1 shuffles halve the number of classes a lane carries, the remaining steps add one
 // value), after which the lanes with (lane % (CV/8)) == 0 hold one class each.  The order of the additions is the same for
 // every pixel wherever it sits, so patch-wise and scene-wise inference and every stripe agree bit for bit.
-// One row of the 3-wide horizontal maximum, as raw loads (consumed one iteration later: the next row's loads are in flight
-// while the current pixel goes through its FMAs and shuffles).
-template <typename T>
-struct PoolRowRaw { Vec8<T> c, l, r; };
-template <typename T>
-__device__ __forceinline__ void pool_row_load(const T* __restrict__ centre, int lo, int ro, PoolRowRaw<T>& v) {
-  v.c = *reinterpret_cast<const Vec8<T>*>(centre);
-  v.l = *reinterpret_cast<const Vec8<T>*>(centre + lo);          // image border: lo / ro == 0, the centre again
-  v.r = *reinterpret_cast<const Vec8<T>*>(centre + ro);
+// K partial class sums per lane -> one class per lane (see the kernel's header comment); every lane of the CV-lane group calls it
+template <int CV>
+__device__ __forceinline__ float cls_butterfly(const float (&acc)[8], unsigned gmask, bool up0, bool up1, bool up2) {
+  float a4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = up0 ? acc[i] : acc[i + 4];
+    const float keep = up0 ? acc[i + 4] : acc[i];
+    a4[i] = keep + __shfl_xor_sync(gmask, send, CV / 2);
+  }
+  float a2[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = up1 ? a4[i] : a4[i + 2];
+    const float keep = up1 ? a4[i + 2] : a4[i];
+    a2[i] = keep + __shfl_xor_sync(gmask, send, CV / 4);
+  }
+  const float send = up2 ? a2[0] : a2[1];
+  const float keep = up2 ? a2[1] : a2[0];
+  float v = keep + __shfl_xor_sync(gmask, send, CV / 8);
+#pragma unroll
+  for (int off = CV / 16; off >= 1; off >>= 1) v += __shfl_xor_sync(gmask, v, off);
+  return v;
 }
-template <typename T>
-__device__ __forceinline__ Vec8<T> pool_row_reduce(const PoolRowRaw<T>& v) {
-  Vec8<T> o = v.c;
-  vmax8(o, v.l);
-  vmax8(o, v.r);
-  return o;
+// first maximum over the classes (Appendix B.7): the smaller index wins a tie; result valid in every lane of the group
+template <int CV>
+__device__ __forceinline__ int cls_argmax(float v, int cls, int K, unsigned gmask) {
+  float bv = cls < K ? v : -INFINITY;
+  int bi = cls;
+#pragma unroll
+  for (int off = CV / 2; off >= CV / 8; off >>= 1) {
+    const float ov = __shfl_xor_sync(gmask, bv, off);
+    const int oi = __shfl_xor_sync(gmask, bi, off);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  return bi;
 }
 
+// Two columns per thread like maxpool3_fwd_packed2_kernel (the reads are latency-bound: what counts is how many unique bytes
+// a thread has on their way), the 8 x K weights in registers serve both pixels.
 template <typename T, int CV, int KC>
 __global__ void __launch_bounds__(256)
 maxpool3_classifier_kernel(const T* __restrict__ in, int in_cs, int in_co, int B, int crop, int seg, int nseg,
                            const float* __restrict__ w, const float* __restrict__ bias, int K, float* __restrict__ logits,
                            uint8_t* __restrict__ pred) {
   static_assert(CV == 8 || CV == 16 || CV == 32, "Ci must be 64, 128 or 256");
-  static_assert(KC <= 8, "the butterfly below carries 8 classes");
+  static_assert(KC <= 8, "the butterfly carries 8 classes");
+  const int xp_n = (crop + 1) >> 1;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (int64_t)B * nseg * crop * CV) return;              // whole groups of CV lanes leave together
+  if (gid >= (int64_t)B * nseg * xp_n * CV) return;              // whole groups of CV lanes leave together
   const int lane = threadIdx.x & 31;
   const unsigned gmask = CV == 32 ? 0xffffffffu : (((1u << CV) - 1u) << (lane & ~(CV - 1)));
   const int g = lane & (CV - 1);
   const int cg = (int)(gid % CV);
   int64_t t = gid / CV;
-  const int x = (int)(t % crop);
-  t /= crop;
+  const int x0 = (int)(t % xp_n) * 2;
+  t /= xp_n;
   const int sg = (int)(t % nseg);
   const int b = (int)(t / nseg);
   const int y0 = sg * seg, y1 = min(crop, y0 + seg);
-  const int64_t img0 = (int64_t)b * crop * crop;
-  const T* inp = in + in_co + cg * 8;
+  const bool has1 = x0 + 1 < crop;
   float wr[8][KC];
 #pragma unroll
   for (int e = 0; e < 8; ++e)
@@ -1108,81 +1130,70 @@ maxpool3_classifier_kernel(const T* __restrict__ in, int in_cs, int in_co, int B
   const int cls = (up0 ? 4 : 0) + (up1 ? 2 : 0) + (up2 ? 1 : 0);
   const bool writer = (g & (CV / 8 - 1)) == 0 && cls < K;
   const float my_bias = cls < K ? bias[cls] : 0.0f;
-  // running pointers: one add per row instead of 64-bit index arithmetic per load
-  const int lo = x > 0 ? -in_cs : 0, ro = x + 1 < crop ? in_cs : 0;
+  const int o_l = x0 > 0 ? -in_cs : 0;
+  const int o_1 = has1 ? in_cs : 0;
+  const int o_r = x0 + 2 < crop ? 2 * in_cs : o_1;
   const int64_t rs = (int64_t)crop * in_cs;
-  const T* q = inp + (img0 + (int64_t)y0 * crop + x) * in_cs;     // centre of the next row to load
-  float* lp = logits + (img0 + (int64_t)y0 * crop + x) * K + cls;
-  uint8_t* pp = pred ? pred + img0 + (int64_t)y0 * crop + x : nullptr;
-  PoolRowRaw<T> nxt;
-  Vec8<T> r0, r1;
-  bool v0 = y0 > 0;
-  if (v0) { pool_row_load<T>(q - rs, lo, ro, nxt); r0 = pool_row_reduce<T>(nxt); }
-  pool_row_load<T>(q, lo, ro, nxt);
-  r1 = pool_row_reduce<T>(nxt);
+  const int64_t pix0 = (int64_t)b * crop * crop + (int64_t)y0 * crop + x0;
+  const T* q = in + in_co + cg * 8 + pix0 * in_cs;               // centre of the next row to load
+  float* lp = logits + pix0 * K + cls;
+  uint8_t* pp = pred ? pred + pix0 : nullptr;
+  Vec8<T> nl, n0, n1, nr;                      // raw loads of the next row
+  Vec8<T> a0, a1, b0, b1, c0, c1;              // horizontal maxima of rows y-1, y, y+1 for the two columns
+  auto load = [&](const T* c) {
+    n0 = *reinterpret_cast<const Vec8<T>*>(c);
+    nl = *reinterpret_cast<const Vec8<T>*>(c + o_l);
+    n1 = *reinterpret_cast<const Vec8<T>*>(c + o_1);
+    nr = *reinterpret_cast<const Vec8<T>*>(c + o_r);
+  };
+  auto reduce = [&](Vec8<T>& h0, Vec8<T>& h1) {
+    Vec8<T> m = n0;
+    vmax8(m, n1);
+    h0 = m; vmax8(h0, nl);
+    h1 = m; vmax8(h1, nr);
+  };
+  bool va = y0 > 0;
+  if (va) { load(q - rs); reduce(a0, a1); }
+  load(q);
+  reduce(b0, b1);
   q += rs;
   bool vn = y0 + 1 < crop;
-  if (vn) pool_row_load<T>(q, lo, ro, nxt);
+  if (vn) load(q);
   for (int y = y0; y < y1; ++y) {
-    const bool v2 = vn;
-    Vec8<T> r2;
-    if (v2) r2 = pool_row_reduce<T>(nxt);
+    const bool vc = vn;
+    if (vc) reduce(c0, c1);
     q += rs;
-    vn = y + 2 < crop && y + 1 < y1;                               // the row the NEXT iteration needs below its centre
-    if (vn) pool_row_load<T>(q, lo, ro, nxt);
-    Vec8<T> o = r1;
-    if (v0) vmax8(o, r0);
-    if (v2) vmax8(o, r2);
-    float acc[8];
+    vn = y + 2 < crop && y + 1 < y1;
+    if (vn) load(q);
+    Vec8<T> r0 = b0, r1 = b1;
+    if (va) { vmax8(r0, a0); vmax8(r1, a1); }
+    if (vc) { vmax8(r0, c0); vmax8(r1, c1); }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+    for (int px = 0; px < 2; ++px) {
+      // (the second column of an odd-width image's last pair computes on a copy of the first and stores nothing;
+      //  the shuffles need every lane of the group either way)
+      const Vec8<T>& o = px == 0 ? r0 : r1;
+      float acc[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float f = to_f32(o.v[e]);
+      for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
 #pragma unroll
-      for (int k = 0; k < KC; ++k) acc[k] = fmaf(f, wr[e][k], acc[k]);
-    }
-    // 8 -> 4 classes per lane
-    float a4[4];
+      for (int e = 0; e < 8; ++e) {
+        const float f = to_f32(o.v[e]);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float send = up0 ? acc[i] : acc[i + 4];
-      const float keep = up0 ? acc[i + 4] : acc[i];
-      a4[i] = keep + __shfl_xor_sync(gmask, send, CV / 2);
-    }
-    float a2[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float send = up1 ? a4[i] : a4[i + 2];
-      const float keep = up1 ? a4[i + 2] : a4[i];
-      a2[i] = keep + __shfl_xor_sync(gmask, send, CV / 4);
-    }
-    float v;
-    {
-      const float send = up2 ? a2[0] : a2[1];
-      const float keep = up2 ? a2[1] : a2[0];
-      v = keep + __shfl_xor_sync(gmask, send, CV / 8);
-    }
-#pragma unroll
-    for (int off = CV / 16; off >= 1; off >>= 1) v += __shfl_xor_sync(gmask, v, off);
-    v += my_bias;
-    if (writer) *lp = v;
-    lp += crop * K;
-    if (pp) {
-      // first maximum over the classes (Appendix B.7): the smaller index wins a tie
-      float bv = cls < K ? v : -INFINITY;
-      int bi = cls;
-#pragma unroll
-      for (int off = CV / 2; off >= CV / 8; off >>= 1) {
-        const float ov = __shfl_xor_sync(gmask, bv, off);
-        const int oi = __shfl_xor_sync(gmask, bi, off);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        for (int k = 0; k < KC; ++k) acc[k] = fmaf(f, wr[e][k], acc[k]);
       }
-      if (g == 0) *pp = (uint8_t)bi;
-      pp += crop;
+      const float v = cls_butterfly<CV>(acc, gmask, up0, up1, up2) + my_bias;
+      const bool live = px == 0 || has1;
+      if (writer && live) lp[px * K] = v;
+      if (pp) {
+        const int bi = cls_argmax<CV>(v, cls, K, gmask);
+        if (g == 0 && live) pp[px] = (uint8_t)bi;
+      }
     }
-    r0 = r1; v0 = true;
-    r1 = r2;
+    lp += crop * K;
+    if (pp) pp += crop;
+    a0 = b0; a1 = b1; va = true;
+    b0 = c0; b1 = c1;
   }
 }
 
@@ -1198,7 +1209,7 @@ template <typename T>
 static void launch_maxpool3_classifier(Handle* h, const T* in, int in_cs, int in_co, int Ci, int B, int crop, const float* w,
                                        const float* b, int K, float* logits, uint8_t* pred) {
   DRS_CHECK(K <= MAX_CLASSES, "classifier: K=%d exceeds %d", K, MAX_CLASSES);
-  const int64_t base = (int64_t)B * crop * (Ci / 8);
+  const int64_t base = (int64_t)B * ((crop + 1) / 2) * (Ci / 8);       // a thread owns two columns
   int nseg = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div((int64_t)h->sm_count * 2048, base)), std::max(1, crop / 4));
   const int seg = (int)ceil_div(crop, nseg);
   nseg = (int)ceil_div(crop, seg);
