@@ -124,11 +124,12 @@ class ClockSampler:
 
 def profiled_traffic(which):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
-    try:
-        return float(json.load(open(p))[which]["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    for name in ("r2c_traffic.json", "r2_traffic.json"):          # newest capture first
+        try:
+            return float(json.load(open(os.path.join(ROOT, "profiles", name)))[which]["dram_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 def dist_env():
