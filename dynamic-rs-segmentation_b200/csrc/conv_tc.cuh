@@ -79,8 +79,9 @@ __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
 // walks the same list.  The order in which a pixel's K blocks are accumulated never depends on the schedule.
 struct ConvSched {
   int G, b, rounds, base, nd, iters, m2;
-  __device__ __forceinline__ ConvSched(int num_units, int mt) {
-    G = gridDim.x; b = blockIdx.x; m2 = mt == 2;
+  // (grid, block) = (gridDim.x, blockIdx.x) in the kernel; host-callable so that tests/test_abi.py can enumerate the schedule
+  __host__ __device__ __forceinline__ ConvSched(int num_units, int mt, int grid, int block) {
+    G = grid; b = block; m2 = mt == 2;
     if (!m2) {
       rounds = b < num_units ? (num_units - b + G - 1) / G : 0;
       iters = rounds; base = 0; nd = 0;
@@ -93,7 +94,7 @@ struct ConvSched {
     }
   }
   // unit index of iteration i and whether it is a pair
-  __device__ __forceinline__ int unit(int i, bool& two) const {
+  __host__ __device__ __forceinline__ int unit(int i, bool& two) const {
     if (!m2) { two = false; return b + i * G; }
     if (i < rounds) { two = true; return (i * G + b) * 2; }
     if (b < nd) { two = true; return base + 2 * b; }
@@ -131,7 +132,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int B_BYTES = p.co * BLOCK_K * 2;
   const int a_bytes = p.mt * A_BYTES;                          // im2col tile(s) of one K block
   const int kb_bytes = a_bytes + B_BYTES;                      // one K block: im2col tile(s) + filter slice
-  const ConvSched sched(p.num_tiles, p.mt);
+  const ConvSched sched(p.num_tiles, p.mt, (int)gridDim.x, (int)blockIdx.x);
   const int stage_bytes = p.kps * kb_bytes;
   uint8_t* stg = smem + p.stages * stage_bytes;                // 2 staging buffers (1024B aligned)
   float* s_scale = reinterpret_cast<float*>(stg + 2 * STG_BYTES);

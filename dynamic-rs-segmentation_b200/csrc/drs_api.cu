@@ -684,6 +684,22 @@ extern "C" int drs_npz_read(const char* path, const char* name, float* out, int6
   API_END
 }
 
+// host-only: the units CTA `block` of a `grid`-CTA conv_tc launch works on, in order (ConvSched is the kernel's own code)
+extern "C" int drs_debug_conv_schedule(int32_t num_units, int32_t mt, int32_t grid, int32_t block, int32_t* units_out,
+                                       uint8_t* pair_out, int32_t cap, int32_t* n_out) {
+  API_BEGIN
+  DRS_CHECK(num_units >= 0 && (mt == 1 || mt == 2) && grid >= 1 && block >= 0 && block < grid && n_out, "bad argument");
+  const ConvSched sc(num_units, mt, grid, block);
+  *n_out = sc.iters;
+  for (int i = 0; i < sc.iters && i < cap; ++i) {
+    bool two;
+    const int u = sc.unit(i, two);
+    if (units_out) units_out[i] = u;
+    if (pair_out) pair_out[i] = two ? 1 : 0;
+  }
+  API_END
+}
+
 extern "C" int drs_set_ignore_label(drs_handle_t h, int32_t label) {
   API_BEGIN
   DRS_CHECK(h, "null handle");

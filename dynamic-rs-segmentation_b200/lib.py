@@ -118,6 +118,7 @@ _SIGNATURES = {
                                  C.c_int32, C.POINTER(C.c_float), _P]),
     "drs_debug_dgrad": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "drs_debug_layer": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "drs_debug_conv_schedule": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "drs_debug_wgrad": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
 }
 EXPORTS = sorted(_SIGNATURES)

@@ -350,6 +350,11 @@ int drs_bench_conv(drs_handle_t h, int32_t B, int32_t crop, int32_t k, int32_t r
  *   precision BF16: tcgen05 MN-major path (operands rounded to bf16); FP32: CUDA-core fixed-order path. */
 int drs_debug_wgrad(drs_handle_t h, const float* x_host, const float* dy_host, int32_t B, int32_t crop, int32_t k,
                     int32_t rate, int32_t Ci, int32_t Co, int32_t precision, float* dw_host);
+/* host-only: the schedule of conv_tc_kernel (csrc/conv_tc.cuh, ConvSched): the 128-pixel units CTA `block` of a `grid`-CTA
+ * launch over `num_units` units works on, in order; pair_out[i] = 1 when unit i is the first of a pair of consecutive
+ * units that share one filter slice (mt = 2, Co <= 128).  *n_out = number of entries (may exceed cap). */
+int drs_debug_conv_schedule(int32_t num_units, int32_t mt, int32_t grid, int32_t block, int32_t* units_out, uint8_t* pair_out,
+                            int32_t cap, int32_t* n_out);
 
 /* unit-test entry: data gradient of one dilated SAME convolution exactly as the step computes it (a convolution of dy
  * with tap-flipped, Ci/Co-transposed weights and the before/after padding swapped):
