@@ -76,3 +76,31 @@ def test_refusals(drs, tmp_path):
         drs.npz_read(str(tmp_path / "bad.npz"))
     with pytest.raises(lib.DrsError, match="cannot create"):
         drs.npz_write(str(tmp_path / "no_such_dir" / "x.npz"), {"a": np.zeros(1, np.float32)})
+
+
+def test_tf_checkpoint_converter_names_and_layout(drs, tmp_path):
+    """tools/tf_checkpoint_to_npz.py on a stand-in checkpoint reader (TensorFlow is not installable here): names as the
+    reference's graphs create them (isprs:655-723, 1685) map onto the library's keys, foreign variables are skipped, the
+    file round-trips through the library's container."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("tfconv", os.path.join(root, "tools", "tf_checkpoint_to_npz.py"))
+    tfconv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tfconv)
+    assert tfconv.npz_key("conv1/weights:0") == "conv1__weights"
+    assert tfconv.npz_key("main_conv3/biases/Momentum") == "main_conv3__biases__Momentum"
+    assert tfconv.npz_key("conv6/moving_variance") == "conv6__moving_variance"
+    assert tfconv.npz_key("se1_fc2/weights/Momentum") == "se1_fc2__weights__Momentum"
+    assert tfconv.npz_key("main_global_step") == "global_step"
+    assert tfconv.npz_key("beta1_power") is None and tfconv.npz_key("save/Const") is None
+    rs = np.random.RandomState(1)
+    fake = {"conv1/weights": rs.randn(5, 5, 4, 64).astype(np.float32), "conv1/weights/Momentum": rs.randn(5, 5, 4, 64).astype(np.float32),
+            "conv1/biases": np.full(64, 0.1, np.float32), "conv1/moving_mean": rs.randn(64).astype(np.float32),
+            "main_global_step": np.int64(150000), "beta1_power": np.float32(0.9)}
+    out = str(tmp_path / "model-150000.npz")
+    arrays, skipped = tfconv.convert(fake.keys(), fake.__getitem__, out, drs.npz_write)
+    assert skipped == ["beta1_power"] and set(arrays) == {"conv1__weights", "conv1__weights__Momentum", "conv1__biases",
+                                                            "conv1__moving_mean", "global_step"}
+    with np.load(out) as z:
+        assert z["global_step"].tolist() == [150000.0] and z["conv1__weights"].shape == (5, 5, 4, 64)
+        assert np.array_equal(z["conv1__weights__Momentum"], fake["conv1/weights/Momentum"])
