@@ -13,7 +13,8 @@
 //   B tile  N x BLOCK_K slice of the packed filter matrix [Co][K] (K-major), tiled TMA load.
 //   Both land in shared memory in the canonical K-major 128B-swizzled (64B when BLOCK_K=32) layout
 //   that tcgen05.mma reads through shared-memory descriptors; the fp32 accumulator lives in TMEM
-//   (two stages, so the epilogue of tile i overlaps the main loop of tile i+1).
+//   (two stages, so the epilogue of tile i overlaps the main loop of tile i+1).  For Co <= 128 a tile is a PAIR of 128-pixel
+//   units: two A tiles per K block against one B slice, two accumulators per stage (ConvSched below).
 //   Epilogue: tcgen05.ld -> y = act(acc*scale[c] + shift[c]) (bias / folded BN) -> fp16|bf16 ->
 //   swizzled staging in shared memory -> TMA store into a channel slice of the NHWC output
 //   (dense nets write straight into the concat buffer: tf.concat, isprs:921-948, costs nothing).
@@ -611,7 +612,8 @@ static void launch_conv_tc_t(Handle* h, const ConvTcArgs& a) {
   const int64_t M = (int64_t)a.B * a.crop * a.crop;
   const int taps = a.k * a.k;
   const int sw_op = BLOCK_K * 2;
-  // experiment word: bits 0-7 timing mode, bits 12-15 K blocks per stage (0 = default), bit 16 instrumented twin, bit 18 dual MMA warps
+  // experiment word: bits 0-7 timing mode, bits 12-15 K blocks per stage (0 = default), bit 16 instrumented twin, bit 18 dual MMA warps,
+  // bits 20-21 tile pairing (1 = single units, 2 = pairs)
   const int exp_word = g_conv_exp_mode >= 0 ? g_conv_exp_mode : (getenv("DRS_EXP_MODE") ? atoi(getenv("DRS_EXP_MODE")) : 0);
   const int exp_mode = exp_word & 0xff;
   const bool instr = ((exp_word >> 16) & 1) != 0;
