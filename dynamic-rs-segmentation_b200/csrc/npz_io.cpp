@@ -159,11 +159,12 @@ std::string read(const std::string& path, std::vector<Array>& arrays) {
   uint64_t cd_off = get32(&buf[eocd + 16]);
   if ((n_entries == 0xFFFF || cd_off == 0xFFFFFFFFu) && eocd >= 20 && get32(&buf[eocd - 20]) == 0x07064b50) {
     const uint64_t z64 = get64(&buf[eocd - 20 + 8]);       // ZIP64 end record
-    if (z64 + 56 <= buf.size() && get32(&buf[z64]) == 0x06064b50) {
+    if (buf.size() >= 56 && z64 <= buf.size() - 56 && get32(&buf[z64]) == 0x06064b50) {
       n_entries = get64(&buf[z64 + 32]);
       cd_off = get64(&buf[z64 + 48]);
     }
   }
+  if (cd_off > buf.size()) return err(path, "corrupt end record");
   size_t p = (size_t)cd_off;
   for (uint64_t e = 0; e < n_entries; ++e) {
     if (p + 46 > buf.size() || get32(&buf[p]) != 0x02014b50) return err(path, "corrupt central directory");
@@ -190,9 +191,9 @@ std::string read(const std::string& path, std::vector<Array>& arrays) {
     p += 46 + nlen + xlen + clen;
     if (method != 0) return err(path, "member '" + name + "' is compressed (numpy.savez_compressed): save with numpy.savez");
     if (csize != usize) return err(path, "member '" + name + "': stored sizes disagree");
-    if (lho + 30 > buf.size() || get32(&buf[lho]) != 0x04034b50) return err(path, "member '" + name + "': bad local header");
+    if (lho > buf.size() || lho + 30 > buf.size() || get32(&buf[lho]) != 0x04034b50) return err(path, "member '" + name + "': bad local header");
     const size_t data = (size_t)lho + 30 + get16(&buf[lho + 26]) + get16(&buf[lho + 28]);
-    if (data + usize > buf.size()) return err(path, "member '" + name + "' is truncated");
+    if (usize > buf.size() || data > buf.size() - usize) return err(path, "member '" + name + "' is truncated");
     if (crc32(&buf[data], (size_t)usize) != crc) return err(path, "member '" + name + "': CRC mismatch");
     if (name.size() < 4 || name.compare(name.size() - 4, 4, ".npy") != 0) continue;     // not an array: ignore
     // ---- NPY payload
@@ -222,6 +223,7 @@ std::string read(const std::string& path, std::vector<Array>& arrays) {
     const int64_t n = a.count();
     const uint8_t* payload = d + hoff + hlen;
     const uint64_t avail = usize - hoff - hlen;
+    if (n < 0 || (uint64_t)n > avail) return err(path, "member '" + name + "': size does not match its shape");   // before allocating
     a.data.resize((size_t)n);
     auto need = [&](int es) { return (uint64_t)n * es == avail; };
     if (descr == "'<f4'") {

@@ -461,7 +461,7 @@ def npz_read(path):
         L.check(lib.drs_npz_entry(str(path).encode(), i, buf, 512, C.byref(nd), dims, C.byref(cnt), None))
         a = np.empty(cnt.value, dtype=np.float32)
         L.check(lib.drs_npz_read(str(path).encode(), buf.value, L.ptr(a), cnt.value))
-        out[buf.value.decode()] = a.reshape([dims[j] for j in range(nd.value)])
+        out[buf.value.decode("utf-8", "replace")] = a.reshape([dims[j] for j in range(nd.value)])
     return out
 
 

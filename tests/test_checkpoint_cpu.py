@@ -104,3 +104,35 @@ def test_tf_checkpoint_converter_names_and_layout(drs, tmp_path):
     with np.load(out) as z:
         assert z["global_step"].tolist() == [150000.0] and z["conv1__weights"].shape == (5, 5, 4, 64)
         assert np.array_equal(z["conv1__weights__Momentum"], fake["conv1/weights/Momentum"])
+
+
+def test_damaged_files_are_refused_not_crashed_on(drs, tmp_path):
+    """drs_load parses files it did not write: every truncation and a few thousand random byte flips of a NumPy-written and
+    of a library-written archive either load or raise DrsError -- never a crash, never an allocation driven by a corrupt
+    header (the process surviving this loop is the assertion)."""
+    from drs_b200 import lib
+    a = str(tmp_path / "a.npz")
+    np.savez(a, conv1__weights=np.arange(60, dtype=np.float32).reshape(1, 3, 4, 5), b=np.arange(7, dtype=np.float64),
+             global_step=np.array([3], dtype=np.int64))
+    b = str(tmp_path / "b.npz")
+    drs.npz_write(b, {"x": np.arange(10, dtype=np.float32), "y": np.zeros((2, 3), np.float32)})
+    q = str(tmp_path / "damaged.npz")
+    rs = np.random.RandomState(0)
+    refused = loaded = 0
+    for src in (a, b):
+        raw = open(src, "rb").read()
+        cases = [raw[:n] for n in range(0, len(raw), 5)]
+        for _ in range(1500):
+            d = bytearray(raw)
+            for _ in range(rs.randint(1, 4)):
+                d[rs.randint(0, len(d))] = rs.randint(0, 256)
+            cases.append(bytes(d))
+        for c in cases:
+            with open(q, "wb") as f:
+                f.write(c)
+            try:
+                drs.npz_read(q)
+                loaded += 1
+            except lib.DrsError:
+                refused += 1
+    assert refused > 1000 and loaded > 0          # flips in names / padding / dates are harmless, payload flips hit the CRC
